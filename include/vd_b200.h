@@ -1,0 +1,193 @@
+/*
+ * vd_b200.h — C ABI of libvd_b200.so, the sm_100a implementation of the distillation inner
+ * loop of yuz1wan/video_distillation.
+ *
+ * The reference is pure Python/PyTorch and has no FFI; each entry point below replaces the
+ * ATen/cuDNN call the reference makes at the cited file:line (paths are relative to the
+ * reference checkout).  INTEGRATION.md shows the ctypes stub a maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (the library never allocates or
+ *     frees device memory and keeps no per-call state);
+ *   - `stream` is a cudaStream_t passed as void*; every call is an asynchronous enqueue;
+ *   - return value: 0 = ok, negative = bad argument / unsupported shape, positive = cudaError_t;
+ *     vd_last_error() returns a thread-local message for the last non-zero return;
+ *   - "f32 NCDHW" tensors are contiguous float32 in PyTorch's (N, C, T, H, W) order;
+ *     videos at the Python API are (B, T, C, H, W) as in the reference (networks.py:739).
+ */
+#ifndef VD_B200_H
+#define VD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------------------------------------------------------- misc */
+const char* vd_last_error(void);
+int vd_abi_version(void);
+/* number of kernels this library has enqueued in this process (bench.py `gpu_launches`) */
+int64_t vd_launch_count(void);
+void vd_launch_count_reset(void);
+
+/* Convolution geometry shared by the three conv entry points. */
+typedef struct {
+    int32_t N, Cin, T, H, W;      /* input  (N, Cin, T, H, W)      */
+    int32_t Cout, To, Ho, Wo;     /* output (N, Cout, To, Ho, Wo)  */
+    int32_t kt, kh, kw;           /* filter extent                 */
+    int32_t st, sh, sw;           /* stride                        */
+    int32_t pt, ph, pw;           /* zero padding                  */
+} vd_conv_geom;
+
+/* ------------------------------------------------- exact fp32 conv trio (CUDA cores)
+ * Replaces nn.Conv3d forward / convolution_backward at networks.py:799 (feature convs),
+ * networks.py:736 (1x1x1 logit conv) and utils.py:1184 (composer conv), and — because the
+ * three are mutually each other's derivatives — ATen's
+ * _convolution_double_backward on the MTT path (distill_s2d_ms.py:264,292).
+ *   fprop: y = conv(x, w) + bias           (bias may be NULL)
+ *   dgrad: gx = conv_transpose(gy, w)      (explicit input extent in geom: stride-2 is not injective)
+ *   wgrad: gw (+)= x (*) gy ; gb (+)= sum gy   (gw/gb must be zeroed by the caller; gb may be NULL)
+ */
+int vd_conv3d_fprop_f32(const float* x, const float* w, const float* bias, float* y,
+                        const vd_conv_geom* g, void* stream);
+int vd_conv3d_dgrad_f32(const float* gy, const float* w, float* gx,
+                        const vd_conv_geom* g, void* stream);
+int vd_conv3d_wgrad_f32(const float* x, const float* gy, float* gw, float* gb,
+                        const vd_conv_geom* g, void* stream);
+
+/* ------------------------------------------------- ReLU + MaxPool3d routing
+ * Replaces nn.ReLU(inplace) networks.py:757 + nn.MaxPool3d networks.py:766-770 and their
+ * backward / double backward.  kernel == stride == (pt, ph, pw) in {1,2}.
+ * code[o] (uint8, one per pooled output): bits 0..2 = argmax position inside the window in
+ * (t,h,w) scan order, first maximum wins (ATen's rule); bit 3 = "max > 0" (ReLU passes).
+ *   fwd     : y = maxpool(relu(x)), writes code
+ *   scatter : gx[src(o)] = code.active ? gy[o] : 0, all other gx = 0     (backward)
+ *   gather  : y[o] = code.active ? x[src(o)] : 0                         (double backward)
+ */
+int vd_relu_maxpool_fwd_f32(const float* x, float* y, uint8_t* code, int64_t NC,
+                            int T, int H, int W, int pt, int ph, int pw, void* stream);
+int vd_route_scatter_f32(const float* gy, const uint8_t* code, float* gx, int64_t NC,
+                         int T, int H, int W, int pt, int ph, int pw, void* stream);
+int vd_route_gather_f32(const float* x, const uint8_t* code, float* y, int64_t NC,
+                        int T, int H, int W, int pt, int ph, int pw, void* stream);
+
+/* ------------------------------------------------- instancenorm / avgpool variant
+ * GroupNorm(C, C, affine) networks.py:784 (+ReLU) and AvgPool3d(2,2) networks.py:772.
+ *   inorm_relu_fwd: per (n,c) mean / rstd over T*H*W (eps 1e-5), y = relu(gamma*xhat+beta);
+ *                   saves mean,rstd (N*C each).
+ *   inorm_relu_bwd: gx from gy (gradient wrt y), plus ggamma/gbeta (+)= (caller zeroes).
+ *   avgpool2_fwd/bwd: 2x2x2 mean, floor semantics (odd tails dropped).
+ */
+int vd_inorm_relu_fwd_f32(const float* x, const float* gamma, const float* beta, float* y,
+                          float* mean, float* rstd, int N, int C, int64_t S, void* stream);
+int vd_inorm_relu_bwd_f32(const float* x, const float* y, const float* gy, const float* gamma,
+                          const float* mean, const float* rstd, float* gx, float* ggamma,
+                          float* gbeta, int N, int C, int64_t S, void* stream);
+int vd_avgpool2_fwd_f32(const float* x, float* y, int64_t NC, int T, int H, int W, void* stream);
+int vd_avgpool2_bwd_f32(const float* gy, float* gx, int64_t NC, int T, int H, int W, void* stream);
+
+/* ------------------------------------------------- static-dynamic composer
+ * Replaces index gather + Conv3DNet.forward (utils.py:1186-1197; distill_s2d_ms.py:409-412,
+ * 249-253) and its backward (index_put accumulate + convolution_backward) with one fused
+ * kernel each.  static_syn (S, 3, H, W); dynamic_syn (C, dpc, T, 1, H, W); weight (3,4,3,3,3);
+ * bias (3); per output video b: static row static_idx[b], dynamic row (label[b], dynamic_idx[b]).
+ * out / gout: (B, T, 3, H, W) contiguous.
+ *   bwd: grad_dynamic (dense, same shape as dynamic_syn, caller zeroes; rows are accumulated
+ *        with atomics so repeated indices are legal), grad_weight (3*4*27), grad_bias (3)
+ *        (caller zeroes), grad_static (S,3,H,W) optional (NULL to skip; caller zeroes).
+ */
+int vd_compose_fwd_f32(const float* static_syn, const float* dynamic_syn,
+                       const int64_t* static_idx, const int64_t* label, const int64_t* dynamic_idx,
+                       const float* weight, const float* bias, float* out,
+                       int B, int T, int H, int W, int dpc, void* stream);
+int vd_compose_bwd_f32(const float* gout, const float* static_syn, const float* dynamic_syn,
+                       const int64_t* static_idx, const int64_t* label, const int64_t* dynamic_idx,
+                       const float* weight, float* grad_dynamic, float* grad_weight,
+                       float* grad_bias, float* grad_static,
+                       int B, int T, int H, int W, int dpc, void* stream);
+
+/* ------------------------------------------------- distribution-matching loss
+ * Replaces mean/sub/square/sum and their backward at distill_baseline.py:351,
+ * distill_s2d_ms.py:422 for ALL classes of a shard in one launch.
+ * emb_real (C, nr, D), emb_syn (C, ns, D).  loss (+)= sum_c ||mean_r - mean_s||^2 (caller
+ * zeroes *loss); grad_syn (C, ns, D) = -(2/ns)(mean_r - mean_s) * loss_scale.
+ * mean_real_out (C, D) optional (NULL to skip).
+ */
+int vd_class_mean_f32(const float* emb, float* mean, int C, int n, int D, void* stream);
+int vd_dm_loss_f32(const float* mean_real, const float* emb_syn, float* loss, float* grad_syn,
+                   int C, int ns, int D, float loss_scale, void* stream);
+
+/* ------------------------------------------------- optimiser / flat-parameter kernels
+ * sgd_momentum: torch.optim.SGD(momentum=m) dense step (distill_baseline.py:107,355;
+ *   distill_s2d_ms.py:105-108,432-438): first ? buf=g : buf=m*buf+g ; p -= lr*buf.
+ * axpy: y = a*x + y_in  (student update distill_baseline.py:252)
+ * sqdist: out (+)= sum (a-b)^2 (mse_loss(reduction='sum') distill_baseline.py:258-259)
+ */
+int vd_sgd_momentum_f32(float* p, const float* g, float* buf, int64_t n, float lr, float momentum,
+                        int first_step, void* stream);
+int vd_axpy_f32(const float* x, const float* y_in, float* y_out, int64_t n, float a, void* stream);
+int vd_sqdist_f32(const float* a, const float* b, float* out, int64_t n, void* stream);
+
+/* =================================================================== tensor-core path
+ * bf16 operands, fp32 accumulation in TMEM (tcgen05.mma), operands staged by bulk async
+ * copies (cp.async.bulk -> UBLKCP) into shared memory in UMMA canonical K-major layout.
+ * The three feature convolutions of ConvNet3D (networks.py:799; k=(3,7,7) s=(1,2,2)
+ * p=(1,3,3)) are computed as "shifted-window" implicit GEMMs: weights are the M=128 operand,
+ * output pixels the N operand; activations live in HBM in padded, parity-split,
+ * channel-chunked bf16 layouts produced by the previous layer's fused epilogue
+ * (bias + ReLU + MaxPool3d + argmax code).  See DESIGN.md §3 for the layouts.
+ *
+ * vd_tc_plan_* fill a plan struct on the host (sizes of every intermediate buffer);
+ * the caller allocates, then calls the pack / run entry points.
+ */
+typedef struct {
+    int32_t T, H, W;               /* input video extent (C=3)                               */
+    int32_t c1, c2, c3;            /* channels of the three conv layers (64,128,128)         */
+    int32_t T1, H1, W1;            /* L0 conv output extent  (T, H/2, W/2)                   */
+    int32_t T1p, H1p, W1p;         /* after pool (1,2,2)                                     */
+    int32_t T2, H2, W2, T2p, H2p, W2p;
+    int32_t T3, H3, W3, T3p, H3p, W3p;
+    int32_t embed_dim;             /* c3*T3p*H3p*W3p                                         */
+    int64_t x0_bytes_per_video;    /* packed L0 input  (bf16, kw-expanded)                   */
+    int64_t a1_bytes_per_video;    /* packed L1 input  (bf16, parity-planar)                 */
+    int64_t a2_bytes_per_video;    /* packed L2 input  (bf16, tap-expanded)                  */
+    int64_t w0_bytes, w1_bytes, w2_bytes;   /* UMMA weight images                            */
+    int64_t tab_bytes;             /* unused (step tables travel as kernel parameters)       */
+    int32_t reserved[16];
+} vd_tc_plan;
+
+int vd_tc_plan_make(vd_tc_plan* plan, int T, int H, int W);
+
+/* fp32 (Bsrc,T,3,H,W) videos -> packed conv-0 operand X0 for B items (zero halo included; x0
+ * need not be zeroed).  index (device int64[B], may be NULL = identity) selects the source
+ * video of each item: the device-resident form of get_images (distill_s2d_ms.py:81-87). */
+int vd_tc_pack_video(const float* video, const int64_t* index, void* x0, const vd_tc_plan* plan,
+                     int B, void* stream);
+/* fp32 OIDHW weights of features.{0,3,6} -> UMMA weight images (any pair may be NULL to skip).
+ * w0 is the frame-pair-stacked form. */
+int vd_tc_pack_weights(const float* w_l0, const float* w_l1, const float* w_l2,
+                       void* w0, void* w1, void* w2, void* stream);
+
+/* One layer: conv + bias + ReLU + MaxPool (+ optional argmax code), layer in {0,1,2}.
+ *   layer 0: in = X0 (B items, or a bigger resident set addressed through item_index),
+ *            out = A1 (B videos);   layer 1: in = A1, out = A2;
+ *   layer 2: in = A2 (allocated for ceil(B/4)*4 videos), out = fp32 embeddings (B, embed_dim)
+ *            in the reference's NCDHW flatten order (networks.py:750).
+ * A1 / A2 must be zeroed ONCE by the caller before first use (halo cells are never written,
+ * data cells are fully overwritten by every call).  code may be NULL (real videos need no
+ * backward).  item_index (device int64[B], layer 0 only, may be NULL) maps item -> video slot
+ * of `in`.  raw != 0 (bring-up / tests): skip the fused epilogue and dump the fp32
+ * accumulators to out as [tile][acc][128][ncols]. */
+int vd_tc_conv_layer(int layer, const void* in, const void* wimg, const float* bias,
+                     void* out, uint8_t* code, const vd_tc_plan* plan, const int64_t* item_index,
+                     int B, int raw, void* stream);
+
+/* Host-only introspection (no GPU work): the launch parameters vd_tc_conv_layer would use,
+ * flattened to int64 (layout documented in tests/tc_emulator.py); cap >= 248. */
+int vd_tc_debug_params(int layer, const vd_tc_plan* plan, int B, int64_t* out, int cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VD_B200_H */

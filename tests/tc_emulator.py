@@ -1,0 +1,275 @@
+"""CPU model of the tensor-core path's data movement (test infrastructure).
+
+* numpy packers / unpackers for the X0, A1, A2 activation layouts and the three weight images
+  (mirror video_distillation_b200/csrc/tc_pack.cu and the fused epilogues in tc_conv.cu);
+* ``emulate_layer``: replays one launch of ws_gemm_kernel exactly as the hardware is expected
+  to execute it — bulk copies into a shared-memory image, then for every step a K=16 MMA whose
+  operands are fetched through UMMA K-major/no-swizzle descriptors (start, LBO, SBO) — using
+  the REAL launch parameters exported by vd_tc_debug_params.  It validates the host-side
+  tables and layouts without a GPU; what it cannot validate is the hardware's reading of the
+  descriptors, which tests/test_tc_gpu.py covers.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from video_distillation_b200 import _lib
+
+MAX_COPIES, MAX_STEPS = 8, 64
+
+
+def bf16_round(x):
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+def to_bf16_bits(x):
+    """float32 torch tensor -> uint16 numpy (round-to-nearest-even bf16 bit patterns)."""
+    return x.to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
+
+
+def from_bf16_bits(u):
+    return torch.from_numpy(u.astype(np.uint16).view(np.int16).copy()).view(torch.bfloat16).to(torch.float32)
+
+
+class Geo:
+    def __init__(self, T, HW):
+        self.T, self.HW = T, HW
+        self.Ho0 = self.Wo0 = HW // 2
+        self.R0 = 8 if self.Wo0 * 8 <= 256 else 4
+        self.RI0 = self.Ho0 + 3
+        self.N0 = self.R0 * self.Wo0
+        self.plane0 = self.RI0 * self.Wo0 * 16
+        self.frame0 = 6 * self.plane0
+        self.video0 = (T + 2) * self.frame0
+        self.H1 = self.Ho0 // 2
+        self.Ho1 = self.Wo1 = self.H1 // 2
+        self.P1, self.RI1 = self.Wo1 + 2, self.Ho1 + 4
+        self.N1 = self.Ho1 * self.P1
+        self.plane1 = self.RI1 * self.P1 * 16
+        self.frame1 = 8 * self.plane1
+        self.slice1 = (T + 2) * self.frame1
+        self.video1 = 4 * self.slice1
+        self.T2, self.H2 = T // 2, self.Ho1 // 2
+        self.To2 = self.T2
+        self.Ho2 = self.Wo2 = (self.H2 - 1) // 2 + 1
+        self.HW2 = self.Ho2 * self.Wo2
+        self.N2 = self.To2 * self.HW2
+        self.chunk2 = (self.To2 + 2) * self.HW2 * 16
+        self.group2 = 8 * self.chunk2
+        self.video2 = 98 * self.group2
+        self.T3p, self.H3p = self.To2 // 2, self.Ho2 // 2
+        self.embed_dim = 128 * self.T3p * self.H3p * self.H3p
+
+
+def tap_par(k):
+    return (k + 1) & 1
+
+
+def tap_shift(k):
+    return (k - 1) // 2 if k & 1 else k // 2
+
+
+def coord_par(x):
+    return x & 1
+
+
+def coord_pos(x):
+    return (x + 3) // 2 if x & 1 else x // 2 + 1
+
+
+def l0_chunk_kh(idx):
+    return 2 * idx + 1 if idx < 3 else 2 * (idx - 3)
+
+
+# ------------------------------------------------------------------ packers (uint16 bf16 bit images)
+def pack_x0(video, g):
+    """video (B,T,3,H,W) float32 -> uint16 (B, T+2, 3, 2, RI0, Wo0, 8)."""
+    B = video.shape[0]
+    bits = to_bf16_bits(video)                                    # (B,T,3,H,W)
+    out = np.zeros((B, g.T + 2, 3, 2, g.RI0, g.Wo0, 8), np.uint16)
+    HW = g.HW
+    for par in range(2):
+        for row in range(g.RI0):
+            h = 2 * row - 3 if par else 2 * row - 2
+            if not (0 <= h < HW):
+                continue
+            for kw in range(7):
+                wo = np.arange(g.Wo0)
+                w = 2 * wo + kw - 3
+                ok = (w >= 0) & (w < HW)
+                out[:, 1:g.T + 1, :, par, row, wo[ok], kw] = bits[:, :, :, h, w[ok]]
+    return out
+
+
+def pack_a1(x, g):
+    """pooled conv-0 output (B,64,T,H1,H1) float32 -> uint16 (B,4,T+2,2,2,2,RI1,P1,8)."""
+    B = x.shape[0]
+    bits = to_bf16_bits(x)
+    out = np.zeros((B, 4, g.T + 2, 2, 2, 2, g.RI1, g.P1, 8), np.uint16)
+    for h in range(g.H1):
+        for w in range(g.H1):
+            v = bits[:, :, :, h, w].reshape(B, 4, 2, 8, g.T)      # (B, slice, k, e, T)
+            out[:, :, 1:g.T + 1, coord_par(h), coord_par(w), :, coord_pos(h), coord_pos(w), :] = \
+                v.transpose(0, 1, 4, 2, 3)
+    return out
+
+
+def unpack_a1(buf, g, B):
+    """inverse of pack_a1 on a uint16 image -> float32 (B,64,T,H1,H1); also returns the halo mask check."""
+    a = buf.reshape(B, 4, g.T + 2, 2, 2, 2, g.RI1, g.P1, 8)
+    out = np.zeros((B, 64, g.T, g.H1, g.H1), np.uint16)
+    for h in range(g.H1):
+        for w in range(g.H1):
+            v = a[:, :, 1:g.T + 1, coord_par(h), coord_par(w), :, coord_pos(h), coord_pos(w), :]   # (B,4,T,2,8)
+            out[:, :, :, h, w] = v.transpose(0, 1, 3, 4, 2).reshape(B, 64, g.T)
+    return from_bf16_bits(out)
+
+
+def pack_a2(x, g, Bpad=None):
+    """pooled conv-1 output (B,128,T2,H2,H2) float32 -> uint16 (Bpad,49,2,8,To2+2,Ho2,Wo2,8)."""
+    B = x.shape[0]
+    Bpad = Bpad or B
+    bits = to_bf16_bits(x)
+    out = np.zeros((Bpad, 49, 2, 8, g.To2 + 2, g.Ho2, g.Wo2, 8), np.uint16)
+    for kh in range(7):
+        for kw in range(7):
+            for ho in range(g.Ho2):
+                h = 2 * ho + kh - 3
+                if not (0 <= h < g.H2):
+                    continue
+                for wo in range(g.Wo2):
+                    w = 2 * wo + kw - 3
+                    if not (0 <= w < g.H2):
+                        continue
+                    v = bits[:, :, :, h, w].reshape(B, 2, 8, 8, g.T2)          # (B, half, k, e, T2)
+                    out[:B, kh * 7 + kw, :, :, 1:g.T2 + 1, ho, wo, :] = v.transpose(0, 1, 2, 4, 3)
+    return out
+
+
+def unpack_a2(buf, g, B):
+    """Recover (B,128,T2,H2,H2) from the tap-expanded image and check that all copies agree."""
+    a = buf.reshape(-1, 49, 2, 8, g.To2 + 2, g.Ho2, g.Wo2, 8)
+    out = np.zeros((B, 128, g.T2, g.H2, g.H2), np.uint16)
+    seen = np.zeros((g.H2, g.H2), bool)
+    consistent = True
+    for kh in range(7):
+        for kw in range(7):
+            for ho in range(g.Ho2):
+                h = 2 * ho + kh - 3
+                if not (0 <= h < g.H2):
+                    continue
+                for wo in range(g.Wo2):
+                    w = 2 * wo + kw - 3
+                    if not (0 <= w < g.H2):
+                        continue
+                    v = a[:B, kh * 7 + kw, :, :, 1:g.T2 + 1, ho, wo, :]            # (B,2,8,T2,8)
+                    v = v.transpose(0, 1, 2, 4, 3).reshape(B, 128, g.T2)
+                    if seen[h, w]:
+                        consistent &= bool((out[:, :, :, h, w] == v).all())
+                    out[:, :, :, h, w] = v
+                    seen[h, w] = True
+    return from_bf16_bits(out), consistent and bool(seen.all())
+
+
+def pack_w0(w):
+    """(64,3,3,7,7) -> uint16 (11,2,5,64,8)."""
+    bits = to_bf16_bits(w)
+    out = np.zeros((11, 2, 5, 64, 8), np.uint16)
+    for p in range(11):
+        for k in range(2):
+            ch = 2 * p + k
+            if ch >= 21:
+                continue
+            c, kh = ch // 7, l0_chunk_kh(ch % 7)
+            for blk in (1, 2, 3):
+                out[p, k, blk, :, :7] = bits[:, c, 3 - blk, kh, :]
+    return out
+
+
+def pack_w1(w):
+    """(128,64,3,7,7) -> uint16 (3,4,7,7,2,128,8)  [kt][slice][kh][kw][k][row][e]."""
+    bits = to_bf16_bits(w).reshape(128, 4, 2, 8, 3, 7, 7)          # row, slice, k, e, kt, kh, kw
+    return np.ascontiguousarray(bits.transpose(4, 1, 5, 6, 2, 0, 3))
+
+
+def pack_w2(w):
+    """(128,128,3,7,7) -> uint16 (7,7,2,3,4,2,128,8)  [kh][kw][half][kt][kc][k][row][e]."""
+    bits = to_bf16_bits(w).reshape(128, 2, 4, 2, 8, 3, 7, 7)       # row, half, kc, k, e, kt, kh, kw
+    return np.ascontiguousarray(bits.transpose(6, 7, 1, 5, 2, 3, 0, 4))
+
+
+# ------------------------------------------------------------------ launch parameters
+class Params:
+    def __init__(self, layer, T, HW, B):
+        lib = _lib.lib()
+        plan = _lib.TcPlan()
+        _lib.check(lib.vd_tc_plan_make(ctypes.byref(plan), T, HW, HW), 'tc_plan_make')
+        self.plan = plan
+        buf = (ctypes.c_int64 * 256)()
+        _lib.check(lib.vd_tc_debug_params(layer, ctypes.byref(plan), B, buf, 256), 'tc_debug_params')
+        v = list(buf)
+        names = ['n_tiles', 'tiles_per_item', 'v_count', 'item_stride', 'u_stride', 'v_stride', 'n_sa', 'n_sb',
+                 'sa_stride', 'sb_stride', 'n_copies', 'stage_bytes', 'stage_pitch', 'n_steps', 'a_sa_stride16',
+                 'a_lbo16', 'a_sbo16', 'w_resident', 'w_bytes', 'G', 'RW', 'RP', 'n_acc', 'acc_delta16', 'ncols',
+                 'acc_cols', 'acc_stages', 'idesc', 'smem_w_off', 'smem_pix_off', 'smem_total', '_']
+        for i, n in enumerate(names):
+            setattr(self, n, v[i])
+        o = 32
+        self.copy_gofs = v[o:o + MAX_COPIES]; o += MAX_COPIES
+        self.copy_sofs = v[o:o + MAX_COPIES]; o += MAX_COPIES
+        self.copy_bytes = v[o:o + MAX_COPIES]; o += MAX_COPIES
+        self.b_off16 = v[o:o + MAX_STEPS]; o += MAX_STEPS
+        self.b_lbo16 = v[o:o + MAX_STEPS]; o += MAX_STEPS
+        self.a_off16 = v[o:o + MAX_STEPS]
+
+
+def _desc_gather(mem16, start_bytes, lbo_bytes, sbo_bytes, rows):
+    """Elements (rows, 16) addressed by a K-major no-swizzle UMMA descriptor over a uint16 image."""
+    r = np.arange(rows)
+    kk = np.arange(16)
+    addr = (start_bytes + (kk[None, :] // 8) * lbo_bytes + (r[:, None] // 8) * sbo_bytes +
+            (r[:, None] % 8) * 16 + (kk[None, :] % 8) * 2)
+    return mem16[addr // 2]
+
+
+def emulate_layer(layer, pix_u16, wimg_u16, T, HW, B, tiles=None):
+    """Returns D of shape (n_tiles_run, n_acc, 128, ncols) float32 (accumulated in float64)."""
+    p = Params(layer, T, HW, B)
+    pix = pix_u16.reshape(-1)
+    wimg = wimg_u16.reshape(-1)
+    tiles = range(p.n_tiles) if tiles is None else tiles
+    out = []
+    # bf16 bit patterns -> float via a lookup of the upper 16 bits
+    def f32(u16):
+        return (u16.astype(np.uint32) << 16).view(np.float32).astype(np.float64)
+    for tile in tiles:
+        item, sub = divmod(tile, p.tiles_per_item)
+        u, v = divmod(sub, p.v_count)
+        gbase = item * p.item_stride + u * p.u_stride + v * p.v_stride
+        D = np.zeros((p.n_acc, 128, p.ncols))
+        st = 0
+        for sa in range(p.n_sa):
+            for sb in range(p.n_sb):
+                smem = np.zeros(p.stage_pitch // 2, np.uint16)
+                src = gbase + sa * p.sa_stride + sb * p.sb_stride
+                for c in range(p.n_copies):
+                    n = p.copy_bytes[c] // 2
+                    s0 = (src + p.copy_gofs[c]) // 2
+                    chunk = pix[s0:s0 + n]
+                    assert chunk.size == n, 'bulk copy reads past the end of the packed input'
+                    smem[p.copy_sofs[c] // 2: p.copy_sofs[c] // 2 + n] = chunk
+                for j in range(p.n_steps):
+                    if p.w_resident:
+                        a_start = (p.a_off16[j] + sa * p.a_sa_stride16) * 16
+                        A = f32(_desc_gather(wimg, a_start, p.a_lbo16 * 16, p.a_sbo16 * 16, 128))
+                    else:
+                        a_start = (st * p.n_steps + j) * 4096
+                        A = f32(_desc_gather(wimg, a_start, p.a_lbo16 * 16, p.a_sbo16 * 16, 128))
+                    for a in range(p.n_acc):
+                        b_start = (p.b_off16[j] + a * p.acc_delta16) * 16
+                        Bm = f32(_desc_gather(smem, b_start, p.b_lbo16[j] * 16, 128, p.ncols))
+                        D[a] += A @ Bm.T
+                st += 1
+        out.append(D)
+    return np.stack(out).astype(np.float32), p

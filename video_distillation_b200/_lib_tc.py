@@ -1,0 +1,19 @@
+"""ctypes signatures of the tensor-core entry points (include/vd_b200.h, second half)."""
+from ctypes import POINTER, c_int, c_int64, c_void_p
+
+
+def declare(lib):
+    from ._lib import TcPlan, EXPORTED
+    P = c_void_p
+    sig = {
+        'vd_tc_plan_make': (c_int, [POINTER(TcPlan), c_int, c_int, c_int]),
+        'vd_tc_pack_video': (c_int, [P, P, P, POINTER(TcPlan), c_int, P]),
+        'vd_tc_pack_weights': (c_int, [P, P, P, P, P, P, P]),
+        'vd_tc_conv_layer': (c_int, [c_int, P, P, P, P, P, POINTER(TcPlan), P, c_int, c_int, P]),
+        'vd_tc_debug_params': (c_int, [c_int, POINTER(TcPlan), c_int, POINTER(c_int64), c_int]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    EXPORTED.update(sig)

@@ -1,0 +1,597 @@
+// Shifted-window implicit-GEMM Conv3d on tcgen05 tensor cores (sm_100a).
+//
+// One persistent, warp-specialised kernel serves the three ConvNet3D feature convolutions
+// (networks.py:799).  Per CTA tile:
+//     D[m, q] = sum_{stage} sum_{step} A_step[m, 0:16] . B_step[q, 0:16]^T        (bf16 x bf16 -> fp32)
+//   m  = output channel (M = 128 lanes of TMEM; conv 0 stacks two output frames x 64 channels)
+//   q  = output pixel of the tile (N = 16..256 TMEM columns), a LINEAR window of the packed input
+//   A  = 128x16 weight tile, UMMA canonical K-major (no swizzle), streamed through a ring of
+//        bulk-copied slots (conv 1/2) or resident in shared memory for the whole kernel (conv 0)
+//   B  = 16-byte channel chunks of the packed activation staged ONCE per (tile, stage) by bulk
+//        async copies; every filter tap is just a different descriptor start address.
+// Warp roles: 0 pixel loader, 1 MMA issuer (single thread), 2 TMEM allocator, 3 weight loader,
+// 4..7 epilogue (TMEM -> registers -> bias/ReLU/MaxPool/argmax -> packed bf16 input of the next
+// layer, or fp32 embeddings after conv 2).  Layouts: tc_layout.h.
+#include "tc_common.cuh"
+#include "tc_layout.h"
+
+namespace vd {
+namespace tc {
+
+constexpr int kMaxSteps = 64;
+constexpr int kMaxCopies = 8;
+constexpr int kThreads = 256;
+
+enum EpiMode { EPI_RAW = 0, EPI_L0 = 1, EPI_L1 = 2, EPI_L2 = 3 };
+
+struct EpiParams {
+    float* raw;            // EPI_RAW: [tile][acc][128][ncols]
+    const float* bias;     // per output channel (64 for conv 0, 128 otherwise)
+    uint8_t* out;          // packed bf16 input of the next layer / fp32 embeddings
+    uint8_t* code;         // optional ReLU/argmax routing codes, NCDHW order of the pooled tensor
+    int T;                 // frames of the video
+    int n_items;           // videos (conv 2: valid videos, tiles may be partially filled)
+    Geo g;
+};
+
+struct WsParams {
+    const uint8_t* pix;
+    const uint8_t* wimg;
+    const int64_t* item_index;          // optional: item -> slot of `pix` (resident dataset)
+    int32_t n_tiles, tiles_per_item, v_count;
+    int64_t item_stride, u_stride, v_stride;
+    int32_t n_sa, n_sb;
+    int64_t sa_stride, sb_stride;
+    int32_t n_copies;
+    uint32_t stage_bytes;               // bytes landing per stage (sum of copy_bytes)
+    uint32_t stage_pitch;               // smem distance between ring slots
+    int64_t copy_gofs[kMaxCopies];
+    uint32_t copy_sofs[kMaxCopies];
+    uint32_t copy_bytes[kMaxCopies];
+    int32_t n_steps;
+    uint32_t b_off16[kMaxSteps];
+    uint32_t b_lbo16[kMaxSteps];
+    uint32_t a_off16[kMaxSteps];        // resident weights: offset of the tile of (sa=0, step)
+    int32_t a_sa_stride16;              // resident weights: offset added per stage index
+    uint32_t a_lbo16, a_sbo16;
+    int32_t w_resident;
+    uint32_t w_bytes;                   // resident image bytes
+    int32_t G, RW, RP;
+    int32_t n_acc;
+    uint32_t acc_delta16;               // B start offset between accumulators
+    uint32_t ncols, acc_cols, acc_stages;
+    uint32_t idesc;
+    uint32_t smem_w_off, smem_pix_off;  // from the 1024-aligned dynamic smem base
+    EpiParams epi;
+};
+
+struct __align__(8) Barriers {
+    uint64_t pix_full[4], pix_empty[4];
+    uint64_t w_full[8], w_empty[8];
+    uint64_t acc_full[2], acc_empty[2];
+    uint64_t w_res;
+    uint32_t tmem_base;
+    uint32_t pad;
+};
+constexpr uint32_t kBarBytes = 256;
+static_assert(sizeof(Barriers) <= kBarBytes, "barrier block too large");
+
+// ------------------------------------------------------------------------------------------
+// epilogues.  Thread `m` (0..127) owns TMEM lane m.  taddr = tmem base of the accumulator stage
+// with the lane quarter already folded in.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void epi_raw(const WsParams& p, int tile, uint32_t taddr, int m) {
+    for (int a = 0; a < p.n_acc; ++a) {
+        float* dst = p.epi.raw + (((int64_t)tile * p.n_acc + a) * 128 + m) * p.ncols;
+        for (uint32_t c = 0; c < p.ncols; c += 8) {
+            float v[8];
+            tmem_ld8(taddr + a * p.acc_cols + c, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dst[c + i] = v[i];
+        }
+    }
+}
+
+// conv 0: lanes 0..63 = frame 2*tp, lanes 64..127 = frame 2*tp+1, columns q = r*Wo0 + wo.
+// bias + ReLU + MaxPool(1,2,2) -> A1 chunks (bf16) [+ code (B,64,T,H1,H1)]
+__device__ __forceinline__ void epi_l0(const WsParams& p, int tile, uint32_t taddr, int m) {
+    const Geo& g = p.epi.g;
+    const int item = tile / p.tiles_per_item, sub = tile % p.tiles_per_item;
+    const int tp = sub / p.v_count, rb = sub % p.v_count;
+    const int f = 2 * tp + (m >> 6), co = m & 63;
+    const float bias = __ldg(p.epi.bias + co);
+    const int slice = co >> 4, k = (co >> 3) & 1, e = co & 7;
+    uint8_t* vbase = p.epi.out + (int64_t)item * g.video1 + (int64_t)slice * g.slice1 + (int64_t)(f + 1) * g.frame1;
+    uint8_t* cbase = p.epi.code ? p.epi.code + (((int64_t)item * 64 + co) * g.T + f) * g.H1 * g.H1 : nullptr;
+    for (int pr = 0; pr < g.R0 / 2; ++pr) {
+        const int hp = (rb * g.R0) / 2 + pr;
+        const int ph = coord_par(hp), pi = coord_pos(hp);
+        for (int wb = 0; wb < g.Wo0; wb += 8) {
+            float r0[8], r1[8];
+            tmem_ld8(taddr + (2 * pr) * g.Wo0 + wb, r0);
+            tmem_ld8(taddr + (2 * pr + 1) * g.Wo0 + wb, r1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                // scan order (h,w): (0,0) (0,1) (1,0) (1,1); first maximum wins
+                float best = r0[2 * j]; int arg = 0;
+                if (r0[2 * j + 1] > best) { best = r0[2 * j + 1]; arg = 1; }
+                if (r1[2 * j] > best) { best = r1[2 * j]; arg = 2; }
+                if (r1[2 * j + 1] > best) { best = r1[2 * j + 1]; arg = 3; }
+                best += bias;
+                const bool act = best > 0.f;
+                const int wp = wb / 2 + j;
+                const int pw = coord_par(wp), pj = coord_pos(wp);
+                uint8_t* dst = vbase + (int64_t)(((ph * 2 + pw) * 2 + k)) * g.plane1 + ((int64_t)pi * g.P1 + pj) * 16 + e * 2;
+                *reinterpret_cast<uint16_t*>(dst) = f2bf(act ? best : 0.f);
+                if (cbase) cbase[hp * g.H1 + wp] = (uint8_t)(arg | (act ? 8 : 0));
+            }
+        }
+    }
+}
+
+// conv 1: accumulator a = frame 2*tp + a, lane = cout, columns q = ho*P1 + wo.
+// bias + ReLU + MaxPool(2,2,2) -> A2 chunks (bf16, every tap copy) [+ code (B,128,T2,H2,H2)]
+__device__ __forceinline__ void epi_l1(const WsParams& p, int tile, uint32_t taddr, int m) {
+    const Geo& g = p.epi.g;
+    const int item = tile / p.tiles_per_item, tp = tile % p.tiles_per_item;   // pooled frame index = tp
+    const float bias = __ldg(p.epi.bias + m);
+    const int half = m >> 6, k = (m >> 3) & 7, e = m & 7;
+    uint8_t* vbase = p.epi.out + (int64_t)item * g.video2;
+    uint8_t* cbase = p.epi.code ? p.epi.code + (((int64_t)item * 128 + m) * g.T2 + tp) * g.H2 * g.H2 : nullptr;
+    for (int hp = 0; hp < g.H2; ++hp) {
+        float a0[16], a1[16], b0[16], b1[16];
+        tmem_ld16(taddr + (2 * hp) * g.P1, a0);
+        tmem_ld16(taddr + (2 * hp + 1) * g.P1, a1);
+        tmem_ld16(taddr + p.acc_cols + (2 * hp) * g.P1, b0);
+        tmem_ld16(taddr + p.acc_cols + (2 * hp + 1) * g.P1, b1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int wp = 0; wp < 8; ++wp) {
+            if (wp < g.H2) {
+                // scan order (t,h,w)
+                float best = a0[2 * wp]; int arg = 0;
+                if (a0[2 * wp + 1] > best) { best = a0[2 * wp + 1]; arg = 1; }
+                if (a1[2 * wp] > best) { best = a1[2 * wp]; arg = 2; }
+                if (a1[2 * wp + 1] > best) { best = a1[2 * wp + 1]; arg = 3; }
+                if (b0[2 * wp] > best) { best = b0[2 * wp]; arg = 4; }
+                if (b0[2 * wp + 1] > best) { best = b0[2 * wp + 1]; arg = 5; }
+                if (b1[2 * wp] > best) { best = b1[2 * wp]; arg = 6; }
+                if (b1[2 * wp + 1] > best) { best = b1[2 * wp + 1]; arg = 7; }
+                best += bias;
+                const bool act = best > 0.f;
+                const uint16_t bv = f2bf(act ? best : 0.f);
+                if (cbase) cbase[hp * g.H2 + wp] = (uint8_t)(arg | (act ? 8 : 0));
+                // input pixel (t=tp, h=hp, w=wp) of conv 2 feeds output (ho,wo) through tap
+                // (kh,kw) iff hp = 2ho+kh-3, wp = 2wo+kw-3
+                for (int kh = (hp + 1) & 1; kh < 7; kh += 2) {
+                    const int ho = (hp + 3 - kh) / 2;
+                    if (hp + 3 - kh < 0 || ho >= g.Ho2) continue;
+                    for (int kw = (wp + 1) & 1; kw < 7; kw += 2) {
+                        const int wo = (wp + 3 - kw) / 2;
+                        if (wp + 3 - kw < 0 || wo >= g.Wo2) continue;
+                        uint8_t* dst = vbase + (int64_t)((kh * 7 + kw) * 2 + half) * g.group2 + (int64_t)k * g.chunk2 +
+                                       ((int64_t)(tp + 1) * g.HW2 + ho * g.Wo2 + wo) * 16 + e * 2;
+                        *reinterpret_cast<uint16_t*>(dst) = bv;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// conv 2: accumulator a = video item*4 + a, lane = cout, columns q = to*HW2 + ho*Wo2 + wo.
+// bias + ReLU + MaxPool(2,2,2) -> fp32 embeddings (B, 128*T3p*H3p*H3p), NCDHW flatten order
+// (networks.py:750) [+ code (B,128,T3p,H3p,H3p)]
+__device__ __forceinline__ void epi_l2(const WsParams& p, int tile, uint32_t taddr, int m) {
+    const Geo& g = p.epi.g;
+    const float bias = __ldg(p.epi.bias + m);
+    const int per = g.T3p * g.H3p * g.H3p;
+    for (int a = 0; a < p.n_acc; ++a) {
+        const int video = tile * p.n_acc + a;
+        if (video >= p.epi.n_items) break;
+        float* dst = reinterpret_cast<float*>(p.epi.out) + (int64_t)video * g.embed_dim + (int64_t)m * per;
+        uint8_t* cdst = p.epi.code ? p.epi.code + (int64_t)video * g.embed_dim + (int64_t)m * per : nullptr;
+        for (int tq = 0; tq < g.T3p; ++tq) {
+            // two frames = 2*HW2 consecutive columns
+            const uint32_t c0 = taddr + a * p.acc_cols + (2 * tq) * g.HW2;
+            if (g.HW2 == 16) {
+                float f0[16], f1[16];
+                tmem_ld16(c0, f0);
+                tmem_ld16(c0 + 16, f1);
+                tmem_ld_wait();
+#pragma unroll
+                for (int hp = 0; hp < 2; ++hp)
+#pragma unroll
+                    for (int wp = 0; wp < 2; ++wp) {
+                        float best = -INFINITY; int arg = 0, pos = 0;
+#pragma unroll
+                        for (int dt = 0; dt < 2; ++dt)
+#pragma unroll
+                            for (int dh = 0; dh < 2; ++dh)
+#pragma unroll
+                                for (int dw = 0; dw < 2; ++dw, ++pos) {
+                                    const float v = (dt ? f1 : f0)[(2 * hp + dh) * 4 + 2 * wp + dw];
+                                    if (v > best) { best = v; arg = pos; }
+                                }
+                        best += bias;
+                        const bool act = best > 0.f;
+                        dst[(tq * 2 + hp) * 2 + wp] = act ? best : 0.f;
+                        if (cdst) cdst[(tq * 2 + hp) * 2 + wp] = (uint8_t)(arg | (act ? 8 : 0));
+                    }
+            } else {   // HW2 == 4 (64x64 videos): one pooled output per frame pair
+                float f[8];
+                tmem_ld8(c0, f);
+                tmem_ld_wait();
+                float best = -INFINITY; int arg = 0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) if (f[i] > best) { best = f[i]; arg = i; }
+                best += bias;
+                const bool act = best > 0.f;
+                dst[tq] = act ? best : 0.f;
+                if (cdst) cdst[tq] = (uint8_t)(arg | (act ? 8 : 0));
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+template <int EPI>
+__global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_constant__ WsParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    // 1024-byte aligned carve-up: [barriers 256 B][weights][pixel ring]
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+    Barriers* bars = reinterpret_cast<Barriers*>(base_ptr);
+    const uint32_t bar0 = base;
+#define BAR(field, i) (bar0 + (uint32_t)offsetof(Barriers, field) + 8u * (uint32_t)(i))
+    const uint32_t smem_w = base + p.smem_w_off;
+    const uint32_t smem_pix = base + p.smem_pix_off;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 4; ++i) { mbar_init(BAR(pix_full, i), 1); mbar_init(BAR(pix_empty, i), 1); }
+        for (int i = 0; i < 8; ++i) { mbar_init(BAR(w_full, i), 1); mbar_init(BAR(w_empty, i), 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(BAR(acc_full, i), 1); mbar_init(BAR(acc_empty, i), 4); }
+        mbar_init(BAR(w_res, 0), 1);
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(bar0 + (uint32_t)offsetof(Barriers, tmem_base), 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    const int stages_per_tile = p.n_sa * p.n_sb;
+
+    if (warp == 0) {
+        // ===================== pixel loader =====================
+        if (lane == 0) {
+            uint32_t slot = 0, phase = 0;
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+                const int item = tile / p.tiles_per_item, sub = tile % p.tiles_per_item;
+                const int u = sub / p.v_count, v = sub % p.v_count;
+                const int64_t slot_item = p.item_index ? __ldg(p.item_index + item) : (int64_t)item;
+                const uint8_t* gbase = p.pix + slot_item * p.item_stride + (int64_t)u * p.u_stride + (int64_t)v * p.v_stride;
+                for (int sa = 0; sa < p.n_sa; ++sa)
+                    for (int sb = 0; sb < p.n_sb; ++sb) {
+                        mbar_wait(BAR(pix_empty, slot), phase ^ 1);
+                        mbar_expect_tx(BAR(pix_full, slot), p.stage_bytes);
+                        const uint8_t* src = gbase + (int64_t)sa * p.sa_stride + (int64_t)sb * p.sb_stride;
+                        const uint32_t dst = smem_pix + slot * p.stage_pitch;
+                        for (int c = 0; c < p.n_copies; ++c)
+                            bulk_g2s(dst + p.copy_sofs[c], src + p.copy_gofs[c], p.copy_bytes[c], BAR(pix_full, slot));
+                        if (++slot == (uint32_t)p.RP) { slot = 0; phase ^= 1; }
+                    }
+            }
+        }
+    } else if (warp == 3) {
+        // ===================== weight loader =====================
+        if (lane == 0) {
+            if (p.w_resident) {
+                mbar_expect_tx(BAR(w_res, 0), p.w_bytes);
+                for (uint32_t o = 0; o < p.w_bytes; o += 16384) {
+                    const uint32_t n = min(16384u, p.w_bytes - o);
+                    bulk_g2s(smem_w + o, p.wimg + o, n, BAR(w_res, 0));
+                }
+            } else {
+                uint32_t slot = 0, phase = 0;
+                const int slots_per_stage = (p.n_steps + p.G - 1) / p.G;
+                for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+                    for (int st = 0; st < stages_per_tile; ++st)
+                        for (int gi = 0; gi < slots_per_stage; ++gi) {
+                            const int s0 = gi * p.G;
+                            const uint32_t nb = (uint32_t)min(p.G, p.n_steps - s0) * kWeightTileBytes;
+                            mbar_wait(BAR(w_empty, slot), phase ^ 1);
+                            mbar_expect_tx(BAR(w_full, slot), nb);
+                            bulk_g2s(smem_w + slot * (uint32_t)p.G * kWeightTileBytes,
+                                     p.wimg + ((int64_t)st * p.n_steps + s0) * kWeightTileBytes, nb, BAR(w_full, slot));
+                            if (++slot == (uint32_t)p.RW) { slot = 0; phase ^= 1; }
+                        }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread) =====================
+        if (lane == 0) {
+            uint32_t pslot = 0, pphase = 0, wslot = 0, wphase = 0, as = 0, aphase = 0;
+            if (p.w_resident) { mbar_wait(BAR(w_res, 0), 0); tc_fence_after(); }
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+                mbar_wait(BAR(acc_empty, as), aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_base = tmem_base + as * (p.acc_cols * (uint32_t)p.n_acc);
+                uint32_t accumulate = 0;
+                for (int sa = 0; sa < p.n_sa; ++sa)
+                    for (int sb = 0; sb < p.n_sb; ++sb) {
+                        mbar_wait(BAR(pix_full, pslot), pphase);
+                        tc_fence_after();
+                        const uint32_t pix16 = (smem_pix + pslot * p.stage_pitch) >> 4;
+                        for (int j = 0; j < p.n_steps; ++j) {
+                            uint32_t a16;
+                            if (p.w_resident) {
+                                a16 = (smem_w >> 4) + p.a_off16[j] + (uint32_t)(sa * p.a_sa_stride16);
+                            } else {
+                                const int jj = j % p.G;
+                                if (jj == 0) { mbar_wait(BAR(w_full, wslot), wphase); tc_fence_after(); }
+                                a16 = ((smem_w + wslot * (uint32_t)p.G * kWeightTileBytes) >> 4) + (uint32_t)jj * (kWeightTileBytes >> 4);
+                            }
+                            const uint64_t a_desc = umma_desc(a16, p.a_lbo16, p.a_sbo16);
+                            const uint32_t b16 = pix16 + p.b_off16[j];
+                            const uint32_t lbo = p.b_lbo16[j];
+                            for (int a = 0; a < p.n_acc; ++a) {
+                                const uint64_t b_desc = umma_desc(b16 + (uint32_t)a * p.acc_delta16, lbo, 8);
+                                umma_bf16(d_base + (uint32_t)a * p.acc_cols, a_desc, b_desc, p.idesc, accumulate);
+                            }
+                            accumulate = 1;
+                            if (!p.w_resident && ((j % p.G) == p.G - 1 || j == p.n_steps - 1)) {
+                                umma_commit(BAR(w_empty, wslot));
+                                if (++wslot == (uint32_t)p.RW) { wslot = 0; wphase ^= 1; }
+                            }
+                        }
+                        umma_commit(BAR(pix_empty, pslot));
+                        if (++pslot == (uint32_t)p.RP) { pslot = 0; pphase ^= 1; }
+                    }
+                umma_commit(BAR(acc_full, as));
+                if (++as == p.acc_stages) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue (128 threads, lane quarter = warp % 4) =====================
+        const int q = warp & 3;
+        const int m = q * 32 + lane;
+        uint32_t as = 0, aphase = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            mbar_wait(BAR(acc_full, as), aphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * (p.acc_cols * (uint32_t)p.n_acc);
+            if (EPI == EPI_RAW) epi_raw(p, tile, taddr, m);
+            else if (EPI == EPI_L0) epi_l0(p, tile, taddr, m);
+            else if (EPI == EPI_L1) epi_l1(p, tile, taddr, m);
+            else epi_l2(p, tile, taddr, m);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(acc_empty, as));
+            if (++as == p.acc_stages) { as = 0; aphase ^= 1; }
+        }
+    }
+    // ===================== teardown =====================
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+#undef BAR
+}
+
+// ------------------------------------------------------------------------------------------
+// host side: per-layer parameter construction
+// ------------------------------------------------------------------------------------------
+static uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
+
+static int finalize_smem(WsParams& p, uint32_t w_region, uint32_t* smem_total) {
+    p.smem_w_off = kBarBytes;
+    p.smem_pix_off = align_up(kBarBytes + w_region, 128);
+    p.stage_pitch = align_up(p.stage_bytes + 16, 128);
+    uint32_t total = p.smem_pix_off + (uint32_t)p.RP * p.stage_pitch + 1024;   // +1024: manual alignment slack
+    if (total < 120 * 1024) total = 120 * 1024;     // one CTA per SM: every CTA allocates all 512 TMEM columns
+    VD_REQUIRE(total <= 232448, "tc conv: shared memory budget exceeded (%u bytes)", total);
+    *smem_total = total;
+    return 0;
+}
+
+static int setup_l0(WsParams& p, const Geo& g, int B, uint32_t* smem) {
+    p.n_tiles = B * (g.T / 2) * (g.Ho0 / g.R0);
+    p.tiles_per_item = (g.T / 2) * (g.Ho0 / g.R0);
+    p.v_count = g.Ho0 / g.R0;
+    p.item_stride = g.video0; p.u_stride = 2 * g.frame0; p.v_stride = (int64_t)g.R0 * g.Wo0 * 16;
+    p.n_sa = 4; p.n_sb = 1; p.sa_stride = g.frame0; p.sb_stride = 0;
+    p.n_copies = 6;
+    uint32_t sofs = 0;
+    uint32_t blk[3][2];
+    for (int c = 0; c < 3; ++c)
+        for (int par = 0; par < 2; ++par) {
+            const int i = c * 2 + par;
+            p.copy_gofs[i] = (int64_t)i * g.plane0;
+            p.copy_sofs[i] = sofs;
+            p.copy_bytes[i] = (uint32_t)(g.R0 + 2 + par) * g.Wo0 * 16;
+            blk[c][par] = sofs;
+            sofs += p.copy_bytes[i];
+        }
+    p.stage_bytes = sofs;
+    // 21 chunks (c,kh) paired into 11 K=16 steps; chunk order = c*7 + idx, kh = l0_chunk_kh(idx)
+    p.n_steps = kW0Steps;
+    for (int s = 0; s < kW0Steps; ++s) {
+        const int c0 = 2 * s, c1 = (2 * s + 1 < 21) ? 2 * s + 1 : 2 * s;    // last step: 2nd half has zero weights
+        auto off = [&](int ch) { int c = ch / 7, kh = l0_chunk_kh(ch % 7); return blk[c][tap_par(kh)] + (uint32_t)tap_shift(kh) * g.Wo0 * 16; };
+        const uint32_t o0 = off(c0), o1 = off(c1);
+        if (o1 >= o0) { p.b_off16[s] = o0 >> 4; p.b_lbo16[s] = (o1 - o0) >> 4; }
+        else { return -2; }   // pairing must be monotone (host packer uses the same order)
+        p.a_off16[s] = (uint32_t)(s * 10240 + 3 * 1024) >> 4;
+    }
+    p.a_sa_stride16 = -(1024 >> 4);
+    p.a_lbo16 = 5120 >> 4; p.a_sbo16 = 8;
+    p.w_resident = 1; p.w_bytes = kW0Bytes;
+    p.G = 1; p.RW = 1;
+    p.RP = 3;
+    p.n_acc = 1; p.acc_delta16 = 0;
+    p.ncols = g.N0; p.acc_cols = 256; p.acc_stages = 2;
+    p.idesc = umma_idesc_bf16(128, g.N0);
+    return finalize_smem(p, kW0Bytes, smem);
+}
+
+static int setup_l1(WsParams& p, const Geo& g, int B, uint32_t* smem) {
+    p.n_tiles = B * (g.T / 2);
+    p.tiles_per_item = g.T / 2; p.v_count = 1;
+    p.item_stride = g.video1; p.u_stride = 2 * g.frame1; p.v_stride = 0;
+    p.n_sa = 3; p.n_sb = 4; p.sa_stride = g.frame1; p.sb_stride = g.slice1;
+    p.n_copies = 1; p.copy_gofs[0] = 0; p.copy_sofs[0] = 0; p.copy_bytes[0] = (uint32_t)(2 * g.frame1);
+    p.stage_bytes = (uint32_t)(2 * g.frame1);
+    p.n_steps = 49;
+    for (int kh = 0; kh < 7; ++kh)
+        for (int kw = 0; kw < 7; ++kw) {
+            const int plane = tap_par(kh) * 2 + tap_par(kw);
+            const uint32_t o = (uint32_t)(plane * 2) * (uint32_t)g.plane1 + (uint32_t)(tap_shift(kh) * g.P1 + tap_shift(kw)) * 16;
+            p.b_off16[kh * 7 + kw] = o >> 4;
+            p.b_lbo16[kh * 7 + kw] = (uint32_t)g.plane1 >> 4;
+        }
+    p.a_lbo16 = 2048 >> 4; p.a_sbo16 = 8;
+    p.w_resident = 0; p.w_bytes = 0;
+    p.G = 7; p.RW = 2; p.RP = 2;
+    p.n_acc = 2; p.acc_delta16 = (uint32_t)g.frame1 >> 4;
+    p.ncols = g.N1; p.acc_cols = 256; p.acc_stages = 1;
+    p.idesc = umma_idesc_bf16(128, g.N1);
+    return finalize_smem(p, (uint32_t)p.G * p.RW * kWeightTileBytes, smem);
+}
+
+static int setup_l2(WsParams& p, const Geo& g, int B, uint32_t* smem) {
+    const int VPT = kVideosPerTile2;
+    p.n_tiles = (B + VPT - 1) / VPT;
+    p.tiles_per_item = 1; p.v_count = 1;
+    p.item_stride = VPT * g.video2; p.u_stride = 0; p.v_stride = 0;
+    p.n_sa = 49; p.n_sb = 2; p.sa_stride = 2 * g.group2; p.sb_stride = g.group2;
+    p.n_copies = VPT;
+    for (int v = 0; v < VPT; ++v) {
+        p.copy_gofs[v] = (int64_t)v * g.video2;
+        p.copy_sofs[v] = (uint32_t)(v * g.group2);
+        p.copy_bytes[v] = (uint32_t)g.group2;
+    }
+    p.stage_bytes = (uint32_t)(VPT * g.group2);
+    p.n_steps = 12;
+    for (int kt = 0; kt < 3; ++kt)
+        for (int kc = 0; kc < 4; ++kc) {
+            p.b_off16[kt * 4 + kc] = (uint32_t)((2 * kc) * g.chunk2 + (int64_t)kt * g.HW2 * 16) >> 4;
+            p.b_lbo16[kt * 4 + kc] = (uint32_t)g.chunk2 >> 4;
+        }
+    p.a_lbo16 = 2048 >> 4; p.a_sbo16 = 8;
+    p.w_resident = 0; p.w_bytes = 0;
+    p.G = 6; p.RW = 2; p.RP = 2;
+    p.n_acc = VPT; p.acc_delta16 = (uint32_t)g.group2 >> 4;
+    p.ncols = g.N2; p.acc_cols = 128; p.acc_stages = 1;
+    p.idesc = umma_idesc_bf16(128, g.N2);
+    return finalize_smem(p, (uint32_t)p.G * p.RW * kWeightTileBytes, smem);
+}
+
+template <int EPI>
+static int launch(const WsParams& p, uint32_t smem, cudaStream_t stream) {
+    static bool configured = false;
+    static int sm_count = 148;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(ws_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(ws_gemm): %s", cudaGetErrorString(e)); return (int)e; }
+        int dev = 0; cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+        configured = true;
+    }
+    if (p.n_tiles <= 0) return 0;
+    const int grid = p.n_tiles < sm_count ? p.n_tiles : sm_count;
+    ws_gemm_kernel<EPI><<<grid, kThreads, smem, stream>>>(p);
+    return check_launch("tc ws_gemm");
+}
+
+}  // namespace tc
+}  // namespace vd
+
+using namespace vd;
+using namespace vd::tc;
+
+extern "C" int vd_tc_plan_make(vd_tc_plan* plan, int T, int H, int W) {
+    VD_REQUIRE(plan != nullptr, "tc_plan_make: NULL plan");
+    VD_REQUIRE(H == W && geo_supported(T, H), "tc path supports square 112x112 (T<=16) or 64x64 videos with T %% 4 == 0 (got T=%d H=%d W=%d)", T, H, W);
+    const Geo g = make_geo(T, H);
+    memset(plan, 0, sizeof(*plan));
+    plan->T = T; plan->H = H; plan->W = W;
+    plan->c1 = 64; plan->c2 = 128; plan->c3 = 128;
+    plan->T1 = T; plan->H1 = g.Ho0; plan->W1 = g.Wo0; plan->T1p = T; plan->H1p = g.H1; plan->W1p = g.H1;
+    plan->T2 = T; plan->H2 = g.Ho1; plan->W2 = g.Wo1; plan->T2p = g.T2; plan->H2p = g.H2; plan->W2p = g.H2;
+    plan->T3 = g.To2; plan->H3 = g.Ho2; plan->W3 = g.Wo2; plan->T3p = g.T3p; plan->H3p = g.H3p; plan->W3p = g.H3p;
+    plan->embed_dim = g.embed_dim;
+    plan->x0_bytes_per_video = g.video0;
+    plan->a1_bytes_per_video = g.video1;
+    plan->a2_bytes_per_video = g.video2;
+    plan->w0_bytes = kW0Bytes;
+    plan->w1_bytes = (int64_t)588 * kWeightTileBytes;
+    plan->w2_bytes = (int64_t)1176 * kWeightTileBytes;
+    plan->tab_bytes = 0;
+    return 0;
+}
+
+extern "C" int vd_tc_conv_layer(int layer, const void* in, const void* wimg, const float* bias, void* out,
+                                uint8_t* code, const vd_tc_plan* plan, const int64_t* item_index, int B, int raw,
+                                void* stream) {
+    VD_REQUIRE(plan && in && wimg && out, "tc_conv_layer: NULL pointer");
+    VD_REQUIRE(layer >= 0 && layer <= 2, "tc_conv_layer: layer must be 0, 1 or 2");
+    VD_REQUIRE(B >= 0, "tc_conv_layer: negative batch");
+    VD_REQUIRE(geo_supported(plan->T, plan->H), "tc_conv_layer: unsupported geometry");
+    VD_REQUIRE(raw || bias, "tc_conv_layer: bias is NULL");
+    if (B == 0) return 0;
+    WsParams p;
+    memset(&p, 0, sizeof(p));
+    const Geo g = make_geo(plan->T, plan->H);
+    uint32_t smem = 0;
+    int rc = layer == 0 ? setup_l0(p, g, B, &smem) : layer == 1 ? setup_l1(p, g, B, &smem) : setup_l2(p, g, B, &smem);
+    if (rc) { if (rc == -2) set_error("tc conv 0: non-monotone chunk pairing"); return rc; }
+    VD_REQUIRE(item_index == nullptr || layer == 0, "tc_conv_layer: item_index is only valid for layer 0");
+    p.pix = (const uint8_t*)in; p.wimg = (const uint8_t*)wimg; p.item_index = item_index;
+    p.epi.bias = bias; p.epi.out = (uint8_t*)out; p.epi.code = code; p.epi.raw = (float*)out;
+    p.epi.T = plan->T; p.epi.n_items = B; p.epi.g = g;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (raw) return launch<EPI_RAW>(p, smem, s);
+    if (layer == 0) return launch<EPI_L0>(p, smem, s);
+    if (layer == 1) return launch<EPI_L1>(p, smem, s);
+    return launch<EPI_L2>(p, smem, s);
+}
+
+// Host-side introspection for the CPU emulator in tests/ (no GPU work): dumps the exact kernel
+// parameters that vd_tc_conv_layer would launch with.
+extern "C" int vd_tc_debug_params(int layer, const vd_tc_plan* plan, int B, int64_t* out, int cap) {
+    VD_REQUIRE(plan && out && cap >= 32 + 3 * kMaxCopies + 3 * kMaxSteps, "tc_debug_params: buffer too small");
+    VD_REQUIRE(layer >= 0 && layer <= 2 && geo_supported(plan->T, plan->H), "tc_debug_params: bad layer / geometry");
+    WsParams p;
+    memset(&p, 0, sizeof(p));
+    const Geo g = make_geo(plan->T, plan->H);
+    uint32_t smem = 0;
+    int rc = layer == 0 ? setup_l0(p, g, B, &smem) : layer == 1 ? setup_l1(p, g, B, &smem) : setup_l2(p, g, B, &smem);
+    if (rc) return rc;
+    int i = 0;
+    out[i++] = p.n_tiles; out[i++] = p.tiles_per_item; out[i++] = p.v_count;
+    out[i++] = p.item_stride; out[i++] = p.u_stride; out[i++] = p.v_stride;
+    out[i++] = p.n_sa; out[i++] = p.n_sb; out[i++] = p.sa_stride; out[i++] = p.sb_stride;
+    out[i++] = p.n_copies; out[i++] = p.stage_bytes; out[i++] = p.stage_pitch; out[i++] = p.n_steps;
+    out[i++] = p.a_sa_stride16; out[i++] = p.a_lbo16; out[i++] = p.a_sbo16; out[i++] = p.w_resident;
+    out[i++] = p.w_bytes; out[i++] = p.G; out[i++] = p.RW; out[i++] = p.RP; out[i++] = p.n_acc;
+    out[i++] = p.acc_delta16; out[i++] = p.ncols; out[i++] = p.acc_cols; out[i++] = p.acc_stages;
+    out[i++] = p.idesc; out[i++] = p.smem_w_off; out[i++] = p.smem_pix_off; out[i++] = smem; out[i++] = 0;
+    for (int k = 0; k < kMaxCopies; ++k) out[i++] = p.copy_gofs[k];
+    for (int k = 0; k < kMaxCopies; ++k) out[i++] = p.copy_sofs[k];
+    for (int k = 0; k < kMaxCopies; ++k) out[i++] = p.copy_bytes[k];
+    for (int k = 0; k < kMaxSteps; ++k) out[i++] = p.b_off16[k];
+    for (int k = 0; k < kMaxSteps; ++k) out[i++] = p.b_lbo16[k];
+    for (int k = 0; k < kMaxSteps; ++k) out[i++] = p.a_off16[k];
+    return 0;
+}

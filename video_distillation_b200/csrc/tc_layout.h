@@ -1,0 +1,107 @@
+// Packed bf16 activation / weight layouts of the tensor-core path (host + device).
+//
+// ConvNet3D feature convs are k=(3,7,7) s=(1,2,2) p=(1,3,3) (networks.py:799).  Each layer is a
+// GEMM  D[cout, q] = sum_j A_j[cout, 0:16] . B_j[q, 0:16]^T  whose B operand (pixels) is read
+// straight out of the packed input through UMMA descriptors with a per-step start offset
+// ("shifted window"), so the input of a tile is staged in shared memory once and reused by
+// every filter tap.  All chunks are 16 bytes = 8 bf16.
+//
+// X0 (input of conv 0, Cin=3): "kw-expanded"
+//   [t_pad T+2][c 3][par 2][row RI0][wo Wo0] chunk = x[t_pad-1][c][h][2wo-3 .. 2wo+4],
+//   h = 2*row-2 (par 0, even h) or 2*row-3 (par 1, odd h); zero outside the video; the 8th
+//   element (kw=7) is stored as 0.  Output pixel (ho,wo) of tap kh reads plane par=(kh+1)&1 at
+//   row ho + (par ? kh/2 : (kh-1)/2): a pure row shift, so q = ho*Wo0+wo is a linear window.
+//
+// A1 (input of conv 1, Cin=64): "parity-planar"
+//   [slice 4 (16 ch)][t_pad T+2][ph 2][pw 2][k 2 (8 ch)][i RI1][j P1] chunk = 8 channels of
+//   pixel (h,w), h = 2i-2 / 2i-3 for ph = 0/1, w = 2j-2 / 2j-3 for pw = 0/1.  P1 = Wo1+2: the
+//   one out-of-row read of the odd plane (j = P1) lands on the next row's j=0, which is also a
+//   zero halo cell.  Window of tap (kh,kw): plane (ph,pw) = ((kh+1)&1,(kw+1)&1), start
+//   (rowshift*P1 + colshift) chunks; q = ho*P1 + wo (columns wo >= Wo1 are discarded).
+//
+// A2 (input of conv 2, Cin=128): "tap-expanded"
+//   [khw 49][half 2][k 8 (8 ch)][t_pad To2+2][ho Ho2][wo Wo2] chunk = 8 channels of input
+//   pixel (t_pad-1, 2ho+kh-3, 2wo+kw-3) (zero outside).  q = to*Ho2*Wo2 + ho*Wo2 + wo; tap kt is a
+//   shift of kt frames.
+#pragma once
+#include <stdint.h>
+
+namespace vd {
+namespace tc {
+
+struct Geo {
+    int T, HW;
+    // conv 0
+    int Ho0, Wo0, R0, RI0, N0;          // R0 output rows per tile, RI0 rows per parity plane
+    int64_t plane0, frame0, video0;     // bytes
+    int stage0;                         // bytes of one pixel stage in smem
+    // after pool (1,2,2)
+    int H1;                             // = W1
+    // conv 1
+    int Ho1, Wo1, P1, RI1, N1;
+    int64_t plane1, frame1, slice1, video1;
+    // after pool (2,2,2)
+    int T2, H2;
+    // conv 2
+    int To2, Ho2, Wo2, HW2, N2;
+    int64_t chunk2, group2, video2;
+    int T3p, H3p, embed_dim;
+};
+
+inline Geo make_geo(int T, int HW) {
+    Geo g{};
+    g.T = T; g.HW = HW;
+    g.Ho0 = HW / 2; g.Wo0 = HW / 2;
+    g.R0 = (g.Wo0 * 8 <= 256) ? 8 : 4;
+    g.RI0 = g.Ho0 + 3;
+    g.N0 = g.R0 * g.Wo0;
+    g.plane0 = (int64_t)g.RI0 * g.Wo0 * 16;
+    g.frame0 = 6 * g.plane0;
+    g.video0 = (int64_t)(T + 2) * g.frame0;
+    g.stage0 = 3 * (2 * g.R0 + 5) * g.Wo0 * 16;
+    g.H1 = g.Ho0 / 2;
+    g.Ho1 = g.H1 / 2; g.Wo1 = g.H1 / 2;
+    g.P1 = g.Wo1 + 2; g.RI1 = g.Ho1 + 4;
+    g.N1 = g.Ho1 * g.P1;
+    g.plane1 = (int64_t)g.RI1 * g.P1 * 16;
+    g.frame1 = 8 * g.plane1;
+    g.slice1 = (int64_t)(T + 2) * g.frame1;
+    g.video1 = 4 * g.slice1;
+    g.T2 = T / 2; g.H2 = g.Ho1 / 2;
+    g.To2 = g.T2; g.Ho2 = (g.H2 - 1) / 2 + 1; g.Wo2 = g.Ho2;
+    g.HW2 = g.Ho2 * g.Wo2;
+    g.N2 = g.To2 * g.HW2;
+    g.chunk2 = (int64_t)(g.To2 + 2) * g.HW2 * 16;
+    g.group2 = 8 * g.chunk2;
+    g.video2 = 98 * g.group2;
+    g.T3p = g.To2 / 2; g.H3p = g.Ho2 / 2;
+    g.embed_dim = 128 * g.T3p * g.H3p * g.H3p;
+    return g;
+}
+
+inline bool geo_supported(int T, int HW) {
+    if (!(HW == 112 || HW == 64)) return false;
+    if (T < 4 || (T % 4) != 0 || T > 32) return false;
+    Geo g = make_geo(T, HW);
+    return g.N0 % 16 == 0 && g.N0 <= 256 && g.N1 % 16 == 0 && g.N1 <= 256 && g.N2 % 16 == 0 && g.N2 <= 128 &&
+           g.Ho0 % g.R0 == 0;
+}
+
+// row / column shift of filter tap k (0..6) inside its parity plane, and the plane it reads
+__host__ __device__ inline int tap_par(int k) { return (k + 1) & 1; }           // 0: even coord, 1: odd coord
+__host__ __device__ inline int tap_shift(int k) { return (k & 1) ? (k - 1) / 2 : k / 2; }
+// plane index of an input coordinate and its position in the plane
+__host__ __device__ inline int coord_par(int x) { return x & 1; }
+__host__ __device__ inline int coord_pos(int x) { return (x & 1) ? (x + 3) / 2 : x / 2 + 1; }
+
+// conv 0 chunk order inside one channel: sorted by shared-memory offset (even-h plane first)
+// so that chunk pairs (2s, 2s+1) always have a positive descriptor LBO.  chunk = c*7 + idx.
+__host__ __device__ inline int l0_chunk_kh(int idx) { return idx < 3 ? 2 * idx + 1 : 2 * (idx - 3); }
+
+constexpr int kWeightTileBytes = 4096;      // [k 2][128 rows][16 B]
+constexpr int kVideosPerTile2 = 4;          // conv 2: accumulators (videos) per CTA tile
+constexpr int kW0Steps = 11;                // conv 0: 21 (c,kh) chunks paired into K=16 steps
+constexpr int kW0Bytes = kW0Steps * 2 * 5 * 1024;
+
+}  // namespace tc
+}  // namespace vd

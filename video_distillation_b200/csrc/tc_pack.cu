@@ -1,0 +1,125 @@
+// Operand packers of the tensor-core path: fp32 videos -> X0 (kw-expanded bf16), fp32 OIDHW
+// weights -> UMMA weight images.  Layouts: tc_layout.h.  Memory-bound, one 16-byte chunk (or
+// one bf16 element for weights) per thread.
+#include "tc_common.cuh"
+#include "tc_layout.h"
+
+namespace vd {
+namespace tc {
+
+// video (Bsrc, T, 3, H, W) fp32 -> x0 (B, T+2, 3, 2, RI0, Wo0) chunks; source video of item b is
+// index ? index[b] : b (the device-resident get_images gather, distill_s2d_ms.py:81-87).
+__global__ void pack_video_kernel(const float* __restrict__ video, const int64_t* __restrict__ index,
+                                  uint4* __restrict__ x0, int64_t total, int T, int HW, int RI0, int Wo0) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int wo = (int)(i % Wo0); int64_t q = i / Wo0;
+        int row = (int)(q % RI0); q /= RI0;
+        int par = (int)(q % 2); q /= 2;
+        int c = (int)(q % 3); q /= 3;
+        int tp = (int)(q % (T + 2)); int64_t b = q / (T + 2);
+        const int t = tp - 1;
+        const int h = par ? 2 * row - 3 : 2 * row - 2;
+        uint16_t v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = 0;
+        if (t >= 0 && t < T && h >= 0 && h < HW) {
+            const int64_t src = index ? index[b] : b;
+            const float* p = video + (((src * T + t) * 3 + c) * HW + h) * (int64_t)HW;
+#pragma unroll
+            for (int k = 0; k < 7; ++k) {
+                const int w = 2 * wo + k - 3;
+                if (w >= 0 && w < HW) v[k] = f2bf(__ldg(p + w));
+            }
+        }
+        uint4 o;
+        o.x = v[0] | ((uint32_t)v[1] << 16); o.y = v[2] | ((uint32_t)v[3] << 16);
+        o.z = v[4] | ((uint32_t)v[5] << 16); o.w = v[6] | ((uint32_t)v[7] << 16);
+        x0[i] = o;
+    }
+}
+
+// conv 0 image: [p 11][k 2][blk 5][64][8] bf16; blk 0,4 = zero, blk b = W[kt = 3-b]
+__global__ void pack_w0_kernel(const float* __restrict__ w, uint16_t* __restrict__ img) {
+    const int total = kW0Bytes / 2;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int e = i % 8; int q = i / 8;
+        int row = q % 64; q /= 64;
+        int blk = q % 5; q /= 5;
+        int k = q % 2; int p = q / 2;
+        const int ch = 2 * p + k;
+        float v = 0.f;
+        if (ch < 21 && e < 7 && blk >= 1 && blk <= 3) {
+            const int c = ch / 7, kh = l0_chunk_kh(ch % 7), kt = 3 - blk;
+            v = w[(((row * 3 + c) * 3 + kt) * 7 + kh) * 7 + e];
+        }
+        img[i] = f2bf(v);
+    }
+}
+
+// conv 1 image: [kt 3][slice 4][kh 7][kw 7][k 2][128][8]
+__global__ void pack_w1_kernel(const float* __restrict__ w, uint16_t* __restrict__ img) {
+    const int total = 588 * kWeightTileBytes / 2;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int e = i % 8; int q = i / 8;
+        int row = q % 128; q /= 128;
+        int k = q % 2; q /= 2;
+        int kw = q % 7; q /= 7;
+        int kh = q % 7; q /= 7;
+        int slice = q % 4; int kt = q / 4;
+        const int ci = slice * 16 + k * 8 + e;
+        img[i] = f2bf(w[(((row * 64 + ci) * 3 + kt) * 7 + kh) * 7 + kw]);
+    }
+}
+
+// conv 2 image: [kh 7][kw 7][half 2][kt 3][kc 4][k 2][128][8]
+__global__ void pack_w2_kernel(const float* __restrict__ w, uint16_t* __restrict__ img) {
+    const int total = 1176 * kWeightTileBytes / 2;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int e = i % 8; int q = i / 8;
+        int row = q % 128; q /= 128;
+        int k = q % 2; q /= 2;
+        int kc = q % 4; q /= 4;
+        int kt = q % 3; q /= 3;
+        int half = q % 2; q /= 2;
+        int kw = q % 7; int kh = q / 7;
+        const int ci = half * 64 + kc * 16 + k * 8 + e;
+        img[i] = f2bf(w[(((row * 128 + ci) * 3 + kt) * 7 + kh) * 7 + kw]);
+    }
+}
+
+}  // namespace tc
+}  // namespace vd
+
+using namespace vd;
+using namespace vd::tc;
+
+extern "C" int vd_tc_pack_video(const float* video, const int64_t* index, void* x0, const vd_tc_plan* plan,
+                                int B, void* stream) {
+    VD_REQUIRE(video && x0 && plan, "tc_pack_video: NULL pointer");
+    VD_REQUIRE(geo_supported(plan->T, plan->H), "tc_pack_video: unsupported geometry");
+    if (B <= 0) return 0;
+    const Geo g = make_geo(plan->T, plan->H);
+    const int64_t total = (int64_t)B * (g.T + 2) * 6 * g.RI0 * g.Wo0;
+    int64_t blocks = ceil_div(total, 256);
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    pack_video_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(video, index, (uint4*)x0, total, g.T, g.HW, g.RI0, g.Wo0);
+    return check_launch("tc_pack_video");
+}
+
+extern "C" int vd_tc_pack_weights(const float* w_l0, const float* w_l1, const float* w_l2, void* w0, void* w1,
+                                  void* w2, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (w_l0 && w0) {
+        pack_w0_kernel<<<148, 256, 0, s>>>(w_l0, (uint16_t*)w0);
+        if (int e = check_launch("tc_pack_w0")) return e;
+    }
+    if (w_l1 && w1) {
+        pack_w1_kernel<<<148 * 4, 256, 0, s>>>(w_l1, (uint16_t*)w1);
+        if (int e = check_launch("tc_pack_w1")) return e;
+    }
+    if (w_l2 && w2) {
+        pack_w2_kernel<<<148 * 4, 256, 0, s>>>(w_l2, (uint16_t*)w2);
+        if (int e = check_launch("tc_pack_w2")) return e;
+    }
+    return 0;
+}
