@@ -1,0 +1,76 @@
+"""Host-side logic that needs no GPU: drop-in module surface, ReparamModule flattening, sampling."""
+import inspect
+
+import numpy as np
+import torch
+
+import oracle
+
+
+def test_dropin_module_names_and_signatures():
+    import networks
+    import reparam_module
+    import utils
+    sig = inspect.signature(utils.get_network)
+    assert list(sig.parameters) == ['model', 'channel', 'num_classes', 'im_size', 'frames', 'dist']
+    sig = inspect.signature(utils.evaluate_synset)
+    assert list(sig.parameters) == ['it_eval', 'net', 'images_train', 'labels_train', 'testloader', 'args', 'mode',
+                                    'return_loss', 'test_freq']
+    sig = inspect.signature(networks.ConvNet3D.__init__)
+    assert list(sig.parameters)[1:] == ['channel', 'num_classes', 'net_width', 'net_depth', 'net_act', 'net_norm',
+                                        'net_pooling', 'frames', 'im_size', 'dropout_keep_prob']
+    sig = inspect.signature(utils.Conv3DNet.__init__)
+    assert list(sig.parameters)[1:] == ['in_channel', 'mid_channel', 'out_channel', 'img_size', 'kernel_size', 'mode']
+    assert hasattr(reparam_module.ReparamModule, 'embed') and hasattr(reparam_module.ReparamModule, 'forward')
+
+
+def test_get_network_seeding_and_param_layout(monkeypatch):
+    """get_network reseeds from the clock (utils.py:519); with the clock patched the parameters equal the
+    oracle's seeded init bit for bit, in the reference's state_dict order."""
+    from video_distillation_b200 import utils
+    monkeypatch.setattr(utils.time, 'time', lambda: 4321 / 1000.0 + 1e-7)
+    net = utils.get_network('ConvNet3D', 3, 50, (112, 112), dist=False)
+    ref = oracle.init_convnet3d(4321, 3, 50)
+    sd = net.state_dict()
+    assert list(sd.keys()) == list(ref.keys())
+    assert all(torch.equal(sd[k], ref[k]) for k in ref)
+    mods = [type(m).__name__ for m in net.features]
+    assert mods == ['Conv3d', 'ReLU', 'MaxPool3d'] * 3                      # none / maxpooling (utils.py:608-609)
+    assert net.features[2].kernel_size == (1, 2, 2) and net.features[5].kernel_size == (2, 2, 2)
+
+
+def test_reparam_module_flat_layout():
+    from video_distillation_b200.networks import ConvNet3D
+    from video_distillation_b200.reparam_module import ReparamModule
+    torch.manual_seed(0)
+    net = ConvNet3D(3, 50, 128, 3, 'relu', 'none', 'maxpooling', 16, (112, 112))
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    rp = ReparamModule(net)
+    assert rp.param_numel == 3647666 and [n for n, _ in rp.named_parameters()] == ['flat_param']
+    assert torch.equal(rp.flat_param.detach(), oracle.flatten_params(sd))
+    assert rp._param_numels == (28224, 64, 1204224, 128, 2408448, 128, 6400, 50)
+    # views are re-installed around a call and restored afterwards
+    other = torch.zeros_like(rp.flat_param)
+    with rp.unflattened_param(other):
+        assert rp.module.features[0].weight.data_ptr() == other.data_ptr()
+    assert rp.module.features[0].weight.data_ptr() == rp.flat_param.data_ptr()
+
+
+def test_device_dataset_sampling_is_reference_stream():
+    """Every rank replays the full numpy stream; shards only differ in what they keep."""
+    from video_distillation_b200.distill import DeviceDataset, owned_classes
+    C, per = 5, 6
+    videos = torch.zeros(C * per, 1, 3, 2, 2)
+    labels = [c for c in range(C) for _ in range(per)]
+    indices_class = [list(range(c * per, (c + 1) * per)) for c in range(C)]
+    np.random.seed(3)
+    want = np.stack([oracle.sample_real_indices(indices_class, c, 4) for c in range(C)])
+    for rank in range(2):
+        ds = DeviceDataset(videos, labels, C, 'cpu', rank=rank, world=2)
+        np.random.seed(3)
+        got = ds.sample_all_classes(4)
+        assert np.array_equal(got, want)
+        own = owned_classes(C, rank, 2)
+        loc = ds.local_index(got[own])
+        assert ds.videos.shape[0] == len(own) * per and int(loc.max()) < ds.videos.shape[0]
+    assert owned_classes(50, 0, 8) == [0, 8, 16, 24, 32, 40, 48] and len(owned_classes(50, 7, 8)) == 6

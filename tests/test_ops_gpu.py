@@ -1,0 +1,218 @@
+"""GPU parity of the exact fp32 kernels against the CPU oracle / plain torch fp64 (through the C ABI).
+
+Tolerance for fp32 kernels vs fp64 truth: 2e-5 relative L2 (summation order only); integer /
+index outputs (routing codes, gathers) are bit-exact.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+GEOMS = [
+    # (N, Cin, T, H, W, Cout, k, s, p)
+    (2, 3, 4, 20, 20, 16, (3, 7, 7), (1, 2, 2), (1, 3, 3)),
+    (2, 8, 4, 7, 7, 12, (3, 7, 7), (1, 2, 2), (1, 3, 3)),          # H=7 -> 4: non-injective output size
+    (3, 4, 5, 9, 8, 3, (3, 3, 3), (1, 1, 1), (1, 1, 1)),           # composer geometry
+    (2, 16, 3, 1, 1, 5, (1, 1, 1), (1, 1, 1), (0, 0, 0)),          # logit conv
+]
+
+
+@pytest.mark.parametrize('geom', GEOMS)
+def test_conv_trio(geom):
+    from video_distillation_b200 import ops
+    N, Cin, T, H, W, Cout, k, s, p = geom
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(N, Cin, T, H, W, generator=g)
+    w = torch.randn(Cout, Cin, *k, generator=g) * 0.1
+    b = torch.randn(Cout, generator=g)
+    xd, wd, bd = x.double().requires_grad_(True), w.double().requires_grad_(True), b.double().requires_grad_(True)
+    y_ref = F.conv3d(xd, wd, bd, stride=s, padding=p)
+    gy = torch.randn(y_ref.shape, generator=g)
+    y_ref.backward(gy.double())
+    xc, wc, bc = x.cuda().requires_grad_(True), w.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    y = ops.conv3d(xc, wc, bc, s, p)
+    assert rel(y, y_ref) < 2e-5
+    y.backward(gy.cuda())
+    assert rel(xc.grad, xd.grad) < 2e-5
+    assert rel(wc.grad, wd.grad) < 2e-5
+    assert rel(bc.grad, bd.grad) < 2e-5
+
+
+def test_conv_double_backward():
+    """grad-of-grad through the Function closure == torch's _convolution_double_backward (MTT path)."""
+    from video_distillation_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, 4, 3, 9, 9, generator=g)
+    w = torch.randn(6, 4, 3, 7, 7, generator=g) * 0.1
+    s, p = (1, 2, 2), (1, 3, 3)
+
+    def run(x, w, conv):
+        x = x.requires_grad_(True)
+        w = w.requires_grad_(True)
+        y = conv(x, w)
+        loss = (y ** 3).sum()
+        gw, = torch.autograd.grad(loss, w, create_graph=True)
+        w2 = w - 0.1 * gw
+        y2 = conv(x, w2)
+        out = (y2 ** 2).sum() + (gw ** 2).sum()
+        gx, gw2 = torch.autograd.grad(out, [x, w])
+        return out, gx, gw2
+
+    ref = run(x.double(), w.double(), lambda a, b: F.conv3d(a, b, None, s, p))
+    got = run(x.cuda(), w.cuda(), lambda a, b: ops.conv3d(a, b, None, s, p))
+    for r, q in zip(ref, got):
+        assert rel(q, r) < 5e-5, rel(q, r)
+
+
+@pytest.mark.parametrize('k', [(1, 2, 2), (2, 2, 2), (1, 1, 1)])
+def test_relu_maxpool_routing(k):
+    from video_distillation_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(3, 5, 4, 6, 10, generator=g)
+    x[0, 0, :, :2, :2] = 0.0                      # all-zero window: first index wins, gradient is zero
+    x[0, 1, 0, 0, :4] = torch.tensor([0.0, 3.0, 3.0, 1.0])   # tie -> first maximum
+    xr = x.clone().requires_grad_(True)
+    y_ref, idx = F.max_pool3d(F.relu(xr), k, k, return_indices=True)
+    gy = torch.randn(y_ref.shape, generator=g)
+    y_ref.backward(gy)
+    xc = x.cuda().requires_grad_(True)
+    y, code = ops.relu_maxpool3d(xc, k, return_code=True)
+    assert torch.equal(y.cpu(), y_ref.detach())
+    y.backward(gy.cuda())
+    assert torch.equal(xc.grad.cpu(), xr.grad)
+    # argmax position equals ATen's wherever the output is active
+    T, H, W = x.shape[2:]
+    it, ih, iw = idx // (H * W), (idx // W) % H, idx % W
+    pos = (it % k[0]) * (k[1] * k[2]) + (ih % k[1]) * k[2] + (iw % k[2])
+    act = (code.cpu() & 8) > 0
+    assert torch.equal(act, y_ref > 0)
+    assert torch.equal((code.cpu() & 7).long()[act], pos[act])
+    # double backward: gather with the saved code
+    c0 = torch.randn(x.shape, generator=g)
+    cr = c0.clone().requires_grad_(True)
+    z_ref = torch.where(act, cr.flatten(2).gather(2, idx.flatten(2)).view_as(idx), torch.zeros(()))
+    z_ref.backward(gy)
+    c = c0.cuda().requires_grad_(True)
+    z = ops.route_with_code(c, code, k)
+    assert torch.equal(z.cpu(), z_ref.detach())
+    z.backward(gy.cuda())
+    assert torch.equal(c.grad.cpu(), cr.grad)
+
+
+def test_composer_golden():
+    from oracle import synth
+    from video_distillation_b200.utils import Conv3DNet
+    gold = np.load(os.path.join(GOLD, 'composer.npz'))
+    hal_p = synth.synth_hallucinator(3)
+    hal = Conv3DNet()
+    hal.load_state_dict(hal_p)
+    hal = hal.cuda()
+    static = synth.hash_uniform((5, 3, 16, 16), 21).cuda().requires_grad_(True)
+    dynamic = synth.hash_uniform((5, 4, 1, 16, 16), 22).cuda().requires_grad_(True)
+    y = hal(static, dynamic)
+    assert rel(y, torch.from_numpy(gold['y'])) < 1e-6
+    gy = synth.hash_uniform(tuple(y.shape), 23).cuda()
+    y.backward(gy)
+    assert rel(static.grad, torch.from_numpy(gold['grad_static'])) < 1e-5
+    assert rel(dynamic.grad, torch.from_numpy(gold['grad_dynamic'])) < 1e-5
+    assert rel(hal.encoder.weight.grad, torch.from_numpy(gold['grad_weight'])) < 1e-5
+    assert rel(hal.encoder.bias.grad, torch.from_numpy(gold['grad_bias'])) < 1e-5
+
+
+def test_composer_gather_and_accumulate():
+    """Fused index gather (distill_s2d_ms.py:409-410) incl. repeated rows -> accumulated gradient."""
+    import oracle
+    from video_distillation_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    C, dpc, T, H, W, spc = 3, 2, 4, 10, 12, 2
+    static_syn = torch.randn(C * spc, 3, H, W, generator=g)
+    dynamic_syn = torch.randn(C, dpc, T, 1, H, W, generator=g)
+    hal = oracle.init_hallucinator(5)
+    label = torch.tensor([0, 1, 1, 2, 1])
+    didx = torch.tensor([1, 0, 0, 1, 1])          # (1,0) appears twice
+    sidx = torch.tensor([1, 2, 2, 5, 3])
+    s = static_syn.clone().requires_grad_(True)
+    d = dynamic_syn.clone().requires_grad_(True)
+    w = hal['encoder.weight'].clone().requires_grad_(True)
+    b = hal['encoder.bias'].clone().requires_grad_(True)
+    y_ref = oracle.compose(s[sidx], d[label, didx], w, b)
+    gy = torch.randn(y_ref.shape, generator=g)
+    y_ref.backward(gy)
+    sc, dc = static_syn.cuda().requires_grad_(True), dynamic_syn.cuda().requires_grad_(True)
+    wc, bc = hal['encoder.weight'].cuda().requires_grad_(True), hal['encoder.bias'].cuda().requires_grad_(True)
+    y = ops.compose(sc, dc, wc, bc, sidx.cuda(), label.cuda(), didx.cuda())
+    assert rel(y, y_ref) < 1e-6
+    y.backward(gy.cuda())
+    assert rel(dc.grad, d.grad) < 1e-5 and rel(sc.grad, s.grad) < 1e-5
+    assert rel(wc.grad, w.grad) < 1e-5 and rel(bc.grad, b.grad) < 1e-5
+
+
+def test_dm_loss_and_class_mean():
+    import oracle
+    from video_distillation_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    C, nr, ns, D = 7, 9, 3, 300
+    er = torch.randn(C, nr, D, generator=g)
+    es = torch.randn(C, ns, D, generator=g).requires_grad_(True)
+    loss_ref = sum(oracle.dm_loss(er[c], es[c]) for c in range(C))
+    loss_ref.backward()
+    esc = es.detach().cuda().requires_grad_(True)
+    mr = ops.class_mean(er.cuda())
+    assert rel(mr, er.mean(1)) < 1e-6
+    loss = ops.dm_loss(mr, esc)
+    assert rel(loss, loss_ref.detach()) < 1e-6
+    (2.0 * loss).backward()
+    assert rel(esc.grad, 2.0 * es.grad) < 1e-6
+
+
+def test_sgd_momentum_matches_torch():
+    from video_distillation_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    p0 = torch.randn(1003, generator=g)
+    p_ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.SGD([p_ref], lr=0.3, momentum=0.95)
+    p = p0.cuda()
+    buf = torch.empty_like(p)
+    for it in range(3):
+        grad = torch.randn(1003, generator=g)
+        if it == 1:
+            grad[::2] = 0.0                      # dense semantics: zero-grad entries still move
+        p_ref.grad = grad.clone()
+        opt.step()
+        ops.sgd_momentum_(p, grad.cuda(), buf, 0.3, 0.95, it == 0)
+        assert rel(p, p_ref.detach()) < 1e-6
+
+
+def test_instancenorm_avgpool_variant():
+    from video_distillation_b200 import ops
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(2, 6, 4, 6, 6, generator=g)
+    gam, bet = torch.rand(6, generator=g) + 0.5, torch.randn(6, generator=g)
+    xd, gd, bd = (t.double().requires_grad_(True) for t in (x, gam, bet))
+    y_ref = F.avg_pool3d(F.relu(F.group_norm(xd, 6, gd, bd, 1e-5)), 2, 2)
+    gy = torch.randn(y_ref.shape, generator=g)
+    y_ref.backward(gy.double())
+    xc, gc, bc = (t.cuda().requires_grad_(True) for t in (x, gam, bet))
+    y = ops.avgpool3d_2(ops.instancenorm_relu(xc, gc, bc))
+    assert rel(y, y_ref) < 2e-5
+    y.backward(gy.cuda())
+    assert rel(xc.grad, xd.grad) < 1e-4 and rel(gc.grad, gd.grad) < 1e-4 and rel(bc.grad, bd.grad) < 1e-4
+
+
+def test_sqdist():
+    from video_distillation_b200 import ops
+    g = torch.Generator().manual_seed(7)
+    a, b = torch.randn(100003, generator=g), torch.randn(100003, generator=g)
+    assert rel(ops.sqdist(a.cuda(), b.cuda()), ((a.double() - b.double()) ** 2).sum()) < 1e-5

@@ -1,0 +1,180 @@
+"""GPU parity of the tcgen05 tensor-core path (all calls go through the C ABI).
+
+Order = bring-up order: packers (bit-exact vs the numpy model), raw accumulators of each layer
+vs fp64 conv on the same bf16-rounded operands, fused epilogues (bias+ReLU+MaxPool+code, packed
+output layouts), then the whole embed vs the oracle.
+Tolerances: fp32 accumulation of bf16 products -> 2e-5 relative L2 on raw accumulators; pooled
+bf16 outputs -> 1 bf16 ulp (4e-3 relative per element); embeddings vs the fp32 oracle on
+bf16-representable inputs/weights -> 1e-2 relL2 (bf16 activations between layers).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import tc_emulator as em
+
+pytestmark = pytest.mark.gpu
+
+DUMP = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out')
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def conv_ref(x, w, bias=None):
+    return F.conv3d(x.double().cpu(), w.double().cpu(), None if bias is None else bias.double().cpu(),
+                    stride=(1, 2, 2), padding=(1, 3, 3)).float()
+
+
+def dump(name, **arrs):
+    os.makedirs(DUMP, exist_ok=True)
+    np.savez_compressed(os.path.join(DUMP, name), **{k: (v.cpu().numpy() if torch.is_tensor(v) else v) for k, v in arrs.items()})
+
+
+def make_net(T, HW, seed=0):
+    from video_distillation_b200.tc import TcConvNet3D
+    g = torch.Generator().manual_seed(seed)
+    w0 = em.bf16_round(torch.randn(64, 3, 3, 7, 7, generator=g) * 0.08)
+    w1 = em.bf16_round(torch.randn(128, 64, 3, 7, 7, generator=g) * 0.02)
+    w2 = em.bf16_round(torch.randn(128, 128, 3, 7, 7, generator=g) * 0.02)
+    b0 = torch.randn(64, generator=g) * 0.1
+    b1 = torch.randn(128, generator=g) * 0.1
+    b2 = torch.randn(128, generator=g) * 0.1
+    net = TcConvNet3D(T, HW, HW, 'cuda')
+    net.load_weights(*(t.cuda() for t in (w0, b0, w1, b1, w2, b2)))
+    return net, (w0, b0, w1, b1, w2, b2)
+
+
+CASES = [(8, 64), (4, 112)]
+
+
+@pytest.mark.parametrize('T,HW', CASES)
+def test_packers_bit_exact(T, HW):
+    net, (w0, b0, w1, b1, w2, b2) = make_net(T, HW)
+    g = em.Geo(T, HW)
+    video = em.bf16_round(torch.randn(3, T, 3, HW, HW, generator=torch.Generator().manual_seed(1)))
+    x0 = net.pack_video(video.cuda()).cpu().numpy().view(np.uint16)
+    ref = em.pack_x0(video, g).reshape(-1)
+    assert np.array_equal(x0[:ref.size], ref)
+    # gather by index
+    idx = torch.tensor([2, 0], device='cuda')
+    x0i = net.pack_video(video.cuda(), index=idx).cpu().numpy().view(np.uint16)
+    refi = em.pack_x0(video[[2, 0]], g).reshape(-1)
+    assert np.array_equal(x0i[:refi.size], refi)
+    assert np.array_equal(net.w0.cpu().numpy().view(np.uint16), em.pack_w0(w0).reshape(-1))
+    assert np.array_equal(net.w1.cpu().numpy().view(np.uint16), em.pack_w1(w1).reshape(-1))
+    assert np.array_equal(net.w2.cpu().numpy().view(np.uint16), em.pack_w2(w2).reshape(-1))
+
+
+@pytest.mark.parametrize('T,HW', CASES)
+def test_raw_layer2(T, HW):
+    """Smallest configuration first: conv 2 (N = To2*HW2, 4 accumulators, streamed weights)."""
+    net, (w0, b0, w1, b1, w2, b2) = make_net(T, HW)
+    g = em.Geo(T, HW)
+    B = 5
+    x = em.bf16_round(torch.randn(B, 128, g.T2, g.H2, g.H2, generator=torch.Generator().manual_seed(2)))
+    a2 = torch.from_numpy(em.pack_a2(x, g, Bpad=8).view(np.int16)).cuda()
+    p = em.Params(2, T, HW, B)
+    raw = torch.zeros(p.n_tiles, p.n_acc, 128, p.ncols, device='cuda')
+    net.conv_layer(2, a2, net.w2, None, raw, B, raw=True)
+    torch.cuda.synchronize()
+    d = raw.cpu().reshape(-1, 128, g.To2, g.Ho2, g.Wo2)[:B]
+    y = conv_ref(x, w2)
+    r = rel(d, y)
+    if r > 2e-5:
+        dump(f'raw_l2_{T}_{HW}.npz', d=raw, x=x, w=w2)
+    assert r < 2e-5, r
+
+
+@pytest.mark.parametrize('T,HW', CASES)
+def test_raw_layer1(T, HW):
+    net, (w0, b0, w1, b1, w2, b2) = make_net(T, HW)
+    g = em.Geo(T, HW)
+    B = 2
+    x = em.bf16_round(torch.randn(B, 64, T, g.H1, g.H1, generator=torch.Generator().manual_seed(3)))
+    a1 = torch.from_numpy(em.pack_a1(x, g).view(np.int16)).cuda()
+    p = em.Params(1, T, HW, B)
+    raw = torch.zeros(p.n_tiles, p.n_acc, 128, p.ncols, device='cuda')
+    net.conv_layer(1, a1, net.w1, None, raw, B, raw=True)
+    torch.cuda.synchronize()
+    d = raw.cpu().reshape(B, T // 2, 2, 128, g.Ho1, g.P1)[..., :g.Wo1]          # (B,tp,a,cout,ho,wo)
+    d = d.permute(0, 3, 1, 2, 4, 5).reshape(B, 128, T, g.Ho1, g.Wo1)
+    y = conv_ref(x, w1)
+    r = rel(d, y)
+    if r > 2e-5:
+        dump(f'raw_l1_{T}_{HW}.npz', d=raw, x=x, w=w1)
+    assert r < 2e-5, r
+
+
+@pytest.mark.parametrize('T,HW', CASES)
+def test_raw_layer0(T, HW):
+    net, (w0, b0, w1, b1, w2, b2) = make_net(T, HW)
+    g = em.Geo(T, HW)
+    B = 2
+    video = em.bf16_round(torch.randn(B, T, 3, HW, HW, generator=torch.Generator().manual_seed(4)))
+    x0 = net.pack_video(video.cuda())
+    p = em.Params(0, T, HW, B)
+    raw = torch.zeros(p.n_tiles, p.n_acc, 128, p.ncols, device='cuda')
+    net.conv_layer(0, x0, net.w0, None, raw, B, raw=True)
+    torch.cuda.synchronize()
+    nrb = g.Ho0 // g.R0
+    d = raw.cpu().reshape(B, T // 2, nrb, 2, 64, g.R0, g.Wo0)                      # (B,tp,rb,f,cout,r,wo)
+    d = d.permute(0, 4, 1, 3, 2, 5, 6).reshape(B, 64, T, g.Ho0, g.Wo0)
+    y = conv_ref(video.permute(0, 2, 1, 3, 4), w0)
+    r = rel(d, y)
+    if r > 2e-5:
+        dump(f'raw_l0_{T}_{HW}.npz', d=raw, video=video, w=w0)
+    assert r < 2e-5, r
+
+
+def _relu_pool(y, k):
+    yp, idx = F.max_pool3d(F.relu(y), k, k, return_indices=True)
+    return yp
+
+
+@pytest.mark.parametrize('T,HW', CASES)
+def test_fused_epilogues_and_embed(T, HW):
+    net, (w0, b0, w1, b1, w2, b2) = make_net(T, HW)
+    g = em.Geo(T, HW)
+    B = 5
+    video = em.bf16_round(torch.randn(B, T, 3, HW, HW, generator=torch.Generator().manual_seed(5)))
+    emb, codes = net.embed(video.cuda(), want_codes=True)
+    torch.cuda.synchronize()
+    # layer-by-layer reference with the same bf16 rounding of the stored activations
+    y0 = conv_ref(video.permute(0, 2, 1, 3, 4), w0, b0)
+    p0 = em.bf16_round(_relu_pool(y0, (1, 2, 2)))
+    a1 = em.unpack_a1(net._a1.cpu().numpy().view(np.uint16)[:B * g.video1 // 2], g, B)
+    assert rel(a1, p0) < 3e-3, rel(a1, p0)
+    # halo of A1 must still be zero: total energy equals the energy of the unpacked interior
+    y1 = conv_ref(a1, w1, b1)
+    p1 = em.bf16_round(_relu_pool(y1, (2, 2, 2)))
+    a2, consistent = em.unpack_a2(net._a2.cpu().numpy().view(np.uint16)[:8 * g.video2 // 2], g, B)
+    assert consistent
+    assert rel(a2, p1) < 3e-3, rel(a2, p1)
+    y2 = conv_ref(a2, w2, b2)
+    p2 = _relu_pool(y2, (2, 2, 2)).reshape(B, -1)
+    assert rel(emb, p2) < 1e-4, rel(emb, p2)
+    # routing codes: active bit must agree with "pooled output > 0" wherever the margin is clear
+    c0, c1, c2 = (c.cpu() for c in codes)
+    act2 = (c2.reshape(B, -1) & 8) > 0
+    clear = p2.abs() > 1e-3
+    assert bool((act2[clear] == (p2[clear] > 0)).all())
+    # argmax of layer 2 against torch's indices on the same input
+    _, idx = F.max_pool3d(F.relu(y2), 2, 2, return_indices=True)
+    To, Ho, Wo = y2.shape[2:]
+    it, ih, iw = idx // (Ho * Wo), (idx // Wo) % Ho, idx % Wo
+    pos = (it % 2) * 4 + (ih % 2) * 2 + (iw % 2)
+    arg2 = (c2 & 7).long()
+    agree = ((arg2 == pos) | ~act2.reshape(arg2.shape)).float().mean().item()
+    assert agree > 0.995, agree
+    # end to end against the fp32 oracle (no intermediate rounding): bf16-grade agreement
+    from oracle import convnet3d_embed
+    params = {'features.0.weight': w0, 'features.0.bias': b0, 'features.3.weight': w1, 'features.3.bias': b1,
+              'features.6.weight': w2, 'features.6.bias': b2}
+    e_or = convnet3d_embed(params, video)
+    assert rel(emb, e_or) < 1e-2, rel(emb, e_or)

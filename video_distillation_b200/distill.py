@@ -1,0 +1,370 @@
+"""The distillation inner loops re-expressed for one-process-per-GPU execution.
+
+* ``DeviceDataset``   — the real set resident in HBM (class-sharded across ranks); ``get_images``
+  keeps the reference's numpy sampling (distill_s2d_ms.py:81-87) but gathers on the device.
+* ``DMS2DTrainer``    — DM + static/dynamic memory (distill_s2d_ms.py:393-438).
+* ``DMBaselineTrainer`` — DM on leaf synthetic videos (distill_baseline.py:334-356).
+* ``MTTS2DTrainer``   — MTT unrolled student over flat parameters (distill_s2d_ms.py:197-300).
+
+The 50..400 per-class Python iterations of the reference become a handful of batched launches:
+all real videos of the rank's classes are embedded in one pass (tensor cores, bf16 operands,
+fp32 accumulate, or the exact fp32 path with precision='fp32'), reduced to class means, and the
+loss + d loss/d embedding come out of one kernel.  Classes are sharded ``c % world == rank``;
+every rank replays the full RNG streams and slices its part, so sampling is bit-identical to a
+single-GPU run; the only collective is one all-reduce of [dynamic-memory grad | hallucinator
+grad | loss] per iteration (NCCL over NVLink).
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .networks import ConvNet3D
+from .reparam_module import ReparamModule
+from .tc import TcConvNet3D, tc_supported
+from .utils import Conv3DNet, get_network
+
+
+def _world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def owned_classes(num_classes, rank, world):
+    """Class shard of a rank: c % world == rank.  50 classes / 8 ranks -> 7,7,6,6,6,6,6,6."""
+    return [c for c in range(num_classes) if c % world == rank]
+
+
+def allreduce_sum_(tensors):
+    """SUM all-reduce of a list of tensors as ONE flat message (in place); no-op for a single rank.
+    The DM path calls this once per iteration with [dynamic-memory grad, hallucinator grads, loss]."""
+    rank, world = _world()
+    if world == 1:
+        return tensors
+    flat = torch.cat([t.reshape(-1) for t in tensors])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    ofs = 0
+    for t in tensors:
+        t.copy_(flat[ofs:ofs + t.numel()].view_as(t))
+        ofs += t.numel()
+    return tensors
+
+
+class DeviceDataset:
+    """Real videos of this rank's classes, resident on the device.
+
+    ``videos`` (N, T, 3, H, W) fp32 and ``labels`` (N,) describe the FULL dataset exactly like the
+    reference's preloaded TensorDataset (distill_s2d_ms.py:28-38); only the rows whose class is
+    owned by this rank (``c % world == rank``) are uploaded.  ``indices_class`` is built as at
+    distill_s2d_ms.py:73-79, so ``np.random.permutation(indices_class[c])[:n]`` is unchanged.
+    """
+
+    def __init__(self, videos, labels, num_classes, device, rank=0, world=1):
+        labels = [int(v) for v in labels]
+        self.num_classes = num_classes
+        self.indices_class = [[] for _ in range(num_classes)]
+        for i, lab in enumerate(labels):
+            self.indices_class[lab].append(i)
+        self.rank, self.world = rank, world
+        self.owned = owned_classes(num_classes, rank, world)
+        keep = [i for i, lab in enumerate(labels) if lab % world == rank]
+        self.local_of_global = np.full(len(labels), -1, dtype=np.int64)
+        self.local_of_global[np.asarray(keep, dtype=np.int64)] = np.arange(len(keep))
+        self.device = torch.device(device)
+        idx = torch.as_tensor(keep, dtype=torch.long)
+        self.videos = videos[idx].to(self.device, non_blocking=True).contiguous()
+        self.shape = tuple(videos.shape[1:])
+
+    def sample_all_classes(self, n):
+        """The reference's per-class draws for ALL classes in order (every rank replays the whole
+        numpy stream); returns the global indices (C, n) — bit-exact with get_images."""
+        return np.stack([np.random.permutation(self.indices_class[c])[:n] for c in range(self.num_classes)])
+
+    def local_index(self, global_idx):
+        """global video indices of owned classes -> rows of ``self.videos`` (device int64)."""
+        loc = self.local_of_global[np.asarray(global_idx).reshape(-1)]
+        assert (loc >= 0).all(), 'requested a video of a class this rank does not own'
+        return torch.as_tensor(loc, dtype=torch.long).to(self.device, non_blocking=True)
+
+    def get_images(self, c, n):
+        """Reference-compatible accessor (one class)."""
+        idx = np.random.permutation(self.indices_class[c])[:n]
+        return self.videos[self.local_index(idx)]
+
+
+def frozen_convnet3d(channel, num_classes, im_size, frames, device, seed=None):
+    """A fresh frozen random ConvNet3D as at distill_s2d_ms.py:393-396.  ``seed`` (tests, multi-GPU:
+    every rank must build the same net) replaces the wall-clock reseed of get_network."""
+    if seed is None:
+        net = get_network('ConvNet3D', channel, num_classes, im_size, frames=frames)
+    else:
+        torch.random.manual_seed(int(seed))
+        net = ConvNet3D(channel, num_classes, 128, 3, 'relu', 'none', 'maxpooling', frames, im_size).to(device)
+    net.train()
+    for p in net.parameters():
+        p.requires_grad = False
+    return net
+
+
+class _RealEmbedder:
+    """Embeds real videos (forward only, frozen net) on tensor cores or on the exact fp32 path."""
+
+    def __init__(self, frames, im_size, device, precision, max_batch):
+        self.precision = precision
+        self.device = device
+        self.max_batch = max_batch
+        self.tc = None
+        if precision == 'bf16':
+            if not tc_supported(frames, im_size[0], im_size[1]):
+                raise RuntimeError(f'tensor-core path does not support videos {frames}x{im_size}')
+            self.tc = TcConvNet3D(frames, im_size[0], im_size[1], device, max_batch=max_batch)
+        elif precision != 'fp32':
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+
+    def load(self, net):
+        self.net = net
+        if self.tc is not None:
+            f = net.features
+            self.tc.load_weights(f[0].weight, f[0].bias, f[3].weight, f[3].bias, f[6].weight, f[6].bias)
+
+    @torch.no_grad()
+    def __call__(self, videos, index):
+        if self.tc is not None:
+            return self.tc.embed(videos, index=index)
+        out = []
+        for s in range(0, index.numel(), self.max_batch):
+            out.append(self.net.embed(videos[index[s:s + self.max_batch]]))
+        return torch.cat(out, 0)
+
+
+class DMS2DTrainer:
+    """State + iteration of DM with static/dynamic memory (distill_s2d_ms.py:89-108, 393-438)."""
+
+    def __init__(self, dataset, *, num_classes, channel=3, im_size=(112, 112), frames=16, vpc=1, spc=2, dpc=2,
+                 batch_real=64, lr_dynamic=1e4, lr_hal=1e-2, lr_static=1e-4, train_static=False, precision='bf16',
+                 static_syn=None, dynamic_syn=None, hal=None, max_batch=128, device='cuda'):
+        self.rank, self.world = _world()
+        self.ds = dataset
+        self.C, self.channel, self.im_size, self.frames = num_classes, channel, tuple(im_size), frames
+        self.vpc, self.spc, self.dpc, self.batch_real = vpc, spc, dpc, batch_real
+        self.lr_dynamic, self.lr_hal, self.lr_static, self.train_static = lr_dynamic, lr_hal, lr_static, train_static
+        self.device = torch.device(device)
+        H, W = self.im_size
+        # distill_s2d_ms.py:89-93 (CPU randn then .to(device), so seeds reproduce the reference)
+        if static_syn is None:
+            static_syn = torch.randn(size=(num_classes * spc, 3, H, W), dtype=torch.float)
+        if dynamic_syn is None:
+            dynamic_syn = torch.randn(size=(num_classes, dpc, frames, 1, H, W), dtype=torch.float)
+        self.hal = (hal if hal is not None else Conv3DNet()).to(self.device)
+        self.static_syn = static_syn.detach().to(self.device).contiguous().requires_grad_(train_static)
+        self.dynamic_syn = dynamic_syn.detach().to(self.device).contiguous().requires_grad_(True)
+        self._bufs = {}
+        self.embedder = _RealEmbedder(frames, self.im_size, self.device, precision, max_batch)
+        self.owned = owned_classes(num_classes, self.rank, self.world)
+        self.owned_t = torch.as_tensor(self.owned, dtype=torch.long, device=self.device)
+        self.last = {}
+
+    # ------------------------------------------------------------------ pieces
+    def sample_syn_indices(self):
+        """distill_s2d_ms.py:402-406 verbatim: two device randint draws of length C*vpc."""
+        C, vpc, spc, dev = self.C, self.vpc, self.spc, self.device
+        label = torch.tensor(np.stack([np.ones(vpc) * i for i in range(0, C)]), dtype=torch.long,
+                             requires_grad=False, device=dev).view(-1)
+        ran = torch.arange(0, C * vpc).to(dev)
+        idx = ran % vpc
+        dynamic_idx = 2 * idx + torch.randint(2, (C * vpc,), device=dev)
+        static_idx = spc * label + 2 * idx + torch.randint(2, (C * vpc,), device=dev)
+        return label, dynamic_idx, static_idx
+
+    def _sgd(self, name, p, grad, lr, momentum=0.95):
+        first = name not in self._bufs
+        if first:
+            self._bufs[name] = torch.empty_like(p)
+        ops.sgd_momentum_(p.data, grad.contiguous(), self._bufs[name], lr, momentum, first)
+
+    # ------------------------------------------------------------------ one iteration
+    def step(self, net=None, net_seed=None, indices=None, real_idx=None):
+        """One DM iteration; returns the loss (0-dim device tensor, summed over ALL classes)."""
+        C, vpc = self.C, self.vpc
+        if net is None:
+            net = frozen_convnet3d(self.channel, C, self.im_size, self.frames, self.device, seed=net_seed)
+        self.embedder.load(net)
+        label, dynamic_idx, static_idx = indices if indices is not None else self.sample_syn_indices()
+        if real_idx is None:
+            real_idx = self.ds.sample_all_classes(self.batch_real)          # (C, batch_real) global, host
+        # ---- this rank's classes
+        own = self.owned
+        n_own = len(own)
+        sel = (self.owned_t[:, None] * vpc + torch.arange(vpc, device=self.device)[None, :]).reshape(-1)
+        image_syn = self.hal.compose(self.static_syn, self.dynamic_syn, static_idx[sel], label[sel], dynamic_idx[sel])
+        ridx = self.ds.local_index(real_idx[own])                           # (n_own*batch_real,)
+        emb_real = self.embedder(self.ds.videos, ridx)                      # (n_own*batch_real, D)
+        D = emb_real.shape[1]
+        mean_real = ops.class_mean(emb_real.view(n_own, self.batch_real, D))
+        emb_syn = net.embed(image_syn).view(n_own, vpc, D)
+        loss = ops.dm_loss(mean_real, emb_syn)
+        for p in (self.dynamic_syn, self.static_syn, *self.hal.parameters()):
+            p.grad = None
+        loss.backward()
+        # ---- combine ranks: one flat all-reduce [dynamic grad | hal grads | (static grad) | loss]
+        grads = [self.dynamic_syn.grad, self.hal.encoder.weight.grad, self.hal.encoder.bias.grad]
+        if self.train_static:
+            grads.append(self.static_syn.grad)
+        loss_d = loss.detach().reshape(1).clone()
+        allreduce_sum_(grads + [loss_d])
+        # ---- optimizer steps (distill_s2d_ms.py:432-435), dense momentum SGD
+        if self.train_static:
+            self._sgd('static', self.static_syn, self.static_syn.grad, self.lr_static)
+        self._sgd('dynamic', self.dynamic_syn, self.dynamic_syn.grad, self.lr_dynamic)
+        self._sgd('hal_w', self.hal.encoder.weight, self.hal.encoder.weight.grad, self.lr_hal)
+        self._sgd('hal_b', self.hal.encoder.bias, self.hal.encoder.bias.grad, self.lr_hal)
+        self.last = dict(label=label, dynamic_idx=dynamic_idx, static_idx=static_idx, real_idx=real_idx,
+                         emb_syn=emb_syn.detach(), mean_real=mean_real, image_syn=image_syn.detach())
+        return loss_d[0]
+
+
+class DMBaselineTrainer:
+    """DM on leaf synthetic videos (distill_baseline.py:92-108, 334-356), SGD momentum 0.5."""
+
+    def __init__(self, dataset, *, num_classes, channel=3, im_size=(112, 112), frames=16, ipc=1, batch_real=64,
+                 lr_img=1.0, precision='bf16', image_syn=None, init='real', max_batch=128, device='cuda'):
+        self.rank, self.world = _world()
+        self.ds = dataset
+        self.C, self.channel, self.im_size, self.frames = num_classes, channel, tuple(im_size), frames
+        self.ipc, self.batch_real, self.lr_img = ipc, batch_real, lr_img
+        self.device = torch.device(device)
+        H, W = self.im_size
+        if image_syn is None:
+            image_syn = torch.randn(size=(num_classes * ipc, frames, channel, H, W), dtype=torch.float)
+            if init == 'real':
+                if self.world != 1:
+                    raise RuntimeError("init='real' draws from every class; build image_syn on rank 0 and pass it in")
+                for c in range(num_classes):                             # distill_baseline.py:96-100
+                    image_syn[c * ipc:(c + 1) * ipc] = dataset.get_images(c, ipc).detach().cpu()
+        self.image_syn = image_syn.detach().to(self.device).contiguous().requires_grad_(True)
+        self._buf = None
+        self.embedder = _RealEmbedder(frames, self.im_size, self.device, precision, max_batch)
+        self.owned = owned_classes(num_classes, self.rank, self.world)
+        self.last = {}
+
+    def step(self, net=None, net_seed=None, real_idx=None):
+        C, ipc = self.C, self.ipc
+        if net is None:
+            net = frozen_convnet3d(self.channel, C, self.im_size, self.frames, self.device, seed=net_seed)
+        self.embedder.load(net)
+        if real_idx is None:
+            real_idx = self.ds.sample_all_classes(self.batch_real)
+        own = self.owned
+        n_own = len(own)
+        rows = torch.as_tensor([c * ipc + i for c in own for i in range(ipc)], dtype=torch.long, device=self.device)
+        emb_real = self.embedder(self.ds.videos, self.ds.local_index(real_idx[own]))
+        D = emb_real.shape[1]
+        mean_real = ops.class_mean(emb_real.view(n_own, self.batch_real, D))
+        img = self.image_syn[rows] if self.world > 1 else self.image_syn
+        emb_syn = net.embed(img).view(n_own, ipc, D)
+        loss = ops.dm_loss(mean_real, emb_syn)
+        self.image_syn.grad = None
+        loss.backward()
+        loss_d = loss.detach().reshape(1).clone()
+        allreduce_sum_([self.image_syn.grad, loss_d])
+        first = self._buf is None
+        if first:
+            self._buf = torch.empty_like(self.image_syn)
+        ops.sgd_momentum_(self.image_syn.data, self.image_syn.grad.contiguous(), self._buf, self.lr_img, 0.5, first)
+        self.last = dict(real_idx=real_idx, emb_syn=emb_syn.detach(), mean_real=mean_real)
+        return loss_d[0]
+
+
+class MTTS2DTrainer:
+    """MTT + static/dynamic memory (distill_s2d_ms.py:197-300): unrolled ReparamModule student with
+    second-order autograd through the conv trio; exact fp32 path."""
+
+    def __init__(self, *, num_classes, channel=3, im_size=(112, 112), frames=16, vpc=1, spc=2, dpc=2, syn_steps=10,
+                 lr_dynamic=1e4, lr_hal=1e-2, lr_static=1e-4, lr_lr=1e-5, lr_teacher=0.01, train_static=False,
+                 train_lr=True, batch_syn=None, static_syn=None, dynamic_syn=None, hal=None, device='cuda'):
+        self.C, self.channel, self.im_size, self.frames = num_classes, channel, tuple(im_size), frames
+        self.vpc, self.spc, self.dpc, self.syn_steps = vpc, spc, dpc, syn_steps
+        self.lr = dict(dynamic=lr_dynamic, hal=lr_hal, static=lr_static, lr=lr_lr)
+        self.train_static, self.train_lr = train_static, train_lr
+        self.batch_syn = batch_syn if batch_syn is not None else num_classes * vpc
+        self.device = torch.device(device)
+        H, W = self.im_size
+        if static_syn is None:
+            static_syn = torch.randn(size=(num_classes * spc, 3, H, W), dtype=torch.float)
+        if dynamic_syn is None:
+            dynamic_syn = torch.randn(size=(num_classes, dpc, frames, 1, H, W), dtype=torch.float)
+        self.hal = (hal if hal is not None else Conv3DNet()).to(self.device)
+        self.static_syn = static_syn.detach().to(self.device).contiguous().requires_grad_(train_static)
+        self.dynamic_syn = dynamic_syn.detach().to(self.device).contiguous().requires_grad_(True)
+        self.syn_lr = torch.tensor(lr_teacher).to(self.device).requires_grad_(train_lr)
+        self._bufs = {}
+        self.criterion = torch.nn.CrossEntropyLoss().to(self.device)
+        self.last = {}
+
+    def _sgd(self, name, p, lr, momentum):
+        first = name not in self._bufs
+        if first:
+            self._bufs[name] = torch.empty_like(p)
+        ops.sgd_momentum_(p.data, p.grad.contiguous(), self._bufs[name], lr, momentum, first)
+
+    def step(self, start_params, target_params, student_net=None, net_seed=None):
+        """start_params / target_params: lists of expert tensors (buffer.py layout) or flat tensors."""
+        C, vpc, spc, dev = self.C, self.vpc, self.spc, self.device
+        if student_net is None:
+            if net_seed is not None:
+                torch.random.manual_seed(int(net_seed))
+                base = ConvNet3D(self.channel, C, 128, 3, 'relu', 'none', 'maxpooling', self.frames, self.im_size).to(dev)
+            else:
+                base = get_network('ConvNet3D', self.channel, C, self.im_size, frames=self.frames, dist=False).to(dev)
+            student_net = ReparamModule(base)
+        student_net.train()
+        num_params = student_net.param_numel
+
+        def flat(ps):
+            if torch.is_tensor(ps):
+                return ps.to(dev).reshape(-1)
+            return torch.cat([p.data.to(dev).reshape(-1) for p in ps], 0)
+        target = flat(target_params)
+        starting = flat(start_params)
+        student_params = [starting.clone().requires_grad_(True)]
+        chunks, draws = [], []
+        for _ in range(self.syn_steps):                                     # distill_s2d_ms.py:238-266
+            if not chunks:
+                indices = torch.randperm(C * vpc, device=dev)
+                chunks = list(torch.split(indices, self.batch_syn))
+            these = chunks.pop()
+            label = these // vpc
+            idx = these % vpc
+            dynamic_idx = 2 * idx + torch.randint(2, (these.shape[0],), device=dev)
+            static_idx = spc * label + 2 * idx + torch.randint(2, (these.shape[0],), device=dev)
+            x = self.hal.compose(self.static_syn, self.dynamic_syn, static_idx, label, dynamic_idx)
+            out = student_net(x, flat_param=student_params[-1])
+            ce = self.criterion(out, label.long())
+            grad = torch.autograd.grad(ce, student_params[-1], create_graph=True)[0]
+            student_params.append(student_params[-1] - self.syn_lr * grad)
+            draws.append((these, dynamic_idx, static_idx))
+        param_loss = torch.nn.functional.mse_loss(student_params[-1], target, reduction='sum') / num_params
+        param_dist = torch.nn.functional.mse_loss(starting, target, reduction='sum') / num_params
+        grand_loss = param_loss / param_dist
+        for p in (self.dynamic_syn, self.static_syn, self.syn_lr, *self.hal.parameters()):
+            p.grad = None
+        grand_loss.backward()
+        if self.train_static:
+            self._sgd('static', self.static_syn, self.lr['static'], 0.95)
+        self._sgd('dynamic', self.dynamic_syn, self.lr['dynamic'], 0.95)
+        self._sgd('hal_w', self.hal.encoder.weight, self.lr['hal'], 0.95)
+        self._sgd('hal_b', self.hal.encoder.bias, self.lr['hal'], 0.95)
+        if self.train_lr:
+            g = self.syn_lr.grad.reshape(1).contiguous()
+            p = self.syn_lr.data.reshape(1)
+            first = 'lr' not in self._bufs
+            if first:
+                self._bufs['lr'] = torch.empty_like(p)
+            # a 1-element tensor is below the kernel's 16-byte alignment contract: plain torch here
+            buf = self._bufs['lr']
+            buf.copy_(g) if first else buf.mul_(0.9).add_(g)
+            p.sub_(self.lr['lr'] * buf)
+            self.syn_lr.data = self.syn_lr.data.clip(min=0.001)
+        self.last = dict(draws=draws, param_loss=param_loss.detach(), param_dist=param_dist.detach())
+        return grand_loss.detach()

@@ -1,0 +1,356 @@
+"""Python face of the C ABI: raw kernel wrappers and the autograd Functions built on them.
+
+The conv trio (fprop / dgrad / wgrad) is closed under differentiation, and
+ReLU+MaxPool routing is linear once its argmax code is fixed, so every Function here has a
+backward expressed with the same kernels and is differentiable to any order — this is what the
+MTT unroll (torch.autograd.grad(create_graph=True), distill_s2d_ms.py:264) needs in place of
+ATen's _convolution_double_backward.  There is no CPU / ATen fallback: tensors must be CUDA.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import ConvGeom, check, lib, ptr, stream
+
+
+def _triple(v):
+    return (v, v, v) if isinstance(v, int) else tuple(v)
+
+
+def conv_geom(x_shape, w_shape, stride, padding):
+    N, Cin, T, H, W = x_shape
+    Cout, Cin2, kt, kh, kw = w_shape
+    assert Cin == Cin2, f'channel mismatch {Cin} vs {Cin2}'
+    st, sh, sw = _triple(stride)
+    pt, ph, pw = _triple(padding)
+    To, Ho, Wo = (T + 2 * pt - kt) // st + 1, (H + 2 * ph - kh) // sh + 1, (W + 2 * pw - kw) // sw + 1
+    return ConvGeom(N, Cin, T, H, W, Cout, To, Ho, Wo, kt, kh, kw, st, sh, sw, pt, ph, pw)
+
+
+def _f32c(t):
+    if t.dtype != torch.float32:
+        raise RuntimeError(f'video_distillation_b200: expected float32, got {t.dtype}')
+    return t.contiguous()
+
+
+# ------------------------------------------------------------------ raw kernels
+def conv3d_fprop_raw(x, w, bias, stride, padding):
+    x, w = _f32c(x), _f32c(w)
+    g = conv_geom(x.shape, w.shape, stride, padding)
+    y = torch.empty(g.N, g.Cout, g.To, g.Ho, g.Wo, dtype=torch.float32, device=x.device)
+    if y.numel():
+        b = _f32c(bias) if bias is not None else None
+        check(lib().vd_conv3d_fprop_f32(ptr(x), ptr(w), ptr(b), ptr(y), ctypes.byref(g), stream()), 'conv3d_fprop')
+    return y
+
+
+def conv3d_dgrad_raw(gy, w, x_shape, stride, padding):
+    gy, w = _f32c(gy), _f32c(w)
+    g = conv_geom(x_shape, w.shape, stride, padding)
+    assert tuple(gy.shape) == (g.N, g.Cout, g.To, g.Ho, g.Wo), (tuple(gy.shape), (g.N, g.Cout, g.To, g.Ho, g.Wo))
+    gx = torch.empty(tuple(x_shape), dtype=torch.float32, device=gy.device)
+    if gx.numel():
+        check(lib().vd_conv3d_dgrad_f32(ptr(gy), ptr(w), ptr(gx), ctypes.byref(g), stream()), 'conv3d_dgrad')
+    return gx
+
+
+def conv3d_wgrad_raw(x, gy, w_shape, stride, padding, want_bias=False):
+    x, gy = _f32c(x), _f32c(gy)
+    g = conv_geom(x.shape, w_shape, stride, padding)
+    gw = torch.zeros(tuple(w_shape), dtype=torch.float32, device=x.device)
+    gb = torch.zeros(g.Cout, dtype=torch.float32, device=x.device) if want_bias else None
+    if x.numel() and gy.numel():
+        check(lib().vd_conv3d_wgrad_f32(ptr(x), ptr(gy), ptr(gw), ptr(gb), ctypes.byref(g), stream()), 'conv3d_wgrad')
+    return (gw, gb) if want_bias else gw
+
+
+# ------------------------------------------------------------------ conv trio as autograd Functions
+class _Fprop(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, stride, padding):
+        ctx.save_for_backward(x, w)
+        ctx.sp = (stride, padding)
+        return conv3d_fprop_raw(x, w, None, stride, padding)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        stride, padding = ctx.sp
+        gx = _Dgrad.apply(gy, w, tuple(x.shape), stride, padding) if ctx.needs_input_grad[0] else None
+        gw = _Wgrad.apply(x, gy, tuple(w.shape), stride, padding) if ctx.needs_input_grad[1] else None
+        return gx, gw, None, None
+
+
+class _Dgrad(torch.autograd.Function):
+    """gx = dgrad(gy, w); linear in both: d/dgy = fprop(c, w), d/dw = wgrad(c, gy)."""
+    @staticmethod
+    def forward(ctx, gy, w, x_shape, stride, padding):
+        ctx.save_for_backward(gy, w)
+        ctx.sp = (x_shape, stride, padding)
+        return conv3d_dgrad_raw(gy, w, x_shape, stride, padding)
+
+    @staticmethod
+    def backward(ctx, c):
+        gy, w = ctx.saved_tensors
+        x_shape, stride, padding = ctx.sp
+        ggy = _Fprop.apply(c, w, stride, padding) if ctx.needs_input_grad[0] else None
+        gw = _Wgrad.apply(c, gy, tuple(w.shape), stride, padding) if ctx.needs_input_grad[1] else None
+        return ggy, gw, None, None, None
+
+
+class _Wgrad(torch.autograd.Function):
+    """gw = wgrad(x, gy); d/dx = dgrad(gy, c), d/dgy = fprop(x, c)."""
+    @staticmethod
+    def forward(ctx, x, gy, w_shape, stride, padding):
+        ctx.save_for_backward(x, gy)
+        ctx.sp = (w_shape, stride, padding)
+        return conv3d_wgrad_raw(x, gy, w_shape, stride, padding)
+
+    @staticmethod
+    def backward(ctx, c):
+        x, gy = ctx.saved_tensors
+        w_shape, stride, padding = ctx.sp
+        gx = _Dgrad.apply(gy, c, tuple(x.shape), stride, padding) if ctx.needs_input_grad[0] else None
+        ggy = _Fprop.apply(x, c, stride, padding) if ctx.needs_input_grad[1] else None
+        return gx, ggy, None, None, None
+
+
+def conv3d(x, w, bias=None, stride=1, padding=0):
+    """F.conv3d replacement (fp32, CUDA cores), differentiable to any order."""
+    y = _Fprop.apply(x, w, _triple(stride), _triple(padding))
+    if bias is not None:
+        y = y + bias.view(1, -1, 1, 1, 1)
+    return y
+
+
+# ------------------------------------------------------------------ ReLU + MaxPool routing
+def _pool_out(shape, k):
+    N, C, T, H, W = shape
+    return (N, C, T // k[0], H // k[1], W // k[2])
+
+
+class _RouteGather(torch.autograd.Function):
+    """y[o] = active(o) ? x[src(o)] : 0 for a fixed routing code (linear in x)."""
+    @staticmethod
+    def forward(ctx, x, code, k):
+        ctx.save_for_backward(code)
+        ctx.meta = (tuple(x.shape), k)
+        x = _f32c(x)
+        N, C, T, H, W = x.shape
+        y = torch.empty(_pool_out(x.shape, k), dtype=torch.float32, device=x.device)
+        if y.numel():
+            check(lib().vd_route_gather_f32(ptr(x), ptr(code), ptr(y), N * C, T, H, W, k[0], k[1], k[2], stream()), 'route_gather')
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (code,) = ctx.saved_tensors
+        shape, k = ctx.meta
+        return _RouteScatter.apply(gy, code, shape, k), None, None
+
+
+class _RouteScatter(torch.autograd.Function):
+    """gx[src(o)] = active(o) ? gy[o] : 0 (transpose of the gather)."""
+    @staticmethod
+    def forward(ctx, gy, code, x_shape, k):
+        ctx.save_for_backward(code)
+        ctx.meta = (x_shape, k)
+        gy = _f32c(gy)
+        N, C, T, H, W = x_shape
+        gx = torch.empty(x_shape, dtype=torch.float32, device=gy.device)
+        if gx.numel():
+            check(lib().vd_route_scatter_f32(ptr(gy), ptr(code), ptr(gx), N * C, T, H, W, k[0], k[1], k[2], stream()), 'route_scatter')
+        return gx
+
+    @staticmethod
+    def backward(ctx, c):
+        (code,) = ctx.saved_tensors
+        _, k = ctx.meta
+        return _RouteGather.apply(c, code, k), None, None, None
+
+
+class _ReluMaxPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, k):
+        x = _f32c(x)
+        N, C, T, H, W = x.shape
+        y = torch.empty(_pool_out(x.shape, k), dtype=torch.float32, device=x.device)
+        code = torch.empty(y.shape, dtype=torch.uint8, device=x.device)
+        if y.numel():
+            check(lib().vd_relu_maxpool_fwd_f32(ptr(x), ptr(y), ptr(code), N * C, T, H, W, k[0], k[1], k[2], stream()), 'relu_maxpool_fwd')
+        ctx.save_for_backward(code)
+        ctx.meta = (tuple(x.shape), k)
+        ctx.mark_non_differentiable(code)
+        return y, code
+
+    @staticmethod
+    def backward(ctx, gy, _gcode):
+        (code,) = ctx.saved_tensors
+        shape, k = ctx.meta
+        return _RouteScatter.apply(gy, code, shape, k), None
+
+
+def relu_maxpool3d(x, kernel, return_code=False):
+    """MaxPool3d(kernel, stride=kernel)(ReLU(x)) fused (networks.py:757,766-770)."""
+    y, code = _ReluMaxPool.apply(x, _triple(kernel))
+    return (y, code) if return_code else y
+
+
+def route_with_code(x, code, kernel):
+    """Apply a GIVEN routing (ReLU mask + pool argmax) to x — used for routing-conditioned parity."""
+    return _RouteGather.apply(x, code, _triple(kernel))
+
+
+# ------------------------------------------------------------------ instancenorm / avgpool variant
+class _InormRelu(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta):
+        x = _f32c(x)
+        N, C = x.shape[0], x.shape[1]
+        S = x.numel() // (N * C)
+        y = torch.empty_like(x)
+        mean = torch.empty(N * C, dtype=torch.float32, device=x.device)
+        rstd = torch.empty_like(mean)
+        check(lib().vd_inorm_relu_fwd_f32(ptr(x), ptr(_f32c(gamma)), ptr(_f32c(beta)), ptr(y), ptr(mean), ptr(rstd), N, C, S, stream()), 'inorm_relu_fwd')
+        ctx.save_for_backward(x, y, gamma, mean, rstd)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        x, y, gamma, mean, rstd = ctx.saved_tensors
+        N, C = x.shape[0], x.shape[1]
+        S = x.numel() // (N * C)
+        gx = torch.empty_like(x)
+        gg = torch.zeros(C, dtype=torch.float32, device=x.device)
+        gb = torch.zeros(C, dtype=torch.float32, device=x.device)
+        check(lib().vd_inorm_relu_bwd_f32(ptr(x), ptr(y), ptr(_f32c(gy)), ptr(_f32c(gamma)), ptr(mean), ptr(rstd),
+                                          ptr(gx), ptr(gg), ptr(gb), N, C, S, stream()), 'inorm_relu_bwd')
+        return gx, gg, gb
+
+
+def instancenorm_relu(x, gamma, beta):
+    """ReLU(GroupNorm(C, C, affine)(x)) fused (networks.py:784,757), first-order differentiable."""
+    return _InormRelu.apply(x, gamma, beta)
+
+
+class _AvgPool2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _f32c(x)
+        N, C, T, H, W = x.shape
+        ctx.shape = tuple(x.shape)
+        y = torch.empty(N, C, T // 2, H // 2, W // 2, dtype=torch.float32, device=x.device)
+        if y.numel():
+            check(lib().vd_avgpool2_fwd_f32(ptr(x), ptr(y), N * C, T, H, W, stream()), 'avgpool2_fwd')
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        return _AvgPool2Bwd.apply(gy, ctx.shape)
+
+
+class _AvgPool2Bwd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, gy, shape):
+        gy = _f32c(gy)
+        N, C, T, H, W = shape
+        gx = torch.empty(shape, dtype=torch.float32, device=gy.device)
+        if gx.numel():
+            check(lib().vd_avgpool2_bwd_f32(ptr(gy), ptr(gx), N * C, T, H, W, stream()), 'avgpool2_bwd')
+        return gx
+
+    @staticmethod
+    def backward(ctx, c):
+        return _AvgPool2.apply(c), None
+
+
+def avgpool3d_2(x):
+    """AvgPool3d(kernel_size=2, stride=2) (networks.py:772)."""
+    return _AvgPool2.apply(x)
+
+
+# ------------------------------------------------------------------ composer
+class _Compose(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, static_syn, dynamic_syn, weight, bias, static_idx, label, dynamic_idx):
+        static_syn, dynamic_syn, weight, bias = map(_f32c, (static_syn, dynamic_syn, weight, bias))
+        C, dpc, T, one, H, W = dynamic_syn.shape
+        assert one == 1 and tuple(weight.shape) == (3, 4, 3, 3, 3) and static_syn.shape[1:] == (3, H, W)
+        B = int(label.numel())
+        idx = [t.to(torch.int64).contiguous() for t in (static_idx, label, dynamic_idx)]
+        out = torch.empty(B, T, 3, H, W, dtype=torch.float32, device=dynamic_syn.device)
+        check(lib().vd_compose_fwd_f32(ptr(static_syn), ptr(dynamic_syn), ptr(idx[0]), ptr(idx[1]), ptr(idx[2]),
+                                       ptr(weight), ptr(bias), ptr(out), B, T, H, W, dpc, stream()), 'compose_fwd')
+        ctx.save_for_backward(static_syn, dynamic_syn, weight, *idx)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gout):
+        static_syn, dynamic_syn, weight, sidx, label, didx = ctx.saved_tensors
+        C, dpc, T, _, H, W = dynamic_syn.shape
+        B = int(label.numel())
+        gout = _f32c(gout)
+        need_s, need_d, need_w, need_b = ctx.needs_input_grad[:4]
+        gd = torch.zeros_like(dynamic_syn)
+        gw = torch.zeros_like(weight) if (need_w or need_b) else None
+        gb = torch.zeros(3, dtype=torch.float32, device=gout.device) if (need_w or need_b) else None
+        gs = torch.zeros_like(static_syn) if need_s else None
+        check(lib().vd_compose_bwd_f32(ptr(gout), ptr(static_syn), ptr(dynamic_syn), ptr(sidx), ptr(label), ptr(didx),
+                                       ptr(weight), ptr(gd), ptr(gw), ptr(gb), ptr(gs), B, T, H, W, dpc, stream()), 'compose_bwd')
+        return gs, (gd if need_d else None), (gw if need_w else None), (gb if need_b else None), None, None, None
+
+
+def compose(static_syn, dynamic_syn, weight, bias, static_idx, label, dynamic_idx):
+    """hal(static_syn[static_idx], dynamic_syn[label, dynamic_idx]) in one kernel
+    (distill_s2d_ms.py:409-412; utils.py:1186-1197, mode='concat')."""
+    return _Compose.apply(static_syn, dynamic_syn, weight, bias, static_idx, label, dynamic_idx)
+
+
+# ------------------------------------------------------------------ DM loss / optimiser kernels
+def class_mean(emb):
+    """(C, n, D) -> (C, D) mean over n (distill_baseline.py:351 torch.mean(output_real, dim=0))."""
+    emb = _f32c(emb)
+    C, n, D = emb.shape
+    out = torch.empty(C, D, dtype=torch.float32, device=emb.device)
+    check(lib().vd_class_mean_f32(ptr(emb), ptr(out), C, n, D, stream()), 'class_mean')
+    return out
+
+
+class _DMLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mean_real, emb_syn):
+        mean_real, emb_syn = _f32c(mean_real), _f32c(emb_syn)
+        C, ns, D = emb_syn.shape
+        loss = torch.zeros((), dtype=torch.float32, device=emb_syn.device)
+        grad = torch.empty_like(emb_syn)
+        check(lib().vd_dm_loss_f32(ptr(mean_real), ptr(emb_syn), ptr(loss), ptr(grad), C, ns, D, 1.0, stream()), 'dm_loss')
+        ctx.save_for_backward(grad)
+        return loss
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return None, grad * g
+
+
+def dm_loss(mean_real, emb_syn):
+    """sum_c || mean_real[c] - mean(emb_syn[c], 0) ||^2 with the gradient wrt emb_syn fused into the
+    same launch (distill_baseline.py:351 summed over classes).  mean_real (C,D), emb_syn (C,ns,D)."""
+    return _DMLoss.apply(mean_real, emb_syn)
+
+
+def sgd_momentum_(p, grad, buf, lr, momentum, first_step):
+    """In-place dense torch.optim.SGD(momentum) step on raw tensors (no autograd)."""
+    assert p.is_contiguous() and grad.is_contiguous() and buf.is_contiguous()
+    check(lib().vd_sgd_momentum_f32(ptr(p), ptr(grad), ptr(buf), p.numel(), float(lr), float(momentum), int(bool(first_step)), stream()), 'sgd_momentum')
+
+
+def sqdist(a, b):
+    a, b = _f32c(a), _f32c(b)
+    out = torch.zeros((), dtype=torch.float32, device=a.device)
+    check(lib().vd_sqdist_f32(ptr(a), ptr(b), ptr(out), a.numel(), stream()), 'sqdist')
+    return out

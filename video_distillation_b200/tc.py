@@ -1,0 +1,111 @@
+"""Host driver of the tensor-core (tcgen05) ConvNet3D feature pipeline.
+
+``TcConvNet3D`` owns the packed operands of one frozen ConvNet3D (weights as UMMA images, the
+per-layer activation buffers) and runs conv0 -> conv1 -> conv2 with their fused
+bias+ReLU+MaxPool epilogues, i.e. ``ConvNet3D.embed`` of the reference
+(networks.py:747-751 with get_network's none/maxpooling setting, utils.py:608-609) in bf16
+operands / fp32 accumulation.  Every launch goes through the C ABI (include/vd_b200.h).
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+
+def make_plan(T, H, W):
+    plan = _lib.TcPlan()
+    _lib.check(_lib.lib().vd_tc_plan_make(ctypes.byref(plan), int(T), int(H), int(W)), 'vd_tc_plan_make')
+    return plan
+
+
+def tc_supported(T, H, W):
+    return H == W and H in (112, 64) and T % 4 == 0 and 4 <= T <= (16 if H == 112 else 32) and not (H == 64 and T < 8)
+
+
+class TcConvNet3D:
+    """bf16 tensor-core embed of a ConvNet3D whose feature weights are given as fp32 tensors."""
+
+    def __init__(self, T, H, W, device, max_batch=128):
+        self.plan = make_plan(T, H, W)
+        self.T, self.H, self.W = T, H, W
+        self.device = torch.device(device)
+        self.max_batch = int(max_batch)
+        p = self.plan
+        u8 = dict(dtype=torch.uint8, device=self.device)
+        self.w0 = torch.empty(p.w0_bytes, **u8)
+        self.w1 = torch.empty(p.w1_bytes, **u8)
+        self.w2 = torch.empty(p.w2_bytes, **u8)
+        self.b0 = self.b1 = self.b2 = None
+        self._x0 = None
+        self._a1 = None
+        self._a2 = None
+        self.embed_dim = int(p.embed_dim)
+
+    # ---------------------------------------------------------------- operands
+    def load_weights(self, w0, b0, w1, b1, w2, b2):
+        """fp32 OIDHW weights/biases of features.{0,3,6} -> UMMA images (3 small pack launches)."""
+        ws = [t.detach().contiguous().float() for t in (w0, w1, w2)]
+        _lib.check(_lib.lib().vd_tc_pack_weights(_lib.ptr(ws[0]), _lib.ptr(ws[1]), _lib.ptr(ws[2]),
+                                                 _lib.ptr(self.w0), _lib.ptr(self.w1), _lib.ptr(self.w2),
+                                                 _lib.stream()), 'vd_tc_pack_weights')
+        self.b0, self.b1, self.b2 = (t.detach().contiguous().float() for t in (b0, b1, b2))
+        return self
+
+    def _buffers(self, n):
+        p = self.plan
+        n4 = (n + 3) // 4 * 4
+        if self._a1 is None or self._a1.numel() < n * p.a1_bytes_per_video:
+            self._a1 = torch.zeros(n * p.a1_bytes_per_video, dtype=torch.uint8, device=self.device)
+            self._a2 = torch.zeros(n4 * p.a2_bytes_per_video, dtype=torch.uint8, device=self.device)
+        return self._a1, self._a2
+
+    def pack_video(self, video, index=None, out=None):
+        """fp32 (Bsrc,T,3,H,W) -> X0 for B = len(index) (or Bsrc) items."""
+        assert video.dtype == torch.float32 and video.dim() == 5 and tuple(video.shape[1:]) == (self.T, 3, self.H, self.W)
+        B = int(index.numel()) if index is not None else int(video.shape[0])
+        nbytes = B * self.plan.x0_bytes_per_video
+        if out is None:
+            if self._x0 is None or self._x0.numel() < nbytes:
+                self._x0 = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            out = self._x0
+        _lib.check(_lib.lib().vd_tc_pack_video(_lib.ptr(video), _lib.ptr(index), _lib.ptr(out),
+                                               ctypes.byref(self.plan), B, _lib.stream()), 'vd_tc_pack_video')
+        return out
+
+    # ---------------------------------------------------------------- layers
+    def conv_layer(self, layer, src, wimg, bias, out, B, code=None, item_index=None, raw=False):
+        _lib.check(_lib.lib().vd_tc_conv_layer(layer, _lib.ptr(src), _lib.ptr(wimg), _lib.ptr(bias), _lib.ptr(out),
+                                               _lib.ptr(code), ctypes.byref(self.plan), _lib.ptr(item_index),
+                                               int(B), int(bool(raw)), _lib.stream()), f'vd_tc_conv_layer({layer})')
+
+    def embed_packed(self, x0, B, item_index=None, out=None, codes=None):
+        """conv0..2 on an already packed X0 (optionally a resident set addressed by item_index)."""
+        a1, a2 = self._buffers(B)
+        if out is None:
+            out = torch.empty(B, self.embed_dim, dtype=torch.float32, device=self.device)
+        c0, c1, c2 = codes if codes is not None else (None, None, None)
+        self.conv_layer(0, x0, self.w0, self.b0, a1, B, code=c0, item_index=item_index)
+        self.conv_layer(1, a1, self.w1, self.b1, a2, B, code=c1)
+        self.conv_layer(2, a2, self.w2, self.b2, out, B, code=c2)
+        return out
+
+    def alloc_codes(self, B):
+        p = self.plan
+        u8 = dict(dtype=torch.uint8, device=self.device)
+        return (torch.empty(B, 64, p.T1p, p.H1p, p.W1p, **u8), torch.empty(B, 128, p.T2p, p.H2p, p.W2p, **u8),
+                torch.empty(B, 128, p.T3p, p.H3p, p.W3p, **u8))
+
+    def embed(self, video, index=None, want_codes=False):
+        """ConvNet3D.embed on fp32 videos (B,T,3,H,W) -> (B, embed_dim) fp32, in chunks of max_batch."""
+        B = int(index.numel()) if index is not None else int(video.shape[0])
+        out = torch.empty(B, self.embed_dim, dtype=torch.float32, device=self.device)
+        codes = self.alloc_codes(B) if want_codes else None
+        for s in range(0, B, self.max_batch):
+            e = min(B, s + self.max_batch)
+            idx = index[s:e] if index is not None else None
+            vid = video if index is not None else video[s:e]
+            x0 = self.pack_video(vid, idx)
+            cc = tuple(c[s:e] for c in codes) if codes is not None else None
+            self.embed_packed(x0, e - s, out=out[s:e], codes=cc)
+        return (out, codes) if want_codes else out
