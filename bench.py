@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""bench.py — DM + S2D distillation iterations/sec on synthetic miniUCF101-shaped data.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1], flags of sh/s2d/s2d_DM_ms.sh): distill_s2d_ms.py --method DM,
+50 classes, videos 16x3x112x112, vpc=1 spc=2 dpc=2, batch_real=64, --no_train_static.  One "step" =
+one full DM iteration: fresh random frozen ConvNet3D, composer, 50x64 real + 50 synthetic video
+embeddings, DM loss, backward to dynamic memory + hallucinator, momentum-SGD updates.
+
+* value : iterations/s with the real set resident in HBM (device-timed, max over ranks).
+* e2e   : same iteration driven from HOST memory: every step copies its 3200 sampled real videos
+          (fp32, 7.7 GB) from pinned host memory and reads the loss back (what the reference's
+          get_images(...).to(device) + loss.item() does, distill_s2d_ms.py:87,440).
+* e2e_resident : the product's intended mode — dataset uploaded once, per-step H2D = sampled indices.
+* roofline : conv-1 tcgen05 kernel (69 % of the FLOPs), CUDA events around its launches.
+* cpu_baseline : the CPU oracle (port of the reference loop, torch CPU) on a bounded sample.
+With --impl reference the CPU oracle alone is timed (rank 0 only) on the same metric.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+C, T, HW, VPC, SPC, DPC, BATCH_REAL, PER_CLASS = 50, 16, 112, 1, 2, 2, 64, 72
+F_L0, F_L1, F_L2 = 2.832e9, 7.553e9, 0.617e9          # algorithmic FLOP per video
+F_EMBED = F_L0 + F_L1 + F_L2
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, 'measured'
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0}, 'fallback'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.idx}', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace('.', '').isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 9 and r[5 + i].lower().startswith('active') for r in self.rows)]
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'power_w_max': max([float(r[3]) for r in self.rows if len(r) >= 9 and r[3].replace('.', '').isdigit()] or [0.0]),
+                'samples': len(sm), 'reasons': reasons}
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def cpu_oracle_rate(n_classes, n_real, threads):
+    """DM+S2D iteration of the CPU oracle on a bounded sample: n_classes classes x (n_real real + 1 syn)
+    videos of the full 16x3x112x112 shape; returns (it/s extrapolated to 50 x (64+1), seconds, description)."""
+    import oracle
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(0)
+    per = n_real + 2
+    videos = torch.randn(n_classes * per, T, 3, HW, HW, generator=g)
+    indices_class = [list(range(c * per, (c + 1) * per)) for c in range(n_classes)]
+    static_syn = torch.randn(n_classes * SPC, 3, HW, HW, generator=g)
+    dyn = torch.randn(n_classes, DPC, T, 1, HW, HW, generator=g)
+    hal = oracle.init_hallucinator(1)
+    params = oracle.init_convnet3d(2, 3, C)
+    cd = torch.randint(2, (n_classes * VPC,), generator=g)
+    cs = torch.randint(2, (n_classes * VPC,), generator=g)
+    np.random.seed(0)
+    t0 = time.perf_counter()
+    r = oracle.dm_s2d_iteration(params, static_syn, dyn, hal, videos, indices_class, vpc=VPC, spc=SPC,
+                                batch_real=n_real, coin_dynamic=cd, coin_static=cs)
+    dt = time.perf_counter() - t0
+    # cost model: a synthetic video is forward + dgrad ~ 2 forward-equivalents
+    sample_units = n_classes * (n_real + 2 * VPC)
+    full_units = C * (BATCH_REAL + 2 * VPC)
+    its = 1.0 / (dt * full_units / sample_units)
+    desc = (f'{n_classes} classes x ({n_real} real + {VPC} syn) videos 16x3x112x112, one oracle DM+S2D iteration '
+            f'(fwd + backward to dynamic memory) = {sample_units}/{full_units} of a full iteration, linearly extrapolated')
+    assert torch.isfinite(r['loss'])
+    return its, dt, desc
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    vals, secs = [], []
+    desc = ''
+    for i in range(args.warmup + args.steps):
+        its, dt, desc = cpu_oracle_rate(2, 16, threads)
+        if i >= args.warmup:
+            vals.append(its)
+            secs.append(dt)
+    v = float(np.mean(vals))
+    print(json.dumps({
+        'impl': 'reference', 'metric': 'DM+S2D distill iters/sec', 'value': v, 'unit': 'it/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1000.0 / v, 'higher_is_better': True,
+        'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'DM+S2D miniUCF101-shape (50 cls, 16x3x112x112) ipc=1 batch_real=64, CPU oracle (torch CPU port of distill_s2d_ms.py:393-438)'},
+        'cpu_baseline': {'value': v, 'unit': 'it/s', 'cores': threads, 'kind': 'port', 'sample': desc,
+                         'sample_seconds': float(np.mean(secs))},
+        'e2e': {'value': v, 'unit': 'it/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    from video_distillation_b200 import _lib
+    from video_distillation_b200.distill import DeviceDataset, DMS2DTrainer, owned_classes
+
+    # ---- synthetic real set: per-class generators so the data does not depend on the world size
+    own = owned_classes(C, rank, world)
+    labels = [c for c in range(C) for _ in range(PER_CLASS)]
+    vids = torch.empty(len(own) * PER_CLASS, T, 3, HW, HW, device=dev)
+    for j, c in enumerate(own):
+        g = torch.Generator(device=dev).manual_seed(1000 + c)
+        vids[j * PER_CLASS:(j + 1) * PER_CLASS].normal_(generator=g)
+    ds = DeviceDataset.from_device_shard(vids, labels, C, dev, rank, world)
+    torch.manual_seed(0)
+    tr = DMS2DTrainer(ds, num_classes=C, im_size=(HW, HW), frames=T, vpc=VPC, spc=SPC, dpc=DPC, batch_real=BATCH_REAL,
+                      lr_dynamic=1e4, lr_hal=1e-2, precision=args.precision, device=dev, init_on_device=True,
+                      max_batch=args.max_batch)
+    np.random.seed(0)
+    torch.cuda.manual_seed(1234)
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        sync()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    seed_box = [0]
+
+    def step_resident():
+        seed_box[0] += 1
+        return tr.step(net_seed=seed_box[0])          # same seed on every rank -> same frozen net
+
+    # ---- warm-up, then the timed region (device-resident inputs)
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    tc = tr.embedder.tc
+    if tc is not None:
+        tc.timing = []
+    _lib.launch_count_reset()
+    ms = timed(step_resident, args.steps)
+    launches = _lib.launch_count()
+    clocks = sampler.stop() if rank == 0 else None
+    layer_ms = {0: 0.0, 1: 0.0, 2: 0.0}
+    layer_videos = {0: 0, 1: 0, 2: 0}
+    layer_launches = {0: 0, 1: 0, 2: 0}
+    if tc is not None:
+        for layer, B, a, b in tc.timing:
+            layer_ms[layer] += a.elapsed_time(b)
+            layer_videos[layer] += B
+            layer_launches[layer] += 1
+        tc.timing = None
+    value = args.steps / (ms / 1000.0)
+
+    # ---- e2e (a): the step's real videos come from pinned host memory, loss is read back
+    n_own_real = len(own) * BATCH_REAL
+    e2e_steps = max(1, min(args.steps, 3))
+    host = torch.empty(vids.shape, dtype=torch.float32, pin_memory=True)
+    host.copy_(vids)
+    stage = torch.empty(n_own_real, T, 3, HW, HW, device=dev)
+    bytes_video = T * 3 * HW * HW * 4
+
+    def step_streaming():
+        seed_box[0] += 1
+        real_idx = ds.sample_all_classes(BATCH_REAL)
+        loc = ds.local_of_global[real_idx[own].reshape(-1)]
+        for j, src in enumerate(loc):
+            stage[j].copy_(host[int(src)], non_blocking=True)
+        loss = tr.step(net_seed=seed_box[0], real_idx=real_idx, real_batch=stage)
+        return loss.item()                                # D2H read of the step's result
+
+    step_streaming()
+    ms_stream = timed(step_streaming, e2e_steps)
+    e2e_stream = e2e_steps / (ms_stream / 1000.0)
+    del host, stage
+
+    # ---- e2e (b): resident dataset, per-step host input = the sampled index table
+    def step_resident_e2e():
+        return step_resident().item()
+    ms_res = timed(step_resident_e2e, e2e_steps)
+    e2e_res = e2e_steps / (ms_res / 1000.0)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks, peak_kind = measured_peaks()
+    l1_avg_ms = layer_ms[1] / max(1, layer_launches[1])
+    l1_flops_per_launch = F_L1 * layer_videos[1] / max(1, layer_launches[1])
+    achieved = l1_flops_per_launch / (l1_avg_ms * 1e-3) / 1e12 if l1_avg_ms > 0 else 0.0
+    peak = float(peaks.get('bf16_tflops_sustained', peaks.get('bf16_tflops', 1400.0)))
+    roofline = {'bound': 'tensor', 'kernel': 'ws_gemm_kernel<EPI_L1> (conv 1, 64->128)', 'achieved': achieved, 'peak': peak,
+                'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': None, 'peak_kind': f'bf16_tflops_sustained of {peak_kind}',
+                'avg_launch_ms': l1_avg_ms, 'flops_per_launch': l1_flops_per_launch,
+                'per_layer_ms_per_step': {f'conv{k}': layer_ms[k] / args.steps for k in layer_ms},
+                'per_layer_tflops': {f'conv{k}': (f * layer_videos[k] / (layer_ms[k] * 1e-3) / 1e12 if layer_ms[k] > 0 else 0.0)
+                                     for k, f in ((0, F_L0), (1, F_L1), (2, F_L2))}}
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        its, dt, desc = cpu_oracle_rate(4, 16, threads)
+        cpu = {'value': its, 'unit': 'it/s', 'cores': threads, 'kind': 'port', 'sample': desc, 'sample_seconds': dt}
+    out = {
+        'metric': 'DM+S2D distill iters/sec', 'value': value, 'unit': 'it/s', 'n_gpus': world, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'strong',
+        'vs_baseline': None, 'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
+        'config': {'workload': 'DM+S2D miniUCF101-shape: 50 classes, videos 16x3x112x112, vpc=1 spc=2 dpc=2, batch_real=64 '
+                               '(BASELINE.json configs[1]); fresh frozen ConvNet3D per step',
+                   'parallelism': f'classes sharded c%{world}, one NCCL all-reduce/step' if world > 1 else 'single GPU',
+                   'real_videos_per_step': C * BATCH_REAL, 'syn_videos_per_step': C * VPC,
+                   'l2_policy': 'inputs larger than L2: each step reads 3200 distinct real videos (7.7 GB fp32)',
+                   'real_embed': 'tcgen05 bf16 operands / fp32 accumulate' if args.precision == 'bf16' else 'fp32 CUDA cores',
+                   'videos_per_sec': value * C * (BATCH_REAL + VPC)},
+        'clocks': clocks, 'gpu_launches': int(launches),
+        'e2e': {'value': e2e_stream, 'unit': 'it/s', 'h2d_bytes_per_step': int(C * BATCH_REAL * bytes_video),
+                'd2h_bytes_per_step': 4, 'steps': e2e_steps,
+                'note': 'per step: 3200 sampled real videos copied from pinned host memory + loss.item()'},
+        'e2e_resident': {'value': e2e_res, 'unit': 'it/s', 'h2d_bytes_per_step': int(C * BATCH_REAL * 8),
+                         'd2h_bytes_per_step': 4, 'steps': e2e_steps,
+                         'note': 'real set uploaded once; per step the host sends the sampled index table and reads the loss'},
+        'roofline': roofline, 'cpu_baseline': cpu}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
+    ap.add_argument('--max-batch', type=int, default=128)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -154,7 +154,11 @@ typedef struct {
     int64_t a2_bytes_per_video;    /* packed L2 input  (bf16, tap-expanded)                  */
     int64_t w0_bytes, w1_bytes, w2_bytes;   /* UMMA weight images                            */
     int64_t tab_bytes;             /* unused (step tables travel as kernel parameters)       */
-    int32_t reserved[16];
+    /* backward (column-GEMM dgrad) operands, see vd_tc_bwd_* below */
+    int64_t wt0_bytes, wt1_bytes, wt2_bytes;                 /* transposed weight images           */
+    int64_t dy0_bytes_per_video, dy1_bytes_per_video, dy2_bytes_per_video;    /* packed output grads (bf16) */
+    int64_t col0_bytes_per_video, col1_bytes_per_video, col2_bytes_per_video; /* fp32 column buffers        */
+    int32_t reserved[8];
 } vd_tc_plan;
 
 int vd_tc_plan_make(vd_tc_plan* plan, int T, int H, int W);
@@ -183,9 +187,38 @@ int vd_tc_conv_layer(int layer, const void* in, const void* wimg, const float* b
                      void* out, uint8_t* code, const vd_tc_plan* plan, const int64_t* item_index,
                      int B, int raw, void* stream);
 
+/* ---- backward of the tensor-core embed (gradient to the input video; weights are frozen in DM).
+ * dgrad of each conv is a plain GEMM on tensor cores, col[(ci,tap), pixel] = sum_co W[co,ci,tap] *
+ * dY[co,pixel] (same ws_gemm kernel: transposed weights = M operand, packed dY = N operand), followed
+ * by a memory-bound col2im gather that also applies the ReLU/MaxPool routing code of the layer below
+ * and re-packs the result as the dY operand of the next GEMM.  Replaces convolution_backward /
+ * max_pool3d_with_indices_backward / threshold_backward on the synthetic branch
+ * (distill_s2d_ms.py:431).
+ *   pack_weights_bwd : fp32 OIDHW -> transposed UMMA images [m-tile][step][k 2][128][8]
+ *   bwd_emb    : g_emb (B, embed_dim) fp32 + code2 -> dy2
+ *   bwd_gemm   : layer in {2,1,0}: dy_layer x wt_layer -> col_layer (fp32 [video][ntile][mtile][128][NC])
+ *   bwd_col2im : layer 2: col2 + code1 -> dy1;  layer 1: col1 + code0 -> dy0;
+ *                layer 0: col0 -> d video (B, T, 3, H, W) fp32 (code must be NULL)
+ */
+int vd_tc_pack_weights_bwd(const float* w_l0, const float* w_l1, const float* w_l2,
+                           void* wt0, void* wt1, void* wt2, void* stream);
+int vd_tc_bwd_emb(const float* g_emb, const uint8_t* code2, void* dy2, const vd_tc_plan* plan,
+                  int B, void* stream);
+int vd_tc_bwd_gemm(int layer, const void* dy, const void* wt, float* col, const vd_tc_plan* plan,
+                   int B, void* stream);
+int vd_tc_bwd_col2im(int layer, const float* col, const uint8_t* code_below, void* out,
+                     const vd_tc_plan* plan, int B, void* stream);
+
+/* Tuning probe (tests/bring-up only): issues 148 x n_sa x n_steps x n_acc MMAs of N=ncols with the
+ * given descriptor words over dummy operands (pix >= 64 KiB, wimg >= 16 KiB, raw >= 148*n_acc*128*ncols
+ * floats) so that the MMA rate of a shared-memory layout can be timed with CUDA events. */
+int vd_tc_probe(const void* pix, const void* wimg, float* raw, int ncols, int n_sa, int n_steps,
+                uint32_t a_lbo16, uint32_t a_hi, uint32_t b_lbo16, uint32_t b_hi, uint32_t b_step16,
+                int n_acc, void* stream);
+
 /* Host-only introspection (no GPU work): the launch parameters vd_tc_conv_layer would use,
  * flattened to int64 (layout documented in tests/tc_emulator.py); cap >= 248. */
-int vd_tc_debug_params(int layer, const vd_tc_plan* plan, int B, int64_t* out, int cap);
+int vd_tc_debug_params(int layer, const vd_tc_plan* plan, int B, int64_t* out, int cap);   /* layer 3,4,5 = bwd gemm of conv 0,1,2 */
 
 #ifdef __cplusplus
 }

@@ -178,3 +178,29 @@ def test_fused_epilogues_and_embed(T, HW):
               'features.6.weight': w2, 'features.6.bias': b2}
     e_or = convnet3d_embed(params, video)
     assert rel(emb, e_or) < 1e-2, rel(emb, e_or)
+
+
+@pytest.mark.parametrize('T,HW', CASES)
+def test_backward_matches_routed_fp32(T, HW):
+    """d embed / d video on tensor cores vs the exact fp32 kernels CONDITIONED on the same routing codes
+    (SURVEY §7.3 contract iii).  bf16 rounding of dY between layers -> 2e-2 relL2."""
+    from video_distillation_b200 import ops
+    net, (w0, b0, w1, b1, w2, b2) = make_net(T, HW)
+    B = 3
+    gen = torch.Generator().manual_seed(6)
+    video = em.bf16_round(torch.randn(B, T, 3, HW, HW, generator=gen)).cuda()
+    v = video.clone().requires_grad_(True)
+    emb = net.embed_autograd(v)
+    gemb = torch.randn(emb.shape, generator=gen).cuda()
+    emb.backward(gemb)
+    _, (c0, c1, c2) = net.embed(video, want_codes=True)
+    S, P = (1, 2, 2), (1, 3, 3)
+    x = video.clone().requires_grad_(True)
+    y = ops.route_with_code(ops.conv3d(x.permute(0, 2, 1, 3, 4), w0.cuda(), b0.cuda(), S, P), c0, (1, 2, 2))
+    y = ops.route_with_code(ops.conv3d(y, w1.cuda(), b1.cuda(), S, P), c1, (2, 2, 2))
+    y = ops.route_with_code(ops.conv3d(y, w2.cuda(), b2.cuda(), S, P), c2, (2, 2, 2))
+    y.reshape(B, -1).backward(gemb)
+    r = rel(v.grad, x.grad)
+    if r > 2e-2:
+        dump(f'bwd_{T}_{HW}.npz', got=v.grad, want=x.grad)
+    assert r < 2e-2, r

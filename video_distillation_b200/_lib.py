@@ -26,8 +26,11 @@ class TcPlan(Structure):
                                         'embed_dim')] +
                 [('_pad0', c_int32)] +
                 [(n, c_int64) for n in ('x0_bytes_per_video', 'a1_bytes_per_video', 'a2_bytes_per_video',
-                                        'w0_bytes', 'w1_bytes', 'w2_bytes', 'tab_bytes')] +
-                [('reserved', c_int32 * 16)])
+                                        'w0_bytes', 'w1_bytes', 'w2_bytes', 'tab_bytes',
+                                        'wt0_bytes', 'wt1_bytes', 'wt2_bytes',
+                                        'dy0_bytes_per_video', 'dy1_bytes_per_video', 'dy2_bytes_per_video',
+                                        'col0_bytes_per_video', 'col1_bytes_per_video', 'col2_bytes_per_video')] +
+                [('reserved', c_int32 * 8)])
 
 
 def _declare(lib):

@@ -1,5 +1,5 @@
 """ctypes signatures of the tensor-core entry points (include/vd_b200.h, second half)."""
-from ctypes import POINTER, c_int, c_int64, c_void_p
+from ctypes import POINTER, c_int, c_int64, c_uint32, c_void_p
 
 
 def declare(lib):
@@ -10,6 +10,11 @@ def declare(lib):
         'vd_tc_pack_video': (c_int, [P, P, P, POINTER(TcPlan), c_int, P]),
         'vd_tc_pack_weights': (c_int, [P, P, P, P, P, P, P]),
         'vd_tc_conv_layer': (c_int, [c_int, P, P, P, P, P, POINTER(TcPlan), P, c_int, c_int, P]),
+        'vd_tc_pack_weights_bwd': (c_int, [P, P, P, P, P, P, P]),
+        'vd_tc_bwd_emb': (c_int, [P, P, P, POINTER(TcPlan), c_int, P]),
+        'vd_tc_bwd_gemm': (c_int, [c_int, P, P, P, POINTER(TcPlan), c_int, P]),
+        'vd_tc_bwd_col2im': (c_int, [c_int, P, P, P, POINTER(TcPlan), c_int, P]),
+        'vd_tc_probe': (c_int, [P, P, P, c_int, c_int, c_int, c_uint32, c_uint32, c_uint32, c_uint32, c_uint32, c_int, P]),
         'vd_tc_debug_params': (c_int, [c_int, POINTER(TcPlan), c_int, POINTER(c_int64), c_int]),
     }
     for name, (res, args) in sig.items():

@@ -1,0 +1,185 @@
+// Memory-bound kernels of the tensor-core backward (gradient of ConvNet3D.embed w.r.t. its input
+// video, frozen weights): transposed weight images, embedding-gradient routing, and the col2im
+// gathers that turn the column-GEMM output of conv `l` into the packed dY operand of conv `l-1`
+// (applying the ReLU/MaxPool routing code in between).  Layouts: tc_layout.h (BwdGeo).
+#include "tc_common.cuh"
+#include "tc_layout.h"
+
+namespace vd {
+namespace tc {
+
+// wT image [mtile][step][k 2][128][8] bf16: row = ci*147 + tap, column co = step*16 + k*8 + e
+__global__ void pack_wt_kernel(const float* __restrict__ w, uint16_t* __restrict__ img, int Cin, int K, int NU) {
+    const int n_steps = K / 16;
+    const int64_t total = (int64_t)NU * n_steps * 2048;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int e = (int)(i % 8); int64_t q = i / 8;
+        int row = (int)(q % 128); q /= 128;
+        int k = (int)(q % 2); q /= 2;
+        int step = (int)(q % n_steps); int u = (int)(q / n_steps);
+        const int r = u * 128 + row;
+        float v = 0.f;
+        if (r < Cin * 147) {
+            const int ci = r / 147, tap = r % 147, co = step * 16 + k * 8 + e;
+            v = w[((int64_t)co * Cin + ci) * 147 + tap];
+        }
+        img[i] = f2bf(v);
+    }
+}
+
+// g_emb (B, 128*T3p*H3p*H3p) + code2 -> dy2 [video][NT][16 chunks][NC][8]; conv-2 output pixel
+// (to,ho,wo) receives the pooled gradient iff it is the recorded argmax of an active window.
+__global__ void bwd_emb_kernel(const float* __restrict__ g_emb, const uint8_t* __restrict__ code, uint4* __restrict__ dy,
+                               int64_t total, Geo g, BwdGeo b) {
+    const int per = g.T3p * g.H3p * g.H3p;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int col = (int)(i % b.NC); int64_t q = i / b.NC;
+        int chunk = (int)(q % 16); q /= 16;
+        int nt = (int)(q % b.NT); int64_t vid = q / b.NT;
+        const int pix = nt * b.NC + col;
+        const int wo = pix % b.Wo, ho = (pix / b.Wo) % b.Ho, to = pix / (b.Wo * b.Ho);
+        const int tq = to >> 1, hp = ho >> 1, wp = wo >> 1;
+        const int pos = (to & 1) * 4 + (ho & 1) * 2 + (wo & 1);
+        uint16_t v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int co = chunk * 8 + e;
+            float val = 0.f;
+            if (tq < g.T3p && hp < g.H3p && wp < g.H3p) {
+                const int64_t o = vid * g.embed_dim + (int64_t)co * per + (tq * g.H3p + hp) * g.H3p + wp;
+                const uint8_t cd = code[o];
+                if ((cd & 8) && (cd & 7) == pos) val = g_emb[o];
+            }
+            v[e] = f2bf(val);
+        }
+        uint4 o4;
+        o4.x = v[0] | ((uint32_t)v[1] << 16); o4.y = v[2] | ((uint32_t)v[3] << 16);
+        o4.z = v[4] | ((uint32_t)v[5] << 16); o4.w = v[6] | ((uint32_t)v[7] << 16);
+        dy[i] = o4;
+    }
+}
+
+// dX[ci,t,h,w] of conv `b.layer` = sum over taps of col[(ci,tap)][pixel(t+1-kt, (h+3-kh)/2, (w+3-kw)/2)]
+__device__ __forceinline__ float col2im_gather(const float* __restrict__ colv, const BwdGeo& b, int ci, int t, int h, int w) {
+    float acc = 0.f;
+    for (int kt = 0; kt < 3; ++kt) {
+        const int to = t + 1 - kt;
+        if ((unsigned)to >= (unsigned)b.To) continue;
+        for (int kh = (h + 1) & 1; kh < 7; kh += 2) {
+            const int hh = h + 3 - kh;
+            if (hh < 0) continue;
+            const int ho = hh >> 1;
+            if (ho >= b.Ho) continue;
+            for (int kw = (w + 1) & 1; kw < 7; kw += 2) {
+                const int ww = w + 3 - kw;
+                if (ww < 0) continue;
+                const int wo = ww >> 1;
+                if (wo >= b.Wo) continue;
+                const int r = ci * 147 + (kt * 7 + kh) * 7 + kw;
+                const int pix = (to * b.Ho + ho) * b.Wo + wo;
+                const int nt = pix / b.NC, col = pix - nt * b.NC;
+                acc += __ldg(colv + (((int64_t)nt * b.NU + (r >> 7)) * 128 + (r & 127)) * b.NC + col);
+            }
+        }
+    }
+    return acc;
+}
+
+// layers 2 and 1: one thread per POOLED element (ci,t,h,w) of the layer below; writes the whole
+// pool window (pt x 2 x 2 conv outputs) of the next dY: the routed gradient at the recorded
+// argmax, zeros elsewhere -> dY below is fully overwritten, no memset needed.
+__global__ void col2im_route_kernel(const float* __restrict__ colbuf, const uint8_t* __restrict__ code,
+                                    uint16_t* __restrict__ dy_below, int64_t total, BwdGeo b, BwdGeo bb, int pt) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int w = (int)(i % b.Wi); int64_t q = i / b.Wi;
+        int h = (int)(q % b.Hi); q /= b.Hi;
+        int t = (int)(q % b.Ti); q /= b.Ti;
+        int ci = (int)(q % b.Cin); int64_t vid = q / b.Cin;
+        const float gsum = col2im_gather(colbuf + vid * b.col_video_elems, b, ci, t, h, w);
+        const uint8_t cd = code[i];                       // code layout (B, Cin, Ti, Hi, Wi) == thread order
+        const uint16_t gv = f2bf((cd & 8) ? gsum : 0.f);
+        const int arg = cd & 7;
+        uint16_t* base = dy_below + vid * (bb.dy_video / 2);
+        const int chunk = ci >> 3, e = ci & 7;
+        int pos = 0;
+        for (int dt = 0; dt < pt; ++dt)
+            for (int dh = 0; dh < 2; ++dh)
+                for (int dw = 0; dw < 2; ++dw, ++pos) {
+                    const int pix = ((t * pt + dt) * bb.Ho + (2 * h + dh)) * bb.Wo + 2 * w + dw;
+                    const int nt = pix / bb.NC, col = pix - nt * bb.NC;
+                    base[(((int64_t)nt * (bb.K / 8) + chunk) * bb.NC + col) * 8 + e] = (pos == arg) ? gv : (uint16_t)0;
+                }
+    }
+}
+
+// layer 0: d video (B, T, 3, H, W) fp32
+__global__ void col2im_video_kernel(const float* __restrict__ colbuf, float* __restrict__ dvideo, int64_t total, BwdGeo b) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int w = (int)(i % b.Wi); int64_t q = i / b.Wi;
+        int h = (int)(q % b.Hi); q /= b.Hi;
+        int c = (int)(q % 3); q /= 3;
+        int t = (int)(q % b.Ti); int64_t vid = q / b.Ti;
+        dvideo[i] = col2im_gather(colbuf + vid * b.col_video_elems, b, c, t, h, w);
+    }
+}
+
+static inline unsigned blocks_for(int64_t n) {
+    int64_t x = (n + 255) / 256;
+    const int64_t cap = 148 * 32;
+    return (unsigned)(x < 1 ? 1 : (x > cap ? cap : x));
+}
+
+}  // namespace tc
+}  // namespace vd
+
+using namespace vd;
+using namespace vd::tc;
+
+extern "C" int vd_tc_pack_weights_bwd(const float* w_l0, const float* w_l1, const float* w_l2, void* wt0, void* wt1,
+                                      void* wt2, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    const float* w[3] = {w_l0, w_l1, w_l2};
+    void* o[3] = {wt0, wt1, wt2};
+    const int cin[3] = {3, 64, 128}, kk[3] = {64, 128, 128};
+    for (int l = 0; l < 3; ++l) {
+        if (!w[l] || !o[l]) continue;
+        const int NU = (cin[l] * 147 + 127) / 128;
+        pack_wt_kernel<<<blocks_for((int64_t)NU * (kk[l] / 16) * 2048), 256, 0, s>>>(w[l], (uint16_t*)o[l], cin[l], kk[l], NU);
+        if (int e = check_launch("tc_pack_wt")) return e;
+    }
+    return 0;
+}
+
+extern "C" int vd_tc_bwd_emb(const float* g_emb, const uint8_t* code2, void* dy2, const vd_tc_plan* plan, int B,
+                             void* stream) {
+    VD_REQUIRE(g_emb && code2 && dy2 && plan, "tc_bwd_emb: NULL pointer");
+    VD_REQUIRE(geo_supported(plan->T, plan->H), "tc_bwd_emb: unsupported geometry");
+    if (B <= 0) return 0;
+    const Geo g = make_geo(plan->T, plan->H);
+    const BwdGeo b = make_bwd_geo(g, 2);
+    const int64_t total = (int64_t)B * b.NT * 16 * b.NC;
+    bwd_emb_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(g_emb, code2, (uint4*)dy2, total, g, b);
+    return check_launch("tc_bwd_emb");
+}
+
+extern "C" int vd_tc_bwd_col2im(int layer, const float* col, const uint8_t* code_below, void* out,
+                                const vd_tc_plan* plan, int B, void* stream) {
+    VD_REQUIRE(col && out && plan, "tc_bwd_col2im: NULL pointer");
+    VD_REQUIRE(layer >= 0 && layer <= 2, "tc_bwd_col2im: bad layer");
+    VD_REQUIRE((layer == 0) == (code_below == nullptr), "tc_bwd_col2im: code_below is required for layers 1,2 and must be NULL for layer 0");
+    VD_REQUIRE(geo_supported(plan->T, plan->H), "tc_bwd_col2im: unsupported geometry");
+    if (B <= 0) return 0;
+    const Geo g = make_geo(plan->T, plan->H);
+    const BwdGeo b = make_bwd_geo(g, layer);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (layer == 0) {
+        const int64_t total = (int64_t)B * b.Ti * 3 * b.Hi * b.Wi;
+        col2im_video_kernel<<<blocks_for(total), 256, 0, s>>>(col, (float*)out, total, b);
+        return check_launch("tc_bwd_col2im_video");
+    }
+    const BwdGeo bb = make_bwd_geo(g, layer - 1);
+    const int pt = (layer == 2) ? 2 : 1;       // pool window of the layer below in T: conv1 -> (2,2,2), conv0 -> (1,2,2)
+    const int64_t total = (int64_t)B * b.Cin * b.Ti * b.Hi * b.Wi;
+    col2im_route_kernel<<<blocks_for(total), 256, 0, s>>>(col, code_below, (uint16_t*)out, total, b, bb, pt);
+    return check_launch("tc_bwd_col2im_route");
+}

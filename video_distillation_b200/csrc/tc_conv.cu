@@ -40,6 +40,8 @@ struct WsParams {
     const int64_t* item_index;          // optional: item -> slot of `pix` (resident dataset)
     int32_t n_tiles, tiles_per_item, v_count;
     int64_t item_stride, u_stride, v_stride;
+    int32_t n_u;                        // accumulator groups per tile sharing ONE pixel stage (column GEMM: M tiles)
+    int64_t w_u_stride;                 // bytes between the weight sequences of consecutive groups
     int32_t n_sa, n_sb;
     int64_t sa_stride, sb_stride;
     int32_t n_copies;
@@ -54,6 +56,7 @@ struct WsParams {
     uint32_t a_off16[kMaxSteps];        // resident weights: offset of the tile of (sa=0, step)
     int32_t a_sa_stride16;              // resident weights: offset added per stage index
     uint32_t a_lbo16, a_sbo16;
+    uint32_t a_hi, b_hi;                // upper descriptor words (SBO | version | layout type); 0 = default no-swizzle
     int32_t w_resident;
     uint32_t w_bytes;                   // resident image bytes
     int32_t G, RW, RP;
@@ -80,9 +83,9 @@ static_assert(sizeof(Barriers) <= kBarBytes, "barrier block too large");
 // epilogues.  Thread `m` (0..127) owns TMEM lane m.  taddr = tmem base of the accumulator stage
 // with the lane quarter already folded in.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void epi_raw(const WsParams& p, int tile, uint32_t taddr, int m) {
+__device__ __forceinline__ void epi_raw(const WsParams& p, int tile, int u, uint32_t taddr, int m) {
     for (int a = 0; a < p.n_acc; ++a) {
-        float* dst = p.epi.raw + (((int64_t)tile * p.n_acc + a) * 128 + m) * p.ncols;
+        float* dst = p.epi.raw + ((((int64_t)tile * p.n_u + u) * p.n_acc + a) * 128 + m) * p.ncols;
         for (uint32_t c = 0; c < p.ncols; c += 8) {
             float v[8];
             tmem_ld8(taddr + a * p.acc_cols + c, v);
@@ -303,16 +306,18 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
                 uint32_t slot = 0, phase = 0;
                 const int slots_per_stage = (p.n_steps + p.G - 1) / p.G;
                 for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-                    for (int st = 0; st < stages_per_tile; ++st)
-                        for (int gi = 0; gi < slots_per_stage; ++gi) {
-                            const int s0 = gi * p.G;
-                            const uint32_t nb = (uint32_t)min(p.G, p.n_steps - s0) * kWeightTileBytes;
-                            mbar_wait(BAR(w_empty, slot), phase ^ 1);
-                            mbar_expect_tx(BAR(w_full, slot), nb);
-                            bulk_g2s(smem_w + slot * (uint32_t)p.G * kWeightTileBytes,
-                                     p.wimg + ((int64_t)st * p.n_steps + s0) * kWeightTileBytes, nb, BAR(w_full, slot));
-                            if (++slot == (uint32_t)p.RW) { slot = 0; phase ^= 1; }
-                        }
+                    for (int u = 0; u < p.n_u; ++u)
+                        for (int st = 0; st < stages_per_tile; ++st)
+                            for (int gi = 0; gi < slots_per_stage; ++gi) {
+                                const int s0 = gi * p.G;
+                                const uint32_t nb = (uint32_t)min(p.G, p.n_steps - s0) * kWeightTileBytes;
+                                mbar_wait(BAR(w_empty, slot), phase ^ 1);
+                                mbar_expect_tx(BAR(w_full, slot), nb);
+                                bulk_g2s(smem_w + slot * (uint32_t)p.G * kWeightTileBytes,
+                                         p.wimg + (int64_t)u * p.w_u_stride + ((int64_t)st * p.n_steps + s0) * kWeightTileBytes,
+                                         nb, BAR(w_full, slot));
+                                if (++slot == (uint32_t)p.RW) { slot = 0; phase ^= 1; }
+                            }
                 }
             }
         }
@@ -320,16 +325,19 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
         // ===================== MMA issuer (one thread) =====================
         if (lane == 0) {
             uint32_t pslot = 0, pphase = 0, wslot = 0, wphase = 0, as = 0, aphase = 0;
+            const uint32_t a_hi = p.a_hi ? p.a_hi : ((p.a_sbo16 & 0x3FFFu) | (1u << 14));
+            const uint32_t b_hi = p.b_hi ? p.b_hi : (8u | (1u << 14));
             if (p.w_resident) { mbar_wait(BAR(w_res, 0), 0); tc_fence_after(); }
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+              // n_u > 1 (column GEMM): one pixel stage per tile, reused by every accumulator group
+              for (int u = 0; u < p.n_u; ++u) {
                 mbar_wait(BAR(acc_empty, as), aphase ^ 1);
                 tc_fence_after();
                 const uint32_t d_base = tmem_base + as * (p.acc_cols * (uint32_t)p.n_acc);
                 uint32_t accumulate = 0;
                 for (int sa = 0; sa < p.n_sa; ++sa)
                     for (int sb = 0; sb < p.n_sb; ++sb) {
-                        mbar_wait(BAR(pix_full, pslot), pphase);
-                        tc_fence_after();
+                        if (u == 0) { mbar_wait(BAR(pix_full, pslot), pphase); tc_fence_after(); }
                         const uint32_t pix16 = (smem_pix + pslot * p.stage_pitch) >> 4;
                         for (int j = 0; j < p.n_steps; ++j) {
                             uint32_t a16;
@@ -340,11 +348,11 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
                                 if (jj == 0) { mbar_wait(BAR(w_full, wslot), wphase); tc_fence_after(); }
                                 a16 = ((smem_w + wslot * (uint32_t)p.G * kWeightTileBytes) >> 4) + (uint32_t)jj * (kWeightTileBytes >> 4);
                             }
-                            const uint64_t a_desc = umma_desc(a16, p.a_lbo16, p.a_sbo16);
+                            const uint64_t a_desc = ((uint64_t)a_hi << 32) | (a16 & 0x3FFFu) | ((p.a_lbo16 & 0x3FFFu) << 16);
                             const uint32_t b16 = pix16 + p.b_off16[j];
                             const uint32_t lbo = p.b_lbo16[j];
                             for (int a = 0; a < p.n_acc; ++a) {
-                                const uint64_t b_desc = umma_desc(b16 + (uint32_t)a * p.acc_delta16, lbo, 8);
+                                const uint64_t b_desc = ((uint64_t)b_hi << 32) | ((b16 + (uint32_t)a * p.acc_delta16) & 0x3FFFu) | ((lbo & 0x3FFFu) << 16);
                                 umma_bf16(d_base + (uint32_t)a * p.acc_cols, a_desc, b_desc, p.idesc, accumulate);
                             }
                             accumulate = 1;
@@ -353,11 +361,14 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
                                 if (++wslot == (uint32_t)p.RW) { wslot = 0; wphase ^= 1; }
                             }
                         }
-                        umma_commit(BAR(pix_empty, pslot));
-                        if (++pslot == (uint32_t)p.RP) { pslot = 0; pphase ^= 1; }
+                        if (u == p.n_u - 1) {
+                            umma_commit(BAR(pix_empty, pslot));
+                            if (++pslot == (uint32_t)p.RP) { pslot = 0; pphase ^= 1; }
+                        }
                     }
                 umma_commit(BAR(acc_full, as));
                 if (++as == p.acc_stages) { as = 0; aphase ^= 1; }
+              }
             }
         }
     } else if (warp >= 4) {
@@ -365,19 +376,20 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
         const int q = warp & 3;
         const int m = q * 32 + lane;
         uint32_t as = 0, aphase = 0;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-            mbar_wait(BAR(acc_full, as), aphase);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * (p.acc_cols * (uint32_t)p.n_acc);
-            if (EPI == EPI_RAW) epi_raw(p, tile, taddr, m);
-            else if (EPI == EPI_L0) epi_l0(p, tile, taddr, m);
-            else if (EPI == EPI_L1) epi_l1(p, tile, taddr, m);
-            else epi_l2(p, tile, taddr, m);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(BAR(acc_empty, as));
-            if (++as == p.acc_stages) { as = 0; aphase ^= 1; }
-        }
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x)
+            for (int u = 0; u < p.n_u; ++u) {
+                mbar_wait(BAR(acc_full, as), aphase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * (p.acc_cols * (uint32_t)p.n_acc);
+                if (EPI == EPI_RAW) epi_raw(p, tile, u, taddr, m);
+                else if (EPI == EPI_L0) epi_l0(p, tile, taddr, m);
+                else if (EPI == EPI_L1) epi_l1(p, tile, taddr, m);
+                else epi_l2(p, tile, taddr, m);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(acc_empty, as));
+                if (++as == p.acc_stages) { as = 0; aphase ^= 1; }
+            }
     }
     // ===================== teardown =====================
     tc_fence_before();
@@ -406,6 +418,7 @@ static int finalize_smem(WsParams& p, uint32_t w_region, uint32_t* smem_total) {
 }
 
 static int setup_l0(WsParams& p, const Geo& g, int B, uint32_t* smem) {
+    p.n_u = 1; p.w_u_stride = 0;
     p.n_tiles = B * (g.T / 2) * (g.Ho0 / g.R0);
     p.tiles_per_item = (g.T / 2) * (g.Ho0 / g.R0);
     p.v_count = g.Ho0 / g.R0;
@@ -446,6 +459,7 @@ static int setup_l0(WsParams& p, const Geo& g, int B, uint32_t* smem) {
 }
 
 static int setup_l1(WsParams& p, const Geo& g, int B, uint32_t* smem) {
+    p.n_u = 1; p.w_u_stride = 0;
     p.n_tiles = B * (g.T / 2);
     p.tiles_per_item = g.T / 2; p.v_count = 1;
     p.item_stride = g.video1; p.u_stride = 2 * g.frame1; p.v_stride = 0;
@@ -470,6 +484,7 @@ static int setup_l1(WsParams& p, const Geo& g, int B, uint32_t* smem) {
 }
 
 static int setup_l2(WsParams& p, const Geo& g, int B, uint32_t* smem) {
+    p.n_u = 1; p.w_u_stride = 0;
     const int VPT = kVideosPerTile2;
     p.n_tiles = (B + VPT - 1) / VPT;
     p.tiles_per_item = 1; p.v_count = 1;
@@ -494,6 +509,26 @@ static int setup_l2(WsParams& p, const Geo& g, int B, uint32_t* smem) {
     p.n_acc = VPT; p.acc_delta16 = (uint32_t)g.group2 >> 4;
     p.ncols = g.N2; p.acc_cols = 128; p.acc_stages = 1;
     p.idesc = umma_idesc_bf16(128, g.N2);
+    return finalize_smem(p, (uint32_t)p.G * p.RW * kWeightTileBytes, smem);
+}
+
+static int setup_bwd(WsParams& p, const Geo& g, int layer, int B, uint32_t* smem) {
+    const BwdGeo b = make_bwd_geo(g, layer);
+    VD_REQUIRE(b.pixels % 16 == 0, "tc bwd: pixel count must be a multiple of 16");
+    p.n_tiles = B * b.NT; p.tiles_per_item = b.NT; p.v_count = b.NT;
+    p.item_stride = b.dy_video; p.u_stride = 0; p.v_stride = (int64_t)(b.K / 8) * b.NC * 16;
+    p.n_u = b.NU; p.w_u_stride = (int64_t)b.n_steps * kWeightTileBytes;
+    p.n_sa = 1; p.n_sb = 1; p.sa_stride = 0; p.sb_stride = 0;
+    p.n_copies = 1; p.copy_gofs[0] = 0; p.copy_sofs[0] = 0; p.copy_bytes[0] = (uint32_t)((b.K / 8) * b.NC * 16);
+    p.stage_bytes = p.copy_bytes[0];
+    p.n_steps = b.n_steps;
+    for (int j = 0; j < b.n_steps; ++j) { p.b_off16[j] = (uint32_t)(2 * j * b.NC); p.b_lbo16[j] = (uint32_t)b.NC; }
+    p.a_lbo16 = 2048 >> 4; p.a_sbo16 = 8;
+    p.w_resident = 0; p.w_bytes = 0;
+    p.G = b.n_steps; p.RW = 2; p.RP = 2;
+    p.n_acc = 1; p.acc_delta16 = 0;
+    p.ncols = b.NC; p.acc_cols = 256; p.acc_stages = 2;
+    p.idesc = umma_idesc_bf16(128, b.NC);
     return finalize_smem(p, (uint32_t)p.G * p.RW * kWeightTileBytes, smem);
 }
 
@@ -538,6 +573,11 @@ extern "C" int vd_tc_plan_make(vd_tc_plan* plan, int T, int H, int W) {
     plan->w1_bytes = (int64_t)588 * kWeightTileBytes;
     plan->w2_bytes = (int64_t)1176 * kWeightTileBytes;
     plan->tab_bytes = 0;
+    const BwdGeo b0 = make_bwd_geo(g, 0), b1 = make_bwd_geo(g, 1), b2 = make_bwd_geo(g, 2);
+    plan->wt0_bytes = b0.wt_bytes; plan->wt1_bytes = b1.wt_bytes; plan->wt2_bytes = b2.wt_bytes;
+    plan->dy0_bytes_per_video = b0.dy_video; plan->dy1_bytes_per_video = b1.dy_video; plan->dy2_bytes_per_video = b2.dy_video;
+    plan->col0_bytes_per_video = b0.col_video_elems * 4; plan->col1_bytes_per_video = b1.col_video_elems * 4;
+    plan->col2_bytes_per_video = b2.col_video_elems * 4;
     return 0;
 }
 
@@ -570,13 +610,14 @@ extern "C" int vd_tc_conv_layer(int layer, const void* in, const void* wimg, con
 // Host-side introspection for the CPU emulator in tests/ (no GPU work): dumps the exact kernel
 // parameters that vd_tc_conv_layer would launch with.
 extern "C" int vd_tc_debug_params(int layer, const vd_tc_plan* plan, int B, int64_t* out, int cap) {
-    VD_REQUIRE(plan && out && cap >= 32 + 3 * kMaxCopies + 3 * kMaxSteps, "tc_debug_params: buffer too small");
-    VD_REQUIRE(layer >= 0 && layer <= 2 && geo_supported(plan->T, plan->H), "tc_debug_params: bad layer / geometry");
+    VD_REQUIRE(plan && out && cap >= 33 + 3 * kMaxCopies + 3 * kMaxSteps, "tc_debug_params: buffer too small");
+    VD_REQUIRE(layer >= 0 && layer <= 5 && geo_supported(plan->T, plan->H), "tc_debug_params: bad layer / geometry");
     WsParams p;
     memset(&p, 0, sizeof(p));
     const Geo g = make_geo(plan->T, plan->H);
     uint32_t smem = 0;
-    int rc = layer == 0 ? setup_l0(p, g, B, &smem) : layer == 1 ? setup_l1(p, g, B, &smem) : setup_l2(p, g, B, &smem);
+    int rc = layer == 0 ? setup_l0(p, g, B, &smem) : layer == 1 ? setup_l1(p, g, B, &smem) : layer == 2 ? setup_l2(p, g, B, &smem)
+                        : setup_bwd(p, g, layer - 3, B, &smem);
     if (rc) return rc;
     int i = 0;
     out[i++] = p.n_tiles; out[i++] = p.tiles_per_item; out[i++] = p.v_count;
@@ -586,12 +627,54 @@ extern "C" int vd_tc_debug_params(int layer, const vd_tc_plan* plan, int B, int6
     out[i++] = p.a_sa_stride16; out[i++] = p.a_lbo16; out[i++] = p.a_sbo16; out[i++] = p.w_resident;
     out[i++] = p.w_bytes; out[i++] = p.G; out[i++] = p.RW; out[i++] = p.RP; out[i++] = p.n_acc;
     out[i++] = p.acc_delta16; out[i++] = p.ncols; out[i++] = p.acc_cols; out[i++] = p.acc_stages;
-    out[i++] = p.idesc; out[i++] = p.smem_w_off; out[i++] = p.smem_pix_off; out[i++] = smem; out[i++] = 0;
+    out[i++] = p.idesc; out[i++] = p.smem_w_off; out[i++] = p.smem_pix_off; out[i++] = smem; out[i++] = p.n_u;
     for (int k = 0; k < kMaxCopies; ++k) out[i++] = p.copy_gofs[k];
     for (int k = 0; k < kMaxCopies; ++k) out[i++] = p.copy_sofs[k];
     for (int k = 0; k < kMaxCopies; ++k) out[i++] = p.copy_bytes[k];
     for (int k = 0; k < kMaxSteps; ++k) out[i++] = p.b_off16[k];
     for (int k = 0; k < kMaxSteps; ++k) out[i++] = p.b_lbo16[k];
     for (int k = 0; k < kMaxSteps; ++k) out[i++] = p.a_off16[k];
+    out[i++] = p.w_u_stride;
     return 0;
+}
+
+extern "C" int vd_tc_bwd_gemm(int layer, const void* dy, const void* wt, float* col, const vd_tc_plan* plan,
+                              int B, void* stream) {
+    VD_REQUIRE(plan && dy && wt && col, "tc_bwd_gemm: NULL pointer");
+    VD_REQUIRE(layer >= 0 && layer <= 2 && B >= 0, "tc_bwd_gemm: bad layer / batch");
+    VD_REQUIRE(geo_supported(plan->T, plan->H), "tc_bwd_gemm: unsupported geometry");
+    if (B == 0) return 0;
+    WsParams p;
+    memset(&p, 0, sizeof(p));
+    const Geo g = make_geo(plan->T, plan->H);
+    uint32_t smem = 0;
+    if (int rc = setup_bwd(p, g, layer, B, &smem)) return rc;
+    p.pix = (const uint8_t*)dy; p.wimg = (const uint8_t*)wt; p.item_index = nullptr;
+    p.epi.raw = col; p.epi.T = plan->T; p.epi.n_items = B; p.epi.g = g;
+    return launch<EPI_RAW>(p, smem, (cudaStream_t)stream);
+}
+
+// Bring-up / tuning probe: MMA issue rate of one layout variant, data content irrelevant.
+//   hi words: SBO>>4 | 1<<14 | layout_type<<29 (0 none, 2 = 128B, 4 = 64B, 6 = 32B swizzle)
+// 148 tiles x n_sa stages x n_steps MMAs of N = ncols; raw accumulators go to `raw`.
+extern "C" int vd_tc_probe(const void* pix, const void* wimg, float* raw, int ncols, int n_sa, int n_steps,
+                           uint32_t a_lbo16, uint32_t a_hi, uint32_t b_lbo16, uint32_t b_hi, uint32_t b_step16,
+                           int n_acc, void* stream) {
+    VD_REQUIRE(pix && wimg && raw && ncols % 16 == 0 && ncols >= 16 && ncols <= 256 && n_steps <= kMaxSteps, "tc_probe: bad argument");
+    WsParams p;
+    memset(&p, 0, sizeof(p));
+    p.n_tiles = 148; p.tiles_per_item = 148; p.v_count = 148; p.item_stride = 0; p.u_stride = 0; p.v_stride = 0;
+    p.n_u = 1; p.w_u_stride = 0;
+    p.n_sa = n_sa; p.n_sb = 1; p.sa_stride = 0; p.sb_stride = 0;
+    p.n_copies = 1; p.copy_gofs[0] = 0; p.copy_sofs[0] = 0; p.copy_bytes[0] = 65536; p.stage_bytes = 65536;
+    p.n_steps = n_steps;
+    for (int j = 0; j < n_steps; ++j) { p.b_off16[j] = (uint32_t)(j % 4) * b_step16; p.b_lbo16[j] = b_lbo16; p.a_off16[j] = 0; }
+    p.a_sa_stride16 = 0; p.a_lbo16 = a_lbo16; p.a_sbo16 = 8; p.a_hi = a_hi; p.b_hi = b_hi;
+    p.w_resident = 1; p.w_bytes = 16384; p.G = 1; p.RW = 1; p.RP = 2;
+    p.n_acc = n_acc; p.acc_delta16 = 0; p.ncols = ncols; p.acc_cols = 256; p.acc_stages = (n_acc == 1) ? 2 : 1;
+    p.idesc = umma_idesc_bf16(128, ncols);
+    uint32_t smem = 0;
+    if (int rc = finalize_smem(p, 16384, &smem)) return rc;
+    p.pix = (const uint8_t*)pix; p.wimg = (const uint8_t*)wimg; p.epi.raw = raw;
+    return launch<EPI_RAW>(p, smem, (cudaStream_t)stream);
 }

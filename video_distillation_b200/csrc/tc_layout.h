@@ -98,6 +98,36 @@ __host__ __device__ inline int coord_pos(int x) { return (x & 1) ? (x + 3) / 2 :
 // so that chunk pairs (2s, 2s+1) always have a positive descriptor LBO.  chunk = c*7 + idx.
 __host__ __device__ inline int l0_chunk_kh(int idx) { return idx < 3 ? 2 * idx + 1 : 2 * (idx - 3); }
 
+// ---- backward column GEMM of conv `layer`: col[(ci,tap), pixel] = sum_co W[co,ci,tap] dY[co,pixel]
+//   dY packed  : [video][ntile NT][chunk K/8][col NC][8]      (bf16, K = Cout)
+//   wT image   : [mtile NU][step K/16][k 2][128 rows][8]      row = ci*147 + tap (zero beyond Cin*147)
+//   col        : [video][ntile NT][mtile NU][128 rows][NC]    (fp32)
+struct BwdGeo {
+    int layer, Cin, K, Mrows, NU, pixels, NC, NT, n_steps;
+    int To, Ho, Wo;            // output (dY) extent of this conv
+    int Ti, Hi, Wi;            // input (dX) extent of this conv
+    int64_t dy_video, col_video_elems, wt_bytes;
+};
+
+inline BwdGeo make_bwd_geo(const Geo& g, int layer) {
+    BwdGeo b{};
+    b.layer = layer;
+    if (layer == 0) { b.Cin = 3; b.K = 64; b.To = g.T; b.Ho = g.Ho0; b.Wo = g.Wo0; b.Ti = g.T; b.Hi = g.HW; b.Wi = g.HW; }
+    else if (layer == 1) { b.Cin = 64; b.K = 128; b.To = g.T; b.Ho = g.Ho1; b.Wo = g.Wo1; b.Ti = g.T; b.Hi = g.H1; b.Wi = g.H1; }
+    else { b.Cin = 128; b.K = 128; b.To = g.To2; b.Ho = g.Ho2; b.Wo = g.Wo2; b.Ti = g.T2; b.Hi = g.H2; b.Wi = g.H2; }
+    b.Mrows = b.Cin * 147;
+    b.NU = (b.Mrows + 127) / 128;
+    b.pixels = b.To * b.Ho * b.Wo;
+    b.NC = 16;
+    for (int c = 256; c >= 16; c -= 16) if (b.pixels % c == 0) { b.NC = c; break; }
+    b.NT = b.pixels / b.NC;
+    b.n_steps = b.K / 16;
+    b.dy_video = (int64_t)b.NT * (b.K / 8) * b.NC * 16;
+    b.col_video_elems = (int64_t)b.NT * b.NU * 128 * b.NC;
+    b.wt_bytes = (int64_t)b.NU * b.n_steps * 4096;
+    return b;
+}
+
 constexpr int kWeightTileBytes = 4096;      // [k 2][128 rows][16 B]
 constexpr int kVideosPerTile2 = 4;          // conv 2: accumulators (videos) per CTA tile
 constexpr int kW0Steps = 11;                // conv 0: 21 (c,kh) chunks paired into K=16 steps

@@ -76,6 +76,27 @@ class DeviceDataset:
         self.videos = videos[idx].to(self.device, non_blocking=True).contiguous()
         self.shape = tuple(videos.shape[1:])
 
+    @classmethod
+    def from_device_shard(cls, shard_videos, labels, num_classes, device, rank=0, world=1):
+        """Same object from an already device-resident shard: ``shard_videos`` holds exactly the rows
+        of the owned classes, in dataset order (synthetic benchmarks generate them on the device)."""
+        self = cls.__new__(cls)
+        labels = [int(v) for v in labels]
+        self.num_classes = num_classes
+        self.indices_class = [[] for _ in range(num_classes)]
+        for i, lab in enumerate(labels):
+            self.indices_class[lab].append(i)
+        self.rank, self.world = rank, world
+        self.owned = owned_classes(num_classes, rank, world)
+        keep = [i for i, lab in enumerate(labels) if lab % world == rank]
+        assert shard_videos.shape[0] == len(keep), 'shard does not match the owned rows'
+        self.local_of_global = np.full(len(labels), -1, dtype=np.int64)
+        self.local_of_global[np.asarray(keep, dtype=np.int64)] = np.arange(len(keep))
+        self.device = torch.device(device)
+        self.videos = shard_videos.contiguous()
+        self.shape = tuple(shard_videos.shape[1:])
+        return self
+
     def sample_all_classes(self, n):
         """The reference's per-class draws for ALL classes in order (every rank replays the whole
         numpy stream); returns the global indices (C, n) — bit-exact with get_images."""
@@ -93,10 +114,18 @@ class DeviceDataset:
         return self.videos[self.local_index(idx)]
 
 
-def frozen_convnet3d(channel, num_classes, im_size, frames, device, seed=None):
+def frozen_convnet3d(channel, num_classes, im_size, frames, device, seed=None, init_on_device=False):
     """A fresh frozen random ConvNet3D as at distill_s2d_ms.py:393-396.  ``seed`` (tests, multi-GPU:
-    every rank must build the same net) replaces the wall-clock reseed of get_network."""
-    if seed is None:
+    every rank must build the same net) replaces the wall-clock reseed of get_network.
+    ``init_on_device`` draws the same default init (kaiming-uniform / uniform bias) with the DEVICE
+    generator instead of initialising 3.65 M parameters on the host and copying them every
+    iteration (same distribution, different stream than the reference's CPU init)."""
+    if init_on_device:
+        if seed is not None:
+            torch.cuda.manual_seed(int(seed))
+        with torch.device(device):
+            net = ConvNet3D(channel, num_classes, 128, 3, 'relu', 'none', 'maxpooling', frames, im_size)
+    elif seed is None:
         net = get_network('ConvNet3D', channel, num_classes, im_size, frames=frames)
     else:
         torch.random.manual_seed(int(seed))
@@ -143,9 +172,14 @@ class DMS2DTrainer:
 
     def __init__(self, dataset, *, num_classes, channel=3, im_size=(112, 112), frames=16, vpc=1, spc=2, dpc=2,
                  batch_real=64, lr_dynamic=1e4, lr_hal=1e-2, lr_static=1e-4, train_static=False, precision='bf16',
-                 static_syn=None, dynamic_syn=None, hal=None, max_batch=128, device='cuda'):
+                 static_syn=None, dynamic_syn=None, hal=None, max_batch=128, device='cuda', init_on_device=False,
+                 syn_on_tensor_cores=True):
         self.rank, self.world = _world()
         self.ds = dataset
+        self.init_on_device = init_on_device
+        # precision='bf16': synthetic branch forward + backward also on tensor cores (bf16 operands);
+        # set False to keep the synthetic branch on the exact fp32 kernels (mixed mode).
+        self.syn_on_tensor_cores = syn_on_tensor_cores
         self.C, self.channel, self.im_size, self.frames = num_classes, channel, tuple(im_size), frames
         self.vpc, self.spc, self.dpc, self.batch_real = vpc, spc, dpc, batch_real
         self.lr_dynamic, self.lr_hal, self.lr_static, self.train_static = lr_dynamic, lr_hal, lr_static, train_static
@@ -184,11 +218,14 @@ class DMS2DTrainer:
         ops.sgd_momentum_(p.data, grad.contiguous(), self._bufs[name], lr, momentum, first)
 
     # ------------------------------------------------------------------ one iteration
-    def step(self, net=None, net_seed=None, indices=None, real_idx=None):
-        """One DM iteration; returns the loss (0-dim device tensor, summed over ALL classes)."""
+    def step(self, net=None, net_seed=None, indices=None, real_idx=None, real_batch=None):
+        """One DM iteration; returns the loss (0-dim device tensor, summed over ALL classes).
+        ``real_batch``: optional device tensor holding this rank's sampled real videos already gathered
+        (class-major, batch_real per owned class) — the host-streaming mode of bench.py."""
         C, vpc = self.C, self.vpc
         if net is None:
-            net = frozen_convnet3d(self.channel, C, self.im_size, self.frames, self.device, seed=net_seed)
+            net = frozen_convnet3d(self.channel, C, self.im_size, self.frames, self.device, seed=net_seed,
+                                   init_on_device=self.init_on_device)
         self.embedder.load(net)
         label, dynamic_idx, static_idx = indices if indices is not None else self.sample_syn_indices()
         if real_idx is None:
@@ -198,11 +235,18 @@ class DMS2DTrainer:
         n_own = len(own)
         sel = (self.owned_t[:, None] * vpc + torch.arange(vpc, device=self.device)[None, :]).reshape(-1)
         image_syn = self.hal.compose(self.static_syn, self.dynamic_syn, static_idx[sel], label[sel], dynamic_idx[sel])
-        ridx = self.ds.local_index(real_idx[own])                           # (n_own*batch_real,)
-        emb_real = self.embedder(self.ds.videos, ridx)                      # (n_own*batch_real, D)
+        if real_batch is None:
+            ridx = self.ds.local_index(real_idx[own])                       # (n_own*batch_real,)
+            emb_real = self.embedder(self.ds.videos, ridx)                  # (n_own*batch_real, D)
+        else:
+            ridx = torch.arange(real_batch.shape[0], device=self.device)
+            emb_real = self.embedder(real_batch, ridx)
         D = emb_real.shape[1]
         mean_real = ops.class_mean(emb_real.view(n_own, self.batch_real, D))
-        emb_syn = net.embed(image_syn).view(n_own, vpc, D)
+        if self.embedder.tc is not None and self.syn_on_tensor_cores:
+            emb_syn = self.embedder.tc.embed_autograd(image_syn).view(n_own, vpc, D)
+        else:
+            emb_syn = net.embed(image_syn).view(n_own, vpc, D)
         loss = ops.dm_loss(mean_real, emb_syn)
         for p in (self.dynamic_syn, self.static_syn, *self.hal.parameters()):
             p.grad = None

@@ -36,11 +36,19 @@ class TcConvNet3D:
         self.w0 = torch.empty(p.w0_bytes, **u8)
         self.w1 = torch.empty(p.w1_bytes, **u8)
         self.w2 = torch.empty(p.w2_bytes, **u8)
+        self.wt0 = torch.empty(p.wt0_bytes, **u8)       # transposed images for the backward column GEMMs
+        self.wt1 = torch.empty(p.wt1_bytes, **u8)
+        self.wt2 = torch.empty(p.wt2_bytes, **u8)
+        self._bwd_ready = False
+        self._fp32_w = None
+        self.bwd_chunk = 8
+        self._ws = {}
         self.b0 = self.b1 = self.b2 = None
         self._x0 = None
         self._a1 = None
         self._a2 = None
         self.embed_dim = int(p.embed_dim)
+        self.timing = None          # set to [] to collect (layer, B, start_event, end_event) per launch
 
     # ---------------------------------------------------------------- operands
     def load_weights(self, w0, b0, w1, b1, w2, b2):
@@ -50,7 +58,57 @@ class TcConvNet3D:
                                                  _lib.ptr(self.w0), _lib.ptr(self.w1), _lib.ptr(self.w2),
                                                  _lib.stream()), 'vd_tc_pack_weights')
         self.b0, self.b1, self.b2 = (t.detach().contiguous().float() for t in (b0, b1, b2))
+        self._fp32_w = ws
+        self._bwd_ready = False
         return self
+
+    def _prepare_bwd(self):
+        if not self._bwd_ready:
+            ws = self._fp32_w
+            _lib.check(_lib.lib().vd_tc_pack_weights_bwd(_lib.ptr(ws[0]), _lib.ptr(ws[1]), _lib.ptr(ws[2]),
+                                                         _lib.ptr(self.wt0), _lib.ptr(self.wt1), _lib.ptr(self.wt2),
+                                                         _lib.stream()), 'vd_tc_pack_weights_bwd')
+            self._bwd_ready = True
+
+    def _workspace(self, name, nbytes, dtype=torch.uint8):
+        t = self._ws.get(name)
+        n = nbytes // torch.empty((), dtype=dtype).element_size()
+        if t is None or t.numel() < n:
+            t = torch.empty(n, dtype=dtype, device=self.device)
+            self._ws[name] = t
+        return t
+
+    def embed_backward(self, g_emb, codes):
+        """Gradient of ``embed`` w.r.t. its input videos for the routing recorded in ``codes``
+        (weights frozen): three column GEMMs on tensor cores + col2im/routing gathers."""
+        self._prepare_bwd()
+        p, lib = self.plan, _lib.lib()
+        g_emb = g_emb.contiguous().float()
+        B = g_emb.shape[0]
+        c0, c1, c2 = codes
+        dvideo = torch.empty(B, self.T, 3, self.H, self.W, dtype=torch.float32, device=self.device)
+        for s in range(0, B, self.bwd_chunk):
+            e = min(B, s + self.bwd_chunk)
+            n = e - s
+            dy2 = self._workspace('dy2', n * p.dy2_bytes_per_video)
+            dy1 = self._workspace('dy1', n * p.dy1_bytes_per_video)
+            dy0 = self._workspace('dy0', n * p.dy0_bytes_per_video)
+            col = self._workspace('col', n * max(p.col0_bytes_per_video, p.col1_bytes_per_video, p.col2_bytes_per_video),
+                                  torch.float32)
+            st = _lib.stream()
+            plan = ctypes.byref(p)
+            _lib.check(lib.vd_tc_bwd_emb(_lib.ptr(g_emb[s:e]), _lib.ptr(c2[s:e]), _lib.ptr(dy2), plan, n, st), 'vd_tc_bwd_emb')
+            _lib.check(lib.vd_tc_bwd_gemm(2, _lib.ptr(dy2), _lib.ptr(self.wt2), _lib.ptr(col), plan, n, st), 'vd_tc_bwd_gemm(2)')
+            _lib.check(lib.vd_tc_bwd_col2im(2, _lib.ptr(col), _lib.ptr(c1[s:e]), _lib.ptr(dy1), plan, n, st), 'vd_tc_bwd_col2im(2)')
+            _lib.check(lib.vd_tc_bwd_gemm(1, _lib.ptr(dy1), _lib.ptr(self.wt1), _lib.ptr(col), plan, n, st), 'vd_tc_bwd_gemm(1)')
+            _lib.check(lib.vd_tc_bwd_col2im(1, _lib.ptr(col), _lib.ptr(c0[s:e]), _lib.ptr(dy0), plan, n, st), 'vd_tc_bwd_col2im(1)')
+            _lib.check(lib.vd_tc_bwd_gemm(0, _lib.ptr(dy0), _lib.ptr(self.wt0), _lib.ptr(col), plan, n, st), 'vd_tc_bwd_gemm(0)')
+            _lib.check(lib.vd_tc_bwd_col2im(0, _lib.ptr(col), None, _lib.ptr(dvideo[s:e]), plan, n, st), 'vd_tc_bwd_col2im(0)')
+        return dvideo
+
+    def embed_autograd(self, video):
+        """Differentiable embed (gradient flows to ``video`` only; the net is frozen as in DM)."""
+        return _TcEmbed.apply(video, self)
 
     def _buffers(self, n):
         p = self.plan
@@ -75,6 +133,16 @@ class TcConvNet3D:
 
     # ---------------------------------------------------------------- layers
     def conv_layer(self, layer, src, wimg, bias, out, B, code=None, item_index=None, raw=False):
+        ev = None
+        if self.timing is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
+        self._conv_layer(layer, src, wimg, bias, out, B, code, item_index, raw)
+        if ev is not None:
+            ev[1].record()
+            self.timing.append((layer, int(B), ev[0], ev[1]))
+
+    def _conv_layer(self, layer, src, wimg, bias, out, B, code=None, item_index=None, raw=False):
         _lib.check(_lib.lib().vd_tc_conv_layer(layer, _lib.ptr(src), _lib.ptr(wimg), _lib.ptr(bias), _lib.ptr(out),
                                                _lib.ptr(code), ctypes.byref(self.plan), _lib.ptr(item_index),
                                                int(B), int(bool(raw)), _lib.stream()), f'vd_tc_conv_layer({layer})')
@@ -109,3 +177,16 @@ class TcConvNet3D:
             cc = tuple(c[s:e] for c in codes) if codes is not None else None
             self.embed_packed(x0, e - s, out=out[s:e], codes=cc)
         return (out, codes) if want_codes else out
+
+
+class _TcEmbed(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, video, net):
+        emb, codes = net.embed(video.contiguous(), want_codes=True)
+        ctx.net, ctx.codes = net, codes
+        return emb
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_emb):
+        return ctx.net.embed_backward(g_emb, ctx.codes), None
