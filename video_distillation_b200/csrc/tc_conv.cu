@@ -322,53 +322,80 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (one thread) =====================
-        if (lane == 0) {
-            uint32_t pslot = 0, pphase = 0, wslot = 0, wphase = 0, as = 0, aphase = 0;
-            const uint32_t a_hi = p.a_hi ? p.a_hi : ((p.a_sbo16 & 0x3FFFu) | (1u << 14));
-            const uint32_t b_hi = p.b_hi ? p.b_hi : (8u | (1u << 14));
-            if (p.w_resident) { mbar_wait(BAR(w_res, 0), 0); tc_fence_after(); }
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-              // n_u > 1 (column GEMM): one pixel stage per tile, reused by every accumulator group
-              for (int u = 0; u < p.n_u; ++u) {
+        // ===================== MMA issuer =====================
+        // The whole warp runs this loop with uniform control flow and ONE elected lane issues the
+        // tcgen05 instructions (operands stay in uniform registers).  Per-step descriptor words are
+        // kept in registers (lane l holds steps l and l+32) and broadcast with a shuffle, so a step
+        // costs a handful of integer ops: the issue rate must beat one MMA per N/2 cycles.
+        uint32_t pslot = 0, pphase = 0, wslot = 0, wphase = 0, as = 0, aphase = 0;
+        const uint32_t a_hi = p.a_hi ? p.a_hi : ((p.a_sbo16 & 0x3FFFu) | (1u << 14));
+        const uint32_t b_hi = p.b_hi ? p.b_hi : (8u | (1u << 14));
+        const uint32_t a_lbo_bits = (p.a_lbo16 & 0x3FFFu) << 16;
+        const int n_steps = p.n_steps;
+        const uint32_t tb0 = (lane < n_steps) ? (p.b_off16[lane] | ((p.b_lbo16[lane] & 0x3FFFu) << 16)) : 0u;
+        const uint32_t tb1 = (lane + 32 < n_steps) ? (p.b_off16[lane + 32] | ((p.b_lbo16[lane + 32] & 0x3FFFu) << 16)) : 0u;
+        const uint32_t ta0 = (lane < n_steps) ? p.a_off16[lane] : 0u;
+        const uint32_t ta1 = (lane + 32 < n_steps) ? p.a_off16[lane + 32] : 0u;
+        const bool resident = p.w_resident != 0;
+        const int G = resident ? n_steps : p.G;
+        const int slots_per_stage = (n_steps + G - 1) / G;
+        const int n_acc = p.n_acc;
+        const uint32_t acc_cols = p.acc_cols, acc_delta16 = p.acc_delta16, idesc = p.idesc;
+        const uint32_t slot_bytes = (uint32_t)G * kWeightTileBytes;
+        if (resident) { mbar_wait(BAR(w_res, 0), 0); tc_fence_after(); }
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            // n_u > 1 (column GEMM): one pixel stage per tile, reused by every accumulator group
+            for (int u = 0; u < p.n_u; ++u) {
                 mbar_wait(BAR(acc_empty, as), aphase ^ 1);
                 tc_fence_after();
-                const uint32_t d_base = tmem_base + as * (p.acc_cols * (uint32_t)p.n_acc);
+                const uint32_t d_base = tmem_base + as * (acc_cols * (uint32_t)n_acc);
                 uint32_t accumulate = 0;
-                for (int sa = 0; sa < p.n_sa; ++sa)
+                for (int sa = 0; sa < p.n_sa; ++sa) {
+                    const uint32_t a_stage16 = (smem_w >> 4) + (uint32_t)(sa * p.a_sa_stride16);
                     for (int sb = 0; sb < p.n_sb; ++sb) {
                         if (u == 0) { mbar_wait(BAR(pix_full, pslot), pphase); tc_fence_after(); }
                         const uint32_t pix16 = (smem_pix + pslot * p.stage_pitch) >> 4;
-                        for (int j = 0; j < p.n_steps; ++j) {
-                            uint32_t a16;
-                            if (p.w_resident) {
-                                a16 = (smem_w >> 4) + p.a_off16[j] + (uint32_t)(sa * p.a_sa_stride16);
-                            } else {
-                                const int jj = j % p.G;
-                                if (jj == 0) { mbar_wait(BAR(w_full, wslot), wphase); tc_fence_after(); }
-                                a16 = ((smem_w + wslot * (uint32_t)p.G * kWeightTileBytes) >> 4) + (uint32_t)jj * (kWeightTileBytes >> 4);
+                        int j = 0;
+                        for (int g = 0; g < slots_per_stage; ++g) {
+                            const int nst = min(G, n_steps - j);
+                            uint32_t a16 = a_stage16;
+                            if (!resident) {
+                                mbar_wait(BAR(w_full, wslot), wphase);
+                                tc_fence_after();
+                                a16 = (smem_w + wslot * slot_bytes) >> 4;
                             }
-                            const uint64_t a_desc = ((uint64_t)a_hi << 32) | (a16 & 0x3FFFu) | ((p.a_lbo16 & 0x3FFFu) << 16);
-                            const uint32_t b16 = pix16 + p.b_off16[j];
-                            const uint32_t lbo = p.b_lbo16[j];
-                            for (int a = 0; a < p.n_acc; ++a) {
-                                const uint64_t b_desc = ((uint64_t)b_hi << 32) | ((b16 + (uint32_t)a * p.acc_delta16) & 0x3FFFu) | ((lbo & 0x3FFFu) << 16);
-                                umma_bf16(d_base + (uint32_t)a * p.acc_cols, a_desc, b_desc, p.idesc, accumulate);
+                            for (int jj = 0; jj < nst; ++jj, ++j) {
+                                const uint32_t tb = __shfl_sync(0xffffffffu, (j & 32) ? tb1 : tb0, j & 31);
+                                uint32_t a_lo;
+                                if (resident) {
+                                    const uint32_t ta = __shfl_sync(0xffffffffu, (j & 32) ? ta1 : ta0, j & 31);
+                                    a_lo = ((a16 + ta) & 0x3FFFu) | a_lbo_bits;
+                                } else {
+                                    a_lo = ((a16 + (uint32_t)jj * (kWeightTileBytes >> 4)) & 0x3FFFu) | a_lbo_bits;
+                                }
+                                const uint32_t b_lo = tb + pix16;          // off16 + pix16 < 2^14: no carry into the LBO field
+                                if (elect_one()) {
+                                    const uint64_t a_desc = ((uint64_t)a_hi << 32) | a_lo;
+                                    for (int a = 0; a < n_acc; ++a) {
+                                        const uint64_t b_desc = ((uint64_t)b_hi << 32) | (b_lo + (uint32_t)a * acc_delta16);
+                                        umma_bf16(d_base + (uint32_t)a * acc_cols, a_desc, b_desc, idesc, accumulate);
+                                    }
+                                }
+                                accumulate = 1;
                             }
-                            accumulate = 1;
-                            if (!p.w_resident && ((j % p.G) == p.G - 1 || j == p.n_steps - 1)) {
-                                umma_commit(BAR(w_empty, wslot));
+                            if (!resident) {
+                                if (elect_one()) umma_commit(BAR(w_empty, wslot));
                                 if (++wslot == (uint32_t)p.RW) { wslot = 0; wphase ^= 1; }
                             }
                         }
                         if (u == p.n_u - 1) {
-                            umma_commit(BAR(pix_empty, pslot));
+                            if (elect_one()) umma_commit(BAR(pix_empty, pslot));
                             if (++pslot == (uint32_t)p.RP) { pslot = 0; pphase ^= 1; }
                         }
                     }
-                umma_commit(BAR(acc_full, as));
+                }
+                if (elect_one()) umma_commit(BAR(acc_full, as));
                 if (++as == p.acc_stages) { as = 0; aphase ^= 1; }
-              }
             }
         }
     } else if (warp >= 4) {
