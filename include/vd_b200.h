@@ -216,6 +216,11 @@ int vd_tc_probe(const void* pix, const void* wimg, float* raw, int ncols, int n_
                 uint32_t a_lbo16, uint32_t a_hi, uint32_t b_lbo16, uint32_t b_hi, uint32_t b_step16,
                 int n_acc, void* stream);
 
+/* Hardware-floor probe: `grid` CTAs each issue iters x n_acc MMAs (M=128, N=ncols, K=16) from constant
+ * descriptors; out[2*cta] = issue cycles, out[2*cta+1] = cycles until all MMAs completed. */
+int vd_tc_mma_rate(long long* out, int n_acc, int ncols, int iters, uint32_t a_hi, uint32_t b_hi, uint32_t lbo16,
+                   int vary, int grid, void* stream);
+
 /* Host-only introspection (no GPU work): the launch parameters vd_tc_conv_layer would use,
  * flattened to int64 (layout documented in tests/tc_emulator.py); cap >= 248. */
 int vd_tc_debug_params(int layer, const vd_tc_plan* plan, int B, int64_t* out, int cap);   /* layer 3,4,5 = bwd gemm of conv 0,1,2 */

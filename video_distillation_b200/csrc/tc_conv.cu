@@ -76,8 +76,8 @@ struct __align__(8) Barriers {
     uint32_t tmem_base;
     uint32_t pad;
 };
-constexpr uint32_t kBarBytes = 256;
-static_assert(sizeof(Barriers) <= kBarBytes, "barrier block too large");
+constexpr uint32_t kBarBytes = 1024;     // barriers (256 B) + MMA step table (64 x 8 B)
+static_assert(sizeof(Barriers) <= 256, "barrier block too large");
 
 // ------------------------------------------------------------------------------------------
 // epilogues.  Thread `m` (0..127) owns TMEM lane m.  taddr = tmem base of the accumulator stage
@@ -240,7 +240,7 @@ __device__ __forceinline__ void epi_l2(const WsParams& p, int tile, uint32_t tad
 }
 
 // ------------------------------------------------------------------------------------------
-template <int EPI>
+template <int EPI, int NACC>
 __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_constant__ WsParams p) {
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte aligned carve-up: [barriers 256 B][weights][pixel ring]
@@ -323,23 +323,24 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        // The whole warp runs this loop with uniform control flow and ONE elected lane issues the
-        // tcgen05 instructions (operands stay in uniform registers).  Per-step descriptor words are
-        // kept in registers (lane l holds steps l and l+32) and broadcast with a shuffle, so a step
-        // costs a handful of integer ops: the issue rate must beat one MMA per N/2 cycles.
+        // Issue-rate critical: one MMA must leave every N/2 cycles.  Per-step descriptor words are
+        // precomputed into a shared-memory table; the warp stays converged for the barrier waits
+        // and ONE elected lane runs the inner step loop (a table load, two adds and NACC
+        // tcgen05.mma per step), then commits.
+        uint2* tab = reinterpret_cast<uint2*>(base_ptr + 256);
+        const bool resident = p.w_resident != 0;
+        const int n_steps = p.n_steps;
+        const int G = resident ? n_steps : p.G;
+        for (int s = lane; s < n_steps; s += 32) {
+            const uint32_t a_rel = resident ? p.a_off16[s] : (uint32_t)(s % G) * (kWeightTileBytes >> 4);
+            tab[s] = make_uint2(a_rel, p.b_off16[s] | ((p.b_lbo16[s] & 0x3FFFu) << 16));
+        }
+        __syncwarp();
         uint32_t pslot = 0, pphase = 0, wslot = 0, wphase = 0, as = 0, aphase = 0;
         const uint32_t a_hi = p.a_hi ? p.a_hi : ((p.a_sbo16 & 0x3FFFu) | (1u << 14));
         const uint32_t b_hi = p.b_hi ? p.b_hi : (8u | (1u << 14));
         const uint32_t a_lbo_bits = (p.a_lbo16 & 0x3FFFu) << 16;
-        const int n_steps = p.n_steps;
-        const uint32_t tb0 = (lane < n_steps) ? (p.b_off16[lane] | ((p.b_lbo16[lane] & 0x3FFFu) << 16)) : 0u;
-        const uint32_t tb1 = (lane + 32 < n_steps) ? (p.b_off16[lane + 32] | ((p.b_lbo16[lane + 32] & 0x3FFFu) << 16)) : 0u;
-        const uint32_t ta0 = (lane < n_steps) ? p.a_off16[lane] : 0u;
-        const uint32_t ta1 = (lane + 32 < n_steps) ? p.a_off16[lane + 32] : 0u;
-        const bool resident = p.w_resident != 0;
-        const int G = resident ? n_steps : p.G;
         const int slots_per_stage = (n_steps + G - 1) / G;
-        const int n_acc = p.n_acc;
         const uint32_t acc_cols = p.acc_cols, acc_delta16 = p.acc_delta16, idesc = p.idesc;
         const uint32_t slot_bytes = (uint32_t)G * kWeightTileBytes;
         if (resident) { mbar_wait(BAR(w_res, 0), 0); tc_fence_after(); }
@@ -348,7 +349,7 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
             for (int u = 0; u < p.n_u; ++u) {
                 mbar_wait(BAR(acc_empty, as), aphase ^ 1);
                 tc_fence_after();
-                const uint32_t d_base = tmem_base + as * (acc_cols * (uint32_t)n_acc);
+                const uint32_t d_base = tmem_base + as * (acc_cols * (uint32_t)NACC);
                 uint32_t accumulate = 0;
                 for (int sa = 0; sa < p.n_sa; ++sa) {
                     const uint32_t a_stage16 = (smem_w >> 4) + (uint32_t)(sa * p.a_sa_stride16);
@@ -364,37 +365,34 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
                                 tc_fence_after();
                                 a16 = (smem_w + wslot * slot_bytes) >> 4;
                             }
-                            for (int jj = 0; jj < nst; ++jj, ++j) {
-                                const uint32_t tb = __shfl_sync(0xffffffffu, (j & 32) ? tb1 : tb0, j & 31);
-                                uint32_t a_lo;
-                                if (resident) {
-                                    const uint32_t ta = __shfl_sync(0xffffffffu, (j & 32) ? ta1 : ta0, j & 31);
-                                    a_lo = ((a16 + ta) & 0x3FFFu) | a_lbo_bits;
-                                } else {
-                                    a_lo = ((a16 + (uint32_t)jj * (kWeightTileBytes >> 4)) & 0x3FFFu) | a_lbo_bits;
-                                }
-                                const uint32_t b_lo = tb + pix16;          // off16 + pix16 < 2^14: no carry into the LBO field
-                                if (elect_one()) {
-                                    const uint64_t a_desc = ((uint64_t)a_hi << 32) | a_lo;
-                                    for (int a = 0; a < n_acc; ++a) {
+                            if (elect_one()) {
+                                const uint2* t = tab + j;
+#pragma unroll 4
+                                for (int jj = 0; jj < nst; ++jj) {
+                                    const uint2 e = t[jj];
+                                    // off16 + base16 < 2^14 (smem < 256 KiB): no carry into the LBO field
+                                    const uint64_t a_desc = ((uint64_t)a_hi << 32) | (((a16 + e.x) & 0x3FFFu) | a_lbo_bits);
+                                    const uint32_t b_lo = e.y + pix16;
+#pragma unroll
+                                    for (int a = 0; a < NACC; ++a) {
                                         const uint64_t b_desc = ((uint64_t)b_hi << 32) | (b_lo + (uint32_t)a * acc_delta16);
                                         umma_bf16(d_base + (uint32_t)a * acc_cols, a_desc, b_desc, idesc, accumulate);
                                     }
+                                    accumulate = 1;
                                 }
-                                accumulate = 1;
+                                if (!resident) umma_commit(BAR(w_empty, wslot));
+                                if (g == slots_per_stage - 1 && u == p.n_u - 1) umma_commit(BAR(pix_empty, pslot));
                             }
-                            if (!resident) {
-                                if (elect_one()) umma_commit(BAR(w_empty, wslot));
-                                if (++wslot == (uint32_t)p.RW) { wslot = 0; wphase ^= 1; }
-                            }
+                            __syncwarp();
+                            accumulate = 1;
+                            j += nst;
+                            if (!resident) { if (++wslot == (uint32_t)p.RW) { wslot = 0; wphase ^= 1; } }
                         }
-                        if (u == p.n_u - 1) {
-                            if (elect_one()) umma_commit(BAR(pix_empty, pslot));
-                            if (++pslot == (uint32_t)p.RP) { pslot = 0; pphase ^= 1; }
-                        }
+                        if (u == p.n_u - 1) { if (++pslot == (uint32_t)p.RP) { pslot = 0; pphase ^= 1; } }
                     }
                 }
                 if (elect_one()) umma_commit(BAR(acc_full, as));
+                __syncwarp();
                 if (++as == p.acc_stages) { as = 0; aphase ^= 1; }
             }
         }
@@ -559,12 +557,12 @@ static int setup_bwd(WsParams& p, const Geo& g, int layer, int B, uint32_t* smem
     return finalize_smem(p, (uint32_t)p.G * p.RW * kWeightTileBytes, smem);
 }
 
-template <int EPI>
-static int launch(const WsParams& p, uint32_t smem, cudaStream_t stream) {
+template <int EPI, int NACC>
+static int launch_n(const WsParams& p, uint32_t smem, cudaStream_t stream) {
     static bool configured = false;
     static int sm_count = 148;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(ws_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        cudaError_t e = cudaFuncSetAttribute(ws_gemm_kernel<EPI, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(ws_gemm): %s", cudaGetErrorString(e)); return (int)e; }
         int dev = 0; cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
@@ -572,8 +570,25 @@ static int launch(const WsParams& p, uint32_t smem, cudaStream_t stream) {
     }
     if (p.n_tiles <= 0) return 0;
     const int grid = p.n_tiles < sm_count ? p.n_tiles : sm_count;
-    ws_gemm_kernel<EPI><<<grid, kThreads, smem, stream>>>(p);
+    ws_gemm_kernel<EPI, NACC><<<grid, kThreads, smem, stream>>>(p);
     return check_launch("tc ws_gemm");
+}
+
+template <int EPI>
+static int launch(const WsParams& p, uint32_t smem, cudaStream_t stream) {
+    if (EPI == EPI_RAW) {
+        if (p.n_acc == 1) return launch_n<EPI_RAW, 1>(p, smem, stream);
+        if (p.n_acc == 2) return launch_n<EPI_RAW, 2>(p, smem, stream);
+        if (p.n_acc == 4) return launch_n<EPI_RAW, 4>(p, smem, stream);
+    } else if (EPI == EPI_L0 && p.n_acc == 1) {
+        return launch_n<EPI_L0, 1>(p, smem, stream);
+    } else if (EPI == EPI_L1 && p.n_acc == 2) {
+        return launch_n<EPI_L1, 2>(p, smem, stream);
+    } else if (EPI == EPI_L2 && p.n_acc == 4) {
+        return launch_n<EPI_L2, 4>(p, smem, stream);
+    }
+    set_error("tc ws_gemm: no kernel instance for epilogue %d with %d accumulators", EPI, p.n_acc);
+    return -1;
 }
 
 }  // namespace tc
