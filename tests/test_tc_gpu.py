@@ -204,3 +204,15 @@ def test_backward_matches_routed_fp32(T, HW):
     if r > 2e-2:
         dump(f'bwd_{T}_{HW}.npz', got=v.grad, want=x.grad)
     assert r < 2e-2, r
+
+
+def test_resident_prepacked_dataset_matches_per_step_packing():
+    """item_index of conv 0 over a pre-packed resident set == packing the gathered videos each step."""
+    T, HW = 8, 64
+    net, _ = make_net(T, HW)
+    videos = torch.randn(7, T, 3, HW, HW, generator=torch.Generator().manual_seed(8)).cuda()
+    idx = torch.tensor([5, 0, 3, 3, 6], device='cuda')
+    x0_all = net.pack_dataset(videos, chunk=3)
+    a = net.embed_resident(x0_all, idx)
+    b = net.embed(videos, index=idx)
+    assert torch.equal(a, b)

@@ -65,6 +65,7 @@ struct WsParams {
     uint32_t ncols, acc_cols, acc_stages;
     uint32_t idesc;
     uint32_t smem_w_off, smem_pix_off;  // from the 1024-aligned dynamic smem base
+    uint32_t smem_epi_off;              // != 0: 4 x 32 x 33 float transpose scratch for coalesced raw stores
     EpiParams epi;
 };
 
@@ -83,15 +84,35 @@ static_assert(sizeof(Barriers) <= 256, "barrier block too large");
 // epilogues.  Thread `m` (0..127) owns TMEM lane m.  taddr = tmem base of the accumulator stage
 // with the lane quarter already folded in.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void epi_raw(const WsParams& p, int tile, int u, uint32_t taddr, int m) {
+__device__ __forceinline__ void epi_raw(const WsParams& p, int tile, int u, uint32_t taddr, int m, float* scratch) {
     for (int a = 0; a < p.n_acc; ++a) {
-        float* dst = p.epi.raw + ((((int64_t)tile * p.n_u + u) * p.n_acc + a) * 128 + m) * p.ncols;
-        for (uint32_t c = 0; c < p.ncols; c += 8) {
-            float v[8];
-            tmem_ld8(taddr + a * p.acc_cols + c, v);
-            tmem_ld_wait();
+        float* tile_base = p.epi.raw + (((int64_t)tile * p.n_u + u) * p.n_acc + a) * 128 * (int64_t)p.ncols;
+        if (scratch == nullptr) {                      // bring-up path (forward layers in raw mode): row per thread
+            float* dst = tile_base + (int64_t)m * p.ncols;
+            for (uint32_t c = 0; c < p.ncols; c += 8) {
+                float v[8];
+                tmem_ld8(taddr + a * p.acc_cols + c, v);
+                tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 8; ++i) dst[c + i] = v[i];
+                for (int i = 0; i < 8; ++i) dst[c + i] = v[i];
+            }
+        } else {                                       // coalesced: transpose 32x32 blocks through shared memory
+            const int lane = m & 31;
+            float* s = scratch + (m >> 5) * (32 * 33);
+            float* rows = tile_base + (int64_t)(m & ~31) * p.ncols;
+            for (uint32_t c0 = 0; c0 < p.ncols; c0 += 32) {
+                float v[32];
+                tmem_ld32(taddr + a * p.acc_cols + c0, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) s[lane * 33 + i] = v[i];
+                __syncwarp();
+                if (c0 + lane < p.ncols) {
+#pragma unroll 8
+                    for (int r = 0; r < 32; ++r) rows[(int64_t)r * p.ncols + c0 + lane] = s[r * 33 + lane];
+                }
+                __syncwarp();
+            }
         }
     }
 }
@@ -406,7 +427,7 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
                 mbar_wait(BAR(acc_full, as), aphase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * (p.acc_cols * (uint32_t)p.n_acc);
-                if (EPI == EPI_RAW) epi_raw(p, tile, u, taddr, m);
+                if (EPI == EPI_RAW) epi_raw(p, tile, u, taddr, m, p.smem_epi_off ? reinterpret_cast<float*>(base_ptr + p.smem_epi_off) : nullptr);
                 else if (EPI == EPI_L0) epi_l0(p, tile, taddr, m);
                 else if (EPI == EPI_L1) epi_l1(p, tile, taddr, m);
                 else epi_l2(p, tile, taddr, m);
@@ -431,11 +452,14 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
 // ------------------------------------------------------------------------------------------
 static uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
 
-static int finalize_smem(WsParams& p, uint32_t w_region, uint32_t* smem_total) {
+static int finalize_smem(WsParams& p, uint32_t w_region, uint32_t* smem_total, bool epi_scratch = false) {
     p.smem_w_off = kBarBytes;
     p.smem_pix_off = align_up(kBarBytes + w_region, 128);
     p.stage_pitch = align_up(p.stage_bytes + 16, 128);
-    uint32_t total = p.smem_pix_off + (uint32_t)p.RP * p.stage_pitch + 1024;   // +1024: manual alignment slack
+    uint32_t total = p.smem_pix_off + (uint32_t)p.RP * p.stage_pitch;
+    p.smem_epi_off = 0;
+    if (epi_scratch) { p.smem_epi_off = align_up(total, 128); total = p.smem_epi_off + 4 * 32 * 33 * 4; }
+    total += 1024;                                  // manual 1024-byte alignment slack
     if (total < 120 * 1024) total = 120 * 1024;     // one CTA per SM: every CTA allocates all 512 TMEM columns
     VD_REQUIRE(total <= 232448, "tc conv: shared memory budget exceeded (%u bytes)", total);
     *smem_total = total;
@@ -554,7 +578,7 @@ static int setup_bwd(WsParams& p, const Geo& g, int layer, int B, uint32_t* smem
     p.n_acc = 1; p.acc_delta16 = 0;
     p.ncols = b.NC; p.acc_cols = 256; p.acc_stages = 2;
     p.idesc = umma_idesc_bf16(128, b.NC);
-    return finalize_smem(p, (uint32_t)p.G * p.RW * kWeightTileBytes, smem);
+    return finalize_smem(p, (uint32_t)p.G * p.RW * kWeightTileBytes, smem, true);
 }
 
 template <int EPI, int NACC>

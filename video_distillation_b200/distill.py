@@ -75,6 +75,7 @@ class DeviceDataset:
         idx = torch.as_tensor(keep, dtype=torch.long)
         self.videos = videos[idx].to(self.device, non_blocking=True).contiguous()
         self.shape = tuple(videos.shape[1:])
+        self.x0 = None
 
     @classmethod
     def from_device_shard(cls, shard_videos, labels, num_classes, device, rank=0, world=1):
@@ -95,6 +96,15 @@ class DeviceDataset:
         self.device = torch.device(device)
         self.videos = shard_videos.contiguous()
         self.shape = tuple(shard_videos.shape[1:])
+        self.x0 = None
+        return self
+
+    def prepack(self, tc_net, free_fp32=False):
+        """Convert the resident set once into the tensor-core path's packed bf16 conv-0 operand
+        (device-resident real-data pipeline); per-iteration packing disappears."""
+        self.x0 = tc_net.pack_dataset(self.videos)
+        if free_fp32:
+            self.videos = None
         return self
 
     def sample_all_classes(self, n):
@@ -158,8 +168,10 @@ class _RealEmbedder:
             self.tc.load_weights(f[0].weight, f[0].bias, f[3].weight, f[3].bias, f[6].weight, f[6].bias)
 
     @torch.no_grad()
-    def __call__(self, videos, index):
+    def __call__(self, videos, index, x0=None):
         if self.tc is not None:
+            if x0 is not None:
+                return self.tc.embed_resident(x0, index)
             return self.tc.embed(videos, index=index)
         out = []
         for s in range(0, index.numel(), self.max_batch):
@@ -237,7 +249,7 @@ class DMS2DTrainer:
         image_syn = self.hal.compose(self.static_syn, self.dynamic_syn, static_idx[sel], label[sel], dynamic_idx[sel])
         if real_batch is None:
             ridx = self.ds.local_index(real_idx[own])                       # (n_own*batch_real,)
-            emb_real = self.embedder(self.ds.videos, ridx)                  # (n_own*batch_real, D)
+            emb_real = self.embedder(self.ds.videos, ridx, x0=self.ds.x0)   # (n_own*batch_real, D)
         else:
             ridx = torch.arange(real_batch.shape[0], device=self.device)
             emb_real = self.embedder(real_batch, ridx)

@@ -164,6 +164,26 @@ class TcConvNet3D:
         return (torch.empty(B, 64, p.T1p, p.H1p, p.W1p, **u8), torch.empty(B, 128, p.T2p, p.H2p, p.W2p, **u8),
                 torch.empty(B, 128, p.T3p, p.H3p, p.W3p, **u8))
 
+    def pack_dataset(self, videos, chunk=256):
+        """One-time conversion of a resident fp32 real set (N,T,3,H,W) into the packed conv-0 operand
+        (bf16, 'kw-expanded'); afterwards ``embed_resident`` reads it in place through item_index."""
+        N = int(videos.shape[0])
+        x0 = torch.empty(N * self.plan.x0_bytes_per_video, dtype=torch.uint8, device=self.device)
+        per = self.plan.x0_bytes_per_video
+        for s in range(0, N, chunk):
+            e = min(N, s + chunk)
+            self.pack_video(videos[s:e], out=x0[s * per:e * per])
+        return x0
+
+    def embed_resident(self, x0_all, index):
+        """embed of the videos ``index`` (device int64) of a pre-packed resident set."""
+        B = int(index.numel())
+        out = torch.empty(B, self.embed_dim, dtype=torch.float32, device=self.device)
+        for s in range(0, B, self.max_batch):
+            e = min(B, s + self.max_batch)
+            self.embed_packed(x0_all, e - s, item_index=index[s:e].contiguous(), out=out[s:e])
+        return out
+
     def embed(self, video, index=None, want_codes=False):
         """ConvNet3D.embed on fp32 videos (B,T,3,H,W) -> (B, embed_dim) fp32, in chunks of max_batch."""
         B = int(index.numel()) if index is not None else int(video.shape[0])
