@@ -96,7 +96,10 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate));
+    // no "memory" clobber on purpose: ordering against the mbarrier waits comes from
+    // tcgen05.fence::after_thread_sync (which has one); a clobber here would forbid the compiler
+    // to hoist the next step's table loads above this instruction and serialise the issue loop.
 }
 // arrive on an mbarrier when every MMA previously issued by this thread has completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {

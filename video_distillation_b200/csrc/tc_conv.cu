@@ -388,18 +388,24 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
                             }
                             if (elect_one()) {
                                 const uint2* t = tab + j;
-#pragma unroll 4
-                                for (int jj = 0; jj < nst; ++jj) {
-                                    const uint2 e = t[jj];
-                                    // off16 + base16 < 2^14 (smem < 256 KiB): no carry into the LBO field
-                                    const uint64_t a_desc = ((uint64_t)a_hi << 32) | (((a16 + e.x) & 0x3FFFu) | a_lbo_bits);
-                                    const uint32_t b_lo = e.y + pix16;
+                                for (int j0 = 0; j0 < nst; j0 += 4) {
+                                    uint2 e[4];
 #pragma unroll
-                                    for (int a = 0; a < NACC; ++a) {
-                                        const uint64_t b_desc = ((uint64_t)b_hi << 32) | (b_lo + (uint32_t)a * acc_delta16);
-                                        umma_bf16(d_base + (uint32_t)a * acc_cols, a_desc, b_desc, idesc, accumulate);
+                                    for (int q = 0; q < 4; ++q) e[q] = t[min(j0 + q, nst - 1)];      // all loads first
+#pragma unroll
+                                    for (int q = 0; q < 4; ++q) {
+                                        if (j0 + q < nst) {
+                                            // off16 + base16 < 2^14 (smem < 256 KiB): no carry into the LBO field
+                                            const uint64_t a_desc = ((uint64_t)a_hi << 32) | (((a16 + e[q].x) & 0x3FFFu) | a_lbo_bits);
+                                            const uint32_t b_lo = e[q].y + pix16;
+#pragma unroll
+                                            for (int a = 0; a < NACC; ++a) {
+                                                const uint64_t b_desc = ((uint64_t)b_hi << 32) | (b_lo + (uint32_t)a * acc_delta16);
+                                                umma_bf16(d_base + (uint32_t)a * acc_cols, a_desc, b_desc, idesc, accumulate);
+                                            }
+                                            accumulate = 1;
+                                        }
                                     }
-                                    accumulate = 1;
                                 }
                                 if (!resident) umma_commit(BAR(w_empty, wslot));
                                 if (g == slots_per_stage - 1 && u == p.n_u - 1) umma_commit(BAR(pix_empty, pslot));

@@ -42,12 +42,17 @@ def allreduce_sum_(tensors):
     rank, world = _world()
     if world == 1:
         return tensors
-    flat = torch.cat([t.reshape(-1) for t in tensors])
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-    ofs = 0
+    small = [t for t in tensors if t.numel() < (1 << 16) or not t.is_contiguous()]
     for t in tensors:
-        t.copy_(flat[ofs:ofs + t.numel()].view_as(t))
-        ofs += t.numel()
+        if t.numel() >= (1 << 16) and t.is_contiguous():
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)            # big (dynamic-memory grad): in place, no staging copy
+    if small:
+        flat = torch.cat([t.reshape(-1) for t in small])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        ofs = 0
+        for t in small:
+            t.copy_(flat[ofs:ofs + t.numel()].view_as(t))
+            ofs += t.numel()
     return tensors
 
 
@@ -116,7 +121,10 @@ class DeviceDataset:
         """global video indices of owned classes -> rows of ``self.videos`` (device int64)."""
         loc = self.local_of_global[np.asarray(global_idx).reshape(-1)]
         assert (loc >= 0).all(), 'requested a video of a class this rank does not own'
-        return torch.as_tensor(loc, dtype=torch.long).to(self.device, non_blocking=True)
+        t = torch.from_numpy(np.ascontiguousarray(loc))
+        if self.device.type == 'cuda':
+            t = t.pin_memory()
+        return t.to(self.device, non_blocking=True)
 
     def get_images(self, c, n):
         """Reference-compatible accessor (one class)."""
@@ -144,6 +152,40 @@ def frozen_convnet3d(channel, num_classes, im_size, frames, device, seed=None, i
     for p in net.parameters():
         p.requires_grad = False
     return net
+
+
+class FrozenNetPool:
+    """The "fresh random frozen ConvNet3D per iteration" (distill_s2d_ms.py:393-396) without rebuilding
+    a module every step: one persistent ConvNet3D whose parameters are views of a flat device buffer;
+    ``fresh(seed)`` redraws the default init (weights and biases ~ U(+-1/sqrt(fan_in)), which is what
+    kaiming_uniform(a=sqrt 5) + the bias rule of nn.Conv3d reduce to) with two launches on the device
+    generator.  Same distribution as get_network, different random stream (device vs host)."""
+
+    def __init__(self, channel, num_classes, im_size, frames, device):
+        with torch.device(device):
+            self.net = ConvNet3D(channel, num_classes, 128, 3, 'relu', 'none', 'maxpooling', frames, im_size)
+        params = list(self.net.parameters())
+        self.flat = torch.empty(sum(p.numel() for p in params), dtype=torch.float32, device=device)
+        self.scale = torch.empty_like(self.flat)
+        ofs = 0
+        convs = [m for m in self.net.modules() if isinstance(m, torch.nn.Conv3d)]
+        for m in convs:
+            fan_in = m.weight.shape[1] * m.weight.shape[2] * m.weight.shape[3] * m.weight.shape[4]
+            for p in (m.weight, m.bias):
+                n = p.numel()
+                self.scale[ofs:ofs + n] = 1.0 / (fan_in ** 0.5)
+                p.data = self.flat[ofs:ofs + n].view_as(p)
+                p.requires_grad = False
+                ofs += n
+        assert ofs == self.flat.numel()
+        self.net.train()
+
+    def fresh(self, seed=None):
+        if seed is not None:
+            torch.cuda.manual_seed(int(seed))
+        self.flat.uniform_(-1.0, 1.0)
+        self.flat.mul_(self.scale)
+        return self.net
 
 
 class _RealEmbedder:
@@ -189,6 +231,8 @@ class DMS2DTrainer:
         self.rank, self.world = _world()
         self.ds = dataset
         self.init_on_device = init_on_device
+        self._pool = None
+        self._const = None
         # precision='bf16': synthetic branch forward + backward also on tensor cores (bf16 operands);
         # set False to keep the synthetic branch on the exact fp32 kernels (mixed mode).
         self.syn_on_tensor_cores = syn_on_tensor_cores
@@ -215,12 +259,16 @@ class DMS2DTrainer:
     def sample_syn_indices(self):
         """distill_s2d_ms.py:402-406 verbatim: two device randint draws of length C*vpc."""
         C, vpc, spc, dev = self.C, self.vpc, self.spc, self.device
-        label = torch.tensor(np.stack([np.ones(vpc) * i for i in range(0, C)]), dtype=torch.long,
-                             requires_grad=False, device=dev).view(-1)
-        ran = torch.arange(0, C * vpc).to(dev)
-        idx = ran % vpc
-        dynamic_idx = 2 * idx + torch.randint(2, (C * vpc,), device=dev)
-        static_idx = spc * label + 2 * idx + torch.randint(2, (C * vpc,), device=dev)
+        if getattr(self, '_const', None) is None:
+            # label / idx are the same every iteration: build them once (the two randint draws are not)
+            label = torch.tensor(np.stack([np.ones(vpc) * i for i in range(0, C)]), dtype=torch.long,
+                                 requires_grad=False, device=dev).view(-1)
+            ran = torch.arange(0, C * vpc).to(dev)
+            idx = ran % vpc
+            self._const = (label, 2 * idx, spc * label + 2 * idx)
+        label, idx2, sbase = self._const
+        dynamic_idx = idx2 + torch.randint(2, (C * vpc,), device=dev)
+        static_idx = sbase + torch.randint(2, (C * vpc,), device=dev)
         return label, dynamic_idx, static_idx
 
     def _sgd(self, name, p, grad, lr, momentum=0.95):
@@ -236,8 +284,12 @@ class DMS2DTrainer:
         (class-major, batch_real per owned class) — the host-streaming mode of bench.py."""
         C, vpc = self.C, self.vpc
         if net is None:
-            net = frozen_convnet3d(self.channel, C, self.im_size, self.frames, self.device, seed=net_seed,
-                                   init_on_device=self.init_on_device)
+            if self.init_on_device:
+                if self._pool is None:
+                    self._pool = FrozenNetPool(self.channel, C, self.im_size, self.frames, self.device)
+                net = self._pool.fresh(net_seed)
+            else:
+                net = frozen_convnet3d(self.channel, C, self.im_size, self.frames, self.device, seed=net_seed)
         self.embedder.load(net)
         label, dynamic_idx, static_idx = indices if indices is not None else self.sample_syn_indices()
         if real_idx is None:
