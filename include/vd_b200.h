@@ -157,7 +157,7 @@ typedef struct {
     /* backward (column-GEMM dgrad) operands, see vd_tc_bwd_* below */
     int64_t wt0_bytes, wt1_bytes, wt2_bytes;                 /* transposed weight images           */
     int64_t dy0_bytes_per_video, dy1_bytes_per_video, dy2_bytes_per_video;    /* packed output grads (bf16) */
-    int64_t col0_bytes_per_video, col1_bytes_per_video, col2_bytes_per_video; /* fp32 column buffers        */
+    int64_t col0_bytes_per_video, col1_bytes_per_video, col2_bytes_per_video; /* bf16 column buffers        */
     int32_t reserved[8];
 } vd_tc_plan;
 
@@ -196,7 +196,7 @@ int vd_tc_conv_layer(int layer, const void* in, const void* wimg, const float* b
  * (distill_s2d_ms.py:431).
  *   pack_weights_bwd : fp32 OIDHW -> transposed UMMA images [m-tile][step][k 2][128][8]
  *   bwd_emb    : g_emb (B, embed_dim) fp32 + code2 -> dy2
- *   bwd_gemm   : layer in {2,1,0}: dy_layer x wt_layer -> col_layer (fp32 [video][ntile][mtile][128][NC])
+ *   bwd_gemm   : layer in {2,1,0}: dy_layer x wt_layer -> col_layer (bf16 [video][ntile][mtile][128][NC])
  *   bwd_col2im : layer 2: col2 + code1 -> dy1;  layer 1: col1 + code0 -> dy0;
  *                layer 0: col0 -> d video (B, T, 3, H, W) fp32 (code must be NULL)
  */
@@ -204,9 +204,9 @@ int vd_tc_pack_weights_bwd(const float* w_l0, const float* w_l1, const float* w_
                            void* wt0, void* wt1, void* wt2, void* stream);
 int vd_tc_bwd_emb(const float* g_emb, const uint8_t* code2, void* dy2, const vd_tc_plan* plan,
                   int B, void* stream);
-int vd_tc_bwd_gemm(int layer, const void* dy, const void* wt, float* col, const vd_tc_plan* plan,
+int vd_tc_bwd_gemm(int layer, const void* dy, const void* wt, void* col, const vd_tc_plan* plan,
                    int B, void* stream);
-int vd_tc_bwd_col2im(int layer, const float* col, const uint8_t* code_below, void* out,
+int vd_tc_bwd_col2im(int layer, const void* col, const uint8_t* code_below, void* out,
                      const vd_tc_plan* plan, int B, void* stream);
 
 /* Tuning probe (tests/bring-up only): issues 148 x n_sa x n_steps x n_acc MMAs of N=ncols with the

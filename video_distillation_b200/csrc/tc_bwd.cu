@@ -60,7 +60,9 @@ __global__ void bwd_emb_kernel(const float* __restrict__ g_emb, const uint8_t* _
 }
 
 // dX[ci,t,h,w] of conv `b.layer` = sum over taps of col[(ci,tap)][pixel(t+1-kt, (h+3-kh)/2, (w+3-kw)/2)]
-__device__ __forceinline__ float col2im_gather(const float* __restrict__ colv, const BwdGeo& b, int ci, int t, int h, int w) {
+__device__ __forceinline__ float bf2f(uint16_t v) { return __uint_as_float((uint32_t)v << 16); }
+
+__device__ __forceinline__ float col2im_gather(const uint16_t* __restrict__ colv, const BwdGeo& b, int ci, int t, int h, int w) {
     float acc = 0.f;
     for (int kt = 0; kt < 3; ++kt) {
         const int to = t + 1 - kt;
@@ -77,8 +79,8 @@ __device__ __forceinline__ float col2im_gather(const float* __restrict__ colv, c
                 if (wo >= b.Wo) continue;
                 const int r = ci * 147 + (kt * 7 + kh) * 7 + kw;
                 const int pix = (to * b.Ho + ho) * b.Wo + wo;
-                const int nt = pix / b.NC, col = pix - nt * b.NC;
-                acc += __ldg(colv + (((int64_t)nt * b.NU + (r >> 7)) * 128 + (r & 127)) * b.NC + col);
+                const int nt = (int)__umulhi((uint32_t)pix, b.nc_magic), col = pix - nt * b.NC;
+                acc += bf2f(__ldg(colv + (((int64_t)nt * b.NU + (r >> 7)) * 128 + (r & 127)) * b.NC + col));
             }
         }
     }
@@ -88,7 +90,7 @@ __device__ __forceinline__ float col2im_gather(const float* __restrict__ colv, c
 // layers 2 and 1: one thread per POOLED element (ci,t,h,w) of the layer below; writes the whole
 // pool window (pt x 2 x 2 conv outputs) of the next dY: the routed gradient at the recorded
 // argmax, zeros elsewhere -> dY below is fully overwritten, no memset needed.
-__global__ void col2im_route_kernel(const float* __restrict__ colbuf, const uint8_t* __restrict__ code,
+__global__ void col2im_route_kernel(const uint16_t* __restrict__ colbuf, const uint8_t* __restrict__ code,
                                     uint16_t* __restrict__ dy_below, int64_t total, BwdGeo b, BwdGeo bb, int pt) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int w = (int)(i % b.Wi); int64_t q = i / b.Wi;
@@ -106,14 +108,14 @@ __global__ void col2im_route_kernel(const float* __restrict__ colbuf, const uint
             for (int dh = 0; dh < 2; ++dh)
                 for (int dw = 0; dw < 2; ++dw, ++pos) {
                     const int pix = ((t * pt + dt) * bb.Ho + (2 * h + dh)) * bb.Wo + 2 * w + dw;
-                    const int nt = pix / bb.NC, col = pix - nt * bb.NC;
+                    const int nt = (int)__umulhi((uint32_t)pix, bb.nc_magic), col = pix - nt * bb.NC;
                     base[(((int64_t)nt * (bb.K / 8) + chunk) * bb.NC + col) * 8 + e] = (pos == arg) ? gv : (uint16_t)0;
                 }
     }
 }
 
 // layer 0: d video (B, T, 3, H, W) fp32
-__global__ void col2im_video_kernel(const float* __restrict__ colbuf, float* __restrict__ dvideo, int64_t total, BwdGeo b) {
+__global__ void col2im_video_kernel(const uint16_t* __restrict__ colbuf, float* __restrict__ dvideo, int64_t total, BwdGeo b) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int w = (int)(i % b.Wi); int64_t q = i / b.Wi;
         int h = (int)(q % b.Hi); q /= b.Hi;
@@ -162,7 +164,7 @@ extern "C" int vd_tc_bwd_emb(const float* g_emb, const uint8_t* code2, void* dy2
     return check_launch("tc_bwd_emb");
 }
 
-extern "C" int vd_tc_bwd_col2im(int layer, const float* col, const uint8_t* code_below, void* out,
+extern "C" int vd_tc_bwd_col2im(int layer, const void* col, const uint8_t* code_below, void* out,
                                 const vd_tc_plan* plan, int B, void* stream) {
     VD_REQUIRE(col && out && plan, "tc_bwd_col2im: NULL pointer");
     VD_REQUIRE(layer >= 0 && layer <= 2, "tc_bwd_col2im: bad layer");
@@ -174,12 +176,12 @@ extern "C" int vd_tc_bwd_col2im(int layer, const float* col, const uint8_t* code
     cudaStream_t s = (cudaStream_t)stream;
     if (layer == 0) {
         const int64_t total = (int64_t)B * b.Ti * 3 * b.Hi * b.Wi;
-        col2im_video_kernel<<<blocks_for(total), 256, 0, s>>>(col, (float*)out, total, b);
+        col2im_video_kernel<<<blocks_for(total), 256, 0, s>>>((const uint16_t*)col, (float*)out, total, b);
         return check_launch("tc_bwd_col2im_video");
     }
     const BwdGeo bb = make_bwd_geo(g, layer - 1);
     const int pt = (layer == 2) ? 2 : 1;       // pool window of the layer below in T: conv1 -> (2,2,2), conv0 -> (1,2,2)
     const int64_t total = (int64_t)B * b.Cin * b.Ti * b.Hi * b.Wi;
-    col2im_route_kernel<<<blocks_for(total), 256, 0, s>>>(col, code_below, (uint16_t*)out, total, b, bb, pt);
+    col2im_route_kernel<<<blocks_for(total), 256, 0, s>>>((const uint16_t*)col, code_below, (uint16_t*)out, total, b, bb, pt);
     return check_launch("tc_bwd_col2im_route");
 }

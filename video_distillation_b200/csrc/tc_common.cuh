@@ -101,6 +101,24 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
     // tcgen05.fence::after_thread_sync (which has one); a clobber here would forbid the compiler
     // to hoist the next step's table loads above this instruction and serialise the issue loop.
 }
+// Same, for warp-uniform code: every lane executes the statement with identical (uniform) operands
+// and the instruction itself is predicated on elect.sync, so the C++ control flow stays convergent
+// and the operands can live in uniform registers (no per-MMA R2UR traffic).
+__device__ __forceinline__ void umma_bf16_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate));
+}
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(bar) : "memory");
+}
 // arrive on an mbarrier when every MMA previously issued by this thread has completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");

@@ -25,7 +25,8 @@ constexpr int kThreads = 256;
 enum EpiMode { EPI_RAW = 0, EPI_L0 = 1, EPI_L1 = 2, EPI_L2 = 3 };
 
 struct EpiParams {
-    float* raw;            // EPI_RAW: [tile][acc][128][ncols]
+    float* raw;            // EPI_RAW: [tile][u][acc][128][ncols]
+    int raw_bf16;          // EPI_RAW: store bf16 instead of fp32 (backward column buffers)
     const float* bias;     // per output channel (64 for conv 0, 128 otherwise)
     uint8_t* out;          // packed bf16 input of the next layer / fp32 embeddings
     uint8_t* code;         // optional ReLU/argmax routing codes, NCDHW order of the pooled tensor
@@ -54,6 +55,8 @@ struct WsParams {
     uint32_t b_off16[kMaxSteps];
     uint32_t b_lbo16[kMaxSteps];
     uint32_t a_off16[kMaxSteps];        // resident weights: offset of the tile of (sa=0, step)
+    uint2 step_tab[kMaxSteps];          // issue table: x = A offset (16 B units) inside the slot / resident image,
+                                        //              y = B offset | LBO << 16   (filled by finalize_smem)
     int32_t a_sa_stride16;              // resident weights: offset added per stage index
     uint32_t a_lbo16, a_sbo16;
     uint32_t a_hi, b_hi;                // upper descriptor words (SBO | version | layout type); 0 = default no-swizzle
@@ -77,7 +80,7 @@ struct __align__(8) Barriers {
     uint32_t tmem_base;
     uint32_t pad;
 };
-constexpr uint32_t kBarBytes = 1024;     // barriers (256 B) + MMA step table (64 x 8 B)
+constexpr uint32_t kBarBytes = 256;
 static_assert(sizeof(Barriers) <= 256, "barrier block too large");
 
 // ------------------------------------------------------------------------------------------
@@ -108,8 +111,15 @@ __device__ __forceinline__ void epi_raw(const WsParams& p, int tile, int u, uint
                 for (int i = 0; i < 32; ++i) s[lane * 33 + i] = v[i];
                 __syncwarp();
                 if (c0 + lane < p.ncols) {
+                    if (p.epi.raw_bf16) {
+                        uint16_t* rows16 = reinterpret_cast<uint16_t*>(p.epi.raw) +
+                                           ((((int64_t)tile * p.n_u + u) * p.n_acc + a) * 128 + (m & ~31)) * (int64_t)p.ncols;
 #pragma unroll 8
-                    for (int r = 0; r < 32; ++r) rows[(int64_t)r * p.ncols + c0 + lane] = s[r * 33 + lane];
+                        for (int r = 0; r < 32; ++r) rows16[(int64_t)r * p.ncols + c0 + lane] = f2bf(s[r * 33 + lane]);
+                    } else {
+#pragma unroll 8
+                        for (int r = 0; r < 32; ++r) rows[(int64_t)r * p.ncols + c0 + lane] = s[r * 33 + lane];
+                    }
                 }
                 __syncwarp();
             }
@@ -344,19 +354,14 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        // Issue-rate critical: one MMA must leave every N/2 cycles.  Per-step descriptor words are
-        // precomputed into a shared-memory table; the warp stays converged for the barrier waits
-        // and ONE elected lane runs the inner step loop (a table load, two adds and NACC
-        // tcgen05.mma per step), then commits.
-        uint2* tab = reinterpret_cast<uint2*>(base_ptr + 256);
+        // Issue-rate critical: tcgen05.mma issue blocks while the tensor pipe is busy, so the scalar
+        // work of a step must fit under one MMA (N/2 cycles).  The whole warp runs this loop with
+        // uniform control flow; per-step descriptor words come from the kernel-parameter table
+        // (constant bank -> uniform registers) and the instruction itself is predicated on
+        // elect.sync, so a step is one constant load, a few uniform adds and NACC tcgen05.mma.
         const bool resident = p.w_resident != 0;
         const int n_steps = p.n_steps;
         const int G = resident ? n_steps : p.G;
-        for (int s = lane; s < n_steps; s += 32) {
-            const uint32_t a_rel = resident ? p.a_off16[s] : (uint32_t)(s % G) * (kWeightTileBytes >> 4);
-            tab[s] = make_uint2(a_rel, p.b_off16[s] | ((p.b_lbo16[s] & 0x3FFFu) << 16));
-        }
-        __syncwarp();
         uint32_t pslot = 0, pphase = 0, wslot = 0, wphase = 0, as = 0, aphase = 0;
         const uint32_t a_hi = p.a_hi ? p.a_hi : ((p.a_sbo16 & 0x3FFFu) | (1u << 14));
         const uint32_t b_hi = p.b_hi ? p.b_hi : (8u | (1u << 14));
@@ -386,40 +391,33 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
                                 tc_fence_after();
                                 a16 = (smem_w + wslot * slot_bytes) >> 4;
                             }
-                            if (elect_one()) {
-                                const uint2* t = tab + j;
-                                for (int j0 = 0; j0 < nst; j0 += 4) {
-                                    uint2 e[4];
-#pragma unroll
-                                    for (int q = 0; q < 4; ++q) e[q] = t[min(j0 + q, nst - 1)];      // all loads first
-#pragma unroll
-                                    for (int q = 0; q < 4; ++q) {
-                                        if (j0 + q < nst) {
-                                            // off16 + base16 < 2^14 (smem < 256 KiB): no carry into the LBO field
-                                            const uint64_t a_desc = ((uint64_t)a_hi << 32) | (((a16 + e[q].x) & 0x3FFFu) | a_lbo_bits);
-                                            const uint32_t b_lo = e[q].y + pix16;
-#pragma unroll
-                                            for (int a = 0; a < NACC; ++a) {
-                                                const uint64_t b_desc = ((uint64_t)b_hi << 32) | (b_lo + (uint32_t)a * acc_delta16);
-                                                umma_bf16(d_base + (uint32_t)a * acc_cols, a_desc, b_desc, idesc, accumulate);
-                                            }
-                                            accumulate = 1;
-                                        }
-                                    }
-                                }
-                                if (!resident) umma_commit(BAR(w_empty, wslot));
-                                if (g == slots_per_stage - 1 && u == p.n_u - 1) umma_commit(BAR(pix_empty, pslot));
-                            }
                             __syncwarp();
-                            accumulate = 1;
+#pragma unroll 2
+                            for (int jj = 0; jj < nst; ++jj) {
+                                const uint2 e = p.step_tab[j + jj];
+                                // off16 + base16 < 2^14 (smem < 256 KiB): no carry into the LBO field
+                                const uint64_t a_desc = ((uint64_t)a_hi << 32) | (((a16 + e.x) & 0x3FFFu) | a_lbo_bits);
+                                const uint32_t b_lo = e.y + pix16;
+#pragma unroll
+                                for (int a = 0; a < NACC; ++a) {
+                                    const uint64_t b_desc = ((uint64_t)b_hi << 32) | (b_lo + (uint32_t)a * acc_delta16);
+                                    umma_bf16_elect(d_base + (uint32_t)a * acc_cols, a_desc, b_desc, idesc, accumulate);
+                                }
+                                accumulate = 1;
+                            }
                             j += nst;
-                            if (!resident) { if (++wslot == (uint32_t)p.RW) { wslot = 0; wphase ^= 1; } }
+                            if (!resident) {
+                                umma_commit_elect(BAR(w_empty, wslot));
+                                if (++wslot == (uint32_t)p.RW) { wslot = 0; wphase ^= 1; }
+                            }
                         }
-                        if (u == p.n_u - 1) { if (++pslot == (uint32_t)p.RP) { pslot = 0; pphase ^= 1; } }
+                        if (u == p.n_u - 1) {
+                            umma_commit_elect(BAR(pix_empty, pslot));
+                            if (++pslot == (uint32_t)p.RP) { pslot = 0; pphase ^= 1; }
+                        }
                     }
                 }
-                if (elect_one()) umma_commit(BAR(acc_full, as));
-                __syncwarp();
+                umma_commit_elect(BAR(acc_full, as));
                 if (++as == p.acc_stages) { as = 0; aphase ^= 1; }
             }
         }
@@ -459,6 +457,13 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
 static uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
 
 static int finalize_smem(WsParams& p, uint32_t w_region, uint32_t* smem_total, bool epi_scratch = false) {
+    {
+        const int G = p.w_resident ? p.n_steps : p.G;
+        for (int j = 0; j < p.n_steps; ++j) {
+            p.step_tab[j].x = p.w_resident ? p.a_off16[j] : (uint32_t)(j % G) * (kWeightTileBytes >> 4);
+            p.step_tab[j].y = p.b_off16[j] | ((p.b_lbo16[j] & 0x3FFFu) << 16);
+        }
+    }
     p.smem_w_off = kBarBytes;
     p.smem_pix_off = align_up(kBarBytes + w_region, 128);
     p.stage_pitch = align_up(p.stage_bytes + 16, 128);
@@ -648,8 +653,8 @@ extern "C" int vd_tc_plan_make(vd_tc_plan* plan, int T, int H, int W) {
     const BwdGeo b0 = make_bwd_geo(g, 0), b1 = make_bwd_geo(g, 1), b2 = make_bwd_geo(g, 2);
     plan->wt0_bytes = b0.wt_bytes; plan->wt1_bytes = b1.wt_bytes; plan->wt2_bytes = b2.wt_bytes;
     plan->dy0_bytes_per_video = b0.dy_video; plan->dy1_bytes_per_video = b1.dy_video; plan->dy2_bytes_per_video = b2.dy_video;
-    plan->col0_bytes_per_video = b0.col_video_elems * 4; plan->col1_bytes_per_video = b1.col_video_elems * 4;
-    plan->col2_bytes_per_video = b2.col_video_elems * 4;
+    plan->col0_bytes_per_video = b0.col_video_elems * 2; plan->col1_bytes_per_video = b1.col_video_elems * 2;
+    plan->col2_bytes_per_video = b2.col_video_elems * 2;      // bf16 column buffers
     return 0;
 }
 
@@ -710,7 +715,7 @@ extern "C" int vd_tc_debug_params(int layer, const vd_tc_plan* plan, int B, int6
     return 0;
 }
 
-extern "C" int vd_tc_bwd_gemm(int layer, const void* dy, const void* wt, float* col, const vd_tc_plan* plan,
+extern "C" int vd_tc_bwd_gemm(int layer, const void* dy, const void* wt, void* col, const vd_tc_plan* plan,
                               int B, void* stream) {
     VD_REQUIRE(plan && dy && wt && col, "tc_bwd_gemm: NULL pointer");
     VD_REQUIRE(layer >= 0 && layer <= 2 && B >= 0, "tc_bwd_gemm: bad layer / batch");
@@ -722,7 +727,7 @@ extern "C" int vd_tc_bwd_gemm(int layer, const void* dy, const void* wt, float* 
     uint32_t smem = 0;
     if (int rc = setup_bwd(p, g, layer, B, &smem)) return rc;
     p.pix = (const uint8_t*)dy; p.wimg = (const uint8_t*)wt; p.item_index = nullptr;
-    p.epi.raw = col; p.epi.T = plan->T; p.epi.n_items = B; p.epi.g = g;
+    p.epi.raw = (float*)col; p.epi.raw_bf16 = 1; p.epi.T = plan->T; p.epi.n_items = B; p.epi.g = g;
     return launch<EPI_RAW>(p, smem, (cudaStream_t)stream);
 }
 

@@ -107,6 +107,7 @@ struct BwdGeo {
     int To, Ho, Wo;            // output (dY) extent of this conv
     int Ti, Hi, Wi;            // input (dX) extent of this conv
     int64_t dy_video, col_video_elems, wt_bytes;
+    uint32_t nc_magic;         // ceil(2^32 / NC): pix / NC == __umulhi(pix, nc_magic) for pix < 2^16
 };
 
 inline BwdGeo make_bwd_geo(const Geo& g, int layer) {
@@ -121,6 +122,7 @@ inline BwdGeo make_bwd_geo(const Geo& g, int layer) {
     b.NC = 16;
     for (int c = 256; c >= 16; c -= 16) if (b.pixels % c == 0) { b.NC = c; break; }
     b.NT = b.pixels / b.NC;
+    b.nc_magic = (uint32_t)(((1ull << 32) + b.NC - 1) / b.NC);
     b.n_steps = b.K / 16;
     b.dy_video = (int64_t)b.NT * (b.K / 8) * b.NC * 16;
     b.col_video_elems = (int64_t)b.NT * b.NU * 128 * b.NC;

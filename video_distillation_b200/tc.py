@@ -41,7 +41,7 @@ class TcConvNet3D:
         self.wt2 = torch.empty(p.wt2_bytes, **u8)
         self._bwd_ready = False
         self._fp32_w = None
-        self.bwd_chunk = 8
+        self.bwd_chunk = 64
         self._ws = {}
         self.b0 = self.b1 = self.b2 = None
         self._x0 = None
@@ -93,8 +93,7 @@ class TcConvNet3D:
             dy2 = self._workspace('dy2', n * p.dy2_bytes_per_video)
             dy1 = self._workspace('dy1', n * p.dy1_bytes_per_video)
             dy0 = self._workspace('dy0', n * p.dy0_bytes_per_video)
-            col = self._workspace('col', n * max(p.col0_bytes_per_video, p.col1_bytes_per_video, p.col2_bytes_per_video),
-                                  torch.float32)
+            col = self._workspace('col', n * max(p.col0_bytes_per_video, p.col1_bytes_per_video, p.col2_bytes_per_video))
             st = _lib.stream()
             plan = ctypes.byref(p)
             _lib.check(lib.vd_tc_bwd_emb(_lib.ptr(g_emb[s:e]), _lib.ptr(c2[s:e]), _lib.ptr(dy2), plan, n, st), 'vd_tc_bwd_emb')
