@@ -219,7 +219,7 @@ int vd_tc_probe(const void* pix, const void* wimg, float* raw, int ncols, int n_
 /* Hardware-floor probe: `grid` CTAs each issue iters x n_acc MMAs (M=128, N=ncols, K=16) from constant
  * descriptors; out[2*cta] = issue cycles, out[2*cta+1] = cycles until all MMAs completed. */
 int vd_tc_mma_rate(long long* out, int n_acc, int ncols, int iters, uint32_t a_hi, uint32_t b_hi, uint32_t lbo16,
-                   int vary, int grid, void* stream);
+                   int vary, int grid, int delay, void* stream);   /* delay: emulated scalar cycles per step */
 
 /* Host-only introspection (no GPU work): the launch parameters vd_tc_conv_layer would use,
  * flattened to int64 (layout documented in tests/tc_emulator.py); cap >= 248. */

@@ -80,7 +80,7 @@ struct __align__(8) Barriers {
     uint32_t tmem_base;
     uint32_t pad;
 };
-constexpr uint32_t kBarBytes = 256;
+constexpr uint32_t kBarBytes = 4352;     // 256 B of barriers + 4 KiB of MMA descriptor tables
 static_assert(sizeof(Barriers) <= 256, "barrier block too large");
 
 // ------------------------------------------------------------------------------------------
@@ -354,21 +354,37 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        // Issue-rate critical: tcgen05.mma issue blocks while the tensor pipe is busy, so the scalar
-        // work of a step must fit under one MMA (N/2 cycles).  The whole warp runs this loop with
-        // uniform control flow; per-step descriptor words come from the kernel-parameter table
-        // (constant bank -> uniform registers) and the instruction itself is predicated on
-        // elect.sync, so a step is one constant load, a few uniform adds and NACC tcgen05.mma.
+        // Issue-rate critical.  Measured on B200 (scripts/mma_rate.py): the tensor pipe runs at
+        // exactly N/2 cycles per MMA and overlaps fully with the issuing thread, so a step is bound
+        // by max(MMA time, scalar instructions of the issue loop) — and a single warp retires only
+        // ~1 dependent instruction per 7-10 cycles.  Hence: every descriptor is precomputed ONCE
+        // into shared-memory tables (per pixel-ring slot / weight-ring slot), and the elected lane's
+        // inner loop is just table loads + tcgen05.mma.
         const bool resident = p.w_resident != 0;
         const int n_steps = p.n_steps;
         const int G = resident ? n_steps : p.G;
-        uint32_t pslot = 0, pphase = 0, wslot = 0, wphase = 0, as = 0, aphase = 0;
         const uint32_t a_hi = p.a_hi ? p.a_hi : ((p.a_sbo16 & 0x3FFFu) | (1u << 14));
         const uint32_t b_hi = p.b_hi ? p.b_hi : (8u | (1u << 14));
         const uint32_t a_lbo_bits = (p.a_lbo16 & 0x3FFFu) << 16;
-        const int slots_per_stage = (n_steps + G - 1) / G;
-        const uint32_t acc_cols = p.acc_cols, acc_delta16 = p.acc_delta16, idesc = p.idesc;
         const uint32_t slot_bytes = (uint32_t)G * kWeightTileBytes;
+        uint64_t* tabB = reinterpret_cast<uint64_t*>(base_ptr + 256);                   // [RP][n_steps][NACC]
+        uint64_t* tabA = tabB + p.RP * n_steps * NACC;                                  // [RW][G] or [n_sa][n_steps]
+        for (int i = lane; i < p.RP * n_steps * NACC; i += 32) {
+            const int a = i % NACC, s = (i / NACC) % n_steps, slot = i / (NACC * n_steps);
+            const uint32_t pix16 = (smem_pix + (uint32_t)slot * p.stage_pitch) >> 4;
+            tabB[i] = ((uint64_t)b_hi << 32) | (p.step_tab[s].y + pix16 + (uint32_t)a * p.acc_delta16);
+        }
+        const int nA = resident ? p.n_sa * n_steps : p.RW * G;
+        for (int i = lane; i < nA; i += 32) {
+            uint32_t a16;
+            if (resident) a16 = (smem_w >> 4) + p.step_tab[i % n_steps].x + (uint32_t)((i / n_steps) * p.a_sa_stride16);
+            else a16 = ((smem_w + (uint32_t)(i / G) * slot_bytes) >> 4) + (uint32_t)(i % G) * (kWeightTileBytes >> 4);
+            tabA[i] = ((uint64_t)a_hi << 32) | ((a16 & 0x3FFFu) | a_lbo_bits);
+        }
+        __syncwarp();
+        uint32_t pslot = 0, pphase = 0, wslot = 0, wphase = 0, as = 0, aphase = 0;
+        const int slots_per_stage = (n_steps + G - 1) / G;
+        const uint32_t acc_cols = p.acc_cols, idesc = p.idesc;
         if (resident) { mbar_wait(BAR(w_res, 0), 0); tc_fence_after(); }
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
             // n_u > 1 (column GEMM): one pixel stage per tile, reused by every accumulator group
@@ -378,46 +394,36 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
                 const uint32_t d_base = tmem_base + as * (acc_cols * (uint32_t)NACC);
                 uint32_t accumulate = 0;
                 for (int sa = 0; sa < p.n_sa; ++sa) {
-                    const uint32_t a_stage16 = (smem_w >> 4) + (uint32_t)(sa * p.a_sa_stride16);
                     for (int sb = 0; sb < p.n_sb; ++sb) {
                         if (u == 0) { mbar_wait(BAR(pix_full, pslot), pphase); tc_fence_after(); }
-                        const uint32_t pix16 = (smem_pix + pslot * p.stage_pitch) >> 4;
                         int j = 0;
                         for (int g = 0; g < slots_per_stage; ++g) {
                             const int nst = min(G, n_steps - j);
-                            uint32_t a16 = a_stage16;
-                            if (!resident) {
-                                mbar_wait(BAR(w_full, wslot), wphase);
-                                tc_fence_after();
-                                a16 = (smem_w + wslot * slot_bytes) >> 4;
+                            if (!resident) { mbar_wait(BAR(w_full, wslot), wphase); tc_fence_after(); }
+                            if (elect_one()) {
+                                const uint64_t* ta = resident ? tabA + sa * n_steps + j : tabA + wslot * G;
+                                const uint64_t* tb = tabB + ((int)pslot * n_steps + j) * NACC;
+#pragma unroll 4
+                                for (int jj = 0; jj < nst; ++jj) {
+                                    const uint64_t a_desc = ta[jj];
+#pragma unroll
+                                    for (int a = 0; a < NACC; ++a)
+                                        umma_bf16(d_base + (uint32_t)a * acc_cols, a_desc, tb[jj * NACC + a], idesc, accumulate);
+                                    accumulate = 1;
+                                }
+                                if (!resident) umma_commit(BAR(w_empty, wslot));
+                                if (g == slots_per_stage - 1 && u == p.n_u - 1) umma_commit(BAR(pix_empty, pslot));
                             }
                             __syncwarp();
-#pragma unroll 2
-                            for (int jj = 0; jj < nst; ++jj) {
-                                const uint2 e = p.step_tab[j + jj];
-                                // off16 + base16 < 2^14 (smem < 256 KiB): no carry into the LBO field
-                                const uint64_t a_desc = ((uint64_t)a_hi << 32) | (((a16 + e.x) & 0x3FFFu) | a_lbo_bits);
-                                const uint32_t b_lo = e.y + pix16;
-#pragma unroll
-                                for (int a = 0; a < NACC; ++a) {
-                                    const uint64_t b_desc = ((uint64_t)b_hi << 32) | (b_lo + (uint32_t)a * acc_delta16);
-                                    umma_bf16_elect(d_base + (uint32_t)a * acc_cols, a_desc, b_desc, idesc, accumulate);
-                                }
-                                accumulate = 1;
-                            }
+                            accumulate = 1;
                             j += nst;
-                            if (!resident) {
-                                umma_commit_elect(BAR(w_empty, wslot));
-                                if (++wslot == (uint32_t)p.RW) { wslot = 0; wphase ^= 1; }
-                            }
+                            if (!resident) { if (++wslot == (uint32_t)p.RW) { wslot = 0; wphase ^= 1; } }
                         }
-                        if (u == p.n_u - 1) {
-                            umma_commit_elect(BAR(pix_empty, pslot));
-                            if (++pslot == (uint32_t)p.RP) { pslot = 0; pphase ^= 1; }
-                        }
+                        if (u == p.n_u - 1) { if (++pslot == (uint32_t)p.RP) { pslot = 0; pphase ^= 1; } }
                     }
                 }
-                umma_commit_elect(BAR(acc_full, as));
+                if (elect_one()) umma_commit(BAR(acc_full, as));
+                __syncwarp();
                 if (++as == p.acc_stages) { as = 0; aphase ^= 1; }
             }
         }

@@ -8,7 +8,7 @@ namespace tc {
 
 template <int NACC>
 __global__ void __launch_bounds__(128, 1) mma_rate_kernel(long long* out, int ncols, int iters, uint32_t a_hi, uint32_t b_hi,
-                                                          uint32_t lbo16, int vary) {
+                                                          uint32_t lbo16, int vary, int delay) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* bp = smem_raw + (base - smem_u32(smem_raw));
@@ -38,6 +38,10 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(long long* out, int nc
                     umma_bf16(tmem_base + (uint32_t)a * acc_cols, a_desc, b_desc, idesc, it > 0);
                 }
             }
+            if (delay > 0) {                       // emulate `delay` cycles of scalar work per step
+                const long long d0 = clock64();
+                while (clock64() - d0 < delay) { }
+            }
         }
         long long t1 = clock64();
         if (elect_one()) umma_commit(base);
@@ -57,12 +61,12 @@ using namespace vd;
 using namespace vd::tc;
 
 extern "C" int vd_tc_mma_rate(long long* out, int n_acc, int ncols, int iters, uint32_t a_hi, uint32_t b_hi, uint32_t lbo16,
-                              int vary, int grid, void* stream) {
+                              int vary, int grid, int delay, void* stream) {
     VD_REQUIRE(out && (n_acc == 1 || n_acc == 2 || n_acc == 4) && ncols % 16 == 0 && ncols * n_acc <= 512, "mma_rate: bad argument");
     const int smem = 120 * 1024;
     cudaStream_t s = (cudaStream_t)stream;
 #define GO(N) do { cudaFuncSetAttribute(mma_rate_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
-                   mma_rate_kernel<N><<<grid, 128, smem, s>>>(out, ncols, iters, a_hi, b_hi, lbo16, vary); } while (0)
+                   mma_rate_kernel<N><<<grid, 128, smem, s>>>(out, ncols, iters, a_hi, b_hi, lbo16, vary, delay); } while (0)
     if (n_acc == 1) GO(1); else if (n_acc == 2) GO(2); else GO(4);
 #undef GO
     return check_launch("tc_mma_rate");
