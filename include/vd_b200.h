@@ -221,6 +221,10 @@ int vd_tc_probe(const void* pix, const void* wimg, float* raw, int ncols, int n_
 int vd_tc_mma_rate(long long* out, int n_acc, int ncols, int iters, uint32_t a_hi, uint32_t b_hi, uint32_t lbo16,
                    int vary, int grid, int delay, void* stream);   /* delay: emulated scalar cycles per step */
 
+/* Tuning aid: device buffer (148*8 int64) receiving per-CTA cycle counters of the MMA warp of the forward
+ * conv launches: [total, wait acc_empty, wait pix_full, wait w_full, issue]; NULL disables. */
+int vd_tc_set_profile_buffer(long long* buf);
+
 /* Host-only introspection (no GPU work): the launch parameters vd_tc_conv_layer would use,
  * flattened to int64 (layout documented in tests/tc_emulator.py); cap >= 248. */
 int vd_tc_debug_params(int layer, const vd_tc_plan* plan, int B, int64_t* out, int cap);   /* layer 3,4,5 = bwd gemm of conv 0,1,2 */

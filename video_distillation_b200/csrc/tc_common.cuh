@@ -44,10 +44,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     return ok != 0;
 }
 // Bounded wait: a protocol bug traps (sticky error on the host) instead of hanging the GPU.
+// `patient` waits (loaders, epilogue) back off with nanosleep so that their polling does not steal
+// issue slots from the MMA warp sharing the same scheduler.
+template <bool kPatient = false>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
+        if (kPatient) __nanosleep(256);
         if (clock64() - t0 > 4000000000LL) {
             printf("vd_b200: mbarrier wait timeout (block %d thread %d bar 0x%x parity %u)\n",
                    (int)blockIdx.x, (int)threadIdx.x, bar, parity);

@@ -12,6 +12,8 @@
 // Warp roles: 0 pixel loader, 1 MMA issuer (single thread), 2 TMEM allocator, 3 weight loader,
 // 4..7 epilogue (TMEM -> registers -> bias/ReLU/MaxPool/argmax -> packed bf16 input of the next
 // layer, or fp32 embeddings after conv 2).  Layouts: tc_layout.h.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 #include "tc_layout.h"
 
@@ -69,6 +71,7 @@ struct WsParams {
     uint32_t idesc;
     uint32_t smem_w_off, smem_pix_off;  // from the 1024-aligned dynamic smem base
     uint32_t smem_epi_off;              // != 0: 4 x 32 x 33 float transpose scratch for coalesced raw stores
+    long long* prof;                    // optional [grid][8] cycle counters of the MMA warp (tuning only)
     EpiParams epi;
 };
 
@@ -314,7 +317,7 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
                 const uint8_t* gbase = p.pix + slot_item * p.item_stride + (int64_t)u * p.u_stride + (int64_t)v * p.v_stride;
                 for (int sa = 0; sa < p.n_sa; ++sa)
                     for (int sb = 0; sb < p.n_sb; ++sb) {
-                        mbar_wait(BAR(pix_empty, slot), phase ^ 1);
+                        mbar_wait<true>(BAR(pix_empty, slot), phase ^ 1);
                         mbar_expect_tx(BAR(pix_full, slot), p.stage_bytes);
                         const uint8_t* src = gbase + (int64_t)sa * p.sa_stride + (int64_t)sb * p.sb_stride;
                         const uint32_t dst = smem_pix + slot * p.stage_pitch;
@@ -342,7 +345,7 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
                             for (int gi = 0; gi < slots_per_stage; ++gi) {
                                 const int s0 = gi * p.G;
                                 const uint32_t nb = (uint32_t)min(p.G, p.n_steps - s0) * kWeightTileBytes;
-                                mbar_wait(BAR(w_empty, slot), phase ^ 1);
+                                mbar_wait<true>(BAR(w_empty, slot), phase ^ 1);
                                 mbar_expect_tx(BAR(w_full, slot), nb);
                                 bulk_g2s(smem_w + slot * (uint32_t)p.G * kWeightTileBytes,
                                          p.wimg + (int64_t)u * p.w_u_stride + ((int64_t)st * p.n_steps + s0) * kWeightTileBytes,
@@ -386,20 +389,25 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
         const int slots_per_stage = (n_steps + G - 1) / G;
         const uint32_t acc_cols = p.acc_cols, idesc = p.idesc;
         if (resident) { mbar_wait(BAR(w_res, 0), 0); tc_fence_after(); }
+        long long c_acc = 0, c_pix = 0, c_w = 0, c_issue = 0;
+        const bool prof = p.prof != nullptr;
+        const long long c_begin = clock64();
+#define TIMED(counter, stmt) do { if (prof) { const long long t_ = clock64(); stmt; counter += clock64() - t_; } else { stmt; } } while (0)
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
             // n_u > 1 (column GEMM): one pixel stage per tile, reused by every accumulator group
             for (int u = 0; u < p.n_u; ++u) {
-                mbar_wait(BAR(acc_empty, as), aphase ^ 1);
+                TIMED(c_acc, mbar_wait(BAR(acc_empty, as), aphase ^ 1));
                 tc_fence_after();
                 const uint32_t d_base = tmem_base + as * (acc_cols * (uint32_t)NACC);
                 uint32_t accumulate = 0;
                 for (int sa = 0; sa < p.n_sa; ++sa) {
                     for (int sb = 0; sb < p.n_sb; ++sb) {
-                        if (u == 0) { mbar_wait(BAR(pix_full, pslot), pphase); tc_fence_after(); }
+                        if (u == 0) { TIMED(c_pix, mbar_wait(BAR(pix_full, pslot), pphase)); tc_fence_after(); }
                         int j = 0;
                         for (int g = 0; g < slots_per_stage; ++g) {
                             const int nst = min(G, n_steps - j);
-                            if (!resident) { mbar_wait(BAR(w_full, wslot), wphase); tc_fence_after(); }
+                            if (!resident) { TIMED(c_w, mbar_wait(BAR(w_full, wslot), wphase)); tc_fence_after(); }
+                            const long long t_issue = prof ? clock64() : 0;
                             if (elect_one()) {
                                 const uint64_t* ta = resident ? tabA + sa * n_steps + j : tabA + wslot * G;
                                 const uint64_t* tb = tabB + ((int)pslot * n_steps + j) * NACC;
@@ -415,6 +423,7 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
                                 if (g == slots_per_stage - 1 && u == p.n_u - 1) umma_commit(BAR(pix_empty, pslot));
                             }
                             __syncwarp();
+                            if (prof) c_issue += clock64() - t_issue;
                             accumulate = 1;
                             j += nst;
                             if (!resident) { if (++wslot == (uint32_t)p.RW) { wslot = 0; wphase ^= 1; } }
@@ -427,6 +436,11 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
                 if (++as == p.acc_stages) { as = 0; aphase ^= 1; }
             }
         }
+#undef TIMED
+        if (prof && lane == 0) {
+            long long* o = p.prof + (int64_t)blockIdx.x * 8;
+            o[0] = clock64() - c_begin; o[1] = c_acc; o[2] = c_pix; o[3] = c_w; o[4] = c_issue;
+        }
     } else if (warp >= 4) {
         // ===================== epilogue (128 threads, lane quarter = warp % 4) =====================
         const int q = warp & 3;
@@ -434,7 +448,7 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
         uint32_t as = 0, aphase = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x)
             for (int u = 0; u < p.n_u; ++u) {
-                mbar_wait(BAR(acc_full, as), aphase);
+                mbar_wait<true>(BAR(acc_full, as), aphase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * (p.acc_cols * (uint32_t)p.n_acc);
                 if (EPI == EPI_RAW) epi_raw(p, tile, u, taddr, m, p.smem_epi_off ? reinterpret_cast<float*>(base_ptr + p.smem_epi_off) : nullptr);
@@ -460,7 +474,15 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
 // ------------------------------------------------------------------------------------------
 // host side: per-layer parameter construction
 // ------------------------------------------------------------------------------------------
+static long long* g_prof = nullptr;      // set by vd_tc_set_profile_buffer (tuning only)
+
 static uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
+
+// tuning override (integer environment variable), used by the ring-depth experiments in profiles/
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
 
 static int finalize_smem(WsParams& p, uint32_t w_region, uint32_t* smem_total, bool epi_scratch = false) {
     {
@@ -517,7 +539,7 @@ static int setup_l0(WsParams& p, const Geo& g, int B, uint32_t* smem) {
     p.a_lbo16 = 5120 >> 4; p.a_sbo16 = 8;
     p.w_resident = 1; p.w_bytes = kW0Bytes;
     p.G = 1; p.RW = 1;
-    p.RP = 3;
+    p.RP = env_int("VD_TC_L0_RP", 3);
     p.n_acc = 1; p.acc_delta16 = 0;
     p.ncols = g.N0; p.acc_cols = 256; p.acc_stages = 2;
     p.idesc = umma_idesc_bf16(128, g.N0);
@@ -542,7 +564,7 @@ static int setup_l1(WsParams& p, const Geo& g, int B, uint32_t* smem) {
         }
     p.a_lbo16 = 2048 >> 4; p.a_sbo16 = 8;
     p.w_resident = 0; p.w_bytes = 0;
-    p.G = 7; p.RW = 2; p.RP = 2;
+    p.G = env_int("VD_TC_L1_G", 7); p.RW = env_int("VD_TC_L1_RW", 2); p.RP = 2;
     p.n_acc = 2; p.acc_delta16 = (uint32_t)g.frame1 >> 4;
     p.ncols = g.N1; p.acc_cols = 256; p.acc_stages = 1;
     p.idesc = umma_idesc_bf16(128, g.N1);
@@ -571,7 +593,7 @@ static int setup_l2(WsParams& p, const Geo& g, int B, uint32_t* smem) {
         }
     p.a_lbo16 = 2048 >> 4; p.a_sbo16 = 8;
     p.w_resident = 0; p.w_bytes = 0;
-    p.G = 6; p.RW = 2; p.RP = 2;
+    p.G = env_int("VD_TC_L2_G", 6); p.RW = env_int("VD_TC_L2_RW", 2); p.RP = 2;
     p.n_acc = VPT; p.acc_delta16 = (uint32_t)g.group2 >> 4;
     p.ncols = g.N2; p.acc_cols = 128; p.acc_stages = 1;
     p.idesc = umma_idesc_bf16(128, g.N2);
@@ -681,6 +703,7 @@ extern "C" int vd_tc_conv_layer(int layer, const void* in, const void* wimg, con
     if (rc) { if (rc == -2) set_error("tc conv 0: non-monotone chunk pairing"); return rc; }
     VD_REQUIRE(item_index == nullptr || layer == 0, "tc_conv_layer: item_index is only valid for layer 0");
     p.pix = (const uint8_t*)in; p.wimg = (const uint8_t*)wimg; p.item_index = item_index;
+    p.prof = g_prof;
     p.epi.bias = bias; p.epi.out = (uint8_t*)out; p.epi.code = code; p.epi.raw = (float*)out;
     p.epi.T = plan->T; p.epi.n_items = B; p.epi.g = g;
     cudaStream_t s = (cudaStream_t)stream;
@@ -761,3 +784,7 @@ extern "C" int vd_tc_probe(const void* pix, const void* wimg, float* raw, int nc
     p.pix = (const uint8_t*)pix; p.wimg = (const uint8_t*)wimg; p.epi.raw = raw;
     return launch<EPI_RAW>(p, smem, (cudaStream_t)stream);
 }
+
+// Tuning aid: when set (device buffer of grid*8 int64, may be NULL to disable), the MMA warp of every
+// forward conv launch records [total, wait acc_empty, wait pix_full, wait w_full, issue] cycles per CTA.
+extern "C" int vd_tc_set_profile_buffer(long long* buf) { g_prof = buf; return 0; }
