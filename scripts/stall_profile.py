@@ -31,5 +31,5 @@ for layer, (src, w, b, dst, ii) in enumerate([(x0, tc.w0, tc.b0, a1, idx), (a1, 
     v = buf.cpu().view(148, 8).double().mean(0)
     tot = v[0].item()
     print(f'conv{layer}: total {tot:10.0f} cyc | wait acc_empty {100 * v[1] / tot:5.1f}% | wait pix_full {100 * v[2] / tot:5.1f}% | '
-          f'wait w_full {100 * v[3] / tot:5.1f}% | issue {100 * v[4] / tot:5.1f}%')
+          f'wait w_full {100 * v[3] / tot:5.1f}% | issue {100 * v[4] / tot:5.1f}% | fences {100 * v[5] / tot:5.1f}% | tile tail {100 * v[6] / tot:5.1f}%')
 lib.vd_tc_set_profile_buffer(None)

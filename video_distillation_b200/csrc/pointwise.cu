@@ -266,37 +266,103 @@ __global__ void __launch_bounds__(256) compose_bwd_data_kernel(
 }
 
 // d_weight[o,i,tap] = sum_{b,t,h,w} g[b,t,o,h,w] X[b,i,t+kt-1,h+kh-1,w+kw-1]; d_bias[o] = sum g.
-// One warp per (o,i) pair and pixel slab: 27 register accumulators per lane, lanes along w.
-__global__ void __launch_bounds__(256) compose_bwd_weight_kernel(
-        const float* __restrict__ gout, const float* __restrict__ static_syn,
-        const float* __restrict__ dynamic_syn, const int64_t* __restrict__ static_idx,
-        const int64_t* __restrict__ label, const int64_t* __restrict__ dynamic_idx,
-        float* __restrict__ grad_weight, float* __restrict__ grad_bias,
+// Two kernels, both: one warp per image row, lanes along w, 81 register accumulators per lane, block
+// reduction in shared memory, one atomicAdd per (block, weight).
+//   dynamic channel (i = 3): acc[o][tap] over rows (b,t,h);  27 + 3 loads per 81 FMAs.
+//   static channels (i < 3): X does not depend on t, so the sum over t collapses to three frame sums of g
+//     (all t | t >= 1 | t <= T-2 for kt = 1 | 0 | 2): rows (b,h), one block column per o.
+__global__ void __launch_bounds__(256) compose_bwd_weight_dyn_kernel(
+        const float* __restrict__ gout, const float* __restrict__ dynamic_syn, const int64_t* __restrict__ label,
+        const int64_t* __restrict__ dynamic_idx, float* __restrict__ grad_weight, float* __restrict__ grad_bias,
         int B, int T, int H, int W, int dpc, int rows_per_block) {
-    const int pair = blockIdx.y;                 // o*4 + i
-    const int o = pair >> 2, i = pair & 3;
+    __shared__ float red[8 * 84];
+    __shared__ int dst[84];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    float acc[27];
+    float acc[84];                               // [o][tap] then the 3 bias sums
 #pragma unroll
-    for (int k = 0; k < 27; ++k) acc[k] = 0.f;
-    float accb = 0.f;
+    for (int k = 0; k < 84; ++k) acc[k] = 0.f;
     const int64_t total_rows = (int64_t)B * T * H;
     const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
     const int64_t r1 = min(total_rows, r0 + rows_per_block);
+    const int64_t HW = (int64_t)H * W;
     for (int64_t r = r0 + warp; r < r1; r += nwarp) {
         const int h = (int)(r % H); const int64_t q = r / H;
         const int t = (int)(q % T); const int b = (int)(q / T);
-        const float* G = gout + ((((int64_t)b * T + t) * 3 + o) * H + h) * W;
-        const float* X = (i < 3) ? static_syn + (static_idx[b] * 3 + i) * (int64_t)H * W
-                                 : dynamic_syn + (label[b] * dpc + dynamic_idx[b]) * (int64_t)T * H * W;
+        const float* G = gout + (((int64_t)b * T + t) * 3) * HW + (int64_t)h * W;
+        const float* D = dynamic_syn + (label[b] * dpc + dynamic_idx[b]) * (int64_t)T * HW;
         for (int w = lane; w < W; w += 32) {
-            const float g = __ldg(G + w);
-            accb += g;
+            float g[3];
+#pragma unroll
+            for (int o = 0; o < 3; ++o) { g[o] = __ldg(G + o * HW + w); acc[81 + o] += g[o]; }
 #pragma unroll
             for (int kt = 0; kt < 3; ++kt) {
                 const int tt = t + kt - 1;
                 if ((unsigned)tt >= (unsigned)T) continue;
-                const float* Xt = (i < 3) ? X : X + (int64_t)tt * H * W;
+#pragma unroll
+                for (int kh = 0; kh < 3; ++kh) {
+                    const int hh = h + kh - 1;
+                    if ((unsigned)hh >= (unsigned)H) continue;
+                    const float* row = D + (int64_t)tt * HW + (int64_t)hh * W;
+#pragma unroll
+                    for (int kw = 0; kw < 3; ++kw) {
+                        const int ww = w + kw - 1;
+                        const float xv = ((unsigned)ww < (unsigned)W) ? __ldg(row + ww) : 0.f;
+                        const int tap = (kt * 3 + kh) * 3 + kw;
+#pragma unroll
+                        for (int o = 0; o < 3; ++o) acc[o * 27 + tap] = fmaf(g[o], xv, acc[o * 27 + tap]);
+                    }
+                }
+            }
+        }
+    }
+    if (threadIdx.x < 81) dst[threadIdx.x] = ((threadIdx.x / 27) * 4 + 3) * 27 + threadIdx.x % 27;
+    else if (threadIdx.x < 84) dst[threadIdx.x] = 324 + (threadIdx.x - 81);     // bias follows the 324 weights in `scratch`
+    __syncthreads();
+    // weights and bias live in different tensors: reduce into a 327-float view [weight | bias]
+    constexpr int n = 84;
+#pragma unroll
+    for (int k = 0; k < n; ++k) {
+        const float s = warp_sum(acc[k]);
+        if (lane == 0) red[warp * n + k] = s;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        float s = 0.f;
+        for (int w = 0; w < nwarp; ++w) s += red[w * n + k];
+        if (k < 81) atomicAdd(grad_weight + dst[k], s);
+        else if (grad_bias) atomicAdd(grad_bias + (k - 81), s);
+    }
+}
+
+__global__ void __launch_bounds__(256) compose_bwd_weight_static_kernel(
+        const float* __restrict__ gout, const float* __restrict__ static_syn, const int64_t* __restrict__ static_idx,
+        float* __restrict__ grad_weight, int B, int T, int H, int W, int rows_per_block) {
+    __shared__ float red[8 * 81];
+    const int o = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    float acc[81];                               // [i][kt][kh][kw]
+#pragma unroll
+    for (int k = 0; k < 81; ++k) acc[k] = 0.f;
+    const int64_t total_rows = (int64_t)B * H;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t r1 = min(total_rows, r0 + rows_per_block);
+    const int64_t HW = (int64_t)H * W;
+    for (int64_t r = r0 + warp; r < r1; r += nwarp) {
+        const int h = (int)(r % H); const int b = (int)(r / H);
+        const float* G = gout + ((int64_t)b * T * 3 + o) * HW + (int64_t)h * W;
+        const float* S = static_syn + static_idx[b] * 3 * HW;
+        for (int w = lane; w < W; w += 32) {
+            float gall = 0.f, gfirst = 0.f, glast = 0.f;
+            for (int t = 0; t < T; ++t) {
+                const float g = __ldg(G + (int64_t)t * 3 * HW + w);
+                gall += g;
+                if (t == 0) gfirst = g;
+                if (t == T - 1) glast = g;
+            }
+            // tap kt reads frame t+kt-1: kt=0 needs t>=1, kt=2 needs t<=T-2
+            const float gk[3] = {gall - gfirst, gall, gall - glast};
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
 #pragma unroll
                 for (int kh = 0; kh < 3; ++kh) {
                     const int hh = h + kh - 1;
@@ -304,21 +370,25 @@ __global__ void __launch_bounds__(256) compose_bwd_weight_kernel(
 #pragma unroll
                     for (int kw = 0; kw < 3; ++kw) {
                         const int ww = w + kw - 1;
-                        const float xv = ((unsigned)ww < (unsigned)W) ? __ldg(Xt + (int64_t)hh * W + ww) : 0.f;
-                        acc[(kt * 3 + kh) * 3 + kw] = fmaf(g, xv, acc[(kt * 3 + kh) * 3 + kw]);
+                        const float xv = ((unsigned)ww < (unsigned)W) ? __ldg(S + i * HW + (int64_t)hh * W + ww) : 0.f;
+#pragma unroll
+                        for (int kt = 0; kt < 3; ++kt)
+                            acc[i * 27 + (kt * 3 + kh) * 3 + kw] = fmaf(gk[kt], xv, acc[i * 27 + (kt * 3 + kh) * 3 + kw]);
                     }
                 }
-            }
         }
     }
+    constexpr int n = 81;
 #pragma unroll
-    for (int k = 0; k < 27; ++k) {
+    for (int k = 0; k < n; ++k) {
         const float s = warp_sum(acc[k]);
-        if (lane == 0) atomicAdd(grad_weight + pair * 27 + k, s);
+        if (lane == 0) red[warp * n + k] = s;
     }
-    if (i == 0 && grad_bias) {
-        const float s = warp_sum(accb);
-        if (lane == 0) atomicAdd(grad_bias + o, s);
+    __syncthreads();
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        float s = 0.f;
+        for (int w = 0; w < nwarp; ++w) s += red[w * n + k];
+        atomicAdd(grad_weight + (o * 4 + k / 27) * 27 + k % 27, s);
     }
 }
 
@@ -504,13 +574,23 @@ extern "C" int vd_compose_bwd_f32(const float* gout, const float* static_syn, co
         if (int e = check_launch("compose_bwd_data_f32")) return e;
     }
     if (grad_weight) {
-        const int64_t rows = (int64_t)B * T * H;
-        int rpb = (int)ceil_div(rows, 148 * 2);
-        if (rpb < 8) rpb = 8;
-        dim3 grid((unsigned)ceil_div(rows, rpb), 12, 1);
-        compose_bwd_weight_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(gout, static_syn, dynamic_syn, static_idx, label,
-                                                                         dynamic_idx, grad_weight, grad_bias, B, T, H, W, dpc, rpb);
-        if (int e = check_launch("compose_bwd_weight_f32")) return e;
+        cudaStream_t s = (cudaStream_t)stream;
+        {
+            const int64_t rows = (int64_t)B * T * H;
+            int rpb = (int)ceil_div(rows, 148 * 4);
+            if (rpb < 8) rpb = 8;
+            compose_bwd_weight_dyn_kernel<<<(unsigned)ceil_div(rows, rpb), 256, 0, s>>>(gout, dynamic_syn, label, dynamic_idx, grad_weight,
+                                                                                      grad_bias, B, T, H, W, dpc, rpb);
+            if (int e = check_launch("compose_bwd_weight_dyn_f32")) return e;
+        }
+        {
+            const int64_t rows = (int64_t)B * H;
+            int rpb = (int)ceil_div(rows, 148);
+            if (rpb < 8) rpb = 8;
+            dim3 grid((unsigned)ceil_div(rows, rpb), 3, 1);
+            compose_bwd_weight_static_kernel<<<grid, 256, 0, s>>>(gout, static_syn, static_idx, grad_weight, B, T, H, W, rpb);
+            if (int e = check_launch("compose_bwd_weight_static_f32")) return e;
+        }
     }
     return 0;
 }

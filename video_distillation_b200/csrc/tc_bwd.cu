@@ -62,66 +62,118 @@ __global__ void bwd_emb_kernel(const float* __restrict__ g_emb, const uint8_t* _
 // dX[ci,t,h,w] of conv `b.layer` = sum over taps of col[(ci,tap)][pixel(t+1-kt, (h+3-kh)/2, (w+3-kw)/2)]
 __device__ __forceinline__ float bf2f(uint16_t v) { return __uint_as_float((uint32_t)v << 16); }
 
-__device__ __forceinline__ float col2im_gather(const uint16_t* __restrict__ colv, const BwdGeo& b, int ci, int t, int h, int w) {
+// Memory-bound col2im: the column buffer is read exactly once (conv 1/2) or ~1.4x (conv 0 row bands),
+// with coalesced 4-byte loads, and summed out of shared memory.
+// One block per (video, ci, t, band of `band` input rows).  For each temporal tap kt the 49 rows
+// (ci, kt, kh, kw) of the column buffer restricted to the output pixels (to = t+1-kt, ho0..ho1, all wo)
+// — one contiguous pixel range — are staged in shared memory [49][npix]; every thread then gathers the
+// taps of its input pixels (same parity rule as the forward conv) into register accumulators.
+constexpr int kC2iMaxOut = 8;            // input pixels per thread (band * Wi <= 256 * kC2iMaxOut)
+
+struct C2iBlock {
+    int vid, ci, t, hb, h_end, ho0, npix;
+};
+
+__device__ __forceinline__ C2iBlock c2i_block(const BwdGeo& b, int band) {
+    C2iBlock k;
+    const int nb = (b.Hi + band - 1) / band;
+    int q = blockIdx.x;                                   // ci fastest: the 8 channels of a 16-byte dY chunk are written
+    k.ci = q % b.Cin; q /= b.Cin;                         // by concurrently running blocks and merge in L2
+    const int ib = q % nb; q /= nb;
+    k.t = q % b.Ti; k.vid = q / b.Ti;
+    k.hb = ib * band;
+    k.h_end = min(b.Hi, k.hb + band);
+    k.ho0 = max(0, (k.hb - 2) / 2);                       // smallest ho with 2*ho + kh - 3 >= hb for some kh <= 6
+    const int ho1 = min(b.Ho - 1, (k.h_end + 2) / 2);     // largest ho with 2*ho + kh - 3 <= h_end - 1 for some kh >= 0
+    k.npix = (ho1 - k.ho0 + 1) * b.Wo;
+    return k;
+}
+
+// stage rows (ci, kt, 0..48) x pixels [pix0, pix0 + npix) of one video's column buffer: smem[tap][npix] (bf16 pairs)
+__device__ __forceinline__ void c2i_stage(const uint16_t* __restrict__ colv, const BwdGeo& b, int ci, int kt, int pix0, int npix,
+                                          uint32_t* __restrict__ sm, int pitch2) {
+    const int np2 = npix >> 1;
+    for (int i = threadIdx.x; i < 49 * np2; i += blockDim.x) {
+        const int tap = i / np2, j = i - tap * np2;
+        const int r = ci * 147 + kt * 49 + tap;
+        const int pix = pix0 + 2 * j;
+        const int nt = (int)__umulhi((uint32_t)pix, b.nc_magic), col = pix - nt * b.NC;
+        sm[tap * pitch2 + j] = __ldg(reinterpret_cast<const uint32_t*>(
+            colv + (((int64_t)nt * b.NU + (r >> 7)) * 128 + (r & 127)) * b.NC + col));
+    }
+}
+
+// gather the (kh,kw) taps of input pixel (h,w) from the staged rows of one kt
+__device__ __forceinline__ float c2i_taps(const uint16_t* __restrict__ sm16, int pitch, const BwdGeo& b, int ho0, int h, int w) {
     float acc = 0.f;
-    for (int kt = 0; kt < 3; ++kt) {
-        const int to = t + 1 - kt;
-        if ((unsigned)to >= (unsigned)b.To) continue;
-        for (int kh = (h + 1) & 1; kh < 7; kh += 2) {
-            const int hh = h + 3 - kh;
-            if (hh < 0) continue;
-            const int ho = hh >> 1;
-            if (ho >= b.Ho) continue;
-            for (int kw = (w + 1) & 1; kw < 7; kw += 2) {
-                const int ww = w + 3 - kw;
-                if (ww < 0) continue;
-                const int wo = ww >> 1;
-                if (wo >= b.Wo) continue;
-                const int r = ci * 147 + (kt * 7 + kh) * 7 + kw;
-                const int pix = (to * b.Ho + ho) * b.Wo + wo;
-                const int nt = (int)__umulhi((uint32_t)pix, b.nc_magic), col = pix - nt * b.NC;
-                acc += bf2f(__ldg(colv + (((int64_t)nt * b.NU + (r >> 7)) * 128 + (r & 127)) * b.NC + col));
-            }
+    for (int kh = (h + 1) & 1; kh < 7; kh += 2) {
+        const int hh = h + 3 - kh;
+        if (hh < 0) continue;
+        const int ho = hh >> 1;
+        if (ho >= b.Ho) continue;
+        const uint16_t* row = sm16 + (kh * 7) * pitch + (ho - ho0) * b.Wo;
+        for (int kw = (w + 1) & 1; kw < 7; kw += 2) {
+            const int ww = w + 3 - kw;
+            if (ww < 0) continue;
+            const int wo = ww >> 1;
+            if (wo >= b.Wo) continue;
+            acc += bf2f(row[kw * pitch + wo]);
         }
     }
     return acc;
 }
 
-// layers 2 and 1: one thread per POOLED element (ci,t,h,w) of the layer below; writes the whole
-// pool window (pt x 2 x 2 conv outputs) of the next dY: the routed gradient at the recorded
-// argmax, zeros elsewhere -> dY below is fully overwritten, no memset needed.
-__global__ void col2im_route_kernel(const uint16_t* __restrict__ colbuf, const uint8_t* __restrict__ code,
-                                    uint16_t* __restrict__ dy_below, int64_t total, BwdGeo b, BwdGeo bb, int pt) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        int w = (int)(i % b.Wi); int64_t q = i / b.Wi;
-        int h = (int)(q % b.Hi); q /= b.Hi;
-        int t = (int)(q % b.Ti); q /= b.Ti;
-        int ci = (int)(q % b.Cin); int64_t vid = q / b.Cin;
-        const float gsum = col2im_gather(colbuf + vid * b.col_video_elems, b, ci, t, h, w);
-        const uint8_t cd = code[i];                       // code layout (B, Cin, Ti, Hi, Wi) == thread order
-        const uint16_t gv = f2bf((cd & 8) ? gsum : 0.f);
+// layers 2 and 1: every thread owns POOLED elements (ci,t,h,w) of the layer below and writes the whole
+// pool window (pt x 2 x 2 conv outputs) of the next dY: the routed gradient at the recorded argmax,
+// zeros elsewhere -> dY below is fully overwritten, no memset needed.
+// layer 0 (code == nullptr): writes d video (B, T, 3, H, W) fp32.
+__global__ void __launch_bounds__(256) col2im_kernel(const uint16_t* __restrict__ colbuf, const uint8_t* __restrict__ code,
+                                                     void* __restrict__ out, BwdGeo b, BwdGeo bb, int pt, int band, int pitch) {
+    extern __shared__ uint32_t c2i_smem[];
+    const C2iBlock k = c2i_block(b, band);
+    const uint16_t* colv = colbuf + (int64_t)k.vid * b.col_video_elems;
+    const int n_out = (k.h_end - k.hb) * b.Wi;
+    float acc[kC2iMaxOut];
+#pragma unroll
+    for (int j = 0; j < kC2iMaxOut; ++j) acc[j] = 0.f;
+    for (int kt = 0; kt < 3; ++kt) {
+        const int to = k.t + 1 - kt;
+        if ((unsigned)to >= (unsigned)b.To) continue;                 // block-uniform
+        __syncthreads();
+        c2i_stage(colv, b, k.ci, kt, (to * b.Ho + k.ho0) * b.Wo, k.npix, c2i_smem, pitch >> 1);
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < kC2iMaxOut; ++j) {
+            const int i = threadIdx.x + j * 256;
+            if (i < n_out) {
+                const int hl = i / b.Wi, w = i - hl * b.Wi;
+                acc[j] += c2i_taps(reinterpret_cast<const uint16_t*>(c2i_smem), pitch, b, k.ho0, k.hb + hl, w);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < kC2iMaxOut; ++j) {
+        const int i = threadIdx.x + j * 256;
+        if (i >= n_out) continue;
+        const int hl = i / b.Wi, w = i - hl * b.Wi, h = k.hb + hl;
+        if (code == nullptr) {
+            float* dv = reinterpret_cast<float*>(out);
+            dv[((((int64_t)k.vid * b.Ti + k.t) * 3 + k.ci) * b.Hi + h) * b.Wi + w] = acc[j];
+            continue;
+        }
+        const uint8_t cd = code[((((int64_t)k.vid * b.Cin + k.ci) * b.Ti + k.t) * b.Hi + h) * b.Wi + w];
+        const uint16_t gv = f2bf((cd & 8) ? acc[j] : 0.f);
         const int arg = cd & 7;
-        uint16_t* base = dy_below + vid * (bb.dy_video / 2);
-        const int chunk = ci >> 3, e = ci & 7;
+        uint16_t* base = reinterpret_cast<uint16_t*>(out) + (int64_t)k.vid * (bb.dy_video / 2);
+        const int chunk = k.ci >> 3, e = k.ci & 7;
         int pos = 0;
         for (int dt = 0; dt < pt; ++dt)
             for (int dh = 0; dh < 2; ++dh)
                 for (int dw = 0; dw < 2; ++dw, ++pos) {
-                    const int pix = ((t * pt + dt) * bb.Ho + (2 * h + dh)) * bb.Wo + 2 * w + dw;
+                    const int pix = ((k.t * pt + dt) * bb.Ho + (2 * h + dh)) * bb.Wo + 2 * w + dw;
                     const int nt = (int)__umulhi((uint32_t)pix, bb.nc_magic), col = pix - nt * bb.NC;
                     base[(((int64_t)nt * (bb.K / 8) + chunk) * bb.NC + col) * 8 + e] = (pos == arg) ? gv : (uint16_t)0;
                 }
-    }
-}
-
-// layer 0: d video (B, T, 3, H, W) fp32
-__global__ void col2im_video_kernel(const uint16_t* __restrict__ colbuf, float* __restrict__ dvideo, int64_t total, BwdGeo b) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        int w = (int)(i % b.Wi); int64_t q = i / b.Wi;
-        int h = (int)(q % b.Hi); q /= b.Hi;
-        int c = (int)(q % 3); q /= 3;
-        int t = (int)(q % b.Ti); int64_t vid = q / b.Ti;
-        dvideo[i] = col2im_gather(colbuf + vid * b.col_video_elems, b, c, t, h, w);
     }
 }
 
@@ -174,14 +226,29 @@ extern "C" int vd_tc_bwd_col2im(int layer, const void* col, const uint8_t* code_
     const Geo g = make_geo(plan->T, plan->H);
     const BwdGeo b = make_bwd_geo(g, layer);
     cudaStream_t s = (cudaStream_t)stream;
-    if (layer == 0) {
-        const int64_t total = (int64_t)B * b.Ti * 3 * b.Hi * b.Wi;
-        col2im_video_kernel<<<blocks_for(total), 256, 0, s>>>((const uint16_t*)col, (float*)out, total, b);
-        return check_launch("tc_bwd_col2im_video");
+    VD_REQUIRE(b.Wo % 2 == 0 && b.NC % 2 == 0, "tc_bwd_col2im: odd output width");
+    // band of input rows per block: the whole frame when it fits kC2iMaxOut pixels per thread, else 16 rows
+    int band = b.Hi;
+    while ((int64_t)band * b.Wi > 256 * kC2iMaxOut) band = (band + 1) / 2;
+    const int n_ho = (band + 2) / 2 + 2;
+    const int npix_max = (n_ho < b.Ho ? n_ho : b.Ho) * b.Wo;
+    const int pitch = (npix_max + 2) | 2;                 // bf16 elements per staged row (even, odd number of words)
+    const size_t smem = (size_t)49 * pitch * 2;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(col2im_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        configured = true;
     }
-    const BwdGeo bb = make_bwd_geo(g, layer - 1);
-    const int pt = (layer == 2) ? 2 : 1;       // pool window of the layer below in T: conv1 -> (2,2,2), conv0 -> (1,2,2)
-    const int64_t total = (int64_t)B * b.Cin * b.Ti * b.Hi * b.Wi;
-    col2im_route_kernel<<<blocks_for(total), 256, 0, s>>>((const uint16_t*)col, code_below, (uint16_t*)out, total, b, bb, pt);
-    return check_launch("tc_bwd_col2im_route");
+    VD_REQUIRE(smem <= 96 * 1024, "tc_bwd_col2im: staging buffer too large (%zu bytes)", smem);
+    const int nb = (b.Hi + band - 1) / band;
+    const int64_t blocks = (int64_t)B * b.Cin * b.Ti * nb;
+    VD_REQUIRE(blocks < (1ll << 31), "tc_bwd_col2im: grid too large");
+    BwdGeo bb = b;
+    int pt = 1;
+    if (layer > 0) {
+        bb = make_bwd_geo(g, layer - 1);
+        pt = (layer == 2) ? 2 : 1;             // pool window of the layer below in T: conv1 -> (2,2,2), conv0 -> (1,2,2)
+    }
+    col2im_kernel<<<(unsigned)blocks, 256, smem, s>>>((const uint16_t*)col, layer == 0 ? nullptr : code_below, out, b, bb, pt, band, pitch);
+    return check_launch("tc_bwd_col2im");
 }

@@ -44,6 +44,7 @@ struct WsParams {
     int32_t n_tiles, tiles_per_item, v_count;
     int64_t item_stride, u_stride, v_stride;
     int32_t n_u;                        // accumulator groups per tile sharing ONE pixel stage (column GEMM: M tiles)
+    int32_t nu_total, ug_count;         // column GEMM: the nu_total M tiles of one pixel stage are split over ug_count CTA tiles
     int64_t w_u_stride;                 // bytes between the weight sequences of consecutive groups
     int32_t n_sa, n_sb;
     int64_t sa_stride, sb_stride;
@@ -71,6 +72,9 @@ struct WsParams {
     uint32_t idesc;
     uint32_t smem_w_off, smem_pix_off;  // from the 1024-aligned dynamic smem base
     uint32_t smem_epi_off;              // != 0: 4 x 32 x 33 float transpose scratch for coalesced raw stores
+    uint32_t smem_stash_off;            // != 0: conv-1 epilogue stash [H2*H2][kStashPitch] bf16 (quick accumulator drain)
+    int32_t dbg;                        // tuning experiments (VD_TC_DBG bitmask; results are garbage when set):
+                                        //   1 no pixel copies, 2 no weight copies, 4 epilogue does no work
     long long* prof;                    // optional [grid][8] cycle counters of the MMA warp (tuning only)
     EpiParams epi;
 };
@@ -90,9 +94,39 @@ static_assert(sizeof(Barriers) <= 256, "barrier block too large");
 // epilogues.  Thread `m` (0..127) owns TMEM lane m.  taddr = tmem base of the accumulator stage
 // with the lane quarter already folded in.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void epi_raw(const WsParams& p, int tile, int u, uint32_t taddr, int m, float* scratch) {
+__device__ __forceinline__ uint32_t pack_bf2(float lo, float hi) { return (uint32_t)f2bf(lo) | ((uint32_t)f2bf(hi) << 16); }
+
+// slot = tile_pix * nu_total + u_abs: index of the 128-row block in the raw output
+__device__ __forceinline__ void epi_raw(const WsParams& p, int64_t slot, uint32_t taddr, int m, float* scratch) {
     for (int a = 0; a < p.n_acc; ++a) {
-        float* tile_base = p.epi.raw + (((int64_t)tile * p.n_u + u) * p.n_acc + a) * 128 * (int64_t)p.ncols;
+        const int64_t blk = (slot * p.n_acc + a) * 128;
+        if (p.epi.raw_bf16) {
+            // backward column buffers: this thread's row, 32 columns = 64 contiguous bytes per step
+            uint16_t* dst = reinterpret_cast<uint16_t*>(p.epi.raw) + (blk + m) * (int64_t)p.ncols;
+            uint32_t c = 0;
+            for (; c + 32 <= p.ncols; c += 32) {
+                float v[32];
+                tmem_ld32(taddr + a * p.acc_cols + c, v);
+                tmem_ld_wait();
+                uint4* d4 = reinterpret_cast<uint4*>(dst + c);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    d4[i] = make_uint4(pack_bf2(v[8 * i], v[8 * i + 1]), pack_bf2(v[8 * i + 2], v[8 * i + 3]),
+                                       pack_bf2(v[8 * i + 4], v[8 * i + 5]), pack_bf2(v[8 * i + 6], v[8 * i + 7]));
+            }
+            for (; c < p.ncols; c += 16) {
+                float v[16];
+                tmem_ld16(taddr + a * p.acc_cols + c, v);
+                tmem_ld_wait();
+                uint4* d4 = reinterpret_cast<uint4*>(dst + c);
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+                    d4[i] = make_uint4(pack_bf2(v[8 * i], v[8 * i + 1]), pack_bf2(v[8 * i + 2], v[8 * i + 3]),
+                                       pack_bf2(v[8 * i + 4], v[8 * i + 5]), pack_bf2(v[8 * i + 6], v[8 * i + 7]));
+            }
+            continue;
+        }
+        float* tile_base = p.epi.raw + blk * (int64_t)p.ncols;
         if (scratch == nullptr) {                      // bring-up path (forward layers in raw mode): row per thread
             float* dst = tile_base + (int64_t)m * p.ncols;
             for (uint32_t c = 0; c < p.ncols; c += 8) {
@@ -102,7 +136,7 @@ __device__ __forceinline__ void epi_raw(const WsParams& p, int tile, int u, uint
 #pragma unroll
                 for (int i = 0; i < 8; ++i) dst[c + i] = v[i];
             }
-        } else {                                       // coalesced: transpose 32x32 blocks through shared memory
+        } else {                                       // coalesced fp32: transpose 32x32 blocks through shared memory
             const int lane = m & 31;
             float* s = scratch + (m >> 5) * (32 * 33);
             float* rows = tile_base + (int64_t)(m & ~31) * p.ncols;
@@ -114,15 +148,8 @@ __device__ __forceinline__ void epi_raw(const WsParams& p, int tile, int u, uint
                 for (int i = 0; i < 32; ++i) s[lane * 33 + i] = v[i];
                 __syncwarp();
                 if (c0 + lane < p.ncols) {
-                    if (p.epi.raw_bf16) {
-                        uint16_t* rows16 = reinterpret_cast<uint16_t*>(p.epi.raw) +
-                                           ((((int64_t)tile * p.n_u + u) * p.n_acc + a) * 128 + (m & ~31)) * (int64_t)p.ncols;
 #pragma unroll 8
-                        for (int r = 0; r < 32; ++r) rows16[(int64_t)r * p.ncols + c0 + lane] = f2bf(s[r * 33 + lane]);
-                    } else {
-#pragma unroll 8
-                        for (int r = 0; r < 32; ++r) rows[(int64_t)r * p.ncols + c0 + lane] = s[r * 33 + lane];
-                    }
+                    for (int r = 0; r < 32; ++r) rows[(int64_t)r * p.ncols + c0 + lane] = s[r * 33 + lane];
                 }
                 __syncwarp();
             }
@@ -170,12 +197,16 @@ __device__ __forceinline__ void epi_l0(const WsParams& p, int tile, uint32_t tad
 
 // conv 1: accumulator a = frame 2*tp + a, lane = cout, columns q = ho*P1 + wo.
 // bias + ReLU + MaxPool(2,2,2) -> A2 chunks (bf16, every tap copy) [+ code (B,128,T2,H2,H2)]
-__device__ __forceinline__ void epi_l1(const WsParams& p, int tile, uint32_t taddr, int m) {
+// Two phases so that the (single-buffered, 2 x 256 column) accumulator is released early:
+//   drain: TMEM -> pooled bf16 values in a shared-memory stash [pos][channel]   (then acc_empty arrives)
+//   store: every lane takes (16-byte chunk of 8 channels, position) items of its warp's 32 channels and
+//          writes the chunk to all tap copies of A2 — 16-byte stores, overlapped with the next tile's MMAs.
+constexpr int kStashPitch = 136;          // bf16 elements per position row (128 + 8: conflict-free 16-byte reads)
+
+__device__ __forceinline__ void epi_l1_drain(const WsParams& p, int tile, uint32_t taddr, int m, uint16_t* stash) {
     const Geo& g = p.epi.g;
     const int item = tile / p.tiles_per_item, tp = tile % p.tiles_per_item;   // pooled frame index = tp
     const float bias = __ldg(p.epi.bias + m);
-    const int half = m >> 6, k = (m >> 3) & 7, e = m & 7;
-    uint8_t* vbase = p.epi.out + (int64_t)item * g.video2;
     uint8_t* cbase = p.epi.code ? p.epi.code + (((int64_t)item * 128 + m) * g.T2 + tp) * g.H2 * g.H2 : nullptr;
     for (int hp = 0; hp < g.H2; ++hp) {
         float a0[16], a1[16], b0[16], b1[16];
@@ -198,21 +229,33 @@ __device__ __forceinline__ void epi_l1(const WsParams& p, int tile, uint32_t tad
                 if (b1[2 * wp + 1] > best) { best = b1[2 * wp + 1]; arg = 7; }
                 best += bias;
                 const bool act = best > 0.f;
-                const uint16_t bv = f2bf(act ? best : 0.f);
+                stash[(hp * g.H2 + wp) * kStashPitch + m] = f2bf(act ? best : 0.f);
                 if (cbase) cbase[hp * g.H2 + wp] = (uint8_t)(arg | (act ? 8 : 0));
-                // input pixel (t=tp, h=hp, w=wp) of conv 2 feeds output (ho,wo) through tap
-                // (kh,kw) iff hp = 2ho+kh-3, wp = 2wo+kw-3
-                for (int kh = (hp + 1) & 1; kh < 7; kh += 2) {
-                    const int ho = (hp + 3 - kh) / 2;
-                    if (hp + 3 - kh < 0 || ho >= g.Ho2) continue;
-                    for (int kw = (wp + 1) & 1; kw < 7; kw += 2) {
-                        const int wo = (wp + 3 - kw) / 2;
-                        if (wp + 3 - kw < 0 || wo >= g.Wo2) continue;
-                        uint8_t* dst = vbase + (int64_t)((kh * 7 + kw) * 2 + half) * g.group2 + (int64_t)k * g.chunk2 +
-                                       ((int64_t)(tp + 1) * g.HW2 + ho * g.Wo2 + wo) * 16 + e * 2;
-                        *reinterpret_cast<uint16_t*>(dst) = bv;
-                    }
-                }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void epi_l1_store(const WsParams& p, int tile, int q, int lane, const uint16_t* stash) {
+    const Geo& g = p.epi.g;
+    const int item = tile / p.tiles_per_item, tp = tile % p.tiles_per_item;
+    const int half = q >> 1;
+    uint8_t* vbase = p.epi.out + (int64_t)item * g.video2 + (int64_t)half * g.group2 + (int64_t)(tp + 1) * g.HW2 * 16;
+    const int npos = g.H2 * g.H2;
+    for (int i = lane; i < 4 * npos; i += 32) {
+        const int kk = i / npos, pos = i - kk * npos;
+        const int hp = pos / g.H2, wp = pos - hp * g.H2;
+        const uint4 v = *reinterpret_cast<const uint4*>(stash + pos * kStashPitch + q * 32 + kk * 8);
+        uint8_t* cb = vbase + (int64_t)((q & 1) * 4 + kk) * g.chunk2;
+        // input pixel (t=tp, h=hp, w=wp) of conv 2 feeds output (ho,wo) through tap (kh,kw) iff
+        // hp = 2ho+kh-3, wp = 2wo+kw-3
+        for (int kh = (hp + 1) & 1; kh < 7; kh += 2) {
+            const int ho = (hp + 3 - kh) / 2;
+            if (hp + 3 - kh < 0 || ho >= g.Ho2) continue;
+            for (int kw = (wp + 1) & 1; kw < 7; kw += 2) {
+                const int wo = (wp + 3 - kw) / 2;
+                if (wp + 3 - kw < 0 || wo >= g.Wo2) continue;
+                *reinterpret_cast<uint4*>(cb + (int64_t)((kh * 7 + kw) * 2) * g.group2 + (ho * g.Wo2 + wo) * 16) = v;
             }
         }
     }
@@ -311,18 +354,22 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
         if (lane == 0) {
             uint32_t slot = 0, phase = 0;
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-                const int item = tile / p.tiles_per_item, sub = tile % p.tiles_per_item;
+                const int tile_pix = tile / p.ug_count;
+                const int item = tile_pix / p.tiles_per_item, sub = tile_pix % p.tiles_per_item;
                 const int u = sub / p.v_count, v = sub % p.v_count;
                 const int64_t slot_item = p.item_index ? __ldg(p.item_index + item) : (int64_t)item;
                 const uint8_t* gbase = p.pix + slot_item * p.item_stride + (int64_t)u * p.u_stride + (int64_t)v * p.v_stride;
                 for (int sa = 0; sa < p.n_sa; ++sa)
                     for (int sb = 0; sb < p.n_sb; ++sb) {
                         mbar_wait<true>(BAR(pix_empty, slot), phase ^ 1);
-                        mbar_expect_tx(BAR(pix_full, slot), p.stage_bytes);
-                        const uint8_t* src = gbase + (int64_t)sa * p.sa_stride + (int64_t)sb * p.sb_stride;
-                        const uint32_t dst = smem_pix + slot * p.stage_pitch;
-                        for (int c = 0; c < p.n_copies; ++c)
-                            bulk_g2s(dst + p.copy_sofs[c], src + p.copy_gofs[c], p.copy_bytes[c], BAR(pix_full, slot));
+                        if (p.dbg & 1) { mbar_arrive(BAR(pix_full, slot)); }
+                        else {
+                            mbar_expect_tx(BAR(pix_full, slot), p.stage_bytes);
+                            const uint8_t* src = gbase + (int64_t)sa * p.sa_stride + (int64_t)sb * p.sb_stride;
+                            const uint32_t dst = smem_pix + slot * p.stage_pitch;
+                            for (int c = 0; c < p.n_copies; ++c)
+                                bulk_g2s(dst + p.copy_sofs[c], src + p.copy_gofs[c], p.copy_bytes[c], BAR(pix_full, slot));
+                        }
                         if (++slot == (uint32_t)p.RP) { slot = 0; phase ^= 1; }
                     }
             }
@@ -340,16 +387,20 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
                 uint32_t slot = 0, phase = 0;
                 const int slots_per_stage = (p.n_steps + p.G - 1) / p.G;
                 for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-                    for (int u = 0; u < p.n_u; ++u)
+                    const int u0 = (tile % p.ug_count) * p.n_u, u1 = min(p.nu_total, u0 + p.n_u);
+                    for (int u = u0; u < u1; ++u)
                         for (int st = 0; st < stages_per_tile; ++st)
                             for (int gi = 0; gi < slots_per_stage; ++gi) {
                                 const int s0 = gi * p.G;
                                 const uint32_t nb = (uint32_t)min(p.G, p.n_steps - s0) * kWeightTileBytes;
                                 mbar_wait<true>(BAR(w_empty, slot), phase ^ 1);
-                                mbar_expect_tx(BAR(w_full, slot), nb);
-                                bulk_g2s(smem_w + slot * (uint32_t)p.G * kWeightTileBytes,
-                                         p.wimg + (int64_t)u * p.w_u_stride + ((int64_t)st * p.n_steps + s0) * kWeightTileBytes,
-                                         nb, BAR(w_full, slot));
+                                if (p.dbg & 2) { mbar_arrive(BAR(w_full, slot)); }
+                                else {
+                                    mbar_expect_tx(BAR(w_full, slot), nb);
+                                    bulk_g2s(smem_w + slot * (uint32_t)p.G * kWeightTileBytes,
+                                             p.wimg + (int64_t)u * p.w_u_stride + ((int64_t)st * p.n_steps + s0) * kWeightTileBytes,
+                                             nb, BAR(w_full, slot));
+                                }
                                 if (++slot == (uint32_t)p.RW) { slot = 0; phase ^= 1; }
                             }
                 }
@@ -389,24 +440,25 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
         const int slots_per_stage = (n_steps + G - 1) / G;
         const uint32_t acc_cols = p.acc_cols, idesc = p.idesc;
         if (resident) { mbar_wait(BAR(w_res, 0), 0); tc_fence_after(); }
-        long long c_acc = 0, c_pix = 0, c_w = 0, c_issue = 0;
+        long long c_acc = 0, c_pix = 0, c_w = 0, c_issue = 0, c_fence = 0, c_tail = 0;
         const bool prof = p.prof != nullptr;
         const long long c_begin = clock64();
 #define TIMED(counter, stmt) do { if (prof) { const long long t_ = clock64(); stmt; counter += clock64() - t_; } else { stmt; } } while (0)
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
             // n_u > 1 (column GEMM): one pixel stage per tile, reused by every accumulator group
-            for (int u = 0; u < p.n_u; ++u) {
+            const int n_u_eff = min(p.n_u, p.nu_total - (tile % p.ug_count) * p.n_u);
+            for (int u = 0; u < n_u_eff; ++u) {
                 TIMED(c_acc, mbar_wait(BAR(acc_empty, as), aphase ^ 1));
-                tc_fence_after();
+                TIMED(c_fence, tc_fence_after());
                 const uint32_t d_base = tmem_base + as * (acc_cols * (uint32_t)NACC);
                 uint32_t accumulate = 0;
                 for (int sa = 0; sa < p.n_sa; ++sa) {
                     for (int sb = 0; sb < p.n_sb; ++sb) {
-                        if (u == 0) { TIMED(c_pix, mbar_wait(BAR(pix_full, pslot), pphase)); tc_fence_after(); }
+                        if (u == 0) { TIMED(c_pix, mbar_wait(BAR(pix_full, pslot), pphase)); TIMED(c_fence, tc_fence_after()); }
                         int j = 0;
                         for (int g = 0; g < slots_per_stage; ++g) {
                             const int nst = min(G, n_steps - j);
-                            if (!resident) { TIMED(c_w, mbar_wait(BAR(w_full, wslot), wphase)); tc_fence_after(); }
+                            if (!resident) { TIMED(c_w, mbar_wait(BAR(w_full, wslot), wphase)); TIMED(c_fence, tc_fence_after()); }
                             const long long t_issue = prof ? clock64() : 0;
                             if (elect_one()) {
                                 const uint64_t* ta = resident ? tabA + sa * n_steps + j : tabA + wslot * G;
@@ -420,7 +472,7 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
                                     accumulate = 1;
                                 }
                                 if (!resident) umma_commit(BAR(w_empty, wslot));
-                                if (g == slots_per_stage - 1 && u == p.n_u - 1) umma_commit(BAR(pix_empty, pslot));
+                                if (g == slots_per_stage - 1 && u == n_u_eff - 1) umma_commit(BAR(pix_empty, pslot));
                             }
                             __syncwarp();
                             if (prof) c_issue += clock64() - t_issue;
@@ -428,38 +480,48 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
                             j += nst;
                             if (!resident) { if (++wslot == (uint32_t)p.RW) { wslot = 0; wphase ^= 1; } }
                         }
-                        if (u == p.n_u - 1) { if (++pslot == (uint32_t)p.RP) { pslot = 0; pphase ^= 1; } }
+                        if (u == n_u_eff - 1) { if (++pslot == (uint32_t)p.RP) { pslot = 0; pphase ^= 1; } }
                     }
                 }
-                if (elect_one()) umma_commit(BAR(acc_full, as));
-                __syncwarp();
+                TIMED(c_tail, { if (elect_one()) umma_commit(BAR(acc_full, as)); __syncwarp(); });
                 if (++as == p.acc_stages) { as = 0; aphase ^= 1; }
             }
         }
 #undef TIMED
         if (prof && lane == 0) {
             long long* o = p.prof + (int64_t)blockIdx.x * 8;
-            o[0] = clock64() - c_begin; o[1] = c_acc; o[2] = c_pix; o[3] = c_w; o[4] = c_issue;
+            o[0] = clock64() - c_begin; o[1] = c_acc; o[2] = c_pix; o[3] = c_w; o[4] = c_issue; o[5] = c_fence; o[6] = c_tail;
         }
     } else if (warp >= 4) {
         // ===================== epilogue (128 threads, lane quarter = warp % 4) =====================
         const int q = warp & 3;
         const int m = q * 32 + lane;
         uint32_t as = 0, aphase = 0;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x)
-            for (int u = 0; u < p.n_u; ++u) {
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            const int tile_pix = tile / p.ug_count, u0 = (tile % p.ug_count) * p.n_u;
+            const int n_u_eff = min(p.n_u, p.nu_total - u0);
+            for (int u = 0; u < n_u_eff; ++u) {
                 mbar_wait<true>(BAR(acc_full, as), aphase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * (p.acc_cols * (uint32_t)p.n_acc);
-                if (EPI == EPI_RAW) epi_raw(p, tile, u, taddr, m, p.smem_epi_off ? reinterpret_cast<float*>(base_ptr + p.smem_epi_off) : nullptr);
-                else if (EPI == EPI_L0) epi_l0(p, tile, taddr, m);
-                else if (EPI == EPI_L1) epi_l1(p, tile, taddr, m);
-                else epi_l2(p, tile, taddr, m);
+                const bool work = !(p.dbg & 4);
+                if (work) {
+                    if (EPI == EPI_RAW) epi_raw(p, (int64_t)tile_pix * p.nu_total + u0 + u, taddr, m, p.smem_epi_off ? reinterpret_cast<float*>(base_ptr + p.smem_epi_off) : nullptr);
+                    else if (EPI == EPI_L0) epi_l0(p, tile, taddr, m);
+                    else if (EPI == EPI_L1) epi_l1_drain(p, tile, taddr, m, reinterpret_cast<uint16_t*>(base_ptr + p.smem_stash_off));
+                    else epi_l2(p, tile, taddr, m);
+                }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(BAR(acc_empty, as));
+                if (EPI == EPI_L1 && work) {
+                    // the accumulator is free again: scatter the stashed tile while the next one is computed
+                    epi_l1_store(p, tile, q, lane, reinterpret_cast<const uint16_t*>(base_ptr + p.smem_stash_off));
+                    __syncwarp();       // the stash rows of this warp are rewritten by the next drain
+                }
                 if (++as == p.acc_stages) { as = 0; aphase ^= 1; }
             }
+        }
     }
     // ===================== teardown =====================
     tc_fence_before();
@@ -484,7 +546,7 @@ static int env_int(const char* name, int dflt) {
     return (v && *v) ? atoi(v) : dflt;
 }
 
-static int finalize_smem(WsParams& p, uint32_t w_region, uint32_t* smem_total, bool epi_scratch = false) {
+static int finalize_smem(WsParams& p, uint32_t w_region, uint32_t* smem_total, bool epi_scratch = false, int stash_rows = 0) {
     {
         const int G = p.w_resident ? p.n_steps : p.G;
         for (int j = 0; j < p.n_steps; ++j) {
@@ -498,6 +560,8 @@ static int finalize_smem(WsParams& p, uint32_t w_region, uint32_t* smem_total, b
     uint32_t total = p.smem_pix_off + (uint32_t)p.RP * p.stage_pitch;
     p.smem_epi_off = 0;
     if (epi_scratch) { p.smem_epi_off = align_up(total, 128); total = p.smem_epi_off + 4 * 32 * 33 * 4; }
+    p.smem_stash_off = 0;
+    if (stash_rows) { p.smem_stash_off = align_up(total, 128); total = p.smem_stash_off + (uint32_t)stash_rows * kStashPitch * 2; }
     total += 1024;                                  // manual 1024-byte alignment slack
     if (total < 120 * 1024) total = 120 * 1024;     // one CTA per SM: every CTA allocates all 512 TMEM columns
     VD_REQUIRE(total <= 232448, "tc conv: shared memory budget exceeded (%u bytes)", total);
@@ -506,7 +570,7 @@ static int finalize_smem(WsParams& p, uint32_t w_region, uint32_t* smem_total, b
 }
 
 static int setup_l0(WsParams& p, const Geo& g, int B, uint32_t* smem) {
-    p.n_u = 1; p.w_u_stride = 0;
+    p.n_u = 1; p.nu_total = 1; p.ug_count = 1; p.w_u_stride = 0;
     p.n_tiles = B * (g.T / 2) * (g.Ho0 / g.R0);
     p.tiles_per_item = (g.T / 2) * (g.Ho0 / g.R0);
     p.v_count = g.Ho0 / g.R0;
@@ -547,7 +611,7 @@ static int setup_l0(WsParams& p, const Geo& g, int B, uint32_t* smem) {
 }
 
 static int setup_l1(WsParams& p, const Geo& g, int B, uint32_t* smem) {
-    p.n_u = 1; p.w_u_stride = 0;
+    p.n_u = 1; p.nu_total = 1; p.ug_count = 1; p.w_u_stride = 0;
     p.n_tiles = B * (g.T / 2);
     p.tiles_per_item = g.T / 2; p.v_count = 1;
     p.item_stride = g.video1; p.u_stride = 2 * g.frame1; p.v_stride = 0;
@@ -568,11 +632,11 @@ static int setup_l1(WsParams& p, const Geo& g, int B, uint32_t* smem) {
     p.n_acc = 2; p.acc_delta16 = (uint32_t)g.frame1 >> 4;
     p.ncols = g.N1; p.acc_cols = 256; p.acc_stages = 1;
     p.idesc = umma_idesc_bf16(128, g.N1);
-    return finalize_smem(p, (uint32_t)p.G * p.RW * kWeightTileBytes, smem);
+    return finalize_smem(p, (uint32_t)p.G * p.RW * kWeightTileBytes, smem, false, g.H2 * g.H2);
 }
 
 static int setup_l2(WsParams& p, const Geo& g, int B, uint32_t* smem) {
-    p.n_u = 1; p.w_u_stride = 0;
+    p.n_u = 1; p.nu_total = 1; p.ug_count = 1; p.w_u_stride = 0;
     const int VPT = kVideosPerTile2;
     p.n_tiles = (B + VPT - 1) / VPT;
     p.tiles_per_item = 1; p.v_count = 1;
@@ -603,9 +667,14 @@ static int setup_l2(WsParams& p, const Geo& g, int B, uint32_t* smem) {
 static int setup_bwd(WsParams& p, const Geo& g, int layer, int B, uint32_t* smem) {
     const BwdGeo b = make_bwd_geo(g, layer);
     VD_REQUIRE(b.pixels % 16 == 0, "tc bwd: pixel count must be a multiple of 16");
-    p.n_tiles = B * b.NT; p.tiles_per_item = b.NT; p.v_count = b.NT;
+    // enough CTA tiles for two waves even at small B: split the NU row tiles of a pixel stage over ug_count CTAs
+    int ug = (2 * 148 + B * b.NT - 1) / (B * b.NT);
+    if (ug < 1) ug = 1;
+    if (ug > b.NU) ug = b.NU;
+    p.nu_total = b.NU; p.n_u = (b.NU + ug - 1) / ug; p.ug_count = (b.NU + p.n_u - 1) / p.n_u;
+    p.n_tiles = B * b.NT * p.ug_count; p.tiles_per_item = b.NT; p.v_count = b.NT;
     p.item_stride = b.dy_video; p.u_stride = 0; p.v_stride = (int64_t)(b.K / 8) * b.NC * 16;
-    p.n_u = b.NU; p.w_u_stride = (int64_t)b.n_steps * kWeightTileBytes;
+    p.w_u_stride = (int64_t)b.n_steps * kWeightTileBytes;
     p.n_sa = 1; p.n_sb = 1; p.sa_stride = 0; p.sb_stride = 0;
     p.n_copies = 1; p.copy_gofs[0] = 0; p.copy_sofs[0] = 0; p.copy_bytes[0] = (uint32_t)((b.K / 8) * b.NC * 16);
     p.stage_bytes = p.copy_bytes[0];
@@ -617,7 +686,7 @@ static int setup_bwd(WsParams& p, const Geo& g, int layer, int B, uint32_t* smem
     p.n_acc = 1; p.acc_delta16 = 0;
     p.ncols = b.NC; p.acc_cols = 256; p.acc_stages = 2;
     p.idesc = umma_idesc_bf16(128, b.NC);
-    return finalize_smem(p, (uint32_t)p.G * p.RW * kWeightTileBytes, smem, true);
+    return finalize_smem(p, (uint32_t)p.G * p.RW * kWeightTileBytes, smem, false);
 }
 
 template <int EPI, int NACC>
@@ -703,7 +772,7 @@ extern "C" int vd_tc_conv_layer(int layer, const void* in, const void* wimg, con
     if (rc) { if (rc == -2) set_error("tc conv 0: non-monotone chunk pairing"); return rc; }
     VD_REQUIRE(item_index == nullptr || layer == 0, "tc_conv_layer: item_index is only valid for layer 0");
     p.pix = (const uint8_t*)in; p.wimg = (const uint8_t*)wimg; p.item_index = item_index;
-    p.prof = g_prof;
+    p.prof = g_prof; p.dbg = env_int("VD_TC_DBG", 0);
     p.epi.bias = bias; p.epi.out = (uint8_t*)out; p.epi.code = code; p.epi.raw = (float*)out;
     p.epi.T = plan->T; p.epi.n_items = B; p.epi.g = g;
     cudaStream_t s = (cudaStream_t)stream;
@@ -770,7 +839,7 @@ extern "C" int vd_tc_probe(const void* pix, const void* wimg, float* raw, int nc
     WsParams p;
     memset(&p, 0, sizeof(p));
     p.n_tiles = 148; p.tiles_per_item = 148; p.v_count = 148; p.item_stride = 0; p.u_stride = 0; p.v_stride = 0;
-    p.n_u = 1; p.w_u_stride = 0;
+    p.n_u = 1; p.nu_total = 1; p.ug_count = 1; p.w_u_stride = 0;
     p.n_sa = n_sa; p.n_sb = 1; p.sa_stride = 0; p.sb_stride = 0;
     p.n_copies = 1; p.copy_gofs[0] = 0; p.copy_sofs[0] = 0; p.copy_bytes[0] = 65536; p.stage_bytes = 65536;
     p.n_steps = n_steps;

@@ -109,11 +109,15 @@ class TcConvNet3D:
         """Differentiable embed (gradient flows to ``video`` only; the net is frozen as in DM)."""
         return _TcEmbed.apply(video, self)
 
-    def _buffers(self, n):
+    def _buffers(self, n, n_total=None):
+        """a1 for one chunk of ``n`` videos, a2 for ``n_total`` (>= n) videos: conv 2 runs ONCE over all
+        chunks of an embed call (its tiles are 4 videos wide, so small launches waste most of a wave)."""
         p = self.plan
-        n4 = (n + 3) // 4 * 4
+        n_total = n if n_total is None else n_total
+        n4 = (n_total + 3) // 4 * 4
         if self._a1 is None or self._a1.numel() < n * p.a1_bytes_per_video:
             self._a1 = torch.zeros(n * p.a1_bytes_per_video, dtype=torch.uint8, device=self.device)
+        if self._a2 is None or self._a2.numel() < n4 * p.a2_bytes_per_video:
             self._a2 = torch.zeros(n4 * p.a2_bytes_per_video, dtype=torch.uint8, device=self.device)
         return self._a1, self._a2
 
@@ -157,6 +161,21 @@ class TcConvNet3D:
         self.conv_layer(2, a2, self.w2, self.b2, out, B, code=c2)
         return out
 
+    def _embed_chunks(self, B, out, codes, front):
+        """conv 0 + conv 1 per chunk of max_batch videos (``front(s, e)`` -> (x0, item_index)), every
+        chunk writing its slice of one A2 buffer; then ONE conv-2 launch over all B videos."""
+        p = self.plan
+        step = max(4, self.max_batch // 4 * 4)              # conv-2 tiles hold 4 consecutive videos
+        a1, a2 = self._buffers(min(B, step), B)
+        c0, c1, c2 = codes if codes is not None else (None, None, None)
+        for s in range(0, B, step):
+            e = min(B, s + step)
+            x0, idx = front(s, e)
+            self.conv_layer(0, x0, self.w0, self.b0, a1, e - s, code=None if c0 is None else c0[s:e], item_index=idx)
+            self.conv_layer(1, a1, self.w1, self.b1, a2[s * p.a2_bytes_per_video:], e - s, code=None if c1 is None else c1[s:e])
+        self.conv_layer(2, a2, self.w2, self.b2, out, B, code=c2)
+        return out
+
     def alloc_codes(self, B):
         p = self.plan
         u8 = dict(dtype=torch.uint8, device=self.device)
@@ -178,23 +197,20 @@ class TcConvNet3D:
         """embed of the videos ``index`` (device int64) of a pre-packed resident set."""
         B = int(index.numel())
         out = torch.empty(B, self.embed_dim, dtype=torch.float32, device=self.device)
-        for s in range(0, B, self.max_batch):
-            e = min(B, s + self.max_batch)
-            self.embed_packed(x0_all, e - s, item_index=index[s:e].contiguous(), out=out[s:e])
-        return out
+        index = index.contiguous()
+        return self._embed_chunks(B, out, None, lambda s, e: (x0_all, index[s:e]))
 
     def embed(self, video, index=None, want_codes=False):
         """ConvNet3D.embed on fp32 videos (B,T,3,H,W) -> (B, embed_dim) fp32, in chunks of max_batch."""
         B = int(index.numel()) if index is not None else int(video.shape[0])
         out = torch.empty(B, self.embed_dim, dtype=torch.float32, device=self.device)
         codes = self.alloc_codes(B) if want_codes else None
-        for s in range(0, B, self.max_batch):
-            e = min(B, s + self.max_batch)
-            idx = index[s:e] if index is not None else None
-            vid = video if index is not None else video[s:e]
-            x0 = self.pack_video(vid, idx)
-            cc = tuple(c[s:e] for c in codes) if codes is not None else None
-            self.embed_packed(x0, e - s, out=out[s:e], codes=cc)
+
+        def front(s, e):
+            if index is not None:
+                return self.pack_video(video, index[s:e]), None
+            return self.pack_video(video[s:e]), None
+        self._embed_chunks(B, out, codes, front)
         return (out, codes) if want_codes else out
 
 
