@@ -71,14 +71,17 @@ __device__ __forceinline__ float bf2f(uint16_t v) { return __uint_as_float((uint
 constexpr int kC2iMaxOut = 8;            // input pixels per thread (band * Wi <= 256 * kC2iMaxOut)
 
 struct C2iBlock {
-    int vid, ci, t, hb, h_end, ho0, npix;
+    int vid, ci0, t, hb, h_end, ho0, npix;
 };
 
-__device__ __forceinline__ C2iBlock c2i_block(const BwdGeo& b, int band) {
+// block -> (video, group of `cib` input channels, frame t, band of `band` input rows); the channel group is the
+// fastest index so that blocks writing neighbouring channels of the same dY chunks run concurrently (L2 merge)
+__device__ __forceinline__ C2iBlock c2i_block(const BwdGeo& b, int band, int cib) {
     C2iBlock k;
     const int nb = (b.Hi + band - 1) / band;
-    int q = blockIdx.x;                                   // ci fastest: the 8 channels of a 16-byte dY chunk are written
-    k.ci = q % b.Cin; q /= b.Cin;                         // by concurrently running blocks and merge in L2
+    const int ngrp = b.Cin / cib;
+    int q = blockIdx.x;
+    k.ci0 = (q % ngrp) * cib; q /= ngrp;
     const int ib = q % nb; q /= nb;
     k.t = q % b.Ti; k.vid = q / b.Ti;
     k.hb = ib * band;
@@ -87,20 +90,6 @@ __device__ __forceinline__ C2iBlock c2i_block(const BwdGeo& b, int band) {
     const int ho1 = min(b.Ho - 1, (k.h_end + 2) / 2);     // largest ho with 2*ho + kh - 3 <= h_end - 1 for some kh >= 0
     k.npix = (ho1 - k.ho0 + 1) * b.Wo;
     return k;
-}
-
-// stage rows (ci, kt, 0..48) x pixels [pix0, pix0 + npix) of one video's column buffer: smem[tap][npix] (bf16 pairs)
-__device__ __forceinline__ void c2i_stage(const uint16_t* __restrict__ colv, const BwdGeo& b, int ci, int kt, int pix0, int npix,
-                                          uint32_t* __restrict__ sm, int pitch2) {
-    const int np2 = npix >> 1;
-    for (int i = threadIdx.x; i < 49 * np2; i += blockDim.x) {
-        const int tap = i / np2, j = i - tap * np2;
-        const int r = ci * 147 + kt * 49 + tap;
-        const int pix = pix0 + 2 * j;
-        const int nt = (int)__umulhi((uint32_t)pix, b.nc_magic), col = pix - nt * b.NC;
-        sm[tap * pitch2 + j] = __ldg(reinterpret_cast<const uint32_t*>(
-            colv + (((int64_t)nt * b.NU + (r >> 7)) * 128 + (r & 127)) * b.NC + col));
-    }
 }
 
 // gather the (kh,kw) taps of input pixel (h,w) from the staged rows of one kt
@@ -123,16 +112,20 @@ __device__ __forceinline__ float c2i_taps(const uint16_t* __restrict__ sm16, int
     return acc;
 }
 
+// Generic kernel (small / odd-width frames, e.g. the 7x7 input of conv 2): one thread per input pixel of
+// `cib` channels; rows staged as bf16 pairs with plain loads.
 // layers 2 and 1: every thread owns POOLED elements (ci,t,h,w) of the layer below and writes the whole
 // pool window (pt x 2 x 2 conv outputs) of the next dY: the routed gradient at the recorded argmax,
 // zeros elsewhere -> dY below is fully overwritten, no memset needed.
 // layer 0 (code == nullptr): writes d video (B, T, 3, H, W) fp32.
 __global__ void __launch_bounds__(256) col2im_kernel(const uint16_t* __restrict__ colbuf, const uint8_t* __restrict__ code,
-                                                     void* __restrict__ out, BwdGeo b, BwdGeo bb, int pt, int band, int pitch) {
+                                                     void* __restrict__ out, BwdGeo b, BwdGeo bb, int pt, int band, int pitch, int cib) {
     extern __shared__ uint32_t c2i_smem[];
-    const C2iBlock k = c2i_block(b, band);
+    const C2iBlock k = c2i_block(b, band, cib);
     const uint16_t* colv = colbuf + (int64_t)k.vid * b.col_video_elems;
     const int n_out = (k.h_end - k.hb) * b.Wi;
+    const int n_all = cib * n_out;
+    const int np2 = k.npix >> 1, pitch2 = pitch >> 1;
     float acc[kC2iMaxOut];
 #pragma unroll
     for (int j = 0; j < kC2iMaxOut; ++j) acc[j] = 0.f;
@@ -140,32 +133,43 @@ __global__ void __launch_bounds__(256) col2im_kernel(const uint16_t* __restrict_
         const int to = k.t + 1 - kt;
         if ((unsigned)to >= (unsigned)b.To) continue;                 // block-uniform
         __syncthreads();
-        c2i_stage(colv, b, k.ci, kt, (to * b.Ho + k.ho0) * b.Wo, k.npix, c2i_smem, pitch >> 1);
+        const int pix0 = (to * b.Ho + k.ho0) * b.Wo;
+        for (int i = threadIdx.x; i < cib * 49 * np2; i += blockDim.x) {
+            const int row = i / np2, j = i - row * np2;              // row = ci_local * 49 + tap
+            const int cl = row / 49, tap = row - cl * 49;
+            const int r = (k.ci0 + cl) * 147 + kt * 49 + tap;
+            const int pix = pix0 + 2 * j;
+            const int nt = (int)__umulhi((uint32_t)pix, b.nc_magic), col = pix - nt * b.NC;
+            c2i_smem[row * pitch2 + j] = __ldg(reinterpret_cast<const uint32_t*>(
+                colv + (((int64_t)nt * b.NU + (r >> 7)) * 128 + (r & 127)) * b.NC + col));
+        }
         __syncthreads();
 #pragma unroll
         for (int j = 0; j < kC2iMaxOut; ++j) {
             const int i = threadIdx.x + j * 256;
-            if (i < n_out) {
-                const int hl = i / b.Wi, w = i - hl * b.Wi;
-                acc[j] += c2i_taps(reinterpret_cast<const uint16_t*>(c2i_smem), pitch, b, k.ho0, k.hb + hl, w);
+            if (i < n_all) {
+                const int cl = i / n_out, o = i - cl * n_out;
+                const int hl = o / b.Wi, w = o - hl * b.Wi;
+                acc[j] += c2i_taps(reinterpret_cast<const uint16_t*>(c2i_smem) + cl * 49 * pitch, pitch, b, k.ho0, k.hb + hl, w);
             }
         }
     }
 #pragma unroll
     for (int j = 0; j < kC2iMaxOut; ++j) {
         const int i = threadIdx.x + j * 256;
-        if (i >= n_out) continue;
-        const int hl = i / b.Wi, w = i - hl * b.Wi, h = k.hb + hl;
+        if (i >= n_all) continue;
+        const int cl = i / n_out, o = i - cl * n_out;
+        const int hl = o / b.Wi, w = o - hl * b.Wi, h = k.hb + hl, ci = k.ci0 + cl;
         if (code == nullptr) {
             float* dv = reinterpret_cast<float*>(out);
-            dv[((((int64_t)k.vid * b.Ti + k.t) * 3 + k.ci) * b.Hi + h) * b.Wi + w] = acc[j];
+            dv[((((int64_t)k.vid * b.Ti + k.t) * 3 + ci) * b.Hi + h) * b.Wi + w] = acc[j];
             continue;
         }
-        const uint8_t cd = code[((((int64_t)k.vid * b.Cin + k.ci) * b.Ti + k.t) * b.Hi + h) * b.Wi + w];
+        const uint8_t cd = code[((((int64_t)k.vid * b.Cin + ci) * b.Ti + k.t) * b.Hi + h) * b.Wi + w];
         const uint16_t gv = f2bf((cd & 8) ? acc[j] : 0.f);
         const int arg = cd & 7;
         uint16_t* base = reinterpret_cast<uint16_t*>(out) + (int64_t)k.vid * (bb.dy_video / 2);
-        const int chunk = k.ci >> 3, e = k.ci & 7;
+        const int chunk = ci >> 3, e = ci & 7;
         int pos = 0;
         for (int dt = 0; dt < pt; ++dt)
             for (int dh = 0; dh < 2; ++dh)
@@ -174,6 +178,157 @@ __global__ void __launch_bounds__(256) col2im_kernel(const uint16_t* __restrict_
                     const int nt = (int)__umulhi((uint32_t)pix, bb.nc_magic), col = pix - nt * bb.NC;
                     base[(((int64_t)nt * (bb.K / 8) + chunk) * bb.NC + col) * 8 + e] = (pos == arg) ? gv : (uint16_t)0;
                 }
+    }
+}
+
+// ---- fast path (conv 1 and conv 0: even widths, Wi/2 a multiple of SEG) -----------------------------------
+// Thread = (input row h of the band, column parity, segment of SEG same-parity columns): SEG register
+// accumulators, every staged column value is touched by exactly one LDS + shift + add.  Staging uses
+// cp.async (LDGSTS) of V bf16 per request, so many requests per thread are in flight without registers.
+template <int BYTES>
+__device__ __forceinline__ void cp_async(uint32_t dst_smem, const void* src) {
+    if (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+    else if (BYTES == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst_smem), "l"(src) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int SEG, int PAR>
+__device__ __forceinline__ void c2i_row_taps(float (&acc)[SEG], const uint16_t* __restrict__ sm16, int pitch, const BwdGeo& b,
+                                             int ho0, int h, int seg, bool l_ok, bool r_ok) {
+    for (int kh = (h + 1) & 1; kh < 7; kh += 2) {
+        const int hh = h + 3 - kh;
+        if (hh < 0) continue;
+        const int ho = hh >> 1;
+        if (ho >= b.Ho) continue;
+        const uint16_t* row = sm16 + (kh * 7) * pitch + (ho - ho0) * b.Wo + seg * SEG;
+#pragma unroll
+        for (int kw = (PAR + 1) & 1; kw < 7; kw += 2) {
+            const int s = (PAR + 3 - kw) / 2;                                   // PAR+3-kw is even: exact, in {2,1,0,-1}
+            const uint16_t* src = row + kw * pitch + s;
+#pragma unroll
+            for (int j = 0; j < SEG; ++j) {
+                const bool ok = (j + s < 0) ? l_ok : ((j + s >= SEG) ? r_ok : true);
+                if (ok) acc[j] += bf2f(src[j]);
+            }
+        }
+    }
+}
+
+// Block = `lanes_ch` channel lanes of `tpc` threads; lane c walks channels ci0 + c, ci0 + c + lanes_ch, ... of the
+// block's `cib` channels with private staging buffers and its own named barrier, so that the lanes' staging
+// latencies and tap sums interleave (the SM always has many warps to issue from).
+template <int SEG, int V>
+__global__ void __launch_bounds__(512) col2im_rows_kernel(const uint16_t* __restrict__ colbuf, const uint8_t* __restrict__ code,
+                                                          void* __restrict__ out, BwdGeo b, BwdGeo bb, int pt, int band, int pitch,
+                                                          int warps_per_par, int cib, int lanes_ch, int nbuf, int stash_off) {
+    // shared memory: lanes_ch * nbuf staging buffers [49][pitch] bf16, then (route mode) the stash
+    // [cib][n_out] u32 = bf16 << 16 | argmax
+    extern __shared__ uint32_t c2i_smem[];
+    const C2iBlock k = c2i_block(b, band, cib);
+    const uint16_t* colv = colbuf + (int64_t)k.vid * b.col_video_elems;
+    const uint16_t* sm16 = reinterpret_cast<const uint16_t*>(c2i_smem);
+    uint32_t* stash = c2i_smem + stash_off;
+    const uint32_t sm_base = smem_u32(c2i_smem);
+    const int stage_elems = 49 * pitch;
+    const int nseg = (b.Wi / 2) / SEG;
+    const int tpc = 2 * warps_per_par * 32;
+    const int chl = (int)threadIdx.x / tpc, tid = (int)threadIdx.x - chl * tpc;
+    const int warp = tid >> 5, lane = tid & 31, nwarp = tpc >> 5;
+    const int par = warp / warps_per_par;
+    const int idx = (warp - par * warps_per_par) * 32 + lane;
+    const int hl = idx / nseg, seg = idx - hl * nseg;
+    const int h = k.hb + hl;
+    const bool active = h < k.h_end;
+    const bool l_ok = seg > 0, r_ok = seg < nseg - 1;
+    const int n_out = (k.h_end - k.hb) * b.Wi;
+    float acc[SEG];
+#pragma unroll
+    for (int j = 0; j < SEG; ++j) acc[j] = 0.f;
+    const int nvec = k.npix / V;
+    // valid temporal taps: 0 <= t + 1 - kt < To
+    const int kt_lo = max(0, k.t + 2 - b.To), kt_hi = min(2, k.t + 1);
+    const int nkt = kt_hi - kt_lo + 1;
+    const int n_stage = (cib / lanes_ch) * nkt;
+    const int64_t tile_pitch = (int64_t)b.NU * 128 * b.NC;
+    const int bar_id = 1 + chl;
+
+    auto lane_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(tpc) : "memory"); };
+    auto issue = [&](int st) {
+        // one warp per tap row; a V-element vector never straddles an NC tile (pix0 and NC are multiples of V)
+        const int ci = k.ci0 + chl + (st / nkt) * lanes_ch, kt = kt_lo + st % nkt;
+        const int to = k.t + 1 - kt;
+        const int pix0 = (to * b.Ho + k.ho0) * b.Wo;
+        const uint32_t buf = sm_base + (uint32_t)((chl * nbuf + st % nbuf) * stage_elems) * 2u;
+        for (int tap = warp; tap < 49; tap += nwarp) {
+            const int r = ci * 147 + kt * 49 + tap;
+            const uint16_t* rbase = colv + ((int64_t)(r >> 7) * 128 + (r & 127)) * b.NC;
+            const uint32_t dst = buf + (uint32_t)(tap * pitch) * 2u;
+            for (int j = lane; j < nvec; j += 32) {
+                const int pix = pix0 + j * V;
+                const int nt = (int)__umulhi((uint32_t)pix, b.nc_magic), col = pix - nt * b.NC;
+                cp_async<2 * V>(dst + (uint32_t)j * (2u * V), rbase + nt * tile_pitch + col);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    if (nbuf > 1) issue(0);
+    for (int st = 0; st < n_stage; ++st) {
+        if (nbuf > 1) {
+            if (st + 1 < n_stage) { issue(st + 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+            else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        } else {
+            issue(st);
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        lane_sync();
+        if (active) {
+            const uint16_t* buf16 = sm16 + (chl * nbuf + st % nbuf) * stage_elems;
+            if (par == 0) c2i_row_taps<SEG, 0>(acc, buf16, pitch, b, k.ho0, h, seg, l_ok, r_ok);
+            else c2i_row_taps<SEG, 1>(acc, buf16, pitch, b, k.ho0, h, seg, l_ok, r_ok);
+            if (st % nkt == nkt - 1) {                                // last temporal tap of this channel
+                const int cl = chl + (st / nkt) * lanes_ch, ci = k.ci0 + cl;
+                if (code == nullptr) {
+                    float* dv = reinterpret_cast<float*>(out) + ((((int64_t)k.vid * b.Ti + k.t) * 3 + ci) * b.Hi + h) * b.Wi + 2 * seg * SEG + par;
+#pragma unroll
+                    for (int j = 0; j < SEG; ++j) { dv[2 * j] = acc[j]; acc[j] = 0.f; }
+                } else {
+                    const uint8_t* cd_row = code + ((((int64_t)k.vid * b.Cin + ci) * b.Ti + k.t) * b.Hi + h) * b.Wi + 2 * seg * SEG + par;
+                    uint32_t* srow = stash + cl * n_out + hl * b.Wi + 2 * seg * SEG + par;
+#pragma unroll
+                    for (int j = 0; j < SEG; ++j) {
+                        const uint32_t cd = cd_row[2 * j];
+                        srow[2 * j] = ((uint32_t)f2bf((cd & 8) ? acc[j] : 0.f) << 16) | (cd & 7);
+                        acc[j] = 0.f;
+                    }
+                }
+            }
+        }
+        lane_sync();                                                  // buffer st % nbuf may be refilled now
+    }
+    if (code == nullptr) return;
+    // route mode: the stash holds `cib` (= 8) channels = one 16-byte chunk of dY below.  One thread per output
+    // pixel of the pool windows: the routed gradient where the pixel is the recorded argmax, zero elsewhere.
+    __syncthreads();
+    uint16_t* base = reinterpret_cast<uint16_t*>(out) + (int64_t)k.vid * (bb.dy_video / 2);
+    const int rows2 = 2 * (k.h_end - k.hb), cols2 = 2 * b.Wi;
+    const int chunk = k.ci0 >> 3;
+    for (int pidx = threadIdx.x; pidx < pt * rows2 * cols2; pidx += blockDim.x) {
+        const int ww = pidx % cols2; int q = pidx / cols2;
+        const int hh = q % rows2, dt = q / rows2;
+        const uint32_t pos = (uint32_t)(dt * 4 + (hh & 1) * 2 + (ww & 1));
+        const uint32_t* sp = stash + (hh >> 1) * b.Wi + (ww >> 1);
+        uint32_t v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const uint32_t x = (e < cib) ? sp[e * n_out] : 0u;
+            v[e] = ((x & 7u) == pos) ? (x >> 16) : 0u;
+        }
+        const int pix = ((k.t * pt + dt) * bb.Ho + (2 * k.hb + hh)) * bb.Wo + ww;
+        const int nt = (int)__umulhi((uint32_t)pix, bb.nc_magic), col = pix - nt * bb.NC;
+        *reinterpret_cast<uint4*>(base + (((int64_t)nt * (bb.K / 8) + chunk) * bb.NC + col) * 8) =
+            make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
     }
 }
 
@@ -227,28 +382,63 @@ extern "C" int vd_tc_bwd_col2im(int layer, const void* col, const uint8_t* code_
     const BwdGeo b = make_bwd_geo(g, layer);
     cudaStream_t s = (cudaStream_t)stream;
     VD_REQUIRE(b.Wo % 2 == 0 && b.NC % 2 == 0, "tc_bwd_col2im: odd output width");
-    // band of input rows per block: the whole frame when it fits kC2iMaxOut pixels per thread, else 16 rows
+    // band of input rows per block: the whole frame when it fits kC2iMaxOut pixels per thread, else halved
     int band = b.Hi;
     while ((int64_t)band * b.Wi > 256 * kC2iMaxOut) band = (band + 1) / 2;
     const int n_ho = (band + 2) / 2 + 2;
     const int npix_max = (n_ho < b.Ho ? n_ho : b.Ho) * b.Wo;
-    const int pitch = (npix_max + 2) | 2;                 // bf16 elements per staged row (even, odd number of words)
-    const size_t smem = (size_t)49 * pitch * 2;
+    const int pitch = ((npix_max + 7) / 8 * 8) | 8;       // bf16 elements per staged row: 16-byte aligned rows, odd multiple of 16 B
+    const size_t stage_bytes = (size_t)49 * pitch * 2;
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(col2im_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+#define VD_C2I_ATTR(S_, V_) cudaFuncSetAttribute(col2im_rows_kernel<S_, V_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)
+        VD_C2I_ATTR(7, 8); VD_C2I_ATTR(7, 4); VD_C2I_ATTR(7, 2); VD_C2I_ATTR(8, 8); VD_C2I_ATTR(8, 4); VD_C2I_ATTR(8, 2);
+#undef VD_C2I_ATTR
         configured = true;
     }
-    VD_REQUIRE(smem <= 96 * 1024, "tc_bwd_col2im: staging buffer too large (%zu bytes)", smem);
     const int nb = (b.Hi + band - 1) / band;
-    const int64_t blocks = (int64_t)B * b.Cin * b.Ti * nb;
-    VD_REQUIRE(blocks < (1ll << 31), "tc_bwd_col2im: grid too large");
     BwdGeo bb = b;
     int pt = 1;
     if (layer > 0) {
         bb = make_bwd_geo(g, layer - 1);
         pt = (layer == 2) ? 2 : 1;             // pool window of the layer below in T: conv1 -> (2,2,2), conv0 -> (1,2,2)
     }
-    col2im_kernel<<<(unsigned)blocks, 256, smem, s>>>((const uint16_t*)col, layer == 0 ? nullptr : code_below, out, b, bb, pt, band, pitch);
+    const uint8_t* cd = layer == 0 ? nullptr : code_below;
+    // fast path: SEG same-parity columns per thread, V-element vector staging; route mode: 8 channels (one dY
+    // chunk) per block on 4 concurrent channel lanes
+    const int half = b.Wi / 2;
+    const int SEG = (b.Wi % 2 == 0 && half % 7 == 0) ? 7 : ((b.Wi % 2 == 0 && half % 8 == 0) ? 8 : 0);
+    int V = 8;
+    const int align_unit = (nb == 1) ? b.Ho * b.Wo : b.Wo;           // pix0 and npix are multiples of this
+    while (V > 1 && (align_unit % V != 0 || b.NC % V != 0)) V >>= 1;
+    const int per_par = SEG ? (band * (half / SEG) + 31) / 32 : 0;   // warps per column parity
+    const int tpc = 2 * per_par * 32;                                // threads per channel lane
+    if (SEG != 0 && V >= 2 && tpc <= 512 && (layer == 0 || (b.Cin % 8 == 0 && bb.NC % 2 == 0))) {
+        const int cib = layer == 0 ? 1 : 8;
+        int lanes_ch = layer == 0 ? 1 : 4;
+        while (lanes_ch > 1 && (lanes_ch * tpc > 512 || lanes_ch * stage_bytes > 100 * 1024)) lanes_ch >>= 1;
+        const size_t stash_bytes = layer == 0 ? 0 : (size_t)cib * band * b.Wi * 4;
+        const int nbuf = (lanes_ch == 1 && 2 * stage_bytes + stash_bytes <= 76 * 1024) ? 2 : 1;
+        const size_t smem = (size_t)lanes_ch * nbuf * stage_bytes + stash_bytes;
+        VD_REQUIRE(smem <= 200 * 1024, "tc_bwd_col2im: shared memory budget exceeded (%zu bytes)", smem);
+        const int64_t blocks = (int64_t)B * (b.Cin / cib) * b.Ti * nb;
+        VD_REQUIRE(blocks < (1ll << 31), "tc_bwd_col2im: grid too large");
+        const int stash_off = (int)(lanes_ch * nbuf * stage_bytes / 4);
+        const int threads = lanes_ch * tpc;
+#define VD_C2I(S_, V_) col2im_rows_kernel<S_, V_><<<(unsigned)blocks, threads, smem, s>>>((const uint16_t*)col, cd, out, b, bb, pt, band, pitch, per_par, cib, lanes_ch, nbuf, stash_off)
+        if (SEG == 7) { if (V == 8) VD_C2I(7, 8); else if (V == 4) VD_C2I(7, 4); else VD_C2I(7, 2); }
+        else { if (V == 8) VD_C2I(8, 8); else if (V == 4) VD_C2I(8, 4); else VD_C2I(8, 2); }
+#undef VD_C2I
+        return check_launch("tc_bwd_col2im_rows");
+    }
+    // generic path: as many channels per block as fit 256 * kC2iMaxOut outputs and 96 KiB of staging
+    int cib = 8;
+    while (cib > 1 && (b.Cin % cib != 0 || (int64_t)cib * band * b.Wi > 256 * kC2iMaxOut || cib * stage_bytes > 96 * 1024)) cib >>= 1;
+    const size_t smem = cib * stage_bytes;
+    VD_REQUIRE(smem <= 96 * 1024, "tc_bwd_col2im: staging buffer too large (%zu bytes)", smem);
+    const int64_t blocks = (int64_t)B * (b.Cin / cib) * b.Ti * nb;
+    VD_REQUIRE(blocks < (1ll << 31), "tc_bwd_col2im: grid too large");
+    col2im_kernel<<<(unsigned)blocks, 256, smem, s>>>((const uint16_t*)col, cd, out, b, bb, pt, band, pitch, cib);
     return check_launch("tc_bwd_col2im");
 }

@@ -101,24 +101,43 @@ __device__ __forceinline__ void epi_raw(const WsParams& p, int64_t slot, uint32_
     for (int a = 0; a < p.n_acc; ++a) {
         const int64_t blk = (slot * p.n_acc + a) * 128;
         if (p.epi.raw_bf16) {
-            // backward column buffers: this thread's row, 32 columns = 64 contiguous bytes per step
-            uint16_t* dst = reinterpret_cast<uint16_t*>(p.epi.raw) + (blk + m) * (int64_t)p.ncols;
+            // backward column buffers (bf16).  A thread holds 32 columns (64 B) of its own row; lane pairs swap
+            // 16-byte pieces so that every store instruction writes whole 32-byte sectors (even lane: first half,
+            // odd lane: second half of the same sector) — half-filled sectors cost full L2 write slots.
+            uint16_t* row_own = reinterpret_cast<uint16_t*>(p.epi.raw) + (blk + m) * (int64_t)p.ncols;
+            uint16_t* row_peer = reinterpret_cast<uint16_t*>(p.epi.raw) + (blk + (m ^ 1)) * (int64_t)p.ncols;
+            const bool odd = m & 1;
+            uint16_t* row_a = odd ? row_peer : row_own;          // instructions 0,1 write the even lane's row
+            uint16_t* row_b = odd ? row_own : row_peer;          // instructions 2,3 write the odd lane's row
             uint32_t c = 0;
             for (; c + 32 <= p.ncols; c += 32) {
                 float v[32];
                 tmem_ld32(taddr + a * p.acc_cols + c, v);
                 tmem_ld_wait();
-                uint4* d4 = reinterpret_cast<uint4*>(dst + c);
+                uint4 pc[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
-                    d4[i] = make_uint4(pack_bf2(v[8 * i], v[8 * i + 1]), pack_bf2(v[8 * i + 2], v[8 * i + 3]),
+                    pc[i] = make_uint4(pack_bf2(v[8 * i], v[8 * i + 1]), pack_bf2(v[8 * i + 2], v[8 * i + 3]),
                                        pack_bf2(v[8 * i + 4], v[8 * i + 5]), pack_bf2(v[8 * i + 6], v[8 * i + 7]));
+                // even lane keeps pieces 0,2 of its row and needs pieces 0,2 of the odd row; odd lane keeps 1,3 and
+                // needs 1,3 of the even row: send what the peer needs, receive what this lane stores
+                const uint4 s0 = odd ? pc[0] : pc[1], s1 = odd ? pc[2] : pc[3];
+                uint4 r0, r1;
+                r0.x = __shfl_xor_sync(0xffffffffu, s0.x, 1); r0.y = __shfl_xor_sync(0xffffffffu, s0.y, 1);
+                r0.z = __shfl_xor_sync(0xffffffffu, s0.z, 1); r0.w = __shfl_xor_sync(0xffffffffu, s0.w, 1);
+                r1.x = __shfl_xor_sync(0xffffffffu, s1.x, 1); r1.y = __shfl_xor_sync(0xffffffffu, s1.y, 1);
+                r1.z = __shfl_xor_sync(0xffffffffu, s1.z, 1); r1.w = __shfl_xor_sync(0xffffffffu, s1.w, 1);
+                const int o = odd ? 8 : 0;                        // bf16 elements: odd lane writes the upper 16 bytes
+                *reinterpret_cast<uint4*>(row_a + c + o) = odd ? r0 : pc[0];
+                *reinterpret_cast<uint4*>(row_a + c + 16 + o) = odd ? r1 : pc[2];
+                *reinterpret_cast<uint4*>(row_b + c + o) = odd ? pc[1] : r0;
+                *reinterpret_cast<uint4*>(row_b + c + 16 + o) = odd ? pc[3] : r1;
             }
             for (; c < p.ncols; c += 16) {
                 float v[16];
                 tmem_ld16(taddr + a * p.acc_cols + c, v);
                 tmem_ld_wait();
-                uint4* d4 = reinterpret_cast<uint4*>(dst + c);
+                uint4* d4 = reinterpret_cast<uint4*>(row_own + c);
 #pragma unroll
                 for (int i = 0; i < 2; ++i)
                     d4[i] = make_uint4(pack_bf2(v[8 * i], v[8 * i + 1]), pack_bf2(v[8 * i + 2], v[8 * i + 3]),
