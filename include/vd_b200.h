@@ -180,12 +180,13 @@ int vd_tc_pack_weights(const float* w_l0, const float* w_l1, const float* w_l2,
  *            in the reference's NCDHW flatten order (networks.py:750).
  * A1 / A2 must be zeroed ONCE by the caller before first use (halo cells are never written,
  * data cells are fully overwritten by every call).  code may be NULL (real videos need no
- * backward).  item_index (device int64[B], layer 0 only, may be NULL) maps item -> video slot
+ * backward); otherwise items >= code_first_item record their routing codes at code[item - code_first_item]
+ * (a batch of frozen real videos followed by differentiable synthetic ones runs as ONE launch).  item_index (device int64[B], layer 0 only, may be NULL) maps item -> video slot
  * of `in`.  raw != 0 (bring-up / tests): skip the fused epilogue and dump the fp32
  * accumulators to out as [tile][acc][128][ncols]. */
 int vd_tc_conv_layer(int layer, const void* in, const void* wimg, const float* bias,
-                     void* out, uint8_t* code, const vd_tc_plan* plan, const int64_t* item_index,
-                     int B, int raw, void* stream);
+                     void* out, uint8_t* code, int code_first_item, const vd_tc_plan* plan,
+                     const int64_t* item_index, int B, int raw, void* stream);
 
 /* ---- backward of the tensor-core embed (gradient to the input video; weights are frozen in DM).
  * dgrad of each conv is a plain GEMM on tensor cores, col[(ci,tap), pixel] = sum_co W[co,ci,tap] *

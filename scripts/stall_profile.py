@@ -26,7 +26,7 @@ out = torch.empty(B, tc.embed_dim, device='cuda')
 lib.vd_tc_set_profile_buffer(_lib.ptr(buf))
 for layer, (src, w, b, dst, ii) in enumerate([(x0, tc.w0, tc.b0, a1, idx), (a1, tc.w1, tc.b1, a2, None), (a2, tc.w2, tc.b2, out, None)]):
     buf.zero_()
-    tc._conv_layer(layer, src, w, b, dst, B, None, ii, False)
+    tc._conv_layer(layer, src, w, b, dst, B, None, ii, False, 0)
     torch.cuda.synchronize()
     v = buf.cpu().view(148, 8).double().mean(0)
     tot = v[0].item()

@@ -24,7 +24,7 @@ ds = DeviceDataset.from_device_shard(vids, labels, C, dev, 0, 1)
 torch.manual_seed(0)
 tr = DMS2DTrainer(ds, num_classes=C, im_size=(HW, HW), frames=T, vpc=1, spc=2, dpc=2, batch_real=64, precision='bf16',
                   device=dev, init_on_device=True, max_batch=args.max_batch)
-ds.prepack(tr.embedder.tc)
+ds.prepack(tr.embedder.tc, extra_slots=len(tr.owned) * tr.vpc)
 np.random.seed(0)
 for i in range(3):
     tr.step(net_seed=i)

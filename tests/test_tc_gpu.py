@@ -216,3 +216,32 @@ def test_resident_prepacked_dataset_matches_per_step_packing():
     a = net.embed_resident(x0_all, idx)
     b = net.embed(videos, index=idx)
     assert torch.equal(a, b)
+
+
+def test_joint_real_and_synthetic_pass_matches_separate_passes():
+    """embed_joint (real videos of the resident set + synthetic videos in the spare slots, one launch per layer,
+    codes only for the synthetic tail) == separate real / synthetic embeds, bit for bit, across chunk borders."""
+    T, HW = 8, 64
+    net, _ = make_net(T, HW)
+    net.max_batch = 8                                   # force several chunks, one of them straddling real|syn
+    gen = torch.Generator().manual_seed(9)
+    videos = torch.randn(9, T, 3, HW, HW, generator=gen).cuda()
+    syn = torch.randn(5, T, 3, HW, HW, generator=gen).cuda()
+    idx = torch.tensor([5, 0, 3, 3, 6, 8, 1, 2, 7, 7, 4], device='cuda')
+    x0_all = net.pack_dataset(videos, chunk=4, extra_slots=5)
+    e_real, e_syn, codes = net.embed_joint(x0_all, idx, syn, 9)
+    ref_real = net.embed(videos, index=idx)
+    ref_syn, ref_codes = net.embed(syn, want_codes=True)
+    assert torch.equal(e_real, ref_real)
+    assert torch.equal(e_syn, ref_syn)
+    for a, b in zip(codes, ref_codes):
+        assert torch.equal(a, b)
+    # and the autograd wrapper routes the gradient to the synthetic videos only
+    v = syn.clone().requires_grad_(True)
+    er, es = net.embed_joint_autograd(x0_all, idx, v, 9)
+    assert not er.requires_grad
+    g = torch.randn(es.shape, generator=gen).cuda()
+    es.backward(g)
+    v2 = syn.clone().requires_grad_(True)
+    net.embed_autograd(v2).backward(g)
+    assert torch.equal(v.grad, v2.grad)

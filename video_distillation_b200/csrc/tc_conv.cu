@@ -32,6 +32,7 @@ struct EpiParams {
     const float* bias;     // per output channel (64 for conv 0, 128 otherwise)
     uint8_t* out;          // packed bf16 input of the next layer / fp32 embeddings
     uint8_t* code;         // optional ReLU/argmax routing codes, NCDHW order of the pooled tensor
+    int code_first;        // items below this index record no codes (frozen real videos ahead of synthetic ones)
     int T;                 // frames of the video
     int n_items;           // videos (conv 2: valid videos, tiles may be partially filled)
     Geo g;
@@ -186,7 +187,8 @@ __device__ __forceinline__ void epi_l0(const WsParams& p, int tile, uint32_t tad
     const float bias = __ldg(p.epi.bias + co);
     const int slice = co >> 4, k = (co >> 3) & 1, e = co & 7;
     uint8_t* vbase = p.epi.out + (int64_t)item * g.video1 + (int64_t)slice * g.slice1 + (int64_t)(f + 1) * g.frame1;
-    uint8_t* cbase = p.epi.code ? p.epi.code + (((int64_t)item * 64 + co) * g.T + f) * g.H1 * g.H1 : nullptr;
+    uint8_t* cbase = (p.epi.code && item >= p.epi.code_first)
+                         ? p.epi.code + (((int64_t)(item - p.epi.code_first) * 64 + co) * g.T + f) * g.H1 * g.H1 : nullptr;
     for (int pr = 0; pr < g.R0 / 2; ++pr) {
         const int hp = (rb * g.R0) / 2 + pr;
         const int ph = coord_par(hp), pi = coord_pos(hp);
@@ -226,7 +228,8 @@ __device__ __forceinline__ void epi_l1_drain(const WsParams& p, int tile, uint32
     const Geo& g = p.epi.g;
     const int item = tile / p.tiles_per_item, tp = tile % p.tiles_per_item;   // pooled frame index = tp
     const float bias = __ldg(p.epi.bias + m);
-    uint8_t* cbase = p.epi.code ? p.epi.code + (((int64_t)item * 128 + m) * g.T2 + tp) * g.H2 * g.H2 : nullptr;
+    uint8_t* cbase = (p.epi.code && item >= p.epi.code_first)
+                         ? p.epi.code + (((int64_t)(item - p.epi.code_first) * 128 + m) * g.T2 + tp) * g.H2 * g.H2 : nullptr;
     for (int hp = 0; hp < g.H2; ++hp) {
         float a0[16], a1[16], b0[16], b1[16];
         tmem_ld16(taddr + (2 * hp) * g.P1, a0);
@@ -291,7 +294,8 @@ __device__ __forceinline__ void epi_l2(const WsParams& p, int tile, uint32_t tad
         const int video = tile * p.n_acc + a;
         if (video >= p.epi.n_items) break;
         float* dst = reinterpret_cast<float*>(p.epi.out) + (int64_t)video * g.embed_dim + (int64_t)m * per;
-        uint8_t* cdst = p.epi.code ? p.epi.code + (int64_t)video * g.embed_dim + (int64_t)m * per : nullptr;
+        uint8_t* cdst = (p.epi.code && video >= p.epi.code_first)
+                            ? p.epi.code + (int64_t)(video - p.epi.code_first) * g.embed_dim + (int64_t)m * per : nullptr;
         for (int tq = 0; tq < g.T3p; ++tq) {
             // two frames = 2*HW2 consecutive columns
             const uint32_t c0 = taddr + a * p.acc_cols + (2 * tq) * g.HW2;
@@ -775,11 +779,12 @@ extern "C" int vd_tc_plan_make(vd_tc_plan* plan, int T, int H, int W) {
 }
 
 extern "C" int vd_tc_conv_layer(int layer, const void* in, const void* wimg, const float* bias, void* out,
-                                uint8_t* code, const vd_tc_plan* plan, const int64_t* item_index, int B, int raw,
-                                void* stream) {
+                                uint8_t* code, int code_first_item, const vd_tc_plan* plan, const int64_t* item_index,
+                                int B, int raw, void* stream) {
     VD_REQUIRE(plan && in && wimg && out, "tc_conv_layer: NULL pointer");
     VD_REQUIRE(layer >= 0 && layer <= 2, "tc_conv_layer: layer must be 0, 1 or 2");
     VD_REQUIRE(B >= 0, "tc_conv_layer: negative batch");
+    VD_REQUIRE(code_first_item >= 0, "tc_conv_layer: negative code_first_item");
     VD_REQUIRE(geo_supported(plan->T, plan->H), "tc_conv_layer: unsupported geometry");
     VD_REQUIRE(raw || bias, "tc_conv_layer: bias is NULL");
     if (B == 0) return 0;
@@ -792,7 +797,7 @@ extern "C" int vd_tc_conv_layer(int layer, const void* in, const void* wimg, con
     VD_REQUIRE(item_index == nullptr || layer == 0, "tc_conv_layer: item_index is only valid for layer 0");
     p.pix = (const uint8_t*)in; p.wimg = (const uint8_t*)wimg; p.item_index = item_index;
     p.prof = g_prof; p.dbg = env_int("VD_TC_DBG", 0);
-    p.epi.bias = bias; p.epi.out = (uint8_t*)out; p.epi.code = code; p.epi.raw = (float*)out;
+    p.epi.bias = bias; p.epi.out = (uint8_t*)out; p.epi.code = code; p.epi.code_first = code_first_item; p.epi.raw = (float*)out;
     p.epi.T = plan->T; p.epi.n_items = B; p.epi.g = g;
     cudaStream_t s = (cudaStream_t)stream;
     if (raw) return launch<EPI_RAW>(p, smem, s);

@@ -104,10 +104,13 @@ class DeviceDataset:
         self.x0 = None
         return self
 
-    def prepack(self, tc_net, free_fp32=False):
+    def prepack(self, tc_net, free_fp32=False, extra_slots=0):
         """Convert the resident set once into the tensor-core path's packed bf16 conv-0 operand
-        (device-resident real-data pipeline); per-iteration packing disappears."""
-        self.x0 = tc_net.pack_dataset(self.videos)
+        (device-resident real-data pipeline); per-iteration packing disappears.
+        ``extra_slots`` spare slots let the trainer embed its synthetic videos in the same launches."""
+        self.x0 = tc_net.pack_dataset(self.videos, extra_slots=extra_slots)
+        self.x0_tail = int(self.videos.shape[0])
+        self.x0_extra = int(extra_slots)
         if free_fp32:
             self.videos = None
         return self
@@ -299,7 +302,14 @@ class DMS2DTrainer:
         n_own = len(own)
         sel = (self.owned_t[:, None] * vpc + torch.arange(vpc, device=self.device)[None, :]).reshape(-1)
         image_syn = self.hal.compose(self.static_syn, self.dynamic_syn, static_idx[sel], label[sel], dynamic_idx[sel])
-        if real_batch is None:
+        tc = self.embedder.tc
+        joint = (tc is not None and self.syn_on_tensor_cores and real_batch is None and self.ds.x0 is not None
+                 and getattr(self.ds, 'x0_extra', 0) >= image_syn.shape[0])
+        if joint:
+            # real + synthetic videos in the same three conv launches (codes only for the synthetic tail)
+            ridx = self.ds.local_index(real_idx[own])
+            emb_real, emb_syn = tc.embed_joint_autograd(self.ds.x0, ridx, image_syn, self.ds.x0_tail)
+        elif real_batch is None:
             ridx = self.ds.local_index(real_idx[own])                       # (n_own*batch_real,)
             emb_real = self.embedder(self.ds.videos, ridx, x0=self.ds.x0)   # (n_own*batch_real, D)
         else:
@@ -307,8 +317,10 @@ class DMS2DTrainer:
             emb_real = self.embedder(real_batch, ridx)
         D = emb_real.shape[1]
         mean_real = ops.class_mean(emb_real.view(n_own, self.batch_real, D))
-        if self.embedder.tc is not None and self.syn_on_tensor_cores:
-            emb_syn = self.embedder.tc.embed_autograd(image_syn).view(n_own, vpc, D)
+        if joint:
+            emb_syn = emb_syn.view(n_own, vpc, D)
+        elif tc is not None and self.syn_on_tensor_cores:
+            emb_syn = tc.embed_autograd(image_syn).view(n_own, vpc, D)
         else:
             emb_syn = net.embed(image_syn).view(n_own, vpc, D)
         loss = ops.dm_loss(mean_real, emb_syn)

@@ -135,19 +135,19 @@ class TcConvNet3D:
         return out
 
     # ---------------------------------------------------------------- layers
-    def conv_layer(self, layer, src, wimg, bias, out, B, code=None, item_index=None, raw=False):
+    def conv_layer(self, layer, src, wimg, bias, out, B, code=None, item_index=None, raw=False, code_first=0):
         ev = None
         if self.timing is not None:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
-        self._conv_layer(layer, src, wimg, bias, out, B, code, item_index, raw)
+        self._conv_layer(layer, src, wimg, bias, out, B, code, item_index, raw, code_first)
         if ev is not None:
             ev[1].record()
             self.timing.append((layer, int(B), ev[0], ev[1]))
 
-    def _conv_layer(self, layer, src, wimg, bias, out, B, code=None, item_index=None, raw=False):
+    def _conv_layer(self, layer, src, wimg, bias, out, B, code=None, item_index=None, raw=False, code_first=0):
         _lib.check(_lib.lib().vd_tc_conv_layer(layer, _lib.ptr(src), _lib.ptr(wimg), _lib.ptr(bias), _lib.ptr(out),
-                                               _lib.ptr(code), ctypes.byref(self.plan), _lib.ptr(item_index),
+                                               _lib.ptr(code), int(code_first), ctypes.byref(self.plan), _lib.ptr(item_index),
                                                int(B), int(bool(raw)), _lib.stream()), f'vd_tc_conv_layer({layer})')
 
     def embed_packed(self, x0, B, item_index=None, out=None, codes=None):
@@ -161,9 +161,10 @@ class TcConvNet3D:
         self.conv_layer(2, a2, self.w2, self.b2, out, B, code=c2)
         return out
 
-    def _embed_chunks(self, B, out, codes, front):
+    def _embed_chunks(self, B, out, codes, front, code_first=0):
         """conv 0 + conv 1 per chunk of max_batch videos (``front(s, e)`` -> (x0, item_index)), every
-        chunk writing its slice of one A2 buffer; then ONE conv-2 launch over all B videos."""
+        chunk writing its slice of one A2 buffer; then ONE conv-2 launch over all B videos.  ``codes``
+        (optional) hold the routing of items code_first..B-1 only."""
         p = self.plan
         step = max(4, self.max_batch // 4 * 4)              # conv-2 tiles hold 4 consecutive videos
         a1, a2 = self._buffers(min(B, step), B)
@@ -171,9 +172,14 @@ class TcConvNet3D:
         for s in range(0, B, step):
             e = min(B, s + step)
             x0, idx = front(s, e)
-            self.conv_layer(0, x0, self.w0, self.b0, a1, e - s, code=None if c0 is None else c0[s:e], item_index=idx)
-            self.conv_layer(1, a1, self.w1, self.b1, a2[s * p.a2_bytes_per_video:], e - s, code=None if c1 is None else c1[s:e])
-        self.conv_layer(2, a2, self.w2, self.b2, out, B, code=c2)
+            cc0 = cc1 = None
+            first = 0
+            if c0 is not None and e > code_first:
+                first = max(0, code_first - s)              # chunk-local index of the first item with codes
+                cc0, cc1 = c0[s + first - code_first:], c1[s + first - code_first:]
+            self.conv_layer(0, x0, self.w0, self.b0, a1, e - s, code=cc0, item_index=idx, code_first=first)
+            self.conv_layer(1, a1, self.w1, self.b1, a2[s * p.a2_bytes_per_video:], e - s, code=cc1, code_first=first)
+        self.conv_layer(2, a2, self.w2, self.b2, out, B, code=c2, code_first=code_first)
         return out
 
     def alloc_codes(self, B):
@@ -182,11 +188,12 @@ class TcConvNet3D:
         return (torch.empty(B, 64, p.T1p, p.H1p, p.W1p, **u8), torch.empty(B, 128, p.T2p, p.H2p, p.W2p, **u8),
                 torch.empty(B, 128, p.T3p, p.H3p, p.W3p, **u8))
 
-    def pack_dataset(self, videos, chunk=256):
+    def pack_dataset(self, videos, chunk=256, extra_slots=0):
         """One-time conversion of a resident fp32 real set (N,T,3,H,W) into the packed conv-0 operand
-        (bf16, 'kw-expanded'); afterwards ``embed_resident`` reads it in place through item_index."""
+        (bf16, 'kw-expanded'); afterwards ``embed_resident`` reads it in place through item_index.
+        ``extra_slots`` spare video slots at the tail receive the synthetic videos of ``embed_joint``."""
         N = int(videos.shape[0])
-        x0 = torch.empty(N * self.plan.x0_bytes_per_video, dtype=torch.uint8, device=self.device)
+        x0 = torch.empty((N + extra_slots) * self.plan.x0_bytes_per_video, dtype=torch.uint8, device=self.device)
         per = self.plan.x0_bytes_per_video
         for s in range(0, N, chunk):
             e = min(N, s + chunk)
@@ -199,6 +206,25 @@ class TcConvNet3D:
         out = torch.empty(B, self.embed_dim, dtype=torch.float32, device=self.device)
         index = index.contiguous()
         return self._embed_chunks(B, out, None, lambda s, e: (x0_all, index[s:e]))
+
+    def embed_joint(self, x0_all, index_real, video_syn, tail_slot):
+        """Frozen real videos (resident, addressed by ``index_real``) and differentiable synthetic videos in ONE
+        pass of the three conv kernels: the synthetic videos are packed into the spare slots ``tail_slot...`` of
+        the resident operand and only they record routing codes.  Returns (emb_real, emb_syn, codes)."""
+        n_real, n_syn = int(index_real.numel()), int(video_syn.shape[0])
+        per = self.plan.x0_bytes_per_video
+        assert x0_all.numel() >= (tail_slot + n_syn) * per, 'resident operand has no spare slots for the synthetic videos'
+        self.pack_video(video_syn.contiguous(), out=x0_all[tail_slot * per:(tail_slot + n_syn) * per])
+        index = torch.cat([index_real.reshape(-1), torch.arange(tail_slot, tail_slot + n_syn, device=self.device)])
+        codes = self.alloc_codes(n_syn)
+        out = torch.empty(n_real + n_syn, self.embed_dim, dtype=torch.float32, device=self.device)
+        self._embed_chunks(n_real + n_syn, out, codes, lambda s, e: (x0_all, index[s:e]), code_first=n_real)
+        return out[:n_real], out[n_real:].clone(), codes
+
+    def embed_joint_autograd(self, x0_all, index_real, video_syn, tail_slot):
+        """(emb_real [no grad], emb_syn [differentiable w.r.t. video_syn]) of one joint pass."""
+        emb_syn, emb_real = _TcEmbedJoint.apply(video_syn, self, x0_all, index_real, tail_slot)
+        return emb_real, emb_syn
 
     def embed(self, video, index=None, want_codes=False):
         """ConvNet3D.embed on fp32 videos (B,T,3,H,W) -> (B, embed_dim) fp32, in chunks of max_batch."""
@@ -225,3 +251,17 @@ class _TcEmbed(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, g_emb):
         return ctx.net.embed_backward(g_emb, ctx.codes), None
+
+
+class _TcEmbedJoint(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, video_syn, net, x0_all, index_real, tail_slot):
+        emb_real, emb_syn, codes = net.embed_joint(x0_all, index_real, video_syn, tail_slot)
+        ctx.net, ctx.codes = net, codes
+        ctx.mark_non_differentiable(emb_real)
+        return emb_syn, emb_real
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_syn, g_real):
+        return ctx.net.embed_backward(g_syn, ctx.codes), None, None, None, None
