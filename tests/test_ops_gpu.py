@@ -159,6 +159,35 @@ def test_composer_gather_and_accumulate():
     assert rel(wc.grad, w.grad) < 1e-5 and rel(bc.grad, b.grad) < 1e-5
 
 
+@pytest.mark.parametrize('T,H,W', [(1, 8, 8), (2, 20, 24), (5, 13, 64), (4, 30, 112)])
+def test_composer_tiled_paths(T, H, W):
+    """Shared-memory tiled composer kernels (frozen static memory, i.e. --no_train_static): forward, gradient to
+    the dynamic memory (repeated rows accumulate) and to the hallucinator, at ragged heights / T = 1."""
+    import oracle
+    from video_distillation_b200 import ops
+    g = torch.Generator().manual_seed(11 + T)
+    C, dpc, spc = 3, 2, 2
+    static_syn = torch.randn(C * spc, 3, H, W, generator=g)
+    dynamic_syn = torch.randn(C, dpc, T, 1, H, W, generator=g)
+    hal = oracle.init_hallucinator(7)
+    label = torch.tensor([0, 1, 1, 2])
+    didx = torch.tensor([1, 0, 0, 1])             # (1,0) appears twice
+    sidx = torch.tensor([1, 2, 3, 5])
+    d = dynamic_syn.clone().requires_grad_(True)
+    w = hal['encoder.weight'].clone().requires_grad_(True)
+    b = hal['encoder.bias'].clone().requires_grad_(True)
+    y_ref = oracle.compose(static_syn[sidx], d[label, didx], w, b)
+    gy = torch.randn(y_ref.shape, generator=g)
+    y_ref.backward(gy)
+    dc = dynamic_syn.cuda().requires_grad_(True)
+    wc, bc = hal['encoder.weight'].cuda().requires_grad_(True), hal['encoder.bias'].cuda().requires_grad_(True)
+    y = ops.compose(static_syn.cuda(), dc, wc, bc, sidx.cuda(), label.cuda(), didx.cuda())
+    assert rel(y, y_ref) < 1e-6
+    y.backward(gy.cuda())
+    assert rel(dc.grad, d.grad) < 1e-5
+    assert rel(wc.grad, w.grad) < 1e-5 and rel(bc.grad, b.grad) < 1e-5
+
+
 def test_dm_loss_and_class_mean():
     import oracle
     from video_distillation_b200 import ops

@@ -547,12 +547,28 @@ extern "C" int vd_avgpool2_bwd_f32(const float* gy, float* gx, int64_t NC, int T
     return check_launch("avgpool2_bwd_f32");
 }
 
+namespace vd {
+// shared-memory tiled versions (compose_tiled.cu); return 1 when the geometry is not covered
+int compose_fwd_tiled(const float* static_syn, const float* dynamic_syn, const int64_t* static_idx, const int64_t* label,
+                      const int64_t* dynamic_idx, const float* weight, const float* bias, float* out, int B, int T, int H,
+                      int W, int dpc, cudaStream_t stream);
+int compose_bwd_data_tiled(const float* gout, const int64_t* label, const int64_t* dynamic_idx, const float* weight,
+                           float* grad_dynamic, int B, int T, int H, int W, int dpc, cudaStream_t stream);
+int compose_bwd_wdyn_tiled(const float* gout, const float* dynamic_syn, const int64_t* label, const int64_t* dynamic_idx,
+                           float* grad_weight, float* grad_bias, int B, int T, int H, int W, int dpc, cudaStream_t stream);
+}  // namespace vd
+
 extern "C" int vd_compose_fwd_f32(const float* static_syn, const float* dynamic_syn, const int64_t* static_idx,
                                   const int64_t* label, const int64_t* dynamic_idx, const float* weight,
                                   const float* bias, float* out, int B, int T, int H, int W, int dpc, void* stream) {
     VD_REQUIRE(static_syn && dynamic_syn && static_idx && label && dynamic_idx && weight && bias && out, "compose_fwd: NULL pointer");
     VD_REQUIRE(B >= 0 && T > 0 && H > 0 && W > 0 && dpc > 0 && T <= 65535 && B <= 65535, "compose_fwd: bad extent");
     if (B == 0) return 0;
+    {
+        const int rc = compose_fwd_tiled(static_syn, dynamic_syn, static_idx, label, dynamic_idx, weight, bias, out, B, T, H, W, dpc,
+                                         (cudaStream_t)stream);
+        if (rc != 1) return rc;                 // 1 = geometry not covered by the tiled kernel
+    }
     const int W4 = (W + 3) / 4;
     dim3 grid((unsigned)ceil_div((int64_t)H * W4, 256), T, B);
     compose_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(static_syn, dynamic_syn, static_idx, label, dynamic_idx,
@@ -567,7 +583,12 @@ extern "C" int vd_compose_bwd_f32(const float* gout, const float* static_syn, co
     VD_REQUIRE(gout && static_syn && dynamic_syn && static_idx && label && dynamic_idx && weight, "compose_bwd: NULL pointer");
     VD_REQUIRE(B >= 0 && T > 0 && H > 0 && W > 0 && dpc > 0 && T <= 65535 && B <= 65535, "compose_bwd: bad extent");
     if (B == 0) return 0;
-    if (grad_dynamic) {
+    int rc_data = 1;
+    if (grad_dynamic && !grad_static) {
+        rc_data = compose_bwd_data_tiled(gout, label, dynamic_idx, weight, grad_dynamic, B, T, H, W, dpc, (cudaStream_t)stream);
+        if (rc_data != 0 && rc_data != 1) return rc_data;
+    }
+    if (grad_dynamic && rc_data == 1) {
         dim3 grid((unsigned)ceil_div((int64_t)H * W, 256), T, B);
         compose_bwd_data_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(gout, static_idx, label, dynamic_idx, weight,
                                                                        grad_dynamic, grad_static, T, H, W, dpc);
@@ -575,7 +596,9 @@ extern "C" int vd_compose_bwd_f32(const float* gout, const float* static_syn, co
     }
     if (grad_weight) {
         cudaStream_t s = (cudaStream_t)stream;
-        {
+        const int rc_w = compose_bwd_wdyn_tiled(gout, dynamic_syn, label, dynamic_idx, grad_weight, grad_bias, B, T, H, W, dpc, s);
+        if (rc_w != 0 && rc_w != 1) return rc_w;
+        if (rc_w == 1) {
             const int64_t rows = (int64_t)B * T * H;
             int rpb = (int)ceil_div(rows, 148 * 4);
             if (rpb < 8) rpb = 8;
