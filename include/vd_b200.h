@@ -182,8 +182,10 @@ int vd_tc_pack_weights(const float* w_l0, const float* w_l1, const float* w_l2,
  * data cells are fully overwritten by every call).  code may be NULL (real videos need no
  * backward); otherwise items >= code_first_item record their routing codes at code[item - code_first_item]
  * (a batch of frozen real videos followed by differentiable synthetic ones runs as ONE launch).  item_index (device int64[B], layer 0 only, may be NULL) maps item -> video slot
- * of `in`.  raw != 0 (bring-up / tests): skip the fused epilogue and dump the fp32
- * accumulators to out as [tile][acc][128][ncols]. */
+ * of `in`.  raw == 1 (bring-up / tests): skip the fused epilogue and dump the fp32
+ * accumulators to out as [tile][acc][128][ncols].  raw == 2: plain convolution, out = fp32 NCDHW
+ * (B, Cout, To, Ho, Wo) pre-activation (+ bias when non-NULL) — F.conv3d of networks.py:799 as used by the
+ * differentiable conv trio. */
 int vd_tc_conv_layer(int layer, const void* in, const void* wimg, const float* bias,
                      void* out, uint8_t* code, int code_first_item, const vd_tc_plan* plan,
                      const int64_t* item_index, int B, int raw, void* stream);
@@ -209,6 +211,24 @@ int vd_tc_bwd_gemm(int layer, const void* dy, const void* wt, void* col, const v
                    int B, void* stream);
 int vd_tc_bwd_col2im(int layer, const void* col, const uint8_t* code_below, void* out,
                      const vd_tc_plan* plan, int B, void* stream);
+
+/* ---- the differentiable conv trio on tensor cores (MTT unroll / double backward, ops.py).  Plain fp32 NCDHW
+ * tensors in and out; geometry = the three ConvNet3D feature convolutions of `plan`.
+ *   fprop(x, w)   : layer 0: vd_tc_pack_video on x permuted to (B,T,3,H,W); layers 1/2: vd_tc_pack_act;
+ *                   then vd_tc_conv_layer(..., raw = 2) -> y (B, Cout, To, Ho, Wo)      [F.conv3d, networks.py:799]
+ *   dgrad(gy, w)  : vd_tc_pack_dy, vd_tc_pack_weights_bwd, vd_tc_bwd_gemm, vd_tc_bwd_col2im_plain -> gx NCDHW
+ *   wgrad(x, gy)  : vd_tc_wgrad_plan (workspace sizes), vd_tc_wgrad_pack (im2col columns + gy image),
+ *                   vd_tc_wgrad_gemm (split-K partial sums), vd_tc_wgrad_reduce -> gw (Cout, Cin, 3, 7, 7)   */
+int vd_tc_pack_act(int layer, const float* x, void* packed, const vd_tc_plan* plan, int B, void* stream);
+int vd_tc_pack_dy(int layer, const float* gy, void* dy, const vd_tc_plan* plan, int B, void* stream);
+int vd_tc_bwd_col2im_plain(int layer, const void* col, float* gx, const vd_tc_plan* plan, int B, void* stream);
+/* out[0] split-K slices, out[1] stages per slice, out[2] column tiles, out[3] xcol bytes, out[4] gyimg bytes, out[5] raw bytes */
+int vd_tc_wgrad_plan(int layer, const vd_tc_plan* plan, int B, int64_t* out);
+int vd_tc_wgrad_pack(int layer, const float* x, const float* gy, void* xcol, void* gyimg, const vd_tc_plan* plan,
+                     int B, void* stream);
+int vd_tc_wgrad_gemm(int layer, const void* xcol, const void* gyimg, float* raw, const vd_tc_plan* plan, int B,
+                     void* stream);
+int vd_tc_wgrad_reduce(int layer, const float* raw, float* gw, const vd_tc_plan* plan, int B, void* stream);
 
 /* Tuning probe (tests/bring-up only): issues 148 x n_sa x n_steps x n_acc MMAs of N=ncols with the
  * given descriptor words over dummy operands (pix >= 64 KiB, wimg >= 16 KiB, raw >= 148*n_acc*128*ncols

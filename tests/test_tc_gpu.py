@@ -245,3 +245,33 @@ def test_joint_real_and_synthetic_pass_matches_separate_passes():
     v2 = syn.clone().requires_grad_(True)
     net.embed_autograd(v2).backward(g)
     assert torch.equal(v.grad, v2.grad)
+
+
+@pytest.mark.parametrize('T,HW', CASES)
+def test_tensor_core_trio_matches_fp32_kernels(T, HW):
+    """fprop / dgrad / wgrad of the three feature convolutions on tensor cores (bf16 operands, fp32 accumulate)
+    against the exact fp32 kernels on bf16-rounded operands (same products, different summation order)."""
+    from video_distillation_b200 import ops
+    S, P = (1, 2, 2), (1, 3, 3)
+    gen = torch.Generator().manual_seed(12)
+    B = 3
+    shapes = [(3, 64, (T, HW, HW)), (64, 128, (T, HW // 4, HW // 4)), (128, 128, (T // 2, HW // 16, HW // 16))]
+    for layer, (cin, cout, ext) in enumerate(shapes):
+        x = em.bf16_round(torch.randn(B, cin, *ext, generator=gen)).cuda()
+        w = em.bf16_round(torch.randn(cout, cin, 3, 7, 7, generator=gen) / (cin * 147) ** 0.5).cuda()
+        prev = ops.set_conv_backend('fp32')
+        try:
+            y_ref = ops.conv3d_fprop_raw(x, w, None, S, P)
+            gy = em.bf16_round(torch.randn(y_ref.shape, generator=gen)).cuda()
+            gx_ref = ops.conv3d_dgrad_raw(gy, w, tuple(x.shape), S, P)
+            gw_ref = ops.conv3d_wgrad_raw(x, gy, tuple(w.shape), S, P)
+            ops.set_conv_backend('tc')
+            y = ops.conv3d_fprop_raw(x, w, None, S, P)
+            gx = ops.conv3d_dgrad_raw(gy, w, tuple(x.shape), S, P)
+            gw = ops.conv3d_wgrad_raw(x, gy, tuple(w.shape), S, P)
+        finally:
+            ops.set_conv_backend(prev)
+        assert y.shape == y_ref.shape and gx.shape == gx_ref.shape and gw.shape == gw_ref.shape
+        assert rel(y, y_ref) < 1e-5, (layer, 'fprop', rel(y, y_ref))
+        assert rel(gx, gx_ref) < 5e-3, (layer, 'dgrad', rel(gx, gx_ref))      # bf16 column buffer
+        assert rel(gw, gw_ref) < 1e-5, (layer, 'wgrad', rel(gw, gw_ref))

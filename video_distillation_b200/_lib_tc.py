@@ -14,6 +14,13 @@ def declare(lib):
         'vd_tc_bwd_emb': (c_int, [P, P, P, POINTER(TcPlan), c_int, P]),
         'vd_tc_bwd_gemm': (c_int, [c_int, P, P, P, POINTER(TcPlan), c_int, P]),
         'vd_tc_bwd_col2im': (c_int, [c_int, P, P, P, POINTER(TcPlan), c_int, P]),
+        'vd_tc_pack_act': (c_int, [c_int, P, P, POINTER(TcPlan), c_int, P]),
+        'vd_tc_pack_dy': (c_int, [c_int, P, P, POINTER(TcPlan), c_int, P]),
+        'vd_tc_bwd_col2im_plain': (c_int, [c_int, P, P, POINTER(TcPlan), c_int, P]),
+        'vd_tc_wgrad_plan': (c_int, [c_int, POINTER(TcPlan), c_int, POINTER(c_int64)]),
+        'vd_tc_wgrad_pack': (c_int, [c_int, P, P, P, P, POINTER(TcPlan), c_int, P]),
+        'vd_tc_wgrad_gemm': (c_int, [c_int, P, P, P, POINTER(TcPlan), c_int, P]),
+        'vd_tc_wgrad_reduce': (c_int, [c_int, P, P, POINTER(TcPlan), c_int, P]),
         'vd_tc_probe': (c_int, [P, P, P, c_int, c_int, c_int, c_uint32, c_uint32, c_uint32, c_uint32, c_uint32, c_int, P]),
         'vd_tc_mma_rate': (c_int, [P, c_int, c_int, c_int, c_uint32, c_uint32, c_uint32, c_int, c_int, c_int, P]),
         'vd_tc_set_profile_buffer': (c_int, [P]),

@@ -119,7 +119,8 @@ __device__ __forceinline__ float c2i_taps(const uint16_t* __restrict__ sm16, int
 // zeros elsewhere -> dY below is fully overwritten, no memset needed.
 // layer 0 (code == nullptr): writes d video (B, T, 3, H, W) fp32.
 __global__ void __launch_bounds__(256) col2im_kernel(const uint16_t* __restrict__ colbuf, const uint8_t* __restrict__ code,
-                                                     void* __restrict__ out, BwdGeo b, BwdGeo bb, int pt, int band, int pitch, int cib) {
+                                                     void* __restrict__ out, BwdGeo b, BwdGeo bb, int pt, int band, int pitch, int cib,
+                                                     int ncdhw) {
     extern __shared__ uint32_t c2i_smem[];
     const C2iBlock k = c2i_block(b, band, cib);
     const uint16_t* colv = colbuf + (int64_t)k.vid * b.col_video_elems;
@@ -160,9 +161,10 @@ __global__ void __launch_bounds__(256) col2im_kernel(const uint16_t* __restrict_
         if (i >= n_all) continue;
         const int cl = i / n_out, o = i - cl * n_out;
         const int hl = o / b.Wi, w = o - hl * b.Wi, h = k.hb + hl, ci = k.ci0 + cl;
-        if (code == nullptr) {
+        if (code == nullptr) {                            // fp32 gradient: (B,T,Cin,H,W) video layout or plain NCDHW
             float* dv = reinterpret_cast<float*>(out);
-            dv[((((int64_t)k.vid * b.Ti + k.t) * 3 + ci) * b.Hi + h) * b.Wi + w] = acc[j];
+            const int64_t plane = ncdhw ? ((int64_t)k.vid * b.Cin + ci) * b.Ti + k.t : ((int64_t)k.vid * b.Ti + k.t) * b.Cin + ci;
+            dv[(plane * b.Hi + h) * b.Wi + w] = acc[j];
             continue;
         }
         const uint8_t cd = code[((((int64_t)k.vid * b.Cin + ci) * b.Ti + k.t) * b.Hi + h) * b.Wi + w];
@@ -221,7 +223,7 @@ __device__ __forceinline__ void c2i_row_taps(float (&acc)[SEG], const uint16_t* 
 template <int SEG, int V>
 __global__ void __launch_bounds__(512) col2im_rows_kernel(const uint16_t* __restrict__ colbuf, const uint8_t* __restrict__ code,
                                                           void* __restrict__ out, BwdGeo b, BwdGeo bb, int pt, int band, int pitch,
-                                                          int warps_per_par, int cib, int lanes_ch, int nbuf, int stash_off) {
+                                                          int warps_per_par, int cib, int lanes_ch, int nbuf, int stash_off, int ncdhw) {
     // shared memory: lanes_ch * nbuf staging buffers [49][pitch] bf16, then (route mode) the stash
     // [cib][n_out] u32 = bf16 << 16 | argmax
     extern __shared__ uint32_t c2i_smem[];
@@ -290,7 +292,8 @@ __global__ void __launch_bounds__(512) col2im_rows_kernel(const uint16_t* __rest
             if (st % nkt == nkt - 1) {                                // last temporal tap of this channel
                 const int cl = chl + (st / nkt) * lanes_ch, ci = k.ci0 + cl;
                 if (code == nullptr) {
-                    float* dv = reinterpret_cast<float*>(out) + ((((int64_t)k.vid * b.Ti + k.t) * 3 + ci) * b.Hi + h) * b.Wi + 2 * seg * SEG + par;
+                    const int64_t plane = ncdhw ? ((int64_t)k.vid * b.Cin + ci) * b.Ti + k.t : ((int64_t)k.vid * b.Ti + k.t) * b.Cin + ci;
+                    float* dv = reinterpret_cast<float*>(out) + (plane * b.Hi + h) * b.Wi + 2 * seg * SEG + par;
 #pragma unroll
                     for (int j = 0; j < SEG; ++j) { dv[2 * j] = acc[j]; acc[j] = 0.f; }
                 } else {
@@ -371,11 +374,13 @@ extern "C" int vd_tc_bwd_emb(const float* g_emb, const uint8_t* code2, void* dy2
     return check_launch("tc_bwd_emb");
 }
 
-extern "C" int vd_tc_bwd_col2im(int layer, const void* col, const uint8_t* code_below, void* out,
-                                const vd_tc_plan* plan, int B, void* stream) {
+// mode 0: route with code_below into the packed dY of the layer below (layers 1,2) / d video (B,T,3,H,W) (layer 0)
+// mode 1: plain fp32 NCDHW gradient (B, Cin, Ti, Hi, Wi) for any layer (dgrad of the differentiable conv trio)
+static int col2im_launch(int layer, const void* col, const uint8_t* code_below, void* out, const vd_tc_plan* plan, int B,
+                         void* stream, int ncdhw) {
     VD_REQUIRE(col && out && plan, "tc_bwd_col2im: NULL pointer");
     VD_REQUIRE(layer >= 0 && layer <= 2, "tc_bwd_col2im: bad layer");
-    VD_REQUIRE((layer == 0) == (code_below == nullptr), "tc_bwd_col2im: code_below is required for layers 1,2 and must be NULL for layer 0");
+    VD_REQUIRE(ncdhw || (layer == 0) == (code_below == nullptr), "tc_bwd_col2im: code_below is required for layers 1,2 and must be NULL for layer 0");
     VD_REQUIRE(geo_supported(plan->T, plan->H), "tc_bwd_col2im: unsupported geometry");
     if (B <= 0) return 0;
     const Geo g = make_geo(plan->T, plan->H);
@@ -400,11 +405,12 @@ extern "C" int vd_tc_bwd_col2im(int layer, const void* col, const uint8_t* code_
     const int nb = (b.Hi + band - 1) / band;
     BwdGeo bb = b;
     int pt = 1;
-    if (layer > 0) {
+    const bool to_f32 = ncdhw || layer == 0;                         // fp32 output (no routing)
+    if (!to_f32) {
         bb = make_bwd_geo(g, layer - 1);
         pt = (layer == 2) ? 2 : 1;             // pool window of the layer below in T: conv1 -> (2,2,2), conv0 -> (1,2,2)
     }
-    const uint8_t* cd = layer == 0 ? nullptr : code_below;
+    const uint8_t* cd = to_f32 ? nullptr : code_below;
     // fast path: SEG same-parity columns per thread, V-element vector staging; route mode: 8 channels (one dY
     // chunk) per block on 4 concurrent channel lanes
     const int half = b.Wi / 2;
@@ -414,11 +420,11 @@ extern "C" int vd_tc_bwd_col2im(int layer, const void* col, const uint8_t* code_
     while (V > 1 && (align_unit % V != 0 || b.NC % V != 0)) V >>= 1;
     const int per_par = SEG ? (band * (half / SEG) + 31) / 32 : 0;   // warps per column parity
     const int tpc = 2 * per_par * 32;                                // threads per channel lane
-    if (SEG != 0 && V >= 2 && tpc <= 512 && (layer == 0 || (b.Cin % 8 == 0 && bb.NC % 2 == 0))) {
-        const int cib = layer == 0 ? 1 : 8;
-        int lanes_ch = layer == 0 ? 1 : 4;
+    if (SEG != 0 && V >= 2 && tpc <= 512 && (to_f32 || (b.Cin % 8 == 0 && bb.NC % 2 == 0))) {
+        const int cib = (b.Cin % 8 == 0) ? 8 : 1;
+        int lanes_ch = (b.Cin % 8 == 0) ? 4 : 1;
         while (lanes_ch > 1 && (lanes_ch * tpc > 512 || lanes_ch * stage_bytes > 100 * 1024)) lanes_ch >>= 1;
-        const size_t stash_bytes = layer == 0 ? 0 : (size_t)cib * band * b.Wi * 4;
+        const size_t stash_bytes = to_f32 ? 0 : (size_t)cib * band * b.Wi * 4;
         const int nbuf = (lanes_ch == 1 && 2 * stage_bytes + stash_bytes <= 76 * 1024) ? 2 : 1;
         const size_t smem = (size_t)lanes_ch * nbuf * stage_bytes + stash_bytes;
         VD_REQUIRE(smem <= 200 * 1024, "tc_bwd_col2im: shared memory budget exceeded (%zu bytes)", smem);
@@ -426,7 +432,7 @@ extern "C" int vd_tc_bwd_col2im(int layer, const void* col, const uint8_t* code_
         VD_REQUIRE(blocks < (1ll << 31), "tc_bwd_col2im: grid too large");
         const int stash_off = (int)(lanes_ch * nbuf * stage_bytes / 4);
         const int threads = lanes_ch * tpc;
-#define VD_C2I(S_, V_) col2im_rows_kernel<S_, V_><<<(unsigned)blocks, threads, smem, s>>>((const uint16_t*)col, cd, out, b, bb, pt, band, pitch, per_par, cib, lanes_ch, nbuf, stash_off)
+#define VD_C2I(S_, V_) col2im_rows_kernel<S_, V_><<<(unsigned)blocks, threads, smem, s>>>((const uint16_t*)col, cd, out, b, bb, pt, band, pitch, per_par, cib, lanes_ch, nbuf, stash_off, ncdhw)
         if (SEG == 7) { if (V == 8) VD_C2I(7, 8); else if (V == 4) VD_C2I(7, 4); else VD_C2I(7, 2); }
         else { if (V == 8) VD_C2I(8, 8); else if (V == 4) VD_C2I(8, 4); else VD_C2I(8, 2); }
 #undef VD_C2I
@@ -439,6 +445,15 @@ extern "C" int vd_tc_bwd_col2im(int layer, const void* col, const uint8_t* code_
     VD_REQUIRE(smem <= 96 * 1024, "tc_bwd_col2im: staging buffer too large (%zu bytes)", smem);
     const int64_t blocks = (int64_t)B * (b.Cin / cib) * b.Ti * nb;
     VD_REQUIRE(blocks < (1ll << 31), "tc_bwd_col2im: grid too large");
-    col2im_kernel<<<(unsigned)blocks, 256, smem, s>>>((const uint16_t*)col, cd, out, b, bb, pt, band, pitch, cib);
+    col2im_kernel<<<(unsigned)blocks, 256, smem, s>>>((const uint16_t*)col, cd, out, b, bb, pt, band, pitch, cib, ncdhw);
     return check_launch("tc_bwd_col2im");
+}
+
+extern "C" int vd_tc_bwd_col2im(int layer, const void* col, const uint8_t* code_below, void* out,
+                                const vd_tc_plan* plan, int B, void* stream) {
+    return col2im_launch(layer, col, code_below, out, plan, B, stream, 0);
+}
+
+extern "C" int vd_tc_bwd_col2im_plain(int layer, const void* col, float* gx, const vd_tc_plan* plan, int B, void* stream) {
+    return col2im_launch(layer, col, nullptr, gx, plan, B, stream, 1);
 }

@@ -24,7 +24,7 @@ constexpr int kMaxSteps = 64;
 constexpr int kMaxCopies = 8;
 constexpr int kThreads = 256;
 
-enum EpiMode { EPI_RAW = 0, EPI_L0 = 1, EPI_L1 = 2, EPI_L2 = 3 };
+enum EpiMode { EPI_RAW = 0, EPI_L0 = 1, EPI_L1 = 2, EPI_L2 = 3, EPI_PLAIN = 4 };
 
 struct EpiParams {
     float* raw;            // EPI_RAW: [tile][u][acc][128][ncols]
@@ -33,6 +33,7 @@ struct EpiParams {
     uint8_t* out;          // packed bf16 input of the next layer / fp32 embeddings
     uint8_t* code;         // optional ReLU/argmax routing codes, NCDHW order of the pooled tensor
     int code_first;        // items below this index record no codes (frozen real videos ahead of synthetic ones)
+    int layer;             // EPI_PLAIN: which conv (tile -> NCDHW mapping)
     int T;                 // frames of the video
     int n_items;           // videos (conv 2: valid videos, tiles may be partially filled)
     Geo g;
@@ -47,6 +48,7 @@ struct WsParams {
     int32_t n_u;                        // accumulator groups per tile sharing ONE pixel stage (column GEMM: M tiles)
     int32_t nu_total, ug_count;         // column GEMM: the nu_total M tiles of one pixel stage are split over ug_count CTA tiles
     int64_t w_u_stride;                 // bytes between the weight sequences of consecutive groups
+    int64_t w_item_stride;              // bytes between the weight sequences of consecutive items (wgrad: split-K slices)
     int32_t n_sa, n_sb;
     int64_t sa_stride, sb_stride;
     int32_t n_copies;
@@ -339,6 +341,57 @@ __device__ __forceinline__ void epi_l2(const WsParams& p, int tile, uint32_t tad
     }
 }
 
+// plain conv output: fp32 NCDHW (B, Cout, To, Ho, Wo), pre-activation (+ bias when given) — the fprop of the
+// differentiable conv trio (ops.py) on tensor cores.  Tile -> output mapping as in epi_l0 / epi_l1 / epi_l2.
+__device__ __forceinline__ void epi_plain(const WsParams& p, int tile, uint32_t taddr, int m) {
+    const Geo& g = p.epi.g;
+    float* out = reinterpret_cast<float*>(p.epi.out);
+    if (p.epi.layer == 0) {
+        const int item = tile / p.tiles_per_item, sub = tile % p.tiles_per_item;
+        const int tp = sub / p.v_count, rb = sub % p.v_count;
+        const int f = 2 * tp + (m >> 6), co = m & 63;
+        const float bias = p.epi.bias ? __ldg(p.epi.bias + co) : 0.f;
+        for (int r = 0; r < g.R0; ++r) {
+            float* dst = out + ((((int64_t)item * 64 + co) * g.T + f) * g.Ho0 + rb * g.R0 + r) * g.Wo0;
+            for (int wb = 0; wb < g.Wo0; wb += 8) {
+                float v[8];
+                tmem_ld8(taddr + r * g.Wo0 + wb, v);
+                tmem_ld_wait();
+                *reinterpret_cast<float4*>(dst + wb) = make_float4(v[0] + bias, v[1] + bias, v[2] + bias, v[3] + bias);
+                *reinterpret_cast<float4*>(dst + wb + 4) = make_float4(v[4] + bias, v[5] + bias, v[6] + bias, v[7] + bias);
+            }
+        }
+    } else if (p.epi.layer == 1) {
+        const int item = tile / p.tiles_per_item, tp = tile % p.tiles_per_item;
+        const float bias = p.epi.bias ? __ldg(p.epi.bias + m) : 0.f;
+        for (int a = 0; a < 2; ++a) {
+            float* dst = out + (((int64_t)item * 128 + m) * g.T + 2 * tp + a) * g.Ho1 * g.Wo1;
+            for (int ho = 0; ho < g.Ho1; ++ho) {
+                float v[16];
+                tmem_ld16(taddr + a * p.acc_cols + ho * g.P1, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; j += 2)
+                    if (j < g.Wo1) *reinterpret_cast<float2*>(dst + ho * g.Wo1 + j) = make_float2(v[j] + bias, v[j + 1] + bias);
+            }
+        }
+    } else {
+        const float bias = p.epi.bias ? __ldg(p.epi.bias + m) : 0.f;
+        for (int a = 0; a < p.n_acc; ++a) {
+            const int video = tile * p.n_acc + a;
+            if (video >= p.epi.n_items) break;
+            float* dst = out + ((int64_t)video * 128 + m) * g.N2;
+            for (int c = 0; c < g.N2; c += 8) {
+                float v[8];
+                tmem_ld8(taddr + a * p.acc_cols + c, v);
+                tmem_ld_wait();
+                *reinterpret_cast<float4*>(dst + c) = make_float4(v[0] + bias, v[1] + bias, v[2] + bias, v[3] + bias);
+                *reinterpret_cast<float4*>(dst + c + 4) = make_float4(v[4] + bias, v[5] + bias, v[6] + bias, v[7] + bias);
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 template <int EPI, int NACC>
 __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_constant__ WsParams p) {
@@ -411,6 +464,7 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
                 const int slots_per_stage = (p.n_steps + p.G - 1) / p.G;
                 for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
                     const int u0 = (tile % p.ug_count) * p.n_u, u1 = min(p.nu_total, u0 + p.n_u);
+                    const uint8_t* wbase = p.wimg + (int64_t)((tile / p.ug_count) / p.tiles_per_item) * p.w_item_stride;
                     for (int u = u0; u < u1; ++u)
                         for (int st = 0; st < stages_per_tile; ++st)
                             for (int gi = 0; gi < slots_per_stage; ++gi) {
@@ -421,7 +475,7 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
                                 else {
                                     mbar_expect_tx(BAR(w_full, slot), nb);
                                     bulk_g2s(smem_w + slot * (uint32_t)p.G * kWeightTileBytes,
-                                             p.wimg + (int64_t)u * p.w_u_stride + ((int64_t)st * p.n_steps + s0) * kWeightTileBytes,
+                                             wbase + (int64_t)u * p.w_u_stride + ((int64_t)st * p.n_steps + s0) * kWeightTileBytes,
                                              nb, BAR(w_full, slot));
                                 }
                                 if (++slot == (uint32_t)p.RW) { slot = 0; phase ^= 1; }
@@ -532,6 +586,7 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
                     if (EPI == EPI_RAW) epi_raw(p, (int64_t)tile_pix * p.nu_total + u0 + u, taddr, m, p.smem_epi_off ? reinterpret_cast<float*>(base_ptr + p.smem_epi_off) : nullptr);
                     else if (EPI == EPI_L0) epi_l0(p, tile, taddr, m);
                     else if (EPI == EPI_L1) epi_l1_drain(p, tile, taddr, m, reinterpret_cast<uint16_t*>(base_ptr + p.smem_stash_off));
+                    else if (EPI == EPI_PLAIN) epi_plain(p, tile, taddr, m);
                     else epi_l2(p, tile, taddr, m);
                 }
                 tc_fence_before();
@@ -741,6 +796,10 @@ static int launch(const WsParams& p, uint32_t smem, cudaStream_t stream) {
         return launch_n<EPI_L1, 2>(p, smem, stream);
     } else if (EPI == EPI_L2 && p.n_acc == 4) {
         return launch_n<EPI_L2, 4>(p, smem, stream);
+    } else if (EPI == EPI_PLAIN) {
+        if (p.n_acc == 1) return launch_n<EPI_PLAIN, 1>(p, smem, stream);
+        if (p.n_acc == 2) return launch_n<EPI_PLAIN, 2>(p, smem, stream);
+        if (p.n_acc == 4) return launch_n<EPI_PLAIN, 4>(p, smem, stream);
     }
     set_error("tc ws_gemm: no kernel instance for epilogue %d with %d accumulators", EPI, p.n_acc);
     return -1;
@@ -787,6 +846,7 @@ extern "C" int vd_tc_conv_layer(int layer, const void* in, const void* wimg, con
     VD_REQUIRE(code_first_item >= 0, "tc_conv_layer: negative code_first_item");
     VD_REQUIRE(geo_supported(plan->T, plan->H), "tc_conv_layer: unsupported geometry");
     VD_REQUIRE(raw || bias, "tc_conv_layer: bias is NULL");
+    VD_REQUIRE(raw >= 0 && raw <= 2, "tc_conv_layer: raw must be 0 (fused), 1 (accumulator dump) or 2 (plain NCDHW fp32)");
     if (B == 0) return 0;
     WsParams p;
     memset(&p, 0, sizeof(p));
@@ -799,7 +859,9 @@ extern "C" int vd_tc_conv_layer(int layer, const void* in, const void* wimg, con
     p.prof = g_prof; p.dbg = env_int("VD_TC_DBG", 0);
     p.epi.bias = bias; p.epi.out = (uint8_t*)out; p.epi.code = code; p.epi.code_first = code_first_item; p.epi.raw = (float*)out;
     p.epi.T = plan->T; p.epi.n_items = B; p.epi.g = g;
+    p.epi.layer = layer;
     cudaStream_t s = (cudaStream_t)stream;
+    if (raw == 2) return launch<EPI_PLAIN>(p, smem, s);
     if (raw) return launch<EPI_RAW>(p, smem, s);
     if (layer == 0) return launch<EPI_L0>(p, smem, s);
     if (layer == 1) return launch<EPI_L1>(p, smem, s);
@@ -850,6 +912,42 @@ extern "C" int vd_tc_bwd_gemm(int layer, const void* dy, const void* wt, void* c
     if (int rc = setup_bwd(p, g, layer, B, &smem)) return rc;
     p.pix = (const uint8_t*)dy; p.wimg = (const uint8_t*)wt; p.item_index = nullptr;
     p.epi.raw = (float*)col; p.epi.raw_bf16 = 1; p.epi.T = plan->T; p.epi.n_items = B; p.epi.g = g;
+    return launch<EPI_RAW>(p, smem, (cudaStream_t)stream);
+}
+
+// wgrad of conv `layer` as a split-K GEMM: raw[(split, ntile)][cout 128][col 256] = sum over the slice's pixels of
+// gy[cout][pixel] * xcol[(ci,tap)][pixel].  Operands from vd_tc_wgrad_pack (tc_trio.cu): the gy image is the M
+// operand (4 KiB tiles streamed through the weight ring, one K = 16 pixel step each), the im2col columns are the
+// N operand (one 64 KiB stage = 128 pixels x 256 columns per bulk copy).
+extern "C" int vd_tc_wgrad_plan(int layer, const vd_tc_plan* plan, int B, int64_t* out);
+
+extern "C" int vd_tc_wgrad_gemm(int layer, const void* xcol, const void* gyimg, float* raw, const vd_tc_plan* plan, int B,
+                                void* stream) {
+    VD_REQUIRE(xcol && gyimg && raw && plan, "tc_wgrad_gemm: NULL pointer");
+    int64_t w[6];
+    if (int rc = vd_tc_wgrad_plan(layer, plan, B, w)) return rc;
+    const int splits = (int)w[0], sps = (int)w[1], ntiles = (int)w[2];
+    WsParams p;
+    memset(&p, 0, sizeof(p));
+    p.n_u = 1; p.nu_total = 1; p.ug_count = 1; p.w_u_stride = 0;
+    p.n_tiles = splits * ntiles; p.tiles_per_item = ntiles; p.v_count = ntiles;      // item = split-K slice, v = column tile
+    p.item_stride = (int64_t)sps * 65536; p.u_stride = 0; p.v_stride = (int64_t)splits * sps * 65536;
+    p.w_item_stride = (int64_t)sps * 8 * kWeightTileBytes;
+    p.n_sa = sps; p.n_sb = 1; p.sa_stride = 65536; p.sb_stride = 0;
+    p.n_copies = 1; p.copy_gofs[0] = 0; p.copy_sofs[0] = 0; p.copy_bytes[0] = 65536; p.stage_bytes = 65536;
+    p.n_steps = 8;
+    for (int j = 0; j < 8; ++j) { p.b_off16[j] = (uint32_t)(2 * j * 256); p.b_lbo16[j] = 256; }
+    p.a_lbo16 = 2048 >> 4; p.a_sbo16 = 8;
+    p.w_resident = 0; p.w_bytes = 0;
+    p.G = 8; p.RW = 2; p.RP = 2;
+    p.n_acc = 1; p.acc_delta16 = 0;
+    p.ncols = 256; p.acc_cols = 256; p.acc_stages = 2;
+    p.idesc = umma_idesc_bf16(128, 256);
+    uint32_t smem = 0;
+    if (int rc = finalize_smem(p, (uint32_t)p.G * p.RW * kWeightTileBytes, &smem, true)) return rc;
+    const Geo g = make_geo(plan->T, plan->H);
+    p.pix = (const uint8_t*)xcol; p.wimg = (const uint8_t*)gyimg; p.item_index = nullptr;
+    p.epi.raw = raw; p.epi.raw_bf16 = 0; p.epi.T = plan->T; p.epi.n_items = B; p.epi.g = g;
     return launch<EPI_RAW>(p, smem, (cudaStream_t)stream);
 }
 

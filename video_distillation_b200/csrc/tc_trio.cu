@@ -1,0 +1,234 @@
+// Operand packers of the differentiable conv trio on tensor cores (ops.py: fprop / dgrad / wgrad of the
+// three ConvNet3D feature convolutions, networks.py:799, as used by the MTT unroll and its double backward).
+// Inputs are plain fp32 NCDHW tensors; outputs are the packed bf16 operands of ws_gemm_kernel (tc_layout.h).
+//   fprop : x -> X0 (vd_tc_pack_video on the permuted tensor) / A1 / A2, then vd_tc_conv_layer(raw = 2)
+//   dgrad : gy -> dY [video][NT][K/8][NC][8], vd_tc_bwd_gemm, vd_tc_bwd_col2im_plain
+//   wgrad : x -> im2col columns, gy -> "weight image", vd_tc_wgrad_gemm (split-K), vd_tc_wgrad_reduce
+// Memory-bound kernels, one 16-byte chunk per thread.
+#include "tc_common.cuh"
+#include "tc_layout.h"
+
+namespace vd {
+namespace tc {
+
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+    uint4 o;
+    o.x = f2bf(v[0]) | ((uint32_t)f2bf(v[1]) << 16); o.y = f2bf(v[2]) | ((uint32_t)f2bf(v[3]) << 16);
+    o.z = f2bf(v[4]) | ((uint32_t)f2bf(v[5]) << 16); o.w = f2bf(v[6]) | ((uint32_t)f2bf(v[7]) << 16);
+    return o;
+}
+
+// x (B, 64, T, H1, H1) fp32 -> A1 [item][slice 4][t_pad T+2][ph 2][pw 2][k 2][i RI1][j P1] chunks (8 channels)
+__global__ void pack_a1_kernel(const float* __restrict__ x, uint4* __restrict__ a1, int64_t total, Geo g) {
+    const int64_t S1 = (int64_t)g.T * g.H1 * g.H1;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int j = (int)(i % g.P1); int64_t q = i / g.P1;
+        int ii = (int)(q % g.RI1); q /= g.RI1;
+        int k = (int)(q % 2); q /= 2;
+        int pw = (int)(q % 2); q /= 2;
+        int ph = (int)(q % 2); q /= 2;
+        int tp = (int)(q % (g.T + 2)); q /= (g.T + 2);
+        int slice = (int)(q % 4); int64_t item = q / 4;
+        const int t = tp - 1, h = ph ? 2 * ii - 3 : 2 * ii - 2, w = pw ? 2 * j - 3 : 2 * j - 2;
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (t >= 0 && t < g.T && h >= 0 && h < g.H1 && w >= 0 && w < g.H1) {
+            const float* p = x + (item * 64 + slice * 16 + k * 8) * S1 + ((int64_t)t * g.H1 + h) * g.H1 + w;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = __ldg(p + e * S1);
+        }
+        a1[i] = pack8(v);
+    }
+}
+
+// x (B, 128, T2, H2, H2) fp32 -> A2 [item][khw 49][half 2][k 8][t_pad To2+2][ho Ho2][wo Wo2] chunks (8 channels)
+__global__ void pack_a2_kernel(const float* __restrict__ x, uint4* __restrict__ a2, int64_t total, Geo g) {
+    const int64_t S2 = (int64_t)g.T2 * g.H2 * g.H2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int wo = (int)(i % g.Wo2); int64_t q = i / g.Wo2;
+        int ho = (int)(q % g.Ho2); q /= g.Ho2;
+        int tp = (int)(q % (g.To2 + 2)); q /= (g.To2 + 2);
+        int k = (int)(q % 8); q /= 8;
+        int half = (int)(q % 2); q /= 2;
+        int khw = (int)(q % 49); int64_t item = q / 49;
+        const int kh = khw / 7, kw = khw % 7;
+        const int t = tp - 1, h = 2 * ho + kh - 3, w = 2 * wo + kw - 3;
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (t >= 0 && t < g.T2 && h >= 0 && h < g.H2 && w >= 0 && w < g.H2) {
+            const float* p = x + (item * 128 + half * 64 + k * 8) * S2 + ((int64_t)t * g.H2 + h) * g.H2 + w;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = __ldg(p + e * S2);
+        }
+        a2[i] = pack8(v);
+    }
+}
+
+// gy (B, K, To, Ho, Wo) fp32 -> dY [video][nt NT][chunk K/8][col NC][8] bf16
+__global__ void pack_dy_kernel(const float* __restrict__ gy, uint4* __restrict__ dy, int64_t total, BwdGeo b) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int col = (int)(i % b.NC); int64_t q = i / b.NC;
+        int chunk = (int)(q % (b.K / 8)); q /= (b.K / 8);
+        int nt = (int)(q % b.NT); int64_t vid = q / b.NT;
+        const float* p = gy + (vid * b.K + chunk * 8) * (int64_t)b.pixels + nt * b.NC + col;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = __ldg(p + (int64_t)e * b.pixels);
+        dy[i] = pack8(v);
+    }
+}
+
+// ---- wgrad operands.  Pixels k = ((video*To + to)*Ho + ho)*Wo + wo are the GEMM's K dimension, padded with
+// zeros to P_pad (a multiple of 128 per split-K slice); columns n = ci*147 + tap (< Cin*147, padded to 256s).
+//   xcol : [ntile][stage P_pad/128][chunk 16][col 256][8 pixels]      (N operand, one 64 KiB stage per bulk copy)
+//   gyimg: [kstep P_pad/16][k 2][128 rows = cout][8 pixels]            (M operand, 4 KiB UMMA tiles)
+__global__ void wgrad_im2col_kernel(const float* __restrict__ x, uint4* __restrict__ xcol, int64_t total, BwdGeo b,
+                                    int64_t P, int64_t n_stage) {
+    const int64_t Si = (int64_t)b.Ti * b.Hi * b.Wi;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int col = (int)(i % 256); int64_t q = i / 256;
+        int c = (int)(q % 16); q /= 16;
+        int64_t stage = q % n_stage; int64_t ntile = q / n_stage;
+        const int n = (int)(ntile * 256 + col);
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (n < b.Cin * 147) {
+            const int ci = n / 147, tap = n - ci * 147;
+            const int kt = tap / 49, kh = (tap / 7) % 7, kw = tap % 7;
+            int64_t k = stage * 128 + c * 8;
+            int wo = (int)(k % b.Wo); int64_t r = k / b.Wo;
+            int ho = (int)(r % b.Ho); r /= b.Ho;
+            int to = (int)(r % b.To); int64_t vid = r / b.To;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                if (k + e < P) {
+                    const int t = to + kt - 1, h = 2 * ho + kh - 3, w = 2 * wo + kw - 3;
+                    if ((unsigned)t < (unsigned)b.Ti && (unsigned)h < (unsigned)b.Hi && (unsigned)w < (unsigned)b.Wi)
+                        v[e] = __ldg(x + (vid * b.Cin + ci) * Si + ((int64_t)t * b.Hi + h) * b.Wi + w);
+                }
+                if (++wo == b.Wo) { wo = 0; if (++ho == b.Ho) { ho = 0; if (++to == b.To) { to = 0; ++vid; } } }
+            }
+        }
+        xcol[i] = pack8(v);
+    }
+}
+
+__global__ void wgrad_gyimg_kernel(const float* __restrict__ gy, uint4* __restrict__ img, int64_t total, BwdGeo b, int64_t P) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int row = (int)(i % 128); int64_t q = i / 128;
+        int k2 = (int)(q % 2); int64_t kstep = q / 2;
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (row < b.K) {
+            const int64_t k0 = kstep * 16 + k2 * 8;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int64_t k = k0 + e;
+                if (k < P) {
+                    const int64_t vid = k / b.pixels, pix = k - vid * b.pixels;
+                    v[e] = __ldg(gy + (vid * b.K + row) * (int64_t)b.pixels + pix);
+                }
+            }
+        }
+        img[i] = pack8(v);
+    }
+}
+
+// gw[co][n] = sum over split-K slices of raw[(split*ntiles + ntile)][co][col], n = ntile*256 + col
+__global__ void wgrad_reduce_kernel(const float* __restrict__ raw, float* __restrict__ gw, int Cout, int Ncols, int ntiles, int splits) {
+    const int64_t total = (int64_t)Cout * Ncols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int n = (int)(i % Ncols), co = (int)(i / Ncols);
+        const int ntile = n >> 8, col = n & 255;
+        float s = 0.f;
+        for (int sp = 0; sp < splits; ++sp) s += raw[(((int64_t)sp * ntiles + ntile) * 128 + co) * 256 + col];
+        gw[i] = s;
+    }
+}
+
+static inline unsigned grid_of(int64_t n) {
+    int64_t x = (n + 255) / 256;
+    const int64_t cap = 148 * 32;
+    return (unsigned)(x < 1 ? 1 : (x > cap ? cap : x));
+}
+
+}  // namespace tc
+}  // namespace vd
+
+using namespace vd;
+using namespace vd::tc;
+
+// x fp32 NCDHW (B, 64, T, H/4, W/4) -> A1 (layer 1) or (B, 128, T/2, H/16.., ..) -> A2 (layer 2); every chunk of the
+// packed operand (halo included) is written.
+extern "C" int vd_tc_pack_act(int layer, const float* x, void* packed, const vd_tc_plan* plan, int B, void* stream) {
+    VD_REQUIRE(x && packed && plan, "tc_pack_act: NULL pointer");
+    VD_REQUIRE(layer == 1 || layer == 2, "tc_pack_act: layer must be 1 or 2 (layer 0 uses vd_tc_pack_video)");
+    VD_REQUIRE(geo_supported(plan->T, plan->H), "tc_pack_act: unsupported geometry");
+    if (B <= 0) return 0;
+    const Geo g = make_geo(plan->T, plan->H);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (layer == 1) {
+        const int64_t total = (int64_t)B * (g.video1 / 16);
+        pack_a1_kernel<<<grid_of(total), 256, 0, s>>>(x, (uint4*)packed, total, g);
+    } else {
+        const int64_t total = (int64_t)B * (g.video2 / 16);
+        pack_a2_kernel<<<grid_of(total), 256, 0, s>>>(x, (uint4*)packed, total, g);
+    }
+    return check_launch("tc_pack_act");
+}
+
+// gy fp32 NCDHW (B, Cout, To, Ho, Wo) of conv `layer` -> packed dY operand of vd_tc_bwd_gemm
+extern "C" int vd_tc_pack_dy(int layer, const float* gy, void* dy, const vd_tc_plan* plan, int B, void* stream) {
+    VD_REQUIRE(gy && dy && plan, "tc_pack_dy: NULL pointer");
+    VD_REQUIRE(layer >= 0 && layer <= 2 && geo_supported(plan->T, plan->H), "tc_pack_dy: bad layer / geometry");
+    if (B <= 0) return 0;
+    const Geo g = make_geo(plan->T, plan->H);
+    const BwdGeo b = make_bwd_geo(g, layer);
+    const int64_t total = (int64_t)B * b.NT * (b.K / 8) * b.NC;
+    pack_dy_kernel<<<grid_of(total), 256, 0, (cudaStream_t)stream>>>(gy, (uint4*)dy, total, b);
+    return check_launch("tc_pack_dy");
+}
+
+// Sizes of the wgrad workspace for B videos: out[0] = split-K slices, out[1] = stages per slice, out[2] = column
+// tiles, out[3] = xcol bytes, out[4] = gyimg bytes, out[5] = raw (fp32 partial sums) bytes
+extern "C" int vd_tc_wgrad_plan(int layer, const vd_tc_plan* plan, int B, int64_t* out) {
+    VD_REQUIRE(plan && out, "tc_wgrad_plan: NULL pointer");
+    VD_REQUIRE(layer >= 0 && layer <= 2 && geo_supported(plan->T, plan->H) && B > 0, "tc_wgrad_plan: bad layer / geometry / batch");
+    const Geo g = make_geo(plan->T, plan->H);
+    const BwdGeo b = make_bwd_geo(g, layer);
+    const int64_t P = (int64_t)B * b.pixels;
+    const int64_t ntiles = (b.Cin * 147 + 255) / 256;
+    const int64_t stages = (P + 127) / 128;
+    int64_t splits = (2 * 148 + ntiles - 1) / ntiles;
+    if (splits > stages) splits = stages;
+    if (splits < 1) splits = 1;
+    const int64_t sps = (stages + splits - 1) / splits;
+    out[0] = splits; out[1] = sps; out[2] = ntiles;
+    out[3] = ntiles * splits * sps * 65536;
+    out[4] = splits * sps * 8 * 4096;
+    out[5] = ntiles * splits * 128 * 256 * 4;
+    return 0;
+}
+
+extern "C" int vd_tc_wgrad_pack(int layer, const float* x, const float* gy, void* xcol, void* gyimg, const vd_tc_plan* plan,
+                                int B, void* stream) {
+    VD_REQUIRE(x && gy && xcol && gyimg && plan, "tc_wgrad_pack: NULL pointer");
+    int64_t w[6];
+    if (int rc = vd_tc_wgrad_plan(layer, plan, B, w)) return rc;
+    const Geo g = make_geo(plan->T, plan->H);
+    const BwdGeo b = make_bwd_geo(g, layer);
+    const int64_t P = (int64_t)B * b.pixels, n_stage = w[0] * w[1];
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t total_x = w[2] * n_stage * 16 * 256;
+    wgrad_im2col_kernel<<<grid_of(total_x), 256, 0, s>>>(x, (uint4*)xcol, total_x, b, P, n_stage);
+    if (int e = check_launch("tc_wgrad_im2col")) return e;
+    const int64_t total_g = n_stage * 8 * 2 * 128;
+    wgrad_gyimg_kernel<<<grid_of(total_g), 256, 0, s>>>(gy, (uint4*)gyimg, total_g, b, P);
+    return check_launch("tc_wgrad_gyimg");
+}
+
+extern "C" int vd_tc_wgrad_reduce(int layer, const float* raw, float* gw, const vd_tc_plan* plan, int B, void* stream) {
+    VD_REQUIRE(raw && gw && plan, "tc_wgrad_reduce: NULL pointer");
+    int64_t w[6];
+    if (int rc = vd_tc_wgrad_plan(layer, plan, B, w)) return rc;
+    const Geo g = make_geo(plan->T, plan->H);
+    const BwdGeo b = make_bwd_geo(g, layer);
+    wgrad_reduce_kernel<<<grid_of((int64_t)b.K * b.Cin * 147), 256, 0, (cudaStream_t)stream>>>(raw, gw, b.K, b.Cin * 147, (int)w[2], (int)w[0]);
+    return check_launch("tc_wgrad_reduce");
+}

@@ -34,9 +34,34 @@ def _f32c(t):
     return t.contiguous()
 
 
+# ------------------------------------------------------------------ conv backend of the trio
+_CONV_BACKEND = 'fp32'
+
+
+def set_conv_backend(name):
+    """'fp32': exact CUDA-core kernels (parity mode).  'tc': the feature-conv geometries of ConvNet3D run as
+    bf16 tcgen05 GEMMs with fp32 accumulation (tc_trio.py); other convolutions stay on the fp32 kernels."""
+    global _CONV_BACKEND
+    if name not in ('fp32', 'tc'):
+        raise ValueError("conv backend must be 'fp32' or 'tc'")
+    prev, _CONV_BACKEND = _CONV_BACKEND, name
+    return prev
+
+
+def _tc_route(x_shape, w_shape, stride, padding, device):
+    if _CONV_BACKEND != 'tc':
+        return None, None
+    from .tc_trio import trio_for
+    return trio_for(tuple(x_shape), tuple(w_shape), _triple(stride), _triple(padding), device)
+
+
 # ------------------------------------------------------------------ raw kernels
 def conv3d_fprop_raw(x, w, bias, stride, padding):
     x, w = _f32c(x), _f32c(w)
+    trio, layer = _tc_route(x.shape, w.shape, stride, padding, x.device)
+    if trio is not None and x.shape[0] > 0:
+        y = trio.fprop(layer, x, w)
+        return y if bias is None else y + bias.view(1, -1, 1, 1, 1)
     g = conv_geom(x.shape, w.shape, stride, padding)
     y = torch.empty(g.N, g.Cout, g.To, g.Ho, g.Wo, dtype=torch.float32, device=x.device)
     if y.numel():
@@ -49,6 +74,9 @@ def conv3d_dgrad_raw(gy, w, x_shape, stride, padding):
     gy, w = _f32c(gy), _f32c(w)
     g = conv_geom(x_shape, w.shape, stride, padding)
     assert tuple(gy.shape) == (g.N, g.Cout, g.To, g.Ho, g.Wo), (tuple(gy.shape), (g.N, g.Cout, g.To, g.Ho, g.Wo))
+    trio, layer = _tc_route(x_shape, w.shape, stride, padding, gy.device)
+    if trio is not None and gy.shape[0] > 0:
+        return trio.dgrad(layer, gy, w)
     gx = torch.empty(tuple(x_shape), dtype=torch.float32, device=gy.device)
     if gx.numel():
         check(lib().vd_conv3d_dgrad_f32(ptr(gy), ptr(w), ptr(gx), ctypes.byref(g), stream()), 'conv3d_dgrad')
@@ -58,6 +86,10 @@ def conv3d_dgrad_raw(gy, w, x_shape, stride, padding):
 def conv3d_wgrad_raw(x, gy, w_shape, stride, padding, want_bias=False):
     x, gy = _f32c(x), _f32c(gy)
     g = conv_geom(x.shape, w_shape, stride, padding)
+    trio, layer = _tc_route(x.shape, w_shape, stride, padding, x.device)
+    if trio is not None and x.shape[0] > 0:
+        gw = trio.wgrad(layer, x, gy)
+        return (gw, gy.sum(dim=(0, 2, 3, 4))) if want_bias else gw
     gw = torch.zeros(tuple(w_shape), dtype=torch.float32, device=x.device)
     gb = torch.zeros(g.Cout, dtype=torch.float32, device=x.device) if want_bias else None
     if x.numel() and gy.numel():

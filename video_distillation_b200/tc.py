@@ -148,7 +148,7 @@ class TcConvNet3D:
     def _conv_layer(self, layer, src, wimg, bias, out, B, code=None, item_index=None, raw=False, code_first=0):
         _lib.check(_lib.lib().vd_tc_conv_layer(layer, _lib.ptr(src), _lib.ptr(wimg), _lib.ptr(bias), _lib.ptr(out),
                                                _lib.ptr(code), int(code_first), ctypes.byref(self.plan), _lib.ptr(item_index),
-                                               int(B), int(bool(raw)), _lib.stream()), f'vd_tc_conv_layer({layer})')
+                                               int(B), int(raw), _lib.stream()), f'vd_tc_conv_layer({layer})')
 
     def embed_packed(self, x0, B, item_index=None, out=None, codes=None):
         """conv0..2 on an already packed X0 (optionally a resident set addressed by item_index)."""

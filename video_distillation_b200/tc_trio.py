@@ -1,0 +1,141 @@
+"""The differentiable conv trio (fprop / dgrad / wgrad) of the three ConvNet3D feature convolutions on tensor
+cores: bf16 operands, fp32 accumulation, plain fp32 NCDHW tensors in and out.
+
+``ops.conv3d`` builds the MTT unroll and its double backward from three primitives (``ops._Fprop/_Dgrad/_Wgrad``,
+closed under differentiation).  With ``ops.set_conv_backend('tc')`` those primitives route here whenever the call
+has the geometry of networks.py:799 (k=(3,7,7), s=(1,2,2), p=(1,3,3)) on a supported video shape; everything else
+(the 1x1x1 logit conv, odd shapes) stays on the exact fp32 kernels.  Every launch goes through the C ABI.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from .tc import make_plan, tc_supported
+
+_KERNEL, _STRIDE, _PAD = (3, 7, 7), (1, 2, 2), (1, 3, 3)
+
+
+class TcTrio:
+    def __init__(self, T, H, W, device):
+        self.plan = make_plan(T, H, W)
+        self.device = torch.device(device)
+        p = self.plan
+        # (Cin, Cout, input extent) per layer
+        self.layers = [
+            (3, 64, (p.T, p.H, p.W)),
+            (64, 128, (p.T1p, p.H1p, p.W1p)),
+            (128, 128, (p.T2p, p.H2p, p.W2p)),
+        ]
+        self._ws = {}
+
+    # ------------------------------------------------------------------ helpers
+    def layer_of(self, cin, cout, extent):
+        for l, (ci, co, ext) in enumerate(self.layers):
+            if ci == cin and co == cout and tuple(ext) == tuple(extent):
+                return l
+        return None
+
+    def _buf(self, name, nbytes, zero=False):
+        t = self._ws.get(name)
+        if t is None or t.numel() < nbytes:
+            t = (torch.zeros if zero else torch.empty)(int(nbytes), dtype=torch.uint8, device=self.device)
+            self._ws[name] = t
+        return t
+
+    def _pack_input(self, layer, x):
+        p, lib, B = self.plan, _lib.lib(), int(x.shape[0])
+        if layer == 0:
+            buf = self._buf('x0', B * p.x0_bytes_per_video)
+            v = x.permute(0, 2, 1, 3, 4).contiguous()
+            _lib.check(lib.vd_tc_pack_video(_lib.ptr(v), None, _lib.ptr(buf), ctypes.byref(p), B, _lib.stream()), 'vd_tc_pack_video')
+        elif layer == 1:
+            buf = self._buf('a1', B * p.a1_bytes_per_video)
+            _lib.check(lib.vd_tc_pack_act(1, _lib.ptr(x), _lib.ptr(buf), ctypes.byref(p), B, _lib.stream()), 'vd_tc_pack_act(1)')
+        else:
+            buf = self._buf('a2', (B + 3) // 4 * 4 * p.a2_bytes_per_video, zero=True)
+            _lib.check(lib.vd_tc_pack_act(2, _lib.ptr(x), _lib.ptr(buf), ctypes.byref(p), B, _lib.stream()), 'vd_tc_pack_act(2)')
+        return buf
+
+    # ------------------------------------------------------------------ the trio
+    def fprop(self, layer, x, w):
+        p, lib, B = self.plan, _lib.lib(), int(x.shape[0])
+        cin, cout, _ = self.layers[layer]
+        wimg = self._buf(f'w{layer}', (p.w0_bytes, p.w1_bytes, p.w2_bytes)[layer])
+        ws = [None, None, None]
+        imgs = [None, None, None]
+        ws[layer], imgs[layer] = w, wimg
+        _lib.check(lib.vd_tc_pack_weights(_lib.ptr(ws[0]), _lib.ptr(ws[1]), _lib.ptr(ws[2]), _lib.ptr(imgs[0]), _lib.ptr(imgs[1]),
+                                          _lib.ptr(imgs[2]), _lib.stream()), 'vd_tc_pack_weights')
+        src = self._pack_input(layer, x)
+        out_ext = [(p.T1, p.H1, p.W1), (p.T2, p.H2, p.W2), (p.T3, p.H3, p.W3)][layer]
+        y = torch.empty(B, cout, *out_ext, dtype=torch.float32, device=self.device)
+        _lib.check(lib.vd_tc_conv_layer(layer, _lib.ptr(src), _lib.ptr(wimg), None, _lib.ptr(y), None, 0, ctypes.byref(p), None,
+                                        B, 2, _lib.stream()), f'vd_tc_conv_layer({layer}, plain)')
+        return y
+
+    def dgrad(self, layer, gy, w):
+        p, lib, B = self.plan, _lib.lib(), int(gy.shape[0])
+        cin, cout, ext = self.layers[layer]
+        wt = self._buf(f'wt{layer}', (p.wt0_bytes, p.wt1_bytes, p.wt2_bytes)[layer])
+        ws = [None, None, None]
+        imgs = [None, None, None]
+        ws[layer], imgs[layer] = w, wt
+        _lib.check(lib.vd_tc_pack_weights_bwd(_lib.ptr(ws[0]), _lib.ptr(ws[1]), _lib.ptr(ws[2]), _lib.ptr(imgs[0]), _lib.ptr(imgs[1]),
+                                              _lib.ptr(imgs[2]), _lib.stream()), 'vd_tc_pack_weights_bwd')
+        dy = self._buf('dy', B * (p.dy0_bytes_per_video, p.dy1_bytes_per_video, p.dy2_bytes_per_video)[layer])
+        col = self._buf('col', B * (p.col0_bytes_per_video, p.col1_bytes_per_video, p.col2_bytes_per_video)[layer])
+        plan, st = ctypes.byref(p), _lib.stream()
+        _lib.check(lib.vd_tc_pack_dy(layer, _lib.ptr(gy), _lib.ptr(dy), plan, B, st), 'vd_tc_pack_dy')
+        _lib.check(lib.vd_tc_bwd_gemm(layer, _lib.ptr(dy), _lib.ptr(wt), _lib.ptr(col), plan, B, st), 'vd_tc_bwd_gemm')
+        gx = torch.empty(B, cin, *ext, dtype=torch.float32, device=self.device)
+        _lib.check(lib.vd_tc_bwd_col2im_plain(layer, _lib.ptr(col), _lib.ptr(gx), plan, B, st), 'vd_tc_bwd_col2im_plain')
+        return gx
+
+    def wgrad(self, layer, x, gy):
+        p, lib, B = self.plan, _lib.lib(), int(x.shape[0])
+        cin, cout, _ = self.layers[layer]
+        sizes = (ctypes.c_int64 * 6)()
+        _lib.check(lib.vd_tc_wgrad_plan(layer, ctypes.byref(p), B, sizes), 'vd_tc_wgrad_plan')
+        xcol = self._buf('xcol', sizes[3])
+        gyimg = self._buf('gyimg', sizes[4])
+        raw = self._buf('wraw', sizes[5])
+        plan, st = ctypes.byref(p), _lib.stream()
+        _lib.check(lib.vd_tc_wgrad_pack(layer, _lib.ptr(x), _lib.ptr(gy), _lib.ptr(xcol), _lib.ptr(gyimg), plan, B, st), 'vd_tc_wgrad_pack')
+        _lib.check(lib.vd_tc_wgrad_gemm(layer, _lib.ptr(xcol), _lib.ptr(gyimg), _lib.ptr(raw), plan, B, st), 'vd_tc_wgrad_gemm')
+        gw = torch.empty(cout, cin, 3, 7, 7, dtype=torch.float32, device=self.device)
+        _lib.check(lib.vd_tc_wgrad_reduce(layer, _lib.ptr(raw), _lib.ptr(gw), plan, B, st), 'vd_tc_wgrad_reduce')
+        return gw
+
+
+_trios = {}
+
+
+def trio_for(x_shape, w_shape, stride, padding, device):
+    """(TcTrio, layer) when the conv (x_shape NCDHW, w_shape OIDHW) is one of the three feature convolutions of a
+    supported video shape, else (None, None)."""
+    if tuple(w_shape[2:]) != _KERNEL or tuple(stride) != _STRIDE or tuple(padding) != _PAD:
+        return None, None
+    N, cin, T, H, W = x_shape
+    cout = w_shape[0]
+    # recover the video shape of the plan this layer belongs to
+    if cin == 3:
+        vid = (T, H, W)
+    elif cin == 64:
+        vid = (T, H * 4, W * 4)
+    elif cin == 128:
+        vid = (T * 2, H * 16, W * 16)
+    else:
+        return None, None
+    cands = [vid] if cin != 128 else [vid, (T * 2, 112, 112), (T * 2, 64, 64)]
+    for (t, h, w) in cands:
+        if not tc_supported(t, h, w):
+            continue
+        key = (t, h, w, str(device))
+        trio = _trios.get(key)
+        if trio is None:
+            trio = _trios[key] = TcTrio(t, h, w, device)
+        layer = trio.layer_of(cin, cout, (T, H, W))
+        if layer is not None:
+            return trio, layer
+    return None, None
