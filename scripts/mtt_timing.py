@@ -12,8 +12,9 @@ from video_distillation_b200.networks import ConvNet3D  # noqa: E402
 
 C, T, HW = 50, 16, 112
 syn_steps = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+precision = sys.argv[2] if len(sys.argv) > 2 else 'bf16'
 torch.manual_seed(0)
-tr = MTTS2DTrainer(num_classes=C, im_size=(HW, HW), frames=T, vpc=1, spc=2, dpc=2, syn_steps=syn_steps, device='cuda')
+tr = MTTS2DTrainer(num_classes=C, im_size=(HW, HW), frames=T, vpc=1, spc=2, dpc=2, syn_steps=syn_steps, device='cuda', precision=precision)
 base = ConvNet3D(3, C, 128, 3, 'relu', 'none', 'maxpooling', T, (HW, HW))
 start = [p.detach().clone() for p in base.parameters()]
 target = [p.detach().clone() + 0.01 * torch.randn_like(p) for p in base.parameters()]
@@ -22,5 +23,5 @@ for i in range(2):
     t0 = time.perf_counter()
     loss = tr.step(start, target, net_seed=1)
     torch.cuda.synchronize()
-    print(f'MTT iteration {i}: syn_steps={syn_steps} batch_syn={C} -> {time.perf_counter() - t0:.3f} s, grand loss {loss.item():.6f}, '
+    print(f'MTT iteration {i} [{precision}]: syn_steps={syn_steps} batch_syn={C} -> {time.perf_counter() - t0:.3f} s, grand loss {loss.item():.6f}, '
           f'peak mem {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB', flush=True)

@@ -176,8 +176,10 @@ def test_dm_s2d_bf16_tensor_core_real_path():
     assert abs(losses['bf16'][0] - losses['fp32'][0]) < 2e-2 * abs(losses['fp32'][0]) + 1e-6
 
 
-def test_mtt_s2d_golden():
-    """Unrolled student with second-order autograd through our conv trio vs the reference."""
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_mtt_s2d_golden(precision):
+    """Unrolled student with second-order autograd through our conv trio vs the reference: exact fp32 kernels,
+    and the tensor-core trio (bf16 operands / fp32 accumulate, every first- and second-order conv term)."""
     from oracle import synth
     from video_distillation_b200.distill import MTTS2DTrainer
     from video_distillation_b200.networks import ConvNet3D
@@ -188,7 +190,7 @@ def test_mtt_s2d_golden():
     hal = Conv3DNet()
     hal.load_state_dict(synth.synth_hallucinator(7))
     tr = MTTS2DTrainer(num_classes=C, im_size=(H, H), frames=T, vpc=vpc, spc=spc, dpc=dpc, syn_steps=syn_steps,
-                       lr_teacher=0.01, hal=hal, static_syn=synth.hash_uniform((C * spc, 3, H, H), 71),
+                       lr_teacher=0.01, hal=hal, precision=precision, static_syn=synth.hash_uniform((C * spc, 3, H, H), 71),
                        dynamic_syn=synth.hash_uniform((C, dpc, T, 1, H, H), 72))
     start = synth.synth_convnet3d_params(80, num_classes=C)
     target = {k: v + synth.hash_uniform(tuple(v.shape), 900 + i, 2.0 ** -10) for i, (k, v) in enumerate(start.items())}
@@ -220,9 +222,18 @@ def test_mtt_s2d_golden():
         grand = tr.step(list(start.values()), list(target.values()), student_net=student)
     finally:
         torch.randperm, torch.randint = real_randperm, real_randint
-    assert rel(grand, gold['grand_loss']) < 1e-5
     assert rel(tr.last['param_dist'], gold['param_dist']) < 1e-5
-    assert rel(tr.hal.encoder.weight.grad, gold['grad_hal_weight']) < 1e-3
-    assert rel(tr.hal.encoder.bias.grad, gold['grad_hal_bias']) < 1e-3
-    assert rel(tr.syn_lr.grad, gold['grad_syn_lr']) < 1e-3
-    check_summary(tr.dynamic_syn.grad, gold['grad_dynamic_sums'], gold['grad_dynamic_sample'])
+    if precision == 'fp32':
+        assert rel(grand, gold['grand_loss']) < 1e-5
+        assert rel(tr.hal.encoder.weight.grad, gold['grad_hal_weight']) < 1e-3
+        assert rel(tr.hal.encoder.bias.grad, gold['grad_hal_bias']) < 1e-3
+        assert rel(tr.syn_lr.grad, gold['grad_syn_lr']) < 1e-3
+        check_summary(tr.dynamic_syn.grad, gold['grad_dynamic_sums'], gold['grad_dynamic_sample'])
+    else:
+        # split-bf16 fprop (3 passes) + single-pass bf16 dgrad / wgrad: hallucinator / lr gradients within 1e-2, dynamic memory 2e-2
+        errs = dict(grand=rel(grand, gold['grand_loss']), hal_w=rel(tr.hal.encoder.weight.grad, gold['grad_hal_weight']),
+                    hal_b=rel(tr.hal.encoder.bias.grad, gold['grad_hal_bias']), lr=rel(tr.syn_lr.grad, gold['grad_syn_lr']))
+        print('mtt bf16 tensor-core trio vs reference:', errs)
+        assert errs['grand'] < 1e-5, errs
+        assert errs['hal_w'] < 1e-2 and errs['hal_b'] < 1e-2 and errs['lr'] < 1e-2, errs
+        check_summary(tr.dynamic_syn.grad, gold['grad_dynamic_sums'], gold['grad_dynamic_sample'], tol=2e-2)   # observed 1.2e-2

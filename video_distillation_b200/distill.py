@@ -398,11 +398,17 @@ class DMBaselineTrainer:
 
 class MTTS2DTrainer:
     """MTT + static/dynamic memory (distill_s2d_ms.py:197-300): unrolled ReparamModule student with
-    second-order autograd through the conv trio; exact fp32 path."""
+    second-order autograd through the conv trio.  precision='fp32': exact CUDA-core kernels (parity mode);
+    'bf16': every fprop / dgrad / wgrad of the three feature convolutions (first and second order) runs as a
+    tcgen05 GEMM with bf16 operands and fp32 accumulation (tc_trio.py)."""
 
     def __init__(self, *, num_classes, channel=3, im_size=(112, 112), frames=16, vpc=1, spc=2, dpc=2, syn_steps=10,
                  lr_dynamic=1e4, lr_hal=1e-2, lr_static=1e-4, lr_lr=1e-5, lr_teacher=0.01, train_static=False,
-                 train_lr=True, batch_syn=None, static_syn=None, dynamic_syn=None, hal=None, device='cuda'):
+                 train_lr=True, batch_syn=None, static_syn=None, dynamic_syn=None, hal=None, device='cuda',
+                 precision='fp32'):
+        if precision not in ('fp32', 'bf16'):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        self.precision = precision
         self.C, self.channel, self.im_size, self.frames = num_classes, channel, tuple(im_size), frames
         self.vpc, self.spc, self.dpc, self.syn_steps = vpc, spc, dpc, syn_steps
         self.lr = dict(dynamic=lr_dynamic, hal=lr_hal, static=lr_static, lr=lr_lr)
@@ -430,6 +436,13 @@ class MTTS2DTrainer:
 
     def step(self, start_params, target_params, student_net=None, net_seed=None):
         """start_params / target_params: lists of expert tensors (buffer.py layout) or flat tensors."""
+        prev = ops.set_conv_backend('tc' if self.precision == 'bf16' else 'fp32')
+        try:
+            return self._step(start_params, target_params, student_net, net_seed)
+        finally:
+            ops.set_conv_backend(prev)
+
+    def _step(self, start_params, target_params, student_net=None, net_seed=None):
         C, vpc, spc, dev = self.C, self.vpc, self.spc, self.device
         if student_net is None:
             if net_seed is not None:

@@ -48,8 +48,12 @@ def set_conv_backend(name):
     return prev
 
 
-def _tc_route(x_shape, w_shape, stride, padding, device):
-    if _CONV_BACKEND != 'tc':
+_TC_FPROP_SPLIT = __import__('os').environ.get('VD_TC_FPROP_SPLIT', '1') != '0'
+_TC_OPS = set(__import__('os').environ.get('VD_TC_OPS', 'fprop,dgrad,wgrad').split(','))     # experiment knob
+
+
+def _tc_route(x_shape, w_shape, stride, padding, device, op='fprop'):
+    if _CONV_BACKEND != 'tc' or op not in _TC_OPS:
         return None, None
     from .tc_trio import trio_for
     return trio_for(tuple(x_shape), tuple(w_shape), _triple(stride), _triple(padding), device)
@@ -60,7 +64,18 @@ def conv3d_fprop_raw(x, w, bias, stride, padding):
     x, w = _f32c(x), _f32c(w)
     trio, layer = _tc_route(x.shape, w.shape, stride, padding, x.device)
     if trio is not None and x.shape[0] > 0:
-        y = trio.fprop(layer, x, w)
+        if _TC_FPROP_SPLIT:
+            # split-bf16: x = xh + xl, w = wh + wl (bf16 each); xh*wh + xh*wl + xl*wh recovers ~16 mantissa bits.
+            # The forward decides ReLU masks / pool argmax and the logits, so it is the precision-critical third of
+            # the trio (single-pass bf16 fprop alone costs 5-7 % on MTT's second-order gradients; measured in
+            # tests/test_dm_gpu.py::test_mtt_s2d_golden).
+            xh = x.to(torch.bfloat16).float()
+            wh = w.to(torch.bfloat16).float()
+            y = trio.fprop(layer, xh, wh)
+            y += trio.fprop(layer, xh, w - wh)
+            y += trio.fprop(layer, x - xh, wh)
+        else:
+            y = trio.fprop(layer, x, w)
         return y if bias is None else y + bias.view(1, -1, 1, 1, 1)
     g = conv_geom(x.shape, w.shape, stride, padding)
     y = torch.empty(g.N, g.Cout, g.To, g.Ho, g.Wo, dtype=torch.float32, device=x.device)
@@ -74,7 +89,7 @@ def conv3d_dgrad_raw(gy, w, x_shape, stride, padding):
     gy, w = _f32c(gy), _f32c(w)
     g = conv_geom(x_shape, w.shape, stride, padding)
     assert tuple(gy.shape) == (g.N, g.Cout, g.To, g.Ho, g.Wo), (tuple(gy.shape), (g.N, g.Cout, g.To, g.Ho, g.Wo))
-    trio, layer = _tc_route(x_shape, w.shape, stride, padding, gy.device)
+    trio, layer = _tc_route(x_shape, w.shape, stride, padding, gy.device, 'dgrad')
     if trio is not None and gy.shape[0] > 0:
         return trio.dgrad(layer, gy, w)
     gx = torch.empty(tuple(x_shape), dtype=torch.float32, device=gy.device)
@@ -86,7 +101,7 @@ def conv3d_dgrad_raw(gy, w, x_shape, stride, padding):
 def conv3d_wgrad_raw(x, gy, w_shape, stride, padding, want_bias=False):
     x, gy = _f32c(x), _f32c(gy)
     g = conv_geom(x.shape, w_shape, stride, padding)
-    trio, layer = _tc_route(x.shape, w_shape, stride, padding, x.device)
+    trio, layer = _tc_route(x.shape, w_shape, stride, padding, x.device, 'wgrad')
     if trio is not None and x.shape[0] > 0:
         gw = trio.wgrad(layer, x, gy)
         return (gw, gy.sum(dim=(0, 2, 3, 4))) if want_bias else gw
