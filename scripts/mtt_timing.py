@@ -10,6 +10,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from video_distillation_b200.distill import MTTS2DTrainer  # noqa: E402
 from video_distillation_b200.networks import ConvNet3D  # noqa: E402
 
+world, rank = int(os.environ.get('WORLD_SIZE', '1')), int(os.environ.get('RANK', '0'))
+if world > 1:                                   # torchrun: every inner step's 50 videos are sharded over the ranks
+    import torch.distributed as dist
+    torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
+    dist.init_process_group('nccl', device_id=torch.device('cuda', int(os.environ.get('LOCAL_RANK', '0'))))
 C, T, HW = 50, 16, 112
 syn_steps = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 precision = sys.argv[2] if len(sys.argv) > 2 else 'bf16'
@@ -18,10 +23,13 @@ tr = MTTS2DTrainer(num_classes=C, im_size=(HW, HW), frames=T, vpc=1, spc=2, dpc=
 base = ConvNet3D(3, C, 128, 3, 'relu', 'none', 'maxpooling', T, (HW, HW))
 start = [p.detach().clone() for p in base.parameters()]
 target = [p.detach().clone() + 0.01 * torch.randn_like(p) for p in base.parameters()]
-for i in range(2):
+for i in range(3):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     loss = tr.step(start, target, net_seed=1)
     torch.cuda.synchronize()
-    print(f'MTT iteration {i} [{precision}]: syn_steps={syn_steps} batch_syn={C} -> {time.perf_counter() - t0:.3f} s, grand loss {loss.item():.6f}, '
-          f'peak mem {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB', flush=True)
+    if rank == 0:
+        print(f'MTT iteration {i} [{precision}]: syn_steps={syn_steps} batch_syn={C} -> {time.perf_counter() - t0:.3f} s, grand loss {loss.item():.6f}, '
+              f'world {world}, peak mem {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB', flush=True)
+if world > 1:
+    dist.destroy_process_group()

@@ -82,3 +82,78 @@ def test_class_sharded_dm_equals_single_rank(tmp_path):
     assert rel(got[0], r['grad_dynamic']) < 1e-5
     assert rel(got[1], r['grad_hal_weight']) < 1e-5 and rel(got[2], r['grad_hal_bias']) < 1e-5
     assert rel(got[3], r['loss'].reshape(1)) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------ MTT batch sharding
+def _mtt_case():
+    C, T, H, vpc, spc, dpc, steps = 4, 8, 64, 1, 2, 2, 2
+    like = synth.synth_convnet3d_params(80, num_classes=C)
+    theta0 = oracle.flatten_params(like)
+    target = theta0 + synth.hash_uniform(tuple(theta0.shape), 901, 2.0 ** -10)
+    static_syn = synth.hash_uniform((C * spc, 3, H, H), 71)
+    dyn = synth.hash_uniform((C, dpc, T, 1, H, H), 72)
+    hal = synth.synth_hallucinator(7)
+    gen = torch.Generator().manual_seed(3)
+    perms = [torch.randperm(C * vpc, generator=gen) for _ in range(steps)]
+    cds = [torch.randint(2, (C * vpc,), generator=gen) for _ in range(steps)]
+    css = [torch.randint(2, (C * vpc,), generator=gen) for _ in range(steps)]
+    return dict(C=C, T=T, H=H, vpc=vpc, spc=spc, like=like, theta0=theta0, target=target, static_syn=static_syn, dyn=dyn,
+                hal=hal, perms=perms, cds=cds, css=css, syn_lr=torch.tensor(0.01))
+
+
+def _mtt_worker(rank, world, port, out):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    import torch.nn.functional as F
+    from oracle.mtt import mtt_sample_step_indices
+    from video_distillation_b200.distill import allreduce_sum_, sharded_inner_grad
+    k = _mtt_case()
+    dyn = k['dyn'].clone().requires_grad_(True)
+    w = k['hal']['encoder.weight'].clone().requires_grad_(True)
+    b = k['hal']['encoder.bias'].clone().requires_grad_(True)
+    syn_lr = k['syn_lr'].clone().requires_grad_(True)
+    student = [k['theta0'].clone().requires_grad_(True)]
+    for perm, cd, cs in zip(k['perms'], k['cds'], k['css']):
+        label, idx, didx, sidx = mtt_sample_step_indices(perm, k['vpc'], k['spc'], cd, cs)
+        sl = slice(rank, None, world)
+        n_step = perm.numel()
+
+        def shard_loss(theta, label=label, didx=didx, sidx=sidx, sl=sl, n_step=n_step):
+            x = oracle.compose(k['static_syn'][sidx[sl]], dyn[label[sl], didx[sl]], w, b)
+            logits = oracle.convnet3d_forward(oracle.unflatten_params(theta, k['like']), x, (k['H'], k['H']),
+                                              dropout_mask=torch.ones(1))
+            return F.cross_entropy(logits, label[sl].long(), reduction='sum') / n_step
+        grad = sharded_inner_grad(student[-1], shard_loss, world)
+        student.append(student[-1] - syn_lr * grad)
+    n = k['theta0'].numel()
+    grand = (F.mse_loss(student[-1], k['target'], reduction='sum') / n) / (F.mse_loss(k['theta0'], k['target'], reduction='sum') / n)
+    grand.backward()
+    grads = [dyn.grad, w.grad, b.grad]
+    allreduce_sum_(grads)
+    if rank == 0:
+        torch.save([g.clone() for g in grads] + [syn_lr.grad.clone(), grand.detach().clone()], out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_batch_sharded_mtt_equals_single_rank(tmp_path):
+    """The product's differentiable collectives (sharded_inner_grad: _ReplicatedInput / _SumAcrossRanks) around the
+    oracle student: 2 ranks, each holding half of every inner step's batch, reproduce the single-rank unroll and
+    its second-order gradients."""
+    out = str(tmp_path / 'mtt_r0.pt')
+    mp.spawn(_mtt_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = torch.load(out)
+    k = _mtt_case()
+    masks = [torch.ones(1) for _ in k['perms']]
+    r = oracle.mtt_s2d_iteration(k['theta0'], k['target'], k['like'], k['static_syn'], k['dyn'], k['hal'], k['syn_lr'],
+                                 vpc=k['vpc'], spc=k['spc'], perms=k['perms'], coins_dynamic=k['cds'], coins_static=k['css'],
+                                 dropout_masks=masks, im_size=(k['H'], k['H']))
+
+    def rel(a, b):
+        return ((a.double() - b.double()).norm() / (b.double().norm() + 1e-30)).item()
+    assert rel(got[4], r['grand_loss']) < 1e-6
+    assert rel(got[0], r['grad_dynamic']) < 1e-4, rel(got[0], r['grad_dynamic'])
+    assert rel(got[1], r['grad_hal_weight']) < 1e-4 and rel(got[2], r['grad_hal_bias']) < 1e-4
+    assert rel(got[3], r['grad_syn_lr']) < 1e-4

@@ -102,6 +102,25 @@ def test_dm_baseline_golden():
         check_summary(tr.image_syn, gold[f'syn_sums{it}'], gold[f'syn_sample{it}'], tol=1e-5)
 
 
+def test_dm_baseline_bf16_tensor_core_path():
+    """DM baseline (distill_baseline.py:334-356) with real AND synthetic embeds on tensor cores vs the exact path."""
+    from oracle import synth
+    from video_distillation_b200.distill import DeviceDataset, DMBaselineTrainer
+    C, per, T, H, ipc, batch_real = 3, 4, 8, 64, 2, 3
+    videos, labels = real_set(C, per, T, H, 31)
+    out = {}
+    for prec in ('fp32', 'bf16'):
+        ds = DeviceDataset(videos, labels, C, 'cuda')
+        tr = DMBaselineTrainer(ds, num_classes=C, im_size=(H, H), frames=T, ipc=ipc, batch_real=batch_real, lr_img=0.5,
+                               precision=prec, image_syn=synth.hash_uniform((C * ipc, T, 3, H, H), 32))
+        np.random.seed(7)
+        net = net_from(synth.synth_convnet3d_params(40, num_classes=C), C, T, H)
+        loss = tr.step(net=net)
+        out[prec] = (loss.item(), tr.image_syn.grad.clone())
+    assert abs(out['bf16'][0] - out['fp32'][0]) < 2e-2 * abs(out['fp32'][0]) + 1e-6
+    assert rel(out['bf16'][1], out['fp32'][1]) < 1e-1, rel(out['bf16'][1], out['fp32'][1])
+
+
 @pytest.mark.parametrize('tag,vpc,spc,dpc', [('v1', 1, 2, 2), ('v2', 2, 4, 4)])
 def test_dm_s2d_golden(tag, vpc, spc, dpc):
     from oracle import synth, s2d_sample_indices

@@ -56,6 +56,46 @@ def allreduce_sum_(tensors):
     return tensors
 
 
+class _SumAcrossRanks(torch.autograd.Function):
+    """y = sum over ranks of x_r (all-reduce).  y feeds a computation that every rank replicates, so the
+    cotangent that arrives on a rank is already the complete one: backward is the identity."""
+    @staticmethod
+    def forward(ctx, x):
+        y = x.clone()
+        dist.all_reduce(y, op=dist.ReduceOp.SUM)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+class _ReplicatedInput(torch.autograd.Function):
+    """Identity on a replicated tensor (the student parameters theta_k) that enters rank-local work (the rank's
+    shard of the step batch).  Every rank produces only its shard's part of d/d theta_k, so the backward sums the
+    cotangents over ranks (all-reduce): the complete cotangent continues into the earlier unroll steps."""
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous().clone()
+        dist.all_reduce(g, op=dist.ReduceOp.SUM)
+        return g
+
+
+def sharded_inner_grad(theta, shard_loss_fn, world):
+    """grad_theta of the FULL step loss when each rank evaluates only its shard:
+    ``shard_loss_fn(theta_local)`` must return sum_{i in shard} loss_i / B_total (0-dim, built on theta_local).
+    Returns the all-reduced gradient, differentiable to second order across ranks (MTT row)."""
+    if world == 1:
+        return torch.autograd.grad(shard_loss_fn(theta), theta, create_graph=True)[0]
+    theta_local = _ReplicatedInput.apply(theta)
+    g_local = torch.autograd.grad(shard_loss_fn(theta_local), theta_local, create_graph=True)[0]
+    return _SumAcrossRanks.apply(g_local)
+
+
 class DeviceDataset:
     """Real videos of this rank's classes, resident on the device.
 
@@ -382,7 +422,10 @@ class DMBaselineTrainer:
         D = emb_real.shape[1]
         mean_real = ops.class_mean(emb_real.view(n_own, self.batch_real, D))
         img = self.image_syn[rows] if self.world > 1 else self.image_syn
-        emb_syn = net.embed(img).view(n_own, ipc, D)
+        if self.embedder.tc is not None:
+            emb_syn = self.embedder.tc.embed_autograd(img).view(n_own, ipc, D)       # tensor cores, like the real branch
+        else:
+            emb_syn = net.embed(img).view(n_own, ipc, D)
         loss = ops.dm_loss(mean_real, emb_syn)
         self.image_syn.grad = None
         loss.backward()
@@ -414,6 +457,7 @@ class MTTS2DTrainer:
         self.lr = dict(dynamic=lr_dynamic, hal=lr_hal, static=lr_static, lr=lr_lr)
         self.train_static, self.train_lr = train_static, train_lr
         self.batch_syn = batch_syn if batch_syn is not None else num_classes * vpc
+        self.rank, self.world = _world()          # world > 1: every inner step's batch is sharded i % world == rank
         self.device = torch.device(device)
         H, W = self.im_size
         if static_syn is None:
@@ -471,10 +515,15 @@ class MTTS2DTrainer:
             idx = these % vpc
             dynamic_idx = 2 * idx + torch.randint(2, (these.shape[0],), device=dev)
             static_idx = spc * label + 2 * idx + torch.randint(2, (these.shape[0],), device=dev)
-            x = self.hal.compose(self.static_syn, self.dynamic_syn, static_idx, label, dynamic_idx)
-            out = student_net(x, flat_param=student_params[-1])
-            ce = self.criterion(out, label.long())
-            grad = torch.autograd.grad(ce, student_params[-1], create_graph=True)[0]
+            n_step = int(these.shape[0])
+            sl = slice(self.rank, None, self.world)               # this rank's videos of the step batch (all for 1 rank)
+
+            def shard_loss(theta, label=label, dynamic_idx=dynamic_idx, static_idx=static_idx, sl=sl, n_step=n_step):
+                x = self.hal.compose(self.static_syn, self.dynamic_syn, static_idx[sl], label[sl], dynamic_idx[sl])
+                out = student_net(x, flat_param=theta)
+                # CrossEntropyLoss() is the batch mean (distill_s2d_ms.py:262): the shard contributes sum / B
+                return torch.nn.functional.cross_entropy(out, label[sl].long(), reduction='sum') / n_step
+            grad = sharded_inner_grad(student_params[-1], shard_loss, self.world)
             student_params.append(student_params[-1] - self.syn_lr * grad)
             draws.append((these, dynamic_idx, static_idx))
         param_loss = torch.nn.functional.mse_loss(student_params[-1], target, reduction='sum') / num_params
@@ -483,6 +532,12 @@ class MTTS2DTrainer:
         for p in (self.dynamic_syn, self.static_syn, self.syn_lr, *self.hal.parameters()):
             p.grad = None
         grand_loss.backward()
+        if self.world > 1:
+            # the grand loss is replicated; each rank holds the gradient that flowed through ITS shard of every step
+            grads = [self.dynamic_syn.grad, self.hal.encoder.weight.grad, self.hal.encoder.bias.grad]
+            if self.train_static:
+                grads.append(self.static_syn.grad)
+            allreduce_sum_(grads)
         if self.train_static:
             self._sgd('static', self.static_syn, self.lr['static'], 0.95)
         self._sgd('dynamic', self.dynamic_syn, self.lr['dynamic'], 0.95)
