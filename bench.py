@@ -228,7 +228,8 @@ def run_ours(args):
     torch.manual_seed(0)
     tr = DMS2DTrainer(ds, num_classes=C, im_size=(HW, HW), frames=T, vpc=VPC, spc=SPC, dpc=DPC, batch_real=BATCH_REAL,
                       lr_dynamic=1e4, lr_hal=1e-2, precision=args.precision, device=dev, init_on_device=True,
-                      max_batch=args.max_batch)
+                      max_batch=args.max_batch,
+                      syn_on_tensor_cores={'fused': True, 'split': 'split', 'fp32': False}[args.syn_mode])
     if tr.embedder.tc is not None and not args.no_prepack:
         ds.prepack(tr.embedder.tc, extra_slots=len(tr.owned) * tr.vpc)          # one-time dataset conversion (outside the timed region, like --preload)
     np.random.seed(0)
@@ -378,6 +379,7 @@ def run_ours(args):
                    'real_videos_per_step': C * BATCH_REAL, 'syn_videos_per_step': C * VPC,
                    'l2_policy': 'inputs larger than L2: each step reads 3200 distinct real videos (7.7 GB fp32)',
                    'real_embed': 'tcgen05 bf16 operands / fp32 accumulate' if args.precision == 'bf16' else 'fp32 CUDA cores',
+                   'syn_branch': args.syn_mode,
                    'real_set': 'resident fp32' + ('' if args.no_prepack else ' + pre-packed bf16 conv-0 operand (one-time)'),
                    'videos_per_sec': value * C * (BATCH_REAL + VPC)},
         'clocks': clocks, 'gpu_launches': int(launches),
@@ -402,6 +404,9 @@ def main():
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--max-batch', type=int, default=640)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--syn-mode', default='fused', choices=['fused', 'split', 'fp32'],
+                    help='synthetic branch: fused bf16 tensor-core pipeline (throughput), split-bf16 trio with fp32 '
+                         'activations (gradients within 1e-2 of fp32), or the exact fp32 CUDA-core kernels')
     ap.add_argument('--no-prepack', action='store_true', help='pack the sampled real videos every step instead of once')
     args = ap.parse_args()
     if args.impl == 'reference':

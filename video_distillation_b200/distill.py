@@ -276,8 +276,12 @@ class DMS2DTrainer:
         self.init_on_device = init_on_device
         self._pool = None
         self._const = None
-        # precision='bf16': synthetic branch forward + backward also on tensor cores (bf16 operands);
-        # set False to keep the synthetic branch on the exact fp32 kernels (mixed mode).
+        # precision='bf16', synthetic branch:
+        #   True    fused tensor-core pipeline (bf16 operands AND bf16 activations between layers; throughput mode —
+        #           ReLU / pool routing can flip against fp32, ~1e-1 relL2 on the synthetic-video gradient)
+        #   'split' tensor-core conv trio with split-bf16 fprop and fp32 activations (routing identical to fp32 up to
+        #           ~1e-5, gradients ~1e-2), unfused: a few ms per 50 videos
+        #   False   exact fp32 CUDA-core kernels (slow)
         self.syn_on_tensor_cores = syn_on_tensor_cores
         self.C, self.channel, self.im_size, self.frames = num_classes, channel, tuple(im_size), frames
         self.vpc, self.spc, self.dpc, self.batch_real = vpc, spc, dpc, batch_real
@@ -325,6 +329,15 @@ class DMS2DTrainer:
         """One DM iteration; returns the loss (0-dim device tensor, summed over ALL classes).
         ``real_batch``: optional device tensor holding this rank's sampled real videos already gathered
         (class-major, batch_real per owned class) — the host-streaming mode of bench.py."""
+        if self.embedder.tc is not None and self.syn_on_tensor_cores == 'split':
+            prev = ops.set_conv_backend('tc')             # forward AND backward of net.embed(image_syn) below
+            try:
+                return self._step(net, net_seed, indices, real_idx, real_batch)
+            finally:
+                ops.set_conv_backend(prev)
+        return self._step(net, net_seed, indices, real_idx, real_batch)
+
+    def _step(self, net=None, net_seed=None, indices=None, real_idx=None, real_batch=None):
         C, vpc = self.C, self.vpc
         if net is None:
             if self.init_on_device:
@@ -343,7 +356,8 @@ class DMS2DTrainer:
         sel = (self.owned_t[:, None] * vpc + torch.arange(vpc, device=self.device)[None, :]).reshape(-1)
         image_syn = self.hal.compose(self.static_syn, self.dynamic_syn, static_idx[sel], label[sel], dynamic_idx[sel])
         tc = self.embedder.tc
-        joint = (tc is not None and self.syn_on_tensor_cores and real_batch is None and self.ds.x0 is not None
+        fused_syn = tc is not None and self.syn_on_tensor_cores is True
+        joint = (fused_syn and real_batch is None and self.ds.x0 is not None
                  and getattr(self.ds, 'x0_extra', 0) >= image_syn.shape[0])
         if joint:
             # real + synthetic videos in the same three conv launches (codes only for the synthetic tail)
@@ -359,7 +373,7 @@ class DMS2DTrainer:
         mean_real = ops.class_mean(emb_real.view(n_own, self.batch_real, D))
         if joint:
             emb_syn = emb_syn.view(n_own, vpc, D)
-        elif tc is not None and self.syn_on_tensor_cores:
+        elif fused_syn:
             emb_syn = tc.embed_autograd(image_syn).view(n_own, vpc, D)
         else:
             emb_syn = net.embed(image_syn).view(n_own, vpc, D)
