@@ -167,9 +167,9 @@ def memory_kernel_rooflines(step_fn, tr, steps=3):
     thw, hw = T * HW * HW, HW * HW
     p = tr.embedder.tc.plan
     rows = [  # (kernel-name substring, algorithmic bytes per launch, what)
-        ('compose_fwd_kernel', n_syn * 4 * (3 * hw + thw + 3 * thw), 'read static+dynamic, write video'),
-        ('compose_bwd_data_kernel', n_syn * 4 * (3 * thw + thw), 'read d video, write d dynamic'),
-        ('compose_bwd_weight_dyn_kernel', n_syn * 4 * (3 * thw + thw), 'read d video + dynamic'),
+        ('compose_fwd_tiled_kernel', n_syn * 4 * (3 * hw + thw + 3 * thw), 'read static+dynamic, write video'),
+        ('compose_bwd_data_tiled_kernel', n_syn * 4 * (3 * thw + thw), 'read d video, write d dynamic'),
+        ('compose_bwd_wdyn_tiled_kernel', n_syn * 4 * (3 * thw + thw), 'read d video + dynamic'),
         ('compose_bwd_weight_static_kernel', n_syn * 4 * (3 * thw + 3 * hw), 'read d video + static'),
         ('col2im_rows_kernel<7, 8>', n_syn * (p.col0_bytes_per_video + 4 * 3 * thw), 'read conv-0 columns, write d video'),
         ('col2im_rows_kernel<7, 4>', n_syn * (p.col1_bytes_per_video + p.dy0_bytes_per_video + 64 * T * 28 * 28), 'read conv-1 columns + codes, write dY0'),

@@ -227,6 +227,36 @@ def test_dm_s2d_bf16_tensor_core_real_path():
     assert abs(losses['bf16'][0] - losses['fp32'][0]) < 2e-2 * abs(losses['fp32'][0]) + 1e-6
 
 
+def test_dm_s2d_bf16x3_parity_mode_on_tensor_cores():
+    """precision='bf16x3': real and synthetic embeds on the tensor-core trio with split-bf16 fprop and fp32
+    activations, against the exact fp32 path: loss / embeddings within 1e-4, gradients within 1e-2."""
+    import oracle
+    from oracle import synth
+    from video_distillation_b200.distill import DeviceDataset, DMS2DTrainer
+    from video_distillation_b200.utils import Conv3DNet
+    C, per, T, H, batch_real = 3, 4, 8, 64, 3
+    videos, labels = real_set(C, per, T, H, 51)
+    ds = DeviceDataset(videos, labels, C, 'cuda')
+    res = {}
+    for prec in ('fp32', 'bf16x3'):
+        hal = Conv3DNet()
+        hal.load_state_dict(synth.synth_hallucinator(5))
+        tr = DMS2DTrainer(ds, num_classes=C, im_size=(H, H), frames=T, vpc=1, spc=2, dpc=2, batch_real=batch_real,
+                          lr_dynamic=10.0, lr_hal=0.01, precision=prec, hal=hal,
+                          static_syn=synth.hash_uniform((C * 2, 3, H, H), 52),
+                          dynamic_syn=synth.hash_uniform((C, 2, T, 1, H, H), 53))
+        np.random.seed(9)
+        net = net_from(synth.synth_convnet3d_params(60, num_classes=C), C, T, H)
+        label, _, didx, sidx = oracle.s2d_sample_indices(C, 1, 2, torch.tensor([0, 1, 1]), torch.tensor([1, 0, 1]))
+        loss = tr.step(net=net, indices=(label.cuda(), didx.cuda(), sidx.cuda()))
+        res[prec] = (loss.item(), tr.last['mean_real'].clone(), tr.dynamic_syn.grad.clone(), tr.hal.encoder.weight.grad.clone())
+    a, b = res['bf16x3'], res['fp32']
+    errs = (abs(a[0] - b[0]) / abs(b[0]), rel(a[1], b[1]), rel(a[2], b[2]), rel(a[3], b[3]))
+    print('bf16x3 vs fp32 (loss, real class means, dynamic-memory grad, hallucinator grad):', errs)
+    assert errs[0] < 1e-4 and errs[1] < 1e-4, errs
+    assert errs[2] < 1e-2 and errs[3] < 1e-2, errs
+
+
 @pytest.mark.parametrize('precision', ['fp32', 'bf16'])
 def test_mtt_s2d_golden(precision):
     """Unrolled student with second-order autograd through our conv trio vs the reference: exact fp32 kernels,

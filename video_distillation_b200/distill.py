@@ -165,9 +165,26 @@ class DeviceDataset:
         loc = self.local_of_global[np.asarray(global_idx).reshape(-1)]
         assert (loc >= 0).all(), 'requested a video of a class this rank does not own'
         t = torch.from_numpy(np.ascontiguousarray(loc))
-        if self.device.type == 'cuda':
-            t = t.pin_memory()
-        return t.to(self.device, non_blocking=True)
+        if self.device.type != 'cuda':
+            return t.to(self.device)
+        # ring of reusable pinned staging buffers: a fresh pin_memory() per call is a cudaHostAlloc, which
+        # synchronises the device (0.5 ms idle per iteration in the timeline); 8 slots keep in-flight copies apart
+        ring = getattr(self, '_pin_ring', None)
+        if ring is None or ring[0].numel() < t.numel():
+            ring = self._pin_ring = [torch.empty(max(t.numel(), 1), dtype=torch.int64).pin_memory() for _ in range(8)]
+            self._pin_done = [None] * len(ring)
+            self._pin_next = 0
+        slot = self._pin_next % len(ring)
+        self._pin_next += 1
+        if self._pin_done[slot] is not None:
+            self._pin_done[slot].synchronize()            # the copy that last read this slot (8 calls ago) has finished
+        buf = ring[slot][:t.numel()]
+        buf.copy_(t)
+        out = buf.to(self.device, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._pin_done[slot] = ev
+        return out
 
     def get_images(self, c, n):
         """Reference-compatible accessor (one class)."""
@@ -243,8 +260,8 @@ class _RealEmbedder:
             if not tc_supported(frames, im_size[0], im_size[1]):
                 raise RuntimeError(f'tensor-core path does not support videos {frames}x{im_size}')
             self.tc = TcConvNet3D(frames, im_size[0], im_size[1], device, max_batch=max_batch)
-        elif precision != 'fp32':
-            raise ValueError("precision must be 'bf16' or 'fp32'")
+        elif precision not in ('fp32', 'bf16x3'):
+            raise ValueError("precision must be 'bf16', 'bf16x3' or 'fp32'")
 
     def load(self, net):
         self.net = net
@@ -258,9 +275,12 @@ class _RealEmbedder:
             if x0 is not None:
                 return self.tc.embed_resident(x0, index)
             return self.tc.embed(videos, index=index)
+        # 'fp32': exact CUDA-core kernels.  'bf16x3': the same module on the tensor-core conv trio with split-bf16
+        # fprop and fp32 activations (embeddings ~1e-5 of fp32) — the caller holds ops.set_conv_backend('tc').
         out = []
-        for s in range(0, index.numel(), self.max_batch):
-            out.append(self.net.embed(videos[index[s:s + self.max_batch]]))
+        chunk = min(self.max_batch, 64) if self.precision == 'bf16x3' else self.max_batch
+        for s in range(0, index.numel(), chunk):
+            out.append(self.net.embed(videos[index[s:s + chunk]]))
         return torch.cat(out, 0)
 
 
@@ -329,8 +349,8 @@ class DMS2DTrainer:
         """One DM iteration; returns the loss (0-dim device tensor, summed over ALL classes).
         ``real_batch``: optional device tensor holding this rank's sampled real videos already gathered
         (class-major, batch_real per owned class) — the host-streaming mode of bench.py."""
-        if self.embedder.tc is not None and self.syn_on_tensor_cores == 'split':
-            prev = ops.set_conv_backend('tc')             # forward AND backward of net.embed(image_syn) below
+        if (self.embedder.tc is not None and self.syn_on_tensor_cores == 'split') or self.embedder.precision == 'bf16x3':
+            prev = ops.set_conv_backend('tc')             # forward AND backward of net.embed(...) below
             try:
                 return self._step(net, net_seed, indices, real_idx, real_batch)
             finally:

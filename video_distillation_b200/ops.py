@@ -49,6 +49,7 @@ def set_conv_backend(name):
 
 
 _TC_FPROP_SPLIT = __import__('os').environ.get('VD_TC_FPROP_SPLIT', '1') != '0'
+_TC_DGRAD_SPLIT = __import__('os').environ.get('VD_TC_DGRAD_SPLIT', '0') != '0'
 _TC_OPS = set(__import__('os').environ.get('VD_TC_OPS', 'fprop,dgrad,wgrad').split(','))     # experiment knob
 
 
@@ -91,6 +92,13 @@ def conv3d_dgrad_raw(gy, w, x_shape, stride, padding):
     assert tuple(gy.shape) == (g.N, g.Cout, g.To, g.Ho, g.Wo), (tuple(gy.shape), (g.N, g.Cout, g.To, g.Ho, g.Wo))
     trio, layer = _tc_route(x_shape, w.shape, stride, padding, gy.device, 'dgrad')
     if trio is not None and gy.shape[0] > 0:
+        if _TC_DGRAD_SPLIT:                               # same split as fprop: gy = gh + gl, w = wh + wl
+            gh = gy.to(torch.bfloat16).float()
+            wh = w.to(torch.bfloat16).float()
+            gx = trio.dgrad(layer, gh, wh)
+            gx += trio.dgrad(layer, gh, w - wh)
+            gx += trio.dgrad(layer, gy - gh, wh)
+            return gx
         return trio.dgrad(layer, gy, w)
     gx = torch.empty(tuple(x_shape), dtype=torch.float32, device=gy.device)
     if gx.numel():

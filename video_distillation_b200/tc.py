@@ -167,6 +167,8 @@ class TcConvNet3D:
         (optional) hold the routing of items code_first..B-1 only."""
         p = self.plan
         step = max(4, self.max_batch // 4 * 4)              # conv-2 tiles hold 4 consecutive videos
+        n_chunks = (B + step - 1) // step
+        step = min(step, ((B + n_chunks - 1) // n_chunks + 3) // 4 * 4)      # equal chunks: no small, wave-inefficient tail
         a1, a2 = self._buffers(min(B, step), B)
         c0, c1, c2 = codes if codes is not None else (None, None, None)
         for s in range(0, B, step):
