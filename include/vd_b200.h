@@ -185,7 +185,7 @@ int vd_tc_pack_weights(const float* w_l0, const float* w_l1, const float* w_l2,
  * of `in`.  raw == 1 (bring-up / tests): skip the fused epilogue and dump the fp32
  * accumulators to out as [tile][acc][128][ncols].  raw == 2: plain convolution, out = fp32 NCDHW
  * (B, Cout, To, Ho, Wo) pre-activation (+ bias when non-NULL) — F.conv3d of networks.py:799 as used by the
- * differentiable conv trio. */
+ * differentiable conv trio; raw == 3: the same, accumulated into out (out += result). */
 int vd_tc_conv_layer(int layer, const void* in, const void* wimg, const float* bias,
                      void* out, uint8_t* code, int code_first_item, const vd_tc_plan* plan,
                      const int64_t* item_index, int B, int raw, void* stream);
@@ -219,7 +219,11 @@ int vd_tc_bwd_col2im(int layer, const void* col, const uint8_t* code_below, void
  *   dgrad(gy, w)  : vd_tc_pack_dy, vd_tc_pack_weights_bwd, vd_tc_bwd_gemm, vd_tc_bwd_col2im_plain -> gx NCDHW
  *   wgrad(x, gy)  : vd_tc_wgrad_plan (workspace sizes), vd_tc_wgrad_pack (im2col columns + gy image),
  *                   vd_tc_wgrad_gemm (split-K partial sums), vd_tc_wgrad_reduce -> gw (Cout, Cin, 3, 7, 7)   */
-int vd_tc_pack_act(int layer, const float* x, void* packed, const vd_tc_plan* plan, int B, void* stream);
+int vd_tc_pack_act(int layer, const float* x, void* packed, const vd_tc_plan* plan, int B, int part, void* stream);
+/* part = 0: the value, 1: its bf16 residual v - bf16(v) (operands of the split-bf16 fprop) */
+int vd_tc_pack_video_ncdhw(const float* x, void* x0, const vd_tc_plan* plan, int B, int part, void* stream);
+int vd_tc_pack_weights_part(const float* w_l0, const float* w_l1, const float* w_l2, void* w0, void* w1, void* w2,
+                            int part, void* stream);
 int vd_tc_pack_dy(int layer, const float* gy, void* dy, const vd_tc_plan* plan, int B, void* stream);
 int vd_tc_bwd_col2im_plain(int layer, const void* col, float* gx, const vd_tc_plan* plan, int B, void* stream);
 /* out[0] split-K slices, out[1] stages per slice, out[2] column tiles, out[3] xcol bytes, out[4] gyimg bytes, out[5] raw bytes */

@@ -15,6 +15,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument('--classes', type=int, default=50)
 ap.add_argument('--max-batch', type=int, default=640)
 ap.add_argument('--steps', type=int, default=3)
+ap.add_argument('--syn-mode', default='fused', choices=['fused', 'split', 'fp32'])
 args = ap.parse_args()
 C, T, HW, PER = args.classes, 16, 112, 72
 dev = torch.device('cuda', 0)
@@ -23,7 +24,8 @@ vids = torch.randn(C * PER, T, 3, HW, HW, device=dev)
 ds = DeviceDataset.from_device_shard(vids, labels, C, dev, 0, 1)
 torch.manual_seed(0)
 tr = DMS2DTrainer(ds, num_classes=C, im_size=(HW, HW), frames=T, vpc=1, spc=2, dpc=2, batch_real=64, precision='bf16',
-                  device=dev, init_on_device=True, max_batch=args.max_batch)
+                  device=dev, init_on_device=True, max_batch=args.max_batch,
+                  syn_on_tensor_cores={'fused': True, 'split': 'split', 'fp32': False}[args.syn_mode])
 ds.prepack(tr.embedder.tc, extra_slots=len(tr.owned) * tr.vpc)
 np.random.seed(0)
 for i in range(3):

@@ -14,7 +14,9 @@ def declare(lib):
         'vd_tc_bwd_emb': (c_int, [P, P, P, POINTER(TcPlan), c_int, P]),
         'vd_tc_bwd_gemm': (c_int, [c_int, P, P, P, POINTER(TcPlan), c_int, P]),
         'vd_tc_bwd_col2im': (c_int, [c_int, P, P, P, POINTER(TcPlan), c_int, P]),
-        'vd_tc_pack_act': (c_int, [c_int, P, P, POINTER(TcPlan), c_int, P]),
+        'vd_tc_pack_act': (c_int, [c_int, P, P, POINTER(TcPlan), c_int, c_int, P]),
+        'vd_tc_pack_video_ncdhw': (c_int, [P, P, POINTER(TcPlan), c_int, c_int, P]),
+        'vd_tc_pack_weights_part': (c_int, [P, P, P, P, P, P, c_int, P]),
         'vd_tc_pack_dy': (c_int, [c_int, P, P, POINTER(TcPlan), c_int, P]),
         'vd_tc_bwd_col2im_plain': (c_int, [c_int, P, P, POINTER(TcPlan), c_int, P]),
         'vd_tc_wgrad_plan': (c_int, [c_int, POINTER(TcPlan), c_int, POINTER(c_int64)]),

@@ -34,6 +34,7 @@ struct EpiParams {
     uint8_t* code;         // optional ReLU/argmax routing codes, NCDHW order of the pooled tensor
     int code_first;        // items below this index record no codes (frozen real videos ahead of synthetic ones)
     int layer;             // EPI_PLAIN: which conv (tile -> NCDHW mapping)
+    int accum;             // EPI_PLAIN: out += result (split-bf16 passes accumulate into the same fp32 tensor)
     int T;                 // frames of the video
     int n_items;           // videos (conv 2: valid videos, tiles may be partially filled)
     Geo g;
@@ -357,8 +358,14 @@ __device__ __forceinline__ void epi_plain(const WsParams& p, int tile, uint32_t 
                 float v[8];
                 tmem_ld8(taddr + r * g.Wo0 + wb, v);
                 tmem_ld_wait();
-                *reinterpret_cast<float4*>(dst + wb) = make_float4(v[0] + bias, v[1] + bias, v[2] + bias, v[3] + bias);
-                *reinterpret_cast<float4*>(dst + wb + 4) = make_float4(v[4] + bias, v[5] + bias, v[6] + bias, v[7] + bias);
+                float4 lo = make_float4(v[0] + bias, v[1] + bias, v[2] + bias, v[3] + bias);
+                float4 hi = make_float4(v[4] + bias, v[5] + bias, v[6] + bias, v[7] + bias);
+                if (p.epi.accum) {
+                    const float4 a = *reinterpret_cast<const float4*>(dst + wb), b = *reinterpret_cast<const float4*>(dst + wb + 4);
+                    lo.x += a.x; lo.y += a.y; lo.z += a.z; lo.w += a.w; hi.x += b.x; hi.y += b.y; hi.z += b.z; hi.w += b.w;
+                }
+                *reinterpret_cast<float4*>(dst + wb) = lo;
+                *reinterpret_cast<float4*>(dst + wb + 4) = hi;
             }
         }
     } else if (p.epi.layer == 1) {
@@ -372,7 +379,12 @@ __device__ __forceinline__ void epi_plain(const WsParams& p, int tile, uint32_t 
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 16; j += 2)
-                    if (j < g.Wo1) *reinterpret_cast<float2*>(dst + ho * g.Wo1 + j) = make_float2(v[j] + bias, v[j + 1] + bias);
+                    if (j < g.Wo1) {
+                        float2 o = make_float2(v[j] + bias, v[j + 1] + bias);
+                        float2* d2 = reinterpret_cast<float2*>(dst + ho * g.Wo1 + j);
+                        if (p.epi.accum) { const float2 a = *d2; o.x += a.x; o.y += a.y; }
+                        *d2 = o;
+                    }
             }
         }
     } else {
@@ -385,8 +397,14 @@ __device__ __forceinline__ void epi_plain(const WsParams& p, int tile, uint32_t 
                 float v[8];
                 tmem_ld8(taddr + a * p.acc_cols + c, v);
                 tmem_ld_wait();
-                *reinterpret_cast<float4*>(dst + c) = make_float4(v[0] + bias, v[1] + bias, v[2] + bias, v[3] + bias);
-                *reinterpret_cast<float4*>(dst + c + 4) = make_float4(v[4] + bias, v[5] + bias, v[6] + bias, v[7] + bias);
+                float4 lo = make_float4(v[0] + bias, v[1] + bias, v[2] + bias, v[3] + bias);
+                float4 hi = make_float4(v[4] + bias, v[5] + bias, v[6] + bias, v[7] + bias);
+                if (p.epi.accum) {
+                    const float4 a4 = *reinterpret_cast<const float4*>(dst + c), b4 = *reinterpret_cast<const float4*>(dst + c + 4);
+                    lo.x += a4.x; lo.y += a4.y; lo.z += a4.z; lo.w += a4.w; hi.x += b4.x; hi.y += b4.y; hi.z += b4.z; hi.w += b4.w;
+                }
+                *reinterpret_cast<float4*>(dst + c) = lo;
+                *reinterpret_cast<float4*>(dst + c + 4) = hi;
             }
         }
     }
@@ -846,7 +864,7 @@ extern "C" int vd_tc_conv_layer(int layer, const void* in, const void* wimg, con
     VD_REQUIRE(code_first_item >= 0, "tc_conv_layer: negative code_first_item");
     VD_REQUIRE(geo_supported(plan->T, plan->H), "tc_conv_layer: unsupported geometry");
     VD_REQUIRE(raw || bias, "tc_conv_layer: bias is NULL");
-    VD_REQUIRE(raw >= 0 && raw <= 2, "tc_conv_layer: raw must be 0 (fused), 1 (accumulator dump) or 2 (plain NCDHW fp32)");
+    VD_REQUIRE(raw >= 0 && raw <= 3, "tc_conv_layer: raw must be 0 (fused), 1 (accumulator dump), 2 (plain NCDHW fp32) or 3 (plain, out += result)");
     if (B == 0) return 0;
     WsParams p;
     memset(&p, 0, sizeof(p));
@@ -861,7 +879,8 @@ extern "C" int vd_tc_conv_layer(int layer, const void* in, const void* wimg, con
     p.epi.T = plan->T; p.epi.n_items = B; p.epi.g = g;
     p.epi.layer = layer;
     cudaStream_t s = (cudaStream_t)stream;
-    if (raw == 2) return launch<EPI_PLAIN>(p, smem, s);
+    p.epi.accum = raw == 3;
+    if (raw >= 2) return launch<EPI_PLAIN>(p, smem, s);
     if (raw) return launch<EPI_RAW>(p, smem, s);
     if (layer == 0) return launch<EPI_L0>(p, smem, s);
     if (layer == 1) return launch<EPI_L1>(p, smem, s);

@@ -9,8 +9,13 @@ namespace tc {
 
 // video (Bsrc, T, 3, H, W) fp32 -> x0 (B, T+2, 3, 2, RI0, Wo0) chunks; source video of item b is
 // index ? index[b] : b (the device-resident get_images gather, distill_s2d_ms.py:81-87).
+// part: 0 = the value (rounded to bf16), 1 = its bf16 residual v - bf16(v) (split-bf16 operands of the conv trio)
+__device__ __forceinline__ float bf16_part(float v, int part) {
+    return part == 0 ? v : v - __uint_as_float((uint32_t)f2bf(v) << 16);
+}
+
 __global__ void pack_video_kernel(const float* __restrict__ video, const int64_t* __restrict__ index,
-                                  uint4* __restrict__ x0, int64_t total, int T, int HW, int RI0, int Wo0) {
+                                  uint4* __restrict__ x0, int64_t total, int T, int HW, int RI0, int Wo0, int part, int ncdhw) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int wo = (int)(i % Wo0); int64_t q = i / Wo0;
         int row = (int)(q % RI0); q /= RI0;
@@ -24,11 +29,12 @@ __global__ void pack_video_kernel(const float* __restrict__ video, const int64_t
         for (int k = 0; k < 8; ++k) v[k] = 0;
         if (t >= 0 && t < T && h >= 0 && h < HW) {
             const int64_t src = index ? index[b] : b;
-            const float* p = video + (((src * T + t) * 3 + c) * HW + h) * (int64_t)HW;
+            const int64_t plane = ncdhw ? (src * 3 + c) * T + t : (src * T + t) * 3 + c;     // (B,3,T,H,W) or (B,T,3,H,W)
+            const float* p = video + (plane * HW + h) * (int64_t)HW;
 #pragma unroll
             for (int k = 0; k < 7; ++k) {
                 const int w = 2 * wo + k - 3;
-                if (w >= 0 && w < HW) v[k] = f2bf(__ldg(p + w));
+                if (w >= 0 && w < HW) v[k] = f2bf(bf16_part(__ldg(p + w), part));
             }
         }
         uint4 o;
@@ -39,7 +45,7 @@ __global__ void pack_video_kernel(const float* __restrict__ video, const int64_t
 }
 
 // conv 0 image: [p 11][k 2][blk 5][64][8] bf16; blk 0,4 = zero, blk b = W[kt = 3-b]
-__global__ void pack_w0_kernel(const float* __restrict__ w, uint16_t* __restrict__ img) {
+__global__ void pack_w0_kernel(const float* __restrict__ w, uint16_t* __restrict__ img, int part) {
     const int total = kW0Bytes / 2;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         int e = i % 8; int q = i / 8;
@@ -50,14 +56,14 @@ __global__ void pack_w0_kernel(const float* __restrict__ w, uint16_t* __restrict
         float v = 0.f;
         if (ch < 21 && e < 7 && blk >= 1 && blk <= 3) {
             const int c = ch / 7, kh = l0_chunk_kh(ch % 7), kt = 3 - blk;
-            v = w[(((row * 3 + c) * 3 + kt) * 7 + kh) * 7 + e];
+            v = bf16_part(w[(((row * 3 + c) * 3 + kt) * 7 + kh) * 7 + e], part);
         }
         img[i] = f2bf(v);
     }
 }
 
 // conv 1 image: [kt 3][slice 4][kh 7][kw 7][k 2][128][8]
-__global__ void pack_w1_kernel(const float* __restrict__ w, uint16_t* __restrict__ img) {
+__global__ void pack_w1_kernel(const float* __restrict__ w, uint16_t* __restrict__ img, int part) {
     const int total = 588 * kWeightTileBytes / 2;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         int e = i % 8; int q = i / 8;
@@ -67,12 +73,12 @@ __global__ void pack_w1_kernel(const float* __restrict__ w, uint16_t* __restrict
         int kh = q % 7; q /= 7;
         int slice = q % 4; int kt = q / 4;
         const int ci = slice * 16 + k * 8 + e;
-        img[i] = f2bf(w[(((row * 64 + ci) * 3 + kt) * 7 + kh) * 7 + kw]);
+        img[i] = f2bf(bf16_part(w[(((row * 64 + ci) * 3 + kt) * 7 + kh) * 7 + kw], part));
     }
 }
 
 // conv 2 image: [kh 7][kw 7][half 2][kt 3][kc 4][k 2][128][8]
-__global__ void pack_w2_kernel(const float* __restrict__ w, uint16_t* __restrict__ img) {
+__global__ void pack_w2_kernel(const float* __restrict__ w, uint16_t* __restrict__ img, int part) {
     const int total = 1176 * kWeightTileBytes / 2;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         int e = i % 8; int q = i / 8;
@@ -83,7 +89,7 @@ __global__ void pack_w2_kernel(const float* __restrict__ w, uint16_t* __restrict
         int half = q % 2; q /= 2;
         int kw = q % 7; int kh = q / 7;
         const int ci = half * 64 + kc * 16 + k * 8 + e;
-        img[i] = f2bf(w[(((row * 128 + ci) * 3 + kt) * 7 + kh) * 7 + kw]);
+        img[i] = f2bf(bf16_part(w[(((row * 128 + ci) * 3 + kt) * 7 + kh) * 7 + kw], part));
     }
 }
 
@@ -93,8 +99,8 @@ __global__ void pack_w2_kernel(const float* __restrict__ w, uint16_t* __restrict
 using namespace vd;
 using namespace vd::tc;
 
-extern "C" int vd_tc_pack_video(const float* video, const int64_t* index, void* x0, const vd_tc_plan* plan,
-                                int B, void* stream) {
+static int pack_video_impl(const float* video, const int64_t* index, void* x0, const vd_tc_plan* plan, int B, int part,
+                           int ncdhw, void* stream) {
     VD_REQUIRE(video && x0 && plan, "tc_pack_video: NULL pointer");
     VD_REQUIRE(geo_supported(plan->T, plan->H), "tc_pack_video: unsupported geometry");
     if (B <= 0) return 0;
@@ -102,24 +108,47 @@ extern "C" int vd_tc_pack_video(const float* video, const int64_t* index, void* 
     const int64_t total = (int64_t)B * (g.T + 2) * 6 * g.RI0 * g.Wo0;
     int64_t blocks = ceil_div(total, 256);
     if (blocks > 148 * 32) blocks = 148 * 32;
-    pack_video_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(video, index, (uint4*)x0, total, g.T, g.HW, g.RI0, g.Wo0);
+    pack_video_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(video, index, (uint4*)x0, total, g.T, g.HW, g.RI0, g.Wo0,
+                                                                          part, ncdhw);
     return check_launch("tc_pack_video");
+}
+
+extern "C" int vd_tc_pack_video(const float* video, const int64_t* index, void* x0, const vd_tc_plan* plan,
+                                int B, void* stream) {
+    return pack_video_impl(video, index, x0, plan, B, 0, 0, stream);
+}
+
+// conv-trio variant: x is fp32 NCDHW (B,3,T,H,W); part = 0 value / 1 bf16 residual
+extern "C" int vd_tc_pack_video_ncdhw(const float* x, void* x0, const vd_tc_plan* plan, int B, int part, void* stream) {
+    VD_REQUIRE(part == 0 || part == 1, "tc_pack_video_ncdhw: part must be 0 or 1");
+    return pack_video_impl(x, nullptr, x0, plan, B, part, 1, stream);
+}
+
+static int pack_weights_impl(const float* w_l0, const float* w_l1, const float* w_l2, void* w0, void* w1, void* w2, int part,
+                             void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (w_l0 && w0) {
+        pack_w0_kernel<<<148, 256, 0, s>>>(w_l0, (uint16_t*)w0, part);
+        if (int e = check_launch("tc_pack_w0")) return e;
+    }
+    if (w_l1 && w1) {
+        pack_w1_kernel<<<148 * 4, 256, 0, s>>>(w_l1, (uint16_t*)w1, part);
+        if (int e = check_launch("tc_pack_w1")) return e;
+    }
+    if (w_l2 && w2) {
+        pack_w2_kernel<<<148 * 4, 256, 0, s>>>(w_l2, (uint16_t*)w2, part);
+        if (int e = check_launch("tc_pack_w2")) return e;
+    }
+    return 0;
 }
 
 extern "C" int vd_tc_pack_weights(const float* w_l0, const float* w_l1, const float* w_l2, void* w0, void* w1,
                                   void* w2, void* stream) {
-    cudaStream_t s = (cudaStream_t)stream;
-    if (w_l0 && w0) {
-        pack_w0_kernel<<<148, 256, 0, s>>>(w_l0, (uint16_t*)w0);
-        if (int e = check_launch("tc_pack_w0")) return e;
-    }
-    if (w_l1 && w1) {
-        pack_w1_kernel<<<148 * 4, 256, 0, s>>>(w_l1, (uint16_t*)w1);
-        if (int e = check_launch("tc_pack_w1")) return e;
-    }
-    if (w_l2 && w2) {
-        pack_w2_kernel<<<148 * 4, 256, 0, s>>>(w_l2, (uint16_t*)w2);
-        if (int e = check_launch("tc_pack_w2")) return e;
-    }
-    return 0;
+    return pack_weights_impl(w_l0, w_l1, w_l2, w0, w1, w2, 0, stream);
+}
+
+extern "C" int vd_tc_pack_weights_part(const float* w_l0, const float* w_l1, const float* w_l2, void* w0, void* w1,
+                                       void* w2, int part, void* stream) {
+    VD_REQUIRE(part == 0 || part == 1, "tc_pack_weights_part: part must be 0 or 1");
+    return pack_weights_impl(w_l0, w_l1, w_l2, w0, w1, w2, part, stream);
 }

@@ -19,7 +19,7 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
 }
 
 // x (B, 64, T, H1, H1) fp32 -> A1 [item][slice 4][t_pad T+2][ph 2][pw 2][k 2][i RI1][j P1] chunks (8 channels)
-__global__ void pack_a1_kernel(const float* __restrict__ x, uint4* __restrict__ a1, int64_t total, Geo g) {
+__global__ void pack_a1_kernel(const float* __restrict__ x, uint4* __restrict__ a1, int64_t total, Geo g, int part) {
     const int64_t S1 = (int64_t)g.T * g.H1 * g.H1;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int j = (int)(i % g.P1); int64_t q = i / g.P1;
@@ -34,14 +34,14 @@ __global__ void pack_a1_kernel(const float* __restrict__ x, uint4* __restrict__ 
         if (t >= 0 && t < g.T && h >= 0 && h < g.H1 && w >= 0 && w < g.H1) {
             const float* p = x + (item * 64 + slice * 16 + k * 8) * S1 + ((int64_t)t * g.H1 + h) * g.H1 + w;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = __ldg(p + e * S1);
+            for (int e = 0; e < 8; ++e) { const float t_ = __ldg(p + e * S1); v[e] = part ? t_ - __uint_as_float((uint32_t)f2bf(t_) << 16) : t_; }
         }
         a1[i] = pack8(v);
     }
 }
 
 // x (B, 128, T2, H2, H2) fp32 -> A2 [item][khw 49][half 2][k 8][t_pad To2+2][ho Ho2][wo Wo2] chunks (8 channels)
-__global__ void pack_a2_kernel(const float* __restrict__ x, uint4* __restrict__ a2, int64_t total, Geo g) {
+__global__ void pack_a2_kernel(const float* __restrict__ x, uint4* __restrict__ a2, int64_t total, Geo g, int part) {
     const int64_t S2 = (int64_t)g.T2 * g.H2 * g.H2;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int wo = (int)(i % g.Wo2); int64_t q = i / g.Wo2;
@@ -56,7 +56,7 @@ __global__ void pack_a2_kernel(const float* __restrict__ x, uint4* __restrict__ 
         if (t >= 0 && t < g.T2 && h >= 0 && h < g.H2 && w >= 0 && w < g.H2) {
             const float* p = x + (item * 128 + half * 64 + k * 8) * S2 + ((int64_t)t * g.H2 + h) * g.H2 + w;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = __ldg(p + e * S2);
+            for (int e = 0; e < 8; ++e) { const float t_ = __ldg(p + e * S2); v[e] = part ? t_ - __uint_as_float((uint32_t)f2bf(t_) << 16) : t_; }
         }
         a2[i] = pack8(v);
     }
@@ -156,19 +156,20 @@ using namespace vd::tc;
 
 // x fp32 NCDHW (B, 64, T, H/4, W/4) -> A1 (layer 1) or (B, 128, T/2, H/16.., ..) -> A2 (layer 2); every chunk of the
 // packed operand (halo included) is written.
-extern "C" int vd_tc_pack_act(int layer, const float* x, void* packed, const vd_tc_plan* plan, int B, void* stream) {
+extern "C" int vd_tc_pack_act(int layer, const float* x, void* packed, const vd_tc_plan* plan, int B, int part, void* stream) {
     VD_REQUIRE(x && packed && plan, "tc_pack_act: NULL pointer");
-    VD_REQUIRE(layer == 1 || layer == 2, "tc_pack_act: layer must be 1 or 2 (layer 0 uses vd_tc_pack_video)");
+    VD_REQUIRE(layer == 1 || layer == 2, "tc_pack_act: layer must be 1 or 2 (layer 0 uses vd_tc_pack_video_ncdhw)");
+    VD_REQUIRE(part == 0 || part == 1, "tc_pack_act: part must be 0 (value) or 1 (bf16 residual)");
     VD_REQUIRE(geo_supported(plan->T, plan->H), "tc_pack_act: unsupported geometry");
     if (B <= 0) return 0;
     const Geo g = make_geo(plan->T, plan->H);
     cudaStream_t s = (cudaStream_t)stream;
     if (layer == 1) {
         const int64_t total = (int64_t)B * (g.video1 / 16);
-        pack_a1_kernel<<<grid_of(total), 256, 0, s>>>(x, (uint4*)packed, total, g);
+        pack_a1_kernel<<<grid_of(total), 256, 0, s>>>(x, (uint4*)packed, total, g, part);
     } else {
         const int64_t total = (int64_t)B * (g.video2 / 16);
-        pack_a2_kernel<<<grid_of(total), 256, 0, s>>>(x, (uint4*)packed, total, g);
+        pack_a2_kernel<<<grid_of(total), 256, 0, s>>>(x, (uint4*)packed, total, g, part);
     }
     return check_launch("tc_pack_act");
 }

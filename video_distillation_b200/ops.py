@@ -65,18 +65,11 @@ def conv3d_fprop_raw(x, w, bias, stride, padding):
     x, w = _f32c(x), _f32c(w)
     trio, layer = _tc_route(x.shape, w.shape, stride, padding, x.device)
     if trio is not None and x.shape[0] > 0:
-        if _TC_FPROP_SPLIT:
-            # split-bf16: x = xh + xl, w = wh + wl (bf16 each); xh*wh + xh*wl + xl*wh recovers ~16 mantissa bits.
-            # The forward decides ReLU masks / pool argmax and the logits, so it is the precision-critical third of
-            # the trio (single-pass bf16 fprop alone costs 5-7 % on MTT's second-order gradients; measured in
-            # tests/test_dm_gpu.py::test_mtt_s2d_golden).
-            xh = x.to(torch.bfloat16).float()
-            wh = w.to(torch.bfloat16).float()
-            y = trio.fprop(layer, xh, wh)
-            y += trio.fprop(layer, xh, w - wh)
-            y += trio.fprop(layer, x - xh, wh)
-        else:
-            y = trio.fprop(layer, x, w)
+        # split-bf16: x = xh + xl, w = wh + wl (bf16 each); xh*wh + xh*wl + xl*wh recovers ~16 mantissa bits.
+        # The forward decides ReLU masks / pool argmax and the logits, so it is the precision-critical third of
+        # the trio (single-pass bf16 fprop alone costs 5-7 % on MTT's second-order gradients; measured in
+        # tests/test_dm_gpu.py::test_mtt_s2d_golden).
+        y = trio.fprop(layer, x, w, split=_TC_FPROP_SPLIT)
         return y if bias is None else y + bias.view(1, -1, 1, 1, 1)
     g = conv_geom(x.shape, w.shape, stride, padding)
     y = torch.empty(g.N, g.Cout, g.To, g.Ho, g.Wo, dtype=torch.float32, device=x.device)

@@ -43,35 +43,49 @@ class TcTrio:
             self._ws[name] = t
         return t
 
-    def _pack_input(self, layer, x):
+    def _pack_input(self, layer, x, part=0):
         p, lib, B = self.plan, _lib.lib(), int(x.shape[0])
         if layer == 0:
             buf = self._buf('x0', B * p.x0_bytes_per_video)
-            v = x.permute(0, 2, 1, 3, 4).contiguous()
-            _lib.check(lib.vd_tc_pack_video(_lib.ptr(v), None, _lib.ptr(buf), ctypes.byref(p), B, _lib.stream()), 'vd_tc_pack_video')
+            _lib.check(lib.vd_tc_pack_video_ncdhw(_lib.ptr(x), _lib.ptr(buf), ctypes.byref(p), B, part, _lib.stream()), 'vd_tc_pack_video_ncdhw')
         elif layer == 1:
             buf = self._buf('a1', B * p.a1_bytes_per_video)
-            _lib.check(lib.vd_tc_pack_act(1, _lib.ptr(x), _lib.ptr(buf), ctypes.byref(p), B, _lib.stream()), 'vd_tc_pack_act(1)')
+            _lib.check(lib.vd_tc_pack_act(1, _lib.ptr(x), _lib.ptr(buf), ctypes.byref(p), B, part, _lib.stream()), 'vd_tc_pack_act(1)')
         else:
             buf = self._buf('a2', (B + 3) // 4 * 4 * p.a2_bytes_per_video, zero=True)
-            _lib.check(lib.vd_tc_pack_act(2, _lib.ptr(x), _lib.ptr(buf), ctypes.byref(p), B, _lib.stream()), 'vd_tc_pack_act(2)')
+            _lib.check(lib.vd_tc_pack_act(2, _lib.ptr(x), _lib.ptr(buf), ctypes.byref(p), B, part, _lib.stream()), 'vd_tc_pack_act(2)')
         return buf
 
-    # ------------------------------------------------------------------ the trio
-    def fprop(self, layer, x, w):
-        p, lib, B = self.plan, _lib.lib(), int(x.shape[0])
-        cin, cout, _ = self.layers[layer]
-        wimg = self._buf(f'w{layer}', (p.w0_bytes, p.w1_bytes, p.w2_bytes)[layer])
+    def _pack_weight(self, layer, w, part, name):
+        p, lib = self.plan, _lib.lib()
+        wimg = self._buf(name, (p.w0_bytes, p.w1_bytes, p.w2_bytes)[layer])
         ws = [None, None, None]
         imgs = [None, None, None]
         ws[layer], imgs[layer] = w, wimg
-        _lib.check(lib.vd_tc_pack_weights(_lib.ptr(ws[0]), _lib.ptr(ws[1]), _lib.ptr(ws[2]), _lib.ptr(imgs[0]), _lib.ptr(imgs[1]),
-                                          _lib.ptr(imgs[2]), _lib.stream()), 'vd_tc_pack_weights')
-        src = self._pack_input(layer, x)
+        _lib.check(lib.vd_tc_pack_weights_part(_lib.ptr(ws[0]), _lib.ptr(ws[1]), _lib.ptr(ws[2]), _lib.ptr(imgs[0]), _lib.ptr(imgs[1]),
+                                               _lib.ptr(imgs[2]), part, _lib.stream()), 'vd_tc_pack_weights_part')
+        return wimg
+
+    def _conv(self, layer, src, wimg, y, B, accumulate):
+        _lib.check(_lib.lib().vd_tc_conv_layer(layer, _lib.ptr(src), _lib.ptr(wimg), None, _lib.ptr(y), None, 0, ctypes.byref(self.plan),
+                                               None, B, 3 if accumulate else 2, _lib.stream()), f'vd_tc_conv_layer({layer}, plain)')
+
+    # ------------------------------------------------------------------ the trio
+    def fprop(self, layer, x, w, split=False):
+        """y = conv3d(x, w).  split: x = xh + xl, w = wh + wl (bf16 parts made inside the packers);
+        y = xh*wh + xh*wl + xl*wh accumulated in fp32 by the plain epilogue (three launches, no temporaries)."""
+        p, B = self.plan, int(x.shape[0])
+        cin, cout, _ = self.layers[layer]
         out_ext = [(p.T1, p.H1, p.W1), (p.T2, p.H2, p.W2), (p.T3, p.H3, p.W3)][layer]
         y = torch.empty(B, cout, *out_ext, dtype=torch.float32, device=self.device)
-        _lib.check(lib.vd_tc_conv_layer(layer, _lib.ptr(src), _lib.ptr(wimg), None, _lib.ptr(y), None, 0, ctypes.byref(p), None,
-                                        B, 2, _lib.stream()), f'vd_tc_conv_layer({layer}, plain)')
+        wh = self._pack_weight(layer, w, 0, f'w{layer}')
+        src = self._pack_input(layer, x, 0)
+        self._conv(layer, src, wh, y, B, False)
+        if split:
+            wl = self._pack_weight(layer, w, 1, f'wl{layer}')
+            self._conv(layer, src, wl, y, B, True)
+            src = self._pack_input(layer, x, 1)
+            self._conv(layer, src, wh, y, B, True)
         return y
 
     def dgrad(self, layer, gy, w):
