@@ -234,6 +234,22 @@ int vd_tc_wgrad_gemm(int layer, const void* xcol, const void* gyimg, float* raw,
                      void* stream);
 int vd_tc_wgrad_reduce(int layer, const float* raw, float* gw, const vd_tc_plan* plan, int B, void* stream);
 
+/* ---- direct (column-free) dgrad of conv 1: a shifted-window GEMM per input-row parity over the "padded planar" dY
+ * of conv 1 (tc_layout.h: Dg1Geo).  Replaces vd_tc_bwd_gemm(1) + vd_tc_bwd_col2im(1) (59 MB of column buffer per video).
+ *   vd_tc_dgrad1_sizes        out[0] dYP bytes per video, out[1..2] weight image bytes (ph = 0, 1)
+ *   vd_tc_pack_dgrad1_weights fp32 OIDHW weights of features.3 -> the two weight images
+ *   vd_tc_pack_dyp1           fp32 NCDHW gy (B,128,T,Ho1,Wo1) -> dYP (every cell written)
+ *   vd_tc_bwd_col2im_ex       layer 2, out_layout 1: col2im + routing of conv 2's columns straight into dYP (halo pre-zeroed)
+ *   vd_tc_dgrad1              code0 != NULL: out = packed dY of conv 0's column GEMM (ReLU/MaxPool routing of conv 0 applied)
+ *                             code0 == NULL: out = fp32 NCDHW (B, 64, T, H1, H1) */
+int vd_tc_dgrad1_sizes(const vd_tc_plan* plan, int64_t* out);
+int vd_tc_pack_dgrad1_weights(const float* w_l1, void* wimg0, void* wimg1, const vd_tc_plan* plan, void* stream);
+int vd_tc_pack_dyp1(const float* gy, void* dyp, const vd_tc_plan* plan, int B, void* stream);
+int vd_tc_bwd_col2im_ex(int layer, const void* col, const uint8_t* code_below, void* out, const vd_tc_plan* plan, int B,
+                        int out_layout, void* stream);
+int vd_tc_dgrad1(const void* dyp, const void* wimg0, const void* wimg1, const uint8_t* code0, void* out,
+                 const vd_tc_plan* plan, int B, void* stream);
+
 /* Tuning probe (tests/bring-up only): issues 148 x n_sa x n_steps x n_acc MMAs of N=ncols with the
  * given descriptor words over dummy operands (pix >= 64 KiB, wimg >= 16 KiB, raw >= 148*n_acc*128*ncols
  * floats) so that the MMA rate of a shared-memory layout can be timed with CUDA events. */

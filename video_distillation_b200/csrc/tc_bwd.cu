@@ -120,7 +120,7 @@ __device__ __forceinline__ float c2i_taps(const uint16_t* __restrict__ sm16, int
 // layer 0 (code == nullptr): writes d video (B, T, 3, H, W) fp32.
 __global__ void __launch_bounds__(256) col2im_kernel(const uint16_t* __restrict__ colbuf, const uint8_t* __restrict__ code,
                                                      void* __restrict__ out, BwdGeo b, BwdGeo bb, int pt, int band, int pitch, int cib,
-                                                     int ncdhw) {
+                                                     int ncdhw, Dg1Geo dg, int padded_planar) {
     extern __shared__ uint32_t c2i_smem[];
     const C2iBlock k = c2i_block(b, band, cib);
     const uint16_t* colv = colbuf + (int64_t)k.vid * b.col_video_elems;
@@ -170,9 +170,20 @@ __global__ void __launch_bounds__(256) col2im_kernel(const uint16_t* __restrict_
         const uint8_t cd = code[((((int64_t)k.vid * b.Cin + ci) * b.Ti + k.t) * b.Hi + h) * b.Wi + w];
         const uint16_t gv = f2bf((cd & 8) ? acc[j] : 0.f);
         const int arg = cd & 7;
-        uint16_t* base = reinterpret_cast<uint16_t*>(out) + (int64_t)k.vid * (bb.dy_video / 2);
         const int chunk = ci >> 3, e = ci & 7;
         int pos = 0;
+        if (padded_planar) {
+            // dY of conv 1 in the padded planar layout of the direct dgrad (Dg1Geo): [t_pad][chunk][row ho+1][col wo+1]
+            uint16_t* base = reinterpret_cast<uint16_t*>(out) + (int64_t)k.vid * (dg.video_bytes / 2);
+            for (int dt = 0; dt < pt; ++dt)
+                for (int dh = 0; dh < 2; ++dh)
+                    for (int dw = 0; dw < 2; ++dw, ++pos) {
+                        const int to = k.t * pt + dt, ho = 2 * h + dh, wo = 2 * w + dw;
+                        base[((((int64_t)(to + 1) * 16 + chunk) * dg.RD + ho + 1) * dg.PD + wo + 1) * 8 + e] = (pos == arg) ? gv : (uint16_t)0;
+                    }
+            continue;
+        }
+        uint16_t* base = reinterpret_cast<uint16_t*>(out) + (int64_t)k.vid * (bb.dy_video / 2);
         for (int dt = 0; dt < pt; ++dt)
             for (int dh = 0; dh < 2; ++dh)
                 for (int dw = 0; dw < 2; ++dw, ++pos) {
@@ -377,7 +388,8 @@ extern "C" int vd_tc_bwd_emb(const float* g_emb, const uint8_t* code2, void* dy2
 // mode 0: route with code_below into the packed dY of the layer below (layers 1,2) / d video (B,T,3,H,W) (layer 0)
 // mode 1: plain fp32 NCDHW gradient (B, Cin, Ti, Hi, Wi) for any layer (dgrad of the differentiable conv trio)
 static int col2im_launch(int layer, const void* col, const uint8_t* code_below, void* out, const vd_tc_plan* plan, int B,
-                         void* stream, int ncdhw) {
+                         void* stream, int ncdhw, int padded_planar = 0) {
+    VD_REQUIRE(!padded_planar || (layer == 2 && !ncdhw), "tc_bwd_col2im: the padded planar output exists for layer 2 (dY of conv 1) only");
     VD_REQUIRE(col && out && plan, "tc_bwd_col2im: NULL pointer");
     VD_REQUIRE(layer >= 0 && layer <= 2, "tc_bwd_col2im: bad layer");
     VD_REQUIRE(ncdhw || (layer == 0) == (code_below == nullptr), "tc_bwd_col2im: code_below is required for layers 1,2 and must be NULL for layer 0");
@@ -445,13 +457,21 @@ static int col2im_launch(int layer, const void* col, const uint8_t* code_below, 
     VD_REQUIRE(smem <= 96 * 1024, "tc_bwd_col2im: staging buffer too large (%zu bytes)", smem);
     const int64_t blocks = (int64_t)B * (b.Cin / cib) * b.Ti * nb;
     VD_REQUIRE(blocks < (1ll << 31), "tc_bwd_col2im: grid too large");
-    col2im_kernel<<<(unsigned)blocks, 256, smem, s>>>((const uint16_t*)col, cd, out, b, bb, pt, band, pitch, cib, ncdhw);
+    col2im_kernel<<<(unsigned)blocks, 256, smem, s>>>((const uint16_t*)col, cd, out, b, bb, pt, band, pitch, cib, ncdhw,
+                                                      make_dg1_geo(g), padded_planar);
     return check_launch("tc_bwd_col2im");
 }
 
 extern "C" int vd_tc_bwd_col2im(int layer, const void* col, const uint8_t* code_below, void* out,
                                 const vd_tc_plan* plan, int B, void* stream) {
     return col2im_launch(layer, col, code_below, out, plan, B, stream, 0);
+}
+
+// layer 2 with out_layout = 1: the routed dY of conv 1 goes to the padded planar layout consumed by vd_tc_dgrad1
+// (the buffer's halo cells must have been zeroed once by the caller; data cells are fully overwritten)
+extern "C" int vd_tc_bwd_col2im_ex(int layer, const void* col, const uint8_t* code_below, void* out,
+                                   const vd_tc_plan* plan, int B, int out_layout, void* stream) {
+    return col2im_launch(layer, col, code_below, out, plan, B, stream, 0, out_layout);
 }
 
 extern "C" int vd_tc_bwd_col2im_plain(int layer, const void* col, float* gx, const vd_tc_plan* plan, int B, void* stream) {

@@ -24,7 +24,7 @@ constexpr int kMaxSteps = 64;
 constexpr int kMaxCopies = 8;
 constexpr int kThreads = 256;
 
-enum EpiMode { EPI_RAW = 0, EPI_L0 = 1, EPI_L1 = 2, EPI_L2 = 3, EPI_PLAIN = 4 };
+enum EpiMode { EPI_RAW = 0, EPI_L0 = 1, EPI_L1 = 2, EPI_L2 = 3, EPI_PLAIN = 4, EPI_DG1 = 5 };
 
 struct EpiParams {
     float* raw;            // EPI_RAW: [tile][u][acc][128][ncols]
@@ -35,6 +35,8 @@ struct EpiParams {
     int code_first;        // items below this index record no codes (frozen real videos ahead of synthetic ones)
     int layer;             // EPI_PLAIN: which conv (tile -> NCDHW mapping)
     int accum;             // EPI_PLAIN: out += result (split-bf16 passes accumulate into the same fp32 tensor)
+    int ph;                // EPI_DG1: input-row parity of this launch
+    BwdGeo bb;             // EPI_DG1 (route mode): geometry of the packed dY operand of conv 0's column GEMM
     int T;                 // frames of the video
     int n_items;           // videos (conv 2: valid videos, tiles may be partially filled)
     Geo g;
@@ -410,6 +412,45 @@ __device__ __forceinline__ void epi_plain(const WsParams& p, int tile, uint32_t 
     }
 }
 
+// direct dgrad of conv 1 (Dg1Geo, tc_layout.h): lane m = pw*64 + ci, columns q = a*PD + b hold
+// dX1[ci, t, 2a+ph, 2b+pw].  code != NULL: apply the ReLU / MaxPool(1,2,2) routing code of conv 0's output and write
+// the 2x2 window of the packed dY of conv 0 (routed gradient at the recorded argmax, zeros elsewhere); code == NULL:
+// plain fp32 NCDHW gradient (B, 64, T, H1, H1).
+__device__ __forceinline__ void epi_dg1(const WsParams& p, int tile, uint32_t taddr, int m) {
+    const Geo& g = p.epi.g;
+    const int item = tile / p.tiles_per_item, t = tile % p.tiles_per_item;
+    const int pw = m >> 6, ci = m & 63, ph = p.epi.ph;
+    const int64_t plane = (((int64_t)item * 64 + ci) * g.T + t) * g.H1 * g.H1;
+    const uint8_t* code = p.epi.code ? p.epi.code + plane : nullptr;
+    float* gx = reinterpret_cast<float*>(p.epi.out) + plane;
+    const BwdGeo& bb = p.epi.bb;
+    uint16_t* dy0 = reinterpret_cast<uint16_t*>(p.epi.out) + (int64_t)item * (bb.dy_video / 2);
+    const int chunk = ci >> 3, e = ci & 7;
+    for (int a = 0; a < g.Ho1; ++a) {
+        float v[16];
+        tmem_ld16(taddr + a * g.P1, v);
+        tmem_ld_wait();
+        const int h = 2 * a + ph;
+#pragma unroll
+        for (int b = 0; b < 16; ++b) {
+            if (b >= g.Wo1) continue;
+            const int w = 2 * b + pw;
+            if (code == nullptr) { gx[h * g.H1 + w] = v[b]; continue; }
+            const uint8_t cd = code[h * g.H1 + w];
+            const uint16_t gv = f2bf((cd & 8) ? v[b] : 0.f);
+            const int arg = cd & 7;
+#pragma unroll
+            for (int dh = 0; dh < 2; ++dh) {
+                const int pix = (t * bb.Ho + 2 * h + dh) * bb.Wo + 2 * w;           // even: pix and pix+1 share a tile
+                const int nt = (int)__umulhi((uint32_t)pix, bb.nc_magic), col = pix - nt * bb.NC;
+                uint16_t* d = dy0 + (((int64_t)nt * (bb.K / 8) + chunk) * bb.NC + col) * 8 + e;
+                d[0] = (arg == 2 * dh) ? gv : (uint16_t)0;
+                d[8] = (arg == 2 * dh + 1) ? gv : (uint16_t)0;
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 template <int EPI, int NACC>
 __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_constant__ WsParams p) {
@@ -605,6 +646,7 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
                     else if (EPI == EPI_L0) epi_l0(p, tile, taddr, m);
                     else if (EPI == EPI_L1) epi_l1_drain(p, tile, taddr, m, reinterpret_cast<uint16_t*>(base_ptr + p.smem_stash_off));
                     else if (EPI == EPI_PLAIN) epi_plain(p, tile, taddr, m);
+                    else if (EPI == EPI_DG1) epi_dg1(p, tile, taddr, m);
                     else epi_l2(p, tile, taddr, m);
                 }
                 tc_fence_before();
@@ -814,6 +856,8 @@ static int launch(const WsParams& p, uint32_t smem, cudaStream_t stream) {
         return launch_n<EPI_L1, 2>(p, smem, stream);
     } else if (EPI == EPI_L2 && p.n_acc == 4) {
         return launch_n<EPI_L2, 4>(p, smem, stream);
+    } else if (EPI == EPI_DG1 && p.n_acc == 1) {
+        return launch_n<EPI_DG1, 1>(p, smem, stream);
     } else if (EPI == EPI_PLAIN) {
         if (p.n_acc == 1) return launch_n<EPI_PLAIN, 1>(p, smem, stream);
         if (p.n_acc == 2) return launch_n<EPI_PLAIN, 2>(p, smem, stream);
@@ -932,6 +976,54 @@ extern "C" int vd_tc_bwd_gemm(int layer, const void* dy, const void* wt, void* c
     p.pix = (const uint8_t*)dy; p.wimg = (const uint8_t*)wt; p.item_index = nullptr;
     p.epi.raw = (float*)col; p.epi.raw_bf16 = 1; p.epi.T = plan->T; p.epi.n_items = B; p.epi.g = g;
     return launch<EPI_RAW>(p, smem, (cudaStream_t)stream);
+}
+
+// Direct dgrad of conv 1 (no column buffer): two launches (input-row parity ph = 0, 1) of the shifted-window GEMM
+// described at Dg1Geo.  dyp = padded planar dY of conv 1 (vd_tc_pack_dyp1 / vd_tc_bwd_col2im_ex), wimg0/1 = weight
+// images of vd_tc_pack_dgrad1_weights.  code0 != NULL: out = packed dY of conv 0's column GEMM (routing applied);
+// code0 == NULL: out = fp32 NCDHW (B, 64, T, H1, H1).
+extern "C" int vd_tc_dgrad1(const void* dyp, const void* wimg0, const void* wimg1, const uint8_t* code0, void* out,
+                            const vd_tc_plan* plan, int B, void* stream) {
+    VD_REQUIRE(dyp && wimg0 && wimg1 && out && plan, "tc_dgrad1: NULL pointer");
+    VD_REQUIRE(geo_supported(plan->T, plan->H) && B >= 0, "tc_dgrad1: unsupported geometry / batch");
+    if (B == 0) return 0;
+    const Geo g = make_geo(plan->T, plan->H);
+    const Dg1Geo d = make_dg1_geo(g);
+    VD_REQUIRE(d.PD <= 16 && d.N % 16 == 0 && d.N <= 256, "tc_dgrad1: tile does not fit one accumulator");
+    for (int ph = 0; ph < 2; ++ph) {
+        WsParams p;
+        memset(&p, 0, sizeof(p));
+        p.n_u = 1; p.nu_total = 1; p.ug_count = 1; p.w_u_stride = 0; p.w_item_stride = 0;
+        p.n_tiles = B * g.T; p.tiles_per_item = g.T; p.v_count = 1;
+        // tile (item, t): stage sa = kt reads the padded frame t + 2 - kt, sb = co half (8 chunks)
+        p.item_stride = d.video_bytes; p.u_stride = d.frame_bytes; p.v_stride = 0;
+        p.n_sa = 3; p.n_sb = 2; p.sa_stride = -d.frame_bytes; p.sb_stride = d.frame_bytes / 2;
+        p.n_copies = 1; p.copy_gofs[0] = 2 * d.frame_bytes; p.copy_sofs[0] = 0; p.copy_bytes[0] = (uint32_t)(d.frame_bytes / 2);
+        p.stage_bytes = p.copy_bytes[0];
+        p.n_steps = d.n_steps[ph];
+        const int first = ph ? 2 : 1;
+        int j = 0;
+        for (int ih = 0; ih < d.n_sh[ph]; ++ih)
+            for (int iw = 0; iw < 4; ++iw)
+                for (int cs = 0; cs < 4; ++cs, ++j) {
+                    const int sh = dg1_shift(ih, first), sw = dg1_shift(iw, 2);
+                    p.b_off16[j] = (uint32_t)(2 * cs * d.plane16 + (sh + 1) * d.PD + (sw + 1));
+                    p.b_lbo16[j] = (uint32_t)d.plane16;
+                }
+        p.a_lbo16 = 2048 >> 4; p.a_sbo16 = 8;
+        p.w_resident = 0; p.w_bytes = 0;
+        p.G = 8; p.RW = 3; p.RP = 3;
+        p.n_acc = 1; p.acc_delta16 = 0;
+        p.ncols = (uint32_t)d.N; p.acc_cols = 256; p.acc_stages = 2;
+        p.idesc = umma_idesc_bf16(128, (uint32_t)d.N);
+        uint32_t smem = 0;
+        if (int rc = finalize_smem(p, (uint32_t)p.G * p.RW * kWeightTileBytes, &smem)) return rc;
+        p.pix = (const uint8_t*)dyp; p.wimg = (const uint8_t*)(ph ? wimg1 : wimg0); p.item_index = nullptr;
+        p.epi.out = (uint8_t*)out; p.epi.code = const_cast<uint8_t*>(code0); p.epi.T = plan->T; p.epi.n_items = B; p.epi.g = g;
+        p.epi.ph = ph; p.epi.bb = make_bwd_geo(g, 0);
+        if (int rc = launch<EPI_DG1>(p, smem, (cudaStream_t)stream)) return rc;
+    }
+    return 0;
 }
 
 // wgrad of conv `layer` as a split-K GEMM: raw[(split, ntile)][cout 128][col 256] = sum over the slice's pixels of

@@ -130,6 +130,39 @@ inline BwdGeo make_bwd_geo(const Geo& g, int layer) {
     return b;
 }
 
+// ---- direct (column-free) dgrad of conv 1 as a shifted-window GEMM, one launch per input-row parity ph:
+//   dX[ci, t, 2a+ph, 2b+pw] = sum_{kt} sum_{s_h, s_w} sum_co W[co, ci, kt, ph+3-2 s_h, pw+3-2 s_w] * dY[co, t+1-kt, a+s_h, b+s_w]
+//   M rows   : m = pw*64 + ci                      (128)
+//   N columns: q = a*PD + b, PD = Wo1 + 2          (= N1 of the forward conv; columns b >= Wo1 are discarded)
+//   K        : (kt 3) x (co half 2) = 6 stages of [s_h slots][s_w 4][co step 4] K=16 steps; s in {2,1,0,-1}
+//   dYP ("padded planar" dY of conv 1): [video][t_pad T+2][chunk 16][row RD = Ho1+4][col PD] x 16 B,
+//       row r <-> ho = r-1, col c <-> wo = c-1; every cell outside the image is zero, so a window shift is a plain
+//       address offset ((s_h+1)*PD + (s_w+1)) and out-of-image taps read zeros.
+struct Dg1Geo {
+    int Ho, Wo, PD, RD, N;
+    int plane16;                   // RD * PD: 16-byte units per chunk plane
+    int64_t frame_bytes, video_bytes;
+    int n_sh[2];                   // valid row shifts for ph = 0 (3: kh 1,3,5) and ph = 1 (4: kh 0,2,4,6)
+    int n_steps[2];                // n_sh * 4 * 4
+    int64_t wimg_bytes[2];         // 6 stages * n_steps * 4 KiB
+};
+
+inline Dg1Geo make_dg1_geo(const Geo& g) {
+    Dg1Geo d{};
+    d.Ho = g.Ho1; d.Wo = g.Wo1; d.PD = g.P1; d.RD = g.Ho1 + 4; d.N = g.N1;
+    d.plane16 = d.RD * d.PD;
+    d.frame_bytes = (int64_t)16 * d.plane16 * 16;
+    d.video_bytes = (int64_t)(g.T + 2) * d.frame_bytes;
+    for (int ph = 0; ph < 2; ++ph) {
+        d.n_sh[ph] = ph ? 4 : 3;
+        d.n_steps[ph] = d.n_sh[ph] * 16;
+        d.wimg_bytes[ph] = (int64_t)6 * d.n_steps[ph] * 4096;
+    }
+    return d;
+}
+// shift value of slot i (0..3): 2, 1, 0, -1; ph = 0 has no s_h = 2 slot (kh would be -1): its slots are 1, 0, -1
+__host__ __device__ inline int dg1_shift(int slot, int first) { return first - slot; }
+
 constexpr int kWeightTileBytes = 4096;      // [k 2][128 rows][16 B]
 constexpr int kVideosPerTile2 = 4;          // conv 2: accumulators (videos) per CTA tile
 constexpr int kW0Steps = 11;                // conv 0: 21 (c,kh) chunks paired into K=16 steps

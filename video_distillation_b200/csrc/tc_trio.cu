@@ -142,6 +142,46 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ raw, float* __rest
     }
 }
 
+// ---- direct dgrad of conv 1 (Dg1Geo): weight images and the padded planar dY
+// image [stage = kt*2 + half][step = (ih*4 + iw)*4 + cs][k2][128 rows m = pw*64 + ci][8]:
+//   co = half*64 + cs*16 + k2*8 + e, kh = ph + 3 - 2*s_h(ih), kw = pw + 3 - 2*s_w(iw)  (zero when outside 0..6)
+__global__ void pack_dg1_w_kernel(const float* __restrict__ w, uint16_t* __restrict__ img, int ph, int n_sh, int64_t total) {
+    const int n_steps = n_sh * 16;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int e = (int)(i % 8); int64_t q = i / 8;
+        int m = (int)(q % 128); q /= 128;
+        int k2 = (int)(q % 2); q /= 2;
+        int step = (int)(q % n_steps); int stage = (int)(q / n_steps);
+        const int cs = step % 4, iw = (step / 4) % 4, ih = step / 16;
+        const int kt = stage / 2, half = stage % 2;
+        const int pw = m >> 6, ci = m & 63;
+        const int co = half * 64 + cs * 16 + k2 * 8 + e;
+        const int kh = ph + 3 - 2 * dg1_shift(ih, ph ? 2 : 1), kw = pw + 3 - 2 * dg1_shift(iw, 2);
+        float v = 0.f;
+        if (kh >= 0 && kh < 7 && kw >= 0 && kw < 7) v = w[((((int64_t)co * 64 + ci) * 3 + kt) * 7 + kh) * 7 + kw];
+        img[i] = f2bf(v);
+    }
+}
+
+// gy (B, 128, T, Ho1, Wo1) fp32 -> dYP [video][t_pad T+2][chunk 16][row RD][col PD] chunks; every cell is written
+__global__ void pack_dyp1_kernel(const float* __restrict__ gy, uint4* __restrict__ dyp, int64_t total, Dg1Geo d, int T) {
+    const int64_t So = (int64_t)T * d.Ho * d.Wo;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(i % d.PD); int64_t q = i / d.PD;
+        int r = (int)(q % d.RD); q /= d.RD;
+        int chunk = (int)(q % 16); q /= 16;
+        int tp = (int)(q % (T + 2)); int64_t vid = q / (T + 2);
+        const int t = tp - 1, ho = r - 1, wo = c - 1;
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (t >= 0 && t < T && ho >= 0 && ho < d.Ho && wo >= 0 && wo < d.Wo) {
+            const float* p = gy + (vid * 128 + chunk * 8) * So + ((int64_t)t * d.Ho + ho) * d.Wo + wo;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = __ldg(p + e * So);
+        }
+        dyp[i] = pack8(v);
+    }
+}
+
 static inline unsigned grid_of(int64_t n) {
     int64_t x = (n + 255) / 256;
     const int64_t cap = 148 * 32;
@@ -232,4 +272,35 @@ extern "C" int vd_tc_wgrad_reduce(int layer, const float* raw, float* gw, const 
     const BwdGeo b = make_bwd_geo(g, layer);
     wgrad_reduce_kernel<<<grid_of((int64_t)b.K * b.Cin * 147), 256, 0, (cudaStream_t)stream>>>(raw, gw, b.K, b.Cin * 147, (int)w[2], (int)w[0]);
     return check_launch("tc_wgrad_reduce");
+}
+
+// sizes of the direct conv-1 dgrad: out[0] = dYP bytes per video, out[1], out[2] = weight image bytes (ph = 0, 1)
+extern "C" int vd_tc_dgrad1_sizes(const vd_tc_plan* plan, int64_t* out) {
+    VD_REQUIRE(plan && out && geo_supported(plan->T, plan->H), "tc_dgrad1_sizes: bad plan");
+    const Dg1Geo d = make_dg1_geo(make_geo(plan->T, plan->H));
+    out[0] = d.video_bytes; out[1] = d.wimg_bytes[0]; out[2] = d.wimg_bytes[1];
+    return 0;
+}
+
+extern "C" int vd_tc_pack_dgrad1_weights(const float* w_l1, void* wimg0, void* wimg1, const vd_tc_plan* plan, void* stream) {
+    VD_REQUIRE(w_l1 && wimg0 && wimg1 && plan && geo_supported(plan->T, plan->H), "tc_pack_dgrad1_weights: bad argument");
+    const Dg1Geo d = make_dg1_geo(make_geo(plan->T, plan->H));
+    void* img[2] = {wimg0, wimg1};
+    for (int ph = 0; ph < 2; ++ph) {
+        const int64_t total = d.wimg_bytes[ph] / 2;
+        pack_dg1_w_kernel<<<grid_of(total), 256, 0, (cudaStream_t)stream>>>(w_l1, (uint16_t*)img[ph], ph, d.n_sh[ph], total);
+        if (int e = check_launch("tc_pack_dg1_w")) return e;
+    }
+    return 0;
+}
+
+// gy fp32 NCDHW (B, 128, T, Ho1, Wo1) -> padded planar dY of conv 1 (every cell written, halo zeros included)
+extern "C" int vd_tc_pack_dyp1(const float* gy, void* dyp, const vd_tc_plan* plan, int B, void* stream) {
+    VD_REQUIRE(gy && dyp && plan && geo_supported(plan->T, plan->H), "tc_pack_dyp1: bad argument");
+    if (B <= 0) return 0;
+    const Geo g = make_geo(plan->T, plan->H);
+    const Dg1Geo d = make_dg1_geo(g);
+    const int64_t total = (int64_t)B * (d.video_bytes / 16);
+    pack_dyp1_kernel<<<grid_of(total), 256, 0, (cudaStream_t)stream>>>(gy, (uint4*)dyp, total, d, g.T);
+    return check_launch("tc_pack_dyp1");
 }

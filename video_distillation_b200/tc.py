@@ -42,6 +42,11 @@ class TcConvNet3D:
         self._bwd_ready = False
         self._fp32_w = None
         self.bwd_chunk = 64
+        sz = (ctypes.c_int64 * 3)()
+        _lib.check(_lib.lib().vd_tc_dgrad1_sizes(ctypes.byref(p), sz), 'vd_tc_dgrad1_sizes')
+        self.dyp1_bytes_per_video = int(sz[0])
+        self.dg1_w = (torch.empty(int(sz[1]), **u8), torch.empty(int(sz[2]), **u8))   # direct conv-1 dgrad weight images
+        self.direct_dgrad1 = True          # False: column GEMM + col2im for conv 1 as for conv 0 / conv 2
         self._ws = {}
         self.b0 = self.b1 = self.b2 = None
         self._x0 = None
@@ -68,13 +73,15 @@ class TcConvNet3D:
             _lib.check(_lib.lib().vd_tc_pack_weights_bwd(_lib.ptr(ws[0]), _lib.ptr(ws[1]), _lib.ptr(ws[2]),
                                                          _lib.ptr(self.wt0), _lib.ptr(self.wt1), _lib.ptr(self.wt2),
                                                          _lib.stream()), 'vd_tc_pack_weights_bwd')
+            _lib.check(_lib.lib().vd_tc_pack_dgrad1_weights(_lib.ptr(ws[1]), _lib.ptr(self.dg1_w[0]), _lib.ptr(self.dg1_w[1]),
+                                                            ctypes.byref(self.plan), _lib.stream()), 'vd_tc_pack_dgrad1_weights')
             self._bwd_ready = True
 
-    def _workspace(self, name, nbytes, dtype=torch.uint8):
+    def _workspace(self, name, nbytes, dtype=torch.uint8, zero=False):
         t = self._ws.get(name)
         n = nbytes // torch.empty((), dtype=dtype).element_size()
         if t is None or t.numel() < n:
-            t = torch.empty(n, dtype=dtype, device=self.device)
+            t = (torch.zeros if zero else torch.empty)(n, dtype=dtype, device=self.device)
             self._ws[name] = t
         return t
 
@@ -93,14 +100,23 @@ class TcConvNet3D:
             dy2 = self._workspace('dy2', n * p.dy2_bytes_per_video)
             dy1 = self._workspace('dy1', n * p.dy1_bytes_per_video)
             dy0 = self._workspace('dy0', n * p.dy0_bytes_per_video)
-            col = self._workspace('col', n * max(p.col0_bytes_per_video, p.col1_bytes_per_video, p.col2_bytes_per_video))
+            col_per = max(p.col0_bytes_per_video, p.col2_bytes_per_video, 0 if self.direct_dgrad1 else p.col1_bytes_per_video)
+            col = self._workspace('col', n * col_per)
             st = _lib.stream()
             plan = ctypes.byref(p)
             _lib.check(lib.vd_tc_bwd_emb(_lib.ptr(g_emb[s:e]), _lib.ptr(c2[s:e]), _lib.ptr(dy2), plan, n, st), 'vd_tc_bwd_emb')
             _lib.check(lib.vd_tc_bwd_gemm(2, _lib.ptr(dy2), _lib.ptr(self.wt2), _lib.ptr(col), plan, n, st), 'vd_tc_bwd_gemm(2)')
-            _lib.check(lib.vd_tc_bwd_col2im(2, _lib.ptr(col), _lib.ptr(c1[s:e]), _lib.ptr(dy1), plan, n, st), 'vd_tc_bwd_col2im(2)')
-            _lib.check(lib.vd_tc_bwd_gemm(1, _lib.ptr(dy1), _lib.ptr(self.wt1), _lib.ptr(col), plan, n, st), 'vd_tc_bwd_gemm(1)')
-            _lib.check(lib.vd_tc_bwd_col2im(1, _lib.ptr(col), _lib.ptr(c0[s:e]), _lib.ptr(dy0), plan, n, st), 'vd_tc_bwd_col2im(1)')
+            if self.direct_dgrad1:
+                # conv 1: column-free dgrad (shifted-window GEMM per row parity) over the padded planar dY of conv 1,
+                # routing of conv 0 fused into its epilogue -> packed dY of conv 0
+                dyp1 = self._workspace('dyp1', n * self.dyp1_bytes_per_video, zero=True)     # halo cells stay zero
+                _lib.check(lib.vd_tc_bwd_col2im_ex(2, _lib.ptr(col), _lib.ptr(c1[s:e]), _lib.ptr(dyp1), plan, n, 1, st), 'vd_tc_bwd_col2im_ex(2)')
+                _lib.check(lib.vd_tc_dgrad1(_lib.ptr(dyp1), _lib.ptr(self.dg1_w[0]), _lib.ptr(self.dg1_w[1]), _lib.ptr(c0[s:e]),
+                                            _lib.ptr(dy0), plan, n, st), 'vd_tc_dgrad1')
+            else:
+                _lib.check(lib.vd_tc_bwd_col2im(2, _lib.ptr(col), _lib.ptr(c1[s:e]), _lib.ptr(dy1), plan, n, st), 'vd_tc_bwd_col2im(2)')
+                _lib.check(lib.vd_tc_bwd_gemm(1, _lib.ptr(dy1), _lib.ptr(self.wt1), _lib.ptr(col), plan, n, st), 'vd_tc_bwd_gemm(1)')
+                _lib.check(lib.vd_tc_bwd_col2im(1, _lib.ptr(col), _lib.ptr(c0[s:e]), _lib.ptr(dy0), plan, n, st), 'vd_tc_bwd_col2im(1)')
             _lib.check(lib.vd_tc_bwd_gemm(0, _lib.ptr(dy0), _lib.ptr(self.wt0), _lib.ptr(col), plan, n, st), 'vd_tc_bwd_gemm(0)')
             _lib.check(lib.vd_tc_bwd_col2im(0, _lib.ptr(col), None, _lib.ptr(dvideo[s:e]), plan, n, st), 'vd_tc_bwd_col2im(0)')
         return dvideo

@@ -28,6 +28,7 @@ class TcTrio:
             (128, 128, (p.T2p, p.H2p, p.W2p)),
         ]
         self._ws = {}
+        self.direct_dgrad1 = True
 
     # ------------------------------------------------------------------ helpers
     def layer_of(self, cin, cout, extent):
@@ -91,6 +92,18 @@ class TcTrio:
     def dgrad(self, layer, gy, w):
         p, lib, B = self.plan, _lib.lib(), int(gy.shape[0])
         cin, cout, ext = self.layers[layer]
+        if layer == 1 and self.direct_dgrad1:
+            # column-free dgrad of conv 1 (tc_layout.h: Dg1Geo): fp32 accumulators go straight to the NCDHW gradient
+            sz = (ctypes.c_int64 * 3)()
+            _lib.check(lib.vd_tc_dgrad1_sizes(ctypes.byref(p), sz), 'vd_tc_dgrad1_sizes')
+            w0, w1 = self._buf('dg1_w0', sz[1]), self._buf('dg1_w1', sz[2])
+            dyp = self._buf('dyp1', B * sz[0])
+            plan, st = ctypes.byref(p), _lib.stream()
+            _lib.check(lib.vd_tc_pack_dgrad1_weights(_lib.ptr(w), _lib.ptr(w0), _lib.ptr(w1), plan, st), 'vd_tc_pack_dgrad1_weights')
+            _lib.check(lib.vd_tc_pack_dyp1(_lib.ptr(gy), _lib.ptr(dyp), plan, B, st), 'vd_tc_pack_dyp1')
+            gx = torch.empty(B, cin, *ext, dtype=torch.float32, device=self.device)
+            _lib.check(lib.vd_tc_dgrad1(_lib.ptr(dyp), _lib.ptr(w0), _lib.ptr(w1), None, _lib.ptr(gx), plan, B, st), 'vd_tc_dgrad1')
+            return gx
         wt = self._buf(f'wt{layer}', (p.wt0_bytes, p.wt1_bytes, p.wt2_bytes)[layer])
         ws = [None, None, None]
         imgs = [None, None, None]
