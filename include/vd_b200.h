@@ -225,7 +225,10 @@ int vd_tc_pack_video_ncdhw(const float* x, void* x0, const vd_tc_plan* plan, int
 int vd_tc_pack_weights_part(const float* w_l0, const float* w_l1, const float* w_l2, void* w0, void* w1, void* w2,
                             int part, void* stream);
 int vd_tc_pack_dy(int layer, const float* gy, void* dy, const vd_tc_plan* plan, int B, void* stream);
-int vd_tc_bwd_col2im_plain(int layer, const void* col, float* gx, const vd_tc_plan* plan, int B, void* stream);
+/* col_fp32: the column buffer is fp32 (written by vd_tc_bwd_gemm_ex(..., col_fp32 = 1)) instead of bf16 */
+int vd_tc_bwd_col2im_plain(int layer, const void* col, float* gx, const vd_tc_plan* plan, int B, int col_fp32, void* stream);
+int vd_tc_bwd_gemm_ex(int layer, const void* dy, const void* wt, void* col, const vd_tc_plan* plan, int B, int col_fp32,
+                      void* stream);
 /* out[0] split-K slices, out[1] stages per slice, out[2] column tiles, out[3] xcol bytes, out[4] gyimg bytes, out[5] raw bytes */
 int vd_tc_wgrad_plan(int layer, const vd_tc_plan* plan, int B, int64_t* out);
 int vd_tc_wgrad_pack(int layer, const float* x, const float* gy, void* xcol, void* gyimg, const vd_tc_plan* plan,

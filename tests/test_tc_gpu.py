@@ -273,6 +273,6 @@ def test_tensor_core_trio_matches_fp32_kernels(T, HW):
             ops.set_conv_backend(prev)
         assert y.shape == y_ref.shape and gx.shape == gx_ref.shape and gw.shape == gw_ref.shape
         assert rel(y, y_ref) < 1e-5, (layer, 'fprop', rel(y, y_ref))
-        # conv 1: column-free dgrad, fp32 accumulators straight to the output; conv 0 / 2: bf16 column buffer
-        assert rel(gx, gx_ref) < (1e-5 if layer == 1 else 5e-3), (layer, 'dgrad', rel(gx, gx_ref))
+        # conv 1: column-free dgrad, fp32 accumulators straight to the output; conv 0 / 2: fp32 column buffers
+        assert rel(gx, gx_ref) < 1e-5, (layer, 'dgrad', rel(gx, gx_ref))
         assert rel(gw, gw_ref) < 1e-5, (layer, 'wgrad', rel(gw, gw_ref))

@@ -18,7 +18,8 @@ def declare(lib):
         'vd_tc_pack_video_ncdhw': (c_int, [P, P, POINTER(TcPlan), c_int, c_int, P]),
         'vd_tc_pack_weights_part': (c_int, [P, P, P, P, P, P, c_int, P]),
         'vd_tc_pack_dy': (c_int, [c_int, P, P, POINTER(TcPlan), c_int, P]),
-        'vd_tc_bwd_col2im_plain': (c_int, [c_int, P, P, POINTER(TcPlan), c_int, P]),
+        'vd_tc_bwd_col2im_plain': (c_int, [c_int, P, P, POINTER(TcPlan), c_int, c_int, P]),
+        'vd_tc_bwd_gemm_ex': (c_int, [c_int, P, P, P, POINTER(TcPlan), c_int, c_int, P]),
         'vd_tc_wgrad_plan': (c_int, [c_int, POINTER(TcPlan), c_int, POINTER(c_int64)]),
         'vd_tc_wgrad_pack': (c_int, [c_int, P, P, P, P, POINTER(TcPlan), c_int, P]),
         'vd_tc_wgrad_gemm': (c_int, [c_int, P, P, P, POINTER(TcPlan), c_int, P]),

@@ -92,21 +92,26 @@ __device__ __forceinline__ C2iBlock c2i_block(const BwdGeo& b, int band, int cib
     return k;
 }
 
+// column buffers are bf16 (throughput) or fp32 (accuracy modes of the conv trio)
+__device__ __forceinline__ float col_ld(const uint16_t* p) { return bf2f(*p); }
+__device__ __forceinline__ float col_ld(const float* p) { return *p; }
+
 // gather the (kh,kw) taps of input pixel (h,w) from the staged rows of one kt
-__device__ __forceinline__ float c2i_taps(const uint16_t* __restrict__ sm16, int pitch, const BwdGeo& b, int ho0, int h, int w) {
+template <typename T>
+__device__ __forceinline__ float c2i_taps(const T* __restrict__ sm16, int pitch, const BwdGeo& b, int ho0, int h, int w) {
     float acc = 0.f;
     for (int kh = (h + 1) & 1; kh < 7; kh += 2) {
         const int hh = h + 3 - kh;
         if (hh < 0) continue;
         const int ho = hh >> 1;
         if (ho >= b.Ho) continue;
-        const uint16_t* row = sm16 + (kh * 7) * pitch + (ho - ho0) * b.Wo;
+        const T* row = sm16 + (kh * 7) * pitch + (ho - ho0) * b.Wo;
         for (int kw = (w + 1) & 1; kw < 7; kw += 2) {
             const int ww = w + 3 - kw;
             if (ww < 0) continue;
             const int wo = ww >> 1;
             if (wo >= b.Wo) continue;
-            acc += bf2f(row[kw * pitch + wo]);
+            acc += col_ld(row + kw * pitch + wo);
         }
     }
     return acc;
@@ -118,15 +123,16 @@ __device__ __forceinline__ float c2i_taps(const uint16_t* __restrict__ sm16, int
 // pool window (pt x 2 x 2 conv outputs) of the next dY: the routed gradient at the recorded argmax,
 // zeros elsewhere -> dY below is fully overwritten, no memset needed.
 // layer 0 (code == nullptr): writes d video (B, T, 3, H, W) fp32.
-__global__ void __launch_bounds__(256) col2im_kernel(const uint16_t* __restrict__ colbuf, const uint8_t* __restrict__ code,
+template <typename T>
+__global__ void __launch_bounds__(256) col2im_kernel(const T* __restrict__ colbuf, const uint8_t* __restrict__ code,
                                                      void* __restrict__ out, BwdGeo b, BwdGeo bb, int pt, int band, int pitch, int cib,
                                                      int ncdhw, Dg1Geo dg, int padded_planar) {
     extern __shared__ uint32_t c2i_smem[];
     const C2iBlock k = c2i_block(b, band, cib);
-    const uint16_t* colv = colbuf + (int64_t)k.vid * b.col_video_elems;
+    const T* colv = colbuf + (int64_t)k.vid * b.col_video_elems;
+    T* smT = reinterpret_cast<T*>(c2i_smem);
     const int n_out = (k.h_end - k.hb) * b.Wi;
     const int n_all = cib * n_out;
-    const int np2 = k.npix >> 1, pitch2 = pitch >> 1;
     float acc[kC2iMaxOut];
 #pragma unroll
     for (int j = 0; j < kC2iMaxOut; ++j) acc[j] = 0.f;
@@ -135,14 +141,13 @@ __global__ void __launch_bounds__(256) col2im_kernel(const uint16_t* __restrict_
         if ((unsigned)to >= (unsigned)b.To) continue;                 // block-uniform
         __syncthreads();
         const int pix0 = (to * b.Ho + k.ho0) * b.Wo;
-        for (int i = threadIdx.x; i < cib * 49 * np2; i += blockDim.x) {
-            const int row = i / np2, j = i - row * np2;              // row = ci_local * 49 + tap
+        for (int i = threadIdx.x; i < cib * 49 * k.npix; i += blockDim.x) {
+            const int row = i / k.npix, j = i - row * k.npix;        // row = ci_local * 49 + tap
             const int cl = row / 49, tap = row - cl * 49;
             const int r = (k.ci0 + cl) * 147 + kt * 49 + tap;
-            const int pix = pix0 + 2 * j;
+            const int pix = pix0 + j;
             const int nt = (int)__umulhi((uint32_t)pix, b.nc_magic), col = pix - nt * b.NC;
-            c2i_smem[row * pitch2 + j] = __ldg(reinterpret_cast<const uint32_t*>(
-                colv + (((int64_t)nt * b.NU + (r >> 7)) * 128 + (r & 127)) * b.NC + col));
+            smT[row * pitch + j] = __ldg(colv + (((int64_t)nt * b.NU + (r >> 7)) * 128 + (r & 127)) * b.NC + col);
         }
         __syncthreads();
 #pragma unroll
@@ -151,7 +156,7 @@ __global__ void __launch_bounds__(256) col2im_kernel(const uint16_t* __restrict_
             if (i < n_all) {
                 const int cl = i / n_out, o = i - cl * n_out;
                 const int hl = o / b.Wi, w = o - hl * b.Wi;
-                acc[j] += c2i_taps(reinterpret_cast<const uint16_t*>(c2i_smem) + cl * 49 * pitch, pitch, b, k.ho0, k.hb + hl, w);
+                acc[j] += c2i_taps<T>(smT + cl * 49 * pitch, pitch, b, k.ho0, k.hb + hl, w);
             }
         }
     }
@@ -206,23 +211,23 @@ __device__ __forceinline__ void cp_async(uint32_t dst_smem, const void* src) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-template <int SEG, int PAR>
-__device__ __forceinline__ void c2i_row_taps(float (&acc)[SEG], const uint16_t* __restrict__ sm16, int pitch, const BwdGeo& b,
+template <int SEG, int PAR, typename T>
+__device__ __forceinline__ void c2i_row_taps(float (&acc)[SEG], const T* __restrict__ sm16, int pitch, const BwdGeo& b,
                                              int ho0, int h, int seg, bool l_ok, bool r_ok) {
     for (int kh = (h + 1) & 1; kh < 7; kh += 2) {
         const int hh = h + 3 - kh;
         if (hh < 0) continue;
         const int ho = hh >> 1;
         if (ho >= b.Ho) continue;
-        const uint16_t* row = sm16 + (kh * 7) * pitch + (ho - ho0) * b.Wo + seg * SEG;
+        const T* row = sm16 + (kh * 7) * pitch + (ho - ho0) * b.Wo + seg * SEG;
 #pragma unroll
         for (int kw = (PAR + 1) & 1; kw < 7; kw += 2) {
             const int s = (PAR + 3 - kw) / 2;                                   // PAR+3-kw is even: exact, in {2,1,0,-1}
-            const uint16_t* src = row + kw * pitch + s;
+            const T* src = row + kw * pitch + s;
 #pragma unroll
             for (int j = 0; j < SEG; ++j) {
                 const bool ok = (j + s < 0) ? l_ok : ((j + s >= SEG) ? r_ok : true);
-                if (ok) acc[j] += bf2f(src[j]);
+                if (ok) acc[j] += col_ld(src + j);
             }
         }
     }
@@ -231,16 +236,16 @@ __device__ __forceinline__ void c2i_row_taps(float (&acc)[SEG], const uint16_t* 
 // Block = `lanes_ch` channel lanes of `tpc` threads; lane c walks channels ci0 + c, ci0 + c + lanes_ch, ... of the
 // block's `cib` channels with private staging buffers and its own named barrier, so that the lanes' staging
 // latencies and tap sums interleave (the SM always has many warps to issue from).
-template <int SEG, int V>
-__global__ void __launch_bounds__(512) col2im_rows_kernel(const uint16_t* __restrict__ colbuf, const uint8_t* __restrict__ code,
+template <int SEG, int V, typename T>
+__global__ void __launch_bounds__(512) col2im_rows_kernel(const T* __restrict__ colbuf, const uint8_t* __restrict__ code,
                                                           void* __restrict__ out, BwdGeo b, BwdGeo bb, int pt, int band, int pitch,
                                                           int warps_per_par, int cib, int lanes_ch, int nbuf, int stash_off, int ncdhw) {
     // shared memory: lanes_ch * nbuf staging buffers [49][pitch] bf16, then (route mode) the stash
     // [cib][n_out] u32 = bf16 << 16 | argmax
     extern __shared__ uint32_t c2i_smem[];
     const C2iBlock k = c2i_block(b, band, cib);
-    const uint16_t* colv = colbuf + (int64_t)k.vid * b.col_video_elems;
-    const uint16_t* sm16 = reinterpret_cast<const uint16_t*>(c2i_smem);
+    const T* colv = colbuf + (int64_t)k.vid * b.col_video_elems;
+    const T* sm16 = reinterpret_cast<const T*>(c2i_smem);
     uint32_t* stash = c2i_smem + stash_off;
     const uint32_t sm_base = smem_u32(c2i_smem);
     const int stage_elems = 49 * pitch;
@@ -272,15 +277,16 @@ __global__ void __launch_bounds__(512) col2im_rows_kernel(const uint16_t* __rest
         const int ci = k.ci0 + chl + (st / nkt) * lanes_ch, kt = kt_lo + st % nkt;
         const int to = k.t + 1 - kt;
         const int pix0 = (to * b.Ho + k.ho0) * b.Wo;
-        const uint32_t buf = sm_base + (uint32_t)((chl * nbuf + st % nbuf) * stage_elems) * 2u;
+        constexpr uint32_t ES = (uint32_t)sizeof(T);
+        const uint32_t buf = sm_base + (uint32_t)((chl * nbuf + st % nbuf) * stage_elems) * ES;
         for (int tap = warp; tap < 49; tap += nwarp) {
             const int r = ci * 147 + kt * 49 + tap;
-            const uint16_t* rbase = colv + ((int64_t)(r >> 7) * 128 + (r & 127)) * b.NC;
-            const uint32_t dst = buf + (uint32_t)(tap * pitch) * 2u;
+            const T* rbase = colv + ((int64_t)(r >> 7) * 128 + (r & 127)) * b.NC;
+            const uint32_t dst = buf + (uint32_t)(tap * pitch) * ES;
             for (int j = lane; j < nvec; j += 32) {
                 const int pix = pix0 + j * V;
                 const int nt = (int)__umulhi((uint32_t)pix, b.nc_magic), col = pix - nt * b.NC;
-                cp_async<2 * V>(dst + (uint32_t)j * (2u * V), rbase + nt * tile_pitch + col);
+                cp_async<(int)ES * V>(dst + (uint32_t)j * (ES * V), rbase + nt * tile_pitch + col);
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -297,9 +303,9 @@ __global__ void __launch_bounds__(512) col2im_rows_kernel(const uint16_t* __rest
         }
         lane_sync();
         if (active) {
-            const uint16_t* buf16 = sm16 + (chl * nbuf + st % nbuf) * stage_elems;
-            if (par == 0) c2i_row_taps<SEG, 0>(acc, buf16, pitch, b, k.ho0, h, seg, l_ok, r_ok);
-            else c2i_row_taps<SEG, 1>(acc, buf16, pitch, b, k.ho0, h, seg, l_ok, r_ok);
+            const T* buf16 = sm16 + (chl * nbuf + st % nbuf) * stage_elems;
+            if (par == 0) c2i_row_taps<SEG, 0, T>(acc, buf16, pitch, b, k.ho0, h, seg, l_ok, r_ok);
+            else c2i_row_taps<SEG, 1, T>(acc, buf16, pitch, b, k.ho0, h, seg, l_ok, r_ok);
             if (st % nkt == nkt - 1) {                                // last temporal tap of this channel
                 const int cl = chl + (st / nkt) * lanes_ch, ci = k.ci0 + cl;
                 if (code == nullptr) {
@@ -388,7 +394,9 @@ extern "C" int vd_tc_bwd_emb(const float* g_emb, const uint8_t* code2, void* dy2
 // mode 0: route with code_below into the packed dY of the layer below (layers 1,2) / d video (B,T,3,H,W) (layer 0)
 // mode 1: plain fp32 NCDHW gradient (B, Cin, Ti, Hi, Wi) for any layer (dgrad of the differentiable conv trio)
 static int col2im_launch(int layer, const void* col, const uint8_t* code_below, void* out, const vd_tc_plan* plan, int B,
-                         void* stream, int ncdhw, int padded_planar = 0) {
+                         void* stream, int ncdhw, int padded_planar = 0, int col_fp32 = 0) {
+    VD_REQUIRE(!col_fp32 || ncdhw, "tc_bwd_col2im: fp32 column buffers exist for the plain (NCDHW fp32) output only");
+    const int ES = col_fp32 ? 4 : 2;
     VD_REQUIRE(!padded_planar || (layer == 2 && !ncdhw), "tc_bwd_col2im: the padded planar output exists for layer 2 (dY of conv 1) only");
     VD_REQUIRE(col && out && plan, "tc_bwd_col2im: NULL pointer");
     VD_REQUIRE(layer >= 0 && layer <= 2, "tc_bwd_col2im: bad layer");
@@ -405,12 +413,15 @@ static int col2im_launch(int layer, const void* col, const uint8_t* code_below, 
     const int n_ho = (band + 2) / 2 + 2;
     const int npix_max = (n_ho < b.Ho ? n_ho : b.Ho) * b.Wo;
     const int pitch = ((npix_max + 7) / 8 * 8) | 8;       // bf16 elements per staged row: 16-byte aligned rows, odd multiple of 16 B
-    const size_t stage_bytes = (size_t)49 * pitch * 2;
+    const size_t stage_bytes = (size_t)49 * pitch * ES;
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(col2im_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-#define VD_C2I_ATTR(S_, V_) cudaFuncSetAttribute(col2im_rows_kernel<S_, V_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)
-        VD_C2I_ATTR(7, 8); VD_C2I_ATTR(7, 4); VD_C2I_ATTR(7, 2); VD_C2I_ATTR(8, 8); VD_C2I_ATTR(8, 4); VD_C2I_ATTR(8, 2);
+        cudaFuncSetAttribute(col2im_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        cudaFuncSetAttribute(col2im_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+#define VD_C2I_ATTR(S_, V_, T_) cudaFuncSetAttribute(col2im_rows_kernel<S_, V_, T_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)
+        VD_C2I_ATTR(7, 8, uint16_t); VD_C2I_ATTR(7, 4, uint16_t); VD_C2I_ATTR(7, 2, uint16_t);
+        VD_C2I_ATTR(8, 8, uint16_t); VD_C2I_ATTR(8, 4, uint16_t); VD_C2I_ATTR(8, 2, uint16_t);
+        VD_C2I_ATTR(7, 4, float); VD_C2I_ATTR(7, 2, float); VD_C2I_ATTR(8, 4, float); VD_C2I_ATTR(8, 2, float);
 #undef VD_C2I_ATTR
         configured = true;
     }
@@ -427,7 +438,7 @@ static int col2im_launch(int layer, const void* col, const uint8_t* code_below, 
     // chunk) per block on 4 concurrent channel lanes
     const int half = b.Wi / 2;
     const int SEG = (b.Wi % 2 == 0 && half % 7 == 0) ? 7 : ((b.Wi % 2 == 0 && half % 8 == 0) ? 8 : 0);
-    int V = 8;
+    int V = col_fp32 ? 4 : 8;                                        // elements per 16-byte cp.async
     const int align_unit = (nb == 1) ? b.Ho * b.Wo : b.Wo;           // pix0 and npix are multiples of this
     while (V > 1 && (align_unit % V != 0 || b.NC % V != 0)) V >>= 1;
     const int per_par = SEG ? (band * (half / SEG) + 31) / 32 : 0;   // warps per column parity
@@ -444,9 +455,12 @@ static int col2im_launch(int layer, const void* col, const uint8_t* code_below, 
         VD_REQUIRE(blocks < (1ll << 31), "tc_bwd_col2im: grid too large");
         const int stash_off = (int)(lanes_ch * nbuf * stage_bytes / 4);
         const int threads = lanes_ch * tpc;
-#define VD_C2I(S_, V_) col2im_rows_kernel<S_, V_><<<(unsigned)blocks, threads, smem, s>>>((const uint16_t*)col, cd, out, b, bb, pt, band, pitch, per_par, cib, lanes_ch, nbuf, stash_off, ncdhw)
-        if (SEG == 7) { if (V == 8) VD_C2I(7, 8); else if (V == 4) VD_C2I(7, 4); else VD_C2I(7, 2); }
-        else { if (V == 8) VD_C2I(8, 8); else if (V == 4) VD_C2I(8, 4); else VD_C2I(8, 2); }
+#define VD_C2I(S_, V_, T_) col2im_rows_kernel<S_, V_, T_><<<(unsigned)blocks, threads, smem, s>>>((const T_*)col, cd, out, b, bb, pt, band, pitch, per_par, cib, lanes_ch, nbuf, stash_off, ncdhw)
+        if (col_fp32) {
+            if (SEG == 7) { if (V == 4) VD_C2I(7, 4, float); else VD_C2I(7, 2, float); }
+            else { if (V == 4) VD_C2I(8, 4, float); else VD_C2I(8, 2, float); }
+        } else if (SEG == 7) { if (V == 8) VD_C2I(7, 8, uint16_t); else if (V == 4) VD_C2I(7, 4, uint16_t); else VD_C2I(7, 2, uint16_t); }
+        else { if (V == 8) VD_C2I(8, 8, uint16_t); else if (V == 4) VD_C2I(8, 4, uint16_t); else VD_C2I(8, 2, uint16_t); }
 #undef VD_C2I
         return check_launch("tc_bwd_col2im_rows");
     }
@@ -457,8 +471,10 @@ static int col2im_launch(int layer, const void* col, const uint8_t* code_below, 
     VD_REQUIRE(smem <= 96 * 1024, "tc_bwd_col2im: staging buffer too large (%zu bytes)", smem);
     const int64_t blocks = (int64_t)B * (b.Cin / cib) * b.Ti * nb;
     VD_REQUIRE(blocks < (1ll << 31), "tc_bwd_col2im: grid too large");
-    col2im_kernel<<<(unsigned)blocks, 256, smem, s>>>((const uint16_t*)col, cd, out, b, bb, pt, band, pitch, cib, ncdhw,
-                                                      make_dg1_geo(g), padded_planar);
+    if (col_fp32) col2im_kernel<float><<<(unsigned)blocks, 256, smem, s>>>((const float*)col, cd, out, b, bb, pt, band, pitch, cib, ncdhw,
+                                                                            make_dg1_geo(g), padded_planar);
+    else col2im_kernel<uint16_t><<<(unsigned)blocks, 256, smem, s>>>((const uint16_t*)col, cd, out, b, bb, pt, band, pitch, cib, ncdhw,
+                                                                    make_dg1_geo(g), padded_planar);
     return check_launch("tc_bwd_col2im");
 }
 
@@ -474,6 +490,7 @@ extern "C" int vd_tc_bwd_col2im_ex(int layer, const void* col, const uint8_t* co
     return col2im_launch(layer, col, code_below, out, plan, B, stream, 0, out_layout);
 }
 
-extern "C" int vd_tc_bwd_col2im_plain(int layer, const void* col, float* gx, const vd_tc_plan* plan, int B, void* stream) {
-    return col2im_launch(layer, col, nullptr, gx, plan, B, stream, 1);
+extern "C" int vd_tc_bwd_col2im_plain(int layer, const void* col, float* gx, const vd_tc_plan* plan, int B, int col_fp32,
+                                      void* stream) {
+    return col2im_launch(layer, col, nullptr, gx, plan, B, stream, 1, 0, col_fp32);
 }

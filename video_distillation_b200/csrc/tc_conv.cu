@@ -802,7 +802,7 @@ static int setup_l2(WsParams& p, const Geo& g, int B, uint32_t* smem) {
     return finalize_smem(p, (uint32_t)p.G * p.RW * kWeightTileBytes, smem);
 }
 
-static int setup_bwd(WsParams& p, const Geo& g, int layer, int B, uint32_t* smem) {
+static int setup_bwd(WsParams& p, const Geo& g, int layer, int B, uint32_t* smem, bool fp32_out = false) {
     const BwdGeo b = make_bwd_geo(g, layer);
     VD_REQUIRE(b.pixels % 16 == 0, "tc bwd: pixel count must be a multiple of 16");
     // enough CTA tiles for two waves even at small B: split the NU row tiles of a pixel stage over ug_count CTAs
@@ -824,7 +824,7 @@ static int setup_bwd(WsParams& p, const Geo& g, int layer, int B, uint32_t* smem
     p.n_acc = 1; p.acc_delta16 = 0;
     p.ncols = b.NC; p.acc_cols = 256; p.acc_stages = 2;
     p.idesc = umma_idesc_bf16(128, b.NC);
-    return finalize_smem(p, (uint32_t)p.G * p.RW * kWeightTileBytes, smem, false);
+    return finalize_smem(p, (uint32_t)p.G * p.RW * kWeightTileBytes, smem, fp32_out);     // fp32 columns: transposed coalesced stores
 }
 
 template <int EPI, int NACC>
@@ -962,8 +962,22 @@ extern "C" int vd_tc_debug_params(int layer, const vd_tc_plan* plan, int B, int6
     return 0;
 }
 
+static int bwd_gemm_impl(int layer, const void* dy, const void* wt, void* col, const vd_tc_plan* plan, int B, int col_fp32,
+                         void* stream);
+
 extern "C" int vd_tc_bwd_gemm(int layer, const void* dy, const void* wt, void* col, const vd_tc_plan* plan,
                               int B, void* stream) {
+    return bwd_gemm_impl(layer, dy, wt, col, plan, B, 0, stream);
+}
+
+// col_fp32 != 0: fp32 column buffer (twice the traffic; the accuracy modes of the conv trio)
+extern "C" int vd_tc_bwd_gemm_ex(int layer, const void* dy, const void* wt, void* col, const vd_tc_plan* plan,
+                                 int B, int col_fp32, void* stream) {
+    return bwd_gemm_impl(layer, dy, wt, col, plan, B, col_fp32, stream);
+}
+
+static int bwd_gemm_impl(int layer, const void* dy, const void* wt, void* col, const vd_tc_plan* plan, int B, int col_fp32,
+                         void* stream) {
     VD_REQUIRE(plan && dy && wt && col, "tc_bwd_gemm: NULL pointer");
     VD_REQUIRE(layer >= 0 && layer <= 2 && B >= 0, "tc_bwd_gemm: bad layer / batch");
     VD_REQUIRE(geo_supported(plan->T, plan->H), "tc_bwd_gemm: unsupported geometry");
@@ -972,9 +986,9 @@ extern "C" int vd_tc_bwd_gemm(int layer, const void* dy, const void* wt, void* c
     memset(&p, 0, sizeof(p));
     const Geo g = make_geo(plan->T, plan->H);
     uint32_t smem = 0;
-    if (int rc = setup_bwd(p, g, layer, B, &smem)) return rc;
+    if (int rc = setup_bwd(p, g, layer, B, &smem, col_fp32 != 0)) return rc;
     p.pix = (const uint8_t*)dy; p.wimg = (const uint8_t*)wt; p.item_index = nullptr;
-    p.epi.raw = (float*)col; p.epi.raw_bf16 = 1; p.epi.T = plan->T; p.epi.n_items = B; p.epi.g = g;
+    p.epi.raw = (float*)col; p.epi.raw_bf16 = col_fp32 ? 0 : 1; p.epi.T = plan->T; p.epi.n_items = B; p.epi.g = g;
     return launch<EPI_RAW>(p, smem, (cudaStream_t)stream);
 }
 

@@ -29,6 +29,7 @@ class TcTrio:
         ]
         self._ws = {}
         self.direct_dgrad1 = True
+        self.col_fp32 = True
 
     # ------------------------------------------------------------------ helpers
     def layer_of(self, cin, cout, extent):
@@ -111,12 +112,13 @@ class TcTrio:
         _lib.check(lib.vd_tc_pack_weights_bwd(_lib.ptr(ws[0]), _lib.ptr(ws[1]), _lib.ptr(ws[2]), _lib.ptr(imgs[0]), _lib.ptr(imgs[1]),
                                               _lib.ptr(imgs[2]), _lib.stream()), 'vd_tc_pack_weights_bwd')
         dy = self._buf('dy', B * (p.dy0_bytes_per_video, p.dy1_bytes_per_video, p.dy2_bytes_per_video)[layer])
-        col = self._buf('col', B * (p.col0_bytes_per_video, p.col1_bytes_per_video, p.col2_bytes_per_video)[layer])
+        f32 = 1 if self.col_fp32 else 0      # fp32 column buffers: no bf16 rounding between the GEMM and the tap sum
+        col = self._buf('col', B * (p.col0_bytes_per_video, p.col1_bytes_per_video, p.col2_bytes_per_video)[layer] * (2 if f32 else 1))
         plan, st = ctypes.byref(p), _lib.stream()
         _lib.check(lib.vd_tc_pack_dy(layer, _lib.ptr(gy), _lib.ptr(dy), plan, B, st), 'vd_tc_pack_dy')
-        _lib.check(lib.vd_tc_bwd_gemm(layer, _lib.ptr(dy), _lib.ptr(wt), _lib.ptr(col), plan, B, st), 'vd_tc_bwd_gemm')
+        _lib.check(lib.vd_tc_bwd_gemm_ex(layer, _lib.ptr(dy), _lib.ptr(wt), _lib.ptr(col), plan, B, f32, st), 'vd_tc_bwd_gemm_ex')
         gx = torch.empty(B, cin, *ext, dtype=torch.float32, device=self.device)
-        _lib.check(lib.vd_tc_bwd_col2im_plain(layer, _lib.ptr(col), _lib.ptr(gx), plan, B, st), 'vd_tc_bwd_col2im_plain')
+        _lib.check(lib.vd_tc_bwd_col2im_plain(layer, _lib.ptr(col), _lib.ptr(gx), plan, B, f32, st), 'vd_tc_bwd_col2im_plain')
         return gx
 
     def wgrad(self, layer, x, gy):
