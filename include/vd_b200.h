@@ -252,6 +252,20 @@ int vd_tc_bwd_col2im_ex(int layer, const void* col, const uint8_t* code_below, v
                         int out_layout, void* stream);
 int vd_tc_dgrad1(const void* dyp, const void* wimg0, const void* wimg1, const uint8_t* code0, void* out,
                  const vd_tc_plan* plan, int B, void* stream);
+/* out_planar != 0: the routed gradient goes to the padded planar dY of conv 0 (input of vd_tc_dgrad0; halo pre-zeroed) */
+int vd_tc_dgrad1_ex(const void* dyp, const void* wimg0, const void* wimg1, const uint8_t* code0, void* out,
+                    const vd_tc_plan* plan, int B, int out_planar, void* stream);
+
+/* ---- direct dgrad of conv 0 (Cin = 3): pixels on M (128 per tile), the 12 (ci, row parity, column parity) outputs on
+ * N = 16, resident 96 KiB weight image; replaces vd_tc_bwd_gemm(0) + vd_tc_bwd_col2im(0) (51 MB of columns per video).
+ *   vd_tc_dgrad0_sizes        out[0] dYP0 bytes per video, out[1] weight image bytes
+ *   vd_tc_pack_dgrad0_weights fp32 OIDHW weights of features.0 -> weight image
+ *   vd_tc_pack_dyp0           fp32 NCDHW gy (B,64,T,Ho0,Wo0) -> dYP0 (every cell written)
+ *   vd_tc_dgrad0              out = fp32 gradient w.r.t. the input video, (B,T,3,H,W) (ncdhw = 0) or (B,3,T,H,W) */
+int vd_tc_dgrad0_sizes(const vd_tc_plan* plan, int64_t* out);
+int vd_tc_pack_dgrad0_weights(const float* w_l0, void* wimg, void* stream);
+int vd_tc_pack_dyp0(const float* gy, void* dyp, const vd_tc_plan* plan, int B, void* stream);
+int vd_tc_dgrad0(const void* dyp0, const void* wimg, float* out, const vd_tc_plan* plan, int B, int ncdhw, void* stream);
 
 /* Tuning probe (tests/bring-up only): issues 148 x n_sa x n_steps x n_acc MMAs of N=ncols with the
  * given descriptor words over dummy operands (pix >= 64 KiB, wimg >= 16 KiB, raw >= 148*n_acc*128*ncols

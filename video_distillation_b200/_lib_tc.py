@@ -29,6 +29,11 @@ def declare(lib):
         'vd_tc_pack_dyp1': (c_int, [P, P, POINTER(TcPlan), c_int, P]),
         'vd_tc_bwd_col2im_ex': (c_int, [c_int, P, P, P, POINTER(TcPlan), c_int, c_int, P]),
         'vd_tc_dgrad1': (c_int, [P, P, P, P, P, POINTER(TcPlan), c_int, P]),
+        'vd_tc_dgrad1_ex': (c_int, [P, P, P, P, P, POINTER(TcPlan), c_int, c_int, P]),
+        'vd_tc_dgrad0_sizes': (c_int, [POINTER(TcPlan), POINTER(c_int64)]),
+        'vd_tc_pack_dgrad0_weights': (c_int, [P, P, P]),
+        'vd_tc_pack_dyp0': (c_int, [P, P, POINTER(TcPlan), c_int, P]),
+        'vd_tc_dgrad0': (c_int, [P, P, P, POINTER(TcPlan), c_int, c_int, P]),
         'vd_tc_probe': (c_int, [P, P, P, c_int, c_int, c_int, c_uint32, c_uint32, c_uint32, c_uint32, c_uint32, c_int, P]),
         'vd_tc_mma_rate': (c_int, [P, c_int, c_int, c_int, c_uint32, c_uint32, c_uint32, c_int, c_int, c_int, P]),
         'vd_tc_set_profile_buffer': (c_int, [P]),

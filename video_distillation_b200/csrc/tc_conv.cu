@@ -24,7 +24,7 @@ constexpr int kMaxSteps = 64;
 constexpr int kMaxCopies = 8;
 constexpr int kThreads = 256;
 
-enum EpiMode { EPI_RAW = 0, EPI_L0 = 1, EPI_L1 = 2, EPI_L2 = 3, EPI_PLAIN = 4, EPI_DG1 = 5 };
+enum EpiMode { EPI_RAW = 0, EPI_L0 = 1, EPI_L1 = 2, EPI_L2 = 3, EPI_PLAIN = 4, EPI_DG1 = 5, EPI_DG0 = 6 };
 
 struct EpiParams {
     float* raw;            // EPI_RAW: [tile][u][acc][128][ncols]
@@ -36,6 +36,8 @@ struct EpiParams {
     int layer;             // EPI_PLAIN: which conv (tile -> NCDHW mapping)
     int accum;             // EPI_PLAIN: out += result (split-bf16 passes accumulate into the same fp32 tensor)
     int ph;                // EPI_DG1: input-row parity of this launch
+    int dy0_planar;        // EPI_DG1 (route mode): write the padded planar dY of conv 0 (Dg0Geo) instead of the column-GEMM operand
+    int ncdhw;             // EPI_DG0: output (B,3,T,H,W) instead of the video layout (B,T,3,H,W)
     BwdGeo bb;             // EPI_DG1 (route mode): geometry of the packed dY operand of conv 0's column GEMM
     int T;                 // frames of the video
     int n_items;           // videos (conv 2: valid videos, tiles may be partially filled)
@@ -79,6 +81,7 @@ struct WsParams {
     uint32_t smem_w_off, smem_pix_off;  // from the 1024-aligned dynamic smem base
     uint32_t smem_epi_off;              // != 0: 4 x 32 x 33 float transpose scratch for coalesced raw stores
     uint32_t smem_stash_off;            // != 0: conv-1 epilogue stash [H2*H2][kStashPitch] bf16 (quick accumulator drain)
+    int32_t swap_ab;                    // the staged pixels are the M operand and the weight tiles the N operand (conv-0 dgrad)
     int32_t dbg;                        // tuning experiments (VD_TC_DBG bitmask; results are garbage when set):
                                         //   1 no pixel copies, 2 no weight copies, 4 epilogue does no work
     long long* prof;                    // optional [grid][8] cycle counters of the MMA warp (tuning only)
@@ -439,6 +442,19 @@ __device__ __forceinline__ void epi_dg1(const WsParams& p, int tile, uint32_t ta
             const uint8_t cd = code[h * g.H1 + w];
             const uint16_t gv = f2bf((cd & 8) ? v[b] : 0.f);
             const int arg = cd & 7;
+            if (p.epi.dy0_planar) {
+                // padded planar dY of conv 0 (Dg0Geo): [t_pad][chunk 8][row ho+1][col wo+1][8 channels]
+                constexpr int PD0 = 64;                              // Dg0Geo::PD
+                const int RD0 = g.Ho0 + 4;                           // Dg0Geo::RD
+                const int64_t video0 = (int64_t)(g.T + 2) * 8 * RD0 * PD0 * 8;      // bf16 elements per video
+                uint16_t* pl = reinterpret_cast<uint16_t*>(p.epi.out) + (int64_t)item * video0 +
+                               ((((int64_t)(t + 1) * 8 + chunk) * RD0 + 2 * h + 1) * PD0 + 2 * w + 1) * 8 + e;
+                pl[0] = (arg == 0) ? gv : (uint16_t)0;
+                pl[8] = (arg == 1) ? gv : (uint16_t)0;
+                pl[PD0 * 8] = (arg == 2) ? gv : (uint16_t)0;
+                pl[PD0 * 8 + 8] = (arg == 3) ? gv : (uint16_t)0;
+                continue;
+            }
 #pragma unroll
             for (int dh = 0; dh < 2; ++dh) {
                 const int pix = (t * bb.Ho + 2 * h + dh) * bb.Wo + 2 * w;           // even: pix and pix+1 share a tile
@@ -448,6 +464,28 @@ __device__ __forceinline__ void epi_dg1(const WsParams& p, int tile, uint32_t ta
                 d[8] = (arg == 2 * dh + 1) ? gv : (uint16_t)0;
             }
         }
+    }
+}
+
+// direct dgrad of conv 0 (Dg0Geo): lane m = pixel ((a - a0)*PD + b), accumulator columns n = ci*4 + ph*2 + pw hold
+// dX0[ci, t, 2a+ph, 2b+pw]: the gradient w.r.t. the input video, fp32, (B,T,3,H,W) or (B,3,T,H,W).
+__device__ __forceinline__ void epi_dg0(const WsParams& p, int tile, uint32_t taddr, int m) {
+    const Geo& g = p.epi.g;
+    const int item = tile / p.tiles_per_item, sub = tile % p.tiles_per_item;
+    const int t = sub / p.v_count, rb = sub % p.v_count;
+    const int a = rb * 2 + (m >> 6), b = m & 63;
+    float v[16];
+    tmem_ld16(taddr, v);
+    tmem_ld_wait();
+    if (b >= g.Wo0 || a >= g.Ho0) return;
+    float* out = reinterpret_cast<float*>(p.epi.out);
+    const int64_t HW = (int64_t)g.HW * g.HW;
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci) {
+        const int64_t plane = p.epi.ncdhw ? ((int64_t)item * 3 + ci) * g.T + t : ((int64_t)item * g.T + t) * 3 + ci;
+        float* dst = out + plane * HW + (int64_t)(2 * a) * g.HW + 2 * b;
+        *reinterpret_cast<float2*>(dst) = make_float2(v[ci * 4 + 0], v[ci * 4 + 1]);
+        *reinterpret_cast<float2*>(dst + g.HW) = make_float2(v[ci * 4 + 2], v[ci * 4 + 3]);
     }
 }
 
@@ -599,13 +637,21 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
                             if (elect_one()) {
                                 const uint64_t* ta = resident ? tabA + sa * n_steps + j : tabA + wslot * G;
                                 const uint64_t* tb = tabB + ((int)pslot * n_steps + j) * NACC;
+                                if (p.swap_ab) {                    // pixels = M operand, weight tile = N operand (NACC == 1)
 #pragma unroll 4
-                                for (int jj = 0; jj < nst; ++jj) {
-                                    const uint64_t a_desc = ta[jj];
+                                    for (int jj = 0; jj < nst; ++jj) {
+                                        umma_bf16(d_base, tb[jj * NACC], ta[jj], idesc, accumulate);
+                                        accumulate = 1;
+                                    }
+                                } else {
+#pragma unroll 4
+                                    for (int jj = 0; jj < nst; ++jj) {
+                                        const uint64_t a_desc = ta[jj];
 #pragma unroll
-                                    for (int a = 0; a < NACC; ++a)
-                                        umma_bf16(d_base + (uint32_t)a * acc_cols, a_desc, tb[jj * NACC + a], idesc, accumulate);
-                                    accumulate = 1;
+                                        for (int a = 0; a < NACC; ++a)
+                                            umma_bf16(d_base + (uint32_t)a * acc_cols, a_desc, tb[jj * NACC + a], idesc, accumulate);
+                                        accumulate = 1;
+                                    }
                                 }
                                 if (!resident) umma_commit(BAR(w_empty, wslot));
                                 if (g == slots_per_stage - 1 && u == n_u_eff - 1) umma_commit(BAR(pix_empty, pslot));
@@ -647,6 +693,7 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
                     else if (EPI == EPI_L1) epi_l1_drain(p, tile, taddr, m, reinterpret_cast<uint16_t*>(base_ptr + p.smem_stash_off));
                     else if (EPI == EPI_PLAIN) epi_plain(p, tile, taddr, m);
                     else if (EPI == EPI_DG1) epi_dg1(p, tile, taddr, m);
+                    else if (EPI == EPI_DG0) epi_dg0(p, tile, taddr, m);
                     else epi_l2(p, tile, taddr, m);
                 }
                 tc_fence_before();
@@ -858,6 +905,8 @@ static int launch(const WsParams& p, uint32_t smem, cudaStream_t stream) {
         return launch_n<EPI_L2, 4>(p, smem, stream);
     } else if (EPI == EPI_DG1 && p.n_acc == 1) {
         return launch_n<EPI_DG1, 1>(p, smem, stream);
+    } else if (EPI == EPI_DG0 && p.n_acc == 1) {
+        return launch_n<EPI_DG0, 1>(p, smem, stream);
     } else if (EPI == EPI_PLAIN) {
         if (p.n_acc == 1) return launch_n<EPI_PLAIN, 1>(p, smem, stream);
         if (p.n_acc == 2) return launch_n<EPI_PLAIN, 2>(p, smem, stream);
@@ -996,8 +1045,24 @@ static int bwd_gemm_impl(int layer, const void* dy, const void* wt, void* col, c
 // described at Dg1Geo.  dyp = padded planar dY of conv 1 (vd_tc_pack_dyp1 / vd_tc_bwd_col2im_ex), wimg0/1 = weight
 // images of vd_tc_pack_dgrad1_weights.  code0 != NULL: out = packed dY of conv 0's column GEMM (routing applied);
 // code0 == NULL: out = fp32 NCDHW (B, 64, T, H1, H1).
+static int dgrad1_impl(const void* dyp, const void* wimg0, const void* wimg1, const uint8_t* code0, void* out,
+                       const vd_tc_plan* plan, int B, int dy0_planar, void* stream);
+
 extern "C" int vd_tc_dgrad1(const void* dyp, const void* wimg0, const void* wimg1, const uint8_t* code0, void* out,
                             const vd_tc_plan* plan, int B, void* stream) {
+    return dgrad1_impl(dyp, wimg0, wimg1, code0, out, plan, B, 0, stream);
+}
+
+// out_planar != 0 (needs code0): the routed gradient goes to the padded planar dY of conv 0 consumed by vd_tc_dgrad0
+// (halo cells zeroed once by the caller) instead of the column-GEMM operand
+extern "C" int vd_tc_dgrad1_ex(const void* dyp, const void* wimg0, const void* wimg1, const uint8_t* code0, void* out,
+                               const vd_tc_plan* plan, int B, int out_planar, void* stream) {
+    VD_REQUIRE(!out_planar || code0, "tc_dgrad1_ex: the planar dY0 output needs the routing code of conv 0");
+    return dgrad1_impl(dyp, wimg0, wimg1, code0, out, plan, B, out_planar, stream);
+}
+
+static int dgrad1_impl(const void* dyp, const void* wimg0, const void* wimg1, const uint8_t* code0, void* out,
+                       const vd_tc_plan* plan, int B, int dy0_planar, void* stream) {
     VD_REQUIRE(dyp && wimg0 && wimg1 && out && plan, "tc_dgrad1: NULL pointer");
     VD_REQUIRE(geo_supported(plan->T, plan->H) && B >= 0, "tc_dgrad1: unsupported geometry / batch");
     if (B == 0) return 0;
@@ -1034,10 +1099,61 @@ extern "C" int vd_tc_dgrad1(const void* dyp, const void* wimg0, const void* wimg
         if (int rc = finalize_smem(p, (uint32_t)p.G * p.RW * kWeightTileBytes, &smem)) return rc;
         p.pix = (const uint8_t*)dyp; p.wimg = (const uint8_t*)(ph ? wimg1 : wimg0); p.item_index = nullptr;
         p.epi.out = (uint8_t*)out; p.epi.code = const_cast<uint8_t*>(code0); p.epi.T = plan->T; p.epi.n_items = B; p.epi.g = g;
-        p.epi.ph = ph; p.epi.bb = make_bwd_geo(g, 0);
+        p.epi.ph = ph; p.epi.bb = make_bwd_geo(g, 0); p.epi.dy0_planar = dy0_planar;
         if (int rc = launch<EPI_DG1>(p, smem, (cudaStream_t)stream)) return rc;
     }
     return 0;
+}
+
+// Direct dgrad of conv 0 (no column buffer, Dg0Geo): dyp0 = padded planar dY of conv 0 (vd_tc_dgrad1_ex /
+// vd_tc_pack_dyp0), wimg = resident weight image (vd_tc_pack_dgrad0_weights), out = fp32 gradient w.r.t. the input
+// video in the (B,T,3,H,W) layout (ncdhw = 0) or (B,3,T,H,W) (ncdhw = 1).
+extern "C" int vd_tc_dgrad0(const void* dyp0, const void* wimg, float* out, const vd_tc_plan* plan, int B, int ncdhw,
+                            void* stream) {
+    VD_REQUIRE(dyp0 && wimg && out && plan, "tc_dgrad0: NULL pointer");
+    VD_REQUIRE(geo_supported(plan->T, plan->H) && B >= 0, "tc_dgrad0: unsupported geometry / batch");
+    if (B == 0) return 0;
+    const Geo g = make_geo(plan->T, plan->H);
+    const Dg0Geo d = make_dg0_geo(g);
+    VD_REQUIRE(g.Wo0 + 3 <= d.PD && g.Ho0 % d.RT == 0, "tc_dgrad0: frame does not fit the pixel tile");
+    WsParams p;
+    memset(&p, 0, sizeof(p));
+    p.n_u = 1; p.nu_total = 1; p.ug_count = 1; p.w_u_stride = 0; p.w_item_stride = 0;
+    const int nrb = g.Ho0 / d.RT;
+    p.n_tiles = B * g.T * nrb; p.tiles_per_item = g.T * nrb; p.v_count = nrb;
+    // tile (item, t, row block): stage sa = kt reads RS rows of the padded frame t + 2 - kt, all 8 chunks
+    p.item_stride = d.video_bytes; p.u_stride = d.frame_bytes; p.v_stride = (int64_t)d.RT * d.PD * 16;
+    p.n_sa = 3; p.n_sb = 1; p.sa_stride = -d.frame_bytes; p.sb_stride = 0;
+    p.n_copies = 8;
+    for (int c = 0; c < 8; ++c) {
+        p.copy_gofs[c] = 2 * d.frame_bytes + (int64_t)c * d.plane16 * 16;
+        p.copy_sofs[c] = (uint32_t)(c * d.stage_plane16 * 16);
+        p.copy_bytes[c] = (uint32_t)(d.stage_plane16 * 16);
+    }
+    p.stage_bytes = (uint32_t)(8 * d.stage_plane16 * 16);
+    p.n_steps = 64;
+    int j = 0;
+    for (int ih = 0; ih < 4; ++ih)
+        for (int iw = 0; iw < 4; ++iw)
+            for (int cs = 0; cs < 4; ++cs, ++j) {
+                const int sh = dg1_shift(ih, 2), sw = dg1_shift(iw, 2);
+                p.b_off16[j] = (uint32_t)(2 * cs * d.stage_plane16 + (sh + 1) * d.PD + (sw + 1));
+                p.b_lbo16[j] = (uint32_t)d.stage_plane16;
+                p.a_off16[j] = (uint32_t)(j * 32);                 // 512-byte weight tiles [k 2][16 rows][8]
+            }
+    p.a_sa_stride16 = 64 * 32;
+    p.a_lbo16 = 256 >> 4; p.a_sbo16 = 8;
+    p.w_resident = 1; p.w_bytes = (uint32_t)d.wimg_bytes;
+    p.G = 1; p.RW = 1; p.RP = 2;
+    p.n_acc = 1; p.acc_delta16 = 0;
+    p.ncols = 16; p.acc_cols = 16; p.acc_stages = 2;
+    p.idesc = umma_idesc_bf16(128, 16);
+    p.swap_ab = 1;
+    uint32_t smem = 0;
+    if (int rc = finalize_smem(p, (uint32_t)d.wimg_bytes, &smem)) return rc;
+    p.pix = (const uint8_t*)dyp0; p.wimg = (const uint8_t*)wimg; p.item_index = nullptr;
+    p.epi.out = (uint8_t*)out; p.epi.T = plan->T; p.epi.n_items = B; p.epi.g = g; p.epi.ncdhw = ncdhw;
+    return launch<EPI_DG0>(p, smem, (cudaStream_t)stream);
 }
 
 // wgrad of conv `layer` as a split-K GEMM: raw[(split, ntile)][cout 128][col 256] = sum over the slice's pixels of

@@ -163,6 +163,33 @@ inline Dg1Geo make_dg1_geo(const Geo& g) {
 // shift value of slot i (0..3): 2, 1, 0, -1; ph = 0 has no s_h = 2 slot (kh would be -1): its slots are 1, 0, -1
 __host__ __device__ inline int dg1_shift(int slot, int first) { return first - slot; }
 
+// ---- direct (column-free) dgrad of conv 0 (Cin = 3): pixels on M, the 12 (ci, ph, pw) outputs on N = 16.
+//   dX[ci, t, 2a+ph, 2b+pw] = sum_{kt, s_h, s_w, co} dY[co, t+1-kt, a+s_h, b+s_w] * W[co, ci, kt, ph+3-2 s_h, pw+3-2 s_w]
+//   M rows   : m = (a - a0)*PD + b, RT = 128 / PD rows of PD = 64 columns per tile (columns b >= Wo0 are discarded)
+//   N columns: n = ci*4 + ph*2 + pw (12 of 16)
+//   K        : kt (3 stages) x [s_h 4][s_w 4][co step 4] K=16 steps; the 96 KiB weight image is resident in smem
+//   dYP0 ("padded planar" dY of conv 0): [video][t_pad T+2][chunk 8][row RD = Ho0+4][col PD] x 16 B, row r <-> ho = r-1,
+//       col c <-> wo = c-1, zeros outside the image: the A operand of step (s_h, s_w) is the stage shifted by
+//       (s_h+1)*PD + (s_w+1) chunks.
+struct Dg0Geo {
+    int Ho, Wo, PD, RT, RD, RS;    // RS = RT + 4 staged rows per chunk
+    int plane16;                   // RD * PD
+    int stage_plane16;             // RS * PD
+    int64_t frame_bytes, video_bytes;
+    int64_t wimg_bytes;            // 3 * 64 * 512
+};
+
+inline Dg0Geo make_dg0_geo(const Geo& g) {
+    Dg0Geo d{};
+    d.Ho = g.Ho0; d.Wo = g.Wo0; d.PD = 64; d.RT = 2; d.RD = g.Ho0 + 4; d.RS = d.RT + 4;
+    d.plane16 = d.RD * d.PD;
+    d.stage_plane16 = d.RS * d.PD;
+    d.frame_bytes = (int64_t)8 * d.plane16 * 16;
+    d.video_bytes = (int64_t)(g.T + 2) * d.frame_bytes;
+    d.wimg_bytes = 3 * 64 * 512;
+    return d;
+}
+
 constexpr int kWeightTileBytes = 4096;      // [k 2][128 rows][16 B]
 constexpr int kVideosPerTile2 = 4;          // conv 2: accumulators (videos) per CTA tile
 constexpr int kW0Steps = 11;                // conv 0: 21 (c,kh) chunks paired into K=16 steps

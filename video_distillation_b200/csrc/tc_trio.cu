@@ -182,6 +182,44 @@ __global__ void pack_dyp1_kernel(const float* __restrict__ gy, uint4* __restrict
     }
 }
 
+// ---- direct dgrad of conv 0 (Dg0Geo): resident weight image and the padded planar dY
+// image [kt 3][step = (ih*4 + iw)*4 + cs][k2][16 rows n = ci*4 + ph*2 + pw][8]:
+//   co = cs*16 + k2*8 + e, kh = ph + 3 - 2*s_h(ih), kw = pw + 3 - 2*s_w(iw), s(i) = 2 - i  (zero outside 0..6, rows >= 12)
+__global__ void pack_dg0_w_kernel(const float* __restrict__ w, uint16_t* __restrict__ img, int total) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int e = i % 8; int q = i / 8;
+        int n = q % 16; q /= 16;
+        int k2 = q % 2; q /= 2;
+        int step = q % 64; int kt = q / 64;
+        const int cs = step % 4, iw = (step / 4) % 4, ih = step / 16;
+        const int ci = n >> 2, ph = (n >> 1) & 1, pw = n & 1;
+        const int co = cs * 16 + k2 * 8 + e;
+        const int kh = ph + 3 - 2 * dg1_shift(ih, 2), kw = pw + 3 - 2 * dg1_shift(iw, 2);
+        float v = 0.f;
+        if (n < 12 && kh >= 0 && kh < 7 && kw >= 0 && kw < 7) v = w[(((co * 3 + ci) * 3 + kt) * 7 + kh) * 7 + kw];
+        img[i] = f2bf(v);
+    }
+}
+
+// gy (B, 64, T, Ho0, Wo0) fp32 -> dYP0 [video][t_pad T+2][chunk 8][row RD][col PD] chunks; every cell is written
+__global__ void pack_dyp0_kernel(const float* __restrict__ gy, uint4* __restrict__ dyp, int64_t total, Dg0Geo d, int T) {
+    const int64_t So = (int64_t)T * d.Ho * d.Wo;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(i % d.PD); int64_t q = i / d.PD;
+        int r = (int)(q % d.RD); q /= d.RD;
+        int chunk = (int)(q % 8); q /= 8;
+        int tp = (int)(q % (T + 2)); int64_t vid = q / (T + 2);
+        const int t = tp - 1, ho = r - 1, wo = c - 1;
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (t >= 0 && t < T && ho >= 0 && ho < d.Ho && wo >= 0 && wo < d.Wo) {
+            const float* p = gy + (vid * 64 + chunk * 8) * So + ((int64_t)t * d.Ho + ho) * d.Wo + wo;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = __ldg(p + e * So);
+        }
+        dyp[i] = pack8(v);
+    }
+}
+
 static inline unsigned grid_of(int64_t n) {
     int64_t x = (n + 255) / 256;
     const int64_t cap = 148 * 32;
@@ -303,4 +341,30 @@ extern "C" int vd_tc_pack_dyp1(const float* gy, void* dyp, const vd_tc_plan* pla
     const int64_t total = (int64_t)B * (d.video_bytes / 16);
     pack_dyp1_kernel<<<grid_of(total), 256, 0, (cudaStream_t)stream>>>(gy, (uint4*)dyp, total, d, g.T);
     return check_launch("tc_pack_dyp1");
+}
+
+// sizes of the direct conv-0 dgrad: out[0] = dYP0 bytes per video, out[1] = weight image bytes
+extern "C" int vd_tc_dgrad0_sizes(const vd_tc_plan* plan, int64_t* out) {
+    VD_REQUIRE(plan && out && geo_supported(plan->T, plan->H), "tc_dgrad0_sizes: bad plan");
+    const Dg0Geo d = make_dg0_geo(make_geo(plan->T, plan->H));
+    out[0] = d.video_bytes; out[1] = d.wimg_bytes;
+    return 0;
+}
+
+extern "C" int vd_tc_pack_dgrad0_weights(const float* w_l0, void* wimg, void* stream) {
+    VD_REQUIRE(w_l0 && wimg, "tc_pack_dgrad0_weights: NULL pointer");
+    const int total = 3 * 64 * 512 / 2;
+    pack_dg0_w_kernel<<<grid_of(total), 256, 0, (cudaStream_t)stream>>>(w_l0, (uint16_t*)wimg, total);
+    return check_launch("tc_pack_dg0_w");
+}
+
+// gy fp32 NCDHW (B, 64, T, Ho0, Wo0) -> padded planar dY of conv 0 (every cell written, halo zeros included)
+extern "C" int vd_tc_pack_dyp0(const float* gy, void* dyp, const vd_tc_plan* plan, int B, void* stream) {
+    VD_REQUIRE(gy && dyp && plan && geo_supported(plan->T, plan->H), "tc_pack_dyp0: bad argument");
+    if (B <= 0) return 0;
+    const Geo g = make_geo(plan->T, plan->H);
+    const Dg0Geo d = make_dg0_geo(g);
+    const int64_t total = (int64_t)B * (d.video_bytes / 16);
+    pack_dyp0_kernel<<<grid_of(total), 256, 0, (cudaStream_t)stream>>>(gy, (uint4*)dyp, total, d, g.T);
+    return check_launch("tc_pack_dyp0");
 }

@@ -46,7 +46,12 @@ class TcConvNet3D:
         _lib.check(_lib.lib().vd_tc_dgrad1_sizes(ctypes.byref(p), sz), 'vd_tc_dgrad1_sizes')
         self.dyp1_bytes_per_video = int(sz[0])
         self.dg1_w = (torch.empty(int(sz[1]), **u8), torch.empty(int(sz[2]), **u8))   # direct conv-1 dgrad weight images
-        self.direct_dgrad1 = True          # False: column GEMM + col2im for conv 1 as for conv 0 / conv 2
+        self.direct_dgrad1 = True          # False: column GEMM + col2im for conv 1 as for conv 2
+        sz0 = (ctypes.c_int64 * 2)()
+        _lib.check(_lib.lib().vd_tc_dgrad0_sizes(ctypes.byref(p), sz0), 'vd_tc_dgrad0_sizes')
+        self.dyp0_bytes_per_video = int(sz0[0])
+        self.dg0_w = torch.empty(int(sz0[1]), **u8)                                   # direct conv-0 dgrad weight image
+        self.direct_dgrad0 = True          # needs direct_dgrad1 (its epilogue writes the padded planar dY of conv 0)
         self._ws = {}
         self.b0 = self.b1 = self.b2 = None
         self._x0 = None
@@ -75,6 +80,7 @@ class TcConvNet3D:
                                                          _lib.stream()), 'vd_tc_pack_weights_bwd')
             _lib.check(_lib.lib().vd_tc_pack_dgrad1_weights(_lib.ptr(ws[1]), _lib.ptr(self.dg1_w[0]), _lib.ptr(self.dg1_w[1]),
                                                             ctypes.byref(self.plan), _lib.stream()), 'vd_tc_pack_dgrad1_weights')
+            _lib.check(_lib.lib().vd_tc_pack_dgrad0_weights(_lib.ptr(ws[0]), _lib.ptr(self.dg0_w), _lib.stream()), 'vd_tc_pack_dgrad0_weights')
             self._bwd_ready = True
 
     def _workspace(self, name, nbytes, dtype=torch.uint8, zero=False):
@@ -100,16 +106,25 @@ class TcConvNet3D:
             dy2 = self._workspace('dy2', n * p.dy2_bytes_per_video)
             dy1 = self._workspace('dy1', n * p.dy1_bytes_per_video)
             dy0 = self._workspace('dy0', n * p.dy0_bytes_per_video)
-            col_per = max(p.col0_bytes_per_video, p.col2_bytes_per_video, 0 if self.direct_dgrad1 else p.col1_bytes_per_video)
+            col_per = max(0 if (self.direct_dgrad1 and self.direct_dgrad0) else p.col0_bytes_per_video, p.col2_bytes_per_video,
+                          0 if self.direct_dgrad1 else p.col1_bytes_per_video)
             col = self._workspace('col', n * col_per)
             st = _lib.stream()
             plan = ctypes.byref(p)
             _lib.check(lib.vd_tc_bwd_emb(_lib.ptr(g_emb[s:e]), _lib.ptr(c2[s:e]), _lib.ptr(dy2), plan, n, st), 'vd_tc_bwd_emb')
             _lib.check(lib.vd_tc_bwd_gemm(2, _lib.ptr(dy2), _lib.ptr(self.wt2), _lib.ptr(col), plan, n, st), 'vd_tc_bwd_gemm(2)')
-            if self.direct_dgrad1:
-                # conv 1: column-free dgrad (shifted-window GEMM per row parity) over the padded planar dY of conv 1,
-                # routing of conv 0 fused into its epilogue -> packed dY of conv 0
+            if self.direct_dgrad1 and self.direct_dgrad0:
+                # conv 1 and conv 0: column-free dgrads (shifted-window GEMMs over padded planar dY tensors); the
+                # routing of conv 0 is fused into conv 1's epilogue, conv 0's epilogue writes d video
                 dyp1 = self._workspace('dyp1', n * self.dyp1_bytes_per_video, zero=True)     # halo cells stay zero
+                dyp0 = self._workspace('dyp0', n * self.dyp0_bytes_per_video, zero=True)
+                _lib.check(lib.vd_tc_bwd_col2im_ex(2, _lib.ptr(col), _lib.ptr(c1[s:e]), _lib.ptr(dyp1), plan, n, 1, st), 'vd_tc_bwd_col2im_ex(2)')
+                _lib.check(lib.vd_tc_dgrad1_ex(_lib.ptr(dyp1), _lib.ptr(self.dg1_w[0]), _lib.ptr(self.dg1_w[1]), _lib.ptr(c0[s:e]),
+                                               _lib.ptr(dyp0), plan, n, 1, st), 'vd_tc_dgrad1_ex')
+                _lib.check(lib.vd_tc_dgrad0(_lib.ptr(dyp0), _lib.ptr(self.dg0_w), _lib.ptr(dvideo[s:e]), plan, n, 0, st), 'vd_tc_dgrad0')
+                continue
+            if self.direct_dgrad1:
+                dyp1 = self._workspace('dyp1', n * self.dyp1_bytes_per_video, zero=True)
                 _lib.check(lib.vd_tc_bwd_col2im_ex(2, _lib.ptr(col), _lib.ptr(c1[s:e]), _lib.ptr(dyp1), plan, n, 1, st), 'vd_tc_bwd_col2im_ex(2)')
                 _lib.check(lib.vd_tc_dgrad1(_lib.ptr(dyp1), _lib.ptr(self.dg1_w[0]), _lib.ptr(self.dg1_w[1]), _lib.ptr(c0[s:e]),
                                             _lib.ptr(dy0), plan, n, st), 'vd_tc_dgrad1')

@@ -29,6 +29,7 @@ class TcTrio:
         ]
         self._ws = {}
         self.direct_dgrad1 = True
+        self.direct_dgrad0 = True
         self.col_fp32 = True
 
     # ------------------------------------------------------------------ helpers
@@ -93,6 +94,18 @@ class TcTrio:
     def dgrad(self, layer, gy, w):
         p, lib, B = self.plan, _lib.lib(), int(gy.shape[0])
         cin, cout, ext = self.layers[layer]
+        if layer == 0 and self.direct_dgrad0:
+            # column-free dgrad of conv 0 (tc_layout.h: Dg0Geo): pixels on M, fp32 accumulators to (B,3,T,H,W)
+            sz = (ctypes.c_int64 * 2)()
+            _lib.check(lib.vd_tc_dgrad0_sizes(ctypes.byref(p), sz), 'vd_tc_dgrad0_sizes')
+            wimg = self._buf('dg0_w', sz[1])
+            dyp = self._buf('dyp0', B * sz[0])
+            plan, st = ctypes.byref(p), _lib.stream()
+            _lib.check(lib.vd_tc_pack_dgrad0_weights(_lib.ptr(w), _lib.ptr(wimg), st), 'vd_tc_pack_dgrad0_weights')
+            _lib.check(lib.vd_tc_pack_dyp0(_lib.ptr(gy), _lib.ptr(dyp), plan, B, st), 'vd_tc_pack_dyp0')
+            gx = torch.empty(B, cin, *ext, dtype=torch.float32, device=self.device)
+            _lib.check(lib.vd_tc_dgrad0(_lib.ptr(dyp), _lib.ptr(wimg), _lib.ptr(gx), plan, B, 1, st), 'vd_tc_dgrad0')
+            return gx
         if layer == 1 and self.direct_dgrad1:
             # column-free dgrad of conv 1 (tc_layout.h: Dg1Geo): fp32 accumulators go straight to the NCDHW gradient
             sz = (ctypes.c_int64 * 3)()
