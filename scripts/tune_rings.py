@@ -31,7 +31,9 @@ F = {0: 2.832e9, 1: 7.553e9, 2: 0.617e9}
 print(' '.join('conv%%d %%6.2f ms %%6.0f TF/s' %% (k, ms[k], F[k] * B / ms[k] / 1e9) for k in ms))
 ''' % ROOT
 configs = [dict(), dict(VD_TC_L1_G='4', VD_TC_L1_RW='4'), dict(VD_TC_L1_G='2', VD_TC_L1_RW='8'), dict(VD_TC_L1_G='3', VD_TC_L1_RW='5'),
-           dict(VD_TC_L1_G='7', VD_TC_L1_RW='2', VD_TC_L2_G='3', VD_TC_L2_RW='4'), dict(VD_TC_L2_G='2', VD_TC_L2_RW='8', VD_TC_L0_RP='2')]
+           dict(VD_TC_L1_G='5', VD_TC_L1_RW='3'), dict(VD_TC_L1_G='8', VD_TC_L1_RW='2'),
+           dict(VD_TC_L2_G='3', VD_TC_L2_RW='4'), dict(VD_TC_L2_G='2', VD_TC_L2_RW='8'), dict(VD_TC_L2_G='4', VD_TC_L2_RW='4'),
+           dict(VD_TC_L2_G='12', VD_TC_L2_RW='2'), dict(VD_TC_L0_RP='2')]
 for cfg in configs:
     env = dict(os.environ, **cfg)
     r = subprocess.run([sys.executable, '-c', CODE], env=env, capture_output=True, text=True)

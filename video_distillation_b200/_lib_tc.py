@@ -36,6 +36,8 @@ def declare(lib):
         'vd_tc_dgrad0': (c_int, [P, P, P, POINTER(TcPlan), c_int, c_int, P]),
         'vd_tc_probe': (c_int, [P, P, P, c_int, c_int, c_int, c_uint32, c_uint32, c_uint32, c_uint32, c_uint32, c_int, P]),
         'vd_tc_mma_rate': (c_int, [P, c_int, c_int, c_int, c_uint32, c_uint32, c_uint32, c_int, c_int, c_int, P]),
+        'vd_tc_mma_rate2': (c_int, [P, c_int, c_int, c_int, c_uint32, c_uint32, c_uint32, c_int, c_uint32, c_uint32, c_uint32, c_int,
+                            c_uint32, c_int, c_int, c_uint32, c_int, c_int, P]),
         'vd_tc_set_profile_buffer': (c_int, [P]),
         'vd_tc_debug_params': (c_int, [c_int, POINTER(TcPlan), c_int, POINTER(c_int64), c_int]),
     }

@@ -9,7 +9,7 @@
 //        bulk-copied slots (conv 1/2) or resident in shared memory for the whole kernel (conv 0)
 //   B  = 16-byte channel chunks of the packed activation staged ONCE per (tile, stage) by bulk
 //        async copies; every filter tap is just a different descriptor start address.
-// Warp roles: 0 pixel loader, 1 MMA issuer (single thread), 2 TMEM allocator, 3 weight loader,
+// Warp roles: 0 pixel loader, 1 and 2 MMA issuers (one thread each, alternating MMA groups; 2 also allocates TMEM), 3 weight loader,
 // 4..7 epilogue (TMEM -> registers -> bias/ReLU/MaxPool/argmax -> packed bf16 input of the next
 // layer, or fp32 embeddings after conv 2).  Layouts: tc_layout.h.
 #include <stdlib.h>
@@ -93,6 +93,7 @@ struct __align__(8) Barriers {
     uint64_t w_full[8], w_empty[8];
     uint64_t acc_full[2], acc_empty[2];
     uint64_t w_res;
+    uint64_t baton[2];                  // MMA issuer hand-over (issuer r arrives on baton[r] after each of its groups)
     uint32_t tmem_base;
     uint32_t pad;
 };
@@ -505,9 +506,9 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 4; ++i) { mbar_init(BAR(pix_full, i), 1); mbar_init(BAR(pix_empty, i), 1); }
+        for (int i = 0; i < 4; ++i) { mbar_init(BAR(pix_full, i), 1); mbar_init(BAR(pix_empty, i), 2); }     // empty: one commit per issuer
         for (int i = 0; i < 8; ++i) { mbar_init(BAR(w_full, i), 1); mbar_init(BAR(w_empty, i), 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(BAR(acc_full, i), 1); mbar_init(BAR(acc_empty, i), 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(BAR(acc_full, i), 2); mbar_init(BAR(acc_empty, i), 4); mbar_init(BAR(baton, i), 1); }
         mbar_init(BAR(w_res, 0), 1);
         fence_mbar_init();
     }
@@ -580,99 +581,143 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        // Issue-rate critical.  Measured on B200 (scripts/mma_rate.py): the tensor pipe runs at
-        // exactly N/2 cycles per MMA and overlaps fully with the issuing thread, so a step is bound
-        // by max(MMA time, scalar instructions of the issue loop) — and a single warp retires only
-        // ~1 dependent instruction per 7-10 cycles.  Hence: every descriptor is precomputed ONCE
-        // into shared-memory tables (per pixel-ring slot / weight-ring slot), and the elected lane's
-        // inner loop is just table loads + tcgen05.mma.
-        const bool resident = p.w_resident != 0;
+    } else if (warp == 1 || warp == 2) {
+        // ===================== MMA issuers (two threads, alternating MMA groups) =====================
+        // Measured on B200 (scripts/mma_operand_probe.py, profiles/r01_mma_operand_probe.log): the tensor pipe sustains
+        // exactly N/2 cycles per MMA at full-chip scale with moving / misaligned operand windows, but it accepts only about
+        // one MMA ahead of the one executing — every cycle the issuing thread spends between two MMAs beyond that slack is
+        // a lost pipe cycle (an idle gap of X cycles between stages costs ~X), and a lone thread needs several hundred
+        // cycles for the bookkeeping of a stage boundary (barrier waits, commits, ring / loop counters).  Hence:
+        //   * every descriptor is precomputed ONCE into shared-memory tables (per pixel-ring slot / weight-ring slot);
+        //   * the loop nest (tile, accumulator group, stage, weight slot) is flattened into a generator of MMA groups;
+        //   * TWO threads (lane 0 of warps 1 and 2) walk the same group sequence and issue alternate groups.  While one
+        //     issues, the other does its bookkeeping and waits for its next group's operands; a baton mbarrier passes
+        //     the right to issue, so the MMAs still enter the pipe in exactly the sequential order (bitwise
+        //     reproducible accumulation) and the hand-over hides behind the MMAs already queued.
+        //   * tcgen05.commit only tracks the MMAs of the executing thread: pix_empty / acc_full expect one commit from
+        //     EACH issuer (the one that did not issue the closing group commits as it walks past it).
+        const int role = warp - 1;
+        const bool RESIDENT = p.w_resident != 0;
         const int n_steps = p.n_steps;
-        const int G = resident ? n_steps : p.G;
+        const int G = RESIDENT ? n_steps : p.G;
         const uint32_t a_hi = p.a_hi ? p.a_hi : ((p.a_sbo16 & 0x3FFFu) | (1u << 14));
         const uint32_t b_hi = p.b_hi ? p.b_hi : (8u | (1u << 14));
         const uint32_t a_lbo_bits = (p.a_lbo16 & 0x3FFFu) << 16;
         const uint32_t slot_bytes = (uint32_t)G * kWeightTileBytes;
         uint64_t* tabB = reinterpret_cast<uint64_t*>(base_ptr + 256);                   // [RP][n_steps][NACC]
         uint64_t* tabA = tabB + p.RP * n_steps * NACC;                                  // [RW][G] or [n_sa][n_steps]
-        for (int i = lane; i < p.RP * n_steps * NACC; i += 32) {
+        const int t64 = role * 32 + lane;
+        for (int i = t64; i < p.RP * n_steps * NACC; i += 64) {
             const int a = i % NACC, s = (i / NACC) % n_steps, slot = i / (NACC * n_steps);
             const uint32_t pix16 = (smem_pix + (uint32_t)slot * p.stage_pitch) >> 4;
             tabB[i] = ((uint64_t)b_hi << 32) | (p.step_tab[s].y + pix16 + (uint32_t)a * p.acc_delta16);
         }
-        const int nA = resident ? p.n_sa * n_steps : p.RW * G;
-        for (int i = lane; i < nA; i += 32) {
+        const int nA = RESIDENT ? p.n_sa * n_steps : p.RW * G;
+        for (int i = t64; i < nA; i += 64) {
             uint32_t a16;
-            if (resident) a16 = (smem_w >> 4) + p.step_tab[i % n_steps].x + (uint32_t)((i / n_steps) * p.a_sa_stride16);
+            if (RESIDENT) a16 = (smem_w >> 4) + p.step_tab[i % n_steps].x + (uint32_t)((i / n_steps) * p.a_sa_stride16);
             else a16 = ((smem_w + (uint32_t)(i / G) * slot_bytes) >> 4) + (uint32_t)(i % G) * (kWeightTileBytes >> 4);
             tabA[i] = ((uint64_t)a_hi << 32) | ((a16 & 0x3FFFu) | a_lbo_bits);
         }
-        __syncwarp();
-        uint32_t pslot = 0, pphase = 0, wslot = 0, wphase = 0, as = 0, aphase = 0;
-        const int slots_per_stage = (n_steps + G - 1) / G;
-        const uint32_t acc_cols = p.acc_cols, idesc = p.idesc;
-        if (resident) { mbar_wait(BAR(w_res, 0), 0); tc_fence_after(); }
-        long long c_acc = 0, c_pix = 0, c_w = 0, c_issue = 0, c_fence = 0, c_tail = 0;
-        const bool prof = p.prof != nullptr;
-        const long long c_begin = clock64();
-#define TIMED(counter, stmt) do { if (prof) { const long long t_ = clock64(); stmt; counter += clock64() - t_; } else { stmt; } } while (0)
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-            // n_u > 1 (column GEMM): one pixel stage per tile, reused by every accumulator group
-            const int n_u_eff = min(p.n_u, p.nu_total - (tile % p.ug_count) * p.n_u);
-            for (int u = 0; u < n_u_eff; ++u) {
-                TIMED(c_acc, mbar_wait(BAR(acc_empty, as), aphase ^ 1));
-                TIMED(c_fence, tc_fence_after());
-                const uint32_t d_base = tmem_base + as * (acc_cols * (uint32_t)NACC);
-                uint32_t accumulate = 0;
-                for (int sa = 0; sa < p.n_sa; ++sa) {
-                    for (int sb = 0; sb < p.n_sb; ++sb) {
-                        if (u == 0) { TIMED(c_pix, mbar_wait(BAR(pix_full, pslot), pphase)); TIMED(c_fence, tc_fence_after()); }
-                        int j = 0;
-                        for (int g = 0; g < slots_per_stage; ++g) {
-                            const int nst = min(G, n_steps - j);
-                            if (!resident) { TIMED(c_w, mbar_wait(BAR(w_full, wslot), wphase)); TIMED(c_fence, tc_fence_after()); }
-                            const long long t_issue = prof ? clock64() : 0;
-                            if (elect_one()) {
-                                const uint64_t* ta = resident ? tabA + sa * n_steps + j : tabA + wslot * G;
-                                const uint64_t* tb = tabB + ((int)pslot * n_steps + j) * NACC;
-                                if (p.swap_ab) {                    // pixels = M operand, weight tile = N operand (NACC == 1)
+        asm volatile("bar.sync 1, 64;" ::: "memory");                                  // tables visible to both issuers
+        // elect.sync (not `lane == 0`): the compiler then knows that exactly one thread runs the block, so descriptors move
+        // to uniform registers with plain R2UR instead of a per-MMA ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop
+        if (elect_one()) {
+            struct Group {
+                uint32_t w_acc, p_acc, w_pix, p_pix, w_w, p_w;      // barriers to wait for (0 = none) and their parities
+                uint32_t c_w, c_pix, c_acc;                           // barriers to commit after the MMAs (0 = none)
+                const uint64_t* ta;
+                const uint64_t* tb;
+                int nst;
+                uint32_t d_base, acc0;
+            };
+            const int slots_per_stage = (n_steps + G - 1) / G;
+            const int n_tiles = p.n_tiles, n_sb = p.n_sb;
+            const uint32_t acc_cols = p.acc_cols, idesc = p.idesc, RP = (uint32_t)p.RP, RW = (uint32_t)p.RW, acc_stages = p.acc_stages;
+            const bool swap_ab = p.swap_ab != 0;
+            // generator state (identical in both issuers)
+            int tile = blockIdx.x, u = 0, st = 0, sa = 0, sb = 0, g = 0, j = 0;
+            int n_u_eff = tile < n_tiles ? min(p.n_u, p.nu_total - (tile % p.ug_count) * p.n_u) : 0;
+            uint32_t pslot = 0, pphase = 0, wslot = 0, wphase = 0, as = 0, aphase = 0;
+            auto next = [&](Group& r) {
+                const bool first = (st == 0 && g == 0);                  // first group of this (tile, u): fresh accumulator
+                const bool last_g = (g == slots_per_stage - 1);
+                const bool last_u = (u == n_u_eff - 1);
+                r.w_acc = BAR(acc_empty, as);                            r.p_acc = aphase ^ 1u;
+                r.w_pix = BAR(pix_full, pslot);                          r.p_pix = pphase;
+                r.w_w = RESIDENT ? 0u : BAR(w_full, wslot);              r.p_w = wphase;
+                r.nst = min(G, n_steps - j);
+                r.ta = RESIDENT ? tabA + sa * n_steps + j : tabA + wslot * G;
+                r.tb = tabB + ((int)pslot * n_steps + j) * NACC;
+                r.d_base = tmem_base + as * (acc_cols * (uint32_t)NACC);
+                r.acc0 = first ? 0u : 1u;
+                r.c_w = RESIDENT ? 0u : BAR(w_empty, wslot);
+                r.c_pix = (last_g && last_u) ? BAR(pix_empty, pslot) : 0u;
+                r.c_acc = (last_g && st == stages_per_tile - 1) ? BAR(acc_full, as) : 0u;
+                // advance
+                if (!RESIDENT) { if (++wslot == RW) { wslot = 0; wphase ^= 1; } }
+                if (!last_g) { ++g; j += r.nst; return; }
+                g = 0; j = 0;
+                if (last_u) { if (++pslot == RP) { pslot = 0; pphase ^= 1; } }
+                if (++sb == n_sb) { sb = 0; ++sa; }
+                if (++st < stages_per_tile) return;
+                st = 0; sa = 0; sb = 0;
+                if (++as == acc_stages) { as = 0; aphase ^= 1; }
+                if (++u < n_u_eff) return;
+                u = 0; tile += gridDim.x;
+                n_u_eff = tile < n_tiles ? min(p.n_u, p.nu_total - (tile % p.ug_count) * p.n_u) : 0;
+            };
+            long long c_acc = 0, c_pix = 0, c_w = 0, c_baton = 0, c_issue = 0;
+            const bool prof = p.prof != nullptr;
+            if (RESIDENT) { mbar_wait(BAR(w_res, 0), 0); tc_fence_after(); }
+            const long long c_begin = clock64();
+            Group r;
+            for (uint32_t k = 0; tile < n_tiles; ++k) {
+                next(r);
+                if ((k & 1u) == (uint32_t)role) {
+                    // ---- my group: operands (usually long there), then the baton of the previous group's issuer
+                    long long t0 = prof ? clock64() : 0;
+                    mbar_wait(r.w_acc, r.p_acc);           // (an already completed phase returns at once)
+                    if (prof) { const long long t1 = clock64(); c_acc += t1 - t0; t0 = t1; }
+                    mbar_wait(r.w_pix, r.p_pix);
+                    if (prof) { const long long t1 = clock64(); c_pix += t1 - t0; t0 = t1; }
+                    if (r.w_w) mbar_wait(r.w_w, r.p_w);
+                    if (prof) { const long long t1 = clock64(); c_w += t1 - t0; t0 = t1; }
+                    if (k > 0) mbar_wait(BAR(baton, role ^ 1), ((k - 1u) >> 1) & 1u);
+                    if (prof) { const long long t1 = clock64(); c_baton += t1 - t0; t0 = t1; }
+                    tc_fence_after();
+                    const uint64_t* ta = r.ta;
+                    const uint64_t* tb = r.tb;
+                    const uint32_t d_base = r.d_base;
+                    const int nst = r.nst;
+                    uint32_t accumulate = r.acc0;
+                    if (swap_ab) {                              // pixels = M operand, weight tile = N operand (NACC == 1)
 #pragma unroll 4
-                                    for (int jj = 0; jj < nst; ++jj) {
-                                        umma_bf16(d_base, tb[jj * NACC], ta[jj], idesc, accumulate);
-                                        accumulate = 1;
-                                    }
-                                } else {
-#pragma unroll 4
-                                    for (int jj = 0; jj < nst; ++jj) {
-                                        const uint64_t a_desc = ta[jj];
-#pragma unroll
-                                        for (int a = 0; a < NACC; ++a)
-                                            umma_bf16(d_base + (uint32_t)a * acc_cols, a_desc, tb[jj * NACC + a], idesc, accumulate);
-                                        accumulate = 1;
-                                    }
-                                }
-                                if (!resident) umma_commit(BAR(w_empty, wslot));
-                                if (g == slots_per_stage - 1 && u == n_u_eff - 1) umma_commit(BAR(pix_empty, pslot));
-                            }
-                            __syncwarp();
-                            if (prof) c_issue += clock64() - t_issue;
+                        for (int jj = 0; jj < nst; ++jj) {
+                            umma_bf16(d_base, tb[jj * NACC], ta[jj], idesc, accumulate);
                             accumulate = 1;
-                            j += nst;
-                            if (!resident) { if (++wslot == (uint32_t)p.RW) { wslot = 0; wphase ^= 1; } }
                         }
-                        if (u == n_u_eff - 1) { if (++pslot == (uint32_t)p.RP) { pslot = 0; pphase ^= 1; } }
+                    } else {
+#pragma unroll 4
+                        for (int jj = 0; jj < nst; ++jj) {
+                            const uint64_t a_desc = ta[jj];
+#pragma unroll
+                            for (int a = 0; a < NACC; ++a)
+                                umma_bf16(d_base + (uint32_t)a * acc_cols, a_desc, tb[jj * NACC + a], idesc, accumulate);
+                            accumulate = 1;
+                        }
                     }
+                    mbar_arrive(BAR(baton, role));            // the other issuer may enter the pipe behind these MMAs
+                    if (r.c_w) umma_commit(r.c_w);
+                    if (prof) c_issue += clock64() - t0;
                 }
-                TIMED(c_tail, { if (elect_one()) umma_commit(BAR(acc_full, as)); __syncwarp(); });
-                if (++as == p.acc_stages) { as = 0; aphase ^= 1; }
+                if (r.c_pix) umma_commit(r.c_pix);            // both issuers: "MY MMAs that read this stage / wrote this
+                if (r.c_acc) umma_commit(r.c_acc);            //  accumulator have completed"
             }
-        }
-#undef TIMED
-        if (prof && lane == 0) {
-            long long* o = p.prof + (int64_t)blockIdx.x * 8;
-            o[0] = clock64() - c_begin; o[1] = c_acc; o[2] = c_pix; o[3] = c_w; o[4] = c_issue; o[5] = c_fence; o[6] = c_tail;
+            if (prof && role == 0) {
+                long long* o = p.prof + (int64_t)blockIdx.x * 8;
+                o[0] = clock64() - c_begin; o[1] = c_acc; o[2] = c_pix; o[3] = c_w; o[4] = c_issue; o[5] = c_baton; o[6] = 0;
+            }
         }
     } else if (warp >= 4) {
         // ===================== epilogue (128 threads, lane quarter = warp % 4) =====================
