@@ -82,8 +82,15 @@ struct WsParams {
     uint32_t smem_epi_off;              // != 0: 4 x 32 x 33 float transpose scratch for coalesced raw stores
     uint32_t smem_stash_off;            // != 0: conv-1 epilogue stash [H2*H2][kStashPitch] bf16 (quick accumulator drain)
     int32_t swap_ab;                    // the staged pixels are the M operand and the weight tiles the N operand (conv-0 dgrad)
+    int32_t stream_pairs;               // conv 0 fused forward, != 0: "input-frame streaming" order (T/2 frame pairs per column):
+                                        //   a tile is a COLUMN (video, row band); its T input frames are staged once each, in
+                                        //   order, and every frame feeds the accumulators of the (up to) two frame pairs it
+                                        //   touches through the 4 Toeplitz weight windows — half the L2->SM pixel traffic of the
+                                        //   pair-by-pair order and no MMAs on the all-zero temporal halo frames
+    int32_t n_wsets;                    // resident weights: number of weight windows in the descriptor table (0: n_sa)
     int32_t dbg;                        // tuning experiments (VD_TC_DBG bitmask; results are garbage when set):
-                                        //   1 no pixel copies, 2 no weight copies, 4 epilogue does no work
+                                        //   1 no pixel copies, 2 no weight copies, 4 epilogue does no work,
+                                        //   16 loaders back off with nanosleep (old behaviour), 32 epilogue spins without nanosleep
     long long* prof;                    // optional [grid][8] cycle counters of the MMA warp (tuning only)
     EpiParams epi;
 };
@@ -188,10 +195,8 @@ __device__ __forceinline__ void epi_raw(const WsParams& p, int64_t slot, uint32_
 
 // conv 0: lanes 0..63 = frame 2*tp, lanes 64..127 = frame 2*tp+1, columns q = r*Wo0 + wo.
 // bias + ReLU + MaxPool(1,2,2) -> A1 chunks (bf16) [+ code (B,64,T,H1,H1)]
-__device__ __forceinline__ void epi_l0(const WsParams& p, int tile, uint32_t taddr, int m) {
+__device__ __forceinline__ void epi_l0(const WsParams& p, int item, int tp, int rb, uint32_t taddr, int m) {
     const Geo& g = p.epi.g;
-    const int item = tile / p.tiles_per_item, sub = tile % p.tiles_per_item;
-    const int tp = sub / p.v_count, rb = sub % p.v_count;
     const int f = 2 * tp + (m >> 6), co = m & 63;
     const float bias = __ldg(p.epi.bias + co);
     const int slice = co >> 4, k = (co >> 3) & 1, e = co & 7;
@@ -220,6 +225,87 @@ __device__ __forceinline__ void epi_l0(const WsParams& p, int tile, uint32_t tad
                 uint8_t* dst = vbase + (int64_t)(((ph * 2 + pw) * 2 + k)) * g.plane1 + ((int64_t)pi * g.P1 + pj) * 16 + e * 2;
                 *reinterpret_cast<uint16_t*>(dst) = f2bf(act ? best : 0.f);
                 if (cbase) cbase[hp * g.H1 + wp] = (uint8_t)(arg | (act ? 8 : 0));
+            }
+        }
+    }
+}
+
+// conv 0 in two phases (as conv 1 below), so that the accumulator is released after a short drain and the packed
+// output leaves as whole 16-byte chunks instead of 2-byte pieces:
+//   drain: TMEM -> bias / ReLU / MaxPool(1,2,2) -> bf16 stash [frame half][pooled position][channel]  (+ routing codes)
+//   store: every lane takes (chunk of 8 channels, position) items of its warp's 32 channels -> one 16-byte store each.
+constexpr int kStash0Pitch = 72;          // bf16 elements per position row (64 + 8: conflict-free 16-byte reads)
+
+__device__ __forceinline__ void epi_l0_drain(const WsParams& p, int item, int tp, int rb, uint32_t taddr, int m, uint16_t* stash) {
+    const Geo& g = p.epi.g;
+    const int half = m >> 6, f = 2 * tp + half, co = m & 63;
+    const float bias = __ldg(p.epi.bias + co);
+    const int Wp = g.Wo0 / 2, npos = (g.R0 / 2) * Wp;
+    uint16_t* srow = stash + (half * npos) * kStash0Pitch + co;
+    if (!(p.epi.code && item >= p.epi.code_first)) {
+        // frozen real videos (no routing codes): max / add / max, ~1/3 of the instructions of the argmax path
+        for (int pr = 0; pr < g.R0 / 2; ++pr) {
+            uint16_t* sp = srow + (pr * Wp) * kStash0Pitch;
+            for (int wb = 0; wb < g.Wo0; wb += 8, sp += 4 * kStash0Pitch) {
+                float r0[8], r1[8];
+                tmem_ld8(taddr + (2 * pr) * g.Wo0 + wb, r0);
+                tmem_ld8(taddr + (2 * pr + 1) * g.Wo0 + wb, r1);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 4; j += 2) {
+                    const float b0 = fmaxf(fmaxf(fmaxf(r0[2 * j], r0[2 * j + 1]), fmaxf(r1[2 * j], r1[2 * j + 1])) + bias, 0.f);
+                    const float b1 = fmaxf(fmaxf(fmaxf(r0[2 * j + 2], r0[2 * j + 3]), fmaxf(r1[2 * j + 2], r1[2 * j + 3])) + bias, 0.f);
+                    const uint32_t pk = pack_bf2(b0, b1);
+                    sp[j * kStash0Pitch] = (uint16_t)pk;
+                    sp[(j + 1) * kStash0Pitch] = (uint16_t)(pk >> 16);
+                }
+            }
+        }
+        return;
+    }
+    uint8_t* cbase = p.epi.code + (((int64_t)(item - p.epi.code_first) * 64 + co) * g.T + f) * g.H1 * g.H1;
+    for (int pr = 0; pr < g.R0 / 2; ++pr) {
+        const int hp = (rb * g.R0) / 2 + pr;
+        for (int wb = 0; wb < g.Wo0; wb += 8) {
+            float r0[8], r1[8];
+            tmem_ld8(taddr + (2 * pr) * g.Wo0 + wb, r0);
+            tmem_ld8(taddr + (2 * pr + 1) * g.Wo0 + wb, r1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                // scan order (h,w): (0,0) (0,1) (1,0) (1,1); first maximum wins
+                float best = r0[2 * j]; int arg = 0;
+                if (r0[2 * j + 1] > best) { best = r0[2 * j + 1]; arg = 1; }
+                if (r1[2 * j] > best) { best = r1[2 * j]; arg = 2; }
+                if (r1[2 * j + 1] > best) { best = r1[2 * j + 1]; arg = 3; }
+                best += bias;
+                const bool act = best > 0.f;
+                const int wp = wb / 2 + j;
+                srow[(pr * Wp + wp) * kStash0Pitch] = f2bf(act ? best : 0.f);
+                cbase[hp * g.H1 + wp] = (uint8_t)(arg | (act ? 8 : 0));
+            }
+        }
+    }
+}
+
+// warp q owns lanes 32q..32q+31 = frame half q >> 1, channels (q & 1) * 32 .. + 31 (4 chunks of 8 channels)
+__device__ __forceinline__ void epi_l0_store(const WsParams& p, int item, int tp, int rb, int q, int lane, const uint16_t* stash) {
+    const Geo& g = p.epi.g;
+    const int half = q >> 1, f = 2 * tp + half;
+    const int Wp = g.Wo0 / 2, npos = (g.R0 / 2) * Wp;
+    uint8_t* fbase = p.epi.out + (int64_t)item * g.video1 + (int64_t)(f + 1) * g.frame1;
+    const uint16_t* sbase = stash + (half * npos) * kStash0Pitch + (q & 1) * 32;
+    for (int pr = 0; pr < g.R0 / 2; ++pr) {
+        const int hp = (rb * g.R0) / 2 + pr;
+        const int64_t row_off = (int64_t)(coord_par(hp) * 4) * g.plane1 + (int64_t)coord_pos(hp) * g.P1 * 16;
+        for (int wp = lane; wp < Wp; wp += 32) {
+            const uint16_t* sp = sbase + (pr * Wp + wp) * kStash0Pitch;
+            uint8_t* dpos = fbase + row_off + (int64_t)(coord_par(wp) * 2) * g.plane1 + coord_pos(wp) * 16;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const int c8 = (q & 1) * 4 + kk;              // chunk of 8 channels: slice = c8 >> 1, k = c8 & 1
+                const uint4 v = *reinterpret_cast<const uint4*>(sp + kk * 8);
+                *reinterpret_cast<uint4*>(dpos + (int64_t)(c8 >> 1) * g.slice1 + (int64_t)(c8 & 1) * g.plane1) = v;
             }
         }
     }
@@ -535,7 +621,7 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
                 const uint8_t* gbase = p.pix + slot_item * p.item_stride + (int64_t)u * p.u_stride + (int64_t)v * p.v_stride;
                 for (int sa = 0; sa < p.n_sa; ++sa)
                     for (int sb = 0; sb < p.n_sb; ++sb) {
-                        mbar_wait<true>(BAR(pix_empty, slot), phase ^ 1);
+                        if (p.dbg & 16) mbar_wait<true>(BAR(pix_empty, slot), phase ^ 1); else mbar_wait(BAR(pix_empty, slot), phase ^ 1);
                         if (p.dbg & 1) { mbar_arrive(BAR(pix_full, slot)); }
                         else {
                             mbar_expect_tx(BAR(pix_full, slot), p.stage_bytes);
@@ -568,7 +654,7 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
                             for (int gi = 0; gi < slots_per_stage; ++gi) {
                                 const int s0 = gi * p.G;
                                 const uint32_t nb = (uint32_t)min(p.G, p.n_steps - s0) * kWeightTileBytes;
-                                mbar_wait<true>(BAR(w_empty, slot), phase ^ 1);
+                                if (p.dbg & 16) mbar_wait<true>(BAR(w_empty, slot), phase ^ 1); else mbar_wait(BAR(w_empty, slot), phase ^ 1);
                                 if (p.dbg & 2) { mbar_arrive(BAR(w_full, slot)); }
                                 else {
                                     mbar_expect_tx(BAR(w_full, slot), nb);
@@ -612,7 +698,7 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
             const uint32_t pix16 = (smem_pix + (uint32_t)slot * p.stage_pitch) >> 4;
             tabB[i] = ((uint64_t)b_hi << 32) | (p.step_tab[s].y + pix16 + (uint32_t)a * p.acc_delta16);
         }
-        const int nA = RESIDENT ? p.n_sa * n_steps : p.RW * G;
+        const int nA = RESIDENT ? (p.n_wsets ? p.n_wsets : p.n_sa) * n_steps : p.RW * G;
         for (int i = t64; i < nA; i += 64) {
             uint32_t a16;
             if (RESIDENT) a16 = (smem_w >> 4) + p.step_tab[i % n_steps].x + (uint32_t)((i / n_steps) * p.a_sa_stride16);
@@ -667,17 +753,52 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
                 u = 0; tile += gridDim.x;
                 n_u_eff = tile < n_tiles ? min(p.n_u, p.nu_total - (tile % p.ug_count) * p.n_u) : 0;
             };
+            // conv 0, input-frame streaming: frame i of the column (pair pp = i / 2) feeds
+            //   even i: X  pair pp-1 (frame 2pp-1, kt=2) through window 3 = [0 ; W2]   (absent for pp = 0; closes pair pp-1)
+            //           Y  pair pp   (kt = 1, 0)         through window 1 = [W1 ; W0]   (first write of pair 0)
+            //   odd  i: Z  pair pp   (kt = 2, 1)         through window 2 = [W2 ; W1]   (closes the last pair)
+            //           V  pair pp+1 (frame 2pp+2, kt=0) through window 0 = [W0 ; 0]    (absent for the last pair; first write)
+            // Pair q (running count over the columns of this CTA) lives in accumulator stage q & 1.
+            const int pairs = p.stream_pairs;
+            int fi = 0, part = 0;
+            uint32_t qbase = 0;
+            auto next_stream = [&](Group& r) {
+                const int pp = fi >> 1;
+                const bool odd = fi & 1;
+                const int kind = odd ? (part == 0 ? 2 : 3) : ((part == 0 && pp > 0) ? 0 : 1);       // 0 X, 1 Y, 2 Z, 3 V
+                const uint32_t q = qbase + (uint32_t)(pp + (kind == 0 ? -1 : kind == 3 ? 1 : 0));
+                const uint32_t buf = q & 1u;
+                const bool first_write = (kind == 3) || (kind == 1 && pp == 0);
+                const bool final_write = (kind == 0) || (kind == 2 && pp == pairs - 1);
+                const bool last_of_frame = odd ? (kind == 3 || pp + 1 >= pairs) : (kind == 1);
+                r.w_acc = first_write ? BAR(acc_empty, buf) : 0u;        r.p_acc = ((q >> 1) & 1u) ^ 1u;
+                r.w_pix = BAR(pix_full, pslot);                          r.p_pix = pphase;
+                r.w_w = 0u;                                              r.p_w = 0u;
+                r.nst = n_steps;
+                r.ta = tabA + (kind == 0 ? 3 : kind == 1 ? 1 : kind == 2 ? 2 : 0) * n_steps;
+                r.tb = tabB + (int)pslot * n_steps * NACC;
+                r.d_base = tmem_base + buf * (acc_cols * (uint32_t)NACC);
+                r.acc0 = first_write ? 0u : 1u;
+                r.c_w = 0u;
+                r.c_pix = last_of_frame ? BAR(pix_empty, pslot) : 0u;
+                r.c_acc = final_write ? BAR(acc_full, buf) : 0u;
+                if (!last_of_frame) { part = 1; return; }
+                part = 0;
+                if (++pslot == RP) { pslot = 0; pphase ^= 1; }
+                if (++fi < 2 * pairs) return;
+                fi = 0; qbase += (uint32_t)pairs; tile += gridDim.x;
+            };
             long long c_acc = 0, c_pix = 0, c_w = 0, c_baton = 0, c_issue = 0;
             const bool prof = p.prof != nullptr;
             if (RESIDENT) { mbar_wait(BAR(w_res, 0), 0); tc_fence_after(); }
             const long long c_begin = clock64();
             Group r;
             for (uint32_t k = 0; tile < n_tiles; ++k) {
-                next(r);
+                if (pairs) next_stream(r); else next(r);
                 if ((k & 1u) == (uint32_t)role) {
                     // ---- my group: operands (usually long there), then the baton of the previous group's issuer
                     long long t0 = prof ? clock64() : 0;
-                    mbar_wait(r.w_acc, r.p_acc);           // (an already completed phase returns at once)
+                    if (r.w_acc) mbar_wait(r.w_acc, r.p_acc);   // (an already completed phase returns at once)
                     if (prof) { const long long t1 = clock64(); c_acc += t1 - t0; t0 = t1; }
                     mbar_wait(r.w_pix, r.p_pix);
                     if (prof) { const long long t1 = clock64(); c_pix += t1 - t0; t0 = t1; }
@@ -726,15 +847,21 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
         uint32_t as = 0, aphase = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
             const int tile_pix = tile / p.ug_count, u0 = (tile % p.ug_count) * p.n_u;
-            const int n_u_eff = min(p.n_u, p.nu_total - u0);
+            // conv 0 streaming: a tile is a column (video, row band) and yields stream_pairs accumulators, pair by pair
+            const int n_u_eff = p.stream_pairs ? p.stream_pairs : min(p.n_u, p.nu_total - u0);
             for (int u = 0; u < n_u_eff; ++u) {
-                mbar_wait<true>(BAR(acc_full, as), aphase);
+                if (p.dbg & 32) mbar_wait(BAR(acc_full, as), aphase); else mbar_wait<true>(BAR(acc_full, as), aphase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * (p.acc_cols * (uint32_t)p.n_acc);
                 const bool work = !(p.dbg & 4);
                 if (work) {
                     if (EPI == EPI_RAW) epi_raw(p, (int64_t)tile_pix * p.nu_total + u0 + u, taddr, m, p.smem_epi_off ? reinterpret_cast<float*>(base_ptr + p.smem_epi_off) : nullptr);
-                    else if (EPI == EPI_L0) epi_l0(p, tile, taddr, m);
+                    else if (EPI == EPI_L0) {
+                        const int item = tile / p.tiles_per_item, sub = tile % p.tiles_per_item;
+                        const int tp = p.stream_pairs ? u : sub / p.v_count, rb = p.stream_pairs ? sub : sub % p.v_count;
+                        if (p.smem_stash_off) epi_l0_drain(p, item, tp, rb, taddr, m, reinterpret_cast<uint16_t*>(base_ptr + p.smem_stash_off));
+                        else epi_l0(p, item, tp, rb, taddr, m);
+                    }
                     else if (EPI == EPI_L1) epi_l1_drain(p, tile, taddr, m, reinterpret_cast<uint16_t*>(base_ptr + p.smem_stash_off));
                     else if (EPI == EPI_PLAIN) epi_plain(p, tile, taddr, m);
                     else if (EPI == EPI_DG1) epi_dg1(p, tile, taddr, m);
@@ -748,6 +875,12 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
                     // the accumulator is free again: scatter the stashed tile while the next one is computed
                     epi_l1_store(p, tile, q, lane, reinterpret_cast<const uint16_t*>(base_ptr + p.smem_stash_off));
                     __syncwarp();       // the stash rows of this warp are rewritten by the next drain
+                }
+                if (EPI == EPI_L0 && work && p.smem_stash_off) {
+                    const int item = tile / p.tiles_per_item, sub = tile % p.tiles_per_item;
+                    const int tp = p.stream_pairs ? u : sub / p.v_count, rb = p.stream_pairs ? sub : sub % p.v_count;
+                    epi_l0_store(p, item, tp, rb, q, lane, reinterpret_cast<const uint16_t*>(base_ptr + p.smem_stash_off));
+                    __syncwarp();
                 }
                 if (++as == p.acc_stages) { as = 0; aphase ^= 1; }
             }
@@ -776,7 +909,7 @@ static int env_int(const char* name, int dflt) {
     return (v && *v) ? atoi(v) : dflt;
 }
 
-static int finalize_smem(WsParams& p, uint32_t w_region, uint32_t* smem_total, bool epi_scratch = false, int stash_rows = 0) {
+static int finalize_smem(WsParams& p, uint32_t w_region, uint32_t* smem_total, bool epi_scratch = false, uint32_t stash_bytes = 0) {
     {
         const int G = p.w_resident ? p.n_steps : p.G;
         for (int j = 0; j < p.n_steps; ++j) {
@@ -791,7 +924,7 @@ static int finalize_smem(WsParams& p, uint32_t w_region, uint32_t* smem_total, b
     p.smem_epi_off = 0;
     if (epi_scratch) { p.smem_epi_off = align_up(total, 128); total = p.smem_epi_off + 4 * 32 * 33 * 4; }
     p.smem_stash_off = 0;
-    if (stash_rows) { p.smem_stash_off = align_up(total, 128); total = p.smem_stash_off + (uint32_t)stash_rows * kStashPitch * 2; }
+    if (stash_bytes) { p.smem_stash_off = align_up(total, 128); total = p.smem_stash_off + stash_bytes; }
     total += 1024;                                  // manual 1024-byte alignment slack
     if (total < 120 * 1024) total = 120 * 1024;     // one CTA per SM: every CTA allocates all 512 TMEM columns
     VD_REQUIRE(total <= 232448, "tc conv: shared memory budget exceeded (%u bytes)", total);
@@ -799,7 +932,7 @@ static int finalize_smem(WsParams& p, uint32_t w_region, uint32_t* smem_total, b
     return 0;
 }
 
-static int setup_l0(WsParams& p, const Geo& g, int B, uint32_t* smem) {
+static int setup_l0(WsParams& p, const Geo& g, int B, uint32_t* smem, bool fused = false) {
     p.n_u = 1; p.nu_total = 1; p.ug_count = 1; p.w_u_stride = 0;
     p.n_tiles = B * (g.T / 2) * (g.Ho0 / g.R0);
     p.tiles_per_item = (g.T / 2) * (g.Ho0 / g.R0);
@@ -833,11 +966,14 @@ static int setup_l0(WsParams& p, const Geo& g, int B, uint32_t* smem) {
     p.a_lbo16 = 5120 >> 4; p.a_sbo16 = 8;
     p.w_resident = 1; p.w_bytes = kW0Bytes;
     p.G = 1; p.RW = 1;
-    p.RP = env_int("VD_TC_L0_RP", 3);
+    // fused forward: two-phase epilogue (bf16 stash of the pooled tile, 2 x npos x kStash0Pitch) and a 2-slot pixel ring —
+    // in the streaming order a stage lasts 22 MMAs, so one slot of prefetch is enough
+    const bool stash = fused && env_int("VD_TC_L0_STASH", 1);
+    p.RP = env_int("VD_TC_L0_RP", stash ? 2 : 3);
     p.n_acc = 1; p.acc_delta16 = 0;
     p.ncols = g.N0; p.acc_cols = 256; p.acc_stages = 2;
     p.idesc = umma_idesc_bf16(128, g.N0);
-    return finalize_smem(p, kW0Bytes, smem);
+    return finalize_smem(p, kW0Bytes, smem, false, stash ? (uint32_t)(2 * (g.R0 / 2) * (g.Wo0 / 2)) * kStash0Pitch * 2 : 0u);
 }
 
 static int setup_l1(WsParams& p, const Geo& g, int B, uint32_t* smem) {
@@ -862,7 +998,7 @@ static int setup_l1(WsParams& p, const Geo& g, int B, uint32_t* smem) {
     p.n_acc = 2; p.acc_delta16 = (uint32_t)g.frame1 >> 4;
     p.ncols = g.N1; p.acc_cols = 256; p.acc_stages = 1;
     p.idesc = umma_idesc_bf16(128, g.N1);
-    return finalize_smem(p, (uint32_t)p.G * p.RW * kWeightTileBytes, smem, false, g.H2 * g.H2);
+    return finalize_smem(p, (uint32_t)p.G * p.RW * kWeightTileBytes, smem, false, (uint32_t)(g.H2 * g.H2) * kStashPitch * 2);
 }
 
 static int setup_l2(WsParams& p, const Geo& g, int B, uint32_t* smem) {
@@ -1008,7 +1144,7 @@ extern "C" int vd_tc_conv_layer(int layer, const void* in, const void* wimg, con
     memset(&p, 0, sizeof(p));
     const Geo g = make_geo(plan->T, plan->H);
     uint32_t smem = 0;
-    int rc = layer == 0 ? setup_l0(p, g, B, &smem) : layer == 1 ? setup_l1(p, g, B, &smem) : setup_l2(p, g, B, &smem);
+    int rc = layer == 0 ? setup_l0(p, g, B, &smem, raw == 0) : layer == 1 ? setup_l1(p, g, B, &smem) : setup_l2(p, g, B, &smem);
     if (rc) { if (rc == -2) set_error("tc conv 0: non-monotone chunk pairing"); return rc; }
     VD_REQUIRE(item_index == nullptr || layer == 0, "tc_conv_layer: item_index is only valid for layer 0");
     p.pix = (const uint8_t*)in; p.wimg = (const uint8_t*)wimg; p.item_index = item_index;
@@ -1020,7 +1156,18 @@ extern "C" int vd_tc_conv_layer(int layer, const void* in, const void* wimg, con
     p.epi.accum = raw == 3;
     if (raw >= 2) return launch<EPI_PLAIN>(p, smem, s);
     if (raw) return launch<EPI_RAW>(p, smem, s);
-    if (layer == 0) return launch<EPI_L0>(p, smem, s);
+    if (layer == 0) {
+        if (env_int("VD_TC_L0_STREAM", 1)) {
+            // input-frame streaming (WsParams::stream_pairs): same tables, columns instead of (pair, row band) tiles
+            p.stream_pairs = g.T / 2;
+            p.n_wsets = 4;
+            p.n_tiles = B * p.v_count;
+            p.tiles_per_item = p.v_count;
+            p.n_sa = g.T; p.n_sb = 1;
+            for (int c = 0; c < p.n_copies; ++c) p.copy_gofs[c] += g.frame0;        // frame i of the video is t_pad = i + 1
+        }
+        return launch<EPI_L0>(p, smem, s);
+    }
     if (layer == 1) return launch<EPI_L1>(p, smem, s);
     return launch<EPI_L2>(p, smem, s);
 }
