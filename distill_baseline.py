@@ -1,0 +1,11 @@
+"""Drop-in for the reference's distill_baseline.py (same flags, :366-417): DM / MTT on leaf synthetic videos on the
+B200 kernels (the DC method is outside the hot path)."""
+from video_distillation_b200.cli import main_baseline as main, baseline_parser
+
+if __name__ == '__main__':
+    import torch.distributed as dist
+    import os
+    if int(os.environ.get('WORLD_SIZE', '1')) > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl')
+    main(baseline_parser().parse_args())

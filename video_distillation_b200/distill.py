@@ -590,3 +590,97 @@ class MTTS2DTrainer:
             self.syn_lr.data = self.syn_lr.data.clip(min=0.001)
         self.last = dict(draws=draws, param_loss=param_loss.detach(), param_dist=param_dist.detach())
         return grand_loss.detach()
+
+
+class MTTBaselineTrainer:
+    """MTT on leaf synthetic videos (distill_baseline.py:92-108, 196-300): the unrolled ReparamModule student of
+    MTTS2DTrainer without the composer — ``x = image_syn[these]``, SGD(momentum=0.5) on the videos and on syn_lr.
+    The step batches come from ``torch.randperm(len(image_syn))`` on the HOST generator, as in the reference
+    (:235), so a seeded run reproduces its index stream."""
+
+    def __init__(self, *, num_classes, channel=3, im_size=(112, 112), frames=16, ipc=1, syn_steps=10, lr_img=1.0,
+                 lr_lr=1e-5, lr_teacher=0.001, train_lr=False, batch_syn=None, image_syn=None, device='cuda',
+                 precision='fp32'):
+        if precision not in ('fp32', 'bf16'):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        self.precision = precision
+        self.C, self.channel, self.im_size, self.frames = num_classes, channel, tuple(im_size), frames
+        self.ipc, self.syn_steps, self.lr_img, self.lr_lr, self.train_lr = ipc, syn_steps, lr_img, lr_lr, train_lr
+        self.batch_syn = batch_syn if batch_syn is not None else num_classes * ipc
+        self.rank, self.world = _world()
+        self.device = torch.device(device)
+        H, W = self.im_size
+        if image_syn is None:
+            image_syn = torch.randn(size=(num_classes * ipc, frames, channel, H, W), dtype=torch.float)
+        self.image_syn = image_syn.detach().to(self.device).contiguous().requires_grad_(True)
+        self.label_syn = torch.tensor(np.stack([np.ones(ipc) * i for i in range(0, num_classes)]), dtype=torch.long,
+                                      requires_grad=False, device=self.device).view(-1)
+        self.syn_lr = torch.tensor(lr_teacher).to(self.device).requires_grad_(train_lr)
+        self._bufs = {}
+        self.last = {}
+
+    def step(self, start_params, target_params, student_net=None, net_seed=None):
+        prev = ops.set_conv_backend('tc' if self.precision == 'bf16' else 'fp32')
+        try:
+            return self._step(start_params, target_params, student_net, net_seed)
+        finally:
+            ops.set_conv_backend(prev)
+
+    def _step(self, start_params, target_params, student_net, net_seed):
+        C, dev = self.C, self.device
+        if student_net is None:
+            if net_seed is not None:
+                torch.random.manual_seed(int(net_seed))
+                base = ConvNet3D(self.channel, C, 128, 3, 'relu', 'none', 'maxpooling', self.frames, self.im_size).to(dev)
+            else:
+                base = get_network('ConvNet3D', self.channel, C, self.im_size, frames=self.frames, dist=False).to(dev)
+            student_net = ReparamModule(base)
+        student_net.train()
+        num_params = student_net.param_numel
+
+        def flat(ps):
+            if torch.is_tensor(ps):
+                return ps.to(dev).reshape(-1)
+            return torch.cat([p.data.to(dev).reshape(-1) for p in ps], 0)
+        target = flat(target_params)
+        starting = flat(start_params)
+        student_params = [starting.clone().requires_grad_(True)]
+        chunks, draws = [], []
+        for _ in range(self.syn_steps):                                      # distill_baseline.py:231-252
+            if not chunks:
+                indices = torch.randperm(len(self.image_syn))               # host generator, like the reference
+                chunks = list(torch.split(indices, self.batch_syn))
+            these = chunks.pop().to(dev)
+            n_step = int(these.shape[0])
+            sl = slice(self.rank, None, self.world)
+
+            def shard_loss(theta, these=these, sl=sl, n_step=n_step):
+                out = student_net(self.image_syn[these[sl]], flat_param=theta)
+                return torch.nn.functional.cross_entropy(out, self.label_syn[these[sl]], reduction='sum') / n_step
+            grad = sharded_inner_grad(student_params[-1], shard_loss, self.world)
+            student_params.append(student_params[-1] - self.syn_lr * grad)
+            draws.append(these)
+        param_loss = torch.nn.functional.mse_loss(student_params[-1], target, reduction='sum') / num_params
+        param_dist = torch.nn.functional.mse_loss(starting, target, reduction='sum') / num_params
+        grand_loss = param_loss / param_dist
+        self.image_syn.grad = None
+        self.syn_lr.grad = None
+        grand_loss.backward()
+        if self.world > 1:
+            allreduce_sum_([self.image_syn.grad])
+        first = 'img' not in self._bufs
+        if first:
+            self._bufs['img'] = torch.empty_like(self.image_syn)
+        ops.sgd_momentum_(self.image_syn.data, self.image_syn.grad.contiguous(), self._bufs['img'], self.lr_img, 0.5, first)
+        if self.train_lr:
+            g = self.syn_lr.grad.reshape(1)
+            p = self.syn_lr.data.reshape(1)
+            first = 'lr' not in self._bufs
+            if first:
+                self._bufs['lr'] = torch.empty_like(p)
+            buf = self._bufs['lr']
+            buf.copy_(g) if first else buf.mul_(0.5).add_(g)
+            p.sub_(self.lr_lr * buf)
+            self.syn_lr.data = self.syn_lr.data.clip(min=0.001)
+        self.last = dict(draws=draws, param_loss=param_loss.detach(), param_dist=param_dist.detach())
+        return grand_loss.detach()

@@ -202,3 +202,45 @@ def _evaluate_synset(it_eval, net, images_train, labels_train, testloader, args,
         print('%s Evaluate_%02d: Ep %d time = %ds loss = %.6f train acc = %.2f, test acc = %.2f' % (
             get_time(), it_eval, Epoch, int(time.time() - start), loss_train, acc_train * 100, acc_test * 100))
     return net, acc_train, acc_test, acc_per
+
+
+def get_loops(ipc, dataset=None):
+    """utils.py:691-709 (outer / inner loop counts of the DC baselines; the distillation drivers only print them)."""
+    table = {1: (1, 1), 5: (1, 1), 10: (10, 50), 20: (20, 25), 30: (30, 20), 40: (40, 15), 50: (50, 10)}
+    if ipc not in table:
+        raise SystemExit('loop hyper-parameters are not defined for %d ipc' % ipc)
+    return table[ipc]
+
+
+class ParamDiffAug:
+    """utils.py:999-1009: parameter bag of the differentiable augmentation (unused by the video scripts' DM / MTT paths)."""
+
+    def __init__(self):
+        self.aug_mode = 'S'
+        self.prob_flip = 0.5
+        self.ratio_scale = 1.2
+        self.ratio_rotate = 15.0
+        self.ratio_crop_pad = 0.125
+        self.ratio_cutout = 0.5
+        self.brightness = 1.0
+        self.saturation = 2.0
+        self.contrast = 0.5
+
+
+def _off_path(name):
+    def fn(*args, **kwargs):
+        raise NotImplementedError(f'{name} belongs to the DC / DSA baselines of the reference, which are outside the B200 hot path '
+                                  f'(SURVEY.md §2); the DM and MTT paths never call it')
+    fn.__name__ = name
+    return fn
+
+
+DiffAugment = _off_path('DiffAugment')
+match_loss = _off_path('match_loss')
+get_daparam = _off_path('get_daparam')
+
+
+def get_dataset(dataset, data_path, batch_size=256, num_workers=0):
+    """utils.py:118 — see video_distillation_b200/datasets.py for what is supported."""
+    from .datasets import get_dataset as _get
+    return _get(dataset, data_path, batch_size, num_workers)
