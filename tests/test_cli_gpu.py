@@ -32,7 +32,7 @@ def test_buffer_then_mtt_and_dm(tmp_path):
     tr = _run('s2d_parser', 'main_s2d', f'--method MTT --dataset {DATA} --vpc 1 --spc 2 --dpc 2 --frames 8 --syn_steps 2 --expert_epochs 1 '
                                         f'--max_start_epoch 1 --lr_teacher 0.01 --lr_dynamic 10 --lr_hal 0.01 --no_train_static --train_lr '
                                         f'--Iteration 1 --startIt 5 --buffer_path {buf} --save_path {save} --precision fp32')
-    assert torch.isfinite(tr.dynamic_syn).all() and tr.dynamic_syn.grad.abs().sum() > 0 and float(tr.syn_lr) >= 0.001
+    assert torch.isfinite(tr.dynamic_syn).all() and tr.dynamic_syn.grad.abs().sum() > 0 and float(tr.syn_lr.detach()) >= 0.001
 
     # DM + S2D on the tensor-core path with one (1-epoch) evaluation and the reference's checkpoint files
     tr = _run('s2d_parser', 'main_s2d', f'--method DM --dataset {DATA} --vpc 1 --spc 2 --dpc 2 --frames 8 --batch_real 4 --no_train_static '
@@ -41,7 +41,7 @@ def test_buffer_then_mtt_and_dm(tmp_path):
     d = os.path.join(save, 'S2D_DM', 't')
     dyn = torch.load(os.path.join(d, 'dynamic_0.pt'))
     hal = torch.load(os.path.join(d, 'hal_0.pt'))
-    assert tuple(dyn.shape) == (6, 8, 1, 64, 64) and set(hal) == {'encoder.weight', 'encoder.bias'}
+    assert tuple(dyn.shape) == (6, 8, 1, 64, 64) and set(hal) == {'0.encoder.weight', '0.encoder.bias'}
     assert os.path.exists(os.path.join(d, 'weights_best.pt')) and not os.path.exists(os.path.join(d, 'images_0.pt'))
     assert tr.dynamic_syn.grad.abs().sum() > 0
 

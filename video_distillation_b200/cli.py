@@ -5,7 +5,7 @@
     buffer.py           (:107-131)   expert-trajectory producer (replay_buffer_{n}.pt)
 
 Same flags, defaults, evaluation / checkpoint cadence and file formats (``images_{it}.pt``, ``dynamic_{it}.pt`` =
-``dynamic_syn.flatten(0, 1)``, ``hal_{it}.pt`` = hallucinator state_dict, ``weights_best.pt``, ``replay_buffer_{n}.pt`` =
+``dynamic_syn.flatten(0, 1)``, ``hal_{it}.pt`` = state_dict of the hallucinator ModuleList, ``weights_best.pt``, ``replay_buffer_{n}.pt`` =
 ``list[trajectory] of list[epoch] of list[8 CPU tensors]``), but the loop bodies are the batched trainers of
 ``distill.py`` on the hand-written kernels, one process per GPU (launch with torchrun to shard classes across GPUs;
 rank 0 evaluates and saves).  Not reproduced: wandb logging (plain prints; ``wandb.run.name`` in the save path becomes
@@ -266,7 +266,11 @@ def main_s2d(args):
         raise NotImplementedError('Method {} not implemented'.format(args.method))
 
     def payload():
-        return [copy.deepcopy(tr.static_syn.detach()), copy.deepcopy(tr.dynamic_syn.detach()), copy.deepcopy(tr.hal)], None
+        return [copy.deepcopy(tr.static_syn.detach()), copy.deepcopy(tr.dynamic_syn.detach()), nn.ModuleList([copy.deepcopy(tr.hal)])], None
+
+    def hals_state():
+        # the reference saves the state_dict of `hals = nn.ModuleList([Conv3DNet()])` (:96, :186): keys '0.encoder.weight/bias'
+        return nn.ModuleList([tr.hal]).state_dict()
 
     for it in range(0, args.Iteration + 1):
         save_this_it = False
@@ -282,12 +286,12 @@ def main_s2d(args):
                 dynamic_save = tr.dynamic_syn.flatten(0, 1).detach()
                 if not args.no_train_static:
                     torch.save(image_save.cpu(), os.path.join(save_dir, 'images_{}.pt'.format(it)))
-                torch.save(tr.hal.state_dict(), os.path.join(save_dir, 'hal_{}.pt'.format(it)))
+                torch.save(hals_state(), os.path.join(save_dir, 'hal_{}.pt'.format(it)))
                 torch.save(dynamic_save.cpu(), os.path.join(save_dir, 'dynamic_{}.pt'.format(it)))
                 if save_this_it:
                     if not args.no_train_static:
                         torch.save(image_save.cpu(), os.path.join(save_dir, 'images_best.pt'))
-                    torch.save(tr.hal.state_dict(), os.path.join(save_dir, 'weights_best.pt'))
+                    torch.save(hals_state(), os.path.join(save_dir, 'weights_best.pt'))
                     torch.save(dynamic_save.cpu(), os.path.join(save_dir, 'dynamic_best.pt'))
         if args.method == 'MTT':
             start, target, start_epoch = experts.draw()
