@@ -33,6 +33,6 @@ def dump(parser):
 
 
 if __name__ == '__main__':
-    data = {s: dump(parser_of(s)) for s in ('distill_s2d_ms.py', 'distill_baseline.py', 'buffer.py')}
+    data = {s: dump(parser_of(s)) for s in ('distill_s2d_ms.py', 'distill_baseline.py', 'buffer.py', 'distill_coreset.py')}
     json.dump(data, open(OUT, 'w'), indent=1, sort_keys=True)
     print('wrote', OUT, {k: len(v) for k, v in data.items()})

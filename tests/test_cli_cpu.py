@@ -14,7 +14,7 @@ EXTRA = {'--precision', '--run_name'}
 
 
 @pytest.mark.parametrize('script,make', [('distill_s2d_ms.py', cli.s2d_parser), ('distill_baseline.py', cli.baseline_parser),
-                                         ('buffer.py', cli.buffer_parser)])
+                                         ('buffer.py', cli.buffer_parser), ('distill_coreset.py', cli.coreset_parser)])
 def test_flags_match_reference(script, make):
     parser = make()
     ours = {a.option_strings[0]: a for a in parser._actions if a.option_strings and a.dest != 'help'}

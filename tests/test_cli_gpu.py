@@ -61,3 +61,10 @@ def test_baseline_dm_and_mtt(tmp_path):
                                                    f'--epoch_eval_train 1 --batch_train 3 --buffer_path {buf} --save_path {save} --run_name m '
                                                    f'--precision fp32')
     assert torch.isfinite(tr.image_syn).all() and tr.image_syn.grad.abs().sum() > 0
+
+
+def test_coreset_driver(tmp_path):
+    img, lab, chosen, best = _run('coreset_parser', 'main_coreset', f'--dataset {DATA} --method herding --ipc 2 --frames 8 --num_eval 1 '
+                                                                    f'--epoch_eval_train 1 --batch_train 6 --lr_net 0.01')
+    assert tuple(img.shape) == (6, 8, 3, 64, 64) and lab.tolist() == [0, 0, 1, 1, 2, 2]
+    assert all(i // 6 == c for i, c in zip(chosen, lab.tolist())) and len(set(chosen)) == 6

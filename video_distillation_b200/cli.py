@@ -133,6 +133,27 @@ def buffer_parser():
     return _extra(parser)
 
 
+def coreset_parser():
+    """distill_coreset.py:148-167, flag for flag."""
+    parser = argparse.ArgumentParser(description='Parameter Processing')
+    parser.add_argument('--dataset', type=str, default='miniUCF101', help='dataset')
+    parser.add_argument('--method', type=str, default='k-center', help='k-center or herding')
+    parser.add_argument('--model', type=str, default='ConvNet3D', help='model')
+    parser.add_argument('--ipc', type=int, default=1, help='image(s) per class')
+    parser.add_argument('--eval_mode', type=str, default='S', help='eval_mode, check utils.py for more info')
+    parser.add_argument('--num_eval', type=int, default=5, help='how many networks to evaluate on')
+    parser.add_argument('--epoch_eval_train', type=int, default=1000, help='epochs to train a model with synthetic data')
+    parser.add_argument('--lr_net', type=float, default=0.001, help='learning rate for network')
+    parser.add_argument('--batch_train', type=int, default=256, help='batch size for training networks')
+    parser.add_argument('--data_path', type=str, default='distill_utils/data', help='dataset path')
+    parser.add_argument('--pretrained_path', type=str, default=None, help='pretrained model path')
+    parser.add_argument('--num_workers', type=int, default=8, help='')
+    parser.add_argument('--save_path', type=str, default='.', help='path to save')
+    parser.add_argument('--frames', type=int, default=16, help='')
+    parser.add_argument('--preload', action='store_true', help='preload dataset')
+    return _extra(parser)
+
+
 # ------------------------------------------------------------------------------------------ shared pieces
 def _require_cuda():
     if not torch.cuda.is_available():
@@ -431,3 +452,38 @@ def main_buffer(args):
                 trajectories = []
     finally:
         ops.set_conv_backend(prev)
+
+
+# ------------------------------------------------------------------------------------------ distill_coreset.py
+def main_coreset(args):
+    """distill_coreset.py:24-144: k-center / herding over ConvNet3D embeddings of every training video, then the usual
+    evaluation of the selected set.  Embeddings: tensor-core path (precision bf16) or the exact fp32 kernels."""
+    from .coreset import select_coreset
+    from .tc import TcConvNet3D, tc_supported
+    dev, rank, world = _require_cuda()
+    args.device = str(dev)
+    model_eval_pool = get_eval_pool(args.eval_mode, args.model, args.model)
+    channel, im_size, num_classes, class_names, mean, std, dst_train, dst_test, testloader = get_dataset(args.dataset, args.data_path)
+    videos, labels = _tensors_of(dst_train)
+    videos = videos.to(dev)
+    net = get_network(args.model, channel, num_classes, im_size, frames=args.frames).to(dev)
+    for param in net.parameters():
+        param.requires_grad = False
+    if args.pretrained_path is not None:
+        print('Loading pretrained model')
+        net.load_state_dict(torch.load(args.pretrained_path))
+    net.eval()
+    if args.precision == 'bf16' and tc_supported(args.frames, im_size[0], im_size[1]):
+        tc = TcConvNet3D(args.frames, im_size[0], im_size[1], dev, max_batch=256)
+        f = net.features
+        tc.load_weights(f[0].weight, f[0].bias, f[3].weight, f[3].bias, f[6].weight, f[6].bias)
+        embed = tc.embed
+    else:
+        embed = net.embed
+    image_syn, label_syn, chosen = select_coreset(embed, videos, labels, num_classes, args.ipc, args.method)
+    print('Synthetic data generated by %s: dataset indices %s' % (args.method, chosen))
+    best_acc = {m: 0 for m in model_eval_pool}
+    best_std = {m: 0 for m in model_eval_pool}
+    _evaluate(args, 0, model_eval_pool, channel, num_classes, im_size, lambda: (image_syn.detach().clone(), label_syn.detach().clone()),
+              testloader, 'none', best_acc, best_std, test_freq=100)
+    return image_syn, label_syn, chosen, best_acc
