@@ -141,6 +141,18 @@ __global__ void __launch_bounds__(256) col2im_kernel(const T* __restrict__ colbu
         if ((unsigned)to >= (unsigned)b.To) continue;                 // block-uniform
         __syncthreads();
         const int pix0 = (to * b.Ho + k.ho0) * b.Wo;
+        // bf16 columns whose staged pixel range is one 16-byte aligned run inside a column tile: 8 elements per load
+        const int nt0 = (int)__umulhi((uint32_t)pix0, b.nc_magic), col0 = pix0 - nt0 * b.NC;
+        if (sizeof(T) == 2 && (k.npix & 7) == 0 && (col0 & 7) == 0 && (b.NC & 7) == 0 && col0 + k.npix <= b.NC && (pitch & 7) == 0) {
+            const int v8 = k.npix >> 3;
+            for (int i = threadIdx.x; i < cib * 49 * v8; i += blockDim.x) {
+                const int row = i / v8, jv = i - row * v8;
+                const int cl = row / 49, tap = row - cl * 49;
+                const int r = (k.ci0 + cl) * 147 + kt * 49 + tap;
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(colv + (((int64_t)nt0 * b.NU + (r >> 7)) * 128 + (r & 127)) * b.NC + col0) + jv);
+                *reinterpret_cast<uint4*>(smT + row * pitch + jv * 8) = v;
+            }
+        } else
         for (int i = threadIdx.x; i < cib * 49 * k.npix; i += blockDim.x) {
             const int row = i / k.npix, j = i - row * k.npix;        // row = ci_local * 49 + tap
             const int cl = row / 49, tap = row - cl * 49;
@@ -154,7 +166,8 @@ __global__ void __launch_bounds__(256) col2im_kernel(const T* __restrict__ colbu
         for (int j = 0; j < kC2iMaxOut; ++j) {
             const int i = threadIdx.x + j * 256;
             if (i < n_all) {
-                const int cl = i / n_out, o = i - cl * n_out;
+                // routed bf16 output: channel fastest, so that the 8 channels of a dY chunk are written by neighbouring threads
+                const int cl = code ? i % cib : i / n_out, o = code ? i / cib : i - cl * n_out;
                 const int hl = o / b.Wi, w = o - hl * b.Wi;
                 acc[j] += c2i_taps<T>(smT + cl * 49 * pitch, pitch, b, k.ho0, k.hb + hl, w);
             }
@@ -164,7 +177,7 @@ __global__ void __launch_bounds__(256) col2im_kernel(const T* __restrict__ colbu
     for (int j = 0; j < kC2iMaxOut; ++j) {
         const int i = threadIdx.x + j * 256;
         if (i >= n_all) continue;
-        const int cl = i / n_out, o = i - cl * n_out;
+        const int cl = code ? i % cib : i / n_out, o = code ? i / cib : i - cl * n_out;
         const int hl = o / b.Wi, w = o - hl * b.Wi, h = k.hb + hl, ci = k.ci0 + cl;
         if (code == nullptr) {                            // fp32 gradient: (B,T,Cin,H,W) video layout or plain NCDHW
             float* dv = reinterpret_cast<float*>(out);
