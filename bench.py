@@ -379,7 +379,7 @@ def run_ours(args):
         ms16 = timed(step_streaming16, e2e_steps)
         e2e_bf16 = {'value': e2e_steps / (ms16 / 1000.0), 'unit': 'it/s', 'h2d_bytes_per_step': int(C * BATCH_REAL * bytes_video // 2),
                     'd2h_bytes_per_step': 4, 'steps': e2e_steps,
-                    'note': 'host copy of the real set stored as bf16 (converted once at load); per step 3200 sampled videos over PCIe'}
+                    'note': f'host copy of the real set stored as bf16 (converted once at load); per step {C * BATCH_REAL} sampled videos over PCIe'}
         torch.cuda.synchronize()
         del host16, stages16, stage32
 
@@ -420,7 +420,7 @@ def run_ours(args):
     peak = float(peaks.get('bf16_tflops_sustained', peaks.get('bf16_tflops', 1400.0)))
     traffic = None
     tpath = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
-    if os.path.exists(tpath):                       # DRAM bytes per launch from the committed ncu --set full capture
+    if os.path.exists(tpath) and (T, HW) == (16, 112):      # DRAM bytes per launch from the committed ncu --set full capture (U shape)
         tj = json.load(open(tpath))['dram_bytes_per_video']['conv1']
         traffic = (tj['read'] + tj['write']) * layer_videos[1] / max(1, layer_launches[1])
     roofline = {'bound': 'tensor', 'kernel': 'ws_gemm_kernel<EPI_L1> (conv 1, 64->128)', 'achieved': achieved, 'peak': peak,
@@ -438,11 +438,11 @@ def run_ours(args):
         'metric': 'DM+S2D distill iters/sec', 'value': value, 'unit': 'it/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'strong',
         'vs_baseline': None, 'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
-        'config': {'workload': 'DM+S2D miniUCF101-shape: 50 classes, videos 16x3x112x112, vpc=1 spc=2 dpc=2, batch_real=64 '
-                               '(BASELINE.json configs[1]); fresh frozen ConvNet3D per step',
+        'config': {'workload': WORKLOAD_DESC,
                    'parallelism': f'classes sharded c%{world}, one NCCL all-reduce/step' if world > 1 else 'single GPU',
                    'real_videos_per_step': C * BATCH_REAL, 'syn_videos_per_step': C * VPC,
-                   'l2_policy': 'inputs larger than L2: each step reads 3200 distinct real videos (7.7 GB fp32)',
+                   'l2_policy': f'inputs larger than L2: each step reads {C * BATCH_REAL} distinct real videos '
+                                f'({C * BATCH_REAL * T * 3 * HW * HW * 4 / 1e9:.1f} GB fp32)',
                    'real_embed': 'tcgen05 bf16 operands / fp32 accumulate' if args.precision == 'bf16' else 'fp32 CUDA cores',
                    'syn_branch': args.syn_mode,
                    'real_set': 'resident fp32' + ('' if args.no_prepack else ' + pre-packed bf16 conv-0 operand (one-time)'),
@@ -450,7 +450,7 @@ def run_ours(args):
         'clocks': clocks, 'gpu_launches': int(launches),
         'e2e': {'value': e2e_stream, 'unit': 'it/s', 'h2d_bytes_per_step': int(C * BATCH_REAL * bytes_video),
                 'd2h_bytes_per_step': 4, 'steps': e2e_steps,
-                'note': 'per step: 3200 sampled real videos (fp32) copied from pinned host memory, double-buffered on a copy stream, + loss.item()'},
+                'note': f'per step: {C * BATCH_REAL} sampled real videos (fp32) copied from pinned host memory, double-buffered on a copy stream, + loss.item()'},
         'e2e_resident': {'value': e2e_res, 'unit': 'it/s', 'h2d_bytes_per_step': int(C * BATCH_REAL * 8),
                          'd2h_bytes_per_step': 4, 'steps': e2e_steps,
                          'note': 'real set uploaded once; per step the host sends the sampled index table and reads the loss'},
@@ -460,6 +460,22 @@ def run_ours(args):
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+WORKLOAD_DESC = ''
+WORKLOADS = {   # name -> (C, T, HW, vpc, spc, dpc, batch_real, per_class, FLOP per video L0/L1/L2, BASELINE.json config)
+    'U-ipc1': (50, 16, 112, 1, 2, 2, 64, 72, (2.832e9, 7.553e9, 0.617e9), 'configs[1]'),
+    'U-ipc5': (50, 16, 112, 5, 10, 10, 64, 72, (2.832e9, 7.553e9, 0.617e9), 'configs[2]'),
+    'K-ipc5': (400, 8, 64, 5, 10, 10, 64, 64, (0.462e9, 1.233e9, 0.077e9), 'configs[4]'),
+}
+
+
+def set_workload(name):
+    global C, T, HW, VPC, SPC, DPC, BATCH_REAL, PER_CLASS, F_L0, F_L1, F_L2, F_EMBED, WORKLOAD_DESC
+    C, T, HW, VPC, SPC, DPC, BATCH_REAL, PER_CLASS, (F_L0, F_L1, F_L2), cfg = WORKLOADS[name]
+    F_EMBED = F_L0 + F_L1 + F_L2
+    WORKLOAD_DESC = (f'DM+S2D {"miniUCF101" if HW == 112 else "Kinetics-400"}-shape: {C} classes, videos {T}x3x{HW}x{HW}, vpc={VPC} spc={SPC} '
+                     f'dpc={DPC}, batch_real={BATCH_REAL} (BASELINE.json {cfg}); fresh frozen ConvNet3D per step')
 
 
 def main():
@@ -475,7 +491,11 @@ def main():
                     help='synthetic branch: fused bf16 tensor-core pipeline (throughput), split-bf16 trio with fp32 '
                          'activations (gradients within 1e-2 of fp32), or the exact fp32 CUDA-core kernels')
     ap.add_argument('--no-prepack', action='store_true', help='pack the sampled real videos every step instead of once')
+    ap.add_argument('--workload', default='U-ipc1', choices=sorted(WORKLOADS),
+                    help='U-ipc1 = the metric workload (BASELINE.json configs[1], default); U-ipc5 / K-ipc5 = configs[2] / configs[4] '
+                         '(parity-test shapes, timed on request)')
     args = ap.parse_args()
+    set_workload(args.workload)
     if args.impl == 'reference':
         run_reference(args)
     else:

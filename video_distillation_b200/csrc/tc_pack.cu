@@ -14,23 +14,33 @@ __device__ __forceinline__ float bf16_part(float v, int part) {
     return part == 0 ? v : v - __uint_as_float((uint32_t)f2bf(v) << 16);
 }
 
-__global__ void pack_video_kernel(const float* __restrict__ video, const int64_t* __restrict__ index,
-                                  uint4* __restrict__ x0, int64_t total, int T, int HW, int RI0, int Wo0, int part, int ncdhw) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        int wo = (int)(i % Wo0); int64_t q = i / Wo0;
-        int row = (int)(q % RI0); q /= RI0;
-        int par = (int)(q % 2); q /= 2;
-        int c = (int)(q % 3); q /= 3;
-        int tp = (int)(q % (T + 2)); int64_t b = q / (T + 2);
-        const int t = tp - 1;
+// one block per (video, padded frame, channel, row parity) plane of RI0 x Wo0 chunks: the plane indices come from the block
+// index (no 64-bit divisions per chunk), the threads walk the plane with coalesced 16-byte stores
+__global__ void __launch_bounds__(256) pack_video_kernel(const float* __restrict__ video, const int64_t* __restrict__ index,
+                                                         uint4* __restrict__ x0, int T, int HW, int RI0, int Wo0, int part, int ncdhw) {
+    int q = blockIdx.x;
+    const int par = q & 1; q >>= 1;
+    const int c = q % 3; q /= 3;
+    const int tp = q % (T + 2);
+    const int64_t b = q / (T + 2);
+    const int t = tp - 1;
+    uint4* dst = x0 + (int64_t)blockIdx.x * RI0 * Wo0;
+    const int n = RI0 * Wo0;
+    if (t < 0 || t >= T) {                                   // temporal halo frame: zeros
+        for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = make_uint4(0u, 0u, 0u, 0u);
+        return;
+    }
+    const int64_t src = index ? index[b] : b;
+    const int64_t plane = ncdhw ? (src * 3 + c) * T + t : (src * T + t) * 3 + c;     // (B,3,T,H,W) or (B,T,3,H,W)
+    const float* pl = video + plane * HW * (int64_t)HW;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int row = i / Wo0, wo = i - row * Wo0;
         const int h = par ? 2 * row - 3 : 2 * row - 2;
         uint16_t v[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) v[k] = 0;
-        if (t >= 0 && t < T && h >= 0 && h < HW) {
-            const int64_t src = index ? index[b] : b;
-            const int64_t plane = ncdhw ? (src * 3 + c) * T + t : (src * T + t) * 3 + c;     // (B,3,T,H,W) or (B,T,3,H,W)
-            const float* p = video + (plane * HW + h) * (int64_t)HW;
+        if (h >= 0 && h < HW) {
+            const float* p = pl + (int64_t)h * HW;
 #pragma unroll
             for (int k = 0; k < 7; ++k) {
                 const int w = 2 * wo + k - 3;
@@ -40,7 +50,7 @@ __global__ void pack_video_kernel(const float* __restrict__ video, const int64_t
         uint4 o;
         o.x = v[0] | ((uint32_t)v[1] << 16); o.y = v[2] | ((uint32_t)v[3] << 16);
         o.z = v[4] | ((uint32_t)v[5] << 16); o.w = v[6] | ((uint32_t)v[7] << 16);
-        x0[i] = o;
+        dst[i] = o;
     }
 }
 
@@ -105,11 +115,9 @@ static int pack_video_impl(const float* video, const int64_t* index, void* x0, c
     VD_REQUIRE(geo_supported(plan->T, plan->H), "tc_pack_video: unsupported geometry");
     if (B <= 0) return 0;
     const Geo g = make_geo(plan->T, plan->H);
-    const int64_t total = (int64_t)B * (g.T + 2) * 6 * g.RI0 * g.Wo0;
-    int64_t blocks = ceil_div(total, 256);
-    if (blocks > 148 * 32) blocks = 148 * 32;
-    pack_video_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(video, index, (uint4*)x0, total, g.T, g.HW, g.RI0, g.Wo0,
-                                                                          part, ncdhw);
+    const int64_t blocks = (int64_t)B * (g.T + 2) * 6;                       // planes [b][t_pad][c][par]
+    VD_REQUIRE(blocks < (1ll << 31), "tc_pack_video: grid too large");
+    pack_video_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(video, index, (uint4*)x0, g.T, g.HW, g.RI0, g.Wo0, part, ncdhw);
     return check_launch("tc_pack_video");
 }
 
