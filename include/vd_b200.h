@@ -168,6 +168,11 @@ int vd_tc_plan_make(vd_tc_plan* plan, int T, int H, int W);
  * video of each item: the device-resident form of get_images (distill_s2d_ms.py:81-87). */
 int vd_tc_pack_video(const float* video, const int64_t* index, void* x0, const vd_tc_plan* plan,
                      int B, void* stream);
+/* Same packing from uint8 frames (B,T,3,H,W) with the dataset normalisation fused in: v = (u/255 - mean[c]) / std[c]
+ * (reference: ToTensor + Normalize of the dataset transforms, utils.py:214-230), rounded to bf16.  mean3 / std3 are HOST
+ * pointers to three floats.  Lets a host-resident real set cross PCIe as 1 byte per element (get_images, distill_s2d_ms.py:81-87). */
+int vd_tc_pack_video_u8(const uint8_t* video, const int64_t* index, void* x0, const vd_tc_plan* plan, int B,
+                        const float* mean3, const float* std3, void* stream);
 /* fp32 OIDHW weights of features.{0,3,6} -> UMMA weight images (any pair may be NULL to skip).
  * w0 is the frame-pair-stacked form. */
 int vd_tc_pack_weights(const float* w_l0, const float* w_l1, const float* w_l2,

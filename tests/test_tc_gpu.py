@@ -276,3 +276,23 @@ def test_tensor_core_trio_matches_fp32_kernels(T, HW):
         # conv 1: column-free dgrad, fp32 accumulators straight to the output; conv 0 / 2: fp32 column buffers
         assert rel(gx, gx_ref) < 1e-5, (layer, 'dgrad', rel(gx, gx_ref))
         assert rel(gw, gw_ref) < 1e-5, (layer, 'wgrad', rel(gw, gw_ref))
+
+
+@pytest.mark.parametrize('T,HW', CASES)
+def test_uint8_packer_fuses_the_dataset_normalisation_bit_exactly(T, HW):
+    """vd_tc_pack_video_u8(frames) == vd_tc_pack_video((frames / 255 - mean) / std): the packed bf16 operands (and hence
+    every embedding) are identical whether the normalised fp32 videos or the raw uint8 frames are handed over."""
+    from video_distillation_b200.tc import TcConvNet3D
+    tc = TcConvNet3D(T, HW, HW, 'cuda', max_batch=8)
+    mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+    tc.set_normalization(mean, std)
+    g = torch.Generator(device='cuda').manual_seed(T * HW)
+    frames = torch.randint(0, 256, (5, T, 3, HW, HW), dtype=torch.uint8, device='cuda', generator=g)
+    m = torch.tensor(mean, device='cuda').view(1, 1, 3, 1, 1)
+    s = torch.tensor(std, device='cuda').view(1, 1, 3, 1, 1)
+    video = ((frames.float() / 255.0) - m) / s
+    idx = torch.tensor([3, 0, 4, 4, 1], device='cuda')
+    n = 5 * tc.plan.x0_bytes_per_video
+    a = tc.pack_video(video, idx, out=torch.empty(n, dtype=torch.uint8, device='cuda')).clone()
+    b = tc.pack_video(frames, idx, out=torch.empty(n, dtype=torch.uint8, device='cuda')).clone()
+    assert torch.equal(a, b)

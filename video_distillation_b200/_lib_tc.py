@@ -8,6 +8,7 @@ def declare(lib):
     sig = {
         'vd_tc_plan_make': (c_int, [POINTER(TcPlan), c_int, c_int, c_int]),
         'vd_tc_pack_video': (c_int, [P, P, P, POINTER(TcPlan), c_int, P]),
+        'vd_tc_pack_video_u8': (c_int, [P, P, P, POINTER(TcPlan), c_int, P, P, P]),
         'vd_tc_pack_weights': (c_int, [P, P, P, P, P, P, P]),
         'vd_tc_conv_layer': (c_int, [c_int, P, P, P, P, P, c_int, POINTER(TcPlan), P, c_int, c_int, P]),
         'vd_tc_pack_weights_bwd': (c_int, [P, P, P, P, P, P, P]),

@@ -54,6 +54,49 @@ __global__ void __launch_bounds__(256) pack_video_kernel(const float* __restrict
     }
 }
 
+// uint8 frames (B,T,3,H,W) -> X0 with the dataset normalisation fused in: v = (u / 255 - mean[c]) / std[c] in fp32 (the same three
+// IEEE operations ToTensor + Normalize perform on the host, utils.py:214-230 of the reference), rounded to bf16.  A host-resident
+// real set then crosses PCIe as one byte per element instead of four.
+struct NormU8 { float mean[3]; float stdv[3]; };
+
+__global__ void __launch_bounds__(256) pack_video_u8_kernel(const uint8_t* __restrict__ video, const int64_t* __restrict__ index,
+                                                            uint4* __restrict__ x0, int T, int HW, int RI0, int Wo0, NormU8 nm) {
+    int q = blockIdx.x;
+    const int par = q & 1; q >>= 1;
+    const int c = q % 3; q /= 3;
+    const int tp = q % (T + 2);
+    const int64_t b = q / (T + 2);
+    const int t = tp - 1;
+    uint4* dst = x0 + (int64_t)blockIdx.x * RI0 * Wo0;
+    const int n = RI0 * Wo0;
+    if (t < 0 || t >= T) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = make_uint4(0u, 0u, 0u, 0u);
+        return;
+    }
+    const int64_t src = index ? index[b] : b;
+    const uint8_t* pl = video + ((src * T + t) * 3 + c) * HW * (int64_t)HW;
+    const float mean = nm.mean[c], stdv = nm.stdv[c];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int row = i / Wo0, wo = i - row * Wo0;
+        const int h = par ? 2 * row - 3 : 2 * row - 2;
+        uint16_t v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = 0;
+        if (h >= 0 && h < HW) {
+            const uint8_t* p = pl + (int64_t)h * HW;
+#pragma unroll
+            for (int k = 0; k < 7; ++k) {
+                const int w = 2 * wo + k - 3;
+                if (w >= 0 && w < HW) v[k] = f2bf(__fdiv_rn(__fsub_rn(__fdiv_rn((float)__ldg(p + w), 255.f), mean), stdv));
+            }
+        }
+        uint4 o;
+        o.x = v[0] | ((uint32_t)v[1] << 16); o.y = v[2] | ((uint32_t)v[3] << 16);
+        o.z = v[4] | ((uint32_t)v[5] << 16); o.w = v[6] | ((uint32_t)v[7] << 16);
+        dst[i] = o;
+    }
+}
+
 // conv 0 image: [p 11][k 2][blk 5][64][8] bf16; blk 0,4 = zero, blk b = W[kt = 3-b]
 __global__ void pack_w0_kernel(const float* __restrict__ w, uint16_t* __restrict__ img, int part) {
     const int total = kW0Bytes / 2;
@@ -119,6 +162,21 @@ static int pack_video_impl(const float* video, const int64_t* index, void* x0, c
     VD_REQUIRE(blocks < (1ll << 31), "tc_pack_video: grid too large");
     pack_video_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(video, index, (uint4*)x0, g.T, g.HW, g.RI0, g.Wo0, part, ncdhw);
     return check_launch("tc_pack_video");
+}
+
+extern "C" int vd_tc_pack_video_u8(const uint8_t* video, const int64_t* index, void* x0, const vd_tc_plan* plan, int B,
+                                   const float* mean3, const float* std3, void* stream) {
+    VD_REQUIRE(video && x0 && plan && B >= 0 && mean3 && std3, "tc_pack_video_u8: bad argument");
+    VD_REQUIRE(geo_supported(plan->T, plan->H), "tc_pack_video_u8: unsupported geometry");
+    VD_REQUIRE(std3[0] != 0.f && std3[1] != 0.f && std3[2] != 0.f, "tc_pack_video_u8: std must be non-zero");
+    if (B == 0) return 0;
+    const Geo g = make_geo(plan->T, plan->H);
+    NormU8 nm;
+    for (int c = 0; c < 3; ++c) { nm.mean[c] = mean3[c]; nm.stdv[c] = std3[c]; }
+    const int64_t blocks = (int64_t)B * (g.T + 2) * 6;
+    VD_REQUIRE(blocks < (1ll << 31), "tc_pack_video_u8: grid too large");
+    pack_video_u8_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(video, index, (uint4*)x0, g.T, g.HW, g.RI0, g.Wo0, nm);
+    return check_launch("tc_pack_video_u8");
 }
 
 extern "C" int vd_tc_pack_video(const float* video, const int64_t* index, void* x0, const vd_tc_plan* plan,

@@ -152,15 +152,25 @@ class TcConvNet3D:
             self._a2 = torch.zeros(n4 * p.a2_bytes_per_video, dtype=torch.uint8, device=self.device)
         return self._a1, self._a2
 
+    def set_normalization(self, mean, std):
+        """Dataset normalisation applied by the uint8 packer: v = (u/255 - mean[c]) / std[c] (utils.py:214-230)."""
+        self._norm = ((ctypes.c_float * 3)(*[float(m) for m in mean]), (ctypes.c_float * 3)(*[float(s) for s in std]))
+
     def pack_video(self, video, index=None, out=None):
-        """fp32 (Bsrc,T,3,H,W) -> X0 for B = len(index) (or Bsrc) items."""
-        assert video.dtype == torch.float32 and video.dim() == 5 and tuple(video.shape[1:]) == (self.T, 3, self.H, self.W)
+        """fp32 (or uint8 frames, see set_normalization) (Bsrc,T,3,H,W) -> X0 for B = len(index) (or Bsrc) items."""
+        assert video.dtype in (torch.float32, torch.uint8) and video.dim() == 5 and tuple(video.shape[1:]) == (self.T, 3, self.H, self.W)
         B = int(index.numel()) if index is not None else int(video.shape[0])
         nbytes = B * self.plan.x0_bytes_per_video
         if out is None:
             if self._x0 is None or self._x0.numel() < nbytes:
                 self._x0 = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
             out = self._x0
+        if video.dtype == torch.uint8:
+            if getattr(self, '_norm', None) is None:
+                raise RuntimeError('uint8 videos need TcConvNet3D.set_normalization(mean, std) first')
+            _lib.check(_lib.lib().vd_tc_pack_video_u8(_lib.ptr(video), _lib.ptr(index), _lib.ptr(out), ctypes.byref(self.plan), B,
+                                                      self._norm[0], self._norm[1], _lib.stream()), 'vd_tc_pack_video_u8')
+            return out
         _lib.check(_lib.lib().vd_tc_pack_video(_lib.ptr(video), _lib.ptr(index), _lib.ptr(out),
                                                ctypes.byref(self.plan), B, _lib.stream()), 'vd_tc_pack_video')
         return out
