@@ -237,13 +237,14 @@ def run_ours(args):
     # tensor is what the reference's preloaded TensorDataset holds
     mean_t = torch.tensor(MEAN, device=dev).view(1, 1, 3, 1, 1)
     std_t = torch.tensor(STD, device=dev).view(1, 1, 3, 1, 1)
+    c255 = torch.tensor(255.0, device=dev)          # tensor divisor: a Python scalar would become a reciprocal multiply
     frames = torch.empty(len(own) * PER_CLASS, T, 3, HW, HW, dtype=torch.uint8, device=dev)
     vids = torch.empty(len(own) * PER_CLASS, T, 3, HW, HW, device=dev)
     for j, c in enumerate(own):
         g = torch.Generator(device=dev).manual_seed(1000 + c)
         fr = torch.randint(0, 256, (PER_CLASS, T, 3, HW, HW), dtype=torch.uint8, device=dev, generator=g)
         frames[j * PER_CLASS:(j + 1) * PER_CLASS] = fr
-        vids[j * PER_CLASS:(j + 1) * PER_CLASS] = ((fr.float() / 255.0) - mean_t) / std_t
+        vids[j * PER_CLASS:(j + 1) * PER_CLASS] = ((fr.float() / c255) - mean_t) / std_t       # IEEE divisions, like the host transform
     frames_host = torch.empty(frames.shape, dtype=torch.uint8, pin_memory=True)
     frames_host.copy_(frames)
     del frames

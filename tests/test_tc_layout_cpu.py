@@ -87,3 +87,14 @@ def test_plan_sizes():
             assert q.smem_total <= 232448 and q.smem_total >= 120 * 1024     # one CTA per SM (512 TMEM cols each)
             assert q.n_acc * q.acc_cols * q.acc_stages <= 512
             assert q.ncols % 16 == 0 and 16 <= q.ncols <= 256
+
+
+def test_python_and_library_agree_on_supported_geometries():
+    import ctypes
+    from video_distillation_b200 import _lib
+    from video_distillation_b200.tc import tc_supported
+    for HW in (32, 64, 96, 112, 128):
+        for T in range(1, 41):
+            plan = _lib.TcPlan()
+            ok = _lib.lib().vd_tc_plan_make(ctypes.byref(plan), T, HW, HW) == 0
+            assert ok == tc_supported(T, HW, HW), (T, HW, ok)

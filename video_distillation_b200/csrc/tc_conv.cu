@@ -1105,7 +1105,7 @@ using namespace vd::tc;
 
 extern "C" int vd_tc_plan_make(vd_tc_plan* plan, int T, int H, int W) {
     VD_REQUIRE(plan != nullptr, "tc_plan_make: NULL plan");
-    VD_REQUIRE(H == W && geo_supported(T, H), "tc path supports square 112x112 (T<=16) or 64x64 videos with T %% 4 == 0 (got T=%d H=%d W=%d)", T, H, W);
+    VD_REQUIRE(H == W && geo_supported(T, H), "tc path supports square 112x112 videos with T in {4,8,12,16} or 64x64 videos with T in {8,16,24,32} (got T=%d H=%d W=%d)", T, H, W);
     const Geo g = make_geo(T, H);
     memset(plan, 0, sizeof(*plan));
     plan->T = T; plan->H = H; plan->W = W;

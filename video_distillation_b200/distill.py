@@ -105,7 +105,12 @@ class DeviceDataset:
     distill_s2d_ms.py:73-79, so ``np.random.permutation(indices_class[c])[:n]`` is unchanged.
     """
 
-    def __init__(self, videos, labels, num_classes, device, rank=0, world=1):
+    def __init__(self, videos, labels, num_classes, device, rank=0, world=1, norm=None):
+        # ``videos`` may be the decoded uint8 frames with ``norm = (mean, std)``: the tensor-core path then normalises inside
+        # its packer ((u/255 - mean)/std, bit-identical operands) and the resident set costs 1 byte per element
+        self.norm = norm
+        if videos.dtype == torch.uint8 and norm is None:
+            raise ValueError('uint8 videos need norm=(mean, std)')
         labels = [int(v) for v in labels]
         self.num_classes = num_classes
         self.indices_class = [[] for _ in range(num_classes)]
@@ -142,12 +147,15 @@ class DeviceDataset:
         self.videos = shard_videos.contiguous()
         self.shape = tuple(shard_videos.shape[1:])
         self.x0 = None
+        self.norm = None
         return self
 
     def prepack(self, tc_net, free_fp32=False, extra_slots=0):
         """Convert the resident set once into the tensor-core path's packed bf16 conv-0 operand
         (device-resident real-data pipeline); per-iteration packing disappears.
         ``extra_slots`` spare slots let the trainer embed its synthetic videos in the same launches."""
+        if self.videos.dtype == torch.uint8:
+            tc_net.set_normalization(*self.norm)
         self.x0 = tc_net.pack_dataset(self.videos, extra_slots=extra_slots)
         self.x0_tail = int(self.videos.shape[0])
         self.x0_extra = int(extra_slots)
@@ -189,7 +197,13 @@ class DeviceDataset:
     def get_images(self, c, n):
         """Reference-compatible accessor (one class)."""
         idx = np.random.permutation(self.indices_class[c])[:n]
-        return self.videos[self.local_index(idx)]
+        v = self.videos[self.local_index(idx)]
+        if v.dtype == torch.uint8:                                         # the normalised floats the reference would hold
+            mean = torch.tensor(self.norm[0], device=v.device).view(1, 1, 3, 1, 1)
+            std = torch.tensor(self.norm[1], device=v.device).view(1, 1, 3, 1, 1)
+            # tensor / tensor: IEEE division like the host transform (a Python-scalar divisor becomes a reciprocal multiply on CUDA)
+            v = ((v.float() / torch.tensor(255.0, device=v.device)) - mean) / std
+        return v
 
 
 def frozen_convnet3d(channel, num_classes, im_size, frames, device, seed=None, init_on_device=False):

@@ -20,7 +20,11 @@ def make_plan(T, H, W):
 
 
 def tc_supported(T, H, W):
-    return H == W and H in (112, 64) and T % 4 == 0 and 4 <= T <= (16 if H == 112 else 32) and not (H == 64 and T < 8)
+    # mirrors geo_supported (csrc/tc_layout.h): 112x112 with T in {4, 8, 12, 16} (conv 2 tile <= 128 columns), 64x64 with
+    # T in {8, 16, 24, 32} (conv 2 tile = 2T columns, a multiple of 16)
+    if H != W or H not in (112, 64):
+        return False
+    return (T % 4 == 0 and 4 <= T <= 16) if H == 112 else (T % 8 == 0 and 8 <= T <= 32)
 
 
 class TcConvNet3D:
