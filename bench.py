@@ -152,7 +152,7 @@ def run_reference(args):
         'impl': 'reference', 'metric': 'DM+S2D distill iters/sec', 'value': v, 'unit': 'it/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1000.0 / v, 'higher_is_better': True,
         'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'DM+S2D miniUCF101-shape (50 cls, 16x3x112x112) ipc=1 batch_real=64, CPU oracle (torch CPU port of distill_s2d_ms.py:393-438)'},
+        'config': {'workload': WORKLOAD_DESC, 'implementation': 'CPU oracle: torch-CPU port of distill_s2d_ms.py:393-438 (oracle/dm.py), all host cores'},
         'cpu_baseline': {'value': v, 'unit': 'it/s', 'cores': threads, 'kind': 'port', 'sample': desc,
                          'sample_seconds': float(np.mean(secs))},
         'e2e': {'value': v, 'unit': 'it/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
