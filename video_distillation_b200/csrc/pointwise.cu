@@ -404,25 +404,33 @@ __global__ void class_mean_kernel(const float* __restrict__ emb, float* __restri
     mean[(int64_t)c * D + d] = s / (float)n;
 }
 
-// per class: diff = mean_real - mean(emb_syn); loss += sum diff^2; grad_syn = -(2/ns) diff * scale
-__global__ void dm_loss_kernel(const float* __restrict__ mean_real, const float* __restrict__ emb_syn,
-                               float* __restrict__ loss, float* __restrict__ grad_syn, int ns, int D, float scale) {
+// per class: diff = mean_real - mean(emb_syn); loss += sum diff^2; grad_syn = -(2/ns) diff * scale.
+// ONE block walks the classes in order: every class sum is a fixed-shape tree and the per-class sums are added in class order
+// (the order of the reference's `loss += torch.sum(...)` loop, distill_s2d_ms.py:414-422), so the scalar is bitwise
+// reproducible — no floating-point atomics.  C x D is ~1e5 elements: a ~10 us kernel either way.
+__global__ void __launch_bounds__(1024) dm_loss_kernel(const float* __restrict__ mean_real, const float* __restrict__ emb_syn,
+                                                       float* __restrict__ loss, float* __restrict__ grad_syn, int C, int ns, int D,
+                                                       float scale) {
     __shared__ float red[32];
-    const int c = blockIdx.x;
-    float part = 0.f;
-    for (int d = threadIdx.x; d < D; d += blockDim.x) {
-        float ms = 0.f;
-        for (int j = 0; j < ns; ++j) ms += emb_syn[((int64_t)c * ns + j) * D + d];
-        ms /= (float)ns;
-        const float diff = mean_real[(int64_t)c * D + d] - ms;
-        part += diff * diff;
-        if (grad_syn) {
-            const float g = -(2.0f / (float)ns) * diff * scale;
-            for (int j = 0; j < ns; ++j) grad_syn[((int64_t)c * ns + j) * D + d] = g;
+    float total = 0.f;
+    for (int c = 0; c < C; ++c) {
+        float part = 0.f;
+        for (int d = threadIdx.x; d < D; d += blockDim.x) {
+            float ms = 0.f;
+            for (int j = 0; j < ns; ++j) ms += emb_syn[((int64_t)c * ns + j) * D + d];
+            ms /= (float)ns;
+            const float diff = mean_real[(int64_t)c * D + d] - ms;
+            part += diff * diff;
+            if (grad_syn) {
+                const float g = -(2.0f / (float)ns) * diff * scale;
+                for (int j = 0; j < ns; ++j) grad_syn[((int64_t)c * ns + j) * D + d] = g;
+            }
         }
+        part = block_sum(part, red);
+        if (threadIdx.x == 0) total += part;
+        __syncthreads();                                  // `red` is reused by the next class
     }
-    part = block_sum(part, red);
-    if (threadIdx.x == 0) atomicAdd(loss, part);
+    if (threadIdx.x == 0) *loss += total;
 }
 
 // =============================================================== optimiser / flat-parameter kernels
@@ -630,7 +638,7 @@ extern "C" int vd_dm_loss_f32(const float* mean_real, const float* emb_syn, floa
                               int C, int ns, int D, float loss_scale, void* stream) {
     VD_REQUIRE(mean_real && emb_syn && loss && C >= 0 && ns > 0 && D > 0, "dm_loss: bad argument");
     if (C == 0) return 0;
-    dm_loss_kernel<<<C, 256, 0, (cudaStream_t)stream>>>(mean_real, emb_syn, loss, grad_syn, ns, D, loss_scale);
+    dm_loss_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(mean_real, emb_syn, loss, grad_syn, C, ns, D, loss_scale);
     return check_launch("dm_loss_f32");
 }
 

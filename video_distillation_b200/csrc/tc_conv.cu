@@ -321,33 +321,39 @@ constexpr int kStashPitch = 136;          // bf16 elements per position row (128
 
 __device__ __forceinline__ void epi_l1_drain(const WsParams& p, int tile, uint32_t taddr, int m, uint16_t* stash) {
     const Geo& g = p.epi.g;
-    const int item = tile / p.tiles_per_item, tp = tile % p.tiles_per_item;   // pooled frame index = tp
+    const int item = tile / p.tiles_per_item, tq = tile % p.tiles_per_item;
+    const int npair = p.n_acc >> 1;                     // accumulator pairs of the tile = pooled frames (2, or 4 accumulators at 64x64)
     const float bias = __ldg(p.epi.bias + m);
-    uint8_t* cbase = (p.epi.code && item >= p.epi.code_first)
-                         ? p.epi.code + (((int64_t)(item - p.epi.code_first) * 128 + m) * g.T2 + tp) * g.H2 * g.H2 : nullptr;
-    for (int hp = 0; hp < g.H2; ++hp) {
-        float a0[16], a1[16], b0[16], b1[16];
-        tmem_ld16(taddr + (2 * hp) * g.P1, a0);
-        tmem_ld16(taddr + (2 * hp + 1) * g.P1, a1);
-        tmem_ld16(taddr + p.acc_cols + (2 * hp) * g.P1, b0);
-        tmem_ld16(taddr + p.acc_cols + (2 * hp + 1) * g.P1, b1);
-        tmem_ld_wait();
+    for (int pp = 0; pp < npair; ++pp) {
+        const int tp = tq * npair + pp;                 // pooled frame index
+        const uint32_t ta = taddr + (uint32_t)(2 * pp) * p.acc_cols;
+        uint16_t* st = stash + pp * (g.H2 * g.H2) * kStashPitch;
+        uint8_t* cbase = (p.epi.code && item >= p.epi.code_first)
+                             ? p.epi.code + (((int64_t)(item - p.epi.code_first) * 128 + m) * g.T2 + tp) * g.H2 * g.H2 : nullptr;
+        for (int hp = 0; hp < g.H2; ++hp) {
+            float a0[16], a1[16], b0[16], b1[16];
+            tmem_ld16(ta + (2 * hp) * g.P1, a0);
+            tmem_ld16(ta + (2 * hp + 1) * g.P1, a1);
+            tmem_ld16(ta + p.acc_cols + (2 * hp) * g.P1, b0);
+            tmem_ld16(ta + p.acc_cols + (2 * hp + 1) * g.P1, b1);
+            tmem_ld_wait();
 #pragma unroll
-        for (int wp = 0; wp < 8; ++wp) {
-            if (wp < g.H2) {
-                // scan order (t,h,w)
-                float best = a0[2 * wp]; int arg = 0;
-                if (a0[2 * wp + 1] > best) { best = a0[2 * wp + 1]; arg = 1; }
-                if (a1[2 * wp] > best) { best = a1[2 * wp]; arg = 2; }
-                if (a1[2 * wp + 1] > best) { best = a1[2 * wp + 1]; arg = 3; }
-                if (b0[2 * wp] > best) { best = b0[2 * wp]; arg = 4; }
-                if (b0[2 * wp + 1] > best) { best = b0[2 * wp + 1]; arg = 5; }
-                if (b1[2 * wp] > best) { best = b1[2 * wp]; arg = 6; }
-                if (b1[2 * wp + 1] > best) { best = b1[2 * wp + 1]; arg = 7; }
-                best += bias;
-                const bool act = best > 0.f;
-                stash[(hp * g.H2 + wp) * kStashPitch + m] = f2bf(act ? best : 0.f);
-                if (cbase) cbase[hp * g.H2 + wp] = (uint8_t)(arg | (act ? 8 : 0));
+            for (int wp = 0; wp < 8; ++wp) {
+                if (wp < g.H2) {
+                    // scan order (t,h,w)
+                    float best = a0[2 * wp]; int arg = 0;
+                    if (a0[2 * wp + 1] > best) { best = a0[2 * wp + 1]; arg = 1; }
+                    if (a1[2 * wp] > best) { best = a1[2 * wp]; arg = 2; }
+                    if (a1[2 * wp + 1] > best) { best = a1[2 * wp + 1]; arg = 3; }
+                    if (b0[2 * wp] > best) { best = b0[2 * wp]; arg = 4; }
+                    if (b0[2 * wp + 1] > best) { best = b0[2 * wp + 1]; arg = 5; }
+                    if (b1[2 * wp] > best) { best = b1[2 * wp]; arg = 6; }
+                    if (b1[2 * wp + 1] > best) { best = b1[2 * wp + 1]; arg = 7; }
+                    best += bias;
+                    const bool act = best > 0.f;
+                    st[(hp * g.H2 + wp) * kStashPitch + m] = f2bf(act ? best : 0.f);
+                    if (cbase) cbase[hp * g.H2 + wp] = (uint8_t)(arg | (act ? 8 : 0));
+                }
             }
         }
     }
@@ -355,24 +361,29 @@ __device__ __forceinline__ void epi_l1_drain(const WsParams& p, int tile, uint32
 
 __device__ __forceinline__ void epi_l1_store(const WsParams& p, int tile, int q, int lane, const uint16_t* stash) {
     const Geo& g = p.epi.g;
-    const int item = tile / p.tiles_per_item, tp = tile % p.tiles_per_item;
+    const int item = tile / p.tiles_per_item, tq = tile % p.tiles_per_item;
+    const int npair = p.n_acc >> 1;
     const int half = q >> 1;
-    uint8_t* vbase = p.epi.out + (int64_t)item * g.video2 + (int64_t)half * g.group2 + (int64_t)(tp + 1) * g.HW2 * 16;
     const int npos = g.H2 * g.H2;
-    for (int i = lane; i < 4 * npos; i += 32) {
-        const int kk = i / npos, pos = i - kk * npos;
-        const int hp = pos / g.H2, wp = pos - hp * g.H2;
-        const uint4 v = *reinterpret_cast<const uint4*>(stash + pos * kStashPitch + q * 32 + kk * 8);
-        uint8_t* cb = vbase + (int64_t)((q & 1) * 4 + kk) * g.chunk2;
-        // input pixel (t=tp, h=hp, w=wp) of conv 2 feeds output (ho,wo) through tap (kh,kw) iff
-        // hp = 2ho+kh-3, wp = 2wo+kw-3
-        for (int kh = (hp + 1) & 1; kh < 7; kh += 2) {
-            const int ho = (hp + 3 - kh) / 2;
-            if (hp + 3 - kh < 0 || ho >= g.Ho2) continue;
-            for (int kw = (wp + 1) & 1; kw < 7; kw += 2) {
-                const int wo = (wp + 3 - kw) / 2;
-                if (wp + 3 - kw < 0 || wo >= g.Wo2) continue;
-                *reinterpret_cast<uint4*>(cb + (int64_t)((kh * 7 + kw) * 2) * g.group2 + (ho * g.Wo2 + wo) * 16) = v;
+    for (int pp = 0; pp < npair; ++pp) {
+        const int tp = tq * npair + pp;
+        const uint16_t* st = stash + pp * npos * kStashPitch;
+        uint8_t* vbase = p.epi.out + (int64_t)item * g.video2 + (int64_t)half * g.group2 + (int64_t)(tp + 1) * g.HW2 * 16;
+        for (int i = lane; i < 4 * npos; i += 32) {
+            const int kk = i / npos, pos = i - kk * npos;
+            const int hp = pos / g.H2, wp = pos - hp * g.H2;
+            const uint4 v = *reinterpret_cast<const uint4*>(st + pos * kStashPitch + q * 32 + kk * 8);
+            uint8_t* cb = vbase + (int64_t)((q & 1) * 4 + kk) * g.chunk2;
+            // input pixel (t=tp, h=hp, w=wp) of conv 2 feeds output (ho,wo) through tap (kh,kw) iff
+            // hp = 2ho+kh-3, wp = 2wo+kw-3
+            for (int kh = (hp + 1) & 1; kh < 7; kh += 2) {
+                const int ho = (hp + 3 - kh) / 2;
+                if (hp + 3 - kh < 0 || ho >= g.Ho2) continue;
+                for (int kw = (wp + 1) & 1; kw < 7; kw += 2) {
+                    const int wo = (wp + 3 - kw) / 2;
+                    if (wp + 3 - kw < 0 || wo >= g.Wo2) continue;
+                    *reinterpret_cast<uint4*>(cb + (int64_t)((kh * 7 + kw) * 2) * g.group2 + (ho * g.Wo2 + wo) * 16) = v;
+                }
             }
         }
     }
@@ -1082,6 +1093,8 @@ static int launch(const WsParams& p, uint32_t smem, cudaStream_t stream) {
         return launch_n<EPI_L0, 1>(p, smem, stream);
     } else if (EPI == EPI_L1 && p.n_acc == 2) {
         return launch_n<EPI_L1, 2>(p, smem, stream);
+    } else if (EPI == EPI_L1 && p.n_acc == 4) {
+        return launch_n<EPI_L1, 4>(p, smem, stream);
     } else if (EPI == EPI_L2 && p.n_acc == 4) {
         return launch_n<EPI_L2, 4>(p, smem, stream);
     } else if (EPI == EPI_DG1 && p.n_acc == 1) {
@@ -1168,7 +1181,21 @@ extern "C" int vd_tc_conv_layer(int layer, const void* in, const void* wimg, con
         }
         return launch<EPI_L0>(p, smem, s);
     }
-    if (layer == 1) return launch<EPI_L1>(p, smem, s);
+    if (layer == 1) {
+        if (g.N1 <= 128 && g.T % 4 == 0 && env_int("VD_TC_L1_NACC4", 1)) {
+            // small frames (64x64: N1 = 80 columns): four consecutive output frames per tile.  With two, a 4 KB weight tile
+            // feeds only 2 x 40 MMA cycles and the weight stream (51 B/clk per SM) exceeds what L2 can deliver to 148 SMs.
+            p.n_acc = 4; p.acc_cols = 128;
+            p.n_tiles = B * (g.T / 4);
+            p.tiles_per_item = g.T / 4;
+            p.u_stride = 4 * g.frame1;
+            p.copy_bytes[0] = (uint32_t)(4 * g.frame1);
+            p.stage_bytes = (uint32_t)(4 * g.frame1);
+            if (int rc2 = finalize_smem(p, (uint32_t)p.G * p.RW * kWeightTileBytes, &smem, false, (uint32_t)(2 * g.H2 * g.H2) * kStashPitch * 2))
+                return rc2;
+        }
+        return launch<EPI_L1>(p, smem, s);
+    }
     return launch<EPI_L2>(p, smem, s);
 }
 
