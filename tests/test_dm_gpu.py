@@ -318,3 +318,42 @@ def test_mtt_s2d_golden(precision):
         assert errs['grand'] < 1e-5, errs
         assert errs['hal_w'] < 1e-2 and errs['hal_b'] < 1e-2 and errs['lr'] < 1e-2, errs
         check_summary(tr.dynamic_syn.grad, gold['grad_dynamic_sums'], gold['grad_dynamic_sample'], tol=2e-2)   # observed 1.2e-2
+
+
+def test_streamed_real_batch_in_any_row_order():
+    """step(real_batch=..., real_batch_index=perm): the uploaded rows may come in another order (merged host ranges, uint8
+    frames) — loss, class means and gradients are bit-identical to the resident-dataset step."""
+    from oracle import synth
+    from video_distillation_b200.distill import DeviceDataset, DMS2DTrainer
+    from video_distillation_b200.utils import Conv3DNet
+    C, per, T, H, batch_real = 3, 5, 8, 64, 4
+    mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+    frames = torch.randint(0, 256, (C * per, T, 3, H, H), dtype=torch.uint8, generator=torch.Generator().manual_seed(4))
+    videos = ((frames.float() / 255.0) - torch.tensor(mean).view(1, 1, 3, 1, 1)) / torch.tensor(std).view(1, 1, 3, 1, 1)
+    labels = [c for c in range(C) for _ in range(per)]
+    ds = DeviceDataset(videos, labels, C, 'cuda')
+    outs = []
+    for mode in ('resident', 'streamed'):
+        hal = Conv3DNet()
+        hal.load_state_dict(synth.synth_hallucinator(5))
+        tr = DMS2DTrainer(ds, num_classes=C, im_size=(H, H), frames=T, vpc=1, spc=2, dpc=2, batch_real=batch_real, lr_dynamic=10.0,
+                          lr_hal=0.01, precision='bf16', hal=hal, static_syn=synth.hash_uniform((C * 2, 3, H, H), 52),
+                          dynamic_syn=synth.hash_uniform((C, 2, T, 1, H, H), 53))
+        net = net_from(synth.synth_convnet3d_params(60, num_classes=C), C, T, H)
+        np.random.seed(9)
+        torch.manual_seed(3)
+        idx = tr.sample_syn_indices()
+        if mode == 'resident':
+            loss = tr.step(net=net, indices=idx)
+        else:
+            real_idx = ds.sample_all_classes(batch_real)
+            loc = real_idx.reshape(-1)
+            order = np.argsort(loc, kind='stable')
+            perm = np.empty_like(order)
+            perm[order] = np.arange(order.size)
+            tr.embedder.tc.set_normalization(mean, std)
+            stage = frames[torch.from_numpy(loc[order])].cuda()              # uint8 rows in ascending host order
+            loss = tr.step(net=net, indices=idx, real_idx=real_idx, real_batch=stage, real_batch_index=torch.from_numpy(perm).cuda())
+        outs.append((loss.clone(), tr.last['mean_real'].clone(), tr.dynamic_syn.grad.clone()))
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)

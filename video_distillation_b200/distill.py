@@ -359,19 +359,20 @@ class DMS2DTrainer:
         ops.sgd_momentum_(p.data, grad.contiguous(), self._bufs[name], lr, momentum, first)
 
     # ------------------------------------------------------------------ one iteration
-    def step(self, net=None, net_seed=None, indices=None, real_idx=None, real_batch=None):
+    def step(self, net=None, net_seed=None, indices=None, real_idx=None, real_batch=None, real_batch_index=None):
         """One DM iteration; returns the loss (0-dim device tensor, summed over ALL classes).
         ``real_batch``: optional device tensor holding this rank's sampled real videos already gathered
-        (class-major, batch_real per owned class) — the host-streaming mode of bench.py."""
+        (class-major, batch_real per owned class) — the host-streaming mode of bench.py; ``real_batch_index`` (device int64)
+        maps sample j to its row of ``real_batch`` when the rows were uploaded in another order (merged host ranges)."""
         if (self.embedder.tc is not None and self.syn_on_tensor_cores == 'split') or self.embedder.precision == 'bf16x3':
             prev = ops.set_conv_backend('tc')             # forward AND backward of net.embed(...) below
             try:
-                return self._step(net, net_seed, indices, real_idx, real_batch)
+                return self._step(net, net_seed, indices, real_idx, real_batch, real_batch_index)
             finally:
                 ops.set_conv_backend(prev)
-        return self._step(net, net_seed, indices, real_idx, real_batch)
+        return self._step(net, net_seed, indices, real_idx, real_batch, real_batch_index)
 
-    def _step(self, net=None, net_seed=None, indices=None, real_idx=None, real_batch=None):
+    def _step(self, net=None, net_seed=None, indices=None, real_idx=None, real_batch=None, real_batch_index=None):
         C, vpc = self.C, self.vpc
         if net is None:
             if self.init_on_device:
@@ -401,7 +402,7 @@ class DMS2DTrainer:
             ridx = self.ds.local_index(real_idx[own])                       # (n_own*batch_real,)
             emb_real = self.embedder(self.ds.videos, ridx, x0=self.ds.x0)   # (n_own*batch_real, D)
         else:
-            ridx = torch.arange(real_batch.shape[0], device=self.device)
+            ridx = real_batch_index if real_batch_index is not None else torch.arange(real_batch.shape[0], device=self.device)
             emb_real = self.embedder(real_batch, ridx)
         D = emb_real.shape[1]
         mean_real = ops.class_mean(emb_real.view(n_own, self.batch_real, D))
