@@ -219,8 +219,9 @@ def run_ours(args):
     dev = torch.device('cuda', local)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        # NCCL_DEBUG=VERSION/INFO prints to stdout, where rank 0 must print exactly one JSON line
-        os.environ['NCCL_DEBUG'] = os.environ.get('VD_NCCL_DEBUG', 'WARN')
+        # NCCL's debug output (the version banner at NCCL_DEBUG=VERSION/WARN/INFO) goes to stdout by default, where rank 0 must
+        # print exactly one JSON line: send it to stderr instead
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=dev)
     import __graft_entry__ as ge
     if rank == 0:
