@@ -273,3 +273,47 @@ def emulate_layer(layer, pix_u16, wimg_u16, T, HW, B, tiles=None):
                 st += 1
         out.append(D)
     return np.stack(out).astype(np.float32), p
+
+
+def emulate_layer0_streaming(pix_u16, wimg_u16, T, HW, B, columns=None):
+    """conv 0 in the kernel's input-frame streaming order (WsParams::stream_pairs, tc_conv.cu: next_stream): a tile is a
+    column (video, row band); frame i is staged once and feeds pair i//2 - 1 / i//2 (even i: windows 3 and 1) or pair
+    (i-1)//2 / (i+1)//2 (odd i: windows 2 and 0) of the resident Toeplitz weight image.  Uses the REAL layer-0 tables.
+    Returns {(item, rb): D of shape (T/2, 128, ncols)}."""
+    p = Params(0, T, HW, B)
+    pix = pix_u16.reshape(-1)
+    wimg = wimg_u16.reshape(-1)
+    g = Geo(T, HW)
+    pairs = T // 2
+    n_cols = B * p.v_count
+    columns = range(n_cols) if columns is None else columns
+
+    def f32(u16):
+        return (u16.astype(np.uint32) << 16).view(np.float32).astype(np.float64)
+    out = {}
+    for col in columns:
+        item, rb = divmod(col, p.v_count)
+        gbase = item * p.item_stride + rb * p.v_stride
+        D = np.zeros((pairs, 128, p.ncols))
+        written = [False] * pairs
+        for i in range(T):
+            smem = np.zeros(p.stage_pitch // 2, np.uint16)
+            src = gbase + (i + 1) * g.frame0                           # frame i of the video is t_pad = i + 1
+            for c in range(p.n_copies):
+                n = p.copy_bytes[c] // 2
+                s0 = (src + p.copy_gofs[c]) // 2
+                smem[p.copy_sofs[c] // 2: p.copy_sofs[c] // 2 + n] = pix[s0:s0 + n]
+            pp, odd = divmod(i, 2)
+            groups = ([(pp - 1, 3)] if pp > 0 else []) + [(pp, 1)] if not odd else [(pp, 2)] + ([(pp + 1, 0)] if pp + 1 < pairs else [])
+            for pair, window in groups:
+                first = not written[pair]
+                acc = np.zeros((128, p.ncols))
+                for j in range(p.n_steps):
+                    a_start = (p.a_off16[j] + window * p.a_sa_stride16) * 16
+                    A = f32(_desc_gather(wimg, a_start, p.a_lbo16 * 16, p.a_sbo16 * 16, 128))
+                    Bm = f32(_desc_gather(smem, p.b_off16[j] * 16, p.b_lbo16[j] * 16, 128, p.ncols))
+                    acc += A @ Bm.T
+                D[pair] = acc if first else D[pair] + acc
+                written[pair] = True
+        out[(item, rb)] = D.astype(np.float32)
+    return out, p

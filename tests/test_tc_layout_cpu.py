@@ -98,3 +98,20 @@ def test_python_and_library_agree_on_supported_geometries():
             plan = _lib.TcPlan()
             ok = _lib.lib().vd_tc_plan_make(ctypes.byref(plan), T, HW, HW) == 0
             assert ok == tc_supported(T, HW, HW), (T, HW, ok)
+
+
+@pytest.mark.parametrize('T,HW,cols', [(8, 64, [0, 3, 5]), (4, 112, [0, 13, 14])])
+def test_layer0_streaming_schedule(T, HW, cols):
+    """The input-frame streaming order of conv 0 (one staged frame -> two frame-pair accumulators through the four
+    Toeplitz windows) reproduces the convolution with the real launch tables."""
+    g = em.Geo(T, HW)
+    B = 2
+    video = em.bf16_round(torch.randn(B, T, 3, HW, HW, generator=torch.Generator().manual_seed(T)))
+    w = em.bf16_round(torch.randn(64, 3, 3, 7, 7, generator=torch.Generator().manual_seed(1)) * 0.1)
+    y = conv_ref(video.permute(0, 2, 1, 3, 4), w)                      # (B,64,T,Ho0,Wo0)
+    out, p = em.emulate_layer0_streaming(em.pack_x0(video, g), em.pack_w0(w), T, HW, B, cols)
+    for (item, rb), D in out.items():
+        for tp in range(T // 2):
+            d = torch.from_numpy(D[tp]).reshape(2, 64, g.R0, g.Wo0)
+            ref = y[item, :, 2 * tp:2 * tp + 2, rb * g.R0:(rb + 1) * g.R0, :].permute(1, 0, 2, 3)
+            assert rel(d, ref) < 1e-5, (item, rb, tp, rel(d, ref))
