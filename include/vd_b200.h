@@ -117,6 +117,10 @@ int vd_compose_bwd_f32(const float* gout, const float* static_syn, const float* 
 int vd_class_mean_f32(const float* emb, float* mean, int C, int n, int D, void* stream);
 int vd_dm_loss_f32(const float* mean_real, const float* emb_syn, float* loss, float* grad_syn,
                    int C, int ns, int D, float loss_scale, void* stream);
+/* Same result with a caller-provided scratch of C floats: one block per class writes class_loss[c] (the per-class terms of
+ * distill_s2d_ms.py:414-422, also an output), a second launch adds them in class order into *loss.  Bitwise reproducible. */
+int vd_dm_loss_ex_f32(const float* mean_real, const float* emb_syn, float* loss, float* grad_syn, float* class_loss,
+                      int C, int ns, int D, float loss_scale, void* stream);
 
 /* ------------------------------------------------- optimiser / flat-parameter kernels
  * sgd_momentum: torch.optim.SGD(momentum=m) dense step (distill_baseline.py:107,355;

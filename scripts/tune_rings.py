@@ -9,7 +9,7 @@ import sys, torch
 sys.path.insert(0, %r)
 from video_distillation_b200.networks import ConvNet3D
 from video_distillation_b200.tc import TcConvNet3D
-B, T, HW = 640, 16, 112
+B, T, HW = 592, 16, 112
 torch.manual_seed(0)
 net = ConvNet3D(3, 50, 128, 3, 'relu', 'none', 'maxpooling', T, (HW, HW)).cuda()
 tc = TcConvNet3D(T, HW, HW, 'cuda', max_batch=B)
@@ -30,10 +30,8 @@ for layer, b, a, e in tc.timing:
 F = {0: 2.832e9, 1: 7.553e9, 2: 0.617e9}
 print(' '.join('conv%%d %%6.2f ms %%6.0f TF/s' %% (k, ms[k], F[k] * B / ms[k] / 1e9) for k in ms))
 ''' % ROOT
-configs = [dict(), dict(VD_TC_L1_G='4', VD_TC_L1_RW='4'), dict(VD_TC_L1_G='2', VD_TC_L1_RW='8'), dict(VD_TC_L1_G='3', VD_TC_L1_RW='5'),
-           dict(VD_TC_L1_G='5', VD_TC_L1_RW='3'), dict(VD_TC_L1_G='8', VD_TC_L1_RW='2'),
-           dict(VD_TC_L2_G='3', VD_TC_L2_RW='4'), dict(VD_TC_L2_G='2', VD_TC_L2_RW='8'), dict(VD_TC_L2_G='4', VD_TC_L2_RW='4'),
-           dict(VD_TC_L2_G='12', VD_TC_L2_RW='2'), dict(VD_TC_L0_RP='2')]
+configs = [dict(), dict(VD_TC_L1_G='5', VD_TC_L1_RW='3'), dict(VD_TC_L1_G='4', VD_TC_L1_RW='4'), dict(VD_TC_L1_G='4', VD_TC_L1_RW='3'),
+           dict(VD_TC_L1_G='3', VD_TC_L1_RW='5'), dict(VD_TC_L2_G='3', VD_TC_L2_RW='4'), dict(VD_TC_L2_G='4', VD_TC_L2_RW='3'), dict()]
 for cfg in configs:
     env = dict(os.environ, **cfg)
     r = subprocess.run([sys.executable, '-c', CODE], env=env, capture_output=True, text=True)

@@ -245,3 +245,24 @@ def test_sqdist():
     g = torch.Generator().manual_seed(7)
     a, b = torch.randn(100003, generator=g), torch.randn(100003, generator=g)
     assert rel(ops.sqdist(a.cuda(), b.cuda()), ((a.double() - b.double()) ** 2).sum()) < 1e-5
+
+
+def test_dm_loss_variants_are_bitwise_identical_and_ordered():
+    """vd_dm_loss_f32 (one block, scratch-free) and vd_dm_loss_ex_f32 (one block per class + ordered finish) give the same
+    bits: every class sum is the same tree and the class sums are added in class order (distill_s2d_ms.py:414-422)."""
+    from video_distillation_b200._lib import check, lib, ptr, stream
+    C, ns, D = 37, 3, 2048
+    g = torch.Generator(device='cuda').manual_seed(5)
+    mean_real = torch.randn(C, D, device='cuda', generator=g)
+    emb_syn = torch.randn(C, ns, D, device='cuda', generator=g)
+    la, lb = torch.zeros((), device='cuda'), torch.zeros((), device='cuda')
+    ga, gb, cl = torch.empty_like(emb_syn), torch.empty_like(emb_syn), torch.empty(C, device='cuda')
+    check(lib().vd_dm_loss_f32(ptr(mean_real), ptr(emb_syn), ptr(la), ptr(ga), C, ns, D, 1.0, stream()), 'a')
+    check(lib().vd_dm_loss_ex_f32(ptr(mean_real), ptr(emb_syn), ptr(lb), ptr(gb), ptr(cl), C, ns, D, 1.0, stream()), 'b')
+    assert torch.equal(la, lb) and torch.equal(ga, gb)
+    per_class = ((mean_real - emb_syn.mean(1)) ** 2).sum(1)
+    assert torch.allclose(cl, per_class, rtol=1e-5)
+    seq = torch.zeros((), device='cuda')
+    for c in range(C):
+        seq = seq + cl[c]
+    assert torch.equal(seq, lb)

@@ -339,3 +339,17 @@ def test_embed_geometry_sweep_against_the_fp32_oracle(T, HW, B):
     vc = video.clone().requires_grad_(True)
     convnet3d_embed(params, vc).square().sum().backward()
     assert rel(v.grad, vc.grad) < 0.4, rel(v.grad, vc.grad)
+
+
+@pytest.mark.parametrize('T,HW', [(8, 64), (16, 112)])
+def test_batch_size_sweep_is_bitwise_consistent(T, HW):
+    """Tile counts below, at and above the grid size (148 persistent CTAs), odd batch sizes, partially filled conv-2 tiles:
+    the embedding of a video is bitwise independent of the batch it is embedded with."""
+    net, _ = make_net(T, HW)
+    nmax = 301 if HW == 64 else 75
+    video = torch.randn(nmax, T, 3, HW, HW, device='cuda', generator=torch.Generator(device='cuda').manual_seed(T))
+    ref_first = net.embed(video[:1]).clone()
+    for B in ([1, 2, 7, 37, 149, 300, 301] if HW == 64 else [1, 3, 10, 19, 75]):
+        e = net.embed(video[:B]).clone()
+        assert torch.equal(e[:1], ref_first), B
+        assert torch.equal(e[B - 1:B], net.embed(video[B - 1:B])), B

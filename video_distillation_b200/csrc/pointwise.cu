@@ -433,6 +433,37 @@ __global__ void __launch_bounds__(1024) dm_loss_kernel(const float* __restrict__
     if (threadIdx.x == 0) *loss += total;
 }
 
+// Parallel variant with caller-provided scratch: one block per class writes its sum to class_loss[c] (and the gradient); a second
+// one-block launch adds the C class sums in class order — the same fixed summation order as dm_loss_kernel, C-way parallel.
+__global__ void __launch_bounds__(256) dm_loss_class_kernel(const float* __restrict__ mean_real, const float* __restrict__ emb_syn,
+                                                            float* __restrict__ class_loss, float* __restrict__ grad_syn, int ns, int D,
+                                                            float scale) {
+    __shared__ float red[32];
+    const int c = blockIdx.x;
+    float part = 0.f;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        float ms = 0.f;
+        for (int j = 0; j < ns; ++j) ms += emb_syn[((int64_t)c * ns + j) * D + d];
+        ms /= (float)ns;
+        const float diff = mean_real[(int64_t)c * D + d] - ms;
+        part += diff * diff;
+        if (grad_syn) {
+            const float g = -(2.0f / (float)ns) * diff * scale;
+            for (int j = 0; j < ns; ++j) grad_syn[((int64_t)c * ns + j) * D + d] = g;
+        }
+    }
+    part = block_sum(part, red);
+    if (threadIdx.x == 0) class_loss[c] = part;
+}
+
+__global__ void dm_loss_finish_kernel(const float* __restrict__ class_loss, float* __restrict__ loss, int C) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        float total = 0.f;
+        for (int c = 0; c < C; ++c) total += class_loss[c];
+        *loss += total;
+    }
+}
+
 // =============================================================== optimiser / flat-parameter kernels
 __global__ void sgd_momentum_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf,
                                     int64_t n, float lr, float momentum, int first) {
@@ -640,6 +671,16 @@ extern "C" int vd_dm_loss_f32(const float* mean_real, const float* emb_syn, floa
     if (C == 0) return 0;
     dm_loss_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(mean_real, emb_syn, loss, grad_syn, C, ns, D, loss_scale);
     return check_launch("dm_loss_f32");
+}
+
+extern "C" int vd_dm_loss_ex_f32(const float* mean_real, const float* emb_syn, float* loss, float* grad_syn, float* class_loss,
+                                 int C, int ns, int D, float loss_scale, void* stream) {
+    VD_REQUIRE(mean_real && emb_syn && loss && class_loss && C >= 0 && ns > 0 && D > 0, "dm_loss_ex: bad argument");
+    if (C == 0) return 0;
+    dm_loss_class_kernel<<<C, 256, 0, (cudaStream_t)stream>>>(mean_real, emb_syn, class_loss, grad_syn, ns, D, loss_scale);
+    if (int e = check_launch("dm_loss_class_f32")) return e;
+    dm_loss_finish_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(class_loss, loss, C);
+    return check_launch("dm_loss_finish_f32");
 }
 
 extern "C" int vd_sgd_momentum_f32(float* p, const float* g, float* buf, int64_t n, float lr, float momentum,

@@ -1005,7 +1005,9 @@ static int setup_l1(WsParams& p, const Geo& g, int B, uint32_t* smem) {
         }
     p.a_lbo16 = 2048 >> 4; p.a_sbo16 = 8;
     p.w_resident = 0; p.w_bytes = 0;
-    p.G = env_int("VD_TC_L1_G", 7); p.RW = env_int("VD_TC_L1_RW", 2); p.RP = 2;
+    // weight ring: 3 slots of 5 K-steps (20 KB each).  With the dual-issuer pipe a slot must be refilled within the time the other
+    // slots last; 2 x 7 steps left the MMA threads waiting 28 % of the time, 3 x 5 measures 5.5 % faster (scripts/tune_rings.py)
+    p.G = env_int("VD_TC_L1_G", 5); p.RW = env_int("VD_TC_L1_RW", 3); p.RP = 2;
     p.n_acc = 2; p.acc_delta16 = (uint32_t)g.frame1 >> 4;
     p.ncols = g.N1; p.acc_cols = 256; p.acc_stages = 1;
     p.idesc = umma_idesc_bf16(128, g.N1);

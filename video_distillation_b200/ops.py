@@ -374,7 +374,9 @@ class _DMLoss(torch.autograd.Function):
         C, ns, D = emb_syn.shape
         loss = torch.zeros((), dtype=torch.float32, device=emb_syn.device)
         grad = torch.empty_like(emb_syn)
-        check(lib().vd_dm_loss_f32(ptr(mean_real), ptr(emb_syn), ptr(loss), ptr(grad), C, ns, D, 1.0, stream()), 'dm_loss')
+        class_loss = torch.empty(C, dtype=torch.float32, device=emb_syn.device)       # per-class terms, summed in class order
+        check(lib().vd_dm_loss_ex_f32(ptr(mean_real), ptr(emb_syn), ptr(loss), ptr(grad), ptr(class_loss), C, ns, D, 1.0, stream()),
+              'dm_loss')
         ctx.save_for_backward(grad)
         return loss
 
