@@ -221,6 +221,9 @@ def run_ours(args):
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         # NCCL's debug output (the version banner at NCCL_DEBUG=VERSION/WARN/INFO) goes to stdout by default, where rank 0 must
         # print exactly one JSON line: send it to stderr instead
+        # (NCCL only honours NCCL_DEBUG_FILE above the VERSION level, so a preset NCCL_DEBUG=VERSION is raised to WARN)
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', ''):
+            os.environ['NCCL_DEBUG'] = 'WARN'
         os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=dev)
     import __graft_entry__ as ge
