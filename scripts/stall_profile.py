@@ -1,4 +1,4 @@
-"""Where does the MMA warp's time go?  Per-layer cycle counters (vd_tc_set_profile_buffer)."""
+"""Where does an MMA issuer thread's time go?  Per-layer cycle counters (vd_tc_set_profile_buffer)."""
 import os
 import sys
 
@@ -30,6 +30,9 @@ for layer, (src, w, b, dst, ii) in enumerate([(x0, tc.w0, tc.b0, a1, idx), (a1, 
     torch.cuda.synchronize()
     v = buf.cpu().view(148, 8).double().mean(0)
     tot = v[0].item()
+    # counters of MMA issuer 0 (issuer 1 mirrors it): o[1..3] = time blocked on acc_empty / pix_full / w_full for ITS groups,
+    # o[4] = fence + MMA issue + baton arrive + weight-slot commit, o[5] = time waiting for the baton of the other issuer
     print(f'conv{layer}: total {tot:10.0f} cyc | wait acc_empty {100 * v[1] / tot:5.1f}% | wait pix_full {100 * v[2] / tot:5.1f}% | '
-          f'wait w_full {100 * v[3] / tot:5.1f}% | issue {100 * v[4] / tot:5.1f}% | fences {100 * v[5] / tot:5.1f}% | tile tail {100 * v[6] / tot:5.1f}%')
+          f'wait w_full {100 * v[3] / tot:5.1f}% | issue {100 * v[4] / tot:5.1f}% | wait baton {100 * v[5] / tot:5.1f}% | '
+          f'other (generator, commits of the peer\'s groups) {100 * (tot - v[1:6].sum().item()) / tot:5.1f}%')
 lib.vd_tc_set_profile_buffer(None)

@@ -91,7 +91,7 @@ struct WsParams {
     int32_t dbg;                        // tuning experiments (VD_TC_DBG bitmask; results are garbage when set):
                                         //   1 no pixel copies, 2 no weight copies, 4 epilogue does no work,
                                         //   16 loaders back off with nanosleep (old behaviour), 32 epilogue spins without nanosleep
-    long long* prof;                    // optional [grid][8] cycle counters of the MMA warp (tuning only)
+    long long* prof;                    // optional [grid][8] cycle counters of MMA issuer 0 (tuning only)
     EpiParams epi;
 };
 
@@ -1438,6 +1438,6 @@ extern "C" int vd_tc_probe(const void* pix, const void* wimg, float* raw, int nc
     return launch<EPI_RAW>(p, smem, (cudaStream_t)stream);
 }
 
-// Tuning aid: when set (device buffer of grid*8 int64, may be NULL to disable), the MMA warp of every
-// forward conv launch records [total, wait acc_empty, wait pix_full, wait w_full, issue] cycles per CTA.
+// Tuning aid: when set (device buffer of grid*8 int64, may be NULL to disable), MMA issuer 0 of every forward conv
+// launch records [total, wait acc_empty, wait pix_full, wait w_full, issue, wait baton] cycles per CTA.
 extern "C" int vd_tc_set_profile_buffer(long long* buf) { g_prof = buf; return 0; }
