@@ -125,42 +125,65 @@ class MultiStaticSharedDataset(Dataset):
         raise ValueError('MultiStaticSharedDataset: spc must be 2 (vpc=1) or 10 (vpc=5)')
 
 
+class EpochStats:
+    """Running statistics of ``epoch`` kept ON THE DEVICE: the reference converts logits and labels to numpy after every
+    batch (utils.py:775-781, 804-816), i.e. one host synchronisation per batch; here the counts accumulate in a few small
+    tensors and are read back once per epoch.  Same definitions: accuracy = first-argmax match, top-k = label among the k
+    largest logits (all classes when there are fewer than k), per-class accuracy over the samples seen."""
+
+    def __init__(self, num_classes, device):
+        self.C = num_classes
+        self.sums = torch.zeros(6, dtype=torch.float64, device=device)           # loss*n, matched, top1, top3, top5, n
+        self.cls = torch.zeros(2, num_classes, dtype=torch.float64, device=device)   # per class: correct, seen
+
+    @torch.no_grad()
+    def add(self, output, lab, loss, train):
+        n_b = lab.shape[0]
+        matched = output.argmax(dim=-1).eq(lab)
+        k5 = min(5, output.shape[1])
+        top = output.topk(k5, dim=-1).indices.eq(lab[:, None])
+        zero = torch.zeros((), dtype=torch.float64, device=output.device)
+        vals = [loss.detach().double() * n_b, matched.sum().double(),
+                zero if train else top[:, :1].any(1).sum().double(),              # the train branch of the reference only counts top-5
+                zero if train else top[:, :min(3, k5)].any(1).sum().double(),
+                top.any(1).sum().double(), zero + n_b]
+        self.sums += torch.stack(vals)
+        self.cls[0] += torch.bincount(lab, weights=matched.double(), minlength=self.C)[:self.C]
+        self.cls[1] += torch.bincount(lab, minlength=self.C)[:self.C].double()
+
+    def result(self, top5_mode):
+        sums = self.sums.tolist()                                                  # the one device -> host read of the epoch
+        correct, seen = self.cls.tolist()
+        n = sums[5]
+        loss_avg, acc_avg = sums[0] / n, sums[1] / n
+        present = [i for i in range(self.C) if seen[i] > 0]
+        # the reference builds a dict over the classes seen and lists range(len(dict)) of it (utils.py:834-839)
+        per_class = [correct[i] / seen[i] if seen[i] > 0 else None for i in range(len(present))]
+        if top5_mode:
+            return loss_avg, [acc_avg, sums[2] / n, sums[3] / n, sums[4] / n], per_class
+        return loss_avg, acc_avg, per_class
+
+
 def epoch(mode, dataloader, net, optimizer, criterion, args):
     """utils.py:752-845: one training epoch, or three test passes; returns (loss, acc, acc_per_class)."""
-    loss_avg, acc_avg, num_exp = 0, 0, 0
-    top = {1: 0.0, 3: 0.0, 5: 0.0}
     net = net.to(args.device)
     net.train() if mode == 'train' else net.eval()
-    correct_per_class = defaultdict(list)
+    stats = None
     for _ in range(1 if mode == 'train' else 3):
         for datum in dataloader:
             img = datum[0].float().to(args.device)
             img = (img - img.mean()) / img.std()
             lab = datum[1].long().to(args.device)
-            n_b = lab.shape[0]
             output = net(img)
             loss = criterion(output, lab)
-            out_np, lab_np = output.detach().cpu().numpy(), lab.cpu().numpy()
-            matched = np.equal(np.argmax(out_np, axis=-1), lab_np)
-            order = np.argsort(out_np, axis=-1)
-            for k in top:
-                top[k] += float(np.sum([lab_np[i] in order[i, -k:] for i in range(n_b)]))
-            for y, c in zip(lab_np.tolist(), matched.tolist()):
-                correct_per_class[y].append(c)
-            loss_avg += loss.item() * n_b
-            acc_avg += float(np.sum(matched))
-            num_exp += n_b
+            if stats is None:
+                stats = EpochStats(output.shape[1], output.device)
+            stats.add(output, lab, loss, mode == 'train')
             if mode == 'train':
                 optimizer.zero_grad()
                 loss.backward()
                 optimizer.step()
-    loss_avg /= num_exp
-    acc_avg /= num_exp
-    correct = dict(correct_per_class)
-    correct = [np.mean(correct[i]) if i in correct else None for i in range(len(correct))]
-    if getattr(args, 'eval_mode', None) == 'top5':
-        return loss_avg, [acc_avg, top[1] / num_exp, top[3] / num_exp, top[5] / num_exp], correct
-    return loss_avg, acc_avg, correct
+    return stats.result(getattr(args, 'eval_mode', None) == 'top5')
 
 
 def evaluate_synset(it_eval, net, images_train, labels_train, testloader, args, mode='hallucinator',
