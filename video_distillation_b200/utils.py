@@ -6,9 +6,7 @@ arguments and return values; tensor work goes through libvd_b200.
 """
 import random
 import time
-from collections import defaultdict
 
-import numpy as np
 import torch
 import torch.nn as nn
 from torch.utils.data import Dataset
