@@ -1,4 +1,5 @@
-"""Gradient / loss error of every precision mode of DMS2DTrainer against the exact fp32 path (same draws)."""
+"""Test tool (imports the CPU oracle, so it lives under tests/): gradient / loss error of every precision mode of DMS2DTrainer
+against the exact fp32 path (same draws).  python tests/parity_modes.py on a GPU box -> profiles/r01_parity_modes.log."""
 import os
 import sys
 
