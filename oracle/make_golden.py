@@ -413,8 +413,70 @@ def case_mtt_s2d():
     print('mtt_s2d ok: grand_loss', float(grand_loss))
 
 
+def case_mtt_baseline():
+    """distill_baseline.py:196-272 transcribed: MTT on leaf synthetic videos, ReparamModule student, 2 inner steps, train mode,
+    ipc = 2 with batch_syn = 4 < C * ipc, so that the split / pop() order of the index chunks (:233-237) is exercised."""
+    C, T, H, ipc, syn_steps, batch_syn = 3, 8, 64, 2, 2, 4
+    image_syn = synth.hash_uniform((C * ipc, T, 3, H, H), 91).requires_grad_(True)
+    label_syn = torch.tensor(np.stack([np.ones(ipc) * i for i in range(0, C)]), dtype=torch.long).view(-1)
+    syn_lr = torch.tensor(0.01).requires_grad_(True)
+    start = synth.synth_convnet3d_params(81, num_classes=C)
+    target = {k: v + synth.hash_uniform(tuple(v.shape), 950 + i, 2.0 ** -10) for i, (k, v) in enumerate(start.items())}
+    net = ref_networks.ConvNet3D(3, C, 128, 3, 'relu', 'none', 'maxpooling', frames=T, im_size=(H, H))
+    student_net = ref_reparam.ReparamModule(net)
+    student_net.train()
+    num_params = sum([np.prod(p.size()) for p in (student_net.parameters())])
+    target_params = torch.cat([p.data.reshape(-1) for p in target.values()], 0)
+    student_params = [torch.cat([p.data.reshape(-1) for p in start.values()], 0).requires_grad_(True)]
+    starting_params = torch.cat([p.data.reshape(-1) for p in start.values()], 0)
+    criterion = torch.nn.CrossEntropyLoss()
+    torch.manual_seed(98)
+    syn_images, y_hat = image_syn, label_syn
+    indices_chunks, perms, used, masks = [], [], [], []
+    for step in range(syn_steps):              # :231-252
+        if not indices_chunks:
+            indices = torch.randperm(len(syn_images))
+            perms.append(indices.clone())
+            indices_chunks = list(torch.split(indices, batch_syn))
+        these_indices = indices_chunks.pop()
+        x = syn_images[these_indices]
+        this_y = y_hat[these_indices]
+        st = torch.get_rng_state()
+        mask = (torch.nn.functional.dropout(torch.ones(these_indices.shape[0], 128, T // 8, 1, 1), 0.5, True) > 0).float()
+        torch.set_rng_state(st)
+        x = student_net(x, flat_param=student_params[-1])
+        ce_loss = criterion(x, this_y)
+        grad = torch.autograd.grad(ce_loss, student_params[-1], create_graph=True)[0]
+        student_params.append(student_params[-1] - syn_lr * grad)
+        used.append(these_indices)
+        masks.append(mask)
+    param_loss = torch.nn.functional.mse_loss(student_params[-1], target_params, reduction="sum")
+    param_dist = torch.nn.functional.mse_loss(starting_params, target_params, reduction="sum")
+    param_loss = param_loss / num_params
+    param_dist = param_dist / num_params
+    grand_loss = param_loss / param_dist
+    grand_loss.backward()
+    r = oracle.mtt_baseline_iteration(starting_params, target_params, start, image_syn.detach(), label_syn, syn_lr.detach(),
+                                      perms=used, dropout_masks=masks, im_size=(H, H))
+    assert rel(r['grand_loss'], grand_loss.detach()) < 1e-6, (r['grand_loss'], grand_loss)
+    assert rel(r['grad_image_syn'], image_syn.grad) < 1e-4, rel(r['grad_image_syn'], image_syn.grad)
+    assert rel(r['grad_syn_lr'], syn_lr.grad) < 1e-4
+    s, samp = synth.summarize(image_syn.grad)
+    np.savez_compressed(
+        os.path.join(GOLD, 'mtt_baseline.npz'), grand_loss=grand_loss.detach().numpy(), param_dist=param_dist.detach().numpy(),
+        perms=torch.stack(perms).numpy(), used_0=used[0].numpy(), used_1=used[1].numpy(),
+        dropout_mask_0=masks[0].numpy(), dropout_mask_1=masks[1].numpy(),
+        grad_image_sums=s, grad_image_sample=samp, grad_syn_lr=syn_lr.grad.numpy(),
+        rows_with_grad=(image_syn.grad.flatten(1).abs().sum(1) > 0).numpy())
+    print('mtt_baseline ok: grand_loss', float(grand_loss), 'chunks', [u.tolist() for u in used])
+
+
 if __name__ == '__main__':
     os.makedirs(GOLD, exist_ok=True)
+    if len(sys.argv) > 1:                      # regenerate selected cases only: python oracle/make_golden.py case_mtt_baseline
+        for name in sys.argv[1:]:
+            globals()[name]()
+        sys.exit(0)
     torch.set_num_threads(8)
     case_init()
     case_convnet3d()
@@ -422,4 +484,5 @@ if __name__ == '__main__':
     case_dm_baseline()
     case_dm_s2d()
     case_mtt_s2d()
+    case_mtt_baseline()
     print('golden vectors written to', GOLD)

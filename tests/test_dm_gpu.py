@@ -357,3 +357,48 @@ def test_streamed_real_batch_in_any_row_order():
         outs.append((loss.clone(), tr.last['mean_real'].clone(), tr.dynamic_syn.grad.clone()))
     for a, b in zip(outs[0], outs[1]):
         assert torch.equal(a, b)
+
+
+def test_mtt_baseline_golden():
+    """MTT on leaf synthetic videos (distill_baseline.py:196-272, MTTBaselineTrainer) against the live-reference golden:
+    ipc = 2 with batch_syn = 4, so the randperm is split and the chunks are consumed last-first like the reference's pop()."""
+    from oracle import synth
+    from video_distillation_b200.distill import MTTBaselineTrainer
+    from video_distillation_b200.networks import ConvNet3D
+    from video_distillation_b200.reparam_module import ReparamModule
+    gold = np.load(os.path.join(GOLD, 'mtt_baseline.npz'))
+    C, T, H, ipc, syn_steps, batch_syn = 3, 8, 64, 2, 2, 4
+    tr = MTTBaselineTrainer(num_classes=C, im_size=(H, H), frames=T, ipc=ipc, syn_steps=syn_steps, lr_img=1.0, lr_lr=1e-5,
+                            lr_teacher=0.01, train_lr=True, batch_syn=batch_syn, image_syn=synth.hash_uniform((C * ipc, T, 3, H, H), 91),
+                            precision='fp32')
+    start = synth.synth_convnet3d_params(81, num_classes=C)
+    target = {k: v + synth.hash_uniform(tuple(v.shape), 950 + i, 2.0 ** -10) for i, (k, v) in enumerate(start.items())}
+    student = ReparamModule(ConvNet3D(3, C, 128, 3, 'relu', 'none', 'maxpooling', T, (H, H)).cuda())
+    masks = [torch.from_numpy(gold['dropout_mask_0']).cuda(), torch.from_numpy(gold['dropout_mask_1']).cuda()]
+    state = {'perm': 0, 'mask': 0}
+    real_randperm = torch.randperm
+
+    def fake_randperm(n, **kw):
+        v = torch.from_numpy(gold['perms'][state['perm']])
+        state['perm'] += 1
+        return v
+
+    class FixedDropout(torch.nn.Module):
+        def forward(self, t):
+            m = masks[state['mask']]
+            state['mask'] += 1
+            return t * m / 0.5
+    student.module.dropout = FixedDropout()
+    torch.randperm = fake_randperm
+    try:
+        grand = tr.step(list(start.values()), list(target.values()), student_net=student)
+    finally:
+        torch.randperm = real_randperm
+    assert state['perm'] == 1                                              # one permutation feeds both steps
+    assert [d.tolist() for d in tr.last['draws']] == [gold['used_0'].tolist(), gold['used_1'].tolist()]
+    assert rel(tr.last['param_dist'], gold['param_dist']) < 1e-5
+    assert rel(grand, gold['grand_loss']) < 1e-5
+    assert rel(tr.syn_lr.grad, gold['grad_syn_lr']) < 1e-3
+    check_summary(tr.image_syn.grad, gold['grad_image_sums'], gold['grad_image_sample'])
+    rows = tr.image_syn.grad.flatten(1).abs().sum(1) > 0
+    assert rows.cpu().tolist() == gold['rows_with_grad'].tolist()
