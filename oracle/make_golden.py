@@ -471,6 +471,49 @@ def case_mtt_baseline():
     print('mtt_baseline ok: grand_loss', float(grand_loss), 'chunks', [u.tolist() for u in used])
 
 
+def epoch_case_inputs(C, sizes, seed):
+    """Hash-generated logits / labels / per-batch losses of the epoch bookkeeping case (shared with tests/test_epoch_stats_cpu.py)."""
+    batches = []
+    for i, n in enumerate(sizes):
+        logits = synth.hash_uniform((n, C), seed + 10 * i, 3.0)
+        labels = (synth.hash_uniform((n,), seed + 10 * i + 1, 0.5) + 0.5).mul(min(C, 12)).long().clamp_(0, C - 1)
+        labels[::2] = logits[::2].argmax(-1)                       # every second sample is classified correctly
+        labels[1::4] = logits[1::4].topk(min(3, C), dim=-1).indices[:, -1]      # ... and some only within the top 3
+        batches.append((logits, labels))
+    return batches
+
+
+def case_epoch():
+    """utils.epoch (:752-845) of the LIVE reference driven by a stub network that returns prescribed logits: pins the accuracy /
+    top-k / per-class bookkeeping that video_distillation_b200.utils.EpochStats reproduces on the device."""
+    out = {}
+    for tag, C, train in (('test50', 50, False), ('train50', 50, True), ('test3', 3, False), ('train7', 7, True)):
+        batches = epoch_case_inputs(C, (16, 16, 5), 400 + C)
+
+        class Stub(torch.nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.w = torch.nn.Parameter(torch.zeros(()))
+                self.k = 0
+
+            def forward(self, x):
+                logits = batches[self.k % len(batches)][0]
+                self.k += 1
+                return logits + 0.0 * self.w
+
+        net = Stub()
+        loader = [(torch.zeros(lab.shape[0], 2, 3, 4, 4) + torch.arange(lab.shape[0]).view(-1, 1, 1, 1, 1).float(), lab) for _, lab in batches]
+        args = type('A', (), {})()
+        args.device, args.model, args.eval_mode = 'cpu', 'ConvNet3D', 'top5'
+        opt = torch.optim.SGD(net.parameters(), lr=0.0)
+        loss, accs, per = ref_utils.epoch('train' if train else 'test', loader, net, opt, torch.nn.CrossEntropyLoss(), args)
+        out[tag + '_loss'] = np.float64(loss)
+        out[tag + '_accs'] = np.asarray(accs, dtype=np.float64)
+        out[tag + '_per_class'] = np.asarray([np.nan if v is None else v for v in per], dtype=np.float64)
+    np.savez_compressed(os.path.join(GOLD, 'epoch_stats.npz'), **out)
+    print('epoch ok:', {k: (v.tolist() if v.size < 6 else v.shape) for k, v in out.items() if 'accs' in k})
+
+
 if __name__ == '__main__':
     os.makedirs(GOLD, exist_ok=True)
     if len(sys.argv) > 1:                      # regenerate selected cases only: python oracle/make_golden.py case_mtt_baseline
@@ -485,4 +528,5 @@ if __name__ == '__main__':
     case_dm_s2d()
     case_mtt_s2d()
     case_mtt_baseline()
+    case_epoch()
     print('golden vectors written to', GOLD)

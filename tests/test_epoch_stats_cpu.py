@@ -46,3 +46,31 @@ def test_epoch_stats_match_reference_bookkeeping(C, train):
     assert len(per) == len(rp) and all((a is None and b is None) or abs(a - b) < 1e-12 for a, b in zip(per, rp))
     loss2, acc2, per2 = st.result(False)
     assert acc2 == accs[0] and per2 == per
+
+
+@pytest.mark.parametrize('tag,C,train', [('test50', 50, False), ('train50', 50, True), ('test3', 3, False), ('train7', 7, True)])
+def test_epoch_stats_match_the_live_reference_golden(tag, C, train):
+    """tests/golden/epoch_stats.npz holds the outputs of the reference's own utils.epoch (run by oracle/make_golden.py with a stub
+    network returning hash-generated logits); EpochStats must reproduce them from the same logits."""
+    import os
+    import torch.nn.functional as F
+    from oracle import synth
+    gold = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'epoch_stats.npz'))
+    batches = []
+    for i, n in enumerate((16, 16, 5)):
+        logits = synth.hash_uniform((n, C), 400 + C + 10 * i, 3.0)
+        labels = (synth.hash_uniform((n,), 400 + C + 10 * i + 1, 0.5) + 0.5).mul(min(C, 12)).long().clamp_(0, C - 1)
+        labels[::2] = logits[::2].argmax(-1)
+        labels[1::4] = logits[1::4].topk(min(3, C), dim=-1).indices[:, -1]
+        batches.append((logits, labels))
+    st = EpochStats(C, 'cpu')
+    for _ in range(1 if train else 3):                      # the test branch of the reference makes three passes
+        for logits, labels in batches:
+            st.add(logits, labels, F.cross_entropy(logits, labels), train)
+    loss, accs, per = st.result(True)
+    assert abs(loss - float(gold[tag + '_loss'])) < 1e-6
+    assert np.allclose(accs, gold[tag + '_accs'], atol=1e-12)
+    ref_per = gold[tag + '_per_class']
+    assert len(per) == len(ref_per)
+    for a, b in zip(per, ref_per):
+        assert (a is None and np.isnan(b)) or abs(a - b) < 1e-12
