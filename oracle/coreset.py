@@ -4,7 +4,10 @@ import torch
 
 
 def k_center(features, ipc):
-    """distill_coreset.py:79-90: the sample nearest to the class mean, then greedy farthest-point additions."""
+    """distill_coreset.py:79-90: the sample nearest to the class mean, then greedy farthest-point additions.  (The reference
+    subtracts the (k, D) matrix of chosen centres from the (n, D) features at :86, which only broadcasts for k = 1: it raises
+    from the third centre on.  This restatement computes the intended distance to the NEAREST chosen centre; it is pinned against
+    the reference for ipc <= 2, tests/golden/coreset.npz.)"""
     mean = features.mean(dim=0, keepdim=True)
     order = torch.argsort(torch.norm(features - mean, dim=1))
     chosen = [int(order[0])]

@@ -471,6 +471,36 @@ def case_mtt_baseline():
     print('mtt_baseline ok: grand_loss', float(grand_loss), 'chunks', [u.tolist() for u in used])
 
 
+def case_coreset():
+    """distill_coreset.py:75-110: the selection statements of the reference's main(), executed verbatim (text between
+    `features = embed(imgs)` and the `image_syn[...] =` assignment of each method) on hash-generated feature matrices."""
+    import textwrap
+    from oracle import coreset as oc
+    src = open(os.path.join(REF, 'distill_coreset.py')).read()
+    blocks = {}
+    for method, result in (('k-center', 'idx_centers'), ('herding', 'idx_selected')):
+        seg = src[src.index("args.method == '%s'" % method):]
+        seg = seg[seg.index('features = embed(imgs)') + len('features = embed(imgs)'):]
+        seg = seg[:seg.index('image_syn[c*args.ipc')]
+        blocks[method] = (textwrap.dedent('\n'.join(seg.splitlines()[1:])), result)
+    out = {}
+    for tag, n, d, ipc in (('a', 7, 5, 1), ('b', 20, 16, 5), ('c', 64, 32, 10), ('d', 5, 3, 5)):
+        features = synth.hash_uniform((n, d), 700 + n)
+        args = type('A', (), {})()
+        args.ipc = ipc
+        for method, fn in (('k-center', oc.k_center), ('herding', oc.herding)):
+            code, result = blocks[method]
+            # the reference's k-center subtracts a (k, D) centre matrix from the (n, D) features (:86) and therefore raises for
+            # more than two centres; it is pinned for ipc <= 2 (the oracle / product implement the intended min over centres)
+            args.ipc = min(ipc, 2) if method == 'k-center' else ipc
+            ns = {'torch': torch, 'np': np, 'features': features, 'args': args}
+            exec(code, ns)
+            assert ns[result] == fn(features, args.ipc), (tag, method, ns[result], fn(features, args.ipc))
+            out[f'{tag}_{method}'] = np.asarray(ns[result], dtype=np.int64)
+    np.savez_compressed(os.path.join(GOLD, 'coreset.npz'), **out)
+    print('coreset ok:', {k: v.tolist() for k, v in out.items() if k.startswith('b_')})
+
+
 def epoch_case_inputs(C, sizes, seed):
     """Hash-generated logits / labels / per-batch losses of the epoch bookkeeping case (shared with tests/test_epoch_stats_cpu.py)."""
     batches = []
@@ -529,4 +559,5 @@ if __name__ == '__main__':
     case_mtt_s2d()
     case_mtt_baseline()
     case_epoch()
+    case_coreset()
     print('golden vectors written to', GOLD)
