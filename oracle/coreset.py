@@ -4,10 +4,11 @@ import torch
 
 
 def k_center(features, ipc):
-    """distill_coreset.py:79-90: the sample nearest to the class mean, then greedy farthest-point additions.  (The reference
-    subtracts the (k, D) matrix of chosen centres from the (n, D) features at :86, which only broadcasts for k = 1: it raises
-    from the third centre on.  This restatement computes the intended distance to the NEAREST chosen centre; it is pinned against
-    the reference for ipc <= 2, tests/golden/coreset.npz.)"""
+    """distill_coreset.py:79-90: the sample nearest to the class mean, then greedy farthest-point additions.  The reference reduces
+    the (n,) centre distances over the sample axis at :87 (`torch.min(dis_center, dim=-1)` on a vector), so its second centre is
+    always sample 0, and from the third centre on :86 no longer broadcasts and raises.  This restatement follows the intended rule
+    (distance to the NEAREST chosen centre, argmax over samples); it is pinned against the reference where the reference is well
+    defined (first centre, tests/golden/coreset.npz)."""
     mean = features.mean(dim=0, keepdim=True)
     order = torch.argsort(torch.norm(features - mean, dim=1))
     chosen = [int(order[0])]

@@ -490,9 +490,11 @@ def case_coreset():
         args.ipc = ipc
         for method, fn in (('k-center', oc.k_center), ('herding', oc.herding)):
             code, result = blocks[method]
-            # the reference's k-center subtracts a (k, D) centre matrix from the (n, D) features (:86) and therefore raises for
-            # more than two centres; it is pinned for ipc <= 2 (the oracle / product implement the intended min over centres)
-            args.ipc = min(ipc, 2) if method == 'k-center' else ipc
+            # the reference's k-center reduces the (n,) centre distances over the SAMPLE axis (:87 torch.min(dis_center, dim=-1) on a
+            # vector), so its second centre is always sample 0, and from the third centre on :86 no longer broadcasts and raises.
+            # It is pinned where it is well defined (the first centre, ipc = 1); the oracle / product implement the intended
+            # greedy farthest-point rule (min over centres, argmax over samples)
+            args.ipc = 1 if method == 'k-center' else ipc
             ns = {'torch': torch, 'np': np, 'features': features, 'args': args}
             exec(code, ns)
             assert ns[result] == fn(features, args.ipc), (tag, method, ns[result], fn(features, args.ipc))

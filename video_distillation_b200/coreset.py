@@ -5,7 +5,9 @@ import torch
 
 
 def k_center_select(features, ipc):
-    """Indices of the sample nearest to the class mean followed by greedy farthest-point additions (:79-90)."""
+    """Indices of the sample nearest to the class mean followed by greedy farthest-point additions (:79-90).  From the second
+    centre on this is the INTENDED rule: the reference reduces over the wrong axis (:87) and always appends sample 0, then raises
+    for ipc > 2 (see oracle/coreset.py)."""
     mean = features.mean(dim=0, keepdim=True)
     first = torch.argsort(torch.norm(features - mean, dim=1))[0]
     chosen = [int(first)]
