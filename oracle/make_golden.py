@@ -503,6 +503,38 @@ def case_coreset():
     print('coreset ok:', {k: v.tolist() for k, v in out.items() if k.startswith('b_')})
 
 
+def write_expert_files(directory, n_files=2, n_traj=3, n_epochs=5):
+    """replay_buffer_{n}.pt in the layout of buffer.py:75-103; every tensor encodes (file, trajectory, epoch)."""
+    for n in range(n_files):
+        traj = [[[torch.full((2,), float(100 * n + 10 * t + e)) for _ in range(3)] for e in range(n_epochs)] for t in range(n_traj)]
+        torch.save(traj, os.path.join(directory, 'replay_buffer_{}.pt'.format(n)))
+
+
+def case_expert_walk():
+    """distill_s2d_ms.py:114-133 (buffer discovery / shuffles) and :209-229 (per-iteration trajectory and start-epoch draw): the
+    reference's own statements executed verbatim on synthetic buffer files; pins cli.ExpertBuffers."""
+    import random
+    import tempfile
+    import textwrap
+    src = open(os.path.join(REF, 'distill_s2d_ms.py')).read()
+    head = src[src.index('        expert_files = []'):src.index('        best_acc = {m: 0 for m in model_eval_pool}')]
+    body = src[src.index('            expert_trajectory = buffer[expert_idx]'):src.index('            target_params = torch.cat([p.data.to(args.device)')]
+    with tempfile.TemporaryDirectory() as d:
+        write_expert_files(d)
+        args = type('A', (), {})()
+        args.max_start_epoch, args.expert_epochs = 3, 1
+        ns = {'os': os, 'torch': torch, 'np': np, 'random': random, 'expert_dir': d, 'args': args, 'print': lambda *a, **k: None}
+        random.seed(11)
+        np.random.seed(12)
+        exec(textwrap.dedent(head), ns)
+        seq = []
+        for _ in range(9):
+            exec(textwrap.dedent(body), ns)
+            seq.append((float(ns['starting_params'][0][0]), float(ns['target_params'][0][0]), int(ns['start_epoch'])))
+    np.savez_compressed(os.path.join(GOLD, 'expert_walk.npz'), walk=np.asarray(seq, dtype=np.float64))
+    print('expert walk ok:', seq[:4])
+
+
 def epoch_case_inputs(C, sizes, seed):
     """Hash-generated logits / labels / per-batch losses of the epoch bookkeeping case (shared with tests/test_epoch_stats_cpu.py)."""
     batches = []
@@ -562,4 +594,5 @@ if __name__ == '__main__':
     case_mtt_baseline()
     case_epoch()
     case_coreset()
+    case_expert_walk()
     print('golden vectors written to', GOLD)

@@ -67,3 +67,22 @@ def test_expert_buffers_walk(tmp_path):
         assert 0 <= e0 < 2 and float(target[0][0]) - float(start[0][0]) == 1.0
         seen.append(float(start[0][0]))
     assert len(set(int(v) // 100 for v in seen)) == 1          # like the reference, the resident buffer is only reshuffled
+
+
+def test_expert_buffers_reproduce_the_reference_walk(tmp_path):
+    """tests/golden/expert_walk.npz: (start tensor, target tensor, start epoch) of nine consecutive iterations drawn by the
+    reference's own buffer statements (executed verbatim by oracle/make_golden.py) with random.seed(11), np.random.seed(12)."""
+    import random
+    import numpy as np
+    gold = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'expert_walk.npz'))['walk']
+    for n in range(2):
+        traj = [[[torch.full((2,), float(100 * n + 10 * t + e)) for _ in range(3)] for e in range(5)] for t in range(3)]
+        torch.save(traj, tmp_path / f'replay_buffer_{n}.pt')
+    random.seed(11)
+    np.random.seed(12)
+    eb = cli.ExpertBuffers(str(tmp_path), max_start_epoch=3, expert_epochs=1)
+    walk = []
+    for _ in range(9):
+        start, target, e0 = eb.draw()
+        walk.append((float(start[0][0]), float(target[0][0]), e0))
+    assert np.array_equal(np.asarray(walk, dtype=np.float64), gold)
