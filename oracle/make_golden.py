@@ -535,6 +535,36 @@ def case_expert_walk():
     print('expert walk ok:', seq[:4])
 
 
+def case_multistatic():
+    """utils.MultiStaticSharedDataset.__getitem__ (:469-488) of the live reference with a recording hallucinator: which static row /
+    dynamic memory each sample pairs, and in which order random.randint is consumed, for spc = 2 (vpc = 1) and spc = 10 (vpc = 5)."""
+    import random
+    out = {}
+    for tag, C, spc, dpc in (('vpc1', 4, 2, 2), ('vpc5', 3, 10, 10)):
+        static = torch.arange(C * spc).float().view(-1, 1, 1, 1).expand(C * spc, 3, 2, 2).contiguous()
+        dynamic = (torch.arange(C).view(C, 1) * 100 + torch.arange(dpc).view(1, dpc)).float().view(C, dpc, 1, 1, 1, 1).expand(C, dpc, 2, 1, 2, 2).contiguous()
+        seen = []
+
+        class Rec(torch.nn.Module):
+            def forward(self, st, dy):
+                seen.append((int(st.flatten()[0]), int(dy.flatten()[0])))
+                return st.unsqueeze(1)
+
+        ds = ref_utils.MultiStaticSharedDataset(static, dynamic, torch.nn.ModuleList([Rec(), Rec(), Rec()]))
+        random.seed(21)
+        rows = []
+        for index in list(range(len(ds))) * 2:
+            _, label = ds[index]
+            st, dy = seen[-1]
+            rows.append((index, st, int(label), dy % 100))
+            assert dy // 100 == int(label)
+        out[tag] = np.asarray(rows, dtype=np.int64)
+        out[tag + '_len'] = np.int64(len(ds))
+        out[tag + '_next_random'] = np.float64(random.random())          # state of the generator after the walk
+    np.savez_compressed(os.path.join(GOLD, 'multistatic.npz'), **out)
+    print('multistatic ok:', out['vpc1'][:4].tolist())
+
+
 def epoch_case_inputs(C, sizes, seed):
     """Hash-generated logits / labels / per-batch losses of the epoch bookkeeping case (shared with tests/test_epoch_stats_cpu.py)."""
     batches = []
@@ -595,4 +625,5 @@ if __name__ == '__main__':
     case_epoch()
     case_coreset()
     case_expert_walk()
+    case_multistatic()
     print('golden vectors written to', GOLD)

@@ -74,3 +74,25 @@ def test_device_dataset_sampling_is_reference_stream():
         loc = ds.local_index(got[own])
         assert ds.videos.shape[0] == len(own) * per and int(loc.max()) < ds.videos.shape[0]
     assert owned_classes(50, 0, 8) == [0, 8, 16, 24, 32, 40, 48] and len(owned_classes(50, 7, 8)) == 6
+
+
+def test_multistatic_dataset_pairing_matches_the_live_reference():
+    """tests/golden/multistatic.npz: (index, static row, label, dynamic memory) chosen by the reference's
+    MultiStaticSharedDataset.__getitem__ (recording hallucinator, random.seed(21)) — same pairing, same consumption of random."""
+    import os
+    import random
+    import numpy as np
+    import torch
+    from video_distillation_b200.utils import MultiStaticSharedDataset
+    gold = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'multistatic.npz'))
+    for tag, C, spc, dpc in (('vpc1', 4, 2, 2), ('vpc5', 3, 10, 10)):
+        ds = MultiStaticSharedDataset(torch.zeros(C * spc, 3, 2, 2), torch.zeros(C, dpc, 2, 1, 2, 2), torch.nn.ModuleList([torch.nn.Identity()] * 3))
+        assert len(ds) == int(gold[tag + '_len'])
+        random.seed(21)
+        rows = []
+        for index in list(range(len(ds))) * 2:
+            static_idx, label, dynamic_idx, hal_idx = ds.pick(index)
+            assert 0 <= hal_idx < 3
+            rows.append((index, static_idx, label, dynamic_idx))
+        assert np.array_equal(np.asarray(rows, dtype=np.int64), gold[tag])
+        assert random.random() == float(gold[tag + '_next_random'])

@@ -96,7 +96,9 @@ class MultiStaticSharedDataset(Dataset):
         self.n_s = static.shape[0]
         self.n_c, self.dpc = dynamic.shape[0], dynamic.shape[1]
 
-    def __getitem__(self, index):
+    def pick(self, index):
+        """(static row, label, dynamic memory, hallucinator) of sample ``index`` — the reference's pairing and its order of
+        ``random.randint`` draws (utils.py:470-484)."""
         per_s = self.n_s // self.n_c
         if per_s == 10:
             label, idx = index // 5, index % 5
@@ -108,7 +110,12 @@ class MultiStaticSharedDataset(Dataset):
             dynamic_idx = random.randint(0, self.dpc - 1)
         else:
             raise ValueError('MultiStaticSharedDataset: spc must be 2 (vpc=1) or 10 (vpc=5)')
-        hal = self.hallucinator[random.randint(0, len(self.hallucinator) - 1)]
+        hal_idx = random.randint(0, len(self.hallucinator) - 1)
+        return static_idx, label, dynamic_idx, hal_idx
+
+    def __getitem__(self, index):
+        static_idx, label, dynamic_idx, hal_idx = self.pick(index)
+        hal = self.hallucinator[hal_idx]
         dev = self.dynamic.device
         with torch.no_grad():
             video = hal.compose(self.static, self.dynamic, torch.tensor([static_idx], device=dev),
