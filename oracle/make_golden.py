@@ -565,6 +565,33 @@ def case_multistatic():
     print('multistatic ok:', out['vpc1'][:4].tolist())
 
 
+def case_eval_schedule():
+    """utils.evaluate_synset (:848-886) of the live reference with utils.epoch replaced by a recorder: the sequence of
+    (mode, learning rate of the optimizer handed to epoch) calls for Epoch = 7 without and with test_freq."""
+    out = {}
+    for tag, test_freq in (('final', None), ('freq3', 3)):
+        calls = []
+
+        def recorder(mode, dataloader, net, optimizer, criterion, args):
+            calls.append((0 if mode == 'train' else 1, optimizer.param_groups[0]['lr'], optimizer.param_groups[0]['momentum'],
+                          optimizer.param_groups[0]['weight_decay']))
+            return 0.5, 0.25, [0.25]
+        real = ref_utils.epoch
+        ref_utils.epoch = recorder
+        try:
+            args = type('A', (), {})()
+            args.lr_net, args.epoch_eval_train, args.device, args.batch_train, args.eval_mode = 0.02, 7, 'cpu', 4, 'S'
+            net = torch.nn.Linear(3, 2)
+            _, acc_train, acc_test, acc_per = ref_utils.evaluate_synset(0, net, torch.zeros(6, 2, 3, 4, 4), torch.zeros(6).long(), None, args,
+                                                                        mode='none', test_freq=test_freq)
+        finally:
+            ref_utils.epoch = real
+        out[tag] = np.asarray(calls, dtype=np.float64)
+        out[tag + '_ret'] = np.asarray([acc_train, acc_test], dtype=np.float64)
+    np.savez_compressed(os.path.join(GOLD, 'eval_schedule.npz'), **out)
+    print('eval schedule ok:', out['final'][:, :2].tolist())
+
+
 def epoch_case_inputs(C, sizes, seed):
     """Hash-generated logits / labels / per-batch losses of the epoch bookkeeping case (shared with tests/test_epoch_stats_cpu.py)."""
     batches = []
@@ -626,4 +653,5 @@ if __name__ == '__main__':
     case_coreset()
     case_expert_walk()
     case_multistatic()
+    case_eval_schedule()
     print('golden vectors written to', GOLD)

@@ -2,6 +2,7 @@
 import inspect
 
 import numpy as np
+import pytest
 import torch
 
 import oracle
@@ -96,3 +97,27 @@ def test_multistatic_dataset_pairing_matches_the_live_reference():
             rows.append((index, static_idx, label, dynamic_idx))
         assert np.array_equal(np.asarray(rows, dtype=np.int64), gold[tag])
         assert random.random() == float(gold[tag + '_next_random'])
+
+
+@pytest.mark.parametrize('tag,test_freq', [('final', None), ('freq3', 3)])
+def test_evaluate_synset_schedule_matches_the_live_reference(tag, test_freq, monkeypatch):
+    """tests/golden/eval_schedule.npz: the (train / test, lr, momentum, weight decay) sequence of epoch() calls the reference's
+    evaluate_synset makes for Epoch = 7 (recorded by oracle/make_golden.py with utils.epoch patched)."""
+    import os
+    import numpy as np
+    import torch
+    from video_distillation_b200 import utils as U
+    gold = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'eval_schedule.npz'))
+    calls = []
+
+    def recorder(mode, dataloader, net, optimizer, criterion, args):
+        g = optimizer.param_groups[0]
+        calls.append((0 if mode == 'train' else 1, g['lr'], g['momentum'], g['weight_decay']))
+        return 0.5, 0.25, [0.25]
+    monkeypatch.setattr(U, 'epoch', recorder)
+    args = type('A', (), {})()
+    args.lr_net, args.epoch_eval_train, args.device, args.batch_train, args.eval_mode = 0.02, 7, 'cpu', 4, 'S'
+    _, acc_train, acc_test, _ = U.evaluate_synset(0, torch.nn.Linear(3, 2), torch.zeros(6, 2, 3, 4, 4), torch.zeros(6).long(), None, args,
+                                                  mode='none', test_freq=test_freq)
+    assert np.allclose(np.asarray(calls, dtype=np.float64), gold[tag], rtol=0, atol=1e-15)
+    assert [acc_train, acc_test] == gold[tag + '_ret'].tolist()
