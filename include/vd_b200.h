@@ -199,6 +199,26 @@ int vd_tc_conv_layer(int layer, const void* in, const void* wimg, const float* b
                      void* out, uint8_t* code, int code_first_item, const vd_tc_plan* plan,
                      const int64_t* item_index, int B, int raw, void* stream);
 
+/* ---- split-fp16 forward ("f16x3"): the parity mode of the fused pipeline.  Every operand value is carried as an fp16
+ * pair v = hi + lo (22 significand bits) and every product as xh*wh + xl*wh + xh*wl (+ xl*wl in conv 0) accumulated in the
+ * SAME fp32 TMEM accumulator, so embeddings equal an fp32 evaluation of networks.py:747-751 to ~3e-6 and ReLU / MaxPool
+ * routing is decided on fp32-equivalent sums.  Same three fused layers, same epilogues, same routing codes as
+ * vd_tc_conv_layer; the packed operands are twice as large (layouts X0s / A1s / A2s in csrc/tc_layout.h).
+ *   vd_tc_x3_sizes         out[0..2] = X0s / A1s / A2s bytes per video, out[3..5] = weight image bytes of conv 0 / 1 / 2
+ *   vd_tc_x3_pack_video    fp32 (Bsrc,T,3,H,W) videos (+ optional gather index) -> X0s          [get_images, distill_s2d_ms.py:81-87]
+ *   vd_tc_x3_pack_video_u8 uint8 frames with (u/255 - mean[c]) / std[c] fused (HOST mean3 / std3) [utils.py:214-230]
+ *   vd_tc_x3_pack_weights  fp32 OIDHW weights of features.{0,3,6} -> weight images (any pair may be NULL)
+ *   vd_tc_x3_conv_layer    layer 0: X0s -> A1s; layer 1: A1s -> A2s; layer 2: A2s (ceil(B/4)*4 videos) -> fp32 embeddings
+ *                          (A1s / A2s zeroed once by the caller; code / code_first_item / item_index as vd_tc_conv_layer) */
+int vd_tc_x3_sizes(const vd_tc_plan* plan, int64_t* out);
+int vd_tc_x3_pack_video(const float* video, const int64_t* index, void* x0s, const vd_tc_plan* plan, int B, void* stream);
+int vd_tc_x3_pack_video_u8(const uint8_t* video, const int64_t* index, void* x0s, const vd_tc_plan* plan, int B,
+                           const float* mean3, const float* std3, void* stream);
+int vd_tc_x3_pack_weights(const float* w_l0, const float* w_l1, const float* w_l2, void* w0s, void* w1s, void* w2s,
+                          void* stream);
+int vd_tc_x3_conv_layer(int layer, const void* in, const void* wimg, const float* bias, void* out, uint8_t* code,
+                        int code_first_item, const vd_tc_plan* plan, const int64_t* item_index, int B, void* stream);
+
 /* ---- backward of the tensor-core embed (gradient to the input video; weights are frozen in DM).
  * dgrad of each conv is a plain GEMM on tensor cores, col[(ci,tap), pixel] = sum_co W[co,ci,tap] *
  * dY[co,pixel] (same ws_gemm kernel: transposed weights = M operand, packed dY = N operand), followed
@@ -298,7 +318,7 @@ int vd_tc_set_profile_buffer(long long* buf);
 
 /* Host-only introspection (no GPU work): the launch parameters vd_tc_conv_layer would use,
  * flattened to int64 (layout documented in tests/tc_emulator.py); cap >= 248. */
-int vd_tc_debug_params(int layer, const vd_tc_plan* plan, int B, int64_t* out, int cap);   /* layer 3,4,5 = bwd gemm of conv 0,1,2 */
+int vd_tc_debug_params(int layer, const vd_tc_plan* plan, int B, int64_t* out, int cap);   /* layer 3,4,5 = bwd gemm of conv 0,1,2; 6,7,8 = split-fp16 conv 0,1,2 */
 
 #ifdef __cplusplus
 }

@@ -38,7 +38,7 @@ class Launch:
     """Launch shape (the fields of WsParams the control flow depends on)."""
 
     def __init__(self, n_tiles, grid, n_sa, n_sb, n_steps, G, RP, RW, acc_stages, resident, n_u=1, nu_total=1, ug_count=1,
-                 stream_pairs=0):
+                 stream_pairs=0, stream_mode=0):
         self.__dict__.update(locals())
         self.G = n_steps if resident else G
 
@@ -101,6 +101,33 @@ def stream_groups(L, cta):
         tile += L.grid
 
 
+def l0s_groups(L, cta):
+    """tc_conv.cu `next_l0s` (split-fp16 conv 0): stage (frame i, part) feeds output frames i + 1 - kt (kt = 2, 1, 0);
+    frame f of the running count lives in accumulator buffer (qbase + f) & 3."""
+    pslot = pphase = 0
+    qbase = 0
+    T = L.stream_pairs
+    tile = cta
+    while tile < L.n_tiles:
+        for ss in range(2 * T):
+            i, part = divmod(ss, 2)
+            kts = [kt for kt in (2, 1, 0) if 0 <= i + 1 - kt < T]
+            for kt in kts:
+                f = i + 1 - kt
+                q = qbase + f
+                buf = q & 3
+                first_write = part == 0 and (kt == 0 or (f == 0 and kt == 1))
+                final_write = part == 1 and (kt == 2 or (f == T - 1 and kt == 1))
+                yield dict(w_acc=('acc_empty', buf, ((q >> 2) & 1) ^ 1) if first_write else None, w_pix=('pix_full', pslot, pphase),
+                           w_w=None, acc=buf, first=first_write, pix=pslot, wt=None, c_w=None,
+                           c_pix=('pix_empty', pslot) if kt == kts[-1] else None, c_acc=('acc_full', buf) if final_write else None)
+            pslot += 1
+            if pslot == L.RP:
+                pslot, pphase = 0, pphase ^ 1
+        qbase += T
+        tile += L.grid
+
+
 def simulate(L, cta=0, mma_latency=3):
     """Runs one CTA of the launch; returns the number of MMA groups issued.  Raises AssertionError on a violation."""
     bars = {('pix_full', i): Barrier(1) for i in range(L.RP)}
@@ -110,7 +137,7 @@ def simulate(L, cta=0, mma_latency=3):
     bars.update({('acc_full', i): Barrier(2) for i in range(L.acc_stages)})
     bars.update({('acc_empty', i): Barrier(1) for i in range(L.acc_stages)})      # the 4 epilogue warps modelled as one actor
     bars.update({('baton', i): Barrier(1) for i in range(2)})
-    groups = list((stream_groups if L.stream_pairs else classic_groups)(L, cta))
+    groups = list((l0s_groups if L.stream_mode == 2 else stream_groups if L.stream_pairs else classic_groups)(L, cta))
     pipe = deque()                       # in-flight groups: [remaining time, group index, issuer]
     issued_by = [-1, -1]                 # index of the last group each issuer put into the pipe
     done = -1                            # index of the last completed group

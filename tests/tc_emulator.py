@@ -16,7 +16,7 @@ import torch
 
 from video_distillation_b200 import _lib
 
-MAX_COPIES, MAX_STEPS = 8, 64
+MAX_COPIES, MAX_STEPS = 8, 80
 
 
 def bf16_round(x):
@@ -206,8 +206,8 @@ class Params:
         plan = _lib.TcPlan()
         _lib.check(lib.vd_tc_plan_make(ctypes.byref(plan), T, HW, HW), 'tc_plan_make')
         self.plan = plan
-        buf = (ctypes.c_int64 * 256)()
-        _lib.check(lib.vd_tc_debug_params(layer, ctypes.byref(plan), B, buf, 256), 'tc_debug_params')
+        buf = (ctypes.c_int64 * 320)()
+        _lib.check(lib.vd_tc_debug_params(layer, ctypes.byref(plan), B, buf, 320), 'tc_debug_params')
         v = list(buf)
         names = ['n_tiles', 'tiles_per_item', 'v_count', 'item_stride', 'u_stride', 'v_stride', 'n_sa', 'n_sb',
                  'sa_stride', 'sb_stride', 'n_copies', 'stage_bytes', 'stage_pitch', 'n_steps', 'a_sa_stride16',
@@ -233,15 +233,18 @@ def _desc_gather(mem16, start_bytes, lbo_bytes, sbo_bytes, rows):
     return mem16[addr // 2]
 
 
-def emulate_layer(layer, pix_u16, wimg_u16, T, HW, B, tiles=None):
-    """Returns D of shape (n_tiles_run, n_acc, 128, ncols) float32 (accumulated in float64)."""
+def emulate_layer(layer, pix_u16, wimg_u16, T, HW, B, tiles=None, fmt='bf16'):
+    """Returns D of shape (n_tiles_run, n_acc, 128, ncols) float32 (accumulated in float64).
+    fmt: element type of the 16-bit operand images ('bf16' or 'f16')."""
     p = Params(layer, T, HW, B)
     pix = pix_u16.reshape(-1)
     wimg = wimg_u16.reshape(-1)
     tiles = range(p.n_tiles) if tiles is None else tiles
     out = []
-    # bf16 bit patterns -> float via a lookup of the upper 16 bits
+    # 16-bit patterns -> float
     def f32(u16):
+        if fmt == 'f16':
+            return u16.astype(np.uint16).view(np.float16).astype(np.float64)
         return (u16.astype(np.uint32) << 16).view(np.float32).astype(np.float64)
     for tile in tiles:
         item, sub = divmod(tile, p.tiles_per_item)
@@ -317,3 +320,231 @@ def emulate_layer0_streaming(pix_u16, wimg_u16, T, HW, B, columns=None):
                 written[pair] = True
         out[(item, rb)] = D.astype(np.float32)
     return out, p
+
+
+# ------------------------------------------------------------------ split-fp16 forward (SGeo, csrc/tc_layout.h)
+def split_f16(x):
+    """float32 torch tensor -> (hi, lo) uint16 numpy fp16 bit patterns with x ~= hi + lo (device: split_h)."""
+    x = x.float().clamp(-65504.0, 65504.0)
+    hi = x.to(torch.float16)
+    lo = (x - hi.float()).to(torch.float16)
+    return hi.view(torch.int16).numpy().view(np.uint16), lo.view(torch.int16).numpy().view(np.uint16)
+
+
+def from_f16_bits(u):
+    return torch.from_numpy(u.astype(np.uint16).view(np.float16).astype(np.float32))
+
+
+def f16x2_round(x):
+    """the value an fp16 pair carries: hi + lo"""
+    hi, lo = split_f16(x)
+    return from_f16_bits(hi) + from_f16_bits(lo)
+
+
+class SGeo:
+    def __init__(self, g):
+        self.R0s = 4 if g.Wo0 * 4 <= 128 else 2
+        self.N0s = self.R0s * g.Wo0
+        self.nrb0s = g.Ho0 // self.R0s
+        self.frame0s = 12 * g.plane0
+        self.video0s = (g.T + 2) * self.frame0s
+        self.video1s = 8 * g.slice1
+        self.video2s = 196 * g.group2
+
+
+def l1s_tap(idx):
+    if idx < 9:
+        ph, pw, r = 0, 0, idx
+    elif idx < 21:
+        ph, pw, r = 0, 1, idx - 9
+    elif idx < 33:
+        ph, pw, r = 1, 0, idx - 21
+    else:
+        ph, pw, r = 1, 1, idx - 33
+    nw = 4 if pw else 3
+    sh, sw = divmod(r, nw)
+    kh = 2 * sh if ph else 2 * sh + 1
+    kw = 2 * sw if pw else 2 * sw + 1
+    return kh * 7 + kw
+
+
+def pack_x0s(video, g):
+    """video (B,T,3,H,W) float32 -> uint16 (B, T+2, 2, 3, 2, RI0, Wo0, 8)."""
+    B = video.shape[0]
+    out = np.zeros((B, g.T + 2, 2, 3, 2, g.RI0, g.Wo0, 8), np.uint16)
+    for part, bits in enumerate(split_f16(video)):
+        for par in range(2):
+            for row in range(g.RI0):
+                h = 2 * row - 3 if par else 2 * row - 2
+                if not (0 <= h < g.HW):
+                    continue
+                for kw in range(7):
+                    wo = np.arange(g.Wo0)
+                    w = 2 * wo + kw - 3
+                    ok = (w >= 0) & (w < g.HW)
+                    o = out[:, 1:g.T + 1, part, :, par, row]                 # (B,T,3,Wo0,8) view
+                    o[:, :, :, wo[ok], kw] = bits[:, :, :, h, w[ok]]
+    return out
+
+
+def pack_a1s(x, g):
+    """pooled conv-0 output (B,64,T,H1,H1) float32 -> uint16 (B, 8, T+2, 2, 2, 2, RI1, P1, 8) [chunk][t][part][ph][pw][i][j][e]."""
+    B = x.shape[0]
+    out = np.zeros((B, 8, g.T + 2, 2, 2, 2, g.RI1, g.P1, 8), np.uint16)
+    for part, bits in enumerate(split_f16(x)):
+        for h in range(g.H1):
+            for w in range(g.H1):
+                v = bits[:, :, :, h, w].reshape(B, 8, 8, g.T)            # (B, chunk, e, T)
+                out[:, :, 1:g.T + 1, part, coord_par(h), coord_par(w), coord_pos(h), coord_pos(w), :] = v.transpose(0, 1, 3, 2)
+    return out
+
+
+def unpack_a1s(buf, g, B):
+    """inverse of pack_a1s -> (hi + lo) float32 (B,64,T,H1,H1)."""
+    a = buf.reshape(B, 8, g.T + 2, 2, 2, 2, g.RI1, g.P1, 8)
+    out = torch.zeros(B, 64, g.T, g.H1, g.H1)
+    for part in range(2):
+        bits = np.zeros((B, 64, g.T, g.H1, g.H1), np.uint16)
+        for h in range(g.H1):
+            for w in range(g.H1):
+                v = a[:, :, 1:g.T + 1, part, coord_par(h), coord_par(w), coord_pos(h), coord_pos(w), :]     # (B,8,T,8)
+                bits[:, :, :, h, w] = v.transpose(0, 1, 3, 2).reshape(B, 64, g.T)
+        out += from_f16_bits(bits)
+    return out
+
+
+def pack_a2s(x, g, Bpad=None):
+    """pooled conv-1 output (B,128,T2,H2,H2) float32 -> uint16 (Bpad, 49, 4, 2, 4, To2+2, Ho2, Wo2, 8) [khw][quarter][part][k][t][ho][wo][e]."""
+    B = x.shape[0]
+    Bpad = Bpad or B
+    out = np.zeros((Bpad, 49, 4, 2, 4, g.To2 + 2, g.Ho2, g.Wo2, 8), np.uint16)
+    for part, bits in enumerate(split_f16(x)):
+        for kh in range(7):
+            for kw in range(7):
+                for ho in range(g.Ho2):
+                    h = 2 * ho + kh - 3
+                    if not (0 <= h < g.H2):
+                        continue
+                    for wo in range(g.Wo2):
+                        w = 2 * wo + kw - 3
+                        if not (0 <= w < g.H2):
+                            continue
+                        v = bits[:, :, :, h, w].reshape(B, 4, 4, 8, g.T2)          # (B, quarter, k, e, T2)
+                        out[:B, kh * 7 + kw, :, part, :, 1:g.T2 + 1, ho, wo, :] = v.transpose(0, 1, 2, 4, 3)
+    return out
+
+
+def unpack_a2s(buf, g, B):
+    a = buf.reshape(-1, 49, 4, 2, 4, g.To2 + 2, g.Ho2, g.Wo2, 8)
+    out = torch.zeros(B, 128, g.T2, g.H2, g.H2)
+    consistent = True
+    for part in range(2):
+        bits = np.zeros((B, 128, g.T2, g.H2, g.H2), np.uint16)
+        seen = np.zeros((g.H2, g.H2), bool)
+        for kh in range(7):
+            for kw in range(7):
+                for ho in range(g.Ho2):
+                    h = 2 * ho + kh - 3
+                    if not (0 <= h < g.H2):
+                        continue
+                    for wo in range(g.Wo2):
+                        w = 2 * wo + kw - 3
+                        if not (0 <= w < g.H2):
+                            continue
+                        v = a[:B, kh * 7 + kw, :, part, :, 1:g.T2 + 1, ho, wo, :]      # (B,4,4,T2,8)
+                        v = v.transpose(0, 1, 2, 4, 3).reshape(B, 128, g.T2)
+                        if seen[h, w]:
+                            consistent &= bool((bits[:, :, :, h, w] == v).all())
+                        bits[:, :, :, h, w] = v
+                        seen[h, w] = True
+        consistent &= bool(seen.all())
+        out += from_f16_bits(bits)
+    return out, consistent
+
+
+def pack_w0s(w):
+    """(64,3,3,7,7) -> uint16 (3, 11, 2, 128, 8) [kt][step][k][row][e]; row 32q + l: channel 16q + (l & 15), part l >> 4."""
+    parts = split_f16(w)
+    out = np.zeros((3, 11, 2, 128, 8), np.uint16)
+    for row in range(128):
+        co, part = (row >> 5) * 16 + (row & 15), (row >> 4) & 1
+        for step in range(11):
+            for k in range(2):
+                ch = 2 * step + k
+                if ch >= 21:
+                    continue
+                c, kh = ch // 7, l0_chunk_kh(ch % 7)
+                out[:, step, k, row, :7] = parts[part][co, c, :, kh, :]
+    return out
+
+
+def pack_w1s(w):
+    """(128,64,3,7,7) -> uint16 (3, 8, 74, 2, 128, 8) [kt][chunk][step][k][row][e]."""
+    hi, lo = (b.reshape(128, 8, 8, 3, 7, 7) for b in split_f16(w))        # row, chunk, e, kt, kh, kw
+    out = np.zeros((3, 8, 74, 2, 128, 8), np.uint16)
+    for step in range(74):
+        for k in range(2):
+            if step < 49:
+                idx, src = step, hi
+            else:
+                idx, src = 2 * (step - 49) + k, lo
+            if idx >= 49:
+                continue
+            kh, kw = divmod(l1s_tap(idx), 7)
+            out[:, :, step, k, :, :] = src[:, :, :, :, kh, kw].transpose(3, 1, 0, 2)      # (kt, chunk, row, e)
+    return out
+
+
+def pack_w2s(w):
+    """(128,128,3,7,7) -> uint16 (7, 7, 4, 18, 2, 128, 8) [kh][kw][quarter][step][k][row][e]."""
+    hi, lo = (b.reshape(128, 4, 4, 8, 3, 7, 7) for b in split_f16(w))     # row, quarter, c, e, kt, kh, kw
+    out = np.zeros((7, 7, 4, 18, 2, 128, 8), np.uint16)
+    for kt in range(3):
+        for s6 in range(6):
+            for k in range(2):
+                c, src = (s6, hi) if s6 < 4 else (2 * (s6 - 4) + k, lo)
+                out[:, :, :, kt * 6 + s6, k, :, :] = src[:, :, c, :, kt, :, :].transpose(3, 4, 1, 0, 2)   # (kh, kw, quarter, row, e)
+    return out
+
+
+def emulate_layer0s(pix_u16, wimg_u16, T, HW, B, columns=None):
+    """Split-fp16 conv 0 in the kernel's order (tc_conv.cu: next_l0s) with the REAL tables (debug layer 6): a tile is a
+    column (video, band of R0s rows); stage (frame i, part) feeds output frames i + 1 - kt through weight window kt.
+    Returns {(item, rb): D (T, 128, ncols)} raw accumulators (rows still M-stacked)."""
+    p = Params(6, T, HW, B)
+    pix = pix_u16.reshape(-1)
+    wimg = wimg_u16.reshape(-1)
+    columns = range(p.n_tiles) if columns is None else columns
+
+    def f32(u16):
+        return u16.astype(np.uint16).view(np.float16).astype(np.float64)
+    out = {}
+    for col in columns:
+        item, rb = divmod(col, p.v_count)
+        gbase = item * p.item_stride + rb * p.v_stride
+        D = np.zeros((T, 128, p.ncols))
+        for i in range(p.n_sa):
+            for part in range(p.n_sb):
+                smem = np.zeros(p.stage_pitch // 2, np.uint16)
+                src = gbase + i * p.sa_stride + part * p.sb_stride
+                for c in range(p.n_copies):
+                    n = p.copy_bytes[c] // 2
+                    s0 = (src + p.copy_gofs[c]) // 2
+                    smem[p.copy_sofs[c] // 2: p.copy_sofs[c] // 2 + n] = pix[s0:s0 + n]
+                for kt in (2, 1, 0):
+                    f = i + 1 - kt
+                    if not (0 <= f < T):
+                        continue
+                    for j in range(p.n_steps):
+                        a_start = (p.a_off16[j] + kt * p.a_sa_stride16) * 16
+                        A = f32(_desc_gather(wimg, a_start, p.a_lbo16 * 16, p.a_sbo16 * 16, 128))
+                        Bm = f32(_desc_gather(smem, p.b_off16[j] * 16, p.b_lbo16[j] * 16, 128, p.ncols))
+                        D[f] += A @ Bm.T
+        out[(item, rb)] = D.astype(np.float32)
+    return out, p
+
+
+def unstack_l0s(D):
+    """(.., 128, n) M-stacked accumulator rows -> (.., 64, n): channel 16q + j = row 32q + j (wh part) + row 32q + 16 + j (wl part)."""
+    d = D.reshape(D.shape[:-2] + (4, 2, 16, D.shape[-1]))
+    return (d[..., 0, :, :] + d[..., 1, :, :]).reshape(D.shape[:-2] + (64, D.shape[-1]))

@@ -13,6 +13,8 @@ SHAPES = {
     'dgrad conv1': (3, 2, 64, 8, 3, 3, 2, False),
     'dgrad conv0': (3, 1, 64, 1, 2, 1, 2, True),
     'wgrad': (5, 1, 8, 8, 2, 2, 2, False),
+    'split conv1': (3, 8, 74, 4, 2, 3, 1, False),
+    'split conv2': (49, 4, 18, 6, 2, 2, 1, False),
 }
 
 
@@ -43,6 +45,17 @@ def test_conv0_streaming_generator(pairs, n_tiles, grid, cta, RP):
     L = Launch(n_tiles, grid, 2 * pairs, 1, 11, 1, RP, 1, 2, True, stream_pairs=pairs)
     columns = len(range(cta, n_tiles, grid))
     assert simulate(L, cta) == columns * (4 * pairs - 2)           # no MMAs on the two all-zero temporal halo frames
+
+
+@pytest.mark.parametrize('T', [4, 8, 16, 32])
+@pytest.mark.parametrize('n_tiles,grid,cta', [(1, 1, 0), (4, 2, 1), (5, 3, 0), (2, 148, 1)])
+@pytest.mark.parametrize('RP', [2, 3, 4])
+def test_split_conv0_generator(T, n_tiles, grid, cta, RP):
+    # split-fp16 conv 0: 2T stages (frame, part), 4 rotating accumulators (output frames), 3T - 2 groups per part
+    L = Launch(n_tiles, grid, T, 2, 11, 1, RP, 1, 4, True, stream_pairs=T, stream_mode=2)
+    columns = len(range(cta, n_tiles, grid))
+    for latency in (1, 3, 11):
+        assert simulate(L, cta, mma_latency=latency) == columns * 2 * (3 * T - 2)
 
 
 @pytest.mark.parametrize('latency', [1, 2, 5, 17])

@@ -115,3 +115,65 @@ def test_layer0_streaming_schedule(T, HW, cols):
             d = torch.from_numpy(D[tp]).reshape(2, 64, g.R0, g.Wo0)
             ref = y[item, :, 2 * tp:2 * tp + 2, rb * g.R0:(rb + 1) * g.R0, :].permute(1, 0, 2, 3)
             assert rel(d, ref) < 1e-5, (item, rb, tp, rel(d, ref))
+
+
+# ------------------------------------------------------------------ split-fp16 forward (SGeo): tables + layouts
+@pytest.mark.parametrize('T,HW,cols', [(8, 64, [0, 5, 15]), (4, 112, [0, 13, 27, 55])])
+def test_split_layer0_tables_and_schedule(T, HW, cols):
+    g = em.Geo(T, HW)
+    sg = em.SGeo(g)
+    B = 2
+    gen = torch.Generator().manual_seed(T)
+    video = torch.randn(B, T, 3, HW, HW, generator=gen)
+    w = torch.randn(64, 3, 3, 7, 7, generator=gen) * 0.05
+    y = conv_ref(em.f16x2_round(video).permute(0, 2, 1, 3, 4), em.f16x2_round(w))     # (B,64,T,Ho0,Wo0)
+    out, p = em.emulate_layer0s(em.pack_x0s(video, g), em.pack_w0s(w), T, HW, B, cols)
+    assert p.ncols == sg.N0s and p.n_acc == 1 and p.acc_cols * p.acc_stages <= 512 and p.smem_total <= 232448
+    for (item, rb), D in out.items():
+        d = torch.from_numpy(em.unstack_l0s(D)).reshape(T, 64, sg.R0s, g.Wo0)
+        ref = y[item, :, :, rb * sg.R0s:(rb + 1) * sg.R0s, :].permute(1, 0, 2, 3)
+        assert rel(d, ref) < 2e-6, (item, rb, rel(d, ref))
+
+
+@pytest.mark.parametrize('T,HW,tiles', [(8, 64, [0, 1]), (4, 112, [1])])
+def test_split_layer1_tables(T, HW, tiles):
+    g = em.Geo(T, HW)
+    B = 1
+    gen = torch.Generator().manual_seed(HW)
+    x = torch.randn(B, 64, T, g.H1, g.H1, generator=gen).abs()
+    w = torch.randn(128, 64, 3, 7, 7, generator=gen) * 0.02
+    xr, wr = em.f16x2_round(x), em.f16x2_round(w)
+    # the split path drops the lo*lo term: compare against hi*hi + lo*hi + hi*lo
+    xh = em.from_f16_bits(em.split_f16(x)[0]); wh = em.from_f16_bits(em.split_f16(w)[0])
+    y = conv_ref(xh, wh) + conv_ref(xr - xh, wh) + conv_ref(xh, wr - wh)
+    a1 = em.pack_a1s(x, g)
+    assert torch.equal(em.unpack_a1s(a1, g, B), xr)
+    D, p = em.emulate_layer(7, a1, em.pack_w1s(w), T, HW, B, tiles, fmt='f16')
+    assert p.ncols == g.N1 and p.n_steps == 74 and p.smem_total <= 232448 and p.n_acc * p.acc_cols <= 512
+    fpt = p.n_acc
+    for k, tile in enumerate(tiles):
+        item, tq = divmod(tile, p.tiles_per_item)
+        d = torch.from_numpy(D[k]).reshape(fpt, 128, g.Ho1, g.P1)[:, :, :, :g.Wo1]
+        ref = y[item, :, fpt * tq:fpt * tq + fpt].permute(1, 0, 2, 3)
+        assert rel(d, ref) < 2e-6, (tile, rel(d, ref))
+        assert rel(d, conv_ref(xr, wr)[item, :, fpt * tq:fpt * tq + fpt].permute(1, 0, 2, 3)) < 1e-5
+
+
+@pytest.mark.parametrize('T,HW', [(8, 64), (8, 112)])
+def test_split_layer2_tables(T, HW):
+    g = em.Geo(T, HW)
+    B = 3
+    gen = torch.Generator().manual_seed(HW + 1)
+    x = torch.randn(B, 128, g.T2, g.H2, g.H2, generator=gen).abs()
+    w = torch.randn(128, 128, 3, 7, 7, generator=gen) * 0.02
+    xr, wr = em.f16x2_round(x), em.f16x2_round(w)
+    xh = em.from_f16_bits(em.split_f16(x)[0]); wh = em.from_f16_bits(em.split_f16(w)[0])
+    y = conv_ref(xh, wh) + conv_ref(xr - xh, wh) + conv_ref(xh, wr - wh)
+    a2 = em.pack_a2s(x, g, Bpad=4)
+    back, ok = em.unpack_a2s(a2, g, B)
+    assert ok and torch.equal(back, xr)
+    D, p = em.emulate_layer(8, a2, em.pack_w2s(w), T, HW, B, fmt='f16')
+    assert p.ncols == g.N2 and p.n_acc == 4 and p.n_tiles == 1 and p.n_steps == 18
+    d = torch.from_numpy(D[0]).reshape(4, 128, g.To2, g.Ho2, g.Wo2)
+    assert rel(d[:B], y) < 2e-6, rel(d[:B], y)
+    assert float(d[B:].abs().max()) == 0.0

@@ -11,6 +11,11 @@ def declare(lib):
         'vd_tc_pack_video_u8': (c_int, [P, P, P, POINTER(TcPlan), c_int, P, P, P]),
         'vd_tc_pack_weights': (c_int, [P, P, P, P, P, P, P]),
         'vd_tc_conv_layer': (c_int, [c_int, P, P, P, P, P, c_int, POINTER(TcPlan), P, c_int, c_int, P]),
+        'vd_tc_x3_sizes': (c_int, [POINTER(TcPlan), POINTER(c_int64)]),
+        'vd_tc_x3_pack_video': (c_int, [P, P, P, POINTER(TcPlan), c_int, P]),
+        'vd_tc_x3_pack_video_u8': (c_int, [P, P, P, POINTER(TcPlan), c_int, P, P, P]),
+        'vd_tc_x3_pack_weights': (c_int, [P, P, P, P, P, P, P]),
+        'vd_tc_x3_conv_layer': (c_int, [c_int, P, P, P, P, P, c_int, POINTER(TcPlan), P, c_int, P]),
         'vd_tc_pack_weights_bwd': (c_int, [P, P, P, P, P, P, P]),
         'vd_tc_bwd_emb': (c_int, [P, P, P, POINTER(TcPlan), c_int, P]),
         'vd_tc_bwd_gemm': (c_int, [c_int, P, P, P, POINTER(TcPlan), c_int, P]),

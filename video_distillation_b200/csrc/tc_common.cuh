@@ -1,6 +1,8 @@
 // sm_100a primitives used by the tensor-core path: mbarrier, bulk async copy (UBLKCP), TMEM
 // allocation, tcgen05.mma / commit / ld, UMMA descriptors.  Inline PTX only.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace vd {
@@ -95,6 +97,10 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t addr16, uint32_t lbo16, u
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
+// Same with fp16 A/B (format code 0): 11-bit significands — the split-fp16 forward (tc_layout.h: SGeo).
+__host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t M, uint32_t N) {
+    return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -161,6 +167,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ uint16_t f2bf(float f) { return __bfloat16_as_ushort(__float2bfloat16_rn(f)); }
+__device__ __forceinline__ uint16_t f2h(float f) { return __half_as_ushort(__float2half_rn(f)); }
+__device__ __forceinline__ float h2f(uint16_t h) { return __half2float(__ushort_as_half(h)); }
+// v = hi + lo with hi = fp16(v), lo = fp16(v - hi): 22 significand bits (values beyond the fp16 range saturate)
+__device__ __forceinline__ void split_h(float v, uint16_t& hi, uint16_t& lo) {
+    v = fminf(fmaxf(v, -65504.f), 65504.f);
+    hi = f2h(v);
+    lo = f2h(v - h2f(hi));
+}
 
 }  // namespace tc
 }  // namespace vd

@@ -20,11 +20,11 @@
 namespace vd {
 namespace tc {
 
-constexpr int kMaxSteps = 64;
+constexpr int kMaxSteps = 80;
 constexpr int kMaxCopies = 8;
 constexpr int kThreads = 256;
 
-enum EpiMode { EPI_RAW = 0, EPI_L0 = 1, EPI_L1 = 2, EPI_L2 = 3, EPI_PLAIN = 4, EPI_DG1 = 5, EPI_DG0 = 6 };
+enum EpiMode { EPI_RAW = 0, EPI_L0 = 1, EPI_L1 = 2, EPI_L2 = 3, EPI_PLAIN = 4, EPI_DG1 = 5, EPI_DG0 = 6, EPI_L0S = 7, EPI_L1S = 8 };
 
 struct EpiParams {
     float* raw;            // EPI_RAW: [tile][u][acc][128][ncols]
@@ -41,6 +41,7 @@ struct EpiParams {
     BwdGeo bb;             // EPI_DG1 (route mode): geometry of the packed dY operand of conv 0's column GEMM
     int T;                 // frames of the video
     int n_items;           // videos (conv 2: valid videos, tiles may be partially filled)
+    int r0s;               // EPI_L0S: output rows per column band (SGeo::R0s)
     Geo g;
 };
 
@@ -78,6 +79,7 @@ struct WsParams {
     uint32_t acc_delta16;               // B start offset between accumulators
     uint32_t ncols, acc_cols, acc_stages;
     uint32_t idesc;
+    uint32_t tab_bytes;                 // bytes of the descriptor tables behind the barrier block
     uint32_t smem_w_off, smem_pix_off;  // from the 1024-aligned dynamic smem base
     uint32_t smem_epi_off;              // != 0: 4 x 32 x 33 float transpose scratch for coalesced raw stores
     uint32_t smem_stash_off;            // != 0: conv-1 epilogue stash [H2*H2][kStashPitch] bf16 (quick accumulator drain)
@@ -87,6 +89,8 @@ struct WsParams {
                                         //   order, and every frame feeds the accumulators of the (up to) two frame pairs it
                                         //   touches through the 4 Toeplitz weight windows — half the L2->SM pixel traffic of the
                                         //   pair-by-pair order and no MMAs on the all-zero temporal halo frames
+    int32_t stream_mode;                // 0 / 1: stream_pairs as described above; 2: split-fp16 conv 0 (SGeo): stream_pairs = T
+                                        //   accumulators per column, stages (frame i, part), groups kt = 2, 1, 0 -> frame i + 1 - kt
     int32_t n_wsets;                    // resident weights: number of weight windows in the descriptor table (0: n_sa)
     int32_t dbg;                        // tuning experiments (VD_TC_DBG bitmask; results are garbage when set):
                                         //   1 no pixel copies, 2 no weight copies, 4 epilogue does no work,
@@ -98,14 +102,14 @@ struct WsParams {
 struct __align__(8) Barriers {
     uint64_t pix_full[4], pix_empty[4];
     uint64_t w_full[8], w_empty[8];
-    uint64_t acc_full[2], acc_empty[2];
+    uint64_t acc_full[4], acc_empty[4];
     uint64_t w_res;
     uint64_t baton[2];                  // MMA issuer hand-over (issuer r arrives on baton[r] after each of its groups)
     uint32_t tmem_base;
     uint32_t pad;
 };
-constexpr uint32_t kBarBytes = 4352;     // 256 B of barriers + 4 KiB of MMA descriptor tables
-static_assert(sizeof(Barriers) <= 256, "barrier block too large");
+constexpr uint32_t kBarBlock = 512;      // barrier block; the MMA descriptor tables follow (WsParams::tab_bytes)
+static_assert(sizeof(Barriers) <= kBarBlock, "barrier block too large");
 
 // ------------------------------------------------------------------------------------------
 // epilogues.  Thread `m` (0..127) owns TMEM lane m.  taddr = tmem base of the accumulator stage
@@ -311,6 +315,75 @@ __device__ __forceinline__ void epi_l0_store(const WsParams& p, int item, int tp
     }
 }
 
+// conv 0, split-fp16 operands (SGeo): accumulator = output frame f of the column (item, rb), columns q = r*Wo0 + wo for
+// the R0s rows of the band.  TMEM lane m = 32*q + l holds channel co = 16*q + (l & 15); lanes l < 16 accumulated wh*x,
+// lanes l >= 16 wl*x (x = xh + xl over the two stages of a frame): y = top + bottom, exchanged with shuffles inside the warp
+// (lane l keeps the columns it pools and sends the partner's).  bias + ReLU + MaxPool(1,2,2) on the fp32 sum -> fp16 hi / lo
+// stash [part][pooled position][channel] (+ routing codes for the synthetic videos).
+constexpr int kStash0sPitch = 72;         // fp16 elements per position row (64 + 8: conflict-free 16-byte reads)
+
+__device__ __forceinline__ void epi_l0s_drain(const WsParams& p, int item, int f, int rb, uint32_t taddr, int m, uint16_t* stash) {
+    const Geo& g = p.epi.g;
+    const int l = m & 31, hsel = l >> 4, co = (m >> 5) * 16 + (l & 15);
+    const float bias = __ldg(p.epi.bias + co);
+    const int R = p.epi.r0s, Wp = g.Wo0 / 2, npos = (R / 2) * Wp;
+    uint16_t* s_hi = stash + co;
+    uint16_t* s_lo = stash + npos * kStash0sPitch + co;
+    uint8_t* cbase = (p.epi.code && item >= p.epi.code_first)
+                         ? p.epi.code + (((int64_t)(item - p.epi.code_first) * 64 + co) * g.T + f) * g.H1 * g.H1 : nullptr;
+    for (int pr = 0; pr < R / 2; ++pr) {
+        const int hp = rb * (R / 2) + pr;
+        for (int wb = 0; wb < g.Wo0; wb += 8) {
+            float r0[8], r1[8];
+            tmem_ld8(taddr + (2 * pr) * g.Wo0 + wb, r0);
+            tmem_ld8(taddr + (2 * pr + 1) * g.Wo0 + wb, r1);
+            tmem_ld_wait();
+            float a0[4], a1[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float s0 = hsel ? r0[i] : r0[4 + i], s1 = hsel ? r1[i] : r1[4 + i];       // columns the partner pools
+                const float k0 = hsel ? r0[4 + i] : r0[i], k1 = hsel ? r1[4 + i] : r1[i];       // columns this lane pools
+                a0[i] = k0 + __shfl_xor_sync(0xffffffffu, s0, 16);
+                a1[i] = k1 + __shfl_xor_sync(0xffffffffu, s1, 16);
+            }
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+                // scan order (h,w): (0,0) (0,1) (1,0) (1,1); first maximum wins
+                float best = a0[2 * jj]; int arg = 0;
+                if (a0[2 * jj + 1] > best) { best = a0[2 * jj + 1]; arg = 1; }
+                if (a1[2 * jj] > best) { best = a1[2 * jj]; arg = 2; }
+                if (a1[2 * jj + 1] > best) { best = a1[2 * jj + 1]; arg = 3; }
+                best += bias;
+                const bool act = best > 0.f;
+                const int wp = wb / 2 + 2 * hsel + jj;
+                uint16_t hi, lo;
+                split_h(act ? best : 0.f, hi, lo);
+                s_hi[(pr * Wp + wp) * kStash0sPitch] = hi;
+                s_lo[(pr * Wp + wp) * kStash0sPitch] = lo;
+                if (cbase) cbase[hp * g.H1 + wp] = (uint8_t)(arg | (act ? 8 : 0));
+            }
+        }
+    }
+}
+
+// warp q owns channels 16q .. 16q+15 = chunks 2q, 2q+1 of A1s: (position, part, chunk) items -> one 16-byte store each
+__device__ __forceinline__ void epi_l0s_store(const WsParams& p, int item, int f, int rb, int q, int lane, const uint16_t* stash) {
+    const Geo& g = p.epi.g;
+    const int R = p.epi.r0s, Wp = g.Wo0 / 2, npos = (R / 2) * Wp;
+    uint8_t* fbase = p.epi.out + (int64_t)item * (8 * g.slice1) + (int64_t)(f + 1) * g.frame1;
+    for (int it = lane; it < 4 * npos; it += 32) {
+        const int sel = it / npos, pos = it - sel * npos;
+        const int part = sel >> 1, kk = sel & 1;
+        const int pr = pos / Wp, wp = pos - pr * Wp;
+        const int hp = rb * (R / 2) + pr;
+        const uint4 v = *reinterpret_cast<const uint4*>(stash + (part * npos + pos) * kStash0sPitch + q * 16 + kk * 8);
+        uint8_t* dst = fbase + (int64_t)(2 * q + kk) * g.slice1 +
+                       (int64_t)((part * 2 + coord_par(hp)) * 2 + coord_par(wp)) * g.plane1 +
+                       ((int64_t)coord_pos(hp) * g.P1 + coord_pos(wp)) * 16;
+        *reinterpret_cast<uint4*>(dst) = v;
+    }
+}
+
 // conv 1: accumulator a = frame 2*tp + a, lane = cout, columns q = ho*P1 + wo.
 // bias + ReLU + MaxPool(2,2,2) -> A2 chunks (bf16, every tap copy) [+ code (B,128,T2,H2,H2)]
 // Two phases so that the (single-buffered, 2 x 256 column) accumulator is released early:
@@ -383,6 +456,81 @@ __device__ __forceinline__ void epi_l1_store(const WsParams& p, int tile, int q,
                     const int wo = (wp + 3 - kw) / 2;
                     if (wp + 3 - kw < 0 || wo >= g.Wo2) continue;
                     *reinterpret_cast<uint4*>(cb + (int64_t)((kh * 7 + kw) * 2) * g.group2 + (ho * g.Wo2 + wo) * 16) = v;
+                }
+            }
+        }
+    }
+}
+
+// conv 1, split-fp16 operands: same tile as epi_l1_*; the pooled fp32 value is split into fp16 hi / lo (stash
+// [part][pooled frame][position][channel]) and both parts go to every tap copy of A2s
+// ([khw 49][quarter 4][part 2][k 4][t_pad][ho][wo] x 16 B).
+__device__ __forceinline__ void epi_l1s_drain(const WsParams& p, int tile, uint32_t taddr, int m, uint16_t* stash) {
+    const Geo& g = p.epi.g;
+    const int item = tile / p.tiles_per_item, tq = tile % p.tiles_per_item;
+    const int npair = p.n_acc >> 1;
+    const int npos = g.H2 * g.H2;
+    const float bias = __ldg(p.epi.bias + m);
+    for (int pp = 0; pp < npair; ++pp) {
+        const int tp = tq * npair + pp;
+        const uint32_t ta = taddr + (uint32_t)(2 * pp) * p.acc_cols;
+        uint16_t* st_hi = stash + pp * npos * kStashPitch;
+        uint16_t* st_lo = stash + (npair + pp) * npos * kStashPitch;
+        uint8_t* cbase = (p.epi.code && item >= p.epi.code_first)
+                             ? p.epi.code + (((int64_t)(item - p.epi.code_first) * 128 + m) * g.T2 + tp) * g.H2 * g.H2 : nullptr;
+        for (int hp = 0; hp < g.H2; ++hp) {
+            float a0[16], a1[16], b0[16], b1[16];
+            tmem_ld16(ta + (2 * hp) * g.P1, a0);
+            tmem_ld16(ta + (2 * hp + 1) * g.P1, a1);
+            tmem_ld16(ta + p.acc_cols + (2 * hp) * g.P1, b0);
+            tmem_ld16(ta + p.acc_cols + (2 * hp + 1) * g.P1, b1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int wp = 0; wp < 8; ++wp) {
+                if (wp < g.H2) {
+                    // scan order (t,h,w)
+                    float best = a0[2 * wp]; int arg = 0;
+                    if (a0[2 * wp + 1] > best) { best = a0[2 * wp + 1]; arg = 1; }
+                    if (a1[2 * wp] > best) { best = a1[2 * wp]; arg = 2; }
+                    if (a1[2 * wp + 1] > best) { best = a1[2 * wp + 1]; arg = 3; }
+                    if (b0[2 * wp] > best) { best = b0[2 * wp]; arg = 4; }
+                    if (b0[2 * wp + 1] > best) { best = b0[2 * wp + 1]; arg = 5; }
+                    if (b1[2 * wp] > best) { best = b1[2 * wp]; arg = 6; }
+                    if (b1[2 * wp + 1] > best) { best = b1[2 * wp + 1]; arg = 7; }
+                    best += bias;
+                    const bool act = best > 0.f;
+                    uint16_t hi, lo;
+                    split_h(act ? best : 0.f, hi, lo);
+                    st_hi[(hp * g.H2 + wp) * kStashPitch + m] = hi;
+                    st_lo[(hp * g.H2 + wp) * kStashPitch + m] = lo;
+                    if (cbase) cbase[hp * g.H2 + wp] = (uint8_t)(arg | (act ? 8 : 0));
+                }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void epi_l1s_store(const WsParams& p, int tile, int q, int lane, const uint16_t* stash) {
+    const Geo& g = p.epi.g;
+    const int item = tile / p.tiles_per_item, tq = tile % p.tiles_per_item;
+    const int npair = p.n_acc >> 1;
+    const int npos = g.H2 * g.H2;
+    for (int pp = 0; pp < npair; ++pp) {
+        const int tp = tq * npair + pp;
+        uint8_t* vbase = p.epi.out + (int64_t)item * (196 * g.group2) + (int64_t)q * g.group2 + (int64_t)(tp + 1) * g.HW2 * 16;
+        for (int i = lane; i < 8 * npos; i += 32) {
+            const int sel = i / npos, pos = i - sel * npos;
+            const int part = sel >> 2, kk = sel & 3;                 // warp q = quarter q, chunk kk of the quarter
+            const int hp = pos / g.H2, wp = pos - hp * g.H2;
+            const uint4 v = *reinterpret_cast<const uint4*>(stash + ((part * npair + pp) * npos + pos) * kStashPitch + q * 32 + kk * 8);
+            uint8_t* cb = vbase + (int64_t)(part * 4 + kk) * g.chunk2;
+            for (int kh = (hp + 1) & 1; kh < 7; kh += 2) {
+                const int ho = (hp + 3 - kh) / 2;
+                if (hp + 3 - kh < 0 || ho >= g.Ho2) continue;
+                for (int kw = (wp + 1) & 1; kw < 7; kw += 2) {
+                    const int wo = (wp + 3 - kw) / 2;
+                    if (wp + 3 - kw < 0 || wo >= g.Wo2) continue;
+                    *reinterpret_cast<uint4*>(cb + (int64_t)((kh * 7 + kw) * 4) * g.group2 + (ho * g.Wo2 + wo) * 16) = v;
                 }
             }
         }
@@ -605,7 +753,8 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
     if (threadIdx.x == 0) {
         for (int i = 0; i < 4; ++i) { mbar_init(BAR(pix_full, i), 1); mbar_init(BAR(pix_empty, i), 2); }     // empty: one commit per issuer
         for (int i = 0; i < 8; ++i) { mbar_init(BAR(w_full, i), 1); mbar_init(BAR(w_empty, i), 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(BAR(acc_full, i), 2); mbar_init(BAR(acc_empty, i), 4); mbar_init(BAR(baton, i), 1); }
+        for (int i = 0; i < 4; ++i) { mbar_init(BAR(acc_full, i), 2); mbar_init(BAR(acc_empty, i), 4); }
+        for (int i = 0; i < 2; ++i) mbar_init(BAR(baton, i), 1);
         mbar_init(BAR(w_res, 0), 1);
         fence_mbar_init();
     }
@@ -701,7 +850,7 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
         const uint32_t b_hi = p.b_hi ? p.b_hi : (8u | (1u << 14));
         const uint32_t a_lbo_bits = (p.a_lbo16 & 0x3FFFu) << 16;
         const uint32_t slot_bytes = (uint32_t)G * kWeightTileBytes;
-        uint64_t* tabB = reinterpret_cast<uint64_t*>(base_ptr + 256);                   // [RP][n_steps][NACC]
+        uint64_t* tabB = reinterpret_cast<uint64_t*>(base_ptr + kBarBlock);                   // [RP][n_steps][NACC]
         uint64_t* tabA = tabB + p.RP * n_steps * NACC;                                  // [RW][G] or [n_sa][n_steps]
         const int t64 = role * 32 + lane;
         for (int i = t64; i < p.RP * n_steps * NACC; i += 64) {
@@ -799,13 +948,48 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
                 if (++fi < 2 * pairs) return;
                 fi = 0; qbase += (uint32_t)pairs; tile += gridDim.x;
             };
+            // conv 0, split-fp16 operands (SGeo, tc_layout.h): stage s = (input frame i = s >> 1, part = s & 1); the stage feeds
+            // output frames f = i + 1 - kt through the weight window kt = 2, 1, 0 (where f exists).  Frame f (running count
+            // qbase + f over the columns of this CTA) lives in accumulator buffer (qbase + f) & 3; its first write is
+            // (i = f - 1, hi part, kt = 0) — for f = 0: (i = 0, hi, kt = 1) — and its last (i = f + 1, lo part, kt = 2) — for
+            // f = T - 1: (i = T - 1, lo, kt = 1).
+            const int smode = p.stream_mode;
+            int ss = 0, sgi = 0;
+            auto next_l0s = [&](Group& r) {
+                const int T = pairs;
+                const int i = ss >> 1, part = ss & 1;
+                const int kt = (i >= 1 ? 2 : 1) - sgi;
+                const int f = i + 1 - kt;
+                const int ngroups = (i >= 1 ? 1 : 0) + 1 + (i + 1 < T ? 1 : 0);
+                const bool last_of_stage = sgi == ngroups - 1;
+                const uint32_t q = qbase + (uint32_t)f;
+                const uint32_t buf = q & 3u;
+                const bool first_write = part == 0 && (kt == 0 || (f == 0 && kt == 1));
+                const bool final_write = part == 1 && (kt == 2 || (f == T - 1 && kt == 1));
+                r.w_acc = first_write ? BAR(acc_empty, buf) : 0u;        r.p_acc = ((q >> 2) & 1u) ^ 1u;
+                r.w_pix = BAR(pix_full, pslot);                          r.p_pix = pphase;
+                r.w_w = 0u;                                              r.p_w = 0u;
+                r.nst = n_steps;
+                r.ta = tabA + kt * n_steps;
+                r.tb = tabB + (int)pslot * n_steps * NACC;
+                r.d_base = tmem_base + buf * (acc_cols * (uint32_t)NACC);
+                r.acc0 = first_write ? 0u : 1u;
+                r.c_w = 0u;
+                r.c_pix = last_of_stage ? BAR(pix_empty, pslot) : 0u;
+                r.c_acc = final_write ? BAR(acc_full, buf) : 0u;
+                if (!last_of_stage) { ++sgi; return; }
+                sgi = 0;
+                if (++pslot == RP) { pslot = 0; pphase ^= 1; }
+                if (++ss < 2 * T) return;
+                ss = 0; qbase += (uint32_t)T; tile += gridDim.x;
+            };
             long long c_acc = 0, c_pix = 0, c_w = 0, c_baton = 0, c_issue = 0;
             const bool prof = p.prof != nullptr;
             if (RESIDENT) { mbar_wait(BAR(w_res, 0), 0); tc_fence_after(); }
             const long long c_begin = clock64();
             Group r;
             for (uint32_t k = 0; tile < n_tiles; ++k) {
-                if (pairs) next_stream(r); else next(r);
+                if (smode == 2) next_l0s(r); else if (pairs) next_stream(r); else next(r);
                 if ((k & 1u) == (uint32_t)role) {
                     // ---- my group: operands (usually long there), then the baton of the previous group's issuer
                     long long t0 = prof ? clock64() : 0;
@@ -873,6 +1057,8 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
                         if (p.smem_stash_off) epi_l0_drain(p, item, tp, rb, taddr, m, reinterpret_cast<uint16_t*>(base_ptr + p.smem_stash_off));
                         else epi_l0(p, item, tp, rb, taddr, m);
                     }
+                    else if (EPI == EPI_L0S) epi_l0s_drain(p, tile / p.tiles_per_item, u, tile % p.tiles_per_item, taddr, m, reinterpret_cast<uint16_t*>(base_ptr + p.smem_stash_off));
+                    else if (EPI == EPI_L1S) epi_l1s_drain(p, tile, taddr, m, reinterpret_cast<uint16_t*>(base_ptr + p.smem_stash_off));
                     else if (EPI == EPI_L1) epi_l1_drain(p, tile, taddr, m, reinterpret_cast<uint16_t*>(base_ptr + p.smem_stash_off));
                     else if (EPI == EPI_PLAIN) epi_plain(p, tile, taddr, m);
                     else if (EPI == EPI_DG1) epi_dg1(p, tile, taddr, m);
@@ -886,6 +1072,14 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
                     // the accumulator is free again: scatter the stashed tile while the next one is computed
                     epi_l1_store(p, tile, q, lane, reinterpret_cast<const uint16_t*>(base_ptr + p.smem_stash_off));
                     __syncwarp();       // the stash rows of this warp are rewritten by the next drain
+                }
+                if (EPI == EPI_L1S && work) {
+                    epi_l1s_store(p, tile, q, lane, reinterpret_cast<const uint16_t*>(base_ptr + p.smem_stash_off));
+                    __syncwarp();
+                }
+                if (EPI == EPI_L0S && work) {
+                    epi_l0s_store(p, tile / p.tiles_per_item, u, tile % p.tiles_per_item, q, lane, reinterpret_cast<const uint16_t*>(base_ptr + p.smem_stash_off));
+                    __syncwarp();
                 }
                 if (EPI == EPI_L0 && work && p.smem_stash_off) {
                     const int item = tile / p.tiles_per_item, sub = tile % p.tiles_per_item;
@@ -928,8 +1122,15 @@ static int finalize_smem(WsParams& p, uint32_t w_region, uint32_t* smem_total, b
             p.step_tab[j].y = p.b_off16[j] | ((p.b_lbo16[j] & 0x3FFFu) << 16);
         }
     }
-    p.smem_w_off = kBarBytes;
-    p.smem_pix_off = align_up(kBarBytes + w_region, 128);
+    {
+        const int G = p.w_resident ? p.n_steps : p.G;
+        const uint32_t nB = (uint32_t)p.RP * p.n_steps * p.n_acc;
+        const uint32_t nA = p.w_resident ? (uint32_t)(p.n_wsets ? p.n_wsets : p.n_sa) * p.n_steps : (uint32_t)p.RW * G;
+        p.tab_bytes = align_up((nB + nA) * 8, 128);
+        if (p.tab_bytes < 3840) p.tab_bytes = 3840;     // (the r01 carve-up: 4352 bytes ahead of the weights)
+    }
+    p.smem_w_off = kBarBlock + p.tab_bytes;
+    p.smem_pix_off = align_up(p.smem_w_off + w_region, 128);
     p.stage_pitch = align_up(p.stage_bytes + 16, 128);
     uint32_t total = p.smem_pix_off + (uint32_t)p.RP * p.stage_pitch;
     p.smem_epi_off = 0;
@@ -1043,6 +1244,122 @@ static int setup_l2(WsParams& p, const Geo& g, int B, uint32_t* smem) {
     return finalize_smem(p, (uint32_t)p.G * p.RW * kWeightTileBytes, smem);
 }
 
+// ---- split-fp16 forward (SGeo, tc_layout.h) ----
+// conv 0: column tiles (video, band of R0s rows); stages (frame i, part) of the X0s operand; resident M-stacked weight
+// image [kt 3][step 11] x 4 KiB; 4 accumulators of 128 columns (output frames f & 3).
+static int setup_l0s(WsParams& p, const Geo& g, int B, uint32_t* smem) {
+    const SGeo sg = make_sgeo(g);
+    p.n_u = 1; p.nu_total = 1; p.ug_count = 1; p.w_u_stride = 0;
+    p.n_tiles = B * sg.nrb0s; p.tiles_per_item = sg.nrb0s; p.v_count = sg.nrb0s;
+    p.item_stride = sg.video0s; p.u_stride = 0; p.v_stride = (int64_t)sg.R0s * g.Wo0 * 16;
+    p.n_sa = g.T; p.n_sb = 2; p.sa_stride = sg.frame0s; p.sb_stride = 6 * g.plane0;
+    p.n_copies = 6;
+    uint32_t sofs = 0;
+    uint32_t blk[3][2];
+    for (int c = 0; c < 3; ++c)
+        for (int par = 0; par < 2; ++par) {
+            const int i = c * 2 + par;
+            p.copy_gofs[i] = sg.frame0s + (int64_t)i * g.plane0;        // frame i of the video is t_pad = i + 1
+            p.copy_sofs[i] = sofs;
+            p.copy_bytes[i] = (uint32_t)(sg.R0s + 2 + par) * g.Wo0 * 16;
+            blk[c][par] = sofs;
+            sofs += p.copy_bytes[i];
+        }
+    p.stage_bytes = sofs;
+    p.n_steps = kW0Steps;
+    for (int s = 0; s < kW0Steps; ++s) {
+        const int c0 = 2 * s, c1 = (2 * s + 1 < 21) ? 2 * s + 1 : 2 * s;    // last step: 2nd half has zero weights
+        auto off = [&](int ch) { int c = ch / 7, kh = l0_chunk_kh(ch % 7); return blk[c][tap_par(kh)] + (uint32_t)tap_shift(kh) * g.Wo0 * 16; };
+        const uint32_t o0 = off(c0), o1 = off(c1);
+        if (o1 < o0) return -2;
+        p.b_off16[s] = o0 >> 4; p.b_lbo16[s] = (o1 - o0) >> 4;
+        p.a_off16[s] = (uint32_t)(s * kWeightTileBytes) >> 4;
+    }
+    p.a_sa_stride16 = (kW0Steps * kWeightTileBytes) >> 4;
+    p.a_lbo16 = 2048 >> 4; p.a_sbo16 = 8;
+    p.w_resident = 1; p.w_bytes = (uint32_t)sg.w0s_bytes;
+    p.n_wsets = 3;
+    p.G = 1; p.RW = 1; p.RP = env_int("VD_TC_L0S_RP", 3);
+    p.n_acc = 1; p.acc_delta16 = 0;
+    p.ncols = sg.N0s; p.acc_cols = 128; p.acc_stages = 4;
+    p.idesc = umma_idesc_f16(128, sg.N0s);
+    p.stream_pairs = g.T; p.stream_mode = 2;
+    const uint32_t npos = (uint32_t)(sg.R0s / 2) * (g.Wo0 / 2);
+    return finalize_smem(p, (uint32_t)sg.w0s_bytes, smem, false, 2 * npos * kStash0sPitch * 2);
+}
+
+// conv 1: the tile / stage geometry of setup_l1 with 8-channel chunks carrying both parts; 74 steps per stage
+static int setup_l1s(WsParams& p, const Geo& g, int B, uint32_t* smem) {
+    p.n_u = 1; p.nu_total = 1; p.ug_count = 1; p.w_u_stride = 0;
+    const bool nacc4 = g.N1 <= 128 && g.T % 4 == 0;
+    const int fpt = nacc4 ? 4 : 2;                                      // output frames per tile
+    p.n_tiles = B * (g.T / fpt);
+    p.tiles_per_item = g.T / fpt; p.v_count = 1;
+    p.item_stride = 8 * g.slice1; p.u_stride = (int64_t)fpt * g.frame1; p.v_stride = 0;
+    p.n_sa = 3; p.n_sb = 8; p.sa_stride = g.frame1; p.sb_stride = g.slice1;
+    p.n_copies = 1; p.copy_gofs[0] = 0; p.copy_sofs[0] = 0; p.copy_bytes[0] = (uint32_t)(fpt * g.frame1);
+    p.stage_bytes = (uint32_t)(fpt * g.frame1);
+    p.n_steps = kSteps1s;
+    uint32_t off[49];
+    for (int i = 0; i < 49; ++i) {
+        const int tap = l1s_tap(i), kh = tap / 7, kw = tap % 7;
+        const int plane = tap_par(kh) * 2 + tap_par(kw);                // hi part: planes 0..3, lo part: 4..7
+        off[i] = (uint32_t)plane * (uint32_t)g.plane1 + (uint32_t)(tap_shift(kh) * g.P1 + tap_shift(kw)) * 16;
+        if (i && off[i] <= off[i - 1]) return -2;
+        p.b_off16[i] = off[i] >> 4;
+        p.b_lbo16[i] = (uint32_t)(4 * g.plane1) >> 4;
+    }
+    for (int pr = 0; pr < 25; ++pr) {
+        const int a = 2 * pr, b = 2 * pr + 1;
+        p.b_off16[49 + pr] = off[a] >> 4;
+        p.b_lbo16[49 + pr] = (b < 49) ? (off[b] - off[a]) >> 4 : (uint32_t)g.plane1 >> 4;     // last: zero weights in the 2nd half
+    }
+    p.a_lbo16 = 2048 >> 4; p.a_sbo16 = 8;
+    p.w_resident = 0; p.w_bytes = 0;
+    p.G = env_int("VD_TC_L1S_G", 4); p.RW = env_int("VD_TC_L1S_RW", 3); p.RP = 2;
+    p.n_acc = fpt; p.acc_delta16 = (uint32_t)g.frame1 >> 4;
+    p.ncols = g.N1; p.acc_cols = nacc4 ? 128 : 256; p.acc_stages = 1;
+    p.idesc = umma_idesc_f16(128, g.N1);
+    return finalize_smem(p, (uint32_t)p.G * p.RW * kWeightTileBytes, smem, false, (uint32_t)(2 * (fpt / 2) * g.H2 * g.H2) * kStashPitch * 2);
+}
+
+// conv 2: the tile / stage geometry of setup_l2 with 32-channel quarters carrying both parts; 18 steps per stage
+static int setup_l2s(WsParams& p, const Geo& g, int B, uint32_t* smem) {
+    p.n_u = 1; p.nu_total = 1; p.ug_count = 1; p.w_u_stride = 0;
+    const int VPT = kVideosPerTile2;
+    const SGeo sg = make_sgeo(g);
+    p.n_tiles = (B + VPT - 1) / VPT;
+    p.tiles_per_item = 1; p.v_count = 1;
+    p.item_stride = VPT * sg.video2s; p.u_stride = 0; p.v_stride = 0;
+    p.n_sa = 49; p.n_sb = 4; p.sa_stride = 4 * g.group2; p.sb_stride = g.group2;
+    p.n_copies = VPT;
+    for (int v = 0; v < VPT; ++v) {
+        p.copy_gofs[v] = (int64_t)v * sg.video2s;
+        p.copy_sofs[v] = (uint32_t)(v * g.group2);
+        p.copy_bytes[v] = (uint32_t)g.group2;
+    }
+    p.stage_bytes = (uint32_t)(VPT * g.group2);
+    p.n_steps = kSteps2s;
+    for (int kt = 0; kt < 3; ++kt) {
+        const uint32_t tofs = (uint32_t)((int64_t)kt * g.HW2 * 16);
+        for (int c = 0; c < 4; ++c) {                                   // [xh_c | xl_c] . [wh_c | wh_c]
+            p.b_off16[kt * 6 + c] = (uint32_t)(c * g.chunk2 + tofs) >> 4;
+            p.b_lbo16[kt * 6 + c] = (uint32_t)(4 * g.chunk2) >> 4;
+        }
+        for (int pr = 0; pr < 2; ++pr) {                                // [xh_c | xh_c+1] . [wl_c | wl_c+1]
+            p.b_off16[kt * 6 + 4 + pr] = (uint32_t)(2 * pr * g.chunk2 + tofs) >> 4;
+            p.b_lbo16[kt * 6 + 4 + pr] = (uint32_t)g.chunk2 >> 4;
+        }
+    }
+    p.a_lbo16 = 2048 >> 4; p.a_sbo16 = 8;
+    p.w_resident = 0; p.w_bytes = 0;
+    p.G = env_int("VD_TC_L2S_G", 6); p.RW = env_int("VD_TC_L2S_RW", 2); p.RP = 2;
+    p.n_acc = VPT; p.acc_delta16 = (uint32_t)g.group2 >> 4;
+    p.ncols = g.N2; p.acc_cols = 128; p.acc_stages = 1;
+    p.idesc = umma_idesc_f16(128, g.N2);
+    return finalize_smem(p, (uint32_t)p.G * p.RW * kWeightTileBytes, smem);
+}
+
 static int setup_bwd(WsParams& p, const Geo& g, int layer, int B, uint32_t* smem, bool fp32_out = false) {
     const BwdGeo b = make_bwd_geo(g, layer);
     VD_REQUIRE(b.pixels % 16 == 0, "tc bwd: pixel count must be a multiple of 16");
@@ -1097,6 +1414,12 @@ static int launch(const WsParams& p, uint32_t smem, cudaStream_t stream) {
         return launch_n<EPI_L1, 2>(p, smem, stream);
     } else if (EPI == EPI_L1 && p.n_acc == 4) {
         return launch_n<EPI_L1, 4>(p, smem, stream);
+    } else if (EPI == EPI_L0S && p.n_acc == 1) {
+        return launch_n<EPI_L0S, 1>(p, smem, stream);
+    } else if (EPI == EPI_L1S && p.n_acc == 2) {
+        return launch_n<EPI_L1S, 2>(p, smem, stream);
+    } else if (EPI == EPI_L1S && p.n_acc == 4) {
+        return launch_n<EPI_L1S, 4>(p, smem, stream);
     } else if (EPI == EPI_L2 && p.n_acc == 4) {
         return launch_n<EPI_L2, 4>(p, smem, stream);
     } else if (EPI == EPI_DG1 && p.n_acc == 1) {
@@ -1201,17 +1524,53 @@ extern "C" int vd_tc_conv_layer(int layer, const void* in, const void* wimg, con
     return launch<EPI_L2>(p, smem, s);
 }
 
+// ---- split-fp16 forward (SGeo): the same three fused layers on fp16 hi / lo operand pairs ----
+extern "C" int vd_tc_x3_sizes(const vd_tc_plan* plan, int64_t* out) {
+    VD_REQUIRE(plan && out && geo_supported(plan->T, plan->H), "tc_x3_sizes: bad argument");
+    const Geo g = make_geo(plan->T, plan->H);
+    const SGeo sg = make_sgeo(g);
+    out[0] = sg.video0s; out[1] = sg.video1s; out[2] = sg.video2s;
+    out[3] = sg.w0s_bytes; out[4] = sg.w1s_bytes; out[5] = sg.w2s_bytes;
+    return 0;
+}
+
+extern "C" int vd_tc_x3_conv_layer(int layer, const void* in, const void* wimg, const float* bias, void* out,
+                                   uint8_t* code, int code_first_item, const vd_tc_plan* plan, const int64_t* item_index,
+                                   int B, void* stream) {
+    VD_REQUIRE(plan && in && wimg && out && bias, "tc_x3_conv_layer: NULL pointer");
+    VD_REQUIRE(layer >= 0 && layer <= 2, "tc_x3_conv_layer: layer must be 0, 1 or 2");
+    VD_REQUIRE(B >= 0 && code_first_item >= 0, "tc_x3_conv_layer: negative batch / code_first_item");
+    VD_REQUIRE(geo_supported(plan->T, plan->H), "tc_x3_conv_layer: unsupported geometry");
+    VD_REQUIRE(item_index == nullptr || layer == 0, "tc_x3_conv_layer: item_index is only valid for layer 0");
+    if (B == 0) return 0;
+    WsParams p;
+    memset(&p, 0, sizeof(p));
+    const Geo g = make_geo(plan->T, plan->H);
+    uint32_t smem = 0;
+    int rc = layer == 0 ? setup_l0s(p, g, B, &smem) : layer == 1 ? setup_l1s(p, g, B, &smem) : setup_l2s(p, g, B, &smem);
+    if (rc) { if (rc == -2) set_error("tc x3 conv %d: non-monotone window offsets", layer); return rc; }
+    p.pix = (const uint8_t*)in; p.wimg = (const uint8_t*)wimg; p.item_index = item_index;
+    p.prof = g_prof; p.dbg = env_int("VD_TC_DBG", 0);
+    p.epi.bias = bias; p.epi.out = (uint8_t*)out; p.epi.code = code; p.epi.code_first = code_first_item; p.epi.raw = (float*)out;
+    p.epi.T = plan->T; p.epi.n_items = B; p.epi.g = g; p.epi.layer = layer; p.epi.r0s = make_sgeo(g).R0s;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (layer == 0) return launch<EPI_L0S>(p, smem, s);
+    if (layer == 1) return launch<EPI_L1S>(p, smem, s);
+    return launch<EPI_L2>(p, smem, s);
+}
+
 // Host-side introspection for the CPU emulator in tests/ (no GPU work): dumps the exact kernel
 // parameters that vd_tc_conv_layer would launch with.
 extern "C" int vd_tc_debug_params(int layer, const vd_tc_plan* plan, int B, int64_t* out, int cap) {
     VD_REQUIRE(plan && out && cap >= 33 + 3 * kMaxCopies + 3 * kMaxSteps, "tc_debug_params: buffer too small");
-    VD_REQUIRE(layer >= 0 && layer <= 5 && geo_supported(plan->T, plan->H), "tc_debug_params: bad layer / geometry");
+    VD_REQUIRE(layer >= 0 && layer <= 8 && geo_supported(plan->T, plan->H), "tc_debug_params: bad layer / geometry");
     WsParams p;
     memset(&p, 0, sizeof(p));
     const Geo g = make_geo(plan->T, plan->H);
     uint32_t smem = 0;
     int rc = layer == 0 ? setup_l0(p, g, B, &smem) : layer == 1 ? setup_l1(p, g, B, &smem) : layer == 2 ? setup_l2(p, g, B, &smem)
-                        : setup_bwd(p, g, layer - 3, B, &smem);
+                        : layer == 6 ? setup_l0s(p, g, B, &smem) : layer == 7 ? setup_l1s(p, g, B, &smem)
+                        : layer == 8 ? setup_l2s(p, g, B, &smem) : setup_bwd(p, g, layer - 3, B, &smem);
     if (rc) return rc;
     int i = 0;
     out[i++] = p.n_tiles; out[i++] = p.tiles_per_item; out[i++] = p.v_count;

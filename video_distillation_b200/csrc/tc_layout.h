@@ -190,6 +190,65 @@ inline Dg0Geo make_dg0_geo(const Geo& g) {
     return d;
 }
 
+// ---- split-fp16 forward ("x3"): every operand value v is carried as an fp16 pair v = hi + lo (hi = fp16(v),
+//   lo = fp16(v - hi): 22 mantissa bits) and every product x*w is evaluated as xh*wh + xl*wh + xh*wl (+ xl*wl in conv 0)
+//   into the SAME fp32 TMEM accumulator, so ReLU / pool-argmax are decided on fp32-equivalent sums.
+//   The hi / lo parts are extra K-chunks of the same shifted-window GEMM — only layouts and step tables change:
+//
+// X0s (input of conv 0): [t_pad T+2][part 2][c 3][par 2][row RI0][wo Wo0] x 16 B (8 fp16 = the kw window, as X0).
+//   conv 0 is "M-stacked": weight-tile row r = 32*q + l holds channel co = 16*q + (l & 15), hi part for l < 16 and lo
+//   part for l >= 16, so ONE 4 KiB tile per (kt, K-step) carries wh and wl and the accumulator rows of a channel are
+//   top = sum wh*x, bottom = sum wl*x; the epilogue adds the two rows (same warp, lanes l and l ^ 16).  A tile is a
+//   column (video, band of R0s output rows, N = R0s*Wo0 <= 128); its T input frames are streamed once each as two
+//   stages (hi part, lo part) and frame i feeds output frames i-1, i, i+1 (kt = 2, 1, 0) held in 4 x 128 TMEM columns.
+//
+// A1s (input of conv 1): [chunk 8 (8 ch)][t_pad T+2][part 2][ph 2][pw 2][i RI1][j P1] x 16 B — the A1 layout with the
+//   16-channel slice replaced by an 8-channel chunk carrying both parts (same bytes per stage).  Per stage (kt, chunk):
+//     steps 0..48   tap idx (smem-offset order, l1s_tap): B = [xh_tap | xl_tap] (LBO = 4 planes), A = [wh_tap | wh_tap]
+//     steps 49..73  tap pairs (2p, 2p+1):                 B = [xh_a | xh_b]  (LBO = window distance), A = [wl_a | wl_b]
+//
+// A2s (input of conv 2): [khw 49][quarter 4][part 2][k 4 (8 ch)][t_pad To2+2][ho][wo] x 16 B.  Per stage (khw, quarter),
+//   for kt = 0..2: steps c = 0..3: B = [xh_c | xl_c], A = [wh_c | wh_c]; steps (0,1), (2,3): B = [xh_c | xh_c'], A = [wl_c | wl_c'].
+struct SGeo {
+    int R0s, N0s, nrb0s;                // conv 0: output rows per column band, accumulator columns, bands per frame
+    int stage0s;                        // bytes of one (frame, part) stage
+    int64_t frame0s, video0s;           // X0s bytes
+    int64_t video1s, video2s;           // A1s / A2s bytes per video
+    int64_t w0s_bytes, w1s_bytes, w2s_bytes;
+};
+constexpr int kSteps1s = 74;                // 49 + 25
+constexpr int kSteps2s = 18;                // 3 kt x (4 + 2)
+
+inline SGeo make_sgeo(const Geo& g) {
+    SGeo s{};
+    s.R0s = (g.Wo0 * 4 <= 128) ? 4 : 2;
+    s.N0s = s.R0s * g.Wo0;
+    s.nrb0s = g.Ho0 / s.R0s;
+    s.stage0s = 3 * (2 * s.R0s + 5) * g.Wo0 * 16;
+    s.frame0s = 12 * g.plane0;
+    s.video0s = (int64_t)(g.T + 2) * s.frame0s;
+    s.video1s = 8 * g.slice1;
+    s.video2s = 196 * g.group2;
+    s.w0s_bytes = (int64_t)3 * 11 * 4096;
+    s.w1s_bytes = (int64_t)3 * 8 * kSteps1s * 4096;
+    s.w2s_bytes = (int64_t)49 * 4 * kSteps2s * 4096;
+    return s;
+}
+
+// conv 1 taps in the order of their window offsets inside a stage: planes (ph,pw) = (0,0) (0,1) (1,0) (1,1), then row
+// shift, then column shift.  Returns kh*7 + kw.
+__host__ __device__ inline int l1s_tap(int idx) {
+    int ph, pw, r;
+    if (idx < 9) { ph = 0; pw = 0; r = idx; }
+    else if (idx < 21) { ph = 0; pw = 1; r = idx - 9; }
+    else if (idx < 33) { ph = 1; pw = 0; r = idx - 21; }
+    else { ph = 1; pw = 1; r = idx - 33; }
+    const int nw = pw ? 4 : 3;
+    const int sh = r / nw, sw = r - sh * nw;
+    const int kh = ph ? 2 * sh : 2 * sh + 1, kw = pw ? 2 * sw : 2 * sw + 1;
+    return kh * 7 + kw;
+}
+
 constexpr int kWeightTileBytes = 4096;      // [k 2][128 rows][16 B]
 constexpr int kVideosPerTile2 = 4;          // conv 2: accumulators (videos) per CTA tile
 constexpr int kW0Steps = 11;                // conv 0: 21 (c,kh) chunks paired into K=16 steps

@@ -146,6 +146,120 @@ __global__ void pack_w2_kernel(const float* __restrict__ w, uint16_t* __restrict
     }
 }
 
+// ---- split-fp16 forward operands (SGeo, tc_layout.h) ----
+// X0s (B, T+2, part 2, 3, 2, RI0, Wo0) chunks of 8 fp16: part 0 = fp16(v), part 1 = fp16(v - part 0).  One block per
+// (video, padded frame, part, channel, row parity) plane.  U8: uint8 frames with the dataset normalisation fused in.
+template <bool U8>
+__global__ void __launch_bounds__(256) pack_video_x3_kernel(const void* __restrict__ video, const int64_t* __restrict__ index,
+                                                            uint4* __restrict__ x0, int T, int HW, int RI0, int Wo0, NormU8 nm) {
+    int q = blockIdx.x;
+    const int par = q & 1; q >>= 1;
+    const int c = q % 3; q /= 3;
+    const int part = q & 1; q >>= 1;
+    const int tp = q % (T + 2);
+    const int64_t b = q / (T + 2);
+    const int t = tp - 1;
+    uint4* dst = x0 + (int64_t)blockIdx.x * RI0 * Wo0;
+    const int n = RI0 * Wo0;
+    if (t < 0 || t >= T) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = make_uint4(0u, 0u, 0u, 0u);
+        return;
+    }
+    const int64_t src = index ? index[b] : b;
+    const int64_t plane = ((src * T + t) * 3 + c) * HW * (int64_t)HW;
+    const float mean = nm.mean[c], stdv = nm.stdv[c];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int row = i / Wo0, wo = i - row * Wo0;
+        const int h = par ? 2 * row - 3 : 2 * row - 2;
+        uint16_t v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = 0;
+        if (h >= 0 && h < HW) {
+#pragma unroll
+            for (int k = 0; k < 7; ++k) {
+                const int w = 2 * wo + k - 3;
+                if (w >= 0 && w < HW) {
+                    float x;
+                    if (U8) x = __fdiv_rn(__fsub_rn(__fdiv_rn((float)__ldg((const uint8_t*)video + plane + (int64_t)h * HW + w), 255.f), mean), stdv);
+                    else x = __ldg((const float*)video + plane + (int64_t)h * HW + w);
+                    uint16_t hi, lo;
+                    split_h(x, hi, lo);
+                    v[k] = part ? lo : hi;
+                }
+            }
+        }
+        uint4 o;
+        o.x = v[0] | ((uint32_t)v[1] << 16); o.y = v[2] | ((uint32_t)v[3] << 16);
+        o.z = v[4] | ((uint32_t)v[5] << 16); o.w = v[6] | ((uint32_t)v[7] << 16);
+        dst[i] = o;
+    }
+}
+
+__device__ __forceinline__ uint16_t h_part(float v, int part) {
+    uint16_t hi, lo;
+    split_h(v, hi, lo);
+    return part ? lo : hi;
+}
+
+// conv 0 image (M-stacked): [kt 3][step 11][k 2][row 128][8]; row r = 32*q + l -> channel 16*q + (l & 15), part l >> 4
+__global__ void pack_w0s_kernel(const float* __restrict__ w, uint16_t* __restrict__ img) {
+    const int total = 3 * kW0Steps * kWeightTileBytes / 2;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int e = i % 8; int q = i / 8;
+        int row = q % 128; q /= 128;
+        int k = q % 2; q /= 2;
+        int step = q % kW0Steps; int kt = q / kW0Steps;
+        const int ch = 2 * step + k;
+        const int co = (row >> 5) * 16 + (row & 15), part = (row >> 4) & 1;
+        uint16_t v = 0;
+        if (ch < 21 && e < 7) {
+            const int c = ch / 7, kh = l0_chunk_kh(ch % 7);
+            v = h_part(w[(((co * 3 + c) * 3 + kt) * 7 + kh) * 7 + e], part);
+        }
+        img[i] = v;
+    }
+}
+
+// conv 1 image: [kt 3][chunk 8][step 74][k 2][128][8]; steps 0..48: hi weights of tap l1s_tap(step) in both K halves;
+// steps 49..73: lo weights of taps l1s_tap(2p), l1s_tap(2p+1)
+__global__ void pack_w1s_kernel(const float* __restrict__ w, uint16_t* __restrict__ img) {
+    const int total = 3 * 8 * kSteps1s * kWeightTileBytes / 2;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int e = i % 8; int q = i / 8;
+        int row = q % 128; q /= 128;
+        int k = q % 2; q /= 2;
+        int step = q % kSteps1s; q /= kSteps1s;
+        int chunk = q % 8; int kt = q / 8;
+        int idx, part;
+        if (step < 49) { idx = step; part = 0; }
+        else { idx = 2 * (step - 49) + k; part = 1; }
+        uint16_t v = 0;
+        if (idx < 49) {
+            const int tap = l1s_tap(idx), kh = tap / 7, kw = tap % 7;
+            v = h_part(w[(((row * 64 + chunk * 8 + e) * 3 + kt) * 7 + kh) * 7 + kw], part);
+        }
+        img[i] = v;
+    }
+}
+
+// conv 2 image: [kh 7][kw 7][quarter 4][step 18 = kt*6 + s][k 2][128][8]; s < 4: hi weights of chunk s in both K halves;
+// s = 4, 5: lo weights of chunks 2(s-4), 2(s-4)+1
+__global__ void pack_w2s_kernel(const float* __restrict__ w, uint16_t* __restrict__ img) {
+    const int total = 49 * 4 * kSteps2s * kWeightTileBytes / 2;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int e = i % 8; int q = i / 8;
+        int row = q % 128; q /= 128;
+        int k = q % 2; q /= 2;
+        int step = q % kSteps2s; q /= kSteps2s;
+        int quarter = q % 4; q /= 4;
+        int kw = q % 7; int kh = q / 7;
+        const int kt = step / 6, s6 = step % 6;
+        const int c = s6 < 4 ? s6 : 2 * (s6 - 4) + k;
+        const int ci = quarter * 32 + c * 8 + e;
+        img[i] = h_part(w[(((row * 128 + ci) * 3 + kt) * 7 + kh) * 7 + kw], s6 < 4 ? 0 : 1);
+    }
+}
+
 }  // namespace tc
 }  // namespace vd
 
@@ -217,4 +331,48 @@ extern "C" int vd_tc_pack_weights_part(const float* w_l0, const float* w_l1, con
                                        void* w2, int part, void* stream) {
     VD_REQUIRE(part == 0 || part == 1, "tc_pack_weights_part: part must be 0 or 1");
     return pack_weights_impl(w_l0, w_l1, w_l2, w0, w1, w2, part, stream);
+}
+
+// ---- split-fp16 forward operands (vd_tc_x3_*) ----
+static int pack_video_x3_impl(const void* video, bool u8, const int64_t* index, void* x0s, const vd_tc_plan* plan, int B,
+                              const float* mean3, const float* std3, void* stream) {
+    VD_REQUIRE(video && x0s && plan && B >= 0, "tc_x3_pack_video: bad argument");
+    VD_REQUIRE(geo_supported(plan->T, plan->H), "tc_x3_pack_video: unsupported geometry");
+    if (B == 0) return 0;
+    const Geo g = make_geo(plan->T, plan->H);
+    NormU8 nm;
+    for (int c = 0; c < 3; ++c) { nm.mean[c] = mean3 ? mean3[c] : 0.f; nm.stdv[c] = std3 ? std3[c] : 1.f; }
+    const int64_t blocks = (int64_t)B * (g.T + 2) * 12;                      // planes [b][t_pad][part][c][par]
+    VD_REQUIRE(blocks < (1ll << 31), "tc_x3_pack_video: grid too large");
+    if (u8) pack_video_x3_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(video, index, (uint4*)x0s, g.T, g.HW, g.RI0, g.Wo0, nm);
+    else pack_video_x3_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(video, index, (uint4*)x0s, g.T, g.HW, g.RI0, g.Wo0, nm);
+    return check_launch("tc_x3_pack_video");
+}
+
+extern "C" int vd_tc_x3_pack_video(const float* video, const int64_t* index, void* x0s, const vd_tc_plan* plan, int B, void* stream) {
+    return pack_video_x3_impl(video, false, index, x0s, plan, B, nullptr, nullptr, stream);
+}
+
+extern "C" int vd_tc_x3_pack_video_u8(const uint8_t* video, const int64_t* index, void* x0s, const vd_tc_plan* plan, int B,
+                                      const float* mean3, const float* std3, void* stream) {
+    VD_REQUIRE(mean3 && std3 && std3[0] != 0.f && std3[1] != 0.f && std3[2] != 0.f, "tc_x3_pack_video_u8: mean / non-zero std required");
+    return pack_video_x3_impl(video, true, index, x0s, plan, B, mean3, std3, stream);
+}
+
+extern "C" int vd_tc_x3_pack_weights(const float* w_l0, const float* w_l1, const float* w_l2, void* w0s, void* w1s, void* w2s,
+                                     void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (w_l0 && w0s) {
+        pack_w0s_kernel<<<148, 256, 0, s>>>(w_l0, (uint16_t*)w0s);
+        if (int e = check_launch("tc_x3_pack_w0")) return e;
+    }
+    if (w_l1 && w1s) {
+        pack_w1s_kernel<<<148 * 8, 256, 0, s>>>(w_l1, (uint16_t*)w1s);
+        if (int e = check_launch("tc_x3_pack_w1")) return e;
+    }
+    if (w_l2 && w2s) {
+        pack_w2s_kernel<<<148 * 8, 256, 0, s>>>(w_l2, (uint16_t*)w2s);
+        if (int e = check_launch("tc_x3_pack_w2")) return e;
+    }
+    return 0;
 }

@@ -270,12 +270,14 @@ class _RealEmbedder:
         self.device = device
         self.max_batch = max_batch
         self.tc = None
-        if precision == 'bf16':
+        if precision in ('bf16', 'f16x3'):
+            # 'f16x3': the fused pipeline on fp16 hi/lo operand pairs (fp32-equivalent embeddings and routing, the parity
+            # mode of the fast path); 'bf16': single-pass bf16 operands and activations (throughput mode)
             if not tc_supported(frames, im_size[0], im_size[1]):
                 raise RuntimeError(f'tensor-core path does not support videos {frames}x{im_size}')
-            self.tc = TcConvNet3D(frames, im_size[0], im_size[1], device, max_batch=max_batch)
+            self.tc = TcConvNet3D(frames, im_size[0], im_size[1], device, max_batch=max_batch, split=(precision == 'f16x3'))
         elif precision not in ('fp32', 'bf16x3'):
-            raise ValueError("precision must be 'bf16', 'bf16x3' or 'fp32'")
+            raise ValueError("precision must be 'f16x3', 'bf16', 'bf16x3' or 'fp32'")
 
     def load(self, net):
         self.net = net

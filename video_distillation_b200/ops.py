@@ -218,6 +218,16 @@ class _RouteScatter(torch.autograd.Function):
         return _RouteGather.apply(c, code, k), None, None, None
 
 
+def route_scatter_raw(gy, code, x_shape, k):
+    """gx[src(o)] = active(o) ? gy[o] : 0 without autograd bookkeeping (backward of the fused tensor-core embed)."""
+    gy = _f32c(gy)
+    N, C, T, H, W = x_shape
+    gx = torch.empty(x_shape, dtype=torch.float32, device=gy.device)
+    if gx.numel():
+        check(lib().vd_route_scatter_f32(ptr(gy), ptr(code.contiguous()), ptr(gx), N * C, T, H, W, k[0], k[1], k[2], stream()), 'route_scatter')
+    return gx
+
+
 class _ReluMaxPool(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, k):

@@ -28,18 +28,33 @@ def tc_supported(T, H, W):
 
 
 class TcConvNet3D:
-    """bf16 tensor-core embed of a ConvNet3D whose feature weights are given as fp32 tensors."""
+    """Tensor-core embed of a ConvNet3D whose feature weights are given as fp32 tensors.
 
-    def __init__(self, T, H, W, device, max_batch=128):
+    split=False: bf16 operands and bf16 activations between the layers (single pass, throughput mode).
+    split=True : "f16x3" — every operand is an fp16 hi/lo pair and every product xh*wh + xl*wh + xh*wl in the same fp32
+                 TMEM accumulator (csrc/tc_layout.h: SGeo): embeddings within ~3e-6 of an fp32 evaluation, ReLU / MaxPool
+                 routing decided on fp32-equivalent sums; the backward runs the dgrads as split-bf16 (three passes each)."""
+
+    def __init__(self, T, H, W, device, max_batch=128, split=False):
         self.plan = make_plan(T, H, W)
         self.T, self.H, self.W = T, H, W
         self.device = torch.device(device)
         self.max_batch = int(max_batch)
+        self.split = bool(split)
         p = self.plan
         u8 = dict(dtype=torch.uint8, device=self.device)
-        self.w0 = torch.empty(p.w0_bytes, **u8)
-        self.w1 = torch.empty(p.w1_bytes, **u8)
-        self.w2 = torch.empty(p.w2_bytes, **u8)
+        if self.split:
+            sz = (ctypes.c_int64 * 6)()
+            _lib.check(_lib.lib().vd_tc_x3_sizes(ctypes.byref(p), sz), 'vd_tc_x3_sizes')
+            self.x0_per, self.a1_per, self.a2_per = int(sz[0]), int(sz[1]), int(sz[2])
+            wb = (int(sz[3]), int(sz[4]), int(sz[5]))
+        else:
+            self.x0_per, self.a1_per, self.a2_per = int(p.x0_bytes_per_video), int(p.a1_bytes_per_video), int(p.a2_bytes_per_video)
+            wb = (int(p.w0_bytes), int(p.w1_bytes), int(p.w2_bytes))
+        self.w0 = torch.empty(wb[0], **u8)
+        self.w1 = torch.empty(wb[1], **u8)
+        self.w2 = torch.empty(wb[2], **u8)
+        self._trio = None
         self.wt0 = torch.empty(p.wt0_bytes, **u8)       # transposed images for the backward column GEMMs
         self.wt1 = torch.empty(p.wt1_bytes, **u8)
         self.wt2 = torch.empty(p.wt2_bytes, **u8)
@@ -68,9 +83,9 @@ class TcConvNet3D:
     def load_weights(self, w0, b0, w1, b1, w2, b2):
         """fp32 OIDHW weights/biases of features.{0,3,6} -> UMMA images (3 small pack launches)."""
         ws = [t.detach().contiguous().float() for t in (w0, w1, w2)]
-        _lib.check(_lib.lib().vd_tc_pack_weights(_lib.ptr(ws[0]), _lib.ptr(ws[1]), _lib.ptr(ws[2]),
-                                                 _lib.ptr(self.w0), _lib.ptr(self.w1), _lib.ptr(self.w2),
-                                                 _lib.stream()), 'vd_tc_pack_weights')
+        pack = _lib.lib().vd_tc_x3_pack_weights if self.split else _lib.lib().vd_tc_pack_weights
+        _lib.check(pack(_lib.ptr(ws[0]), _lib.ptr(ws[1]), _lib.ptr(ws[2]), _lib.ptr(self.w0), _lib.ptr(self.w1), _lib.ptr(self.w2),
+                        _lib.stream()), 'vd_tc_pack_weights')
         self.b0, self.b1, self.b2 = (t.detach().contiguous().float() for t in (b0, b1, b2))
         self._fp32_w = ws
         self._bwd_ready = False
@@ -98,6 +113,8 @@ class TcConvNet3D:
     def embed_backward(self, g_emb, codes):
         """Gradient of ``embed`` w.r.t. its input videos for the routing recorded in ``codes``
         (weights frozen): three column GEMMs on tensor cores + col2im/routing gathers."""
+        if self.split:
+            return self._embed_backward_split(g_emb, codes)
         self._prepare_bwd()
         p, lib = self.plan, _lib.lib()
         g_emb = g_emb.contiguous().float()
@@ -140,6 +157,36 @@ class TcConvNet3D:
             _lib.check(lib.vd_tc_bwd_col2im(0, _lib.ptr(col), None, _lib.ptr(dvideo[s:e]), plan, n, st), 'vd_tc_bwd_col2im(0)')
         return dvideo
 
+    def _embed_backward_split(self, g_emb, codes):
+        """Backward of the f16x3 mode: route-scatter (fp32) + tensor-core dgrad of each conv evaluated as split-bf16,
+        gx = dgrad(gh, wh) + dgrad(gh, wl) + dgrad(gl, wh) with g = gh + gl, w = wh + wl (bf16 parts, fp32 accumulate):
+        ~16 significand bits per operand, no range limits on the gradient.  Returns d video (B,T,3,H,W)."""
+        from . import ops
+        from .tc_trio import TcTrio
+        if self._trio is None:
+            self._trio = TcTrio(self.T, self.H, self.W, self.device)
+        trio, p = self._trio, self.plan
+        ws = self._fp32_w
+        wh = [w.to(torch.bfloat16).float() for w in ws]
+        wl = [w - h for w, h in zip(ws, wh)]
+        g_emb = g_emb.contiguous().float()
+        B = g_emb.shape[0]
+        out = torch.empty(B, self.T, 3, self.H, self.W, dtype=torch.float32, device=self.device)
+        ext_conv = [(p.T1, p.H1, p.W1), (p.T2, p.H2, p.W2), (p.T3, p.H3, p.W3)]        # conv outputs (pre-pool)
+        cout = (64, 128, 128)
+        pool = [(1, 2, 2), (2, 2, 2), (2, 2, 2)]
+        for s in range(0, B, self.bwd_chunk):
+            e = min(B, s + self.bwd_chunk)
+            g = g_emb[s:e].view(e - s, 128, p.T3p, p.H3p, p.W3p)
+            for layer in (2, 1, 0):
+                gy = ops.route_scatter_raw(g, codes[layer][s:e], (e - s, cout[layer]) + tuple(ext_conv[layer]), pool[layer])
+                gh = gy.to(torch.bfloat16).float()
+                g = trio.dgrad(layer, gh, wh[layer])
+                g += trio.dgrad(layer, gh, wl[layer])
+                g += trio.dgrad(layer, gy - gh, wh[layer])
+            out[s:e] = g.permute(0, 2, 1, 3, 4)
+        return out
+
     def embed_autograd(self, video):
         """Differentiable embed (gradient flows to ``video`` only; the net is frozen as in DM)."""
         return _TcEmbed.apply(video, self)
@@ -147,13 +194,12 @@ class TcConvNet3D:
     def _buffers(self, n, n_total=None):
         """a1 for one chunk of ``n`` videos, a2 for ``n_total`` (>= n) videos: conv 2 runs ONCE over all
         chunks of an embed call (its tiles are 4 videos wide, so small launches waste most of a wave)."""
-        p = self.plan
         n_total = n if n_total is None else n_total
         n4 = (n_total + 3) // 4 * 4
-        if self._a1 is None or self._a1.numel() < n * p.a1_bytes_per_video:
-            self._a1 = torch.zeros(n * p.a1_bytes_per_video, dtype=torch.uint8, device=self.device)
-        if self._a2 is None or self._a2.numel() < n4 * p.a2_bytes_per_video:
-            self._a2 = torch.zeros(n4 * p.a2_bytes_per_video, dtype=torch.uint8, device=self.device)
+        if self._a1 is None or self._a1.numel() < n * self.a1_per:
+            self._a1 = torch.zeros(n * self.a1_per, dtype=torch.uint8, device=self.device)
+        if self._a2 is None or self._a2.numel() < n4 * self.a2_per:
+            self._a2 = torch.zeros(n4 * self.a2_per, dtype=torch.uint8, device=self.device)
         return self._a1, self._a2
 
     def set_normalization(self, mean, std):
@@ -164,7 +210,7 @@ class TcConvNet3D:
         """fp32 (or uint8 frames, see set_normalization) (Bsrc,T,3,H,W) -> X0 for B = len(index) (or Bsrc) items."""
         assert video.dtype in (torch.float32, torch.uint8) and video.dim() == 5 and tuple(video.shape[1:]) == (self.T, 3, self.H, self.W)
         B = int(index.numel()) if index is not None else int(video.shape[0])
-        nbytes = B * self.plan.x0_bytes_per_video
+        nbytes = B * self.x0_per
         if out is None:
             if self._x0 is None or self._x0.numel() < nbytes:
                 self._x0 = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
@@ -172,11 +218,12 @@ class TcConvNet3D:
         if video.dtype == torch.uint8:
             if getattr(self, '_norm', None) is None:
                 raise RuntimeError('uint8 videos need TcConvNet3D.set_normalization(mean, std) first')
-            _lib.check(_lib.lib().vd_tc_pack_video_u8(_lib.ptr(video), _lib.ptr(index), _lib.ptr(out), ctypes.byref(self.plan), B,
-                                                      self._norm[0], self._norm[1], _lib.stream()), 'vd_tc_pack_video_u8')
+            fn = _lib.lib().vd_tc_x3_pack_video_u8 if self.split else _lib.lib().vd_tc_pack_video_u8
+            _lib.check(fn(_lib.ptr(video), _lib.ptr(index), _lib.ptr(out), ctypes.byref(self.plan), B,
+                          self._norm[0], self._norm[1], _lib.stream()), 'vd_tc_pack_video_u8')
             return out
-        _lib.check(_lib.lib().vd_tc_pack_video(_lib.ptr(video), _lib.ptr(index), _lib.ptr(out),
-                                               ctypes.byref(self.plan), B, _lib.stream()), 'vd_tc_pack_video')
+        fn = _lib.lib().vd_tc_x3_pack_video if self.split else _lib.lib().vd_tc_pack_video
+        _lib.check(fn(_lib.ptr(video), _lib.ptr(index), _lib.ptr(out), ctypes.byref(self.plan), B, _lib.stream()), 'vd_tc_pack_video')
         return out
 
     # ---------------------------------------------------------------- layers
@@ -191,6 +238,12 @@ class TcConvNet3D:
             self.timing.append((layer, int(B), ev[0], ev[1]))
 
     def _conv_layer(self, layer, src, wimg, bias, out, B, code=None, item_index=None, raw=False, code_first=0):
+        if self.split:
+            assert not raw, 'the split-fp16 path has fused epilogues only'
+            _lib.check(_lib.lib().vd_tc_x3_conv_layer(layer, _lib.ptr(src), _lib.ptr(wimg), _lib.ptr(bias), _lib.ptr(out),
+                                                      _lib.ptr(code), int(code_first), ctypes.byref(self.plan), _lib.ptr(item_index),
+                                                      int(B), _lib.stream()), f'vd_tc_x3_conv_layer({layer})')
+            return
         _lib.check(_lib.lib().vd_tc_conv_layer(layer, _lib.ptr(src), _lib.ptr(wimg), _lib.ptr(bias), _lib.ptr(out),
                                                _lib.ptr(code), int(code_first), ctypes.byref(self.plan), _lib.ptr(item_index),
                                                int(B), int(raw), _lib.stream()), f'vd_tc_conv_layer({layer})')
@@ -225,7 +278,7 @@ class TcConvNet3D:
                 first = max(0, code_first - s)              # chunk-local index of the first item with codes
                 cc0, cc1 = c0[s + first - code_first:], c1[s + first - code_first:]
             self.conv_layer(0, x0, self.w0, self.b0, a1, e - s, code=cc0, item_index=idx, code_first=first)
-            self.conv_layer(1, a1, self.w1, self.b1, a2[s * p.a2_bytes_per_video:], e - s, code=cc1, code_first=first)
+            self.conv_layer(1, a1, self.w1, self.b1, a2[s * self.a2_per:], e - s, code=cc1, code_first=first)
         self.conv_layer(2, a2, self.w2, self.b2, out, B, code=c2, code_first=code_first)
         return out
 
@@ -240,8 +293,8 @@ class TcConvNet3D:
         (bf16, 'kw-expanded'); afterwards ``embed_resident`` reads it in place through item_index.
         ``extra_slots`` spare video slots at the tail receive the synthetic videos of ``embed_joint``."""
         N = int(videos.shape[0])
-        x0 = torch.empty((N + extra_slots) * self.plan.x0_bytes_per_video, dtype=torch.uint8, device=self.device)
-        per = self.plan.x0_bytes_per_video
+        x0 = torch.empty((N + extra_slots) * self.x0_per, dtype=torch.uint8, device=self.device)
+        per = self.x0_per
         for s in range(0, N, chunk):
             e = min(N, s + chunk)
             self.pack_video(videos[s:e], out=x0[s * per:e * per])
@@ -259,7 +312,7 @@ class TcConvNet3D:
         pass of the three conv kernels: the synthetic videos are packed into the spare slots ``tail_slot...`` of
         the resident operand and only they record routing codes.  Returns (emb_real, emb_syn, codes)."""
         n_real, n_syn = int(index_real.numel()), int(video_syn.shape[0])
-        per = self.plan.x0_bytes_per_video
+        per = self.x0_per
         assert x0_all.numel() >= (tail_slot + n_syn) * per, 'resident operand has no spare slots for the synthetic videos'
         self.pack_video(video_syn.contiguous(), out=x0_all[tail_slot * per:(tail_slot + n_syn) * per])
         index = torch.cat([index_real.reshape(-1), torch.arange(tail_slot, tail_slot + n_syn, device=self.device)])
