@@ -9,16 +9,20 @@ Workload (BASELINE.json configs[1], flags of sh/s2d/s2d_DM_ms.sh): distill_s2d_m
 one full DM iteration: fresh random frozen ConvNet3D, composer, 50x64 real + 50 synthetic video
 embeddings, DM loss, backward to dynamic memory + hallucinator, momentum-SGD updates.
 
+* precision (default f16x3): the parity mode of the fused tcgen05 pipeline — fp16 hi/lo operand pairs, three products per
+          MAC into one fp32 TMEM accumulator (embeddings ~5e-5 of fp32, routing-conditioned gradients < 1e-3; tests/test_x3_gpu.py,
+          tests/test_parity_fullsize_gpu.py).  `throughput_mode` reports the single-pass bf16 line beside it.
 * value : iterations/s with the real set resident in HBM (device-timed, max over ranks).
-* e2e   : same iteration driven from HOST memory: every step copies its 3200 sampled real videos from pinned host memory
-          (double-buffered on a copy stream) and reads the loss back (get_images(...).to(device) + loss.item(),
-          distill_s2d_ms.py:87,440).  Headline: the host holds the decoded uint8 frames and the (u/255 - mean)/std
-          normalisation is fused into the packer (bit-identical operands, 1.9 GB per step); `e2e_fp32_host` is the same
-          with the reference's preloaded fp32 tensors (7.7 GB per step), `e2e_bf16_host` with bf16 host tensors.
-* e2e_resident : the product's intended mode — dataset uploaded once, per-step H2D = sampled indices.
-* roofline : conv-1 tcgen05 kernel (69 % of the FLOPs), CUDA events around its launches.
-* cpu_baseline : the CPU oracle (port of the reference loop, torch CPU) on a bounded sample.
-With --impl reference the CPU oracle alone is timed (rank 0 only) on the same metric.
+* e2e   : same iteration driven from HOST memory the way the reference holds its data (get_images, distill_s2d_ms.py:81-87):
+          every step copies its sampled real videos as normalised fp32 from pinned host memory (double-buffered on a copy
+          stream) and reads the loss back.  `e2e_uint8_host` (decoded uint8 frames on the host, normalisation fused into the
+          packer, a quarter of the PCIe bytes) and `e2e_resident` (dataset uploaded once) are reported next to it.
+* check : loss of the last timed step and checksums of the trained memories after the timed steps — equal for every --gpus N.
+* roofline : conv-1 tcgen05 kernel (69 % of the FLOPs), CUDA events around its launches, algorithmic FLOPs.
+* reference_torch_cuda : the reference's OWN modules (baseline/_ref) running the verbatim loop body on this GPU (cuDNN),
+          allow_tf32 off and on (BASELINE.json configs[1] "vs reference torch-CUDA").
+* cpu_baseline : the reference's own modules on the host cores, bounded sample (kind "reference"; the oracle port if absent).
+With --impl reference the reference's CPU path alone is timed (rank 0 only) on the same metric.
 """
 import argparse
 import json
@@ -95,9 +99,99 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ reference arm
+def reference_dir():
+    """Where the reference's own python modules live: baseline/_ref (staged from /root/reference by __graft_entry__.build();
+    git-ignored, travels to the GPU box) -> $VD_REFERENCE -> /root/reference.  None when absent."""
+    for cand in (os.path.join(ROOT, 'baseline', '_ref'), os.environ.get('VD_REFERENCE'), '/root/reference'):
+        if cand and os.path.exists(os.path.join(cand, 'utils.py')) and os.path.exists(os.path.join(cand, 'networks.py')):
+            return cand
+    return None
+
+
+_REF_MODS = {}
+
+
+def import_reference(path):
+    """The reference's top-level modules (utils, networks) imported from `path` without being shadowed by this repo's
+    drop-in modules of the same names."""
+    if path in _REF_MODS:
+        return _REF_MODS[path]
+    saved = list(sys.path)
+    hidden = {n: sys.modules.pop(n) for n in ('networks', 'utils', 'reparam_module', 'distill_utils') if n in sys.modules}
+    sys.path[:] = [path] + [q for q in saved if os.path.abspath(q or '.') != ROOT]
+    try:
+        import networks as ref_networks          # noqa
+        import utils as ref_utils                # noqa
+    finally:
+        for n in ('networks', 'utils', 'reparam_module', 'distill_utils', 'distill_utils.dataset'):
+            sys.modules.pop(n, None)
+        sys.modules.update(hidden)
+        sys.path[:] = saved
+    _REF_MODS[path] = (ref_utils, ref_networks)
+    return _REF_MODS[path]
+
+
+class ReferenceLoop:
+    """State of distill_s2d_ms.py:89-108 and the VERBATIM iteration body of :393-438 (--method DM, --no_train_static) driven
+    through the reference's own modules (utils.get_network -> networks.ConvNet3D, utils.Conv3DNet, torch.optim.SGD) on
+    `device`.  The real set is a host TensorDataset of normalised fp32 videos like the reference's --preload.  `n_cls` < C
+    runs a bounded sample of the workload: the first n_cls classes of the per-class loop (the loop body is per class)."""
+
+    def __init__(self, ref_utils, device, n_cls, videos_host=None, per_class=None):
+        self.u, self.device, self.n_cls = ref_utils, device, n_cls
+        per_class = per_class or (BATCH_REAL + 2)
+        if videos_host is None:
+            g = torch.Generator().manual_seed(0)
+            videos_host = torch.randn(n_cls * per_class, T, 3, HW, HW, generator=g)
+        labels = torch.arange(n_cls).repeat_interleave(per_class)
+        self.dst_train = torch.utils.data.TensorDataset(videos_host, labels)
+        self.indices_class = [list(range(c * per_class, (c + 1) * per_class)) for c in range(n_cls)]
+        torch.manual_seed(0)
+        self.static_syn = torch.randn(size=(C * SPC, 3, HW, HW), dtype=torch.float).detach().to(device).requires_grad_(False)
+        self.dynamic_syn = torch.randn(size=(C, DPC, T, 1, HW, HW), dtype=torch.float).detach().to(device).requires_grad_(True)
+        self.hals = torch.nn.ModuleList([ref_utils.Conv3DNet()]).to(device)
+        self.optimizer_dynamic = torch.optim.SGD([self.dynamic_syn], lr=1e4, momentum=0.95)
+        self.optimizer_hals = torch.optim.SGD(self.hals.parameters(), lr=1e-2, momentum=0.95)
+
+    def get_images(self, c, n):                                                      # distill_s2d_ms.py:81-87
+        idx_shuffle = np.random.permutation(self.indices_class[c])[:n]
+        imgs = torch.cat([self.dst_train[i][0].unsqueeze(0) for i in idx_shuffle], 0)
+        return imgs.to(self.device)
+
+    def iteration(self):
+        dev, num_classes, vpc, spc = self.device, C, VPC, SPC
+        net = self.u.get_network('ConvNet3D', 3, num_classes, (HW, HW), frames=T, dist=False).to(dev)  # get a random model (:393)
+        net.train()
+        for param in list(net.parameters()):
+            param.requires_grad = False
+        embed = net.embed
+        label = torch.tensor(np.stack([np.ones(vpc) * i for i in range(0, num_classes)]), dtype=torch.long, requires_grad=False, device=dev).view(-1)
+        ran = torch.arange(0, num_classes * vpc).to(dev)
+        idx = ran % vpc
+        dynamic_idx = 2 * idx + torch.randint(2, (num_classes * vpc,), device=dev)
+        static_idx = spc * label + 2 * idx + torch.randint(2, (num_classes * vpc,), device=dev)
+        static = self.static_syn[static_idx, :, :, :]
+        dynamic = self.dynamic_syn[label, dynamic_idx, :, :, :, :]
+        hal = self.hals[0]
+        image_syn = hal(static, dynamic)
+        loss = torch.tensor(0.0).to(dev)
+        for c in range(0, self.n_cls):                                               # the reference runs range(0, num_classes)
+            img_real = self.get_images(c, BATCH_REAL)
+            img_syn = image_syn[c * vpc:(c + 1) * vpc].reshape((vpc, T, 3, HW, HW))
+            output_real = embed(img_real).detach()
+            output_syn = embed(img_syn)
+            loss += torch.sum((torch.mean(output_real, dim=0) - torch.mean(output_syn, dim=0)) ** 2)
+        self.optimizer_dynamic.zero_grad()
+        self.optimizer_hals.zero_grad()
+        loss.backward()
+        self.optimizer_dynamic.step()
+        self.optimizer_hals.step()
+        return loss.item()
+
+
 def cpu_oracle_rate(n_classes, n_real, threads):
-    """DM+S2D iteration of the CPU oracle on a bounded sample: n_classes classes x (n_real real + 1 syn)
-    videos of the full 16x3x112x112 shape; returns (it/s extrapolated to 50 x (64+1), seconds, description)."""
+    """Fallback when the reference's modules are absent: one DM+S2D iteration of the CPU oracle port (oracle/dm.py) on
+    n_classes classes; returns (it/s extrapolated to the full workload, seconds, description)."""
     import oracle
     torch.set_num_threads(threads)
     g = torch.Generator().manual_seed(0)
@@ -115,22 +209,38 @@ def cpu_oracle_rate(n_classes, n_real, threads):
     r = oracle.dm_s2d_iteration(params, static_syn, dyn, hal, videos, indices_class, vpc=VPC, spc=SPC,
                                 batch_real=n_real, coin_dynamic=cd, coin_static=cs)
     dt = time.perf_counter() - t0
-    # cost model: a synthetic video is forward + dgrad ~ 2 forward-equivalents
     sample_units = n_classes * (n_real + 2 * VPC)
     full_units = C * (BATCH_REAL + 2 * VPC)
     its = 1.0 / (dt * full_units / sample_units)
-    desc = (f'{n_classes} classes x ({n_real} real + {VPC} syn) videos 16x3x112x112, one oracle DM+S2D iteration '
-            f'(fwd + backward to dynamic memory) = {sample_units}/{full_units} of a full iteration, linearly extrapolated')
+    desc = (f'{n_classes} of {C} classes x ({n_real} real + {VPC} syn) videos {T}x3x{HW}x{HW}, one oracle-port DM+S2D iteration, '
+            f'linearly extrapolated to {C} classes')
     assert torch.isfinite(r['loss'])
     return its, dt, desc
 
 
-def sample_classes(seconds, threads):
-    """How many full classes (batch_real real + vpc syn videos each) of the workload fit in `seconds` of
-    CPU-oracle time on this host (calibrated on a 2-class x 8-video pass)."""
-    _, dt, _ = cpu_oracle_rate(2, 8, threads)
-    per_class = dt / (2 * (8 + 2 * VPC)) * (BATCH_REAL + 2 * VPC)
-    return int(max(1, min(C // 2, seconds / max(per_class, 1e-3))))
+def reference_cpu_rate(loop, threads):
+    """One iteration of the reference's own loop on the host cores over loop.n_cls classes -> (it/s extrapolated to all C
+    classes, measured seconds, description).  The per-class loop body is the whole cost; the class-independent part
+    (get_network, composer, optimiser) is timed inside and not scaled."""
+    torch.set_num_threads(threads)
+    t0 = time.perf_counter()
+    loss = loop.iteration()
+    dt = time.perf_counter() - t0
+    assert np.isfinite(loss)
+    its = 1.0 / (dt * C / loop.n_cls)
+    desc = (f'{loop.n_cls} of {C} classes x ({BATCH_REAL} real + {VPC} syn) videos {T}x3x{HW}x{HW} through the reference\'s own '
+            f'modules (utils.get_network / networks.ConvNet3D.embed / utils.Conv3DNet / torch.optim.SGD, loop body of '
+            f'distill_s2d_ms.py:393-438), time scaled by {C}/{loop.n_cls}')
+    return its, dt, desc
+
+
+def bench_config(n_gpus):
+    """The workload description shared verbatim by both arms (no implementation keys)."""
+    return {'workload': WORKLOAD_DESC,
+            'parallelism': f'classes sharded c%{n_gpus}, dynamic-memory gradient all-reduced (NCCL)' if n_gpus > 1 else 'single GPU',
+            'real_videos_per_step': C * BATCH_REAL, 'syn_videos_per_step': C * VPC,
+            'l2_policy': f'inputs larger than L2: each step reads {C * BATCH_REAL} distinct real videos '
+                         f'({C * BATCH_REAL * T * 3 * HW * HW * 4 / 1e9:.1f} GB fp32)'}
 
 
 def run_reference(args):
@@ -138,24 +248,80 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
+    total = max(1, args.warmup + args.steps)
+    refdir = reference_dir()
     vals, secs = [], []
-    desc = ''
-    # bounded sample sized from a calibration pass so that the whole run stays near 150 s on any host
-    n_cls = sample_classes(150.0 / max(1, args.warmup + args.steps), threads)
-    for i in range(args.warmup + args.steps):
-        its, dt, desc = cpu_oracle_rate(n_cls, BATCH_REAL, threads)
-        if i >= args.warmup:
-            vals.append(its)
-            secs.append(dt)
+    if refdir is not None:
+        ref_utils, _ = import_reference(refdir)
+        # bounded sample: calibrate on 2 classes, then as many classes per step as fit ~150 s in total (at least 10)
+        probe = ReferenceLoop(ref_utils, 'cpu', 2)
+        _, dt2, _ = reference_cpu_rate(probe, threads)
+        n_cls = int(max(min(10, C), min(C, (150.0 / total) / max(dt2 / 2, 1e-3))))
+        np.random.seed(0)
+        loop = ReferenceLoop(ref_utils, 'cpu', n_cls)
+        for i in range(total):
+            its, dt, desc = reference_cpu_rate(loop, threads)
+            if i >= args.warmup:
+                vals.append(its)
+                secs.append(dt)
+        kind, impl = 'reference', f'the reference\'s own modules from {os.path.relpath(refdir, ROOT) if refdir.startswith(ROOT) else refdir}, torch CPU, all host cores'
+    else:
+        n_cls = sample_classes(150.0 / total, threads)
+        for i in range(total):
+            its, dt, desc = cpu_oracle_rate(n_cls, BATCH_REAL, threads)
+            if i >= args.warmup:
+                vals.append(its)
+                secs.append(dt)
+        kind, impl = 'port', 'CPU oracle port (oracle/dm.py): reference modules not found'
     v = float(np.mean(vals))
     print(json.dumps({
         'impl': 'reference', 'metric': 'DM+S2D distill iters/sec', 'value': v, 'unit': 'it/s', 'n_gpus': args.gpus,
-        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1000.0 / v, 'higher_is_better': True,
-        'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD_DESC, 'implementation': 'CPU oracle: torch-CPU port of distill_s2d_ms.py:393-438 (oracle/dm.py), all host cores'},
-        'cpu_baseline': {'value': v, 'unit': 'it/s', 'cores': threads, 'kind': 'port', 'sample': desc,
+        'steps': args.steps, 'warmup': args.warmup,
+        # a step of this arm is the bounded sample: ms_per_step is what a step actually took, value is scaled to the workload
+        'ms_per_step': 1000.0 * float(np.mean(secs)), 'ms_per_full_iteration': 1000.0 / v,
+        'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': bench_config(args.gpus), 'reference_impl': impl,
+        'cpu_baseline': {'value': v, 'unit': 'it/s', 'cores': threads, 'kind': kind, 'sample': desc,
                          'sample_seconds': float(np.mean(secs))},
         'e2e': {'value': v, 'unit': 'it/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+
+
+def sample_classes(seconds, threads):
+    """How many full classes of the workload fit in `seconds` of CPU-oracle-port time (calibrated on 2 classes x 8 videos)."""
+    _, dt, _ = cpu_oracle_rate(2, 8, threads)
+    per_class = dt / (2 * (8 + 2 * VPC)) * (BATCH_REAL + 2 * VPC)
+    return int(max(1, min(C // 2, seconds / max(per_class, 1e-3))))
+
+
+def reference_torch_cuda(dev, videos_host, iters=2):
+    """The reference's own modules on this GPU (ATen -> cuDNN), verbatim loop body, all C classes, host-resident fp32 real set:
+    it/s with cudnn.allow_tf32 off (fp32 parity setting) and on (PyTorch's default = the reference as shipped)."""
+    refdir = reference_dir()
+    if refdir is None:
+        return {'unavailable': 'reference modules not found (baseline/_ref, $VD_REFERENCE, /root/reference)'}
+    ref_utils, _ = import_reference(refdir)
+    out = {'source': os.path.relpath(refdir, ROOT) if refdir.startswith(ROOT) else refdir, 'iterations_timed': iters,
+           'note': 'reference loop body distill_s2d_ms.py:393-438 through utils.get_network / networks.ConvNet3D / utils.Conv3DNet on '
+                   'cuda (cuDNN); real set = host TensorDataset of normalised fp32 videos, get_images(...).to(device) per class'}
+    prev = torch.backends.cudnn.allow_tf32
+    try:
+        for name, tf32 in (('allow_tf32_false', False), ('allow_tf32_true', True)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            np.random.seed(0)
+            loop = ReferenceLoop(ref_utils, dev, C, videos_host=videos_host, per_class=PER_CLASS)
+            loop.iteration()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(iters):
+                loss = loop.iteration()
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / iters
+            out[name] = {'value': 1.0 / dt, 'unit': 'it/s', 'ms_per_step': dt * 1e3, 'loss': loss}
+            del loop
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    return out
 
 
 def memory_kernel_rooflines(step_fn, tr, steps=3):
@@ -176,15 +342,20 @@ def memory_kernel_rooflines(step_fn, tr, steps=3):
     hbm = float(peaks['hbm_gbs'])
     n_syn = C * VPC
     thw, hw = T * HW * HW, HW * HW
-    p = tr.embedder.tc.plan
+    tcn = tr.embedder.tc
+    p = tcn.plan
+    dyp1 = getattr(tcn, 'dyp1_bytes_per_video', 0)
     rows = [  # (kernel-name substring, algorithmic bytes per launch, what)
         ('compose_fwd_tiled_kernel', n_syn * 4 * (3 * hw + thw + 3 * thw), 'read static+dynamic, write video'),
+        ('compose_bwd_fused_kernel', n_syn * 4 * (3 * thw + thw + 3 * hw + thw), 'read d video + dynamic + static, write d dynamic'),
         ('compose_bwd_data_tiled_kernel', n_syn * 4 * (3 * thw + thw), 'read d video, write d dynamic'),
         ('compose_bwd_wdyn_tiled_kernel', n_syn * 4 * (3 * thw + thw), 'read d video + dynamic'),
         ('compose_bwd_weight_static_kernel', n_syn * 4 * (3 * thw + 3 * hw), 'read d video + static'),
         ('col2im_rows_kernel<7, 8', n_syn * (p.col0_bytes_per_video + 4 * 3 * thw), 'read conv-0 columns, write d video'),
-        ('col2im_kernel<', n_syn * (p.col2_bytes_per_video + 128 * (T // 2) * 49), 'read conv-2 columns + codes, write padded planar dY1'),
+        ('col2im_kernel<', n_syn * (p.col2_bytes_per_video + 128 * int(p.T2p) * int(p.H2p) * int(p.W2p) + dyp1),
+         'read conv-2 columns + codes, write padded planar dY1'),
         ('pack_video_kernel', n_syn * (4 * 3 * thw + p.x0_bytes_per_video), 'read fp32 video, write packed bf16 conv-0 operand'),
+        ('pack_video_x3_kernel', n_syn * (4 * 3 * thw + tcn.x0_per), 'read fp32 video, write packed fp16 hi/lo conv-0 operand'),
         ('sgd_momentum_kernel', None, '20 B / element (dynamic memory)'),
         ('class_mean_kernel', C * BATCH_REAL * p.embed_dim * 4, 'read real embeddings'),
     ]
@@ -209,6 +380,7 @@ def memory_kernel_rooflines(step_fn, tr, steps=3):
 
 # ------------------------------------------------------------------------------------------ our arm
 def run_ours(args):
+    import copy
     import torch.distributed as dist
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -253,13 +425,23 @@ def run_ours(args):
     frames_host.copy_(frames)
     del frames
     ds = DeviceDataset.from_device_shard(vids, labels, C, dev, rank, world)
-    torch.manual_seed(0)
-    tr = DMS2DTrainer(ds, num_classes=C, im_size=(HW, HW), frames=T, vpc=VPC, spc=SPC, dpc=DPC, batch_real=BATCH_REAL,
-                      lr_dynamic=1e4, lr_hal=1e-2, precision=args.precision, device=dev, init_on_device=True,
-                      max_batch=args.max_batch,
-                      syn_on_tensor_cores={'fused': True, 'split': 'split', 'fp32': False}[args.syn_mode])
+
+    def make_trainer(precision, dataset):
+        torch.manual_seed(0)
+        return DMS2DTrainer(dataset, num_classes=C, im_size=(HW, HW), frames=T, vpc=VPC, spc=SPC, dpc=DPC, batch_real=BATCH_REAL,
+                            lr_dynamic=1e4, lr_hal=1e-2, precision=precision, device=dev, init_on_device=True,
+                            max_batch=args.max_batch,
+                            syn_on_tensor_cores={'fused': True, 'split': 'split', 'fp32': False}[args.syn_mode])
+    tr = make_trainer(args.precision, ds)
+    prepack = None
     if tr.embedder.tc is not None and not args.no_prepack:
-        ds.prepack(tr.embedder.tc, extra_slots=len(tr.owned) * tr.vpc)          # one-time dataset conversion (outside the timed region, like --preload)
+        # one-time conversion of the resident real set into the packed conv-0 operand (outside the timed region, like --preload)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ds.prepack(tr.embedder.tc, extra_slots=len(tr.owned) * tr.vpc)
+        torch.cuda.synchronize()
+        prepack = {'ms': (time.perf_counter() - t0) * 1e3, 'bytes_per_video': int(tr.embedder.tc.x0_per),
+                   'resident_bytes': int(ds.x0.numel()), 'videos': int(vids.shape[0])}
     np.random.seed(0)
     torch.cuda.manual_seed(1234)
 
@@ -282,10 +464,12 @@ def run_ours(args):
         return ms.item()
 
     seed_box = [0]
+    last_loss = [None]
 
-    def step_resident():
+    def step_resident(trainer=None):
         seed_box[0] += 1
-        return tr.step(net_seed=seed_box[0])          # same seed on every rank -> same frozen net
+        last_loss[0] = (trainer or tr).step(net_seed=seed_box[0])          # same seed on every rank -> same frozen net
+        return last_loss[0]
 
     # ---- warm-up, then the timed region (device-resident inputs)
     sampler = ClockSampler(local)
@@ -312,13 +496,20 @@ def run_ours(args):
             layer_launches[layer] += 1
         tc.timing = None
     value = args.steps / (ms / 1000.0)
+    # result fingerprint after warmup + steps iterations: every world size must print the same numbers (class sharding and
+    # the all-reduce only change the order of a few fp32 additions)
+    dsyn = tr.dynamic_syn.detach().double()
+    check = {'iterations': args.warmup + args.steps, 'loss_last': float(last_loss[0]),
+             'dynamic_syn_sum': float(dsyn.sum()), 'dynamic_syn_sumsq': float((dsyn * dsyn).sum()),
+             'hal_weight_sum': float(tr.hal.encoder.weight.detach().double().sum())}
+    del dsyn
 
-    # ---- e2e (a): the step's real videos come from pinned host memory, loss is read back.
-    # Double-buffered: while step i computes, the host->device copies of step i+1's sampled videos run on a
-    # copy stream (the sampling only depends on the numpy RNG stream, not on results).  Every timed step
-    # issues exactly one full set of copies inside the timed region.
+    # ---- e2e: the step's real videos come from pinned host memory as normalised fp32 (the reference's TensorDataset,
+    # get_images(...).to(device), distill_s2d_ms.py:81-87), the loss is read back.  Double-buffered: while step i computes,
+    # the host->device copies of step i+1's sampled videos run on a copy stream (the sampling only depends on the numpy RNG
+    # stream, not on results).  Every timed step issues exactly one full set of copies inside the timed region.
     n_own_real = len(own) * BATCH_REAL
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = max(1, args.steps)
     host = torch.empty(vids.shape, dtype=torch.float32, pin_memory=True)
     host.copy_(vids)
     bytes_video = T * 3 * HW * HW * 4
@@ -328,95 +519,11 @@ def run_ours(args):
     free = [torch.cuda.Event() for _ in range(2)]
     pending = [None, None]
     slot_box = [0]
+    perm_dev = [torch.empty(n_own_real, dtype=torch.int64, device=dev) for _ in range(2)]
+    perm_pin = [torch.empty(n_own_real, dtype=torch.int64).pin_memory() for _ in range(2)]
 
-    def prefetch(slot):
-        real_idx = ds.sample_all_classes(BATCH_REAL)
-        loc = ds.local_of_global[real_idx[own].reshape(-1)]
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(free[slot])            # the step that last read this buffer has finished
-            dst = stages[slot]
-            for j, src in enumerate(loc):
-                dst[j].copy_(host[int(src)], non_blocking=True)
-            ready[slot].record(copy_stream)
-        pending[slot] = real_idx
-
-    def step_streaming():
-        seed_box[0] += 1
-        slot = slot_box[0]
-        slot_box[0] ^= 1
-        torch.cuda.current_stream().wait_event(ready[slot])
-        loss = tr.step(net_seed=seed_box[0], real_idx=pending[slot], real_batch=stages[slot])
-        free[slot].record()
-        prefetch(slot ^ 1)                                # next step's inputs: H2D overlaps this step's kernels
-        return loss.item()                                # D2H read of the step's result
-
-    for ev in free:
-        ev.record()
-    prefetch(0)
-    step_streaming()
-    ms_stream = timed(step_streaming, e2e_steps)
-    e2e_stream = e2e_steps / (ms_stream / 1000.0)
-    torch.cuda.synchronize()
-    del host, stages
-
-    e2e_fp32 = {'value': e2e_stream, 'unit': 'it/s', 'h2d_bytes_per_step': int(C * BATCH_REAL * bytes_video), 'd2h_bytes_per_step': 4,
-                'steps': e2e_steps,
-                'note': f'per step: {C * BATCH_REAL} sampled real videos (normalised fp32, the reference\'s preloaded TensorDataset) copied from '
-                        f'pinned host memory, double-buffered on a copy stream, + loss.item()'}
-
-    # ---- e2e (a'): the same streaming step with the host copy of the real set kept in bf16 (one-time conversion at
-    # load; the tensor-core path rounds its inputs to bf16 anyway, so results are bit-identical): half the PCIe bytes
-    e2e_bf16 = None
-    if tr.embedder.tc is not None:
-        host16 = torch.empty(vids.shape, dtype=torch.bfloat16, pin_memory=True)
-        host16.copy_(vids)
-        stages16 = [torch.empty(n_own_real, T, 3, HW, HW, dtype=torch.bfloat16, device=dev) for _ in range(2)]
-        stage32 = torch.empty(n_own_real, T, 3, HW, HW, device=dev)
-
-        def prefetch16(slot):
-            real_idx = ds.sample_all_classes(BATCH_REAL)
-            loc = ds.local_of_global[real_idx[own].reshape(-1)]
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(free[slot])
-                dst = stages16[slot]
-                for j, src in enumerate(loc):
-                    dst[j].copy_(host16[int(src)], non_blocking=True)
-                ready[slot].record(copy_stream)
-            pending[slot] = real_idx
-
-        def step_streaming16():
-            seed_box[0] += 1
-            slot = slot_box[0]
-            slot_box[0] ^= 1
-            torch.cuda.current_stream().wait_event(ready[slot])
-            stage32.copy_(stages16[slot])                  # bf16 -> fp32 on the device (exact)
-            free[slot].record()
-            loss = tr.step(net_seed=seed_box[0], real_idx=pending[slot], real_batch=stage32)
-            prefetch16(slot ^ 1)
-            return loss.item()
-
-        for ev in free:
-            ev.record()
-        prefetch16(slot_box[0])
-        step_streaming16()
-        ms16 = timed(step_streaming16, e2e_steps)
-        e2e_bf16 = {'value': e2e_steps / (ms16 / 1000.0), 'unit': 'it/s', 'h2d_bytes_per_step': int(C * BATCH_REAL * bytes_video // 2),
-                    'd2h_bytes_per_step': 4, 'steps': e2e_steps,
-                    'note': f'host copy of the real set stored as bf16 (converted once at load); per step {C * BATCH_REAL} sampled videos over PCIe'}
-        torch.cuda.synchronize()
-        del host16, stages16, stage32
-
-    # ---- e2e (a''): the host keeps the decoded uint8 frames; the normalisation (u/255 - mean)/std is fused into the packer
-    # (vd_tc_pack_video_u8, bit-identical operands): a quarter of the PCIe bytes of the fp32 host tensors
-    e2e_u8 = None
-    if tr.embedder.tc is not None:
-        tr.embedder.tc.set_normalization(MEAN, STD)
-        stages8 = [torch.empty(n_own_real, T, 3, HW, HW, dtype=torch.uint8, device=dev) for _ in range(2)]
-
-        perm_dev = [torch.empty(n_own_real, dtype=torch.int64, device=dev) for _ in range(2)]
-        perm_pin = [torch.empty(n_own_real, dtype=torch.int64).pin_memory() for _ in range(2)]
-
-        def prefetch8(slot):
+    def make_prefetch(src_host, dst_stages):
+        def prefetch(slot):
             # the sampled rows are uploaded in ascending host order with adjacent rows merged into one copy (64 of a class's
             # 72 videos are drawn, so runs are long): same bytes, ~8x fewer and larger PCIe transfers; `perm` maps sample j to
             # its row of the staging buffer, so embeddings (and the result) keep the sampled order
@@ -429,52 +536,60 @@ def run_ours(args):
             starts = np.flatnonzero(np.concatenate(([True], np.diff(srt) != 1)))
             ends = np.concatenate((starts[1:], [srt.size]))
             with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(free[slot])
-                dst = stages8[slot]
+                copy_stream.wait_event(free[slot])            # the step that last read this buffer has finished
+                dst = dst_stages[slot]
                 for a, b in zip(starts, ends):
-                    dst[a:b].copy_(frames_host[int(srt[a]):int(srt[a]) + int(b - a)], non_blocking=True)
+                    dst[a:b].copy_(src_host[int(srt[a]):int(srt[a]) + int(b - a)], non_blocking=True)
                 perm_pin[slot].copy_(torch.from_numpy(perm))
                 perm_dev[slot].copy_(perm_pin[slot], non_blocking=True)
                 ready[slot].record(copy_stream)
             pending[slot] = real_idx
+        return prefetch
 
-        def step_streaming8():
+    def make_step(prefetch, dst_stages):
+        def step_streaming():
             seed_box[0] += 1
             slot = slot_box[0]
             slot_box[0] ^= 1
             torch.cuda.current_stream().wait_event(ready[slot])
-            loss = tr.step(net_seed=seed_box[0], real_idx=pending[slot], real_batch=stages8[slot], real_batch_index=perm_dev[slot])
+            loss = tr.step(net_seed=seed_box[0], real_idx=pending[slot], real_batch=dst_stages[slot], real_batch_index=perm_dev[slot])
             free[slot].record()
-            prefetch8(slot ^ 1)
-            return loss.item()
+            prefetch(slot ^ 1)                                # next step's inputs: H2D overlaps this step's kernels
+            return loss.item()                                # D2H read of the step's result
+        return step_streaming
 
+    def streaming_leg(src_host, dst_stages, nbytes, note):
+        prefetch = make_prefetch(src_host, dst_stages)
+        step = make_step(prefetch, dst_stages)
         for ev in free:
             ev.record()
-        prefetch8(slot_box[0])
-        step_streaming8()
-        ms8 = timed(step_streaming8, e2e_steps)
-        e2e_u8 = {'value': e2e_steps / (ms8 / 1000.0), 'unit': 'it/s', 'h2d_bytes_per_step': int(C * BATCH_REAL * bytes_video // 4),
-                  'd2h_bytes_per_step': 4, 'steps': e2e_steps,
-                  'note': f'host keeps the decoded uint8 frames; per step {C * BATCH_REAL} sampled videos over PCIe, normalisation fused into the packer'}
+        prefetch(slot_box[0])
+        step()
+        ms_s = timed(step, e2e_steps)
         torch.cuda.synchronize()
+        return {'value': e2e_steps / (ms_s / 1000.0), 'unit': 'it/s', 'h2d_bytes_per_step': int(nbytes), 'd2h_bytes_per_step': 4,
+                'steps': e2e_steps, 'ms_per_step': ms_s / e2e_steps, 'note': note}
+
+    e2e_fp32 = streaming_leg(host, stages, C * BATCH_REAL * bytes_video + C * BATCH_REAL * 8,
+                             f'per step: {C * BATCH_REAL} sampled real videos (normalised fp32, the reference\'s preloaded TensorDataset) '
+                             f'copied from pinned host memory, double-buffered on a copy stream, + loss.item()')
+    del stages
+
+    # ---- e2e (uint8 host): the host keeps the decoded uint8 frames; the normalisation (u/255 - mean)/std is fused into the
+    # packer (bit-identical operands): a quarter of the PCIe bytes of the fp32 host tensors
+    e2e_u8 = None
+    if tr.embedder.tc is not None:
+        tr.embedder.tc.set_normalization(MEAN, STD)
+        stages8 = [torch.empty(n_own_real, T, 3, HW, HW, dtype=torch.uint8, device=dev) for _ in range(2)]
+        e2e_u8 = streaming_leg(frames_host, stages8, C * BATCH_REAL * bytes_video // 4 + C * BATCH_REAL * 8,
+                               f'host keeps the decoded uint8 frames; per step {C * BATCH_REAL} sampled videos over PCIe, normalisation fused into the packer')
         del stages8
 
-    # ---- e2e (b): resident dataset, per-step host input = the sampled index table
+    # ---- e2e (resident): dataset uploaded once, per-step host input = the sampled index table
     def step_resident_e2e():
         return step_resident().item()
     ms_res = timed(step_resident_e2e, e2e_steps)
     e2e_res = e2e_steps / (ms_res / 1000.0)
-
-    # ---- the accuracy-first variant of the same step: synthetic branch on the split-bf16 conv trio with fp32
-    # activations (gradients within ~5e-3 of fp32 instead of ~1.3e-1, profiles/r01_parity_modes.log)
-    split_leg = None
-    if tr.embedder.tc is not None and args.syn_mode == 'fused':
-        tr.syn_on_tensor_cores = 'split'
-        step_resident()
-        ms_split = timed(step_resident, e2e_steps)
-        tr.syn_on_tensor_cores = True
-        split_leg = {'value': e2e_steps / (ms_split / 1000.0), 'unit': 'it/s', 'ms_per_step': ms_split / e2e_steps, 'steps': e2e_steps,
-                     'note': "syn_on_tensor_cores='split': split-bf16 fprop + fp32 activations for the synthetic videos"}
 
     # ---- memory-bound kernels inside the real step: CUPTI durations (torch.profiler) vs algorithmic bytes
     mem_kernels = None
@@ -483,6 +598,32 @@ def run_ours(args):
             mem_kernels = memory_kernel_rooflines(step_resident, tr)
         except Exception as e:                        # profiling aid only; never fail the bench line
             mem_kernels = {'error': repr(e)[:200]}
+
+    # ---- throughput mode beside the parity mode: the single-pass bf16 pipeline on the same workload
+    throughput = None
+    if args.precision == 'f16x3' and not args.no_throughput_mode:
+        ds.x0 = None
+        torch.cuda.empty_cache()
+        ds2 = copy.copy(ds)
+        tr2 = make_trainer('bf16', ds2)
+        ds2.prepack(tr2.embedder.tc, extra_slots=len(tr2.owned) * tr2.vpc)
+        for _ in range(max(2, args.warmup // 2)):
+            step_resident(tr2)
+        ms_t = timed(lambda: step_resident(tr2), e2e_steps)
+        throughput = {'value': e2e_steps / (ms_t / 1000.0), 'unit': 'it/s', 'ms_per_step': ms_t / e2e_steps, 'steps': e2e_steps, 'dtype': 'bf16',
+                      'note': "precision='bf16': single-pass bf16 operands and bf16 activations between the layers (embeddings ~2e-3, "
+                              'unconditioned synthetic gradient ~1e-1 of fp32: NOT the parity mode)'}
+        del tr2, ds2
+        torch.cuda.empty_cache()
+
+    # ---- the reference's own modules on this GPU (cuDNN), BASELINE.json configs[1] "vs reference torch-CUDA"
+    ref_cuda = None
+    if rank == 0 and world == 1 and not args.no_reference_cuda:
+        try:
+            ref_cuda = reference_torch_cuda(dev, host)
+        except Exception as e:
+            ref_cuda = {'error': repr(e)[:300]}
+    del host
 
     if rank != 0:
         if world > 1:
@@ -494,46 +635,57 @@ def run_ours(args):
     l1_flops_per_launch = F_L1 * layer_videos[1] / max(1, layer_launches[1])
     achieved = l1_flops_per_launch / (l1_avg_ms * 1e-3) / 1e12 if l1_avg_ms > 0 else 0.0
     peak = float(peaks.get('bf16_tflops_sustained', peaks.get('bf16_tflops', 1400.0)))
+    split = args.precision == 'f16x3'
     traffic = None
-    tpath = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
+    tpath = os.path.join(ROOT, 'profiles', 'r02_traffic.json' if split else 'r01_traffic.json')
     if os.path.exists(tpath) and (T, HW) == (16, 112):      # DRAM bytes per launch from the committed ncu --set full capture (U shape)
         tj = json.load(open(tpath))['dram_bytes_per_video']['conv1']
         traffic = (tj['read'] + tj['write']) * layer_videos[1] / max(1, layer_launches[1])
-    roofline = {'bound': 'tensor', 'kernel': 'ws_gemm_kernel<EPI_L1> (conv 1, 64->128)', 'achieved': achieved, 'peak': peak,
+    mma_per_mac = 3 if split else 1
+    roofline = {'bound': 'tensor', 'kernel': f'ws_gemm_kernel<{"EPI_L1S" if split else "EPI_L1"}> (conv 1, 64->128)', 'achieved': achieved, 'peak': peak,
                 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': traffic, 'peak_kind': f'bf16_tflops_sustained of {peak_kind}',
                 'avg_launch_ms': l1_avg_ms, 'flops_per_launch': l1_flops_per_launch,
+                'note': ('algorithmic FLOPs (2*M*N*K of the convolution); the f16x3 mode issues 3 tensor-core MACs per algorithmic MAC '
+                         '(xh*wh + xl*wh + xh*wl), so the tensor pipe runs at 3x this rate' if split else 'algorithmic FLOPs (2*M*N*K of the convolution)'),
+                'issued_tflops': achieved * mma_per_mac * (74.0 / 73.5 if split else 1.0), 'issued_frac': achieved * mma_per_mac / peak,
                 'per_layer_ms_per_step': {f'conv{k}': layer_ms[k] / args.steps for k in layer_ms},
                 'per_layer_tflops': {f'conv{k}': (f * layer_videos[k] / (layer_ms[k] * 1e-3) / 1e12 if layer_ms[k] > 0 else 0.0)
                                      for k, f in ((0, F_L0), (1, F_L1), (2, F_L2))}}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        its, dt, desc = cpu_oracle_rate(sample_classes(15.0, threads), BATCH_REAL, threads)     # ~15 s of CPU work
-        cpu = {'value': its, 'unit': 'it/s', 'cores': threads, 'kind': 'port', 'sample': desc, 'sample_seconds': dt}
+        refdir = reference_dir()
+        if refdir is not None:
+            ref_utils, _ = import_reference(refdir)
+            probe = ReferenceLoop(ref_utils, 'cpu', 2)
+            _, dt2, _ = reference_cpu_rate(probe, threads)
+            n_cls = int(max(2, min(C // 2, 15.0 / max(dt2 / 2, 1e-3))))                       # ~15 s of CPU work
+            np.random.seed(0)
+            its, dt, desc = reference_cpu_rate(ReferenceLoop(ref_utils, 'cpu', n_cls), threads)
+            cpu = {'value': its, 'unit': 'it/s', 'cores': threads, 'kind': 'reference', 'sample': desc, 'sample_seconds': dt}
+        else:
+            its, dt, desc = cpu_oracle_rate(sample_classes(15.0, threads), BATCH_REAL, threads)
+            cpu = {'value': its, 'unit': 'it/s', 'cores': threads, 'kind': 'port', 'sample': desc, 'sample_seconds': dt}
+    dtype = {'f16x3': 'f16x3', 'bf16': 'bf16'}.get(args.precision, 'f32')
     out = {
         'metric': 'DM+S2D distill iters/sec', 'value': value, 'unit': 'it/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'strong',
-        'vs_baseline': None, 'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD_DESC,
-                   'parallelism': f'classes sharded c%{world}, one NCCL all-reduce/step' if world > 1 else 'single GPU',
-                   'real_videos_per_step': C * BATCH_REAL, 'syn_videos_per_step': C * VPC,
-                   'l2_policy': f'inputs larger than L2: each step reads {C * BATCH_REAL} distinct real videos '
-                                f'({C * BATCH_REAL * T * 3 * HW * HW * 4 / 1e9:.1f} GB fp32)',
-                   'real_embed': 'tcgen05 bf16 operands / fp32 accumulate' if args.precision == 'bf16' else 'fp32 CUDA cores',
-                   'syn_branch': args.syn_mode,
-                   'real_set': 'resident fp32' + ('' if args.no_prepack else ' + pre-packed bf16 conv-0 operand (one-time)'),
-                   'videos_per_sec': value * C * (BATCH_REAL + VPC)},
-        'clocks': clocks, 'gpu_launches': int(launches),
-        # headline end-to-end number: the host holds the decoded uint8 frames (what a video dataset is before ToTensor/Normalize);
-        # the fp32-host variant (the reference's preloaded float TensorDataset, 4x the PCIe bytes) is reported next to it
-        'e2e': e2e_u8 if e2e_u8 is not None else e2e_fp32,
-        'e2e_fp32_host': e2e_fp32,
+        'vs_baseline': None, 'dtype': dtype, 'data': 'synthetic',
+        'config': bench_config(world),
+        'impl_detail': {'precision': args.precision,
+                        'real_embed': {'f16x3': 'tcgen05, fp16 hi/lo operand pairs (3 MMAs per MAC), fp32 accumulate in TMEM',
+                                       'bf16': 'tcgen05 bf16 operands / fp32 accumulate'}.get(args.precision, 'fp32 CUDA cores'),
+                        'syn_branch': args.syn_mode,
+                        'real_set': 'resident fp32' + ('' if args.no_prepack else ' + pre-packed conv-0 operand (one-time, outside the timed region)'),
+                        'prepack': prepack, 'videos_per_sec': value * C * (BATCH_REAL + VPC)},
+        'clocks': clocks, 'gpu_launches': int(launches), 'check': check,
+        # headline end-to-end number: the reference's own host format (normalised fp32 TensorDataset)
+        'e2e': e2e_fp32,
+        'e2e_uint8_host': e2e_u8,
         'e2e_resident': {'value': e2e_res, 'unit': 'it/s', 'h2d_bytes_per_step': int(C * BATCH_REAL * 8),
                          'd2h_bytes_per_step': 4, 'steps': e2e_steps,
                          'note': 'real set uploaded once; per step the host sends the sampled index table and reads the loss'},
-        'e2e_bf16_host': e2e_bf16,
-        'e2e_uint8_host': e2e_u8,
-        'syn_split_mode': split_leg,
+        'throughput_mode': throughput, 'reference_torch_cuda': ref_cuda,
         'roofline': roofline, 'memory_kernels': mem_kernels, 'cpu_baseline': cpu}
     print(json.dumps(out))
     if world > 1:
@@ -562,7 +714,11 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
+    ap.add_argument('--precision', default='f16x3', choices=['f16x3', 'bf16', 'fp32'],
+                    help='f16x3 (default): fused tcgen05 pipeline on fp16 hi/lo operand pairs, the parity mode; bf16: single-pass '
+                         'throughput mode; fp32: exact CUDA-core kernels')
+    ap.add_argument('--no-throughput-mode', action='store_true', help='skip the single-pass bf16 line reported beside the default mode')
+    ap.add_argument('--no-reference-cuda', action='store_true', help="skip the reference's own modules on this GPU (cuDNN)")
     ap.add_argument('--max-batch', type=int, default=640)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--syn-mode', default='fused', choices=['fused', 'split', 'fp32'],

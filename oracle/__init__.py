@@ -13,7 +13,7 @@ committed under ``tests/golden/`` and re-checked by ``tests/test_oracle_golden.p
 """
 from .convnet3d import (  # noqa: F401
     init_convnet3d, convnet3d_features, convnet3d_embed, convnet3d_forward,
-    convnet3d_param_names, flatten_params, unflatten_params, embed_dim,
+    convnet3d_param_names, flatten_params, unflatten_params, embed_dim, routing_codes,
 )
 from .composer import init_hallucinator, compose  # noqa: F401
 from .dm import (  # noqa: F401

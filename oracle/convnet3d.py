@@ -174,3 +174,21 @@ def embed_dim(frames, im_size, net_width=128, net_depth=3, net_pooling='maxpooli
             h //= 2
             w //= 2
     return net_width * t * h * w
+
+
+def routing_codes(params, video, dtype=torch.float32):
+    """ReLU masks / MaxPool argmax of the oracle forward (networks.py:757,766-770 with get_network's none/maxpooling setting) in
+    the CUDA library's routing-code format: per pooled output, ``arg | active << 3`` with arg the window position in (t,h,w)
+    scan order.  Lets a test impose the ORACLE's routing on the CUDA backward (routing-conditioned parity).
+    Returns [code0 (B,64,T,H1,H1), code1, code2] (uint8)."""
+    h = video.permute(0, 2, 1, 3, 4).to(dtype)
+    codes = []
+    for d in range(3):
+        y = F.conv3d(h, params[f'features.{3 * d}.weight'].to(dtype), params[f'features.{3 * d}.bias'].to(dtype), STRIDE, PADDING)
+        k = (1, 2, 2) if d == 0 else (2, 2, 2)
+        h, idx = F.max_pool3d(F.relu(y), k, k, return_indices=True)
+        To, Ho, Wo = y.shape[2:]
+        it, ih, iw = idx // (Ho * Wo), (idx // Wo) % Ho, idx % Wo
+        pos = (it % k[0]) * (k[1] * k[2]) + (ih % k[1]) * k[2] + (iw % k[2])
+        codes.append((pos | ((h > 0).long() << 3)).to(torch.uint8))
+    return codes

@@ -12,7 +12,8 @@ from video_distillation_b200.tc import TcConvNet3D  # noqa: E402
 B, T, HW = 592, 16, 112
 torch.manual_seed(0)
 net = ConvNet3D(3, 50, 128, 3, 'relu', 'none', 'maxpooling', T, (HW, HW)).cuda()
-tc = TcConvNet3D(T, HW, HW, 'cuda', max_batch=B)
+SPLIT = len(sys.argv) > 1 and sys.argv[1] == 'x3'
+tc = TcConvNet3D(T, HW, HW, 'cuda', max_batch=B, split=SPLIT)
 f = net.features
 tc.load_weights(f[0].weight, f[0].bias, f[3].weight, f[3].bias, f[6].weight, f[6].bias)
 video = torch.randn(64, T, 3, HW, HW, device='cuda')

@@ -55,6 +55,7 @@ class TcConvNet3D:
         self.w1 = torch.empty(wb[1], **u8)
         self.w2 = torch.empty(wb[2], **u8)
         self._trio = None
+        self.codes_override = None   # (c0, c1, c2): embed_backward uses these ReLU / MaxPool routing codes instead of its own
         self.wt0 = torch.empty(p.wt0_bytes, **u8)       # transposed images for the backward column GEMMs
         self.wt1 = torch.empty(p.wt1_bytes, **u8)
         self.wt2 = torch.empty(p.wt2_bytes, **u8)
@@ -113,6 +114,8 @@ class TcConvNet3D:
     def embed_backward(self, g_emb, codes):
         """Gradient of ``embed`` w.r.t. its input videos for the routing recorded in ``codes``
         (weights frozen): three column GEMMs on tensor cores + col2im/routing gathers."""
+        if self.codes_override is not None:
+            codes = self.codes_override           # routing-conditioned parity (tests): backward along a GIVEN routing
         if self.split:
             return self._embed_backward_split(g_emb, codes)
         self._prepare_bwd()
