@@ -42,6 +42,9 @@ C, T, HW, VPC, SPC, DPC, BATCH_REAL, PER_CLASS = 50, 16, 112, 1, 2, 2, 64, 72
 F_L0, F_L1, F_L2 = 2.832e9, 7.553e9, 0.617e9          # algorithmic FLOP per video
 MEAN, STD = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]     # dataset normalisation (utils.py:214-230)
 F_EMBED = F_L0 + F_L1 + F_L2
+# learning rates of both arms (script arguments L_D / L_H of the reference's sh/s2d/s2d_DM_ms.sh): small enough that the memories stay
+# finite on random data over any number of bench iterations, so that `check` is a meaningful fingerprint
+LR_DYNAMIC, LR_HAL = 1.0, 1e-4
 
 
 def measured_peaks():
@@ -150,8 +153,8 @@ class ReferenceLoop:
         self.static_syn = torch.randn(size=(C * SPC, 3, HW, HW), dtype=torch.float).detach().to(device).requires_grad_(False)
         self.dynamic_syn = torch.randn(size=(C, DPC, T, 1, HW, HW), dtype=torch.float).detach().to(device).requires_grad_(True)
         self.hals = torch.nn.ModuleList([ref_utils.Conv3DNet()]).to(device)
-        self.optimizer_dynamic = torch.optim.SGD([self.dynamic_syn], lr=1e4, momentum=0.95)
-        self.optimizer_hals = torch.optim.SGD(self.hals.parameters(), lr=1e-2, momentum=0.95)
+        self.optimizer_dynamic = torch.optim.SGD([self.dynamic_syn], lr=LR_DYNAMIC, momentum=0.95)
+        self.optimizer_hals = torch.optim.SGD(self.hals.parameters(), lr=LR_HAL, momentum=0.95)
 
     def get_images(self, c, n):                                                      # distill_s2d_ms.py:81-87
         idx_shuffle = np.random.permutation(self.indices_class[c])[:n]
@@ -429,7 +432,7 @@ def run_ours(args):
     def make_trainer(precision, dataset):
         torch.manual_seed(0)
         return DMS2DTrainer(dataset, num_classes=C, im_size=(HW, HW), frames=T, vpc=VPC, spc=SPC, dpc=DPC, batch_real=BATCH_REAL,
-                            lr_dynamic=1e4, lr_hal=1e-2, precision=precision, device=dev, init_on_device=True,
+                            lr_dynamic=LR_DYNAMIC, lr_hal=LR_HAL, precision=precision, device=dev, init_on_device=True,
                             max_batch=args.max_batch,
                             syn_on_tensor_cores={'fused': True, 'split': 'split', 'fp32': False}[args.syn_mode])
     tr = make_trainer(args.precision, ds)
@@ -501,7 +504,8 @@ def run_ours(args):
     dsyn = tr.dynamic_syn.detach().double()
     check = {'iterations': args.warmup + args.steps, 'loss_last': float(last_loss[0]),
              'dynamic_syn_sum': float(dsyn.sum()), 'dynamic_syn_sumsq': float((dsyn * dsyn).sum()),
-             'hal_weight_sum': float(tr.hal.encoder.weight.detach().double().sum())}
+             'hal_weight_sum': float(tr.hal.encoder.weight.detach().double().sum()),
+             'grad_dynamic_absmax': float(tr.dynamic_syn.grad.abs().max()), 'lr_dynamic': LR_DYNAMIC, 'lr_hal': LR_HAL}
     del dsyn
 
     # ---- e2e: the step's real videos come from pinned host memory as normalised fp32 (the reference's TensorDataset,

@@ -3,9 +3,6 @@ B200 kernels (the DC method is outside the hot path)."""
 from video_distillation_b200.cli import main_baseline as main, baseline_parser
 
 if __name__ == '__main__':
-    import torch.distributed as dist
-    import os
-    if int(os.environ.get('WORLD_SIZE', '1')) > 1:
-        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        dist.init_process_group('nccl')
+    from video_distillation_b200.cli import init_distributed
+    init_distributed()
     main(baseline_parser().parse_args())

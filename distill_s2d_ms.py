@@ -4,9 +4,6 @@ B200 kernels.  `python distill_s2d_ms.py --method DM --dataset miniUCF101-synthe
 from video_distillation_b200.cli import main_s2d as main, s2d_parser
 
 if __name__ == '__main__':
-    import torch.distributed as dist
-    import os
-    if int(os.environ.get('WORLD_SIZE', '1')) > 1:
-        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        dist.init_process_group('nccl')
+    from video_distillation_b200.cli import init_distributed
+    init_distributed()
     main(s2d_parser().parse_args())

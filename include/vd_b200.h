@@ -296,26 +296,6 @@ int vd_tc_pack_dgrad0_weights(const float* w_l0, void* wimg, void* stream);
 int vd_tc_pack_dyp0(const float* gy, void* dyp, const vd_tc_plan* plan, int B, void* stream);
 int vd_tc_dgrad0(const void* dyp0, const void* wimg, float* out, const vd_tc_plan* plan, int B, int ncdhw, void* stream);
 
-/* Tuning probe (tests/bring-up only): issues 148 x n_sa x n_steps x n_acc MMAs of N=ncols with the
- * given descriptor words over dummy operands (pix >= 64 KiB, wimg >= 16 KiB, raw >= 148*n_acc*128*ncols
- * floats) so that the MMA rate of a shared-memory layout can be timed with CUDA events. */
-int vd_tc_probe(const void* pix, const void* wimg, float* raw, int ncols, int n_sa, int n_steps,
-                uint32_t a_lbo16, uint32_t a_hi, uint32_t b_lbo16, uint32_t b_hi, uint32_t b_step16,
-                int n_acc, void* stream);
-
-/* Hardware-floor probe: `grid` CTAs each issue iters x n_acc MMAs (M=128, N=ncols, K=16) from constant
- * descriptors; out[2*cta] = issue cycles, out[2*cta+1] = cycles until all MMAs completed. */
-int vd_tc_mma_rate(long long* out, int n_acc, int ncols, int iters, uint32_t a_hi, uint32_t b_hi, uint32_t lbo16,
-                   int vary, int grid, int delay, void* stream);
-/* Bring-up probe: tcgen05.mma rate with moving A tiles / B windows (operand-fetch cost), not on the product path. */
-int vd_tc_mma_rate2(long long* out, int n_acc, int ncols, int iters, uint32_t a_hi, uint32_t a_lbo16, uint32_t a_step16,
-                    int a_n, uint32_t b_hi, uint32_t b_lbo16, uint32_t b_step16, int b_n, uint32_t b_base16, int group,
-                    int same_acc, uint32_t fill, int group_delay, int grid, void* stream);   /* delay: emulated scalar cycles per step */
-
-/* Tuning aid: device buffer (148*8 int64) receiving per-CTA cycle counters of the MMA warp of the forward
- * conv launches: [total, wait acc_empty, wait pix_full, wait w_full, issue]; NULL disables. */
-int vd_tc_set_profile_buffer(long long* buf);
-
 /* Host-only introspection (no GPU work): the launch parameters vd_tc_conv_layer would use,
  * flattened to int64 (layout documented in tests/tc_emulator.py); cap >= 248. */
 int vd_tc_debug_params(int layer, const vd_tc_plan* plan, int B, int64_t* out, int cap);   /* layer 3,4,5 = bwd gemm of conv 0,1,2; 6,7,8 = split-fp16 conv 0,1,2 */

@@ -7,6 +7,9 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from _probe_lib import use_probe_library  # noqa: E402
+use_probe_library()               # probe entry points live in scripts/libvd_b200_probe.so, not in the product library
 from video_distillation_b200 import _lib  # noqa: E402
 
 lib = _lib.lib()

@@ -102,8 +102,8 @@ def stream_groups(L, cta):
 
 
 def l0s_groups(L, cta):
-    """tc_conv.cu `next_l0s` (split-fp16 conv 0): stage (frame i, part) feeds output frames i + 1 - kt (kt = 2, 1, 0);
-    frame f of the running count lives in accumulator buffer (qbase + f) & 3."""
+    """tc_conv.cu `next_l0s` (split-fp16 conv 0): ONE group per stage (frame i, part) with up to three segments, kt = 2, 1, 0 ->
+    output frame i + 1 - kt; frame f of the running count lives in accumulator buffer (qbase + f) & 3."""
     pslot = pphase = 0
     qbase = 0
     T = L.stream_pairs
@@ -111,21 +111,37 @@ def l0s_groups(L, cta):
     while tile < L.n_tiles:
         for ss in range(2 * T):
             i, part = divmod(ss, 2)
-            kts = [kt for kt in (2, 1, 0) if 0 <= i + 1 - kt < T]
-            for kt in kts:
+            segs, w_accs, c_accs = [], [], []
+            for kt in (2, 1, 0):
                 f = i + 1 - kt
+                if not (0 <= f < T):
+                    continue
                 q = qbase + f
                 buf = q & 3
                 first_write = part == 0 and (kt == 0 or (f == 0 and kt == 1))
                 final_write = part == 1 and (kt == 2 or (f == T - 1 and kt == 1))
-                yield dict(w_acc=('acc_empty', buf, ((q >> 2) & 1) ^ 1) if first_write else None, w_pix=('pix_full', pslot, pphase),
-                           w_w=None, acc=buf, first=first_write, pix=pslot, wt=None, c_w=None,
-                           c_pix=('pix_empty', pslot) if kt == kts[-1] else None, c_acc=('acc_full', buf) if final_write else None)
+                segs.append((buf, first_write))
+                if first_write:
+                    w_accs.append(('acc_empty', buf, ((q >> 2) & 1) ^ 1))
+                if final_write:
+                    c_accs.append(('acc_full', buf))
+            assert len(w_accs) <= 2 and len(c_accs) <= 2
+            yield dict(w_acc=w_accs, w_pix=('pix_full', pslot, pphase), w_w=None, segs=segs, pix=pslot, wt=None, c_w=None,
+                       c_pix=('pix_empty', pslot), c_acc=c_accs, nmma=len(segs))
             pslot += 1
             if pslot == L.RP:
                 pslot, pphase = 0, pphase ^ 1
         qbase += T
         tile += L.grid
+
+
+def _norm(g):
+    """Group records of the single-accumulator generators in the multi-segment form used by simulate()."""
+    if 'segs' not in g:
+        g['segs'] = [(g['acc'], g['first'])]
+        g['w_acc'] = [g['w_acc']] if g['w_acc'] is not None else []
+        g['c_acc'] = [g['c_acc']] if g['c_acc'] is not None else []
+    return g
 
 
 def simulate(L, cta=0, mma_latency=3):
@@ -137,7 +153,7 @@ def simulate(L, cta=0, mma_latency=3):
     bars.update({('acc_full', i): Barrier(2) for i in range(L.acc_stages)})
     bars.update({('acc_empty', i): Barrier(1) for i in range(L.acc_stages)})      # the 4 epilogue warps modelled as one actor
     bars.update({('baton', i): Barrier(1) for i in range(2)})
-    groups = list((l0s_groups if L.stream_mode == 2 else stream_groups if L.stream_pairs else classic_groups)(L, cta))
+    groups = [_norm(g) for g in (l0s_groups if L.stream_mode == 2 else stream_groups if L.stream_pairs else classic_groups)(L, cta)]
     pipe = deque()                       # in-flight groups: [remaining time, group index, issuer]
     issued_by = [-1, -1]                 # index of the last group each issuer put into the pipe
     done = -1                            # index of the last completed group
@@ -177,16 +193,17 @@ def simulate(L, cta=0, mma_latency=3):
     def issuer(role):
         for k, g in enumerate(groups):
             if (k & 1) == role:
-                for w in (g['w_acc'], g['w_pix'], g['w_w']):
+                for w in g['w_acc'] + [g['w_pix'], g['w_w']]:
                     if w is not None:
                         yield from wait(w)
                 if k > 0:
                     yield from wait(('baton', role ^ 1, ((k - 1) >> 1) & 1))
-                if g['first']:
-                    assert acc_state[g['acc']] == 'free', 'accumulator re-initialised before the epilogue drained it'
-                    acc_state[g['acc']] = 'accumulating'
-                else:
-                    assert acc_state[g['acc']] == 'accumulating', 'accumulate into an accumulator that was not initialised'
+                for acc, first in g['segs']:
+                    if first:
+                        assert acc_state[acc] == 'free', 'accumulator re-initialised before the epilogue drained it'
+                        acc_state[acc] = 'accumulating'
+                    else:
+                        assert acc_state[acc] == 'accumulating', 'accumulate into an accumulator that was not initialised'
                 order.append(k)
                 pipe.append([mma_latency, k, role])
                 issued_by[role] = k
@@ -196,26 +213,28 @@ def simulate(L, cta=0, mma_latency=3):
                 bars[('baton', role)].arrive()
                 if g['c_w']:
                     pending_commits.append((role, issued_by[role], g['c_w']))
-            for c in (g['c_pix'], g['c_acc']):           # both issuers commit: "MY MMAs up to here have completed"
+            for c in [g['c_pix']] + g['c_acc']:          # both issuers commit: "MY MMAs up to here have completed"
                 if c:
                     pending_commits.append((role, issued_by[role], c))
             yield
 
     def epilogue():
         as_ = aphase = 0
-        for g in groups:
-            if not g['c_acc']:
-                continue
-            yield from wait(('acc_full', as_, aphase))
-            assert g['acc'] == as_, 'epilogue and issuers disagree on the accumulator stage'
-            assert acc_state[as_] == 'accumulating' and all(groups[k]['acc'] != as_ for _, k, _ in pipe), \
-                'epilogue drains an accumulator with MMAs in flight'
-            acc_state[as_] = 'free'
-            yield                                          # drain time
-            bars[('acc_empty', as_)].arrive()
-            as_ += 1
-            if as_ == L.acc_stages:
-                as_, aphase = 0, aphase ^ 1
+        for gi, g in enumerate(groups):
+            for c in g['c_acc']:
+                yield from wait(('acc_full', as_, aphase))
+                assert c[1] == as_, 'epilogue and issuers disagree on the accumulator stage'
+                # MMAs of LATER groups may already be in flight into other accumulators; none may touch this one
+                assert acc_state[as_] == 'accumulating' and all(k > gi or all(a != as_ for a, _ in groups[k]['segs']) for _, k, _ in pipe) \
+                    and all(k > gi or True for _, k, _ in pipe), 'epilogue drains an accumulator with MMAs in flight'
+                assert not any(k <= gi and any(a == as_ for a, _ in groups[k]['segs']) for _, k, _ in pipe), \
+                    'epilogue drains an accumulator with MMAs in flight'
+                acc_state[as_] = 'free'
+                yield                                          # drain time
+                bars[('acc_empty', as_)].arrive()
+                as_ += 1
+                if as_ == L.acc_stages:
+                    as_, aphase = 0, aphase ^ 1
 
     actors = [pixel_loader(), weight_loader(), issuer(0), issuer(1), epilogue()]
     alive = [True] * len(actors)

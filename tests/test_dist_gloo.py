@@ -157,3 +157,51 @@ def test_batch_sharded_mtt_equals_single_rank(tmp_path):
     assert rel(got[0], r['grad_dynamic']) < 1e-4, rel(got[0], r['grad_dynamic'])
     assert rel(got[1], r['grad_hal_weight']) < 1e-4 and rel(got[2], r['grad_hal_bias']) < 1e-4
     assert rel(got[3], r['grad_syn_lr']) < 1e-4
+
+
+# ------------------------------------------------------------------ driver-level replica consistency (cli.py)
+def _seed_worker(rank, world, port, out):
+    """Two entropy-seeded processes follow the driver's protocol (cli.main_s2d): shared base seed, broadcast of the initial
+    state, rank-0-only work that consumes random numbers (the evaluation block), per-iteration re-seeding.  Everything a rank
+    draws afterwards — memories, expert walk, per-iteration indices — must be identical on both ranks."""
+    import random
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from video_distillation_b200 import cli
+    # processes start with different entropy, like two fresh torchrun workers
+    torch.manual_seed(1234 + 99 * rank)
+    np.random.seed(77 + rank)
+    random.seed(5 + rank)
+    base = cli._shared_seed(world, torch.device('cpu'))
+    cli._seed_all(base)
+    static_syn = torch.randn(6, 3, 8, 8)
+    perm = np.random.permutation(20)
+    shuffled = list(range(10))
+    random.shuffle(shuffled)
+    state = [static_syn + (0.0 if rank == 0 else 0.0)]
+    cli._broadcast_state(state, world)
+    draws = []
+    for it in range(3):
+        if rank == 0 and it in (0, 2):                  # "evaluation": only rank 0 consumes its generators
+            torch.randn(100 + it)
+            np.random.rand(7)
+            random.random()
+        cli._barrier(world)
+        cli._seed_all(base + 7919 * (it + 1))
+        draws.append((torch.randperm(12).tolist(), int(torch.randint(2, (1,))), int(np.random.randint(0, 50)), random.random()))
+    out[rank] = dict(base=base, static=static_syn, perm=perm.tolist(), shuffled=shuffled, draws=draws,
+                     agree=cli._replicas_agree(state, world))
+    dist.destroy_process_group()
+
+
+def test_driver_replicas_share_seed_and_stay_aligned():
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_seed_worker, args=(world, port, out), nprocs=world, join=True)
+    a, b = out[0], out[1]
+    assert a['base'] == b['base']
+    assert torch.equal(a['static'], b['static']) and a['perm'] == b['perm'] and a['shuffled'] == b['shuffled']
+    assert a['draws'] == b['draws']
+    assert a['agree'] == 0.0 and b['agree'] == 0.0

@@ -51,11 +51,11 @@ def test_conv0_streaming_generator(pairs, n_tiles, grid, cta, RP):
 @pytest.mark.parametrize('n_tiles,grid,cta', [(1, 1, 0), (4, 2, 1), (5, 3, 0), (2, 148, 1)])
 @pytest.mark.parametrize('RP', [2, 3, 4])
 def test_split_conv0_generator(T, n_tiles, grid, cta, RP):
-    # split-fp16 conv 0: 2T stages (frame, part), 4 rotating accumulators (output frames), 3T - 2 groups per part
+    # split-fp16 conv 0: 2T stages (frame, part) = one MMA group each, 4 rotating accumulators (output frames)
     L = Launch(n_tiles, grid, T, 2, 11, 1, RP, 1, 4, True, stream_pairs=T, stream_mode=2)
     columns = len(range(cta, n_tiles, grid))
     for latency in (1, 3, 11):
-        assert simulate(L, cta, mma_latency=latency) == columns * 2 * (3 * T - 2)
+        assert simulate(L, cta, mma_latency=latency) == columns * 2 * T
 
 
 @pytest.mark.parametrize('latency', [1, 2, 5, 17])

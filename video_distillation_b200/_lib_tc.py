@@ -1,5 +1,5 @@
 """ctypes signatures of the tensor-core entry points (include/vd_b200.h, second half)."""
-from ctypes import POINTER, c_int, c_int64, c_uint32, c_void_p
+from ctypes import POINTER, c_int, c_int64, c_void_p
 
 
 def declare(lib):
@@ -40,11 +40,6 @@ def declare(lib):
         'vd_tc_pack_dgrad0_weights': (c_int, [P, P, P]),
         'vd_tc_pack_dyp0': (c_int, [P, P, POINTER(TcPlan), c_int, P]),
         'vd_tc_dgrad0': (c_int, [P, P, P, POINTER(TcPlan), c_int, c_int, P]),
-        'vd_tc_probe': (c_int, [P, P, P, c_int, c_int, c_int, c_uint32, c_uint32, c_uint32, c_uint32, c_uint32, c_int, P]),
-        'vd_tc_mma_rate': (c_int, [P, c_int, c_int, c_int, c_uint32, c_uint32, c_uint32, c_int, c_int, c_int, P]),
-        'vd_tc_mma_rate2': (c_int, [P, c_int, c_int, c_int, c_uint32, c_uint32, c_uint32, c_int, c_uint32, c_uint32, c_uint32, c_int,
-                            c_uint32, c_int, c_int, c_uint32, c_int, c_int, P]),
-        'vd_tc_set_profile_buffer': (c_int, [P]),
         'vd_tc_debug_params': (c_int, [c_int, POINTER(TcPlan), c_int, POINTER(c_int64), c_int]),
     }
     for name, (res, args) in sig.items():

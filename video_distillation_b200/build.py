@@ -12,7 +12,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libvd_b200.so')
-SOURCES = ['api.cu', 'simt_conv.cu', 'pointwise.cu', 'compose_tiled.cu', 'tc_conv.cu', 'tc_pack.cu', 'tc_bwd.cu', 'tc_trio.cu', 'tc_probe.cu']
+SOURCES = ['api.cu', 'simt_conv.cu', 'pointwise.cu', 'compose_tiled.cu', 'tc_conv.cu', 'tc_pack.cu', 'tc_bwd.cu', 'tc_trio.cu']
+PROBE_SOURCES = SOURCES + ['tc_probe.cu']      # + -DVD_PROBE: scripts/libvd_b200_probe.so (tuning tools only, see scripts/_probe_lib.py)
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
          '-Xcompiler', '-fPIC']
@@ -50,6 +51,33 @@ def build(force=False, verbose=False):
     if r.returncode != 0:
         raise RuntimeError('link failed:\n' + r.stdout)
     return LIB
+
+
+def build_probe(out_path, verbose=False):
+    """The same sources + csrc/tc_probe.cu compiled with -DVD_PROBE into `out_path`: the tuning / bring-up entry points
+    (vd_tc_probe, vd_tc_mma_rate*, vd_tc_set_profile_buffer) live ONLY there."""
+    srcs = [os.path.join(CSRC, s) for s in PROBE_SOURCES]
+    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cuh', '.h'))]
+    if os.path.exists(out_path) and not any(_newer(d, out_path) for d in deps):
+        return out_path
+    bdir = os.path.join(HERE, 'build', 'probe')
+    os.makedirs(bdir, exist_ok=True)
+    procs, objs = [], []
+    for s in srcs:
+        o = os.path.join(bdir, os.path.basename(s) + '.o')
+        objs.append(o)
+        procs.append((s, subprocess.Popen([NVCC] + FLAGS + ['-DVD_PROBE', '-c', s, '-o', o], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for s, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError(f'nvcc failed on {s}:\n{out}')
+        if verbose:
+            sys.stderr.write(out)
+    r = subprocess.run([NVCC, '-shared', '-o', out_path] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a', '-cudart', 'static'],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError('link failed:\n' + r.stdout)
+    return out_path
 
 
 if __name__ == '__main__':

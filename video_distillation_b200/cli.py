@@ -10,7 +10,12 @@ Same flags, defaults, evaluation / checkpoint cadence and file formats (``images
 ``distill.py`` on the hand-written kernels, one process per GPU (launch with torchrun to shard classes across GPUs;
 rank 0 evaluates and saves).  Not reproduced: wandb logging (plain prints; ``wandb.run.name`` in the save path becomes
 ``--run_name``), the DC method and DSA / ZCA options (off the hot path).  Two optional flags are added:
-``--precision`` (bf16 tensor-core path | fp32 exact path) and ``--run_name``.
+``--precision`` (f16x3 parity mode of the tensor-core path | bf16 throughput mode | fp32 exact CUDA-core path) and ``--run_name``.
+
+Multi-process runs (torchrun): ``init_distributed`` creates the process group with a long timeout; all ranks share one base
+seed (rank 0's, broadcast), the initial memories are broadcast from rank 0, every iteration re-seeds all RNG streams from
+(base seed, iteration) — rank 0 alone consumes random numbers while it evaluates — and the ranks meet at a barrier after each
+evaluation block, so the replicas of the synthetic memories stay identical.
 """
 import argparse
 import copy
@@ -30,8 +35,9 @@ from .utils import (Conv3DNet, MultiStaticSharedDataset, epoch, evaluate_synset,
 
 # ------------------------------------------------------------------------------------------ parsers
 def _extra(parser):
-    parser.add_argument('--precision', type=str, default='bf16', choices=['bf16', 'fp32', 'bf16x3'],
-                        help='[B200] tensor-core path (bf16 operands, fp32 accumulate) or the exact fp32 CUDA-core path')
+    parser.add_argument('--precision', type=str, default='f16x3', choices=['f16x3', 'bf16', 'fp32', 'bf16x3'],
+                        help='[B200] f16x3: fused tensor-core pipeline on fp16 hi/lo operand pairs (parity mode, default); bf16: single-pass '
+                             'throughput mode; fp32: exact CUDA-core kernels; bf16x3: unfused split-bf16 conv trio')
     parser.add_argument('--run_name', type=str, default=None, help='[B200] directory name under save_path/<project> (wandb.run.name in the reference)')
     return parser
 
@@ -164,6 +170,71 @@ def _require_cuda():
     return torch.device('cuda', local), rank, world
 
 
+def init_distributed():
+    """torchrun entry: NCCL process group with a LONG timeout — rank 0 alone runs the evaluation blocks (num_eval networks x
+    epoch_eval_train epochs) while the other ranks wait at the barrier behind them, far longer than NCCL's default 10 minutes."""
+    import torch.distributed as dist
+    if int(os.environ.get('WORLD_SIZE', '1')) > 1 and not dist.is_initialized():
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        local = int(os.environ.get('LOCAL_RANK', '0'))
+        backend = 'nccl' if torch.cuda.is_available() else 'gloo'
+        kw = dict(device_id=torch.device('cuda', local)) if backend == 'nccl' else {}
+        dist.init_process_group(backend, timeout=datetime.timedelta(hours=24), **kw)
+
+
+def _seed_all(seed):
+    seed = int(seed) % (2 ** 31 - 1)
+    random.seed(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed_all(seed)
+
+
+def _shared_seed(world, dev):
+    """One base seed for ALL ranks (drawn on rank 0 from its entropy-seeded generator, broadcast): every rank must draw the
+    same static / dynamic memories, hallucinator, init='real' videos, expert trajectories and per-iteration indices — the
+    trainers only shard the WORK of an iteration, every rank applies the full update to its replica.  Single process: None
+    (the RNG streams stay exactly the reference's)."""
+    if world == 1:
+        return None
+    import torch.distributed as dist
+    t = torch.randint(0, 2 ** 31 - 1, (1,), dtype=torch.int64)
+    t = t.to(dev) if dist.get_backend() == 'nccl' else t
+    dist.broadcast(t, src=0)
+    return int(t.item())
+
+
+def _broadcast_state(tensors, world):
+    """Rank 0's initial values become everybody's (belt and braces on top of the shared seed)."""
+    if world == 1:
+        return
+    import torch.distributed as dist
+    for t in tensors:
+        dist.broadcast(t.data, src=0)
+
+
+def _replicas_agree(tensors, world):
+    """max |x_rank - x_0| over the given tensors and all ranks (diagnostic; 0.0 for a single process)."""
+    if world == 1:
+        return 0.0
+    import torch.distributed as dist
+    worst = 0.0
+    for t in tensors:
+        ref = t.detach().clone()
+        dist.broadcast(ref, src=0)
+        d = (t.detach() - ref).abs().max().reshape(1).float()
+        dist.all_reduce(d, op=dist.ReduceOp.MAX)
+        worst = max(worst, float(d.item()))
+    return worst
+
+
+def _barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+
+
 def _tensors_of(dst):
     """(videos, labels) of a dataset object: TensorDataset members, or one pass over __getitem__ (what --preload does,
     distill_s2d_ms.py:28-38)."""
@@ -178,7 +249,7 @@ def _tensors_of(dst):
 
 
 def _eval_precision(args):
-    return 'bf16' if args.precision in ('bf16', 'bf16x3') else 'fp32'
+    return 'bf16' if args.precision in ('bf16', 'bf16x3', 'f16x3') else 'fp32'
 
 
 class ExpertBuffers:
@@ -248,7 +319,7 @@ def main_s2d(args):
     print('Evaluation iterations: ', eval_it_pool)
     channel, im_size, num_classes, class_names, mean, std, dst_train, dst_test, testloader = get_dataset(args.dataset, args.data_path)
     model_eval_pool = get_eval_pool(args.eval_mode, args.model, args.model)
-    project_name = 'S2D_{}'.format(args.method)
+    project_name = 'S2D_multis_{}'.format(args.method)          # distill_s2d_ms.py:47
     run_name = args.run_name or f'{args.dataset}_vpc{args.vpc}_{datetime.datetime.now().strftime("%Y%m%d%H%M%S")}'
     if args.batch_syn is None:
         args.batch_syn = num_classes * args.vpc
@@ -257,6 +328,9 @@ def main_s2d(args):
     print('Evaluation model pool: ', model_eval_pool)
     if args.n_hal != 1:
         raise NotImplementedError('the reference only ever applies hals[0] (distill_s2d_ms.py:412); n_hal must be 1')
+    base_seed = _shared_seed(world, dev)
+    if base_seed is not None:
+        _seed_all(base_seed)
 
     static_syn = torch.randn(size=(num_classes * args.spc, 3, im_size[0], im_size[1]), dtype=torch.float)
     dynamic_syn = torch.randn(size=(num_classes, args.dpc, args.frames, 1, im_size[0], im_size[1]), dtype=torch.float)
@@ -280,11 +354,13 @@ def main_s2d(args):
         videos, labels = _tensors_of(dst_train)
         ds = DeviceDataset(videos, labels, num_classes, dev, rank, world)
         prec = args.precision
-        tr = DMS2DTrainer(ds, batch_real=args.batch_real, precision=prec, max_batch=640 if prec == 'bf16' else 128, **common)
+        tr = DMS2DTrainer(ds, batch_real=args.batch_real, precision=prec, max_batch=640 if prec in ('bf16', 'f16x3') else 128, **common)
         if tr.embedder.tc is not None:
             ds.prepack(tr.embedder.tc, extra_slots=len(tr.owned) * tr.vpc)
     else:
         raise NotImplementedError('Method {} not implemented'.format(args.method))
+
+    _broadcast_state([tr.static_syn, tr.dynamic_syn, *tr.hal.parameters()] + ([tr.syn_lr] if args.method == 'MTT' else []), world)
 
     def payload():
         return [copy.deepcopy(tr.static_syn.detach()), copy.deepcopy(tr.dynamic_syn.detach()), nn.ModuleList([copy.deepcopy(tr.hal)])], None
@@ -314,9 +390,13 @@ def main_s2d(args):
                         torch.save(image_save.cpu(), os.path.join(save_dir, 'images_best.pt'))
                     torch.save(hals_state(), os.path.join(save_dir, 'weights_best.pt'))
                     torch.save(dynamic_save.cpu(), os.path.join(save_dir, 'dynamic_best.pt'))
+        if base_seed is not None:
+            if it in eval_it_pool:
+                _barrier(world)                       # the other ranks wait here while rank 0 evaluates / saves
+            _seed_all(base_seed + 7919 * (it + 1))    # rank 0's evaluation consumed RNG: realign every stream, every iteration
         if args.method == 'MTT':
             start, target, start_epoch = experts.draw()
-            grand_loss = tr.step(start, target)
+            grand_loss = tr.step(start, target, net_seed=None if world == 1 else 1000003 + it)
             if it % 10 == 0:
                 print('%s iter = %04d, param_loss = %.4f, param_dist = %.4f, grand_loss = %.4f (start epoch %d)' % (
                     get_time(), it, tr.last['param_loss'].item(), tr.last['param_dist'].item(), grand_loss.item(), start_epoch))
@@ -347,6 +427,9 @@ def main_baseline(args):
         args.batch_syn = num_classes * args.ipc
     args.distributed = world > 1
     print('Hyper-parameters: \n', args.__dict__)
+    base_seed = _shared_seed(world, dev)
+    if base_seed is not None:
+        _seed_all(base_seed)
     videos, labels = _tensors_of(dst_train)
     ds = DeviceDataset(videos, labels, num_classes, dev, rank, world)
     image_syn = torch.randn(size=(num_classes * args.ipc, args.frames, channel, im_size[0], im_size[1]), dtype=torch.float)
@@ -370,11 +453,13 @@ def main_baseline(args):
         prec = args.precision
         tr = DMBaselineTrainer(ds, num_classes=num_classes, channel=channel, im_size=im_size, frames=args.frames, ipc=args.ipc,
                                batch_real=args.batch_real, lr_img=args.lr_img, precision=prec, image_syn=image_syn,
-                               max_batch=640 if prec == 'bf16' else 128, device=dev)
+                               max_batch=640 if prec in ('bf16', 'f16x3') else 128, device=dev)
     else:
         raise NotImplementedError('Method {} not implemented (DC is outside the B200 hot path)'.format(args.method))
     label_syn = torch.tensor(np.stack([np.ones(args.ipc) * i for i in range(0, num_classes)]), dtype=torch.long,
                              requires_grad=False, device=dev).view(-1)
+
+    _broadcast_state([tr.image_syn] + ([tr.syn_lr] if args.method == 'MTT' else []), world)
 
     def payload():
         return tr.image_syn.detach().clone(), label_syn.detach().clone()
@@ -385,7 +470,7 @@ def main_baseline(args):
             if args.method == 'MTT':
                 args.lr_net = tr.syn_lr.detach()
             save_this_it = _evaluate(args, it, model_eval_pool, channel, num_classes, im_size, payload, testloader, 'none',
-                                     best_acc, best_std, test_freq=100 if args.method == 'DM' else None)
+                                     best_acc, best_std, test_freq=100 if args.method == 'DM' else 200)     # distill_baseline.py:304 / :158
         if it in eval_it_pool and (save_this_it or it % 1000 == 0) and rank == 0:
             save_dir = os.path.join(args.save_path, project_name, run_name)
             os.makedirs(save_dir, exist_ok=True)
@@ -393,9 +478,13 @@ def main_baseline(args):
             torch.save(image_save.cpu(), os.path.join(save_dir, 'images_{}.pt'.format(it)))
             if save_this_it:
                 torch.save(image_save.cpu(), os.path.join(save_dir, 'images_best.pt'))
+        if base_seed is not None:
+            if it in eval_it_pool:
+                _barrier(world)
+            _seed_all(base_seed + 7919 * (it + 1))
         if args.method == 'MTT':
             start, target, start_epoch = experts.draw()
-            grand_loss = tr.step(start, target)
+            grand_loss = tr.step(start, target, net_seed=None if world == 1 else 1000003 + it)
             if it % 10 == 0:
                 print('%s iter = %04d, grand_loss = %.4f (start epoch %d)' % (get_time(), it, grand_loss.item(), start_epoch))
         else:
@@ -412,7 +501,7 @@ def main_buffer(args):
     dev, rank, world = _require_cuda()
     args.device = str(dev)
     channel, im_size, num_classes, class_names, mean, std, dst_train, dst_test, testloader = get_dataset(
-        args.dataset, args.data_path, batch_size=args.batch_train)
+        args.dataset, args.data_path)
     save_dir = args.buffer_path
     os.makedirs(save_dir, exist_ok=True)
     criterion = nn.CrossEntropyLoss().to(args.device)
@@ -473,8 +562,8 @@ def main_coreset(args):
         print('Loading pretrained model')
         net.load_state_dict(torch.load(args.pretrained_path))
     net.eval()
-    if args.precision == 'bf16' and tc_supported(args.frames, im_size[0], im_size[1]):
-        tc = TcConvNet3D(args.frames, im_size[0], im_size[1], dev, max_batch=256)
+    if args.precision in ('bf16', 'f16x3') and tc_supported(args.frames, im_size[0], im_size[1]):
+        tc = TcConvNet3D(args.frames, im_size[0], im_size[1], dev, max_batch=256, split=(args.precision == 'f16x3'))
         f = net.features
         tc.load_weights(f[0].weight, f[0].bias, f[3].weight, f[3].bias, f[6].weight, f[6].bias)
         embed = tc.embed

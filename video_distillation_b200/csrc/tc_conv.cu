@@ -876,6 +876,14 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
                 const uint64_t* tb;
                 int nst;
                 uint32_t d_base, acc0;
+                // split-fp16 conv 0 only: up to two more (weight window, accumulator) segments issued in the same group over the
+                // same pixel stage, a second accumulator to wait for and a second accumulator to commit
+                // (scalar fields on purpose: arrays indexed at run time would move the whole record to local memory)
+                int nseg;
+                const uint64_t* ta_b;
+                const uint64_t* ta_c;
+                uint32_t d_b, d_c, acc0_b, acc0_c;
+                uint32_t w_acc2, p_acc2, c_acc2;
             };
             const int slots_per_stage = (n_steps + G - 1) / G;
             const int n_tiles = p.n_tiles, n_sb = p.n_sb;
@@ -954,31 +962,41 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
             // (i = f - 1, hi part, kt = 0) — for f = 0: (i = 0, hi, kt = 1) — and its last (i = f + 1, lo part, kt = 2) — for
             // f = T - 1: (i = T - 1, lo, kt = 1).
             const int smode = p.stream_mode;
-            int ss = 0, sgi = 0;
+            int ss = 0;
             auto next_l0s = [&](Group& r) {
+                // ONE group per stage (up to 3 x n_steps MMAs): a hand-over between the two issuers costs ~300 cycles, more than the
+                // two queued N = 112 MMAs (2 x 56 cycles) hide, so groups of 11 short MMAs left the pipe 38 % idle
                 const int T = pairs;
                 const int i = ss >> 1, part = ss & 1;
-                const int kt = (i >= 1 ? 2 : 1) - sgi;
-                const int f = i + 1 - kt;
-                const int ngroups = (i >= 1 ? 1 : 0) + 1 + (i + 1 < T ? 1 : 0);
-                const bool last_of_stage = sgi == ngroups - 1;
-                const uint32_t q = qbase + (uint32_t)f;
-                const uint32_t buf = q & 3u;
-                const bool first_write = part == 0 && (kt == 0 || (f == 0 && kt == 1));
-                const bool final_write = part == 1 && (kt == 2 || (f == T - 1 && kt == 1));
-                r.w_acc = first_write ? BAR(acc_empty, buf) : 0u;        r.p_acc = ((q >> 2) & 1u) ^ 1u;
+                r.nseg = 0;
+                r.w_acc = 0u; r.w_acc2 = 0u; r.c_acc = 0u; r.c_acc2 = 0u; r.p_acc = 0u; r.p_acc2 = 0u;
+                for (int kt = 2; kt >= 0; --kt) {
+                    const int f = i + 1 - kt;
+                    if (f < 0 || f >= T) continue;
+                    const uint32_t q = qbase + (uint32_t)f;
+                    const uint32_t buf = q & 3u;
+                    const bool first_write = part == 0 && (kt == 0 || (f == 0 && kt == 1));
+                    const bool final_write = part == 1 && (kt == 2 || (f == T - 1 && kt == 1));
+                    const uint64_t* ta = tabA + kt * n_steps;
+                    const uint32_t d = tmem_base + buf * (acc_cols * (uint32_t)NACC);
+                    if (r.nseg == 0) { r.ta = ta; r.d_base = d; r.acc0 = first_write ? 0u : 1u; }
+                    else if (r.nseg == 1) { r.ta_b = ta; r.d_b = d; r.acc0_b = first_write ? 0u : 1u; }
+                    else { r.ta_c = ta; r.d_c = d; r.acc0_c = first_write ? 0u : 1u; }
+                    ++r.nseg;
+                    if (first_write) {
+                        if (!r.w_acc) { r.w_acc = BAR(acc_empty, buf); r.p_acc = ((q >> 2) & 1u) ^ 1u; }
+                        else { r.w_acc2 = BAR(acc_empty, buf); r.p_acc2 = ((q >> 2) & 1u) ^ 1u; }
+                    }
+                    if (final_write) {
+                        if (!r.c_acc) r.c_acc = BAR(acc_full, buf); else r.c_acc2 = BAR(acc_full, buf);
+                    }
+                }
                 r.w_pix = BAR(pix_full, pslot);                          r.p_pix = pphase;
                 r.w_w = 0u;                                              r.p_w = 0u;
                 r.nst = n_steps;
-                r.ta = tabA + kt * n_steps;
                 r.tb = tabB + (int)pslot * n_steps * NACC;
-                r.d_base = tmem_base + buf * (acc_cols * (uint32_t)NACC);
-                r.acc0 = first_write ? 0u : 1u;
                 r.c_w = 0u;
-                r.c_pix = last_of_stage ? BAR(pix_empty, pslot) : 0u;
-                r.c_acc = final_write ? BAR(acc_full, buf) : 0u;
-                if (!last_of_stage) { ++sgi; return; }
-                sgi = 0;
+                r.c_pix = BAR(pix_empty, pslot);
                 if (++pslot == RP) { pslot = 0; pphase ^= 1; }
                 if (++ss < 2 * T) return;
                 ss = 0; qbase += (uint32_t)T; tile += gridDim.x;
@@ -988,12 +1006,14 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
             if (RESIDENT) { mbar_wait(BAR(w_res, 0), 0); tc_fence_after(); }
             const long long c_begin = clock64();
             Group r;
+            r.nseg = 1; r.w_acc2 = 0u; r.p_acc2 = 0u; r.c_acc2 = 0u;
             for (uint32_t k = 0; tile < n_tiles; ++k) {
-                if (smode == 2) next_l0s(r); else if (pairs) next_stream(r); else next(r);
+                if (EPI == EPI_L0S) next_l0s(r); else if (pairs) next_stream(r); else next(r);
                 if ((k & 1u) == (uint32_t)role) {
                     // ---- my group: operands (usually long there), then the baton of the previous group's issuer
                     long long t0 = prof ? clock64() : 0;
                     if (r.w_acc) mbar_wait(r.w_acc, r.p_acc);   // (an already completed phase returns at once)
+                    if (EPI == EPI_L0S) { if (r.w_acc2) mbar_wait(r.w_acc2, r.p_acc2); }
                     if (prof) { const long long t1 = clock64(); c_acc += t1 - t0; t0 = t1; }
                     mbar_wait(r.w_pix, r.p_pix);
                     if (prof) { const long long t1 = clock64(); c_pix += t1 - t0; t0 = t1; }
@@ -1022,6 +1042,28 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
                                 umma_bf16(d_base + (uint32_t)a * acc_cols, a_desc, tb[jj * NACC + a], idesc, accumulate);
                             accumulate = 1;
                         }
+                        if (EPI == EPI_L0S) {                       // split-fp16 conv 0: further weight windows / accumulators, same stage
+                            if (r.nseg > 1) {
+                                const uint64_t* ta_s = r.ta_b;
+                                const uint32_t d_s = r.d_b;
+                                accumulate = r.acc0_b;
+#pragma unroll 4
+                                for (int jj = 0; jj < nst; ++jj) {
+                                    umma_bf16(d_s, ta_s[jj], tb[jj * NACC], idesc, accumulate);
+                                    accumulate = 1;
+                                }
+                            }
+                            if (r.nseg > 2) {
+                                const uint64_t* ta_s = r.ta_c;
+                                const uint32_t d_s = r.d_c;
+                                accumulate = r.acc0_c;
+#pragma unroll 4
+                                for (int jj = 0; jj < nst; ++jj) {
+                                    umma_bf16(d_s, ta_s[jj], tb[jj * NACC], idesc, accumulate);
+                                    accumulate = 1;
+                                }
+                            }
+                        }
                     }
                     mbar_arrive(BAR(baton, role));            // the other issuer may enter the pipe behind these MMAs
                     if (r.c_w) umma_commit(r.c_w);
@@ -1029,6 +1071,7 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
                 }
                 if (r.c_pix) umma_commit(r.c_pix);            // both issuers: "MY MMAs that read this stage / wrote this
                 if (r.c_acc) umma_commit(r.c_acc);            //  accumulator have completed"
+                if (EPI == EPI_L0S) { if (r.c_acc2) umma_commit(r.c_acc2); }
             }
             if (prof && role == 0) {
                 long long* o = p.prof + (int64_t)blockIdx.x * 8;
@@ -1772,6 +1815,7 @@ extern "C" int vd_tc_wgrad_gemm(int layer, const void* xcol, const void* gyimg, 
     return launch<EPI_RAW>(p, smem, (cudaStream_t)stream);
 }
 
+#ifdef VD_PROBE   // bring-up / tuning entry points: only in scripts/libvd_b200_probe.so (scripts/_probe_lib.py), never in the product library
 // Bring-up / tuning probe: MMA issue rate of one layout variant, data content irrelevant.
 //   hi words: SBO>>4 | 1<<14 | layout_type<<29 (0 none, 2 = 128B, 4 = 64B, 6 = 32B swizzle)
 // 148 tiles x n_sa stages x n_steps MMAs of N = ncols; raw accumulators go to `raw`.
@@ -1800,3 +1844,4 @@ extern "C" int vd_tc_probe(const void* pix, const void* wimg, float* raw, int nc
 // Tuning aid: when set (device buffer of grid*8 int64, may be NULL to disable), MMA issuer 0 of every forward conv
 // launch records [total, wait acc_empty, wait pix_full, wait w_full, issue, wait baton] cycles per CTA.
 extern "C" int vd_tc_set_profile_buffer(long long* buf) { g_prof = buf; return 0; }
+#endif  // VD_PROBE

@@ -44,7 +44,12 @@ def _synthetic(C, n_train, n_test, T, H, seed=0):
     return xtr, ytr, xte, yte
 
 
-def get_dataset(dataset, data_path, batch_size=256, num_workers=0):
+def get_dataset(dataset, data_path, num_workers=0, img_size=(112, 112), split_num=1, split_id=0, split_mode='mean', *,
+                test_batch_size=64):
+    """Reference argument order (utils.py:21).  ``img_size`` / ``split_*`` are accepted for call compatibility (the tensor-file
+    and synthetic sources have their own shapes and are not split).  The test loader uses the reference's hard-wired batch
+    size 64 (utils.py:459) — `epoch` normalises per batch, so test loss / accuracy depend on it; ``test_batch_size`` is a
+    keyword-only override."""
     mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]        # utils.py:214-230 (ImageNet statistics)
     class_names = None
     path = os.path.join(data_path or '.', f'{dataset}.pt')
@@ -74,5 +79,5 @@ def get_dataset(dataset, data_path, batch_size=256, num_workers=0):
     channel, im_size = int(xtr.shape[2]), (int(xtr.shape[3]), int(xtr.shape[4]))
     dst_train = _LabelledTensorDataset(xtr, ytr)
     dst_test = _LabelledTensorDataset(xte, yte)
-    testloader = DataLoader(dst_test, batch_size=batch_size, shuffle=False, num_workers=num_workers)
+    testloader = DataLoader(dst_test, batch_size=test_batch_size, shuffle=False, num_workers=num_workers)
     return channel, im_size, num_classes, class_names, mean, std, dst_train, dst_test, testloader

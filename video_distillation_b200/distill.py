@@ -570,6 +570,8 @@ class MTTS2DTrainer:
             sl = slice(self.rank, None, self.world)               # this rank's videos of the step batch (all for 1 rank)
 
             def shard_loss(theta, label=label, dynamic_idx=dynamic_idx, static_idx=static_idx, sl=sl, n_step=n_step):
+                if label[sl].numel() == 0:                      # fewer videos in this step batch than ranks: this rank contributes 0
+                    return theta.sum() * 0.0                    # (still attached to theta, so the collectives of the backward line up)
                 x = self.hal.compose(self.static_syn, self.dynamic_syn, static_idx[sl], label[sl], dynamic_idx[sl])
                 out = student_net(x, flat_param=theta)
                 # CrossEntropyLoss() is the batch mean (distill_s2d_ms.py:262): the shard contributes sum / B
@@ -672,6 +674,8 @@ class MTTBaselineTrainer:
             sl = slice(self.rank, None, self.world)
 
             def shard_loss(theta, these=these, sl=sl, n_step=n_step):
+                if these[sl].numel() == 0:
+                    return theta.sum() * 0.0
                 out = student_net(self.image_syn[these[sl]], flat_param=theta)
                 return torch.nn.functional.cross_entropy(out, self.label_syn[these[sl]], reduction='sum') / n_step
             grad = sharded_inner_grad(student_params[-1], shard_loss, self.world)

@@ -268,7 +268,7 @@ match_loss = _off_path('match_loss')
 get_daparam = _off_path('get_daparam')
 
 
-def get_dataset(dataset, data_path, batch_size=256, num_workers=0):
-    """utils.py:118 — see video_distillation_b200/datasets.py for what is supported."""
+def get_dataset(dataset, data_path, num_workers=0, img_size=(112, 112), split_num=1, split_id=0, split_mode='mean', **kw):
+    """utils.py:21 (same argument order) — see video_distillation_b200/datasets.py for what is supported."""
     from .datasets import get_dataset as _get
-    return _get(dataset, data_path, batch_size, num_workers)
+    return _get(dataset, data_path, num_workers, img_size, split_num, split_id, split_mode, **kw)
