@@ -240,7 +240,8 @@ def reference_cpu_rate(loop, threads):
 def bench_config(n_gpus):
     """The workload description shared verbatim by both arms (no implementation keys)."""
     return {'workload': WORKLOAD_DESC,
-            'parallelism': f'classes sharded c%{n_gpus}, dynamic-memory gradient all-reduced (NCCL)' if n_gpus > 1 else 'single GPU',
+            'parallelism': (f'synthetic branch + memories sharded by class c%{n_gpus}, sampled real videos spread over the ranks, '
+                            f'all-reduce of (C,D) partial embedding sums + [hal grad | loss] (NCCL)') if n_gpus > 1 else 'single GPU',
             'real_videos_per_step': C * BATCH_REAL, 'syn_videos_per_step': C * VPC,
             'l2_policy': f'inputs larger than L2: each step reads {C * BATCH_REAL} distinct real videos '
                          f'({C * BATCH_REAL * T * 3 * HW * HW * 4 / 1e9:.1f} GB fp32)'}
@@ -412,22 +413,25 @@ def run_ours(args):
     # ---- synthetic real set: per-class generators so the data does not depend on the world size
     own = owned_classes(C, rank, world)
     labels = [c for c in range(C) for _ in range(PER_CLASS)]
+    assert PER_CLASS % world == 0, 'the synthetic set spreads every class evenly over the ranks'
+    per_rank = PER_CLASS // world                   # shard='video': positions p % world == rank of every class
     # frames are uint8 like decoded video, normalised with the dataset statistics (reference: utils.py:214-230); the fp32
     # tensor is what the reference's preloaded TensorDataset holds
     mean_t = torch.tensor(MEAN, device=dev).view(1, 1, 3, 1, 1)
     std_t = torch.tensor(STD, device=dev).view(1, 1, 3, 1, 1)
     c255 = torch.tensor(255.0, device=dev)          # tensor divisor: a Python scalar would become a reciprocal multiply
-    frames = torch.empty(len(own) * PER_CLASS, T, 3, HW, HW, dtype=torch.uint8, device=dev)
-    vids = torch.empty(len(own) * PER_CLASS, T, 3, HW, HW, device=dev)
-    for j, c in enumerate(own):
+    frames = torch.empty(C * per_rank, T, 3, HW, HW, dtype=torch.uint8, device=dev)
+    vids = torch.empty(C * per_rank, T, 3, HW, HW, device=dev)
+    for c in range(C):
         g = torch.Generator(device=dev).manual_seed(1000 + c)
-        fr = torch.randint(0, 256, (PER_CLASS, T, 3, HW, HW), dtype=torch.uint8, device=dev, generator=g)
-        frames[j * PER_CLASS:(j + 1) * PER_CLASS] = fr
-        vids[j * PER_CLASS:(j + 1) * PER_CLASS] = ((fr.float() / c255) - mean_t) / std_t       # IEEE divisions, like the host transform
+        fr = torch.randint(0, 256, (PER_CLASS, T, 3, HW, HW), dtype=torch.uint8, device=dev, generator=g)[rank::world]
+        frames[c * per_rank:(c + 1) * per_rank] = fr
+        vids[c * per_rank:(c + 1) * per_rank] = ((fr.float() / c255) - mean_t) / std_t       # IEEE divisions, like the host transform
+        del fr
     frames_host = torch.empty(frames.shape, dtype=torch.uint8, pin_memory=True)
     frames_host.copy_(frames)
     del frames
-    ds = DeviceDataset.from_device_shard(vids, labels, C, dev, rank, world)
+    ds = DeviceDataset.from_device_shard(vids, labels, C, dev, rank, world, shard='video')
 
     def make_trainer(precision, dataset):
         torch.manual_seed(0)
@@ -501,18 +505,21 @@ def run_ours(args):
     value = args.steps / (ms / 1000.0)
     # result fingerprint after warmup + steps iterations: every world size must print the same numbers (class sharding and
     # the all-reduce only change the order of a few fp32 additions)
-    dsyn = tr.dynamic_syn.detach().double()
+    dsyn = tr.full_memories()[1].double()           # (collective for N > 1: the memories are sharded by class)
+    gmax = tr.dynamic_syn.grad.abs().max().reshape(1)
+    if world > 1:
+        dist.all_reduce(gmax, op=dist.ReduceOp.MAX)
     check = {'iterations': args.warmup + args.steps, 'loss_last': float(last_loss[0]),
              'dynamic_syn_sum': float(dsyn.sum()), 'dynamic_syn_sumsq': float((dsyn * dsyn).sum()),
              'hal_weight_sum': float(tr.hal.encoder.weight.detach().double().sum()),
-             'grad_dynamic_absmax': float(tr.dynamic_syn.grad.abs().max()), 'lr_dynamic': LR_DYNAMIC, 'lr_hal': LR_HAL}
+             'grad_dynamic_absmax': float(gmax), 'lr_dynamic': LR_DYNAMIC, 'lr_hal': LR_HAL}
     del dsyn
 
     # ---- e2e: the step's real videos come from pinned host memory as normalised fp32 (the reference's TensorDataset,
     # get_images(...).to(device), distill_s2d_ms.py:81-87), the loss is read back.  Double-buffered: while step i computes,
     # the host->device copies of step i+1's sampled videos run on a copy stream (the sampling only depends on the numpy RNG
     # stream, not on results).  Every timed step issues exactly one full set of copies inside the timed region.
-    n_own_real = len(own) * BATCH_REAL
+    n_own_real = C * min(BATCH_REAL, per_rank)       # upper bound of this rank's share of a draw (every class, its positions)
     e2e_steps = max(1, args.steps)
     host = torch.empty(vids.shape, dtype=torch.float32, pin_memory=True)
     host.copy_(vids)
@@ -525,6 +532,8 @@ def run_ours(args):
     slot_box = [0]
     perm_dev = [torch.empty(n_own_real, dtype=torch.int64, device=dev) for _ in range(2)]
     perm_pin = [torch.empty(n_own_real, dtype=torch.int64).pin_memory() for _ in range(2)]
+    offs_dev = [torch.empty(C + 1, dtype=torch.int32, device=dev) for _ in range(2)]
+    offs_pin = [torch.empty(C + 1, dtype=torch.int32).pin_memory() for _ in range(2)]
 
     def make_prefetch(src_host, dst_stages):
         def prefetch(slot):
@@ -532,7 +541,11 @@ def run_ours(args):
             # 72 videos are drawn, so runs are long): same bytes, ~8x fewer and larger PCIe transfers; `perm` maps sample j to
             # its row of the staging buffer, so embeddings (and the result) keep the sampled order
             real_idx = ds.sample_all_classes(BATCH_REAL)
-            loc = ds.local_of_global[real_idx[own].reshape(-1)]
+            loc_all = ds.local_of_global[real_idx]                     # (C, n): -1 = held by another rank
+            mask = loc_all >= 0
+            offs = np.zeros(C + 1, dtype=np.int32)
+            np.cumsum(mask.sum(1), out=offs[1:])
+            loc = loc_all[mask]
             order = np.argsort(loc, kind='stable')
             srt = loc[order]
             perm = np.empty_like(order)
@@ -544,10 +557,12 @@ def run_ours(args):
                 dst = dst_stages[slot]
                 for a, b in zip(starts, ends):
                     dst[a:b].copy_(src_host[int(srt[a]):int(srt[a]) + int(b - a)], non_blocking=True)
-                perm_pin[slot].copy_(torch.from_numpy(perm))
+                perm_pin[slot][:perm.size].copy_(torch.from_numpy(perm))
                 perm_dev[slot].copy_(perm_pin[slot], non_blocking=True)
+                offs_pin[slot].copy_(torch.from_numpy(offs))
+                offs_dev[slot].copy_(offs_pin[slot], non_blocking=True)
                 ready[slot].record(copy_stream)
-            pending[slot] = real_idx
+            pending[slot] = (real_idx, int(perm.size))
         return prefetch
 
     def make_step(prefetch, dst_stages):
@@ -556,7 +571,9 @@ def run_ours(args):
             slot = slot_box[0]
             slot_box[0] ^= 1
             torch.cuda.current_stream().wait_event(ready[slot])
-            loss = tr.step(net_seed=seed_box[0], real_idx=pending[slot], real_batch=dst_stages[slot], real_batch_index=perm_dev[slot])
+            real_idx, n_loc = pending[slot]
+            loss = tr.step(net_seed=seed_box[0], real_idx=real_idx, real_batch=dst_stages[slot], real_batch_index=perm_dev[slot][:n_loc],
+                           real_batch_offsets=offs_dev[slot] if world > 1 else None)
             free[slot].record()
             prefetch(slot ^ 1)                                # next step's inputs: H2D overlaps this step's kernels
             return loss.item()                                # D2H read of the step's result

@@ -115,6 +115,10 @@ int vd_compose_bwd_f32(const float* gout, const float* static_syn, const float* 
  * mean_real_out (C, D) optional (NULL to skip).
  */
 int vd_class_mean_f32(const float* emb, float* mean, int C, int n, int D, void* stream);
+/* Ragged form for the multi-GPU path (the sampled real videos of a class are spread over the ranks): sum[c,:] = sum of the rows
+ * offsets[c] .. offsets[c+1]-1 of emb (n_rows, D), added in row order; offsets = device int32[C+1].  The (C, D) partial sums of
+ * the ranks are all-reduced and divided by batch_real: torch.mean(output_real, dim=0) of distill_s2d_ms.py:422. */
+int vd_class_sum_ragged_f32(const float* emb, const int32_t* offsets, float* sum, int C, int D, void* stream);
 int vd_dm_loss_f32(const float* mean_real, const float* emb_syn, float* loss, float* grad_syn,
                    int C, int ns, int D, float loss_scale, void* stream);
 /* Same result with a caller-provided scratch of C floats: one block per class writes class_loss[c] (the per-class terms of

@@ -121,3 +121,39 @@ def test_evaluate_synset_schedule_matches_the_live_reference(tag, test_freq, mon
                                                   mode='none', test_freq=test_freq)
     assert np.allclose(np.asarray(calls, dtype=np.float64), gold[tag], rtol=0, atol=1e-15)
     assert [acc_train, acc_test] == gold[tag + '_ret'].tolist()
+
+
+def test_video_sharded_dataset_covers_every_draw_exactly_once():
+    """DeviceDataset(shard='video'): every class is spread over the ranks by position; the ranks' local shares of a draw
+    partition it, keep the sampled order inside a class, and their per-class partial sums add up to the class sums."""
+    import numpy as np
+    import torch
+    from video_distillation_b200.distill import DeviceDataset
+    C, per, world, n = 5, 12, 4, 9
+    labels = [c for c in range(C) for _ in range(per)]
+    rng = np.random.RandomState(3)
+    order = rng.permutation(len(labels))                      # classes interleaved in dataset order
+    labels = [labels[i] for i in order]
+    videos = torch.arange(len(labels), dtype=torch.float32).view(-1, 1, 1, 1, 1).expand(-1, 2, 3, 4, 4).contiguous()
+    shards = [DeviceDataset(videos, labels, C, 'cpu', r, world, shard='video') for r in range(world)]
+    assert sum(len(s.keep) for s in shards) == len(labels) and all(len(s.keep) == C * per // world for s in shards)
+    np.random.seed(11)
+    real_idx = shards[0].sample_all_classes(n)
+    np.random.seed(11)
+    assert np.array_equal(real_idx, shards[3].sample_all_classes(n))          # every rank replays the same stream
+    seen = []
+    sums = torch.zeros(C)
+    for s in shards:
+        loc, offs = s.local_sample(real_idx)
+        offs = offs.tolist()
+        assert offs[0] == 0 and offs[-1] == loc.numel() and len(offs) == C + 1
+        vals = s.videos[loc][:, 0, 0, 0, 0]                  # = global index of the row
+        for c in range(C):
+            seg = vals[offs[c]:offs[c + 1]].long().tolist()
+            assert all(labels[g] == c for g in seg)
+            assert seg == [g for g in real_idx[c].tolist() if g in set(seg)]   # sampled order kept
+            seen += seg
+            sums[c] += float(sum(seg))
+            assert abs(len(seg) - n / world) <= 3
+    assert sorted(seen) == sorted(real_idx.reshape(-1).tolist())
+    assert torch.equal(sums, torch.tensor([float(real_idx[c].sum()) for c in range(C)]))

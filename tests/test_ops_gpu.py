@@ -266,3 +266,19 @@ def test_dm_loss_variants_are_bitwise_identical_and_ordered():
     for c in range(C):
         seq = seq + cl[c]
     assert torch.equal(seq, lb)
+
+
+def test_class_sum_ragged_matches_torch():
+    from video_distillation_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    counts = [5, 0, 9, 1, 64, 3]
+    emb = torch.randn(sum(counts), 2048, generator=g).cuda()
+    offs = torch.tensor([0] + list(np.cumsum(counts)), dtype=torch.int32).cuda()
+    out = ops.class_sum_ragged(emb, offs, len(counts))
+    ref = torch.stack([emb[int(offs[c]):int(offs[c + 1])].double().sum(0) for c in range(len(counts))]).float()
+    assert float((out - ref).abs().max()) < 1e-4 and float(out[1].abs().max()) == 0.0
+    # rows are added in row order: equal, bit for bit, to a sequential fp32 sum
+    seq = torch.zeros(2048, device='cuda')
+    for r in range(5):
+        seq = seq + emb[r]
+    assert torch.equal(out[0], seq)

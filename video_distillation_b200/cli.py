@@ -352,7 +352,7 @@ def main_s2d(args):
                            batch_syn=args.batch_syn, precision='fp32' if args.precision == 'fp32' else 'bf16', **common)
     elif args.method == 'DM':
         videos, labels = _tensors_of(dst_train)
-        ds = DeviceDataset(videos, labels, num_classes, dev, rank, world)
+        ds = DeviceDataset(videos, labels, num_classes, dev, rank, world, shard='video' if world > 1 else 'class')
         prec = args.precision
         tr = DMS2DTrainer(ds, batch_real=args.batch_real, precision=prec, max_batch=640 if prec in ('bf16', 'f16x3') else 128, **common)
         if tr.embedder.tc is not None:
@@ -360,10 +360,16 @@ def main_s2d(args):
     else:
         raise NotImplementedError('Method {} not implemented'.format(args.method))
 
-    _broadcast_state([tr.static_syn, tr.dynamic_syn, *tr.hal.parameters()] + ([tr.syn_lr] if args.method == 'MTT' else []), world)
+    # DM shards the memories by class (every rank sliced the same seeded full-size init); MTT keeps full replicas
+    _broadcast_state(list(tr.hal.parameters()) + ([tr.static_syn, tr.dynamic_syn, tr.syn_lr] if args.method == 'MTT' else []), world)
+    full = {}
+
+    def memories():
+        return full['m'] if 'm' in full else (tr.static_syn.detach(), tr.dynamic_syn.detach())
 
     def payload():
-        return [copy.deepcopy(tr.static_syn.detach()), copy.deepcopy(tr.dynamic_syn.detach()), nn.ModuleList([copy.deepcopy(tr.hal)])], None
+        st, dy = memories()
+        return [copy.deepcopy(st), copy.deepcopy(dy), nn.ModuleList([copy.deepcopy(tr.hal)])], None
 
     def hals_state():
         # the reference saves the state_dict of `hals = nn.ModuleList([Conv3DNet()])` (:96, :186): keys '0.encoder.weight/bias'
@@ -371,6 +377,8 @@ def main_s2d(args):
 
     for it in range(0, args.Iteration + 1):
         save_this_it = False
+        if it in eval_it_pool and args.method == 'DM' and world > 1:
+            full['m'] = tr.full_memories()            # collective: every rank contributes its class shard
         if it in eval_it_pool and rank == 0:
             args.lr_net = tr.syn_lr.detach() if args.method == 'MTT' else torch.tensor(args.lr_teacher)
             save_this_it = _evaluate(args, it, model_eval_pool, channel, num_classes, im_size, payload, testloader, 'multi-static',
@@ -379,8 +387,8 @@ def main_s2d(args):
             with torch.no_grad():
                 save_dir = os.path.join(args.save_path, project_name, run_name)
                 os.makedirs(save_dir, exist_ok=True)
-                image_save = tr.static_syn.detach()
-                dynamic_save = tr.dynamic_syn.flatten(0, 1).detach()
+                image_save, dynamic_save = memories()
+                dynamic_save = dynamic_save.flatten(0, 1)
                 if not args.no_train_static:
                     torch.save(image_save.cpu(), os.path.join(save_dir, 'images_{}.pt'.format(it)))
                 torch.save(hals_state(), os.path.join(save_dir, 'hal_{}.pt'.format(it)))

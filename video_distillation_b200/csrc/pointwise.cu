@@ -404,6 +404,25 @@ __global__ void class_mean_kernel(const float* __restrict__ emb, float* __restri
     mean[(int64_t)c * D + d] = s / (float)n;
 }
 
+// Ragged class sums: rows offsets[c] .. offsets[c+1]-1 of emb (class-major order) are added IN ROW ORDER into sum[c,:] (an empty
+// segment gives zeros).  The multi-GPU DM path shards the sampled real videos of every class over the ranks; each rank reduces
+// the embeddings of ITS videos with this kernel and the (C, D) partial sums are all-reduced (distill.py).  float4 along d.
+__global__ void __launch_bounds__(128) class_sum_ragged_kernel(const float* __restrict__ emb, const int32_t* __restrict__ offsets,
+                                                               float* __restrict__ sum, int D) {
+    const int c = blockIdx.y;
+    const int d = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (d >= D) return;
+    const int r0 = __ldg(offsets + c), r1 = __ldg(offsets + c + 1);
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* p = emb + (int64_t)r0 * D + d;
+#pragma unroll 8
+    for (int r = r0; r < r1; ++r, p += D) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    *reinterpret_cast<float4*>(sum + (int64_t)c * D + d) = s;
+}
+
 // per class: diff = mean_real - mean(emb_syn); loss += sum diff^2; grad_syn = -(2/ns) diff * scale.
 // ONE block walks the classes in order: every class sum is a fixed-shape tree and the per-class sums are added in class order
 // (the order of the reference's `loss += torch.sum(...)` loop, distill_s2d_ms.py:414-422), so the scalar is bitwise
@@ -663,6 +682,15 @@ extern "C" int vd_class_mean_f32(const float* emb, float* mean, int C, int n, in
     dim3 grid((unsigned)ceil_div(D, 128), C, 1);
     class_mean_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(emb, mean, n, D);
     return check_launch("class_mean_f32");
+}
+
+extern "C" int vd_class_sum_ragged_f32(const float* emb, const int32_t* offsets, float* sum, int C, int D, void* stream) {
+    VD_REQUIRE(emb && offsets && sum && C >= 0 && D > 0 && C <= 65535, "class_sum_ragged: bad argument");
+    VD_REQUIRE(D % 4 == 0 && ((uintptr_t)emb & 15) == 0 && ((uintptr_t)sum & 15) == 0, "class_sum_ragged: D must be a multiple of 4 and the pointers 16-byte aligned");
+    if (C == 0) return 0;
+    dim3 grid((unsigned)ceil_div(D, 512), C, 1);
+    class_sum_ragged_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(emb, offsets, sum, D);
+    return check_launch("class_sum_ragged_f32");
 }
 
 extern "C" int vd_dm_loss_f32(const float* mean_real, const float* emb_syn, float* loss, float* grad_syn,

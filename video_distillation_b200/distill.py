@@ -9,10 +9,12 @@
 The 50..400 per-class Python iterations of the reference become a handful of batched launches:
 all real videos of the rank's classes are embedded in one pass (tensor cores, bf16 operands,
 fp32 accumulate, or the exact fp32 path with precision='fp32'), reduced to class means, and the
-loss + d loss/d embedding come out of one kernel.  Classes are sharded ``c % world == rank``;
-every rank replays the full RNG streams and slices its part, so sampling is bit-identical to a
-single-GPU run; the only collective is one all-reduce of [dynamic-memory grad | hallucinator
-grad | loss] per iteration (NCCL over NVLink).
+loss + d loss/d embedding come out of one kernel.  Multi-GPU: the synthetic branch and the memories
+(with their momentum buffers) are sharded by class ``c % world == rank``; the sampled real videos of
+every class are spread over the ranks (``DeviceDataset(shard='video')``) and completed by an all-reduce
+of the (C, D) partial embedding sums; every rank replays the full RNG streams and slices its part, so
+sampling is bit-identical to a single-GPU run.  Per iteration two small collectives cross NVLink:
+the partial sums (C*D floats) and [hallucinator grad | loss] (328 floats).
 """
 import numpy as np
 import torch
@@ -37,8 +39,9 @@ def owned_classes(num_classes, rank, world):
 
 
 def allreduce_sum_(tensors):
-    """SUM all-reduce of a list of tensors as ONE flat message (in place); no-op for a single rank.
-    The DM path calls this once per iteration with [dynamic-memory grad, hallucinator grads, loss]."""
+    """SUM all-reduce of a list of tensors, in place; no-op for a single rank.  Tensors below 64 Ki elements travel as ONE
+    flat message, larger contiguous ones are reduced in place one by one (no staging copy).  The DM path calls this once per
+    iteration with [hallucinator grads, loss] (a single 328-float message: the memory gradients are class-local)."""
     rank, world = _world()
     if world == 1:
         return tensors
@@ -105,20 +108,15 @@ class DeviceDataset:
     distill_s2d_ms.py:73-79, so ``np.random.permutation(indices_class[c])[:n]`` is unchanged.
     """
 
-    def __init__(self, videos, labels, num_classes, device, rank=0, world=1, norm=None):
+    def __init__(self, videos, labels, num_classes, device, rank=0, world=1, norm=None, shard='class'):
         # ``videos`` may be the decoded uint8 frames with ``norm = (mean, std)``: the tensor-core path then normalises inside
         # its packer ((u/255 - mean)/std, bit-identical operands) and the resident set costs 1 byte per element
         self.norm = norm
         if videos.dtype == torch.uint8 and norm is None:
             raise ValueError('uint8 videos need norm=(mean, std)')
         labels = [int(v) for v in labels]
-        self.num_classes = num_classes
-        self.indices_class = [[] for _ in range(num_classes)]
-        for i, lab in enumerate(labels):
-            self.indices_class[lab].append(i)
-        self.rank, self.world = rank, world
-        self.owned = owned_classes(num_classes, rank, world)
-        keep = [i for i, lab in enumerate(labels) if lab % world == rank]
+        self._index(labels, num_classes, rank, world, shard)
+        keep = self.keep
         self.local_of_global = np.full(len(labels), -1, dtype=np.int64)
         self.local_of_global[np.asarray(keep, dtype=np.int64)] = np.arange(len(keep))
         self.device = torch.device(device)
@@ -127,19 +125,37 @@ class DeviceDataset:
         self.shape = tuple(videos.shape[1:])
         self.x0 = None
 
-    @classmethod
-    def from_device_shard(cls, shard_videos, labels, num_classes, device, rank=0, world=1):
-        """Same object from an already device-resident shard: ``shard_videos`` holds exactly the rows
-        of the owned classes, in dataset order (synthetic benchmarks generate them on the device)."""
-        self = cls.__new__(cls)
-        labels = [int(v) for v in labels]
+    def _index(self, labels, num_classes, rank, world, shard):
+        """indices_class as at distill_s2d_ms.py:73-79 and the rows this rank holds:
+        shard='class': the videos of the classes c % world == rank (the rank embeds whole classes);
+        shard='video': the videos whose POSITION inside their class is p % world == rank — every class is spread evenly over
+                       the ranks, so a draw of batch_real videos per class gives every rank ~batch_real / world of EVERY class
+                       (hypergeometric, +-1) and the real-video work balances to ~1 % whatever C / world is; the per-class
+                       embedding sums are completed by an all-reduce of (C, D) partial sums."""
+        if shard not in ('class', 'video'):
+            raise ValueError("shard must be 'class' or 'video'")
+        self.shard = shard
         self.num_classes = num_classes
         self.indices_class = [[] for _ in range(num_classes)]
+        pos = []
         for i, lab in enumerate(labels):
+            pos.append(len(self.indices_class[lab]))
             self.indices_class[lab].append(i)
         self.rank, self.world = rank, world
         self.owned = owned_classes(num_classes, rank, world)
-        keep = [i for i, lab in enumerate(labels) if lab % world == rank]
+        if shard == 'class':
+            self.keep = [i for i, lab in enumerate(labels) if lab % world == rank]
+        else:
+            self.keep = [i for i in range(len(labels)) if pos[i] % world == rank]
+
+    @classmethod
+    def from_device_shard(cls, shard_videos, labels, num_classes, device, rank=0, world=1, shard='class'):
+        """Same object from an already device-resident shard: ``shard_videos`` holds exactly the rows this rank keeps
+        (``_index``), in dataset order (synthetic benchmarks generate them on the device)."""
+        self = cls.__new__(cls)
+        labels = [int(v) for v in labels]
+        self._index(labels, num_classes, rank, world, shard)
+        keep = self.keep
         assert shard_videos.shape[0] == len(keep), 'shard does not match the owned rows'
         self.local_of_global = np.full(len(labels), -1, dtype=np.int64)
         self.local_of_global[np.asarray(keep, dtype=np.int64)] = np.arange(len(keep))
@@ -168,25 +184,38 @@ class DeviceDataset:
         numpy stream); returns the global indices (C, n) — bit-exact with get_images."""
         return np.stack([np.random.permutation(self.indices_class[c])[:n] for c in range(self.num_classes)])
 
+    def local_sample(self, real_idx):
+        """shard='video': of the (C, n) sampled global indices of ALL classes, the ones this rank holds — as rows of
+        ``self.videos`` in class-major order (sampled order inside a class) plus the (C+1,) int32 segment offsets."""
+        loc_all = self.local_of_global[np.asarray(real_idx)]
+        mask = loc_all >= 0
+        offsets = np.zeros(loc_all.shape[0] + 1, dtype=np.int32)
+        np.cumsum(mask.sum(1), out=offsets[1:])
+        return self._to_device(np.ascontiguousarray(loc_all[mask])), self._to_device(offsets)
+
     def local_index(self, global_idx):
         """global video indices of owned classes -> rows of ``self.videos`` (device int64)."""
         loc = self.local_of_global[np.asarray(global_idx).reshape(-1)]
-        assert (loc >= 0).all(), 'requested a video of a class this rank does not own'
-        t = torch.from_numpy(np.ascontiguousarray(loc))
+        assert (loc >= 0).all(), 'requested a video this rank does not hold'
+        return self._to_device(np.ascontiguousarray(loc))
+
+    def _to_device(self, arr):
+        t = torch.from_numpy(arr)
         if self.device.type != 'cuda':
             return t.to(self.device)
         # ring of reusable pinned staging buffers: a fresh pin_memory() per call is a cudaHostAlloc, which
         # synchronises the device (0.5 ms idle per iteration in the timeline); 8 slots keep in-flight copies apart
         ring = getattr(self, '_pin_ring', None)
-        if ring is None or ring[0].numel() < t.numel():
-            ring = self._pin_ring = [torch.empty(max(t.numel(), 1), dtype=torch.int64).pin_memory() for _ in range(8)]
+        nbytes = t.numel() * t.element_size()
+        if ring is None or ring[0].numel() < nbytes:
+            ring = self._pin_ring = [torch.empty(max(nbytes, 8), dtype=torch.uint8).pin_memory() for _ in range(8)]
             self._pin_done = [None] * len(ring)
             self._pin_next = 0
         slot = self._pin_next % len(ring)
         self._pin_next += 1
         if self._pin_done[slot] is not None:
             self._pin_done[slot].synchronize()            # the copy that last read this slot (8 calls ago) has finished
-        buf = ring[slot][:t.numel()]
+        buf = ring[slot][:nbytes].view(t.dtype)
         buf.copy_(t)
         out = buf.to(self.device, non_blocking=True)
         ev = torch.cuda.Event()
@@ -330,12 +359,21 @@ class DMS2DTrainer:
         if dynamic_syn is None:
             dynamic_syn = torch.randn(size=(num_classes, dpc, frames, 1, H, W), dtype=torch.float)
         self.hal = (hal if hal is not None else Conv3DNet()).to(self.device)
+        self.owned = owned_classes(num_classes, self.rank, self.world)
+        self.owned_t = torch.as_tensor(self.owned, dtype=torch.long, device=self.device)
+        # Multi-GPU: the memories (and their momentum buffers) are SHARDED by class — a class's synthetic videos only ever read
+        # and update that class's rows (distill_s2d_ms.py:402-412), so a rank keeps the rows of its classes c % world == rank
+        # and nothing of the 80..520 MB dynamic memory crosses NVLink during training (`full_memories` gathers for eval / save).
+        # Every rank receives the same full-size init (same seeds / broadcast) and slices its rows.
+        self.sharded_memories = self.world > 1
+        if self.sharded_memories:
+            own_cpu = torch.as_tensor(self.owned, dtype=torch.long)
+            static_syn = static_syn.detach().cpu().view(num_classes, spc, *static_syn.shape[1:])[own_cpu].reshape(-1, *static_syn.shape[1:])
+            dynamic_syn = dynamic_syn.detach().cpu()[own_cpu]
         self.static_syn = static_syn.detach().to(self.device).contiguous().requires_grad_(train_static)
         self.dynamic_syn = dynamic_syn.detach().to(self.device).contiguous().requires_grad_(True)
         self._bufs = {}
         self.embedder = _RealEmbedder(frames, self.im_size, self.device, precision, max_batch)
-        self.owned = owned_classes(num_classes, self.rank, self.world)
-        self.owned_t = torch.as_tensor(self.owned, dtype=torch.long, device=self.device)
         self.last = {}
 
     # ------------------------------------------------------------------ pieces
@@ -360,21 +398,38 @@ class DMS2DTrainer:
             self._bufs[name] = torch.empty_like(p)
         ops.sgd_momentum_(p.data, grad.contiguous(), self._bufs[name], lr, momentum, first)
 
+    def full_memories(self):
+        """(static_syn (C*spc,3,H,W), dynamic_syn (C,dpc,T,1,H,W)) of ALL classes on every rank (collective when world > 1:
+        each rank contributes its class shard).  For evaluation / checkpoints, outside the iteration."""
+        if not self.sharded_memories:
+            return self.static_syn.detach(), self.dynamic_syn.detach()
+        H, W = self.im_size
+        st = torch.zeros(self.C, self.spc, 3, H, W, device=self.device)
+        dy = torch.zeros(self.C, self.dpc, self.frames, 1, H, W, device=self.device)
+        st[self.owned_t] = self.static_syn.detach().view(len(self.owned), self.spc, 3, H, W)
+        dy[self.owned_t] = self.dynamic_syn.detach()
+        dist.all_reduce(st)
+        dist.all_reduce(dy)
+        return st.view(self.C * self.spc, 3, H, W), dy
+
     # ------------------------------------------------------------------ one iteration
-    def step(self, net=None, net_seed=None, indices=None, real_idx=None, real_batch=None, real_batch_index=None):
+    def step(self, net=None, net_seed=None, indices=None, real_idx=None, real_batch=None, real_batch_index=None,
+             real_batch_offsets=None):
         """One DM iteration; returns the loss (0-dim device tensor, summed over ALL classes).
         ``real_batch``: optional device tensor holding this rank's sampled real videos already gathered
         (class-major, batch_real per owned class) — the host-streaming mode of bench.py; ``real_batch_index`` (device int64)
-        maps sample j to its row of ``real_batch`` when the rows were uploaded in another order (merged host ranges)."""
+        maps sample j to its row of ``real_batch`` when the rows were uploaded in another order (merged host ranges);
+        ``real_batch_offsets`` (device int32, C+1): class segments of the batch when the set is video-sharded."""
         if (self.embedder.tc is not None and self.syn_on_tensor_cores == 'split') or self.embedder.precision == 'bf16x3':
             prev = ops.set_conv_backend('tc')             # forward AND backward of net.embed(...) below
             try:
-                return self._step(net, net_seed, indices, real_idx, real_batch, real_batch_index)
+                return self._step(net, net_seed, indices, real_idx, real_batch, real_batch_index, real_batch_offsets)
             finally:
                 ops.set_conv_backend(prev)
-        return self._step(net, net_seed, indices, real_idx, real_batch, real_batch_index)
+        return self._step(net, net_seed, indices, real_idx, real_batch, real_batch_index, real_batch_offsets)
 
-    def _step(self, net=None, net_seed=None, indices=None, real_idx=None, real_batch=None, real_batch_index=None):
+    def _step(self, net=None, net_seed=None, indices=None, real_idx=None, real_batch=None, real_batch_index=None,
+              real_batch_offsets=None):
         C, vpc = self.C, self.vpc
         if net is None:
             if self.init_on_device:
@@ -391,23 +446,42 @@ class DMS2DTrainer:
         own = self.owned
         n_own = len(own)
         sel = (self.owned_t[:, None] * vpc + torch.arange(vpc, device=self.device)[None, :]).reshape(-1)
-        image_syn = self.hal.compose(self.static_syn, self.dynamic_syn, static_idx[sel], label[sel], dynamic_idx[sel])
+        if self.sharded_memories:
+            # rows of the class shard: class c = own[k] lives at local position k (static rows spc*k .. spc*k + spc - 1)
+            lab_loc = torch.arange(n_own, device=self.device).repeat_interleave(vpc)
+            image_syn = self.hal.compose(self.static_syn, self.dynamic_syn, static_idx[sel] - self.spc * (label[sel] - lab_loc),
+                                         lab_loc, dynamic_idx[sel])
+        else:
+            image_syn = self.hal.compose(self.static_syn, self.dynamic_syn, static_idx[sel], label[sel], dynamic_idx[sel])
         tc = self.embedder.tc
         fused_syn = tc is not None and self.syn_on_tensor_cores is True
         joint = (fused_syn and real_batch is None and self.ds.x0 is not None
                  and getattr(self.ds, 'x0_extra', 0) >= image_syn.shape[0])
+        video_sharded = self.world > 1 and getattr(self.ds, 'shard', 'class') == 'video'
+        offsets = real_batch_offsets
+        if real_batch is not None:
+            assert not video_sharded or offsets is not None, 'a streamed batch of a video-sharded set needs its class offsets'
+        elif video_sharded:
+            ridx, offsets = self.ds.local_sample(real_idx)                  # this rank's share of EVERY class's draw
+        else:
+            ridx = self.ds.local_index(real_idx[own])                       # (n_own*batch_real,)
         if joint:
             # real + synthetic videos in the same three conv launches (codes only for the synthetic tail)
-            ridx = self.ds.local_index(real_idx[own])
             emb_real, emb_syn = tc.embed_joint_autograd(self.ds.x0, ridx, image_syn, self.ds.x0_tail)
         elif real_batch is None:
-            ridx = self.ds.local_index(real_idx[own])                       # (n_own*batch_real,)
             emb_real = self.embedder(self.ds.videos, ridx, x0=self.ds.x0)   # (n_own*batch_real, D)
         else:
             ridx = real_batch_index if real_batch_index is not None else torch.arange(real_batch.shape[0], device=self.device)
             emb_real = self.embedder(real_batch, ridx)
         D = emb_real.shape[1]
-        mean_real = ops.class_mean(emb_real.view(n_own, self.batch_real, D))
+        if video_sharded:
+            # (C, D) partial sums of this rank's videos -> all-reduce -> the class means of the classes this rank owns
+            sums = ops.class_sum_ragged(emb_real, offsets, C)
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+            # tensor divisor: IEEE division like the class_mean kernel (a Python scalar would become a reciprocal multiply)
+            mean_real = (sums[self.owned_t] / torch.tensor(float(self.batch_real), device=self.device)).contiguous()
+        else:
+            mean_real = ops.class_mean(emb_real.view(n_own, self.batch_real, D))
         if joint:
             emb_syn = emb_syn.view(n_own, vpc, D)
         elif fused_syn:
@@ -418,12 +492,9 @@ class DMS2DTrainer:
         for p in (self.dynamic_syn, self.static_syn, *self.hal.parameters()):
             p.grad = None
         loss.backward()
-        # ---- combine ranks: one flat all-reduce [dynamic grad | hal grads | (static grad) | loss]
-        grads = [self.dynamic_syn.grad, self.hal.encoder.weight.grad, self.hal.encoder.bias.grad]
-        if self.train_static:
-            grads.append(self.static_syn.grad)
+        # ---- combine ranks: ONE small all-reduce [hallucinator grads (327) | loss]; the memory gradients are class-local
         loss_d = loss.detach().reshape(1).clone()
-        allreduce_sum_(grads + [loss_d])
+        allreduce_sum_([self.hal.encoder.weight.grad, self.hal.encoder.bias.grad, loss_d])
         # ---- optimizer steps (distill_s2d_ms.py:432-435), dense momentum SGD
         if self.train_static:
             self._sgd('static', self.static_syn, self.static_syn.grad, self.lr_static)

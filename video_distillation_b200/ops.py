@@ -377,6 +377,18 @@ def class_mean(emb):
     return out
 
 
+def class_sum_ragged(emb, offsets, C):
+    """(n_rows, D) embeddings in class-major order + device int32 offsets (C+1,) -> (C, D) per-class SUMS, rows added in order
+    (the per-rank partial sums of the video-sharded multi-GPU DM path)."""
+    emb = _f32c(emb)
+    D = emb.shape[1]
+    out = torch.empty(C, D, dtype=torch.float32, device=emb.device)
+    if emb.shape[0] == 0:
+        return out.zero_()
+    check(lib().vd_class_sum_ragged_f32(ptr(emb), ptr(offsets), ptr(out), C, D, stream()), 'class_sum_ragged')
+    return out
+
+
 class _DMLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, mean_real, emb_syn):
