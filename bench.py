@@ -482,8 +482,19 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()                         # started before the warm-up so that it is sampling when the timed region begins
-    for _ in range(args.warmup):
+    first = None
+    for i in range(args.warmup):
         step_resident()
+        if i == 0:
+            # fingerprint of the FIRST iteration (identical state on every world size, no feedback yet): loss and the
+            # dynamic-memory / hallucinator gradients must agree between --gpus 1, 2, 4, 8 to fp32 rounding
+            gd = tr.dynamic_syn.grad.detach().double()
+            part = torch.stack([gd.sum(), (gd * gd).sum()])
+            if world > 1:
+                dist.all_reduce(part)
+            first = {'loss': float(last_loss[0]), 'grad_dynamic_sum': float(part[0]), 'grad_dynamic_sumsq': float(part[1]),
+                     'grad_hal_weight_sumsq': float((tr.hal.encoder.weight.grad.double() ** 2).sum())}
+            del gd
     tc = tr.embedder.tc
     if tc is not None:
         tc.timing = []
@@ -509,7 +520,7 @@ def run_ours(args):
     gmax = tr.dynamic_syn.grad.abs().max().reshape(1)
     if world > 1:
         dist.all_reduce(gmax, op=dist.ReduceOp.MAX)
-    check = {'iterations': args.warmup + args.steps, 'loss_last': float(last_loss[0]),
+    check = {'first_iteration': first, 'iterations': args.warmup + args.steps, 'loss_last': float(last_loss[0]),
              'dynamic_syn_sum': float(dsyn.sum()), 'dynamic_syn_sumsq': float((dsyn * dsyn).sum()),
              'hal_weight_sum': float(tr.hal.encoder.weight.detach().double().sum()),
              'grad_dynamic_absmax': float(gmax), 'lr_dynamic': LR_DYNAMIC, 'lr_hal': LR_HAL}

@@ -106,6 +106,16 @@ int vd_compose_bwd_f32(const float* gout, const float* static_syn, const float* 
                        const float* weight, float* grad_dynamic, float* grad_weight,
                        float* grad_bias, float* grad_static,
                        int B, int T, int H, int W, int dpc, void* stream);
+/* The same backward in ONE pass over the video gradient, without floating-point atomics on the 327 hallucinator sums: every
+ * (video, 8-row band) block writes its sums to a row of `scratch` (>= B * ceil(H/8) * 328 floats) and a finishing launch adds
+ * the rows in block order, so the hallucinator gradient is bitwise reproducible; grad_weight / grad_bias are accumulated
+ * (+=), grad_dynamic rows are written with plain stores when unique_rows != 0 (no two videos select the same dynamic memory,
+ * distill_s2d_ms.py:405) and with atomics otherwise.  grad_static is not produced (--no_train_static path). */
+int vd_compose_bwd_fused_f32(const float* gout, const float* static_syn, const float* dynamic_syn,
+                             const int64_t* static_idx, const int64_t* label, const int64_t* dynamic_idx,
+                             const float* weight, float* grad_dynamic, float* grad_weight, float* grad_bias,
+                             float* scratch, int64_t scratch_floats, int unique_rows,
+                             int B, int T, int H, int W, int dpc, void* stream);
 
 /* ------------------------------------------------- distribution-matching loss
  * Replaces mean/sub/square/sum and their backward at distill_baseline.py:351,

@@ -38,7 +38,7 @@ def test_buffer_then_mtt_and_dm(tmp_path):
     tr = _run('s2d_parser', 'main_s2d', f'--method DM --dataset {DATA} --vpc 1 --spc 2 --dpc 2 --frames 8 --batch_real 4 --no_train_static '
                                         f'--lr_dynamic 10 --lr_hal 0.01 --Iteration 2 --eval_it 100 --num_eval 1 --epoch_eval_train 1 '
                                         f'--batch_train 4 --save_path {save} --run_name t')
-    d = os.path.join(save, 'S2D_DM', 't')
+    d = os.path.join(save, 'S2D_multis_DM', 't')
     dyn = torch.load(os.path.join(d, 'dynamic_0.pt'))
     hal = torch.load(os.path.join(d, 'hal_0.pt'))
     assert tuple(dyn.shape) == (6, 8, 1, 64, 64) and set(hal) == {'0.encoder.weight', '0.encoder.bias'}

@@ -157,3 +157,14 @@ def test_video_sharded_dataset_covers_every_draw_exactly_once():
             assert abs(len(seg) - n / world) <= 3
     assert sorted(seen) == sorted(real_idx.reshape(-1).tolist())
     assert torch.equal(sums, torch.tensor([float(real_idx[c].sum()) for c in range(C)]))
+    # gather plan: padded per-rank blocks, concatenated in rank order, indexed back into sample order
+    n_max, gidx = shards[1].gather_plan(real_idx)
+    blocks = []
+    for s in shards:
+        loc, _ = s.local_sample(real_idx)
+        v = s.videos[loc][:, 0, 0, 0, 0]
+        assert v.numel() <= n_max
+        blocks.append(torch.cat([v, torch.full((n_max - v.numel(),), -1.0)]))
+    gathered = torch.cat(blocks)
+    assert torch.equal(gathered[gidx].long().view(C, n), torch.from_numpy(real_idx))
+    assert all(torch.equal(s.gather_plan(real_idx)[1], gidx) for s in shards)

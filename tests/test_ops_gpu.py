@@ -282,3 +282,42 @@ def test_class_sum_ragged_matches_torch():
     for r in range(5):
         seq = seq + emb[r]
     assert torch.equal(out[0], seq)
+
+
+@pytest.mark.parametrize('T,H,W,vpc', [(8, 64, 64, 1), (16, 112, 112, 1), (4, 20, 24, 2)])
+def test_fused_composer_backward_is_exact_and_reproducible(T, H, W, vpc):
+    """vd_compose_bwd_fused_f32 (one pass, fixed-order block sums) against fp64 autograd of utils.py:1186-1197 and against
+    itself: two runs give bitwise identical hallucinator gradients (no floating-point atomics)."""
+    from video_distillation_b200 import ops
+    g = torch.Generator().manual_seed(T + H)
+    C, spc, dpc = 5, 2 * vpc, 2 * vpc
+    static = torch.randn(C * spc, 3, H, W, generator=g)
+    dyn = torch.randn(C, dpc, T, 1, H, W, generator=g)
+    w = torch.randn(3, 4, 3, 3, 3, generator=g) * 0.2
+    b = torch.randn(3, generator=g) * 0.1
+    label = torch.arange(C).repeat_interleave(vpc)
+    idx = torch.arange(C * vpc) % vpc
+    didx = 2 * idx + torch.randint(2, (C * vpc,), generator=g)
+    sidx = spc * label + 2 * idx + torch.randint(2, (C * vpc,), generator=g)
+    gout = torch.randn(C * vpc, T, 3, H, W, generator=g)
+
+    def run(unique):
+        d = dyn.cuda().requires_grad_(True)
+        wc, bc = w.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+        out = ops.compose(static.cuda(), d, wc, bc, sidx.cuda(), label.cuda(), didx.cuda(), unique_rows=unique)
+        out.backward(gout.cuda())
+        return out.detach(), d.grad, wc.grad, bc.grad
+    o1, gd1, gw1, gb1 = run(True)
+    o2, gd2, gw2, gb2 = run(True)
+    o3, gd3, gw3, gb3 = run(False)
+    assert torch.equal(gw1, gw2) and torch.equal(gb1, gb2) and torch.equal(gd1, gd2)
+    assert torch.equal(gd1, gd3) and torch.equal(gw1, gw3)            # atomics onto zeros with distinct rows: the same bits
+    # fp64 reference
+    d64 = dyn.double().requires_grad_(True)
+    w64, b64 = w.double().requires_grad_(True), b.double().requires_grad_(True)
+    x = torch.cat([static.double()[sidx].unsqueeze(2).expand(-1, -1, T, -1, -1), d64[label, didx].permute(0, 2, 1, 3, 4)], 1)
+    ref = F.conv3d(x, w64, b64, padding=1).permute(0, 2, 1, 3, 4)
+    ref.backward(gout.double())
+    rel = lambda a, r: float((a.double().cpu() - r).norm() / r.norm())
+    assert rel(o1, ref.detach()) < 1e-6
+    assert rel(gd1, d64.grad) < 1e-6 and rel(gw1, w64.grad) < 1e-5 and rel(gb1, b64.grad) < 1e-5

@@ -614,6 +614,10 @@ int compose_bwd_data_tiled(const float* gout, const int64_t* label, const int64_
                            float* grad_dynamic, int B, int T, int H, int W, int dpc, cudaStream_t stream);
 int compose_bwd_wdyn_tiled(const float* gout, const float* dynamic_syn, const int64_t* label, const int64_t* dynamic_idx,
                            float* grad_weight, float* grad_bias, int B, int T, int H, int W, int dpc, cudaStream_t stream);
+int compose_bwd_fused(const float* gout, const float* static_syn, const float* dynamic_syn, const int64_t* static_idx,
+                      const int64_t* label, const int64_t* dynamic_idx, const float* weight, float* grad_dynamic, float* grad_weight,
+                      float* grad_bias, float* scratch, int64_t scratch_floats, int unique_rows, int B, int T, int H, int W, int dpc,
+                      cudaStream_t stream);
 }  // namespace vd
 
 extern "C" int vd_compose_fwd_f32(const float* static_syn, const float* dynamic_syn, const int64_t* static_idx,
@@ -674,6 +678,25 @@ extern "C" int vd_compose_bwd_f32(const float* gout, const float* static_syn, co
         }
     }
     return 0;
+}
+
+// One-pass deterministic backward of the composer (compose_tiled.cu: compose_bwd_fused_kernel): grad_dynamic rows written (or
+// accumulated with atomics when unique_rows == 0), grad_weight / grad_bias += block sums added in a fixed order.  Falls back to
+// vd_compose_bwd_f32 when the geometry is not covered by the tiled kernels.
+extern "C" int vd_compose_bwd_fused_f32(const float* gout, const float* static_syn, const float* dynamic_syn,
+                                        const int64_t* static_idx, const int64_t* label, const int64_t* dynamic_idx,
+                                        const float* weight, float* grad_dynamic, float* grad_weight, float* grad_bias,
+                                        float* scratch, int64_t scratch_floats, int unique_rows,
+                                        int B, int T, int H, int W, int dpc, void* stream) {
+    VD_REQUIRE(gout && static_syn && dynamic_syn && static_idx && label && dynamic_idx && weight && grad_dynamic && grad_weight && scratch,
+               "compose_bwd_fused: NULL pointer");
+    VD_REQUIRE(B >= 0 && T > 0 && H > 0 && W > 0 && dpc > 0 && T <= 65535 && B <= 65535, "compose_bwd_fused: bad extent");
+    if (B == 0) return 0;
+    const int rc = compose_bwd_fused(gout, static_syn, dynamic_syn, static_idx, label, dynamic_idx, weight, grad_dynamic, grad_weight,
+                                     grad_bias, scratch, scratch_floats, unique_rows, B, T, H, W, dpc, (cudaStream_t)stream);
+    if (rc != 1) return rc;
+    return vd_compose_bwd_f32(gout, static_syn, dynamic_syn, static_idx, label, dynamic_idx, weight, grad_dynamic, grad_weight,
+                              grad_bias, nullptr, B, T, H, W, dpc, stream);
 }
 
 extern "C" int vd_class_mean_f32(const float* emb, float* mean, int C, int n, int D, void* stream) {

@@ -14,7 +14,9 @@ loss + d loss/d embedding come out of one kernel.  Multi-GPU: the synthetic bran
 every class are spread over the ranks (``DeviceDataset(shard='video')``) and completed by an all-reduce
 of the (C, D) partial embedding sums; every rank replays the full RNG streams and slices its part, so
 sampling is bit-identical to a single-GPU run.  Per iteration two small collectives cross NVLink:
-the partial sums (C*D floats) and [hallucinator grad | loss] (328 floats).
+an all-gather of the real embeddings (C*n*D floats, reduced in single-GPU order: class means bitwise
+independent of the world size; `exact_means=False` all-reduces (C, D) partial sums instead) and
+[hallucinator grad | loss] (328 floats).
 """
 import numpy as np
 import torch
@@ -142,6 +144,7 @@ class DeviceDataset:
             pos.append(len(self.indices_class[lab]))
             self.indices_class[lab].append(i)
         self.rank, self.world = rank, world
+        self.pos_in_class = np.asarray(pos, dtype=np.int64)
         self.owned = owned_classes(num_classes, rank, world)
         if shard == 'class':
             self.keep = [i for i, lab in enumerate(labels) if lab % world == rank]
@@ -192,6 +195,24 @@ class DeviceDataset:
         offsets = np.zeros(loc_all.shape[0] + 1, dtype=np.int32)
         np.cumsum(mask.sum(1), out=offsets[1:])
         return self._to_device(np.ascontiguousarray(loc_all[mask])), self._to_device(offsets)
+
+    def gather_plan(self, real_idx):
+        """shard='video': how the ranks' local shares of a (C, n) draw reassemble into sample order.  Every rank can compute
+        this for ALL ranks (the draw and the position rule are replicated).  Returns (n_max, index) where n_max is the largest
+        local share and index (device int64, C*n) addresses the (world * n_max, D) all-gathered embedding rows such that
+        gathered[index].view(C, n, D) is the embedding of real_idx[c, j] — the order a single GPU computes them in."""
+        real_idx = np.asarray(real_idx)
+        C, n = real_idx.shape
+        owner = self.pos_in_class[real_idx] % self.world                   # (C, n) rank holding each sampled video
+        flat_owner = owner.reshape(-1)
+        counts = np.bincount(flat_owner, minlength=self.world)
+        n_max = int(counts.max())
+        # a rank's local rows are in class-major / sample order = the order of appearance in the flattened draw
+        rank_pos = np.zeros(C * n, dtype=np.int64)
+        for r in range(self.world):
+            m = flat_owner == r
+            rank_pos[m] = np.arange(int(m.sum()))
+        return n_max, self._to_device(np.ascontiguousarray(flat_owner.astype(np.int64) * n_max + rank_pos))
 
     def local_index(self, global_idx):
         """global video indices of owned classes -> rows of ``self.videos`` (device int64)."""
@@ -366,6 +387,7 @@ class DMS2DTrainer:
         # and nothing of the 80..520 MB dynamic memory crosses NVLink during training (`full_memories` gathers for eval / save).
         # Every rank receives the same full-size init (same seeds / broadcast) and slices its rows.
         self.sharded_memories = self.world > 1
+        self.exact_means = True          # video-sharded real set: all-gather embeddings (bitwise = 1 GPU) instead of partial sums
         if self.sharded_memories:
             own_cpu = torch.as_tensor(self.owned, dtype=torch.long)
             static_syn = static_syn.detach().cpu().view(num_classes, spc, *static_syn.shape[1:])[own_cpu].reshape(-1, *static_syn.shape[1:])
@@ -450,9 +472,11 @@ class DMS2DTrainer:
             # rows of the class shard: class c = own[k] lives at local position k (static rows spc*k .. spc*k + spc - 1)
             lab_loc = torch.arange(n_own, device=self.device).repeat_interleave(vpc)
             image_syn = self.hal.compose(self.static_syn, self.dynamic_syn, static_idx[sel] - self.spc * (label[sel] - lab_loc),
-                                         lab_loc, dynamic_idx[sel])
+                                         lab_loc, dynamic_idx[sel], unique_rows=indices is None)
         else:
-            image_syn = self.hal.compose(self.static_syn, self.dynamic_syn, static_idx[sel], label[sel], dynamic_idx[sel])
+            # (label, dynamic_idx) pairs of distill_s2d_ms.py:405 are distinct by construction; caller-supplied indices may not be
+            image_syn = self.hal.compose(self.static_syn, self.dynamic_syn, static_idx[sel], label[sel], dynamic_idx[sel],
+                                         unique_rows=indices is None)
         tc = self.embedder.tc
         fused_syn = tc is not None and self.syn_on_tensor_cores is True
         joint = (fused_syn and real_batch is None and self.ds.x0 is not None
@@ -474,8 +498,20 @@ class DMS2DTrainer:
             ridx = real_batch_index if real_batch_index is not None else torch.arange(real_batch.shape[0], device=self.device)
             emb_real = self.embedder(real_batch, ridx)
         D = emb_real.shape[1]
-        if video_sharded:
-            # (C, D) partial sums of this rank's videos -> all-reduce -> the class means of the classes this rank owns
+        if video_sharded and self.exact_means:
+            # all-gather the ranks' embedding rows (C*n*D floats: 26 MB at the bench shape, ~0.1 ms over NVLink), put them back
+            # in sample order and reduce them with the SAME kernel in the SAME order as a single GPU: the class means — and so
+            # the loss, routing and memory gradients — are bitwise independent of the world size
+            n_max, gidx = self.ds.gather_plan(real_idx)
+            pad = torch.zeros(n_max, D, device=self.device) if emb_real.shape[0] < n_max else None
+            mine = emb_real if pad is None else torch.cat([emb_real, pad[:n_max - emb_real.shape[0]]])
+            gathered = torch.empty(self.world * n_max, D, device=self.device)
+            dist.all_gather_into_tensor(gathered, mine.contiguous())
+            own_rows = gidx.view(C, self.batch_real)[self.owned_t].reshape(-1)
+            mean_real = ops.class_mean(gathered[own_rows].view(n_own, self.batch_real, D))
+        elif video_sharded:
+            # cheaper variant: (C, D) partial sums of this rank's videos -> all-reduce (0.4 MB); the summation order differs
+            # from a single GPU's by re-association (1e-7 relative)
             sums = ops.class_sum_ragged(emb_real, offsets, C)
             dist.all_reduce(sums, op=dist.ReduceOp.SUM)
             # tensor divisor: IEEE division like the class_mean kernel (a Python scalar would become a reciprocal multiply)

@@ -332,7 +332,8 @@ def avgpool3d_2(x):
 # ------------------------------------------------------------------ composer
 class _Compose(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, static_syn, dynamic_syn, weight, bias, static_idx, label, dynamic_idx):
+    def forward(ctx, static_syn, dynamic_syn, weight, bias, static_idx, label, dynamic_idx, unique_rows=False):
+        ctx.unique_rows = bool(unique_rows)
         static_syn, dynamic_syn, weight, bias = map(_f32c, (static_syn, dynamic_syn, weight, bias))
         C, dpc, T, one, H, W = dynamic_syn.shape
         assert one == 1 and tuple(weight.shape) == (3, 4, 3, 3, 3) and static_syn.shape[1:] == (3, H, W)
@@ -356,15 +357,24 @@ class _Compose(torch.autograd.Function):
         gw = torch.zeros_like(weight) if (need_w or need_b) else None
         gb = torch.zeros(3, dtype=torch.float32, device=gout.device) if (need_w or need_b) else None
         gs = torch.zeros_like(static_syn) if need_s else None
-        check(lib().vd_compose_bwd_f32(ptr(gout), ptr(static_syn), ptr(dynamic_syn), ptr(sidx), ptr(label), ptr(didx),
-                                       ptr(weight), ptr(gd), ptr(gw), ptr(gb), ptr(gs), B, T, H, W, dpc, stream()), 'compose_bwd')
-        return gs, (gd if need_d else None), (gw if need_w else None), (gb if need_b else None), None, None, None
+        if gw is not None and gs is None:
+            # one pass over the video gradient, block sums added in a fixed order (no float atomics): reproducible bit for bit
+            scratch = torch.empty(B * ((H + 7) // 8) * 328, dtype=torch.float32, device=gout.device)
+            check(lib().vd_compose_bwd_fused_f32(ptr(gout), ptr(static_syn), ptr(dynamic_syn), ptr(sidx), ptr(label), ptr(didx),
+                                                 ptr(weight), ptr(gd), ptr(gw), ptr(gb), ptr(scratch), scratch.numel(),
+                                                 int(ctx.unique_rows), B, T, H, W, dpc, stream()), 'compose_bwd_fused')
+        else:
+            check(lib().vd_compose_bwd_f32(ptr(gout), ptr(static_syn), ptr(dynamic_syn), ptr(sidx), ptr(label), ptr(didx),
+                                           ptr(weight), ptr(gd), ptr(gw), ptr(gb), ptr(gs), B, T, H, W, dpc, stream()), 'compose_bwd')
+        return gs, (gd if need_d else None), (gw if need_w else None), (gb if need_b else None), None, None, None, None
 
 
-def compose(static_syn, dynamic_syn, weight, bias, static_idx, label, dynamic_idx):
+def compose(static_syn, dynamic_syn, weight, bias, static_idx, label, dynamic_idx, unique_rows=False):
     """hal(static_syn[static_idx], dynamic_syn[label, dynamic_idx]) in one kernel
-    (distill_s2d_ms.py:409-412; utils.py:1186-1197, mode='concat')."""
-    return _Compose.apply(static_syn, dynamic_syn, weight, bias, static_idx, label, dynamic_idx)
+    (distill_s2d_ms.py:409-412; utils.py:1186-1197, mode='concat').  unique_rows: the caller guarantees that no two videos of
+    the batch select the same dynamic memory (true for the reference's index formula, :405): the backward then writes the
+    memory gradient with plain stores instead of atomics."""
+    return _Compose.apply(static_syn, dynamic_syn, weight, bias, static_idx, label, dynamic_idx, unique_rows)
 
 
 # ------------------------------------------------------------------ DM loss / optimiser kernels

@@ -64,8 +64,8 @@ class Conv3DNet(nn.Module):
         self.mode = mode
         self.encoder = nn.Conv3d(in_channel, mid_channel, kernel_size, padding=1)   # parameters + default init only
 
-    def compose(self, static_syn, dynamic_syn, static_idx, label, dynamic_idx):
-        return ops.compose(static_syn, dynamic_syn, self.encoder.weight, self.encoder.bias, static_idx, label, dynamic_idx)
+    def compose(self, static_syn, dynamic_syn, static_idx, label, dynamic_idx, unique_rows=False):
+        return ops.compose(static_syn, dynamic_syn, self.encoder.weight, self.encoder.bias, static_idx, label, dynamic_idx, unique_rows)
 
     def forward(self, static, dynamic):
         b = dynamic.shape[0]
