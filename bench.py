@@ -623,6 +623,32 @@ def run_ours(args):
     ms_res = timed(step_resident_e2e, e2e_steps)
     e2e_res = e2e_steps / (ms_res / 1000.0)
 
+    # ---- per-phase device timeline of the resident step (CUDA events between the phases; max over ranks per phase)
+    timeline = None
+    if args.timeline:
+        tr.timeline = []
+        n_tl = 5
+        host_t0 = time.perf_counter()
+        for _ in range(n_tl):
+            step_resident()
+        host_enqueue_ms = (time.perf_counter() - host_t0) * 1e3 / n_tl
+        torch.cuda.synchronize()
+        marks, tr.timeline = tr.timeline, None
+        per = len(marks) // n_tl
+        names = [marks[i][0] for i in range(1, per)]
+        acc = torch.zeros(per - 1, device=dev)
+        for k in range(n_tl):
+            for i in range(1, per):
+                acc[i - 1] += marks[k * per + i - 1][1].elapsed_time(marks[k * per + i][1])
+        acc /= n_tl
+        mx, mn = acc.clone(), acc.clone()
+        if world > 1:
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+        timeline = {'phases_ms_max_over_ranks': {n: float(v) for n, v in zip(names, mx)},
+                    'phases_ms_min_over_ranks': {n: float(v) for n, v in zip(names, mn)},
+                    'sum_ms': float(mx.sum()), 'host_enqueue_ms_per_step_rank0': host_enqueue_ms, 'steps': n_tl}
+
     # ---- memory-bound kernels inside the real step: CUPTI durations (torch.profiler) vs algorithmic bytes
     mem_kernels = None
     if rank == 0 and world == 1:
@@ -717,7 +743,7 @@ def run_ours(args):
         'e2e_resident': {'value': e2e_res, 'unit': 'it/s', 'h2d_bytes_per_step': int(C * BATCH_REAL * 8),
                          'd2h_bytes_per_step': 4, 'steps': e2e_steps,
                          'note': 'real set uploaded once; per step the host sends the sampled index table and reads the loss'},
-        'throughput_mode': throughput, 'reference_torch_cuda': ref_cuda,
+        'throughput_mode': throughput, 'reference_torch_cuda': ref_cuda, 'timeline': timeline,
         'roofline': roofline, 'memory_kernels': mem_kernels, 'cpu_baseline': cpu}
     print(json.dumps(out))
     if world > 1:
@@ -749,6 +775,7 @@ def main():
     ap.add_argument('--precision', default='f16x3', choices=['f16x3', 'bf16', 'fp32'],
                     help='f16x3 (default): fused tcgen05 pipeline on fp16 hi/lo operand pairs, the parity mode; bf16: single-pass '
                          'throughput mode; fp32: exact CUDA-core kernels')
+    ap.add_argument('--timeline', action='store_true', help='add a per-phase device timeline of the step (CUDA events, max / min over ranks)')
     ap.add_argument('--no-throughput-mode', action='store_true', help='skip the single-pass bf16 line reported beside the default mode')
     ap.add_argument('--no-reference-cuda', action='store_true', help="skip the reference's own modules on this GPU (cuDNN)")
     ap.add_argument('--max-batch', type=int, default=640)

@@ -397,6 +397,13 @@ class DMS2DTrainer:
         self._bufs = {}
         self.embedder = _RealEmbedder(frames, self.im_size, self.device, precision, max_batch)
         self.last = {}
+        self.timeline = None             # set to [] to collect (phase name, CUDA event) marks of every step (bench.py --timeline)
+
+    def _mark(self, name):
+        if self.timeline is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.timeline.append((name, ev))
 
     # ------------------------------------------------------------------ pieces
     def sample_syn_indices(self):
@@ -453,6 +460,7 @@ class DMS2DTrainer:
     def _step(self, net=None, net_seed=None, indices=None, real_idx=None, real_batch=None, real_batch_index=None,
               real_batch_offsets=None):
         C, vpc = self.C, self.vpc
+        self._mark('begin')
         if net is None:
             if self.init_on_device:
                 if self._pool is None:
@@ -461,6 +469,7 @@ class DMS2DTrainer:
             else:
                 net = frozen_convnet3d(self.channel, C, self.im_size, self.frames, self.device, seed=net_seed)
         self.embedder.load(net)
+        self._mark('fresh net + weight images')
         label, dynamic_idx, static_idx = indices if indices is not None else self.sample_syn_indices()
         if real_idx is None:
             real_idx = self.ds.sample_all_classes(self.batch_real)          # (C, batch_real) global, host
@@ -477,6 +486,7 @@ class DMS2DTrainer:
             # (label, dynamic_idx) pairs of distill_s2d_ms.py:405 are distinct by construction; caller-supplied indices may not be
             image_syn = self.hal.compose(self.static_syn, self.dynamic_syn, static_idx[sel], label[sel], dynamic_idx[sel],
                                          unique_rows=indices is None)
+        self._mark('composer forward')
         tc = self.embedder.tc
         fused_syn = tc is not None and self.syn_on_tensor_cores is True
         joint = (fused_syn and real_batch is None and self.ds.x0 is not None
@@ -498,6 +508,7 @@ class DMS2DTrainer:
             ridx = real_batch_index if real_batch_index is not None else torch.arange(real_batch.shape[0], device=self.device)
             emb_real = self.embedder(real_batch, ridx)
         D = emb_real.shape[1]
+        self._mark('embed (conv 0/1/2)')
         if video_sharded and self.exact_means:
             # all-gather the ranks' embedding rows (C*n*D floats: 26 MB at the bench shape, ~0.1 ms over NVLink), put them back
             # in sample order and reduce them with the SAME kernel in the SAME order as a single GPU: the class means — and so
@@ -524,19 +535,23 @@ class DMS2DTrainer:
             emb_syn = tc.embed_autograd(image_syn).view(n_own, vpc, D)
         else:
             emb_syn = net.embed(image_syn).view(n_own, vpc, D)
+        self._mark('class means (+ all-gather)')
         loss = ops.dm_loss(mean_real, emb_syn)
         for p in (self.dynamic_syn, self.static_syn, *self.hal.parameters()):
             p.grad = None
         loss.backward()
+        self._mark('loss + backward (dgrads, composer)')
         # ---- combine ranks: ONE small all-reduce [hallucinator grads (327) | loss]; the memory gradients are class-local
         loss_d = loss.detach().reshape(1).clone()
         allreduce_sum_([self.hal.encoder.weight.grad, self.hal.encoder.bias.grad, loss_d])
+        self._mark('all-reduce [hal grad | loss]')
         # ---- optimizer steps (distill_s2d_ms.py:432-435), dense momentum SGD
         if self.train_static:
             self._sgd('static', self.static_syn, self.static_syn.grad, self.lr_static)
         self._sgd('dynamic', self.dynamic_syn, self.dynamic_syn.grad, self.lr_dynamic)
         self._sgd('hal_w', self.hal.encoder.weight, self.hal.encoder.weight.grad, self.lr_hal)
         self._sgd('hal_b', self.hal.encoder.bias, self.hal.encoder.bias.grad, self.lr_hal)
+        self._mark('momentum SGD')
         self.last = dict(label=label, dynamic_idx=dynamic_idx, static_idx=static_idx, real_idx=real_idx,
                          emb_syn=emb_syn.detach(), mean_real=mean_real, image_syn=image_syn.detach())
         return loss_d[0]
