@@ -9,10 +9,11 @@ from video_distillation_b200.networks import ConvNet3D  # noqa: E402
 from video_distillation_b200.tc import TcConvNet3D  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 296
+SPLIT = len(sys.argv) > 2 and sys.argv[2] == 'x3'          # f16x3 (split-fp16) pipeline instead of single-pass bf16
 T, HW = 16, 112
 torch.manual_seed(0)
 net = ConvNet3D(3, 50, 128, 3, 'relu', 'none', 'maxpooling', T, (HW, HW)).cuda()
-tc = TcConvNet3D(T, HW, HW, 'cuda', max_batch=B)
+tc = TcConvNet3D(T, HW, HW, 'cuda', max_batch=B, split=SPLIT)
 f = net.features
 tc.load_weights(f[0].weight, f[0].bias, f[3].weight, f[3].bias, f[6].weight, f[6].bias)
 video = torch.randn(B, T, 3, HW, HW, device='cuda')
