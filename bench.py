@@ -750,18 +750,267 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------ MTT + S2D (configs[3])
+def mtt_flops_per_iteration():
+    """Algorithmic FLOPs of one MTT+S2D iteration, BASELINE.md section 3: "<= 45.3 TFLOP" for syn_steps = 10 x 50 videos of the
+    U shape (per step and video: fprop + dgrad + wgrad of the inner gradient and their second-order counterparts in
+    grand_loss.backward(), ~8.2 conv-equivalents of 11.002 GFLOP), scaled linearly to other shapes."""
+    return 45.3e12 * (F_EMBED / 11.002e9) * (SYN_STEPS / 10.0) * (C * VPC / 50.0)
+
+
+def mtt_config(n_gpus):
+    return {'workload': WORKLOAD_DESC,
+            'parallelism': f'every unrolled step batch sharded i%{n_gpus}, flat-parameter gradient all-reduced (NCCL)' if n_gpus > 1 else 'single GPU',
+            'syn_steps': SYN_STEPS, 'batch_syn': C * VPC,
+            'l2_policy': 'each unrolled step re-packs activations and weights (> L2); 14.6 MB flat parameters per expert snapshot'}
+
+
+class ReferenceMTTLoop:
+    """distill_s2d_ms.py:89-108 state and the VERBATIM MTT iteration body (:196-300) through the reference's own modules
+    (utils.get_network, reparam_module.ReparamModule, utils.Conv3DNet, torch.optim.SGD).  `batch_syn` / `syn_steps` smaller
+    than the workload's give a bounded sample (cost is linear in steps x videos)."""
+
+    def __init__(self, ref_utils, ref_reparam, device, syn_steps, batch_syn):
+        self.u, self.rp, self.device, self.syn_steps, self.batch_syn = ref_utils, ref_reparam, device, syn_steps, batch_syn
+        torch.manual_seed(0)
+        self.static_syn = torch.randn(size=(C * SPC, 3, HW, HW), dtype=torch.float).detach().to(device).requires_grad_(False)
+        self.dynamic_syn = torch.randn(size=(C, DPC, T, 1, HW, HW), dtype=torch.float).detach().to(device).requires_grad_(True)
+        self.hals = torch.nn.ModuleList([ref_utils.Conv3DNet()]).to(device)
+        self.syn_lr = torch.tensor(0.01).detach().to(device).requires_grad_(True)
+        self.optimizer_dynamic = torch.optim.SGD([self.dynamic_syn], lr=LR_DYNAMIC, momentum=0.95)
+        self.optimizer_hals = torch.optim.SGD(self.hals.parameters(), lr=LR_HAL, momentum=0.95)
+        self.optimizer_lr = torch.optim.SGD([self.syn_lr], lr=1e-5, momentum=0.9)
+        self.criterion = torch.nn.CrossEntropyLoss().to(device)
+        base = ref_utils.get_network('ConvNet3D', 3, C, (HW, HW), frames=T, dist=False)
+        self.start = [p.detach().clone() for p in base.parameters()]
+        self.target = [p.detach().clone() + 0.01 * torch.randn_like(p) for p in base.parameters()]
+
+    def iteration(self):
+        dev, num_classes, vpc, spc = self.device, C, VPC, SPC
+        student_net = self.u.get_network('ConvNet3D', 3, num_classes, (HW, HW), frames=T, dist=False).to(dev)
+        student_net = self.rp.ReparamModule(student_net)
+        student_net.train()
+        num_params = sum([np.prod(p.size()) for p in (student_net.parameters())])
+        target_params = torch.cat([p.data.to(dev).reshape(-1) for p in self.target], 0)
+        student_params = [torch.cat([p.data.to(dev).reshape(-1) for p in self.start], 0).requires_grad_(True)]
+        starting_params = torch.cat([p.data.to(dev).reshape(-1) for p in self.start], 0)
+        indices_chunks = []
+        for step in range(self.syn_steps):
+            if not indices_chunks:
+                indices = torch.randperm(num_classes * vpc, device=dev)
+                indices_chunks = list(torch.split(indices, self.batch_syn))
+            these_indices = indices_chunks.pop()
+            label = these_indices // vpc
+            idx = these_indices % vpc
+            dynamic_idx = 2 * idx + torch.randint(2, (these_indices.shape[0],), device=dev)
+            static_idx = spc * label + 2 * idx + torch.randint(2, (these_indices.shape[0],), device=dev)
+            static = self.static_syn[static_idx, :, :, :]
+            dynamic = self.dynamic_syn[label, dynamic_idx, :, :, :, :]
+            x = self.hals[0](static, dynamic)
+            this_y = label.long()
+            x = student_net(x, flat_param=student_params[-1])
+            loss = self.criterion(x, this_y)
+            grad = torch.autograd.grad(loss, student_params[-1], create_graph=True)[0]
+            student_params.append(student_params[-1] - self.syn_lr * grad)
+        param_loss = torch.nn.functional.mse_loss(student_params[-1], target_params, reduction='sum')
+        param_dist = torch.nn.functional.mse_loss(starting_params, target_params, reduction='sum')
+        param_loss = param_loss / num_params
+        param_dist = param_dist / num_params
+        grand_loss = param_loss / param_dist
+        self.optimizer_dynamic.zero_grad()
+        self.optimizer_hals.zero_grad()
+        self.optimizer_lr.zero_grad()
+        grand_loss.backward()
+        self.optimizer_dynamic.step()
+        self.optimizer_hals.step()
+        self.optimizer_lr.step()
+        self.syn_lr.data = self.syn_lr.data.clip(min=0.001)
+        return grand_loss.item()
+
+
+def import_reference_reparam(path):
+    saved = list(sys.path)
+    hidden = {n: sys.modules.pop(n) for n in ('reparam_module',) if n in sys.modules}
+    sys.path[:] = [path] + [q for q in saved if os.path.abspath(q or '.') != ROOT]
+    try:
+        import reparam_module as ref_reparam          # noqa
+    finally:
+        sys.modules.pop('reparam_module', None)
+        sys.modules.update(hidden)
+        sys.path[:] = saved
+    return ref_reparam
+
+
+def reference_mtt_cpu_rate(threads, syn_steps=2, batch_syn=4):
+    """One reference MTT iteration on the host cores over a bounded sample (syn_steps x batch_syn of the workload's 10 x 50);
+    returns (it/s scaled linearly in steps x videos, seconds, description) or None when the reference modules are absent."""
+    refdir = reference_dir()
+    if refdir is None:
+        return None
+    ref_utils, _ = import_reference(refdir)
+    torch.set_num_threads(threads)
+    loop = ReferenceMTTLoop(ref_utils, import_reference_reparam(refdir), 'cpu', syn_steps, batch_syn)
+    t0 = time.perf_counter()
+    loss = loop.iteration()
+    dt = time.perf_counter() - t0
+    assert np.isfinite(loss)
+    scale = (SYN_STEPS * C * VPC) / (syn_steps * batch_syn)
+    desc = (f'{syn_steps} of {SYN_STEPS} unrolled steps x {batch_syn} of {C * VPC} videos {T}x3x{HW}x{HW} through the reference\'s own modules '
+            f'(ReparamModule student, loop body of distill_s2d_ms.py:196-300, incl. grand_loss.backward()), time scaled by {scale:.1f}')
+    return 1.0 / (dt * scale), dt, desc
+
+
+def run_mtt_reference(args):
+    if int(os.environ.get('RANK', '0')) != 0:
+        return
+    threads = os.cpu_count() or 1
+    vals, secs, desc = [], [], ''
+    for i in range(max(1, args.warmup + args.steps)):
+        r = reference_mtt_cpu_rate(threads)
+        if r is None:
+            print(json.dumps({'impl': 'reference', 'unavailable': 'reference modules not found (baseline/_ref, $VD_REFERENCE, /root/reference)'}))
+            return
+        if i >= args.warmup:
+            vals.append(r[0]); secs.append(r[1]); desc = r[2]
+    v = float(np.mean(vals))
+    print(json.dumps({'impl': 'reference', 'metric': 'MTT+S2D distill iters/sec', 'value': v, 'unit': 'it/s', 'n_gpus': args.gpus,
+                      'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1000.0 * float(np.mean(secs)), 'ms_per_full_iteration': 1000.0 / v,
+                      'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                      'config': mtt_config(args.gpus),
+                      'cpu_baseline': {'value': v, 'unit': 'it/s', 'cores': threads, 'kind': 'reference', 'sample': desc, 'sample_seconds': float(np.mean(secs))},
+                      'e2e': {'value': v, 'unit': 'it/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+
+
+def run_mtt_ours(args):
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', ''):
+            os.environ['NCCL_DEBUG'] = 'WARN'
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+        dist.init_process_group('nccl', device_id=dev)
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    from video_distillation_b200 import _lib
+    from video_distillation_b200.distill import MTTS2DTrainer
+    from video_distillation_b200.networks import ConvNet3D
+    precision = 'fp32' if args.precision == 'fp32' else 'bf16'
+    torch.manual_seed(0)
+    tr = MTTS2DTrainer(num_classes=C, im_size=(HW, HW), frames=T, vpc=VPC, spc=SPC, dpc=DPC, syn_steps=SYN_STEPS, lr_dynamic=LR_DYNAMIC,
+                       lr_hal=LR_HAL, device=dev, precision=precision)
+    base = ConvNet3D(3, C, 128, 3, 'relu', 'none', 'maxpooling', T, (HW, HW))
+    # synthetic expert segment: (start, target) parameter snapshots in pinned host memory, like a loaded replay buffer
+    start = [p.detach().clone().pin_memory() for p in base.parameters()]
+    target = [(p.detach() + 0.01 * torch.randn_like(p)).pin_memory() for p in base.parameters()]
+    start_dev, target_dev = [p.to(dev) for p in start], [p.to(dev) for p in target]
+    h2d = 2 * sum(p.numel() * 4 for p in start)
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        sync()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+    it_box = [0]
+    last = [None]
+
+    def step_resident():
+        it_box[0] += 1
+        last[0] = tr.step(start_dev, target_dev, net_seed=it_box[0])
+        return last[0]
+
+    def step_e2e():                        # expert snapshots come from (pinned) host memory every iteration, the grand loss is read back
+        it_box[0] += 1
+        return tr.step([p.to(dev, non_blocking=True) for p in start], [p.to(dev, non_blocking=True) for p in target], net_seed=it_box[0]).item()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    for _ in range(args.warmup):
+        step_resident()
+    _lib.launch_count_reset()
+    t_wall0 = time.time()
+    ms = timed(step_resident, args.steps)
+    sampler.mark(t_wall0, time.time())
+    launches = _lib.launch_count()
+    clocks = sampler.stop() if rank == 0 else None
+    value = args.steps / (ms / 1000.0)
+    check = {'iterations': args.warmup + args.steps, 'grand_loss_last': float(last[0]), 'syn_lr': float(tr.syn_lr.detach()),
+             'dynamic_syn_sumsq': float((tr.dynamic_syn.detach().double() ** 2).sum())}
+    ms_e = timed(step_e2e, args.steps)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks, peak_kind = measured_peaks()
+    peak = float(peaks.get('bf16_tflops_sustained', peaks.get('bf16_tflops', 1400.0)))
+    flops = mtt_flops_per_iteration()
+    achieved = flops / (ms / args.steps * 1e-3) / 1e12
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        r = reference_mtt_cpu_rate(os.cpu_count() or 1)
+        if r is not None:
+            cpu = {'value': r[0], 'unit': 'it/s', 'cores': os.cpu_count() or 1, 'kind': 'reference', 'sample': r[2], 'sample_seconds': r[1]}
+    print(json.dumps({
+        'metric': 'MTT+S2D distill iters/sec', 'value': value, 'unit': 'it/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+        'dtype': 'bf16x3 fprop / bf16 dgrad+wgrad' if precision == 'bf16' else 'f32', 'data': 'synthetic', 'config': mtt_config(world),
+        'impl_detail': {'precision': precision, 'student': 'ReparamModule over flat parameters; conv trio (fprop / dgrad / wgrad, closed under '
+                        'differentiation) on tcgen05 GEMMs' if precision == 'bf16' else 'exact fp32 CUDA-core conv trio'},
+        'clocks': clocks, 'gpu_launches': int(launches), 'check': check,
+        'e2e': {'value': args.steps / (ms_e / 1000.0), 'unit': 'it/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': 4, 'steps': args.steps,
+                'note': 'expert start / target snapshots copied from pinned host memory every iteration + grand_loss.item()'},
+        'roofline': {'bound': 'tensor', 'kernel': 'whole iteration (the conv-trio GEMMs ws_gemm_kernel<...> are ~all of it)', 'achieved': achieved,
+                     'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': None, 'peak_kind': f'bf16_tflops_sustained of {peak_kind}',
+                     'flops_per_iteration': flops,
+                     'note': 'algorithmic FLOPs of the unroll (BASELINE.md section 3, <= 45.3 TFLOP) / device time of the iteration; the trio still '
+                             'materialises im2col (wgrad) and column buffers (dgrad of conv 2) in HBM'},
+        'cpu_baseline': cpu}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 WORKLOAD_DESC = ''
 WORKLOADS = {   # name -> (C, T, HW, vpc, spc, dpc, batch_real, per_class, FLOP per video L0/L1/L2 (SURVEY §8d), BASELINE.json config)
     'U-ipc1': (50, 16, 112, 1, 2, 2, 64, 72, (2.832e9, 7.553e9, 0.617e9), 'configs[1]'),
     'U-ipc5': (50, 16, 112, 5, 10, 10, 64, 72, (2.832e9, 7.553e9, 0.617e9), 'configs[2]'),
     'K-ipc5': (400, 8, 64, 5, 10, 10, 64, 64, (0.462e9, 1.233e9, 0.077e9), 'configs[4]'),
+    # MTT + S2D (BASELINE.json configs[3]): batch_real / per_class unused; syn_steps = 10 unrolled student steps of C*vpc videos
+    'MTT-U-ipc1': (50, 16, 112, 1, 2, 2, 0, 0, (2.832e9, 7.553e9, 0.617e9), 'configs[3]'),
 }
+SYN_STEPS = 10
+MTT = False
 
 
 def set_workload(name):
-    global C, T, HW, VPC, SPC, DPC, BATCH_REAL, PER_CLASS, F_L0, F_L1, F_L2, F_EMBED, WORKLOAD_DESC
+    global C, T, HW, VPC, SPC, DPC, BATCH_REAL, PER_CLASS, F_L0, F_L1, F_L2, F_EMBED, WORKLOAD_DESC, MTT
     C, T, HW, VPC, SPC, DPC, BATCH_REAL, PER_CLASS, (F_L0, F_L1, F_L2), cfg = WORKLOADS[name]
     F_EMBED = F_L0 + F_L1 + F_L2
+    MTT = name.startswith('MTT')
+    if MTT:
+        WORKLOAD_DESC = (f'MTT+S2D miniUCF101-shape: {C} classes, videos {T}x3x{HW}x{HW}, vpc={VPC} spc={SPC} dpc={DPC}, syn_steps={SYN_STEPS} '
+                         f'unrolled ReparamModule student steps of batch_syn={C * VPC} videos against a synthetic expert segment (BASELINE.json {cfg})')
+        return
     WORKLOAD_DESC = (f'DM+S2D {"miniUCF101" if HW == 112 else "Kinetics-400"}-shape: {C} classes, videos {T}x3x{HW}x{HW}, vpc={VPC} spc={SPC} '
                      f'dpc={DPC}, batch_real={BATCH_REAL} (BASELINE.json {cfg}); fresh frozen ConvNet3D per step')
 
@@ -789,7 +1038,9 @@ def main():
                          '(parity-test shapes, timed on request)')
     args = ap.parse_args()
     set_workload(args.workload)
-    if args.impl == 'reference':
+    if MTT:
+        run_mtt_reference(args) if args.impl == 'reference' else run_mtt_ours(args)
+    elif args.impl == 'reference':
         run_reference(args)
     else:
         run_ours(args)
