@@ -221,7 +221,10 @@ class Params:
         self.copy_bytes = v[o:o + MAX_COPIES]; o += MAX_COPIES
         self.b_off16 = v[o:o + MAX_STEPS]; o += MAX_STEPS
         self.b_lbo16 = v[o:o + MAX_STEPS]; o += MAX_STEPS
-        self.a_off16 = v[o:o + MAX_STEPS]
+        self.a_off16 = v[o:o + MAX_STEPS]; o += MAX_STEPS
+        self.w_u_stride = v[o]; o += 1
+        self.Gt, self.n_wtiles = v[o], v[o + 1]; o += 2          # streamed weights with tile reuse inside a group (0: none)
+        self.a_in_group = v[o:o + 16]
 
 
 def _desc_gather(mem16, start_bytes, lbo_bytes, sbo_bytes, rows):
@@ -267,7 +270,10 @@ def emulate_layer(layer, pix_u16, wimg_u16, T, HW, B, tiles=None, fmt='bf16'):
                         a_start = (p.a_off16[j] + sa * p.a_sa_stride16) * 16
                         A = f32(_desc_gather(wimg, a_start, p.a_lbo16 * 16, p.a_sbo16 * 16, 128))
                     else:
-                        a_start = (st * p.n_steps + j) * 4096
+                        if p.Gt:      # MMA j of the stage reads tile a_in_group[j % G] of ring slot j // G (Gt tiles per slot)
+                            a_start = (st * p.n_wtiles + (j // p.G) * p.Gt + p.a_in_group[j % p.G]) * 4096
+                        else:
+                            a_start = (st * p.n_steps + j) * 4096
                         A = f32(_desc_gather(wimg, a_start, p.a_lbo16 * 16, p.a_sbo16 * 16, 128))
                     for a in range(p.n_acc):
                         b_start = (p.b_off16[j] + a * p.acc_delta16) * 16
@@ -479,31 +485,29 @@ def pack_w0s(w):
 
 
 def pack_w1s(w):
-    """(128,64,3,7,7) -> uint16 (3, 8, 74, 2, 128, 8) [kt][chunk][step][k][row][e]."""
-    hi, lo = (b.reshape(128, 8, 8, 3, 7, 7) for b in split_f16(w))        # row, chunk, e, kt, kh, kw
-    out = np.zeros((3, 8, 74, 2, 128, 8), np.uint16)
-    for step in range(74):
+    """(128,64,3,7,7) -> uint16 (3, 8, 25, 2, 2, 128, 8) [kt][chunk][pair][part hi/lo][k][row][e]; pair 0 = (tap 0, zeros), pair p = taps l1s_tap(2p-1), l1s_tap(2p)."""
+    parts = [b.reshape(128, 8, 8, 3, 7, 7) for b in split_f16(w)]        # row, chunk, e, kt, kh, kw
+    out = np.zeros((3, 8, 25, 2, 2, 128, 8), np.uint16)
+    for pair in range(25):
         for k in range(2):
-            if step < 49:
-                idx, src = step, hi
-            else:
-                idx, src = 2 * (step - 49) + k, lo
-            if idx >= 49:
+            idx = 2 * pair - 1 + k if pair else (-1 if k else 0)        # pair 0 = (tap 0, zeros), pair p = taps 2p-1, 2p
+            if idx < 0:
                 continue
             kh, kw = divmod(l1s_tap(idx), 7)
-            out[:, :, step, k, :, :] = src[:, :, :, :, kh, kw].transpose(3, 1, 0, 2)      # (kt, chunk, row, e)
+            for part in range(2):
+                out[:, :, pair, part, k, :, :] = parts[part][:, :, :, :, kh, kw].transpose(3, 1, 0, 2)      # (kt, chunk, row, e)
     return out
 
 
 def pack_w2s(w):
-    """(128,128,3,7,7) -> uint16 (7, 7, 4, 18, 2, 128, 8) [kh][kw][quarter][step][k][row][e]."""
-    hi, lo = (b.reshape(128, 4, 4, 8, 3, 7, 7) for b in split_f16(w))     # row, quarter, c, e, kt, kh, kw
-    out = np.zeros((7, 7, 4, 18, 2, 128, 8), np.uint16)
+    """(128,128,3,7,7) -> uint16 (7, 7, 4, 3, 2, 2, 2, 128, 8) [kh][kw][quarter][kt][pair][part][k][row][e]; chunk = 2*pair + k."""
+    parts = [b.reshape(128, 4, 4, 8, 3, 7, 7) for b in split_f16(w)]     # row, quarter, c, e, kt, kh, kw
+    out = np.zeros((7, 7, 4, 3, 2, 2, 2, 128, 8), np.uint16)
     for kt in range(3):
-        for s6 in range(6):
+        for pair in range(2):
             for k in range(2):
-                c, src = (s6, hi) if s6 < 4 else (2 * (s6 - 4) + k, lo)
-                out[:, :, :, kt * 6 + s6, k, :, :] = src[:, :, c, :, kt, :, :].transpose(3, 4, 1, 0, 2)   # (kh, kw, quarter, row, e)
+                for part in range(2):
+                    out[:, :, :, kt, pair, part, k, :, :] = parts[part][:, :, 2 * pair + k, :, kt, :, :].transpose(3, 4, 1, 0, 2)   # (kh, kw, quarter, row, e)
     return out
 
 

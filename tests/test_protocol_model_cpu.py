@@ -13,8 +13,8 @@ SHAPES = {
     'dgrad conv1': (3, 2, 64, 8, 3, 3, 2, False),
     'dgrad conv0': (3, 1, 64, 1, 2, 1, 2, True),
     'wgrad': (5, 1, 8, 8, 2, 2, 2, False),
-    'split conv1': (3, 8, 74, 4, 2, 3, 1, False),
-    'split conv2': (49, 4, 18, 6, 2, 2, 1, False),
+    'split conv1': (3, 8, 75, 6, 2, 3, 1, False),          # groups of 6 MMAs over ring slots of 4 weight tiles
+    'split conv2': (49, 4, 18, 6, 2, 3, 1, False),
 }
 
 

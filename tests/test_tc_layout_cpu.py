@@ -149,7 +149,7 @@ def test_split_layer1_tables(T, HW, tiles):
     a1 = em.pack_a1s(x, g)
     assert torch.equal(em.unpack_a1s(a1, g, B), xr)
     D, p = em.emulate_layer(7, a1, em.pack_w1s(w), T, HW, B, tiles, fmt='f16')
-    assert p.ncols == g.N1 and p.n_steps == 74 and p.smem_total <= 232448 and p.n_acc * p.acc_cols <= 512
+    assert p.ncols == g.N1 and p.n_steps == 75 and p.n_wtiles == 50 and p.smem_total <= 232448 and p.n_acc * p.acc_cols <= 512
     fpt = p.n_acc
     for k, tile in enumerate(tiles):
         item, tq = divmod(tile, p.tiles_per_item)
@@ -173,7 +173,7 @@ def test_split_layer2_tables(T, HW):
     back, ok = em.unpack_a2s(a2, g, B)
     assert ok and torch.equal(back, xr)
     D, p = em.emulate_layer(8, a2, em.pack_w2s(w), T, HW, B, fmt='f16')
-    assert p.ncols == g.N2 and p.n_acc == 4 and p.n_tiles == 1 and p.n_steps == 18
+    assert p.ncols == g.N2 and p.n_acc == 4 and p.n_tiles == 1 and p.n_steps == 18 and p.n_wtiles == 12
     d = torch.from_numpy(D[0]).reshape(4, 128, g.To2, g.Ho2, g.Wo2)
     assert rel(d[:B], y) < 2e-6, rel(d[:B], y)
     assert float(d[B:].abs().max()) == 0.0

@@ -75,6 +75,11 @@ struct WsParams {
     int32_t w_resident;
     uint32_t w_bytes;                   // resident image bytes
     int32_t G, RW, RP;
+    // streamed weights with tile REUSE inside a group (split-fp16 conv 1 / 2: one hi-weight tile feeds the xh and the xl MMA):
+    // a ring slot holds Gt tiles (0: = G) and a stage n_wtiles tiles (0: = n_steps); MMA jj of a group reads tile a_in_group[jj]
+    // of its slot.  A partial last group uses a prefix of both the MMA and the tile sequence.
+    int32_t Gt, n_wtiles;
+    uint8_t a_in_group[16];
     int32_t n_acc;
     uint32_t acc_delta16;               // B start offset between accumulators
     uint32_t ncols, acc_cols, acc_stages;
@@ -806,20 +811,21 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
             } else {
                 uint32_t slot = 0, phase = 0;
                 const int slots_per_stage = (p.n_steps + p.G - 1) / p.G;
+                const int Gt = p.Gt ? p.Gt : p.G, n_wtiles = p.n_wtiles ? p.n_wtiles : p.n_steps;
                 for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
                     const int u0 = (tile % p.ug_count) * p.n_u, u1 = min(p.nu_total, u0 + p.n_u);
                     const uint8_t* wbase = p.wimg + (int64_t)((tile / p.ug_count) / p.tiles_per_item) * p.w_item_stride;
                     for (int u = u0; u < u1; ++u)
                         for (int st = 0; st < stages_per_tile; ++st)
                             for (int gi = 0; gi < slots_per_stage; ++gi) {
-                                const int s0 = gi * p.G;
-                                const uint32_t nb = (uint32_t)min(p.G, p.n_steps - s0) * kWeightTileBytes;
+                                const int s0 = gi * Gt;
+                                const uint32_t nb = (uint32_t)min(Gt, n_wtiles - s0) * kWeightTileBytes;
                                 if (p.dbg & 16) mbar_wait<true>(BAR(w_empty, slot), phase ^ 1); else mbar_wait(BAR(w_empty, slot), phase ^ 1);
                                 if (p.dbg & 2) { mbar_arrive(BAR(w_full, slot)); }
                                 else {
                                     mbar_expect_tx(BAR(w_full, slot), nb);
-                                    bulk_g2s(smem_w + slot * (uint32_t)p.G * kWeightTileBytes,
-                                             wbase + (int64_t)u * p.w_u_stride + ((int64_t)st * p.n_steps + s0) * kWeightTileBytes,
+                                    bulk_g2s(smem_w + slot * (uint32_t)Gt * kWeightTileBytes,
+                                             wbase + (int64_t)u * p.w_u_stride + ((int64_t)st * n_wtiles + s0) * kWeightTileBytes,
                                              nb, BAR(w_full, slot));
                                 }
                                 if (++slot == (uint32_t)p.RW) { slot = 0; phase ^= 1; }
@@ -849,7 +855,7 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
         const uint32_t a_hi = p.a_hi ? p.a_hi : ((p.a_sbo16 & 0x3FFFu) | (1u << 14));
         const uint32_t b_hi = p.b_hi ? p.b_hi : (8u | (1u << 14));
         const uint32_t a_lbo_bits = (p.a_lbo16 & 0x3FFFu) << 16;
-        const uint32_t slot_bytes = (uint32_t)G * kWeightTileBytes;
+        const uint32_t slot_bytes = (uint32_t)(p.Gt ? p.Gt : G) * kWeightTileBytes;
         uint64_t* tabB = reinterpret_cast<uint64_t*>(base_ptr + kBarBlock);                   // [RP][n_steps][NACC]
         uint64_t* tabA = tabB + p.RP * n_steps * NACC;                                  // [RW][G] or [n_sa][n_steps]
         const int t64 = role * 32 + lane;
@@ -862,7 +868,7 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
         for (int i = t64; i < nA; i += 64) {
             uint32_t a16;
             if (RESIDENT) a16 = (smem_w >> 4) + p.step_tab[i % n_steps].x + (uint32_t)((i / n_steps) * p.a_sa_stride16);
-            else a16 = ((smem_w + (uint32_t)(i / G) * slot_bytes) >> 4) + (uint32_t)(i % G) * (kWeightTileBytes >> 4);
+            else a16 = ((smem_w + (uint32_t)(i / G) * slot_bytes) >> 4) + (uint32_t)(p.Gt ? p.a_in_group[i % G] : (i % G)) * (kWeightTileBytes >> 4);
             tabA[i] = ((uint64_t)a_hi << 32) | ((a16 & 0x3FFFu) | a_lbo_bits);
         }
         asm volatile("bar.sync 1, 64;" ::: "memory");                                  // tables visible to both issuers
@@ -1349,21 +1355,25 @@ static int setup_l1s(WsParams& p, const Geo& g, int B, uint32_t* smem) {
         const int plane = tap_par(kh) * 2 + tap_par(kw);                // hi part: planes 0..3, lo part: 4..7
         off[i] = (uint32_t)plane * (uint32_t)g.plane1 + (uint32_t)(tap_shift(kh) * g.P1 + tap_shift(kw)) * 16;
         if (i && off[i] <= off[i - 1]) return -2;
-        p.b_off16[i] = off[i] >> 4;
-        p.b_lbo16[i] = (uint32_t)(4 * g.plane1) >> 4;
     }
+    // tap pairs in the two K halves: pair 0 = (tap 0, -) and pair p = (tap 2p-1, tap 2p); three MMAs per pair: xh.wh, xl.wh (same
+    // weight tile), xh.wl.  The empty second half of pair 0 has zero weights and addresses tap 1's window (valid staged data).
     for (int pr = 0; pr < 25; ++pr) {
-        const int a = 2 * pr, b = 2 * pr + 1;
-        p.b_off16[49 + pr] = off[a] >> 4;
-        p.b_lbo16[49 + pr] = (b < 49) ? (off[b] - off[a]) >> 4 : (uint32_t)g.plane1 >> 4;     // last: zero weights in the 2nd half
+        const int a = pr ? 2 * pr - 1 : 0, b = pr ? 2 * pr : 1;
+        for (int m = 0; m < 3; ++m) {
+            p.b_off16[3 * pr + m] = (off[a] + (m == 1 ? 4u * (uint32_t)g.plane1 : 0u)) >> 4;
+            p.b_lbo16[3 * pr + m] = (off[b] - off[a]) >> 4;
+        }
     }
     p.a_lbo16 = 2048 >> 4; p.a_sbo16 = 8;
     p.w_resident = 0; p.w_bytes = 0;
-    p.G = env_int("VD_TC_L1S_G", 4); p.RW = env_int("VD_TC_L1S_RW", 3); p.RP = 2;
+    // a group = two tap pairs: 6 MMAs per accumulator over 4 weight tiles [wh_p, wl_p, wh_p+1, wl_p+1]
+    p.G = 6; p.Gt = 4; p.n_wtiles = 50; p.RW = env_int("VD_TC_L1S_RW", 3); p.RP = 2;
+    { const uint8_t pat[6] = {0, 0, 1, 2, 2, 3}; for (int i = 0; i < 6; ++i) p.a_in_group[i] = pat[i]; }
     p.n_acc = fpt; p.acc_delta16 = (uint32_t)g.frame1 >> 4;
     p.ncols = g.N1; p.acc_cols = nacc4 ? 128 : 256; p.acc_stages = 1;
     p.idesc = umma_idesc_f16(128, g.N1);
-    return finalize_smem(p, (uint32_t)p.G * p.RW * kWeightTileBytes, smem, false, (uint32_t)(2 * (fpt / 2) * g.H2 * g.H2) * kStashPitch * 2);
+    return finalize_smem(p, (uint32_t)p.Gt * p.RW * kWeightTileBytes, smem, false, (uint32_t)(2 * (fpt / 2) * g.H2 * g.H2) * kStashPitch * 2);
 }
 
 // conv 2: the tile / stage geometry of setup_l2 with 32-channel quarters carrying both parts; 18 steps per stage
@@ -1385,22 +1395,20 @@ static int setup_l2s(WsParams& p, const Geo& g, int B, uint32_t* smem) {
     p.n_steps = kSteps2s;
     for (int kt = 0; kt < 3; ++kt) {
         const uint32_t tofs = (uint32_t)((int64_t)kt * g.HW2 * 16);
-        for (int c = 0; c < 4; ++c) {                                   // [xh_c | xl_c] . [wh_c | wh_c]
-            p.b_off16[kt * 6 + c] = (uint32_t)(c * g.chunk2 + tofs) >> 4;
-            p.b_lbo16[kt * 6 + c] = (uint32_t)(4 * g.chunk2) >> 4;
-        }
-        for (int pr = 0; pr < 2; ++pr) {                                // [xh_c | xh_c+1] . [wl_c | wl_c+1]
-            p.b_off16[kt * 6 + 4 + pr] = (uint32_t)(2 * pr * g.chunk2 + tofs) >> 4;
-            p.b_lbo16[kt * 6 + 4 + pr] = (uint32_t)g.chunk2 >> 4;
-        }
+        for (int pr = 0; pr < 2; ++pr)                                  // chunk pair (2pr, 2pr+1) in the two K halves
+            for (int m = 0; m < 3; ++m) {                               // xh.wh, xl.wh (same weight tile), xh.wl
+                p.b_off16[kt * 6 + pr * 3 + m] = (uint32_t)((2 * pr + (m == 1 ? 4 : 0)) * g.chunk2 + tofs) >> 4;
+                p.b_lbo16[kt * 6 + pr * 3 + m] = (uint32_t)g.chunk2 >> 4;
+            }
     }
     p.a_lbo16 = 2048 >> 4; p.a_sbo16 = 8;
     p.w_resident = 0; p.w_bytes = 0;
-    p.G = env_int("VD_TC_L2S_G", 6); p.RW = env_int("VD_TC_L2S_RW", 2); p.RP = 2;
+    p.G = 6; p.Gt = 4; p.n_wtiles = 12; p.RW = env_int("VD_TC_L2S_RW", 3); p.RP = 2;
+    { const uint8_t pat[6] = {0, 0, 1, 2, 2, 3}; for (int i = 0; i < 6; ++i) p.a_in_group[i] = pat[i]; }
     p.n_acc = VPT; p.acc_delta16 = (uint32_t)g.group2 >> 4;
     p.ncols = g.N2; p.acc_cols = 128; p.acc_stages = 1;
     p.idesc = umma_idesc_f16(128, g.N2);
-    return finalize_smem(p, (uint32_t)p.G * p.RW * kWeightTileBytes, smem);
+    return finalize_smem(p, (uint32_t)p.Gt * p.RW * kWeightTileBytes, smem);
 }
 
 static int setup_bwd(WsParams& p, const Geo& g, int layer, int B, uint32_t* smem, bool fp32_out = false) {
@@ -1605,7 +1613,7 @@ extern "C" int vd_tc_x3_conv_layer(int layer, const void* in, const void* wimg, 
 // Host-side introspection for the CPU emulator in tests/ (no GPU work): dumps the exact kernel
 // parameters that vd_tc_conv_layer would launch with.
 extern "C" int vd_tc_debug_params(int layer, const vd_tc_plan* plan, int B, int64_t* out, int cap) {
-    VD_REQUIRE(plan && out && cap >= 33 + 3 * kMaxCopies + 3 * kMaxSteps, "tc_debug_params: buffer too small");
+    VD_REQUIRE(plan && out && cap >= 33 + 3 * kMaxCopies + 3 * kMaxSteps + 18, "tc_debug_params: buffer too small");
     VD_REQUIRE(layer >= 0 && layer <= 8 && geo_supported(plan->T, plan->H), "tc_debug_params: bad layer / geometry");
     WsParams p;
     memset(&p, 0, sizeof(p));
@@ -1631,6 +1639,8 @@ extern "C" int vd_tc_debug_params(int layer, const vd_tc_plan* plan, int B, int6
     for (int k = 0; k < kMaxSteps; ++k) out[i++] = p.b_lbo16[k];
     for (int k = 0; k < kMaxSteps; ++k) out[i++] = p.a_off16[k];
     out[i++] = p.w_u_stride;
+    out[i++] = p.Gt; out[i++] = p.n_wtiles;
+    for (int k = 0; k < 16; ++k) out[i++] = p.a_in_group[k];
     return 0;
 }
 

@@ -203,12 +203,16 @@ inline Dg0Geo make_dg0_geo(const Geo& g) {
 //   stages (hi part, lo part) and frame i feeds output frames i-1, i, i+1 (kt = 2, 1, 0) held in 4 x 128 TMEM columns.
 //
 // A1s (input of conv 1): [chunk 8 (8 ch)][t_pad T+2][part 2][ph 2][pw 2][i RI1][j P1] x 16 B — the A1 layout with the
-//   16-channel slice replaced by an 8-channel chunk carrying both parts (same bytes per stage).  Per stage (kt, chunk):
-//     steps 0..48   tap idx (smem-offset order, l1s_tap): B = [xh_tap | xl_tap] (LBO = 4 planes), A = [wh_tap | wh_tap]
-//     steps 49..73  tap pairs (2p, 2p+1):                 B = [xh_a | xh_b]  (LBO = window distance), A = [wl_a | wl_b]
+//   16-channel slice replaced by an 8-channel chunk carrying both parts (same bytes per stage).  Per stage (kt, chunk) the 49
+//   taps (smem-offset order, l1s_tap) are paired (a, b) = (2p-1, 2p), pair 0 = (tap 0, zero weights), into the two K halves of a
+//   K = 16 MMA, three MMAs a pair:
+//     B = [xh_a | xh_b] (LBO = window distance)  x  A = [wh_a | wh_b]
+//     B = [xl_a | xl_b] (the same + 4 planes)    x  A = [wh_a | wh_b]   (the SAME weight tile: streamed once, used twice)
+//     B = [xh_a | xh_b]                          x  A = [wl_a | wl_b]
+//   -> 75 MMAs and 50 streamed weight tiles per stage.
 //
-// A2s (input of conv 2): [khw 49][quarter 4][part 2][k 4 (8 ch)][t_pad To2+2][ho][wo] x 16 B.  Per stage (khw, quarter),
-//   for kt = 0..2: steps c = 0..3: B = [xh_c | xl_c], A = [wh_c | wh_c]; steps (0,1), (2,3): B = [xh_c | xh_c'], A = [wl_c | wl_c'].
+// A2s (input of conv 2): [khw 49][quarter 4][part 2][k 4 (8 ch)][t_pad To2+2][ho][wo] x 16 B.  Per stage (khw, quarter) and
+//   kt = 0..2 the chunk pairs (0,1), (2,3) get the same three MMAs: 18 MMAs and 12 streamed weight tiles per stage.
 struct SGeo {
     int R0s, N0s, nrb0s;                // conv 0: output rows per column band, accumulator columns, bands per frame
     int stage0s;                        // bytes of one (frame, part) stage
@@ -216,8 +220,9 @@ struct SGeo {
     int64_t video1s, video2s;           // A1s / A2s bytes per video
     int64_t w0s_bytes, w1s_bytes, w2s_bytes;
 };
-constexpr int kSteps1s = 74;                // 49 + 25
-constexpr int kSteps2s = 18;                // 3 kt x (4 + 2)
+constexpr int kSteps1s = 75;                // 25 tap pairs x 3 MMAs (xh.wh, xl.wh, xh.wl)
+constexpr int kSteps2s = 18;                // 3 kt x 2 chunk pairs x 3 MMAs
+constexpr int kWTiles1s = 50, kWTiles2s = 12;   // streamed weight tiles per stage: [hi, lo] per pair
 
 inline SGeo make_sgeo(const Geo& g) {
     SGeo s{};
@@ -230,8 +235,8 @@ inline SGeo make_sgeo(const Geo& g) {
     s.video1s = 8 * g.slice1;
     s.video2s = 196 * g.group2;
     s.w0s_bytes = (int64_t)3 * 11 * 4096;
-    s.w1s_bytes = (int64_t)3 * 8 * kSteps1s * 4096;
-    s.w2s_bytes = (int64_t)49 * 4 * kSteps2s * 4096;
+    s.w1s_bytes = (int64_t)3 * 8 * kWTiles1s * 4096;
+    s.w2s_bytes = (int64_t)49 * 4 * kWTiles2s * 4096;
     return s;
 }
 

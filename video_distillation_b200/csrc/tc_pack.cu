@@ -220,21 +220,19 @@ __global__ void pack_w0s_kernel(const float* __restrict__ w, uint16_t* __restric
     }
 }
 
-// conv 1 image: [kt 3][chunk 8][step 74][k 2][128][8]; steps 0..48: hi weights of tap l1s_tap(step) in both K halves;
-// steps 49..73: lo weights of taps l1s_tap(2p), l1s_tap(2p+1)
+// conv 1 image: [kt 3][chunk 8][pair 25][part 2 (hi, lo)][k 2][128][8]; pair 0 = (tap 0, zeros), pair p = taps l1s_tap(2p-1), l1s_tap(2p)
 __global__ void pack_w1s_kernel(const float* __restrict__ w, uint16_t* __restrict__ img) {
-    const int total = 3 * 8 * kSteps1s * kWeightTileBytes / 2;
+    const int total = 3 * 8 * kWTiles1s * kWeightTileBytes / 2;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         int e = i % 8; int q = i / 8;
         int row = q % 128; q /= 128;
         int k = q % 2; q /= 2;
-        int step = q % kSteps1s; q /= kSteps1s;
+        int part = q % 2; q /= 2;
+        int pair = q % 25; q /= 25;
         int chunk = q % 8; int kt = q / 8;
-        int idx, part;
-        if (step < 49) { idx = step; part = 0; }
-        else { idx = 2 * (step - 49) + k; part = 1; }
+        const int idx = pair ? 2 * pair - 1 + k : (k ? -1 : 0);
         uint16_t v = 0;
-        if (idx < 49) {
+        if (idx >= 0) {
             const int tap = l1s_tap(idx), kh = tap / 7, kw = tap % 7;
             v = h_part(w[(((row * 64 + chunk * 8 + e) * 3 + kt) * 7 + kh) * 7 + kw], part);
         }
@@ -242,21 +240,20 @@ __global__ void pack_w1s_kernel(const float* __restrict__ w, uint16_t* __restric
     }
 }
 
-// conv 2 image: [kh 7][kw 7][quarter 4][step 18 = kt*6 + s][k 2][128][8]; s < 4: hi weights of chunk s in both K halves;
-// s = 4, 5: lo weights of chunks 2(s-4), 2(s-4)+1
+// conv 2 image: [kh 7][kw 7][quarter 4][kt 3][pair 2][part 2 (hi, lo)][k 2][128][8]; K half k of pair p = chunk 2p + k
 __global__ void pack_w2s_kernel(const float* __restrict__ w, uint16_t* __restrict__ img) {
-    const int total = 49 * 4 * kSteps2s * kWeightTileBytes / 2;
+    const int total = 49 * 4 * kWTiles2s * kWeightTileBytes / 2;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         int e = i % 8; int q = i / 8;
         int row = q % 128; q /= 128;
         int k = q % 2; q /= 2;
-        int step = q % kSteps2s; q /= kSteps2s;
+        int part = q % 2; q /= 2;
+        int pair = q % 2; q /= 2;
+        int kt = q % 3; q /= 3;
         int quarter = q % 4; q /= 4;
         int kw = q % 7; int kh = q / 7;
-        const int kt = step / 6, s6 = step % 6;
-        const int c = s6 < 4 ? s6 : 2 * (s6 - 4) + k;
-        const int ci = quarter * 32 + c * 8 + e;
-        img[i] = h_part(w[(((row * 128 + ci) * 3 + kt) * 7 + kh) * 7 + kw], s6 < 4 ? 0 : 1);
+        const int ci = quarter * 32 + (2 * pair + k) * 8 + e;
+        img[i] = h_part(w[(((row * 128 + ci) * 3 + kt) * 7 + kh) * 7 + kw], part);
     }
 }
 
