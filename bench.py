@@ -356,7 +356,9 @@ def memory_kernel_rooflines(step_fn, tr, steps=3):
         ('compose_bwd_wdyn_tiled_kernel', n_syn * 4 * (3 * thw + thw), 'read d video + dynamic'),
         ('compose_bwd_weight_static_kernel', n_syn * 4 * (3 * thw + 3 * hw), 'read d video + static'),
         ('col2im_rows_kernel<7, 8', n_syn * (p.col0_bytes_per_video + 4 * 3 * thw), 'read conv-0 columns, write d video'),
-        ('col2im_kernel<', n_syn * (p.col2_bytes_per_video + 128 * int(p.T2p) * int(p.H2p) * int(p.W2p) + dyp1),
+        ('col2im_kernel<float', n_syn * (2 * p.col2_bytes_per_video + 4 * 128 * int(p.T2p) * int(p.H2p) * int(p.W2p)),
+         'read fp32 conv-2 columns, write fp32 d input of conv 2 (split-bf16 backward, one of three passes)'),
+        ('col2im_kernel<unsigned short', n_syn * (p.col2_bytes_per_video + 128 * int(p.T2p) * int(p.H2p) * int(p.W2p) + dyp1),
          'read conv-2 columns + codes, write padded planar dY1'),
         ('pack_video_kernel', n_syn * (4 * 3 * thw + p.x0_bytes_per_video), 'read fp32 video, write packed bf16 conv-0 operand'),
         ('pack_video_x3_kernel', n_syn * (4 * 3 * thw + tcn.x0_per), 'read fp32 video, write packed fp16 hi/lo conv-0 operand'),

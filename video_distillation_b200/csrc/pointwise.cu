@@ -393,8 +393,37 @@ __global__ void __launch_bounds__(256) compose_bwd_weight_static_kernel(
 }
 
 // =============================================================== class mean + DM loss
-// mean[c,d] = (1/n) sum_j emb[c,j,d]; threads along d (coalesced float4 when D%4==0).
-__global__ void class_mean_kernel(const float* __restrict__ emb, float* __restrict__ mean, int n, int D) {
+// mean[c,d] = (1/n) sum_j emb[c,j,d].  A block owns (class, 256 columns): 64 threads x float4 along d, 4 row groups; group g adds
+// rows g, g+4, g+8, ... in order and the four partial sums are combined in a fixed order ((g0 + g1) + (g2 + g3)) through shared
+// memory — the same bits on every launch and for every world size, with 4x the loads in flight of a one-thread-per-column loop.
+__global__ void __launch_bounds__(256) class_mean_kernel(const float* __restrict__ emb, float* __restrict__ mean, int n, int D) {
+    __shared__ float4 part[4][64];
+    const int c = blockIdx.y;
+    const int lane4 = threadIdx.x & 63, grp = threadIdx.x >> 6;
+    const int d = (blockIdx.x * 64 + lane4) * 4;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (d < D) {
+        const float* p = emb + (int64_t)c * n * D + d;
+#pragma unroll 4
+        for (int j = grp; j < n; j += 4) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(p + (int64_t)j * D));
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+    }
+    part[grp][lane4] = s;
+    __syncthreads();
+    if (grp == 0 && d < D) {
+        const float4 a = part[0][lane4], b = part[1][lane4], e = part[2][lane4], f = part[3][lane4];
+        const float inv = (float)n;
+        float4 o;
+        o.x = ((a.x + b.x) + (e.x + f.x)) / inv; o.y = ((a.y + b.y) + (e.y + f.y)) / inv;
+        o.z = ((a.z + b.z) + (e.z + f.z)) / inv; o.w = ((a.w + b.w) + (e.w + f.w)) / inv;
+        *reinterpret_cast<float4*>(mean + (int64_t)c * D + d) = o;
+    }
+}
+
+// scalar fallback (D not a multiple of 4 or unaligned pointers): one thread per column, rows added in order
+__global__ void class_mean_scalar_kernel(const float* __restrict__ emb, float* __restrict__ mean, int n, int D) {
     const int c = blockIdx.y;
     const int d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= D) return;
@@ -702,8 +731,13 @@ extern "C" int vd_compose_bwd_fused_f32(const float* gout, const float* static_s
 extern "C" int vd_class_mean_f32(const float* emb, float* mean, int C, int n, int D, void* stream) {
     VD_REQUIRE(emb && mean && C >= 0 && n > 0 && D > 0 && C <= 65535, "class_mean: bad argument");
     if (C == 0) return 0;
-    dim3 grid((unsigned)ceil_div(D, 128), C, 1);
-    class_mean_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(emb, mean, n, D);
+    if (D % 4 == 0 && ((uintptr_t)emb & 15) == 0 && ((uintptr_t)mean & 15) == 0) {
+        dim3 grid((unsigned)ceil_div(D, 256), C, 1);
+        class_mean_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(emb, mean, n, D);
+    } else {
+        dim3 grid((unsigned)ceil_div(D, 128), C, 1);
+        class_mean_scalar_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(emb, mean, n, D);
+    }
     return check_launch("class_mean_f32");
 }
 
