@@ -110,13 +110,16 @@ def embed(params, x, fwd, bwd, routing=None):
     return h.reshape(h.shape[0], -1), rec
 
 
+SCALE = [1.0]
+
+
 def run(params, real, syn, fwd, bwd, routing=None):
     syn = syn.clone().requires_grad_(True)
     er, _ = embed(params, real, fwd, bwd)
     es, rec = embed(params, syn, fwd, bwd, routing)
     loss = ((er.detach().mean(0) - es.mean(0)) ** 2).sum()
-    loss.backward()
-    return dict(er=er.detach(), es=es.detach(), loss=loss.detach(), g=syn.grad.detach(), rec=rec)
+    (loss * SCALE[0]).backward()
+    return dict(er=er.detach(), es=es.detach(), loss=loss.detach(), g=syn.grad.detach() / SCALE[0], rec=rec)
 
 
 def rel(a, b):
@@ -131,6 +134,8 @@ if __name__ == '__main__':
     ap.add_argument('--n_syn', type=int, default=2)
     ap.add_argument('--seeds', type=int, default=2)
     ap.add_argument('--modes', default='fp32,f16,f16a,f16x3,bf16,bf16x3')
+    ap.add_argument('--bwd', default=None, help='override the backward format: f16 (with --scale), bf16, bf16x3, f16x3')
+    ap.add_argument('--scale', type=float, default=1.0, help='loss scale applied before the backward (power of two)')
     a = ap.parse_args()
     torch.set_num_threads(8)
     for seed in range(a.seeds):
@@ -160,6 +165,9 @@ if __name__ == '__main__':
                 continue
             bwd = mode if mode != 'f16a' else 'f16a'
             bwd = {'f16': 'bf16', 'f16a': 'bf16x3', 'f16x3': 'bf16x3'}.get(mode, mode)
+            if a.bwd:
+                bwd = a.bwd
+            SCALE[0] = a.scale
             r = run(params, real, syn, mode, bwd)
             rc = run(params, real, syn, mode, bwd, routing=ref['rec'])
             # same emulated forward / backward, but with exact operands and forced routing = truth gradient

@@ -192,3 +192,21 @@ def test_x3_gradient_vs_oracle_conditioned_on_routing(T, HW):
     assert rel(g_cond, g32) < 1e-3, rel(g_cond, g32)
     # unconditioned: within a small multiple of the floor that fp32 itself has against fp64
     assert rel(g_unc, g32) < 5e-2, (rel(g_unc, g32), rel(g32, g64))
+
+
+@pytest.mark.parametrize('T,HW,B', [(4, 112, 3), (12, 112, 2), (16, 112, 5), (8, 64, 9), (16, 64, 3), (24, 64, 2), (32, 64, 5)])
+def test_x3_embed_geometry_sweep_against_the_fp32_oracle(T, HW, B):
+    """Every supported (frames, size) geometry of the split-fp16 pipeline against the fp32 CPU oracle; odd batch sizes exercise
+    the partially filled conv-2 tiles and multi-tile CTAs."""
+    net, ws = make_net(T, HW, seed=T + HW, reference_init=True)
+    video = torch.randn(B, T, 3, HW, HW, generator=torch.Generator().manual_seed(B))
+    emb, codes = net.embed(video.cuda(), want_codes=True)
+    from oracle import convnet3d_embed
+    e32 = convnet3d_embed(params_of(ws), video)
+    assert torch.isfinite(emb).all()
+    assert rel(emb, e32) < 2e-4, (T, HW, B, rel(emb, e32))
+    codes32 = __import__('oracle').routing_codes(params_of(ws), video)
+    for d in range(3):
+        got, want = codes[d].cpu(), codes32[d]
+        same = (((got & 8) > 0) == ((want & 8) > 0)) & (((got & 7) == (want & 7)) | ((want & 8) == 0))
+        assert same.float().mean().item() > 0.999, (d, same.float().mean().item())
