@@ -449,7 +449,7 @@ def run_ours(args):
         t0 = time.perf_counter()
         ds.prepack(tr.embedder.tc, extra_slots=len(tr.owned) * tr.vpc)
         torch.cuda.synchronize()
-        prepack = {'ms': (time.perf_counter() - t0) * 1e3, 'bytes_per_video': int(tr.embedder.tc.x0_per),
+        prepack = {'ms': (time.perf_counter() - t0) * 1e3, 'bytes_per_video': int(ds.x0.numel() // max(1, vids.shape[0] + (0 if tr.embedder.tc.real_products == 2 else len(tr.owned) * tr.vpc))),
                    'resident_bytes': int(ds.x0.numel()), 'videos': int(vids.shape[0])}
     np.random.seed(0)
     torch.cuda.manual_seed(1234)
@@ -509,8 +509,13 @@ def run_ours(args):
     layer_ms = {0: 0.0, 1: 0.0, 2: 0.0}
     layer_videos = {0: 0, 1: 0, 2: 0}
     layer_launches = {0: 0, 1: 0, 2: 0}
+    real_products = tc.real_products if tc is not None and tc.split else 1
     if tc is not None:
-        for layer, B, a, b in tc.timing:
+        # the launches of the frozen real videos (the differentiable synthetic videos of the two-product mode run in their own,
+        # three-product launches: 1.5 % of the videos, counted in ms_per_step but not in the per-layer roofline figures)
+        for layer, B, a, b, products in tc.timing:
+            if products != real_products:
+                continue
             layer_ms[layer] += a.elapsed_time(b)
             layer_videos[layer] += B
             layer_launches[layer] += 1
@@ -661,20 +666,26 @@ def run_ours(args):
 
     # ---- throughput mode beside the parity mode: the single-pass bf16 pipeline on the same workload
     throughput = None
-    if args.precision == 'f16x3' and not args.no_throughput_mode:
-        ds.x0 = None
-        torch.cuda.empty_cache()
-        ds2 = copy.copy(ds)
-        tr2 = make_trainer('bf16', ds2)
-        ds2.prepack(tr2.embedder.tc, extra_slots=len(tr2.owned) * tr2.vpc)
-        for _ in range(max(2, args.warmup // 2)):
-            step_resident(tr2)
-        ms_t = timed(lambda: step_resident(tr2), e2e_steps)
-        throughput = {'value': e2e_steps / (ms_t / 1000.0), 'unit': 'it/s', 'ms_per_step': ms_t / e2e_steps, 'steps': e2e_steps, 'dtype': 'bf16',
-                      'note': "precision='bf16': single-pass bf16 operands and bf16 activations between the layers (embeddings ~2e-3, "
-                              'unconditioned synthetic gradient ~1e-1 of fp32: NOT the parity mode)'}
-        del tr2, ds2
-        torch.cuda.empty_cache()
+    other_modes = None
+    if args.precision.startswith('f16x3') and not args.no_throughput_mode:
+        def other(precision, note):
+            ds.x0 = None
+            torch.cuda.empty_cache()
+            ds2 = copy.copy(ds)
+            tr2 = make_trainer(precision, ds2)
+            ds2.prepack(tr2.embedder.tc, extra_slots=len(tr2.owned) * tr2.vpc)
+            for _ in range(max(2, args.warmup // 2)):
+                step_resident(tr2)
+            ms_t = timed(lambda: step_resident(tr2), e2e_steps)
+            del tr2, ds2
+            torch.cuda.empty_cache()
+            return {'value': e2e_steps / (ms_t / 1000.0), 'unit': 'it/s', 'ms_per_step': ms_t / e2e_steps, 'steps': e2e_steps,
+                    'dtype': precision, 'note': note}
+        throughput = other('bf16', "precision='bf16': single-pass bf16 operands and bf16 activations between the layers (embeddings ~2e-3, "
+                                   'unconditioned synthetic gradient ~1e-1 of fp32: NOT the parity mode)')
+        if args.precision == 'f16x3r2':
+            other_modes = {'f16x3': other('f16x3', "precision='f16x3': three products per MAC for the frozen real videos too (per-video real "
+                                                   'embeddings 7e-5 instead of 2e-4; class means, loss and gradients as the default mode)')}
 
     # ---- the reference's own modules on this GPU (cuDNN), BASELINE.json configs[1] "vs reference torch-CUDA"
     ref_cuda = None
@@ -695,19 +706,21 @@ def run_ours(args):
     l1_flops_per_launch = F_L1 * layer_videos[1] / max(1, layer_launches[1])
     achieved = l1_flops_per_launch / (l1_avg_ms * 1e-3) / 1e12 if l1_avg_ms > 0 else 0.0
     peak = float(peaks.get('bf16_tflops_sustained', peaks.get('bf16_tflops', 1400.0)))
-    split = args.precision == 'f16x3'
+    split = args.precision.startswith('f16x3')
     traffic = None
     tpath = os.path.join(ROOT, 'profiles', 'r02_traffic.json' if split else 'r01_traffic.json')
     if os.path.exists(tpath) and (T, HW) == (16, 112):      # DRAM bytes per launch from the committed ncu --set full capture (U shape)
         tj = json.load(open(tpath))['dram_bytes_per_video']['conv1']
         traffic = (tj['read'] + tj['write']) * layer_videos[1] / max(1, layer_launches[1])
-    mma_per_mac = 3 if split else 1
+    mma_per_mac = real_products if split else 1
     roofline = {'bound': 'tensor', 'kernel': f'ws_gemm_kernel<{"EPI_L1S" if split else "EPI_L1"}> (conv 1, 64->128)', 'achieved': achieved, 'peak': peak,
                 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': traffic, 'peak_kind': f'bf16_tflops_sustained of {peak_kind}',
                 'avg_launch_ms': l1_avg_ms, 'flops_per_launch': l1_flops_per_launch,
-                'note': ('algorithmic FLOPs (2*M*N*K of the convolution); the f16x3 mode issues 3 tensor-core MACs per algorithmic MAC '
-                         '(xh*wh + xl*wh + xh*wl), so the tensor pipe runs at 3x this rate' if split else 'algorithmic FLOPs (2*M*N*K of the convolution)'),
-                'issued_tflops': achieved * mma_per_mac * (74.0 / 73.5 if split else 1.0), 'issued_frac': achieved * mma_per_mac / peak,
+                'note': (f'algorithmic FLOPs (2*M*N*K of the convolution); this launch issues {mma_per_mac} tensor-core MACs per algorithmic MAC '
+                         + ('(xh*wh + xl*wh + xh*wl)' if mma_per_mac == 3 else '(xh*wh + xh*wl: frozen real videos, exact weights)')
+                         + f', so the tensor pipe runs at {mma_per_mac}x this rate' if split else 'algorithmic FLOPs (2*M*N*K of the convolution)'),
+                'mma_per_mac': mma_per_mac,
+                'issued_tflops': achieved * mma_per_mac * (50.0 / 49.0 if split else 1.0), 'issued_frac': achieved * mma_per_mac / peak,
                 'per_layer_ms_per_step': {f'conv{k}': layer_ms[k] / args.steps for k in layer_ms},
                 'per_layer_tflops': {f'conv{k}': (f * layer_videos[k] / (layer_ms[k] * 1e-3) / 1e12 if layer_ms[k] > 0 else 0.0)
                                      for k, f in ((0, F_L0), (1, F_L1), (2, F_L2))}}
@@ -726,7 +739,7 @@ def run_ours(args):
         else:
             its, dt, desc = cpu_oracle_rate(sample_classes(15.0, threads), BATCH_REAL, threads)
             cpu = {'value': its, 'unit': 'it/s', 'cores': threads, 'kind': 'port', 'sample': desc, 'sample_seconds': dt}
-    dtype = {'f16x3': 'f16x3', 'bf16': 'bf16'}.get(args.precision, 'f32')
+    dtype = {'f16x3': 'f16x3', 'f16x3r2': 'f16x3 (synthetic) / f16x2 (frozen real)', 'bf16': 'bf16'}.get(args.precision, 'f32')
     out = {
         'metric': 'DM+S2D distill iters/sec', 'value': value, 'unit': 'it/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'strong',
@@ -734,6 +747,9 @@ def run_ours(args):
         'config': bench_config(world),
         'impl_detail': {'precision': args.precision,
                         'real_embed': {'f16x3': 'tcgen05, fp16 hi/lo operand pairs (3 MMAs per MAC), fp32 accumulate in TMEM',
+                                       'f16x3r2': 'tcgen05, fp16 activations x fp16 hi/lo weight pairs (2 MMAs per MAC: exact weights, one rounding '
+                                                  'per activation that averages out of the class mean), fp32 accumulate in TMEM; synthetic videos: '
+                                                  'hi/lo pairs on both operands (3 MMAs per MAC)',
                                        'bf16': 'tcgen05 bf16 operands / fp32 accumulate'}.get(args.precision, 'fp32 CUDA cores'),
                         'syn_branch': args.syn_mode,
                         'real_set': 'resident fp32' + ('' if args.no_prepack else ' + pre-packed conv-0 operand (one-time, outside the timed region)'),
@@ -745,7 +761,7 @@ def run_ours(args):
         'e2e_resident': {'value': e2e_res, 'unit': 'it/s', 'h2d_bytes_per_step': int(C * BATCH_REAL * 8),
                          'd2h_bytes_per_step': 4, 'steps': e2e_steps,
                          'note': 'real set uploaded once; per step the host sends the sampled index table and reads the loss'},
-        'throughput_mode': throughput, 'reference_torch_cuda': ref_cuda, 'timeline': timeline,
+        'throughput_mode': throughput, 'other_modes': other_modes, 'reference_torch_cuda': ref_cuda, 'timeline': timeline,
         'roofline': roofline, 'memory_kernels': mem_kernels, 'cpu_baseline': cpu}
     print(json.dumps(out))
     if world > 1:
@@ -1023,9 +1039,10 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--precision', default='f16x3', choices=['f16x3', 'bf16', 'fp32'],
-                    help='f16x3 (default): fused tcgen05 pipeline on fp16 hi/lo operand pairs, the parity mode; bf16: single-pass '
-                         'throughput mode; fp32: exact CUDA-core kernels')
+    ap.add_argument('--precision', default='f16x3r2', choices=['f16x3r2', 'f16x3', 'bf16', 'fp32'],
+                    help='f16x3r2 (default): fused tcgen05 pipeline on fp16 hi/lo operand pairs, the parity mode — three products per MAC '
+                         'for the synthetic videos, two (exact weights, fp16 activations) for the frozen real videos; f16x3: three products '
+                         'everywhere; bf16: single-pass throughput mode; fp32: exact CUDA-core kernels')
     ap.add_argument('--timeline', action='store_true', help='add a per-phase device timeline of the step (CUDA events, max / min over ranks)')
     ap.add_argument('--no-throughput-mode', action='store_true', help='skip the single-pass bf16 line reported beside the default mode')
     ap.add_argument('--no-reference-cuda', action='store_true', help="skip the reference's own modules on this GPU (cuDNN)")

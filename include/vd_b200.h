@@ -233,6 +233,20 @@ int vd_tc_x3_pack_weights(const float* w_l0, const float* w_l1, const float* w_l
 int vd_tc_x3_conv_layer(int layer, const void* in, const void* wimg, const float* bias, void* out, uint8_t* code,
                         int code_first_item, const vd_tc_plan* plan, const int64_t* item_index, int B, void* stream);
 
+/* Two-product mode of the FROZEN real videos (passes = 2; passes = 3 is vd_tc_x3_conv_layer).  The real branch of the DM loop
+ * (distill_s2d_ms.py:416-419: output_real = embed(img_real).detach(), read only through torch.mean(output_real, dim=0)) needs no
+ * routing codes and no gradient, and its embeddings enter the loss as a mean over batch_real videos.  Here every activation is
+ * carried as ONE fp16 value and only the weights as an fp16 pair: y = xh*wh + xh*wl in the same TMEM accumulator — exact
+ * weights, one rounding per activation (relative 2^-12, independent from video to video, so it averages out of the class
+ * mean): 2/3 of the MMAs of conv 1 / conv 2, half of conv 0's stages, half of the activation bytes.  Same weight images.
+ *   vd_tc_x3_pack_video_hi(_u8)  videos -> X0h: the X0 layout of vd_tc_pack_video (plan->x0_bytes_per_video) holding fp16 values
+ *   vd_tc_x3_conv_layer_ex       layer 0: X0h -> hi planes of A1s; layer 1: hi planes of A1s -> hi chunks of A2s; layer 2: -> embeddings */
+int vd_tc_x3_pack_video_hi(const float* video, const int64_t* index, void* x0h, const vd_tc_plan* plan, int B, void* stream);
+int vd_tc_x3_pack_video_hi_u8(const uint8_t* video, const int64_t* index, void* x0h, const vd_tc_plan* plan, int B,
+                              const float* mean3, const float* std3, void* stream);
+int vd_tc_x3_conv_layer_ex(int layer, const void* in, const void* wimg, const float* bias, void* out, uint8_t* code,
+                           int code_first_item, const vd_tc_plan* plan, const int64_t* item_index, int B, int passes, void* stream);
+
 /* ---- backward of the tensor-core embed (gradient to the input video; weights are frozen in DM).
  * dgrad of each conv is a plain GEMM on tensor cores, col[(ci,tap), pixel] = sum_co W[co,ci,tap] *
  * dY[co,pixel] (same ws_gemm kernel: transposed weights = M operand, packed dY = N operand), followed

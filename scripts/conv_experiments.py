@@ -36,7 +36,7 @@ for dbg in [int(v) for v in os.environ.get("VD_EXP_DBG", "0,4,1,2,3,7").split(",
         tc.embed_resident(x0, idx)
     torch.cuda.synchronize()
     ms = {0: 0.0, 1: 0.0, 2: 0.0}
-    for layer, b, a, e in tc.timing:
+    for layer, b, a, e, _ in tc.timing:
         ms[layer] += a.elapsed_time(e) / reps
     tc.timing = None
     print(f'dbg={dbg}: ' + ' | '.join('conv%d %6.3f ms %5.0f TF/s useful %5.0f issued' % (k, ms[k], F[k] * B / ms[k] / 1e9, F[k] * ISSUED[k] * B / ms[k] / 1e9)

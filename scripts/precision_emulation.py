@@ -12,6 +12,7 @@ Operand formats of a conv  y = sum_k x_k w_k  (accumulation emulated in fp64):
   f16 / bf16  single pass, both operands rounded
   f16x3 / bf16x3   x = xh + xl, w = wh + wl, y = xh wh + xl wh + xh wl
   f16a        activations exact (xh + xl), weights rounded once  (2 passes)
+  A+B         frozen real videos in format A, differentiable synthetic videos in format B
 The backward (dgrad) uses `bwd` format for (dy, w) the same way.
 """
 import argparse
@@ -59,6 +60,8 @@ def products(a, b, mode):
         return [(ah, bh), (al, bh), (ah, bl)]
     if mode.endswith('a'):
         return [(ah, bh), (al, bh)]
+    if mode.endswith('w'):     # weights exact (wh + wl), activations rounded once  (2 passes)
+        return [(ah, bh), (ah, bl)]
     return [(ah, bh)]
 
 
@@ -113,9 +116,10 @@ def embed(params, x, fwd, bwd, routing=None):
 SCALE = [1.0]
 
 
-def run(params, real, syn, fwd, bwd, routing=None):
+def run(params, real, syn, fwd, bwd, routing=None, real_fwd=None):
     syn = syn.clone().requires_grad_(True)
-    er, _ = embed(params, real, fwd, bwd)
+    with torch.no_grad():
+        er, _ = embed(params, real, real_fwd or fwd, bwd)
     es, rec = embed(params, syn, fwd, bwd, routing)
     loss = ((er.detach().mean(0) - es.mean(0)) ** 2).sum()
     (loss * SCALE[0]).backward()
@@ -168,8 +172,14 @@ if __name__ == '__main__':
             if a.bwd:
                 bwd = a.bwd
             SCALE[0] = a.scale
-            r = run(params, real, syn, mode, bwd)
-            rc = run(params, real, syn, mode, bwd, routing=ref['rec'])
+            real_fwd = None
+            if '+' in mode:            # "<real format>+<synthetic format>", e.g. f16+f16x3
+                real_fwd, fmode = mode.split('+')
+                bwd = a.bwd or 'bf16x3'
+            else:
+                fmode = mode
+            r = run(params, real, syn, fmode, bwd, real_fwd=real_fwd)
+            rc = run(params, real, syn, fmode, bwd, routing=ref['rec'], real_fwd=real_fwd)
             # same emulated forward / backward, but with exact operands and forced routing = truth gradient
             print(f'  {mode:8s} embed {rel(r["es"], ref["es"]):.2e} real-mean {rel(r["er"].mean(0), ref["er"].mean(0)):.2e} '
                   f'loss {abs(float(r["loss"]) - float(ref["loss"])) / float(ref["loss"]):.2e} grad(uncond) {rel(r["g"], ref["g"]):.2e} '

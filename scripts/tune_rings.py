@@ -25,7 +25,7 @@ for _ in range(3):
     tc.embed_resident(x0, idx)
 torch.cuda.synchronize()
 ms = {0: 0.0, 1: 0.0, 2: 0.0}
-for layer, b, a, e in tc.timing:
+for layer, b, a, e, _ in tc.timing:
     ms[layer] += a.elapsed_time(e) / 3
 F = {0: 2.832e9, 1: 7.553e9, 2: 0.617e9}
 print(' '.join('conv%%d %%6.2f ms %%6.0f TF/s' %% (k, ms[k], F[k] * B / ms[k] / 1e9) for k in ms))

@@ -18,27 +18,33 @@ torch.manual_seed(0)
 net = ConvNet3D(3, 50, 128, 3, 'relu', 'none', 'maxpooling', T, (HW, HW)).cuda()
 video = torch.randn(B, T, 3, HW, HW, device='cuda')
 ref = None
-for split in (False, True):
-    tc = TcConvNet3D(T, HW, HW, 'cuda', max_batch=B, split=split)
+for split, products in ((False, 1), (True, 3), (True, 2)):
+    tc = TcConvNet3D(T, HW, HW, 'cuda', max_batch=B, split=split, real_products=products if split else 3)
     f = net.features
     tc.load_weights(f[0].weight, f[0].bias, f[3].weight, f[3].bias, f[6].weight, f[6].bias)
-    x0 = tc.pack_video(video)
+    if products == 2:
+        x0 = tc.pack_dataset(video)
+        idx = torch.arange(B, device='cuda')
+        run = lambda: tc.embed_resident(x0, idx)
+    else:
+        x0 = tc.pack_video(video)
+        run = lambda: tc.embed_packed(x0, B)
     for _ in range(2):
-        emb = tc.embed_packed(x0, B)
+        emb = run()
     torch.cuda.synchronize()
     tc.timing = []
     for _ in range(5):
-        emb = tc.embed_packed(x0, B)
+        emb = run()
     torch.cuda.synchronize()
     per = {0: [], 1: [], 2: []}
-    for layer, b, e0, e1 in tc.timing:
+    for layer, b, e0, e1, _ in tc.timing:
         per[layer].append(e0.elapsed_time(e1))
-    name = 'f16x3' if split else 'bf16 '
+    name = ('f16x3' if products == 3 else 'f16x2') if split else 'bf16 '
     tot = 0.0
     for layer in range(3):
         ms = sorted(per[layer])[len(per[layer]) // 2]
         tot += ms
-        print(f'{name} conv{layer}: {ms:8.3f} ms  {GF[layer] * B / ms:8.1f} useful TFLOP/s ({(3 if split else 1) * GF[layer] * B / ms:8.1f} issued-equivalent)')
+        print(f'{name} conv{layer}: {ms:8.3f} ms  {GF[layer] * B / ms:8.1f} useful TFLOP/s ({products * GF[layer] * B / ms:8.1f} issued-equivalent)')
     print(f'{name} embed of {B} videos: {tot:.3f} ms -> {B / tot * 1e3:.0f} videos/s')
     if ref is None:
         with torch.no_grad():

@@ -109,8 +109,9 @@ def l0s_groups(L, cta):
     T = L.stream_pairs
     tile = cta
     while tile < L.n_tiles:
-        for ss in range(2 * T):
-            i, part = divmod(ss, 2)
+        nparts = L.n_sb                         # 2: (frame, hi / lo part) stages; 1: the two-product mode (hi part only)
+        for ss in range(nparts * T):
+            i, part = divmod(ss, nparts)
             segs, w_accs, c_accs = [], [], []
             for kt in (2, 1, 0):
                 f = i + 1 - kt
@@ -119,7 +120,7 @@ def l0s_groups(L, cta):
                 q = qbase + f
                 buf = q & 3
                 first_write = part == 0 and (kt == 0 or (f == 0 and kt == 1))
-                final_write = part == 1 and (kt == 2 or (f == T - 1 and kt == 1))
+                final_write = part == nparts - 1 and (kt == 2 or (f == T - 1 and kt == 1))
                 segs.append((buf, first_write))
                 if first_write:
                     w_accs.append(('acc_empty', buf, ((q >> 2) & 1) ^ 1))

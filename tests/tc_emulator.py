@@ -393,6 +393,11 @@ def pack_x0s(video, g):
     return out
 
 
+def pack_x0h(video, g):
+    """hi-only operand of the two-product mode: uint16 (B, T+2, 3, 2, RI0, Wo0, 8) = part 0 of pack_x0s."""
+    return np.ascontiguousarray(pack_x0s(video, g)[:, :, 0])
+
+
 def pack_a1s(x, g):
     """pooled conv-0 output (B,64,T,H1,H1) float32 -> uint16 (B, 8, T+2, 2, 2, 2, RI1, P1, 8) [chunk][t][part][ph][pw][i][j][e]."""
     B = x.shape[0]
@@ -511,11 +516,11 @@ def pack_w2s(w):
     return out
 
 
-def emulate_layer0s(pix_u16, wimg_u16, T, HW, B, columns=None):
-    """Split-fp16 conv 0 in the kernel's order (tc_conv.cu: next_l0s) with the REAL tables (debug layer 6): a tile is a
-    column (video, band of R0s rows); stage (frame i, part) feeds output frames i + 1 - kt through weight window kt.
-    Returns {(item, rb): D (T, 128, ncols)} raw accumulators (rows still M-stacked)."""
-    p = Params(6, T, HW, B)
+def emulate_layer0s(pix_u16, wimg_u16, T, HW, B, columns=None, layer=6):
+    """Split-fp16 conv 0 in the kernel's order (tc_conv.cu: next_l0s) with the REAL tables (debug layer 6; 9 = the two-product
+    mode on the hi-only operand X0h): a tile is a column (video, band of R0s rows); stage (frame i, part) feeds output frames
+    i + 1 - kt through weight window kt.  Returns {(item, rb): D (T, 128, ncols)} raw accumulators (rows still M-stacked)."""
+    p = Params(layer, T, HW, B)
     pix = pix_u16.reshape(-1)
     wimg = wimg_u16.reshape(-1)
     columns = range(p.n_tiles) if columns is None else columns

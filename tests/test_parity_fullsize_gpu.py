@@ -37,7 +37,13 @@ def oracle_codes(params, video, dtype=torch.float32):
     return codes
 
 
-def test_default_mode_matches_the_cpu_oracle_on_two_full_classes():
+_ORACLE = {}
+
+
+@pytest.mark.parametrize('precision', ['f16x3r2', 'f16x3'])
+def test_default_mode_matches_the_cpu_oracle_on_two_full_classes(precision):
+    """f16x3r2 (default): synthetic branch on three products per MAC, frozen real branch on two (exact weights, activations
+    rounded once to fp16); f16x3: three products everywhere."""
     import oracle
     from oracle import synth
     from video_distillation_b200.distill import DeviceDataset, DMS2DTrainer
@@ -55,14 +61,16 @@ def test_default_mode_matches_the_cpu_oracle_on_two_full_classes():
     real_idx = [np.random.RandomState(7 + c).permutation(np.arange(c * PER, (c + 1) * PER))[:BATCH_REAL] for c in range(C)]
     indices_class = [list(range(c * PER, (c + 1) * PER)) for c in range(C)]
 
-    # ---- CPU oracle, fp32 (what the reference computes) and fp64 (for the floor)
-    ref = oracle.dm_s2d_iteration(params, static, dynamic, halp, videos, indices_class, vpc=1, spc=2, batch_real=BATCH_REAL,
-                                  coin_dynamic=coin_d, coin_static=coin_s, real_idx=real_idx)
-    p64 = {k: v.double() for k, v in params.items()}
-    ref64 = oracle.dm_s2d_iteration(p64, static.double(), dynamic.double(), {k: v.double() for k, v in halp.items()},
-                                    videos.double(), indices_class, vpc=1, spc=2, batch_real=BATCH_REAL,
-                                    coin_dynamic=coin_d, coin_static=coin_s, real_idx=real_idx)
-    codes32 = oracle_codes(params, ref['image_syn'])
+    # ---- CPU oracle, fp32 (what the reference computes) and fp64 (for the floor); computed once for both precisions
+    if not _ORACLE:
+        _ORACLE['ref'] = oracle.dm_s2d_iteration(params, static, dynamic, halp, videos, indices_class, vpc=1, spc=2, batch_real=BATCH_REAL,
+                                                 coin_dynamic=coin_d, coin_static=coin_s, real_idx=real_idx)
+        p64 = {k: v.double() for k, v in params.items()}
+        _ORACLE['ref64'] = oracle.dm_s2d_iteration(p64, static.double(), dynamic.double(), {k: v.double() for k, v in halp.items()},
+                                                   videos.double(), indices_class, vpc=1, spc=2, batch_real=BATCH_REAL,
+                                                   coin_dynamic=coin_d, coin_static=coin_s, real_idx=real_idx)
+        _ORACLE['codes32'] = oracle_codes(params, _ORACLE['ref']['image_syn'])
+    ref, ref64, codes32 = _ORACLE['ref'], _ORACLE['ref64'], _ORACLE['codes32']
 
     # ---- the CUDA path in its default precision
     ds = DeviceDataset(videos, labels, C, 'cuda')
@@ -77,7 +85,7 @@ def test_default_mode_matches_the_cpu_oracle_on_two_full_classes():
         hal = Conv3DNet()
         hal.load_state_dict(halp)
         tr = DMS2DTrainer(ds, num_classes=C, im_size=(HW, HW), frames=T, vpc=1, spc=2, dpc=2, batch_real=BATCH_REAL,
-                          lr_dynamic=1e4, lr_hal=1e-2, precision='f16x3', hal=hal, static_syn=static, dynamic_syn=dynamic)
+                          lr_dynamic=1e4, lr_hal=1e-2, precision=precision, hal=hal, static_syn=static, dynamic_syn=dynamic)
         tr.embedder.tc.codes_override = codes
         loss = tr.step(net=net, indices=(label.cuda(), didx.cuda(), sidx.cuda()), real_idx=np.stack(real_idx))
         return loss.item(), tr.last, tr.dynamic_syn.grad.clone(), tr.hal.encoder.weight.grad.clone(), tr.hal.encoder.bias.grad.clone()
@@ -93,7 +101,7 @@ def test_default_mode_matches_the_cpu_oracle_on_two_full_classes():
     unc = dict(dyn=rel(g_dyn, ref['grad_dynamic']), hal_w=rel(g_hw, ref['grad_hal_weight']), hal_b=rel(g_hb, ref['grad_hal_bias']))
     floor = dict(dyn=rel(ref['grad_dynamic'], ref64['grad_dynamic']), hal_w=rel(ref['grad_hal_weight'], ref64['grad_hal_weight']),
                  hal_b=rel(ref['grad_hal_bias'], ref64['grad_hal_bias']))
-    print('f16x3 vs CPU oracle at the bench shape (2 full classes):', {k: f'{v:.2e}' for k, v in e.items()})
+    print(f'{precision} vs CPU oracle at the bench shape (2 full classes):', {k: f'{v:.2e}' for k, v in e.items()})
     print('  gradients conditioned on the oracle routing :', {k: f'{v:.2e}' for k, v in cond.items()})
     print('  gradients unconditioned                     :', {k: f'{v:.2e}' for k, v in unc.items()})
     print('  fp32 oracle vs fp64 oracle (the floor)      :', {k: f'{v:.2e}' for k, v in floor.items()})

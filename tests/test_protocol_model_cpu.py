@@ -15,6 +15,8 @@ SHAPES = {
     'wgrad': (5, 1, 8, 8, 2, 2, 2, False),
     'split conv1': (3, 8, 75, 6, 2, 3, 1, False),          # groups of 6 MMAs over ring slots of 4 weight tiles
     'split conv2': (49, 4, 18, 6, 2, 3, 1, False),
+    'two-product conv1': (3, 8, 50, 5, 2, 3, 1, False),    # frozen real videos: xh.wh + xh.wl, every weight tile used once
+    'two-product conv2': (49, 4, 12, 6, 2, 3, 1, False),
 }
 
 
@@ -56,6 +58,17 @@ def test_split_conv0_generator(T, n_tiles, grid, cta, RP):
     columns = len(range(cta, n_tiles, grid))
     for latency in (1, 3, 11):
         assert simulate(L, cta, mma_latency=latency) == columns * 2 * T
+
+
+@pytest.mark.parametrize('T', [4, 8, 16, 32])
+@pytest.mark.parametrize('n_tiles,grid,cta', [(1, 1, 0), (4, 2, 1), (5, 3, 0), (2, 148, 1)])
+@pytest.mark.parametrize('RP', [2, 3, 4])
+def test_two_product_conv0_generator(T, n_tiles, grid, cta, RP):
+    # two-product conv 0 (hi part only): T stages = one MMA group each, 4 rotating accumulators
+    L = Launch(n_tiles, grid, T, 1, 11, 1, RP, 1, 4, True, stream_pairs=T, stream_mode=2)
+    columns = len(range(cta, n_tiles, grid))
+    for latency in (1, 3, 11):
+        assert simulate(L, cta, mma_latency=latency) == columns * T
 
 
 @pytest.mark.parametrize('latency', [1, 2, 5, 17])

@@ -177,3 +177,62 @@ def test_split_layer2_tables(T, HW):
     d = torch.from_numpy(D[0]).reshape(4, 128, g.To2, g.Ho2, g.Wo2)
     assert rel(d[:B], y) < 2e-6, rel(d[:B], y)
     assert float(d[B:].abs().max()) == 0.0
+
+
+# ------------------------------------------------------------------ two-product mode of the frozen real videos (passes = 2)
+# y = xh*wh + xh*wl on the hi part of the operands only (debug layers 9 / 10 / 11): same layouts and weight images
+@pytest.mark.parametrize('T,HW,cols', [(8, 64, [0, 15]), (4, 112, [0, 27, 55])])
+def test_two_product_layer0_tables_and_schedule(T, HW, cols):
+    g = em.Geo(T, HW)
+    sg = em.SGeo(g)
+    B = 2
+    gen = torch.Generator().manual_seed(T + 7)
+    video = torch.randn(B, T, 3, HW, HW, generator=gen)
+    w = torch.randn(64, 3, 3, 7, 7, generator=gen) * 0.05
+    xh = em.from_f16_bits(em.split_f16(video)[0])
+    y = conv_ref(xh.permute(0, 2, 1, 3, 4), em.f16x2_round(w))
+    out, p = em.emulate_layer0s(em.pack_x0h(video, g), em.pack_w0s(w), T, HW, B, cols, layer=9)
+    assert p.n_sb == 1 and p.item_stride == (T + 2) * 6 * g.plane0 and p.ncols == sg.N0s and p.smem_total <= 232448
+    for (item, rb), D in out.items():
+        d = torch.from_numpy(em.unstack_l0s(D)).reshape(T, 64, sg.R0s, g.Wo0)
+        ref = y[item, :, :, rb * sg.R0s:(rb + 1) * sg.R0s, :].permute(1, 0, 2, 3)
+        assert rel(d, ref) < 2e-6, (item, rb, rel(d, ref))
+
+
+@pytest.mark.parametrize('T,HW,tiles', [(8, 64, [0, 1]), (4, 112, [1])])
+def test_two_product_layer1_tables(T, HW, tiles):
+    g = em.Geo(T, HW)
+    B = 1
+    gen = torch.Generator().manual_seed(HW + 3)
+    x = torch.randn(B, 64, T, g.H1, g.H1, generator=gen).abs()
+    w = torch.randn(128, 64, 3, 7, 7, generator=gen) * 0.02
+    xh = em.from_f16_bits(em.split_f16(x)[0])
+    y = conv_ref(xh, em.f16x2_round(w))
+    a1 = em.pack_a1s(x, g)
+    a1[:, :, :, 1] = 0x7e00                       # the lo planes are never read (NaN if they were)
+    D, p = em.emulate_layer(10, a1, em.pack_w1s(w), T, HW, B, tiles, fmt='f16')
+    assert p.n_steps == 50 and p.Gt == 0 and p.smem_total <= 232448 and p.n_acc * p.acc_cols <= 512
+    assert p.stage_bytes == p.n_acc * 4 * g.plane1
+    fpt = p.n_acc
+    for k, tile in enumerate(tiles):
+        item, tq = divmod(tile, p.tiles_per_item)
+        d = torch.from_numpy(D[k]).reshape(fpt, 128, g.Ho1, g.P1)[:, :, :, :g.Wo1]
+        ref = y[item, :, fpt * tq:fpt * tq + fpt].permute(1, 0, 2, 3)
+        assert rel(d, ref) < 2e-6, (tile, rel(d, ref))
+
+
+@pytest.mark.parametrize('T,HW', [(8, 64), (8, 112)])
+def test_two_product_layer2_tables(T, HW):
+    g = em.Geo(T, HW)
+    B = 3
+    gen = torch.Generator().manual_seed(HW + 5)
+    x = torch.randn(B, 128, g.T2, g.H2, g.H2, generator=gen).abs()
+    w = torch.randn(128, 128, 3, 7, 7, generator=gen) * 0.02
+    xh = em.from_f16_bits(em.split_f16(x)[0])
+    y = conv_ref(xh, em.f16x2_round(w))
+    a2 = em.pack_a2s(x, g, Bpad=4)
+    a2.reshape(4, 49, 4, 2, -1)[:, :, :, 1] = 0x7e00      # lo chunks [video][khw][quarter][part][...] are never read
+    D, p = em.emulate_layer(11, a2, em.pack_w2s(w), T, HW, B, fmt='f16')
+    assert p.n_acc == 4 and p.n_tiles == 1 and p.n_steps == 12 and p.Gt == 0
+    d = torch.from_numpy(D[0]).reshape(4, 128, g.To2, g.Ho2, g.Wo2)
+    assert rel(d[:B], y) < 2e-6, rel(d[:B], y)

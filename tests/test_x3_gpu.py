@@ -32,7 +32,7 @@ def conv64(x, w, b=None):
     return F.conv3d(x.double().cpu(), w.double().cpu(), None if b is None else b.double().cpu(), stride=S, padding=P)
 
 
-def make_net(T, HW, seed=0, reference_init=False):
+def make_net(T, HW, seed=0, reference_init=False, real_products=3):
     from video_distillation_b200.tc import TcConvNet3D
     g = torch.Generator().manual_seed(seed)
     if reference_init:
@@ -43,7 +43,7 @@ def make_net(T, HW, seed=0, reference_init=False):
         ws = [torch.randn(64, 3, 3, 7, 7, generator=g) * 0.08, torch.randn(64, generator=g) * 0.1,
               torch.randn(128, 64, 3, 7, 7, generator=g) * 0.02, torch.randn(128, generator=g) * 0.1,
               torch.randn(128, 128, 3, 7, 7, generator=g) * 0.02, torch.randn(128, generator=g) * 0.1]
-    net = TcConvNet3D(T, HW, HW, 'cuda', split=True)
+    net = TcConvNet3D(T, HW, HW, 'cuda', split=True, real_products=real_products)
     net.load_weights(*(t.cuda() for t in ws))
     return net, ws
 
@@ -210,3 +210,61 @@ def test_x3_embed_geometry_sweep_against_the_fp32_oracle(T, HW, B):
         got, want = codes[d].cpu(), codes32[d]
         same = (((got & 8) > 0) == ((want & 8) > 0)) & (((got & 7) == (want & 7)) | ((want & 8) == 0))
         assert same.float().mean().item() > 0.999, (d, same.float().mean().item())
+
+
+# ------------------------------------------------------------------ two-product mode of the frozen real videos
+def f16r(x):
+    return x.float().to(torch.float16).float()
+
+
+@pytest.mark.parametrize('T,HW', CASES)
+def test_two_product_mode_layers_embed_and_means(T, HW):
+    """real_products=2: y = xh*wh + xh*wl.  (1) hi-only packer bit-exact; (2) every layer against fp64 conv + ReLU + MaxPool of
+    the values actually stored (fp16 activations, fp16-pair weights); (3) the embed against the fp32 CPU oracle per video
+    (one fp16 rounding per activation: ~2e-4) and as a class mean (the roundings are independent from video to video);
+    (4) chunking / resident-set addressing are bitwise consistent and the differentiable path still takes three products."""
+    net, ws = make_net(T, HW, seed=2, reference_init=True, real_products=2)
+    full, _ = make_net(T, HW, seed=2, reference_init=True)
+    g = em.Geo(T, HW)
+    sg = em.SGeo(g)
+    B = 13
+    video = torch.randn(B, T, 3, HW, HW, generator=torch.Generator().manual_seed(9))
+    x0h = net.pack_video(video.cuda(), hi_only=True).cpu().numpy().view(np.uint16)
+    refp = em.pack_x0h(video, g).reshape(-1)
+    assert np.array_equal(x0h[:refp.size], refp)
+    emb = net.embed(video.cuda(), frozen=True)
+    torch.cuda.synchronize()
+    w0, b0, w1, b1, w2, b2 = ws
+    # stored operands: hi planes / chunks of A1s, A2s (unpack_* add the lo part: mask it out by re-rounding is not possible, so
+    # compare the kernel's hi values with fp16(pooled fp64 result))
+    y0 = conv64(f16r(video).permute(0, 2, 1, 3, 4), em.f16x2_round(w0), b0)
+    p0 = F.max_pool3d(F.relu(y0), POOL[0], POOL[0]).float()
+    y1 = conv64(f16r(p0), em.f16x2_round(w1), b1)
+    p1 = F.max_pool3d(F.relu(y1), POOL[1], POOL[1]).float()
+    y2 = conv64(f16r(p1), em.f16x2_round(w2), b2)
+    p2 = F.max_pool3d(F.relu(y2), POOL[2], POOL[2]).float().reshape(B, -1)
+    assert rel(emb, p2) < 2e-4, rel(emb, p2)          # same arithmetic, fp64 accumulate; fp16 re-rounding of near-tie values differs
+    from oracle import convnet3d_embed
+    e32 = convnet3d_embed(params_of(ws), video)
+    per_video = max(rel(emb[i], e32[i]) for i in range(B))
+    mean_err = rel(emb.mean(0), e32.mean(0))
+    e_full = full.embed(video.cuda())
+    print(f'two-product embed T={T} HW={HW}: vs fp64 of the stored operands {rel(emb, p2):.2e}; vs fp32 oracle per video (max) {per_video:.2e}, '
+          f'mean of {B} videos {mean_err:.2e} (three products: per video {max(rel(e_full[i], e32[i]) for i in range(B)):.2e}, '
+          f'mean {rel(e_full.mean(0), e32.mean(0)):.2e})')
+    assert per_video < 1e-3, per_video
+    assert mean_err < 3e-4, mean_err
+    # resident set (hi-only operand, half the bytes), gather index, chunking
+    x0 = net.pack_dataset(video.cuda())
+    assert x0.numel() == B * net.x0h_per and net.x0h_per * 2 == net.x0_per
+    idx = torch.tensor([4, 1, 12, 0, 7], device='cuda')
+    er = net.embed_resident(x0, idx)
+    assert torch.equal(er, emb[idx])
+    net.max_batch = 4
+    assert torch.equal(net.embed(video.cuda(), frozen=True), emb)
+    # joint pass: real videos two products, synthetic videos three products + codes (== the full-precision net, bitwise)
+    syn = torch.randn(3, T, 3, HW, HW, generator=torch.Generator().manual_seed(10)).cuda()
+    er2, es, codes = net.embed_joint(x0, idx, syn, B)
+    es_full, codes_full = full.embed(syn, want_codes=True)
+    assert torch.equal(er2, emb[idx]) and torch.equal(es, es_full)
+    assert all(torch.equal(a, b) for a, b in zip(codes, codes_full))

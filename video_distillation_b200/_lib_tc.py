@@ -16,6 +16,9 @@ def declare(lib):
         'vd_tc_x3_pack_video_u8': (c_int, [P, P, P, POINTER(TcPlan), c_int, P, P, P]),
         'vd_tc_x3_pack_weights': (c_int, [P, P, P, P, P, P, P]),
         'vd_tc_x3_conv_layer': (c_int, [c_int, P, P, P, P, P, c_int, POINTER(TcPlan), P, c_int, P]),
+        'vd_tc_x3_conv_layer_ex': (c_int, [c_int, P, P, P, P, P, c_int, POINTER(TcPlan), P, c_int, c_int, P]),
+        'vd_tc_x3_pack_video_hi': (c_int, [P, P, P, POINTER(TcPlan), c_int, P]),
+        'vd_tc_x3_pack_video_hi_u8': (c_int, [P, P, P, POINTER(TcPlan), c_int, P, P, P]),
         'vd_tc_pack_weights_bwd': (c_int, [P, P, P, P, P, P, P]),
         'vd_tc_bwd_emb': (c_int, [P, P, P, POINTER(TcPlan), c_int, P]),
         'vd_tc_bwd_gemm': (c_int, [c_int, P, P, P, POINTER(TcPlan), c_int, P]),

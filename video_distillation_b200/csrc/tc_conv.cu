@@ -42,6 +42,8 @@ struct EpiParams {
     int T;                 // frames of the video
     int n_items;           // videos (conv 2: valid videos, tiles may be partially filled)
     int r0s;               // EPI_L0S: output rows per column band (SGeo::R0s)
+    int hi_only;           // EPI_L0S / EPI_L1S: write only the hi part of the next layer's operand (two-product mode of the
+                           //   frozen real videos: the next layer reads xh only)
     Geo g;
 };
 
@@ -96,6 +98,8 @@ struct WsParams {
                                         //   pair-by-pair order and no MMAs on the all-zero temporal halo frames
     int32_t stream_mode;                // 0 / 1: stream_pairs as described above; 2: split-fp16 conv 0 (SGeo): stream_pairs = T
                                         //   accumulators per column, stages (frame i, part), groups kt = 2, 1, 0 -> frame i + 1 - kt
+    int32_t l0s_parts;                  // stream_mode 2: stages per input frame (2: hi and lo part; 1: hi part only = the
+                                        //   two-product mode xh*wh + xh*wl of the frozen real videos)
     int32_t n_wsets;                    // resident weights: number of weight windows in the descriptor table (0: n_sa)
     int32_t dbg;                        // tuning experiments (VD_TC_DBG bitmask; results are garbage when set):
                                         //   1 no pixel copies, 2 no weight copies, 4 epilogue does no work,
@@ -364,7 +368,7 @@ __device__ __forceinline__ void epi_l0s_drain(const WsParams& p, int item, int f
                 uint16_t hi, lo;
                 split_h(act ? best : 0.f, hi, lo);
                 s_hi[(pr * Wp + wp) * kStash0sPitch] = hi;
-                s_lo[(pr * Wp + wp) * kStash0sPitch] = lo;
+                if (!p.epi.hi_only) s_lo[(pr * Wp + wp) * kStash0sPitch] = lo;
                 if (cbase) cbase[hp * g.H1 + wp] = (uint8_t)(arg | (act ? 8 : 0));
             }
         }
@@ -376,7 +380,8 @@ __device__ __forceinline__ void epi_l0s_store(const WsParams& p, int item, int f
     const Geo& g = p.epi.g;
     const int R = p.epi.r0s, Wp = g.Wo0 / 2, npos = (R / 2) * Wp;
     uint8_t* fbase = p.epi.out + (int64_t)item * (8 * g.slice1) + (int64_t)(f + 1) * g.frame1;
-    for (int it = lane; it < 4 * npos; it += 32) {
+    const int n_it = (p.epi.hi_only ? 2 : 4) * npos;
+    for (int it = lane; it < n_it; it += 32) {
         const int sel = it / npos, pos = it - sel * npos;
         const int part = sel >> 1, kk = sel & 1;
         const int pr = pos / Wp, wp = pos - pr * Wp;
@@ -507,7 +512,7 @@ __device__ __forceinline__ void epi_l1s_drain(const WsParams& p, int tile, uint3
                     uint16_t hi, lo;
                     split_h(act ? best : 0.f, hi, lo);
                     st_hi[(hp * g.H2 + wp) * kStashPitch + m] = hi;
-                    st_lo[(hp * g.H2 + wp) * kStashPitch + m] = lo;
+                    if (!p.epi.hi_only) st_lo[(hp * g.H2 + wp) * kStashPitch + m] = lo;
                     if (cbase) cbase[hp * g.H2 + wp] = (uint8_t)(arg | (act ? 8 : 0));
                 }
             }
@@ -520,10 +525,11 @@ __device__ __forceinline__ void epi_l1s_store(const WsParams& p, int tile, int q
     const int item = tile / p.tiles_per_item, tq = tile % p.tiles_per_item;
     const int npair = p.n_acc >> 1;
     const int npos = g.H2 * g.H2;
+    const int n_it = (p.epi.hi_only ? 4 : 8) * npos;
     for (int pp = 0; pp < npair; ++pp) {
         const int tp = tq * npair + pp;
         uint8_t* vbase = p.epi.out + (int64_t)item * (196 * g.group2) + (int64_t)q * g.group2 + (int64_t)(tp + 1) * g.HW2 * 16;
-        for (int i = lane; i < 8 * npos; i += 32) {
+        for (int i = lane; i < n_it; i += 32) {
             const int sel = i / npos, pos = i - sel * npos;
             const int part = sel >> 2, kk = sel & 3;                 // warp q = quarter q, chunk kk of the quarter
             const int hp = pos / g.H2, wp = pos - hp * g.H2;
@@ -967,13 +973,13 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
             // qbase + f over the columns of this CTA) lives in accumulator buffer (qbase + f) & 3; its first write is
             // (i = f - 1, hi part, kt = 0) — for f = 0: (i = 0, hi, kt = 1) — and its last (i = f + 1, lo part, kt = 2) — for
             // f = T - 1: (i = T - 1, lo, kt = 1).
-            const int smode = p.stream_mode;
+            const int nparts = p.l0s_parts == 1 ? 1 : 2;
             int ss = 0;
             auto next_l0s = [&](Group& r) {
                 // ONE group per stage (up to 3 x n_steps MMAs): a hand-over between the two issuers costs ~300 cycles, more than the
                 // two queued N = 112 MMAs (2 x 56 cycles) hide, so groups of 11 short MMAs left the pipe 38 % idle
                 const int T = pairs;
-                const int i = ss >> 1, part = ss & 1;
+                const int i = nparts == 2 ? ss >> 1 : ss, part = nparts == 2 ? (ss & 1) : 0;
                 r.nseg = 0;
                 r.w_acc = 0u; r.w_acc2 = 0u; r.c_acc = 0u; r.c_acc2 = 0u; r.p_acc = 0u; r.p_acc2 = 0u;
                 for (int kt = 2; kt >= 0; --kt) {
@@ -982,7 +988,7 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
                     const uint32_t q = qbase + (uint32_t)f;
                     const uint32_t buf = q & 3u;
                     const bool first_write = part == 0 && (kt == 0 || (f == 0 && kt == 1));
-                    const bool final_write = part == 1 && (kt == 2 || (f == T - 1 && kt == 1));
+                    const bool final_write = part == nparts - 1 && (kt == 2 || (f == T - 1 && kt == 1));
                     const uint64_t* ta = tabA + kt * n_steps;
                     const uint32_t d = tmem_base + buf * (acc_cols * (uint32_t)NACC);
                     if (r.nseg == 0) { r.ta = ta; r.d_base = d; r.acc0 = first_write ? 0u : 1u; }
@@ -1004,7 +1010,7 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
                 r.c_w = 0u;
                 r.c_pix = BAR(pix_empty, pslot);
                 if (++pslot == RP) { pslot = 0; pphase ^= 1; }
-                if (++ss < 2 * T) return;
+                if (++ss < nparts * T) return;
                 ss = 0; qbase += (uint32_t)T; tile += gridDim.x;
             };
             long long c_acc = 0, c_pix = 0, c_w = 0, c_baton = 0, c_issue = 0;
@@ -1296,19 +1302,27 @@ static int setup_l2(WsParams& p, const Geo& g, int B, uint32_t* smem) {
 // ---- split-fp16 forward (SGeo, tc_layout.h) ----
 // conv 0: column tiles (video, band of R0s rows); stages (frame i, part) of the X0s operand; resident M-stacked weight
 // image [kt 3][step 11] x 4 KiB; 4 accumulators of 128 columns (output frames f & 3).
-static int setup_l0s(WsParams& p, const Geo& g, int B, uint32_t* smem) {
+//
+// passes = 3 (default): all products of the hi / lo pairs.  passes = 2 ("two-product" mode of the frozen real videos):
+// the activations are carried as ONE fp16 value (xh) and only the weights as a pair, y = xh*wh + xh*wl — the weights are
+// exact, and the single rounding of each activation is independent from video to video, so it averages out of the class
+// means the DM loss reads (distill_s2d_ms.py:419-422).  The operand is then the hi-only layout X0h = X0 of tc_layout.h
+// holding fp16 values (6 planes per frame), a frame is ONE stage, and the epilogues write the hi part only.
+static int setup_l0s(WsParams& p, const Geo& g, int B, uint32_t* smem, int passes = 3) {
     const SGeo sg = make_sgeo(g);
+    const bool two = passes == 2;
     p.n_u = 1; p.nu_total = 1; p.ug_count = 1; p.w_u_stride = 0;
     p.n_tiles = B * sg.nrb0s; p.tiles_per_item = sg.nrb0s; p.v_count = sg.nrb0s;
-    p.item_stride = sg.video0s; p.u_stride = 0; p.v_stride = (int64_t)sg.R0s * g.Wo0 * 16;
-    p.n_sa = g.T; p.n_sb = 2; p.sa_stride = sg.frame0s; p.sb_stride = 6 * g.plane0;
+    p.item_stride = two ? g.video0 : sg.video0s; p.u_stride = 0; p.v_stride = (int64_t)sg.R0s * g.Wo0 * 16;
+    p.n_sa = g.T; p.n_sb = two ? 1 : 2; p.sa_stride = two ? g.frame0 : sg.frame0s; p.sb_stride = 6 * g.plane0;
+    p.l0s_parts = two ? 1 : 2;
     p.n_copies = 6;
     uint32_t sofs = 0;
     uint32_t blk[3][2];
     for (int c = 0; c < 3; ++c)
         for (int par = 0; par < 2; ++par) {
             const int i = c * 2 + par;
-            p.copy_gofs[i] = sg.frame0s + (int64_t)i * g.plane0;        // frame i of the video is t_pad = i + 1
+            p.copy_gofs[i] = (two ? g.frame0 : sg.frame0s) + (int64_t)i * g.plane0;        // frame i of the video is t_pad = i + 1
             p.copy_sofs[i] = sofs;
             p.copy_bytes[i] = (uint32_t)(sg.R0s + 2 + par) * g.Wo0 * 16;
             blk[c][par] = sofs;
@@ -1338,7 +1352,10 @@ static int setup_l0s(WsParams& p, const Geo& g, int B, uint32_t* smem) {
 }
 
 // conv 1: the tile / stage geometry of setup_l1 with 8-channel chunks carrying both parts; 74 steps per stage
-static int setup_l1s(WsParams& p, const Geo& g, int B, uint32_t* smem) {
+// passes = 2: the stage copies only the hi planes of each frame and a tap pair gets two MMAs, xh.wh and xh.wl (50 per stage,
+// every streamed weight tile used once)
+static int setup_l1s(WsParams& p, const Geo& g, int B, uint32_t* smem, int passes = 3) {
+    const bool two = passes == 2;
     p.n_u = 1; p.nu_total = 1; p.ug_count = 1; p.w_u_stride = 0;
     const bool nacc4 = g.N1 <= 128 && g.T % 4 == 0;
     const int fpt = nacc4 ? 4 : 2;                                      // output frames per tile
@@ -1348,7 +1365,13 @@ static int setup_l1s(WsParams& p, const Geo& g, int B, uint32_t* smem) {
     p.n_sa = 3; p.n_sb = 8; p.sa_stride = g.frame1; p.sb_stride = g.slice1;
     p.n_copies = 1; p.copy_gofs[0] = 0; p.copy_sofs[0] = 0; p.copy_bytes[0] = (uint32_t)(fpt * g.frame1);
     p.stage_bytes = (uint32_t)(fpt * g.frame1);
-    p.n_steps = kSteps1s;
+    const uint32_t fstride = two ? 4u * (uint32_t)g.plane1 : (uint32_t)g.frame1;          // staged bytes per frame
+    if (two) {
+        p.n_copies = fpt;
+        for (int f = 0; f < fpt; ++f) { p.copy_gofs[f] = (int64_t)f * g.frame1; p.copy_sofs[f] = (uint32_t)f * fstride; p.copy_bytes[f] = fstride; }
+        p.stage_bytes = (uint32_t)fpt * fstride;
+    }
+    p.n_steps = two ? 50 : kSteps1s;
     uint32_t off[49];
     for (int i = 0; i < 49; ++i) {
         const int tap = l1s_tap(i), kh = tap / 7, kw = tap % 7;
@@ -1360,6 +1383,10 @@ static int setup_l1s(WsParams& p, const Geo& g, int B, uint32_t* smem) {
     // weight tile), xh.wl.  The empty second half of pair 0 has zero weights and addresses tap 1's window (valid staged data).
     for (int pr = 0; pr < 25; ++pr) {
         const int a = pr ? 2 * pr - 1 : 0, b = pr ? 2 * pr : 1;
+        if (two) {
+            for (int m = 0; m < 2; ++m) { p.b_off16[2 * pr + m] = off[a] >> 4; p.b_lbo16[2 * pr + m] = (off[b] - off[a]) >> 4; }
+            continue;
+        }
         for (int m = 0; m < 3; ++m) {
             p.b_off16[3 * pr + m] = (off[a] + (m == 1 ? 4u * (uint32_t)g.plane1 : 0u)) >> 4;
             p.b_lbo16[3 * pr + m] = (off[b] - off[a]) >> 4;
@@ -1367,17 +1394,24 @@ static int setup_l1s(WsParams& p, const Geo& g, int B, uint32_t* smem) {
     }
     p.a_lbo16 = 2048 >> 4; p.a_sbo16 = 8;
     p.w_resident = 0; p.w_bytes = 0;
-    // a group = two tap pairs: 6 MMAs per accumulator over 4 weight tiles [wh_p, wl_p, wh_p+1, wl_p+1]
-    p.G = 6; p.Gt = 4; p.n_wtiles = 50; p.RW = env_int("VD_TC_L1S_RW", 3); p.RP = 2;
-    { const uint8_t pat[6] = {0, 0, 1, 2, 2, 3}; for (int i = 0; i < 6; ++i) p.a_in_group[i] = pat[i]; }
-    p.n_acc = fpt; p.acc_delta16 = (uint32_t)g.frame1 >> 4;
+    if (two) {
+        // tiles [wh_p, wl_p] in image order, one MMA each: the ring of the single-pass conv 1 (3 slots x 5 steps)
+        p.G = env_int("VD_TC_L1W_G", 5); p.Gt = 0; p.n_wtiles = 0; p.RW = env_int("VD_TC_L1W_RW", 3); p.RP = env_int("VD_TC_L1W_RP", 2);
+    } else {
+        // a group = two tap pairs: 6 MMAs per accumulator over 4 weight tiles [wh_p, wl_p, wh_p+1, wl_p+1]
+        p.G = 6; p.Gt = 4; p.n_wtiles = 50; p.RW = env_int("VD_TC_L1S_RW", 3); p.RP = 2;
+        const uint8_t pat[6] = {0, 0, 1, 2, 2, 3}; for (int i = 0; i < 6; ++i) p.a_in_group[i] = pat[i];
+    }
+    p.n_acc = fpt; p.acc_delta16 = fstride >> 4;
     p.ncols = g.N1; p.acc_cols = nacc4 ? 128 : 256; p.acc_stages = 1;
     p.idesc = umma_idesc_f16(128, g.N1);
-    return finalize_smem(p, (uint32_t)p.Gt * p.RW * kWeightTileBytes, smem, false, (uint32_t)(2 * (fpt / 2) * g.H2 * g.H2) * kStashPitch * 2);
+    return finalize_smem(p, (uint32_t)(p.Gt ? p.Gt : p.G) * p.RW * kWeightTileBytes, smem, false, (uint32_t)(2 * (fpt / 2) * g.H2 * g.H2) * kStashPitch * 2);
 }
 
 // conv 2: the tile / stage geometry of setup_l2 with 32-channel quarters carrying both parts; 18 steps per stage
-static int setup_l2s(WsParams& p, const Geo& g, int B, uint32_t* smem) {
+// passes = 2: hi chunks only, two MMAs per chunk pair (xh.wh, xh.wl): 12 per stage
+static int setup_l2s(WsParams& p, const Geo& g, int B, uint32_t* smem, int passes = 3) {
+    const bool two = passes == 2;
     p.n_u = 1; p.nu_total = 1; p.ug_count = 1; p.w_u_stride = 0;
     const int VPT = kVideosPerTile2;
     const SGeo sg = make_sgeo(g);
@@ -1386,29 +1420,42 @@ static int setup_l2s(WsParams& p, const Geo& g, int B, uint32_t* smem) {
     p.item_stride = VPT * sg.video2s; p.u_stride = 0; p.v_stride = 0;
     p.n_sa = 49; p.n_sb = 4; p.sa_stride = 4 * g.group2; p.sb_stride = g.group2;
     p.n_copies = VPT;
+    const uint32_t vbytes = (uint32_t)(two ? g.group2 / 2 : g.group2);       // staged bytes per video: [part][k 4] chunks, hi part first
     for (int v = 0; v < VPT; ++v) {
         p.copy_gofs[v] = (int64_t)v * sg.video2s;
-        p.copy_sofs[v] = (uint32_t)(v * g.group2);
-        p.copy_bytes[v] = (uint32_t)g.group2;
+        p.copy_sofs[v] = (uint32_t)v * vbytes;
+        p.copy_bytes[v] = vbytes;
     }
-    p.stage_bytes = (uint32_t)(VPT * g.group2);
-    p.n_steps = kSteps2s;
+    p.stage_bytes = (uint32_t)VPT * vbytes;
+    p.n_steps = two ? 12 : kSteps2s;
     for (int kt = 0; kt < 3; ++kt) {
         const uint32_t tofs = (uint32_t)((int64_t)kt * g.HW2 * 16);
-        for (int pr = 0; pr < 2; ++pr)                                  // chunk pair (2pr, 2pr+1) in the two K halves
+        for (int pr = 0; pr < 2; ++pr) {                                // chunk pair (2pr, 2pr+1) in the two K halves
+            if (two) {
+                for (int m = 0; m < 2; ++m) {                           // xh.wh, xh.wl
+                    p.b_off16[kt * 4 + pr * 2 + m] = (uint32_t)((2 * pr) * g.chunk2 + tofs) >> 4;
+                    p.b_lbo16[kt * 4 + pr * 2 + m] = (uint32_t)g.chunk2 >> 4;
+                }
+                continue;
+            }
             for (int m = 0; m < 3; ++m) {                               // xh.wh, xl.wh (same weight tile), xh.wl
                 p.b_off16[kt * 6 + pr * 3 + m] = (uint32_t)((2 * pr + (m == 1 ? 4 : 0)) * g.chunk2 + tofs) >> 4;
                 p.b_lbo16[kt * 6 + pr * 3 + m] = (uint32_t)g.chunk2 >> 4;
             }
+        }
     }
     p.a_lbo16 = 2048 >> 4; p.a_sbo16 = 8;
     p.w_resident = 0; p.w_bytes = 0;
-    p.G = 6; p.Gt = 4; p.n_wtiles = 12; p.RW = env_int("VD_TC_L2S_RW", 3); p.RP = 2;
-    { const uint8_t pat[6] = {0, 0, 1, 2, 2, 3}; for (int i = 0; i < 6; ++i) p.a_in_group[i] = pat[i]; }
-    p.n_acc = VPT; p.acc_delta16 = (uint32_t)g.group2 >> 4;
+    if (two) {
+        p.G = env_int("VD_TC_L2W_G", 6); p.Gt = 0; p.n_wtiles = 0; p.RW = env_int("VD_TC_L2W_RW", 3); p.RP = env_int("VD_TC_L2W_RP", 2);
+    } else {
+        p.G = 6; p.Gt = 4; p.n_wtiles = 12; p.RW = env_int("VD_TC_L2S_RW", 3); p.RP = 2;
+        const uint8_t pat[6] = {0, 0, 1, 2, 2, 3}; for (int i = 0; i < 6; ++i) p.a_in_group[i] = pat[i];
+    }
+    p.n_acc = VPT; p.acc_delta16 = vbytes >> 4;
     p.ncols = g.N2; p.acc_cols = 128; p.acc_stages = 1;
     p.idesc = umma_idesc_f16(128, g.N2);
-    return finalize_smem(p, (uint32_t)p.Gt * p.RW * kWeightTileBytes, smem);
+    return finalize_smem(p, (uint32_t)(p.Gt ? p.Gt : p.G) * p.RW * kWeightTileBytes, smem);
 }
 
 static int setup_bwd(WsParams& p, const Geo& g, int layer, int B, uint32_t* smem, bool fp32_out = false) {
@@ -1585,9 +1632,29 @@ extern "C" int vd_tc_x3_sizes(const vd_tc_plan* plan, int64_t* out) {
     return 0;
 }
 
+static int x3_conv_layer_impl(int layer, const void* in, const void* wimg, const float* bias, void* out,
+                              uint8_t* code, int code_first_item, const vd_tc_plan* plan, const int64_t* item_index,
+                              int B, int passes, void* stream);
+
 extern "C" int vd_tc_x3_conv_layer(int layer, const void* in, const void* wimg, const float* bias, void* out,
                                    uint8_t* code, int code_first_item, const vd_tc_plan* plan, const int64_t* item_index,
                                    int B, void* stream) {
+    return x3_conv_layer_impl(layer, in, wimg, bias, out, code, code_first_item, plan, item_index, B, 3, stream);
+}
+
+// passes = 3: vd_tc_x3_conv_layer.  passes = 2: the two-product mode of the frozen real videos (setup_l0s): `in` holds the
+// hi part only (layer 0: the X0h layout = X0 with fp16 values, vd_tc_x3_pack_video_hi; layers 1 / 2: the A1s / A2s layouts
+// with their lo planes unused), the same weight images, and layers 0 / 1 write the hi part of their output only.
+extern "C" int vd_tc_x3_conv_layer_ex(int layer, const void* in, const void* wimg, const float* bias, void* out,
+                                      uint8_t* code, int code_first_item, const vd_tc_plan* plan, const int64_t* item_index,
+                                      int B, int passes, void* stream) {
+    VD_REQUIRE(passes == 2 || passes == 3, "tc_x3_conv_layer_ex: passes must be 2 or 3");
+    return x3_conv_layer_impl(layer, in, wimg, bias, out, code, code_first_item, plan, item_index, B, passes, stream);
+}
+
+static int x3_conv_layer_impl(int layer, const void* in, const void* wimg, const float* bias, void* out,
+                              uint8_t* code, int code_first_item, const vd_tc_plan* plan, const int64_t* item_index,
+                              int B, int passes, void* stream) {
     VD_REQUIRE(plan && in && wimg && out && bias, "tc_x3_conv_layer: NULL pointer");
     VD_REQUIRE(layer >= 0 && layer <= 2, "tc_x3_conv_layer: layer must be 0, 1 or 2");
     VD_REQUIRE(B >= 0 && code_first_item >= 0, "tc_x3_conv_layer: negative batch / code_first_item");
@@ -1598,12 +1665,13 @@ extern "C" int vd_tc_x3_conv_layer(int layer, const void* in, const void* wimg, 
     memset(&p, 0, sizeof(p));
     const Geo g = make_geo(plan->T, plan->H);
     uint32_t smem = 0;
-    int rc = layer == 0 ? setup_l0s(p, g, B, &smem) : layer == 1 ? setup_l1s(p, g, B, &smem) : setup_l2s(p, g, B, &smem);
+    int rc = layer == 0 ? setup_l0s(p, g, B, &smem, passes) : layer == 1 ? setup_l1s(p, g, B, &smem, passes) : setup_l2s(p, g, B, &smem, passes);
     if (rc) { if (rc == -2) set_error("tc x3 conv %d: non-monotone window offsets", layer); return rc; }
     p.pix = (const uint8_t*)in; p.wimg = (const uint8_t*)wimg; p.item_index = item_index;
     p.prof = g_prof; p.dbg = env_int("VD_TC_DBG", 0);
     p.epi.bias = bias; p.epi.out = (uint8_t*)out; p.epi.code = code; p.epi.code_first = code_first_item; p.epi.raw = (float*)out;
     p.epi.T = plan->T; p.epi.n_items = B; p.epi.g = g; p.epi.layer = layer; p.epi.r0s = make_sgeo(g).R0s;
+    p.epi.hi_only = passes == 2;
     cudaStream_t s = (cudaStream_t)stream;
     if (layer == 0) return launch<EPI_L0S>(p, smem, s);
     if (layer == 1) return launch<EPI_L1S>(p, smem, s);
@@ -1614,14 +1682,16 @@ extern "C" int vd_tc_x3_conv_layer(int layer, const void* in, const void* wimg, 
 // parameters that vd_tc_conv_layer would launch with.
 extern "C" int vd_tc_debug_params(int layer, const vd_tc_plan* plan, int B, int64_t* out, int cap) {
     VD_REQUIRE(plan && out && cap >= 33 + 3 * kMaxCopies + 3 * kMaxSteps + 18, "tc_debug_params: buffer too small");
-    VD_REQUIRE(layer >= 0 && layer <= 8 && geo_supported(plan->T, plan->H), "tc_debug_params: bad layer / geometry");
+    VD_REQUIRE(layer >= 0 && layer <= 11 && geo_supported(plan->T, plan->H), "tc_debug_params: bad layer / geometry");
     WsParams p;
     memset(&p, 0, sizeof(p));
     const Geo g = make_geo(plan->T, plan->H);
     uint32_t smem = 0;
     int rc = layer == 0 ? setup_l0(p, g, B, &smem) : layer == 1 ? setup_l1(p, g, B, &smem) : layer == 2 ? setup_l2(p, g, B, &smem)
                         : layer == 6 ? setup_l0s(p, g, B, &smem) : layer == 7 ? setup_l1s(p, g, B, &smem)
-                        : layer == 8 ? setup_l2s(p, g, B, &smem) : setup_bwd(p, g, layer - 3, B, &smem);
+                        : layer == 8 ? setup_l2s(p, g, B, &smem)
+                        : layer == 9 ? setup_l0s(p, g, B, &smem, 2) : layer == 10 ? setup_l1s(p, g, B, &smem, 2)
+                        : layer == 11 ? setup_l2s(p, g, B, &smem, 2) : setup_bwd(p, g, layer - 3, B, &smem);
     if (rc) return rc;
     int i = 0;
     out[i++] = p.n_tiles; out[i++] = p.tiles_per_item; out[i++] = p.v_count;

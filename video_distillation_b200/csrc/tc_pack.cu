@@ -149,13 +149,15 @@ __global__ void pack_w2_kernel(const float* __restrict__ w, uint16_t* __restrict
 // ---- split-fp16 forward operands (SGeo, tc_layout.h) ----
 // X0s (B, T+2, part 2, 3, 2, RI0, Wo0) chunks of 8 fp16: part 0 = fp16(v), part 1 = fp16(v - part 0).  One block per
 // (video, padded frame, part, channel, row parity) plane.  U8: uint8 frames with the dataset normalisation fused in.
+// parts = 1: the hi-only layout X0h (B, T+2, 3, 2, RI0, Wo0) of the two-product mode (operand of vd_tc_x3_conv_layer_ex, passes = 2).
 template <bool U8>
 __global__ void __launch_bounds__(256) pack_video_x3_kernel(const void* __restrict__ video, const int64_t* __restrict__ index,
-                                                            uint4* __restrict__ x0, int T, int HW, int RI0, int Wo0, NormU8 nm) {
+                                                            uint4* __restrict__ x0, int T, int HW, int RI0, int Wo0, NormU8 nm, int parts) {
     int q = blockIdx.x;
     const int par = q & 1; q >>= 1;
     const int c = q % 3; q /= 3;
-    const int part = q & 1; q >>= 1;
+    int part = 0;
+    if (parts == 2) { part = q & 1; q >>= 1; }
     const int tp = q % (T + 2);
     const int64_t b = q / (T + 2);
     const int t = tp - 1;
@@ -332,18 +334,29 @@ extern "C" int vd_tc_pack_weights_part(const float* w_l0, const float* w_l1, con
 
 // ---- split-fp16 forward operands (vd_tc_x3_*) ----
 static int pack_video_x3_impl(const void* video, bool u8, const int64_t* index, void* x0s, const vd_tc_plan* plan, int B,
-                              const float* mean3, const float* std3, void* stream) {
+                              const float* mean3, const float* std3, void* stream, int parts = 2) {
     VD_REQUIRE(video && x0s && plan && B >= 0, "tc_x3_pack_video: bad argument");
     VD_REQUIRE(geo_supported(plan->T, plan->H), "tc_x3_pack_video: unsupported geometry");
     if (B == 0) return 0;
     const Geo g = make_geo(plan->T, plan->H);
     NormU8 nm;
     for (int c = 0; c < 3; ++c) { nm.mean[c] = mean3 ? mean3[c] : 0.f; nm.stdv[c] = std3 ? std3[c] : 1.f; }
-    const int64_t blocks = (int64_t)B * (g.T + 2) * 12;                      // planes [b][t_pad][part][c][par]
+    const int64_t blocks = (int64_t)B * (g.T + 2) * 6 * parts;               // planes [b][t_pad][part][c][par]
     VD_REQUIRE(blocks < (1ll << 31), "tc_x3_pack_video: grid too large");
-    if (u8) pack_video_x3_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(video, index, (uint4*)x0s, g.T, g.HW, g.RI0, g.Wo0, nm);
-    else pack_video_x3_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(video, index, (uint4*)x0s, g.T, g.HW, g.RI0, g.Wo0, nm);
+    if (u8) pack_video_x3_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(video, index, (uint4*)x0s, g.T, g.HW, g.RI0, g.Wo0, nm, parts);
+    else pack_video_x3_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(video, index, (uint4*)x0s, g.T, g.HW, g.RI0, g.Wo0, nm, parts);
     return check_launch("tc_x3_pack_video");
+}
+
+// hi-only operand X0h of the two-product mode (plan->x0_bytes_per_video bytes per video: the X0 layout with fp16 values)
+extern "C" int vd_tc_x3_pack_video_hi(const float* video, const int64_t* index, void* x0h, const vd_tc_plan* plan, int B, void* stream) {
+    return pack_video_x3_impl(video, false, index, x0h, plan, B, nullptr, nullptr, stream, 1);
+}
+
+extern "C" int vd_tc_x3_pack_video_hi_u8(const uint8_t* video, const int64_t* index, void* x0h, const vd_tc_plan* plan, int B,
+                                         const float* mean3, const float* std3, void* stream) {
+    VD_REQUIRE(mean3 && std3 && std3[0] != 0.f && std3[1] != 0.f && std3[2] != 0.f, "tc_x3_pack_video_hi_u8: mean / non-zero std required");
+    return pack_video_x3_impl(video, true, index, x0h, plan, B, mean3, std3, stream, 1);
 }
 
 extern "C" int vd_tc_x3_pack_video(const float* video, const int64_t* index, void* x0s, const vd_tc_plan* plan, int B, void* stream) {

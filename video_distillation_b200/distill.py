@@ -320,14 +320,16 @@ class _RealEmbedder:
         self.device = device
         self.max_batch = max_batch
         self.tc = None
-        if precision in ('bf16', 'f16x3'):
+        if precision in ('bf16', 'f16x3', 'f16x3r2'):
             # 'f16x3': the fused pipeline on fp16 hi/lo operand pairs (fp32-equivalent embeddings and routing, the parity
-            # mode of the fast path); 'bf16': single-pass bf16 operands and activations (throughput mode)
+            # mode of the fast path); 'f16x3r2': the same, with the frozen real videos in the two-product mode (exact weights,
+            # activations rounded once to fp16 — tc.TcConvNet3D); 'bf16': single-pass bf16 operands and activations
             if not tc_supported(frames, im_size[0], im_size[1]):
                 raise RuntimeError(f'tensor-core path does not support videos {frames}x{im_size}')
-            self.tc = TcConvNet3D(frames, im_size[0], im_size[1], device, max_batch=max_batch, split=(precision == 'f16x3'))
+            self.tc = TcConvNet3D(frames, im_size[0], im_size[1], device, max_batch=max_batch, split=precision.startswith('f16x3'),
+                                  real_products=2 if precision == 'f16x3r2' else 3)
         elif precision not in ('fp32', 'bf16x3'):
-            raise ValueError("precision must be 'f16x3', 'bf16', 'bf16x3' or 'fp32'")
+            raise ValueError("precision must be 'f16x3r2', 'f16x3', 'bf16', 'bf16x3' or 'fp32'")
 
     def load(self, net):
         self.net = net
@@ -340,7 +342,7 @@ class _RealEmbedder:
         if self.tc is not None:
             if x0 is not None:
                 return self.tc.embed_resident(x0, index)
-            return self.tc.embed(videos, index=index)
+            return self.tc.embed(videos, index=index, frozen=True)
         # 'fp32': exact CUDA-core kernels.  'bf16x3': the same module on the tensor-core conv trio with split-bf16
         # fprop and fp32 activations (embeddings ~1e-5 of fp32) — the caller holds ops.set_conv_backend('tc').
         out = []
@@ -490,7 +492,7 @@ class DMS2DTrainer:
         tc = self.embedder.tc
         fused_syn = tc is not None and self.syn_on_tensor_cores is True
         joint = (fused_syn and real_batch is None and self.ds.x0 is not None
-                 and getattr(self.ds, 'x0_extra', 0) >= image_syn.shape[0])
+                 and (tc.real_products == 2 or getattr(self.ds, 'x0_extra', 0) >= image_syn.shape[0]))
         video_sharded = self.world > 1 and getattr(self.ds, 'shard', 'class') == 'video'
         offsets = real_batch_offsets
         if real_batch is not None:

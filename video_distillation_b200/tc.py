@@ -33,20 +33,28 @@ class TcConvNet3D:
     split=False: bf16 operands and bf16 activations between the layers (single pass, throughput mode).
     split=True : "f16x3" — every operand is an fp16 hi/lo pair and every product xh*wh + xl*wh + xh*wl in the same fp32
                  TMEM accumulator (csrc/tc_layout.h: SGeo): embeddings within ~3e-6 of an fp32 evaluation, ReLU / MaxPool
-                 routing decided on fp32-equivalent sums; the backward runs the dgrads as split-bf16 (three passes each)."""
+                 routing decided on fp32-equivalent sums; the backward runs the dgrads as split-bf16 (three passes each).
+    real_products=2 (split only): the FROZEN real videos (``embed_resident``, the real part of ``embed_joint``, ``embed`` without
+                 codes when ``frozen=True``) run in the two-product mode xh*wh + xh*wl — weights exact, each activation
+                 rounded once to fp16 (independent from video to video: it averages out of the class means), 2/3 of the MMAs
+                 and half of the operand bytes.  Differentiable videos always take the full three products."""
 
-    def __init__(self, T, H, W, device, max_batch=128, split=False):
+    def __init__(self, T, H, W, device, max_batch=128, split=False, real_products=3):
         self.plan = make_plan(T, H, W)
         self.T, self.H, self.W = T, H, W
         self.device = torch.device(device)
         self.max_batch = int(max_batch)
         self.split = bool(split)
+        if real_products not in (2, 3):
+            raise ValueError('real_products must be 2 or 3')
+        self.real_products = int(real_products) if self.split else 3
         p = self.plan
         u8 = dict(dtype=torch.uint8, device=self.device)
         if self.split:
             sz = (ctypes.c_int64 * 6)()
             _lib.check(_lib.lib().vd_tc_x3_sizes(ctypes.byref(p), sz), 'vd_tc_x3_sizes')
             self.x0_per, self.a1_per, self.a2_per = int(sz[0]), int(sz[1]), int(sz[2])
+            self.x0h_per = int(p.x0_bytes_per_video)         # hi-only operand of the two-product mode (X0 layout, fp16 values)
             wb = (int(sz[3]), int(sz[4]), int(sz[5]))
         else:
             self.x0_per, self.a1_per, self.a2_per = int(p.x0_bytes_per_video), int(p.a1_bytes_per_video), int(p.a2_bytes_per_video)
@@ -78,7 +86,7 @@ class TcConvNet3D:
         self._a1 = None
         self._a2 = None
         self.embed_dim = int(p.embed_dim)
-        self.timing = None          # set to [] to collect (layer, B, start_event, end_event) per launch
+        self.timing = None          # set to [] to collect (layer, B, start_event, end_event, products per MAC) per launch
 
     # ---------------------------------------------------------------- operands
     def load_weights(self, w0, b0, w1, b1, w2, b2):
@@ -209,11 +217,14 @@ class TcConvNet3D:
         """Dataset normalisation applied by the uint8 packer: v = (u/255 - mean[c]) / std[c] (utils.py:214-230)."""
         self._norm = ((ctypes.c_float * 3)(*[float(m) for m in mean]), (ctypes.c_float * 3)(*[float(s) for s in std]))
 
-    def pack_video(self, video, index=None, out=None):
-        """fp32 (or uint8 frames, see set_normalization) (Bsrc,T,3,H,W) -> X0 for B = len(index) (or Bsrc) items."""
+    def pack_video(self, video, index=None, out=None, hi_only=False):
+        """fp32 (or uint8 frames, see set_normalization) (Bsrc,T,3,H,W) -> X0 for B = len(index) (or Bsrc) items.
+        hi_only (split mode): the hi-only operand X0h of the two-product mode."""
         assert video.dtype in (torch.float32, torch.uint8) and video.dim() == 5 and tuple(video.shape[1:]) == (self.T, 3, self.H, self.W)
+        assert not hi_only or self.split
         B = int(index.numel()) if index is not None else int(video.shape[0])
-        nbytes = B * self.x0_per
+        nbytes = B * (self.x0h_per if hi_only else self.x0_per)
+        lib = _lib.lib()
         if out is None:
             if self._x0 is None or self._x0.numel() < nbytes:
                 self._x0 = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
@@ -221,31 +232,32 @@ class TcConvNet3D:
         if video.dtype == torch.uint8:
             if getattr(self, '_norm', None) is None:
                 raise RuntimeError('uint8 videos need TcConvNet3D.set_normalization(mean, std) first')
-            fn = _lib.lib().vd_tc_x3_pack_video_u8 if self.split else _lib.lib().vd_tc_pack_video_u8
+            fn = (lib.vd_tc_x3_pack_video_hi_u8 if hi_only else lib.vd_tc_x3_pack_video_u8) if self.split else lib.vd_tc_pack_video_u8
             _lib.check(fn(_lib.ptr(video), _lib.ptr(index), _lib.ptr(out), ctypes.byref(self.plan), B,
                           self._norm[0], self._norm[1], _lib.stream()), 'vd_tc_pack_video_u8')
             return out
-        fn = _lib.lib().vd_tc_x3_pack_video if self.split else _lib.lib().vd_tc_pack_video
+        fn = (lib.vd_tc_x3_pack_video_hi if hi_only else lib.vd_tc_x3_pack_video) if self.split else lib.vd_tc_pack_video
         _lib.check(fn(_lib.ptr(video), _lib.ptr(index), _lib.ptr(out), ctypes.byref(self.plan), B, _lib.stream()), 'vd_tc_pack_video')
         return out
 
     # ---------------------------------------------------------------- layers
-    def conv_layer(self, layer, src, wimg, bias, out, B, code=None, item_index=None, raw=False, code_first=0):
+    def conv_layer(self, layer, src, wimg, bias, out, B, code=None, item_index=None, raw=False, code_first=0, products=3):
         ev = None
         if self.timing is not None:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
-        self._conv_layer(layer, src, wimg, bias, out, B, code, item_index, raw, code_first)
+        self._conv_layer(layer, src, wimg, bias, out, B, code, item_index, raw, code_first, products)
         if ev is not None:
             ev[1].record()
-            self.timing.append((layer, int(B), ev[0], ev[1]))
+            self.timing.append((layer, int(B), ev[0], ev[1], int(products) if self.split else 1))
 
-    def _conv_layer(self, layer, src, wimg, bias, out, B, code=None, item_index=None, raw=False, code_first=0):
+    def _conv_layer(self, layer, src, wimg, bias, out, B, code=None, item_index=None, raw=False, code_first=0, products=3):
         if self.split:
             assert not raw, 'the split-fp16 path has fused epilogues only'
-            _lib.check(_lib.lib().vd_tc_x3_conv_layer(layer, _lib.ptr(src), _lib.ptr(wimg), _lib.ptr(bias), _lib.ptr(out),
-                                                      _lib.ptr(code), int(code_first), ctypes.byref(self.plan), _lib.ptr(item_index),
-                                                      int(B), _lib.stream()), f'vd_tc_x3_conv_layer({layer})')
+            assert products == 3 or code is None, 'the two-product mode is for frozen videos (no routing codes)'
+            _lib.check(_lib.lib().vd_tc_x3_conv_layer_ex(layer, _lib.ptr(src), _lib.ptr(wimg), _lib.ptr(bias), _lib.ptr(out),
+                                                         _lib.ptr(code), int(code_first), ctypes.byref(self.plan), _lib.ptr(item_index),
+                                                         int(B), int(products), _lib.stream()), f'vd_tc_x3_conv_layer_ex({layer})')
             return
         _lib.check(_lib.lib().vd_tc_conv_layer(layer, _lib.ptr(src), _lib.ptr(wimg), _lib.ptr(bias), _lib.ptr(out),
                                                _lib.ptr(code), int(code_first), ctypes.byref(self.plan), _lib.ptr(item_index),
@@ -262,7 +274,7 @@ class TcConvNet3D:
         self.conv_layer(2, a2, self.w2, self.b2, out, B, code=c2)
         return out
 
-    def _embed_chunks(self, B, out, codes, front, code_first=0):
+    def _embed_chunks(self, B, out, codes, front, code_first=0, products=3):
         """conv 0 + conv 1 per chunk of max_batch videos (``front(s, e)`` -> (x0, item_index)), every
         chunk writing its slice of one A2 buffer; then ONE conv-2 launch over all B videos.  ``codes``
         (optional) hold the routing of items code_first..B-1 only."""
@@ -280,9 +292,9 @@ class TcConvNet3D:
             if c0 is not None and e > code_first:
                 first = max(0, code_first - s)              # chunk-local index of the first item with codes
                 cc0, cc1 = c0[s + first - code_first:], c1[s + first - code_first:]
-            self.conv_layer(0, x0, self.w0, self.b0, a1, e - s, code=cc0, item_index=idx, code_first=first)
-            self.conv_layer(1, a1, self.w1, self.b1, a2[s * self.a2_per:], e - s, code=cc1, code_first=first)
-        self.conv_layer(2, a2, self.w2, self.b2, out, B, code=c2, code_first=code_first)
+            self.conv_layer(0, x0, self.w0, self.b0, a1, e - s, code=cc0, item_index=idx, code_first=first, products=products)
+            self.conv_layer(1, a1, self.w1, self.b1, a2[s * self.a2_per:], e - s, code=cc1, code_first=first, products=products)
+        self.conv_layer(2, a2, self.w2, self.b2, out, B, code=c2, code_first=code_first, products=products)
         return out
 
     def alloc_codes(self, B):
@@ -296,11 +308,12 @@ class TcConvNet3D:
         (bf16, 'kw-expanded'); afterwards ``embed_resident`` reads it in place through item_index.
         ``extra_slots`` spare video slots at the tail receive the synthetic videos of ``embed_joint``."""
         N = int(videos.shape[0])
-        x0 = torch.empty((N + extra_slots) * self.x0_per, dtype=torch.uint8, device=self.device)
-        per = self.x0_per
+        hi_only = self.real_products == 2        # frozen set in the two-product mode: hi part only, half the bytes, no spare slots
+        per = self.x0h_per if hi_only else self.x0_per
+        x0 = torch.empty((N + (0 if hi_only else extra_slots)) * per, dtype=torch.uint8, device=self.device)
         for s in range(0, N, chunk):
             e = min(N, s + chunk)
-            self.pack_video(videos[s:e], out=x0[s * per:e * per])
+            self.pack_video(videos[s:e], out=x0[s * per:e * per], hi_only=hi_only)
         return x0
 
     def embed_resident(self, x0_all, index):
@@ -308,13 +321,19 @@ class TcConvNet3D:
         B = int(index.numel())
         out = torch.empty(B, self.embed_dim, dtype=torch.float32, device=self.device)
         index = index.contiguous()
-        return self._embed_chunks(B, out, None, lambda s, e: (x0_all, index[s:e]))
+        return self._embed_chunks(B, out, None, lambda s, e: (x0_all, index[s:e]), products=self.real_products)
 
     def embed_joint(self, x0_all, index_real, video_syn, tail_slot):
         """Frozen real videos (resident, addressed by ``index_real``) and differentiable synthetic videos in ONE
         pass of the three conv kernels: the synthetic videos are packed into the spare slots ``tail_slot...`` of
         the resident operand and only they record routing codes.  Returns (emb_real, emb_syn, codes)."""
         n_real, n_syn = int(index_real.numel()), int(video_syn.shape[0])
+        if self.real_products == 2:
+            # two launches per layer: the frozen real videos in the two-product mode on the hi-only resident operand, the
+            # differentiable synthetic videos (1.5 % of the work at ipc = 1) with all three products and routing codes
+            emb_real = self.embed_resident(x0_all, index_real.reshape(-1))
+            emb_syn, codes = self.embed(video_syn.contiguous(), want_codes=True)
+            return emb_real, emb_syn, codes
         per = self.x0_per
         assert x0_all.numel() >= (tail_slot + n_syn) * per, 'resident operand has no spare slots for the synthetic videos'
         self.pack_video(video_syn.contiguous(), out=x0_all[tail_slot * per:(tail_slot + n_syn) * per])
@@ -329,17 +348,19 @@ class TcConvNet3D:
         emb_syn, emb_real = _TcEmbedJoint.apply(video_syn, self, x0_all, index_real, tail_slot)
         return emb_real, emb_syn
 
-    def embed(self, video, index=None, want_codes=False):
-        """ConvNet3D.embed on fp32 videos (B,T,3,H,W) -> (B, embed_dim) fp32, in chunks of max_batch."""
+    def embed(self, video, index=None, want_codes=False, frozen=False):
+        """ConvNet3D.embed on fp32 videos (B,T,3,H,W) -> (B, embed_dim) fp32, in chunks of max_batch.
+        frozen=True (no codes): these are real videos whose embeddings are only averaged — two-product mode if enabled."""
         B = int(index.numel()) if index is not None else int(video.shape[0])
         out = torch.empty(B, self.embed_dim, dtype=torch.float32, device=self.device)
         codes = self.alloc_codes(B) if want_codes else None
+        hi_only = frozen and not want_codes and self.real_products == 2
 
         def front(s, e):
             if index is not None:
-                return self.pack_video(video, index[s:e]), None
-            return self.pack_video(video[s:e]), None
-        self._embed_chunks(B, out, codes, front)
+                return self.pack_video(video, index[s:e], hi_only=hi_only), None
+            return self.pack_video(video[s:e], hi_only=hi_only), None
+        self._embed_chunks(B, out, codes, front, products=2 if hi_only else 3)
         return (out, codes) if want_codes else out
 
 
