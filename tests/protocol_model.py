@@ -194,12 +194,17 @@ def simulate(L, cta=0, mma_latency=3):
     def issuer(role):
         for k, g in enumerate(groups):
             if (k & 1) == role:
-                for w in g['w_acc'] + [g['w_pix'], g['w_w']]:
+                # (key, index, parity) waits are taken before the group; (key, index, parity, segment) waits — split-fp16 conv 0 —
+                # just before the MMAs of that segment, with the earlier segments of the group already in the pipe
+                for w in [w for w in g['w_acc'] if len(w) == 3 or w[3] == 0] + [g['w_pix'], g['w_w']]:
                     if w is not None:
                         yield from wait(w)
                 if k > 0:
                     yield from wait(('baton', role ^ 1, ((k - 1) >> 1) & 1))
-                for acc, first in g['segs']:
+                for si, (acc, first) in enumerate(g['segs']):
+                    for w in g['w_acc']:
+                        if len(w) == 4 and w[3] == si and si > 0:
+                            yield from wait(w)
                     if first:
                         assert acc_state[acc] == 'free', 'accumulator re-initialised before the epilogue drained it'
                         acc_state[acc] = 'accumulating'

@@ -32,7 +32,7 @@ def test_reference_command_lines_parse():
     # sh/s2d/s2d_DM_ms.sh and sh/baseline/DM.sh style invocations
     a = cli.s2d_parser().parse_args('--method DM --dataset miniUCF101 --vpc 1 --spc 2 --dpc 2 --batch_real 64 --no_train_static '
                                     '--lr_dynamic 1e4 --lr_hal 1e-2 --eval_it 500 --preload --frames 16'.split())
-    assert a.method == 'DM' and a.no_train_static and a.lr_dynamic == 1e4 and a.precision == 'f16x3'
+    assert a.method == 'DM' and a.no_train_static and a.lr_dynamic == 1e4 and a.precision == 'f16x3r2'
     b = cli.baseline_parser().parse_args('--method DM --ipc 1 --batch_real 64 --init real --model ConvNet3D --frames 16'.split())
     assert b.ipc == 1 and b.init == 'real' and b.lr_img == 1
 

@@ -35,9 +35,11 @@ from .utils import (Conv3DNet, MultiStaticSharedDataset, epoch, evaluate_synset,
 
 # ------------------------------------------------------------------------------------------ parsers
 def _extra(parser):
-    parser.add_argument('--precision', type=str, default='f16x3', choices=['f16x3', 'bf16', 'fp32', 'bf16x3'],
-                        help='[B200] f16x3: fused tensor-core pipeline on fp16 hi/lo operand pairs (parity mode, default); bf16: single-pass '
-                             'throughput mode; fp32: exact CUDA-core kernels; bf16x3: unfused split-bf16 conv trio')
+    parser.add_argument('--precision', type=str, default='f16x3r2', choices=['f16x3r2', 'f16x3', 'bf16', 'fp32', 'bf16x3'],
+                        help='[B200] f16x3r2 (default): fused tensor-core pipeline on fp16 hi/lo operand pairs, the parity mode — three products '
+                             'per MAC for the differentiable synthetic videos, two (exact weights, fp16 activations) for the frozen real videos '
+                             'of the DM loss; f16x3: three products everywhere; bf16: single-pass throughput mode; fp32: exact CUDA-core '
+                             'kernels; bf16x3: unfused split-bf16 conv trio')
     parser.add_argument('--run_name', type=str, default=None, help='[B200] directory name under save_path/<project> (wandb.run.name in the reference)')
     return parser
 
@@ -249,7 +251,7 @@ def _tensors_of(dst):
 
 
 def _eval_precision(args):
-    return 'bf16' if args.precision in ('bf16', 'bf16x3', 'f16x3') else 'fp32'
+    return 'bf16' if args.precision in ('bf16', 'bf16x3', 'f16x3', 'f16x3r2') else 'fp32'
 
 
 class ExpertBuffers:
@@ -354,7 +356,7 @@ def main_s2d(args):
         videos, labels = _tensors_of(dst_train)
         ds = DeviceDataset(videos, labels, num_classes, dev, rank, world, shard='video' if world > 1 else 'class')
         prec = args.precision
-        tr = DMS2DTrainer(ds, batch_real=args.batch_real, precision=prec, max_batch=640 if prec in ('bf16', 'f16x3') else 128, **common)
+        tr = DMS2DTrainer(ds, batch_real=args.batch_real, precision=prec, max_batch=640 if prec in ('bf16', 'f16x3', 'f16x3r2') else 128, **common)
         if tr.embedder.tc is not None:
             ds.prepack(tr.embedder.tc, extra_slots=len(tr.owned) * tr.vpc)
     else:
@@ -461,7 +463,7 @@ def main_baseline(args):
         prec = args.precision
         tr = DMBaselineTrainer(ds, num_classes=num_classes, channel=channel, im_size=im_size, frames=args.frames, ipc=args.ipc,
                                batch_real=args.batch_real, lr_img=args.lr_img, precision=prec, image_syn=image_syn,
-                               max_batch=640 if prec in ('bf16', 'f16x3') else 128, device=dev)
+                               max_batch=640 if prec in ('bf16', 'f16x3', 'f16x3r2') else 128, device=dev)
     else:
         raise NotImplementedError('Method {} not implemented (DC is outside the B200 hot path)'.format(args.method))
     label_syn = torch.tensor(np.stack([np.ones(args.ipc) * i for i in range(0, num_classes)]), dtype=torch.long,
@@ -570,8 +572,9 @@ def main_coreset(args):
         print('Loading pretrained model')
         net.load_state_dict(torch.load(args.pretrained_path))
     net.eval()
-    if args.precision in ('bf16', 'f16x3') and tc_supported(args.frames, im_size[0], im_size[1]):
-        tc = TcConvNet3D(args.frames, im_size[0], im_size[1], dev, max_batch=256, split=(args.precision == 'f16x3'))
+    if args.precision in ('bf16', 'f16x3', 'f16x3r2') and tc_supported(args.frames, im_size[0], im_size[1]):
+        # coreset selection compares individual embeddings: three products per MAC ('f16x3r2' only shortens class MEANS)
+        tc = TcConvNet3D(args.frames, im_size[0], im_size[1], dev, max_batch=256, split=args.precision.startswith('f16x3'))
         f = net.features
         tc.load_weights(f[0].weight, f[0].bias, f[3].weight, f[3].bias, f[6].weight, f[6].bias)
         embed = tc.embed

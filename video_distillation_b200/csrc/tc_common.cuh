@@ -62,6 +62,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
 }
 
+// the same with a chosen back-off (ns) between polls
+template <int kSleepNs>
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(kSleepNs);
+        if (clock64() - t0 > 4000000000LL) {
+            printf("vd_b200: mbarrier wait timeout (block %d thread %d bar 0x%x parity %u)\n",
+                   (int)blockIdx.x, (int)threadIdx.x, bar, parity);
+            __trap();
+        }
+    }
+}
+
 // ------------------------------------------------------------------ bulk async copy (global -> smem)
 __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile(

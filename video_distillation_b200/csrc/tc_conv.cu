@@ -23,6 +23,7 @@ namespace tc {
 constexpr int kMaxSteps = 80;
 constexpr int kMaxCopies = 8;
 constexpr int kThreads = 256;
+constexpr int kThreadsL0S = 384;         // split-fp16 conv 0: a second group of four epilogue warps (see ws_gemm_kernel)
 
 enum EpiMode { EPI_RAW = 0, EPI_L0 = 1, EPI_L1 = 2, EPI_L2 = 3, EPI_PLAIN = 4, EPI_DG1 = 5, EPI_DG0 = 6, EPI_L0S = 7, EPI_L1S = 8 };
 
@@ -90,6 +91,7 @@ struct WsParams {
     uint32_t smem_w_off, smem_pix_off;  // from the 1024-aligned dynamic smem base
     uint32_t smem_epi_off;              // != 0: 4 x 32 x 33 float transpose scratch for coalesced raw stores
     uint32_t smem_stash_off;            // != 0: conv-1 epilogue stash [H2*H2][kStashPitch] bf16 (quick accumulator drain)
+    uint32_t stash_group_bytes;         // EPI_L0S: stash bytes of ONE epilogue group (two groups of four warps drain alternate frames)
     int32_t swap_ab;                    // the staged pixels are the M operand and the weight tiles the N operand (conv-0 dgrad)
     int32_t stream_pairs;               // conv 0 fused forward, != 0: "input-frame streaming" order (T/2 frame pairs per column):
                                         //   a tile is a COLUMN (video, row band); its T input frames are staged once each, in
@@ -208,10 +210,10 @@ __device__ __forceinline__ void epi_raw(const WsParams& p, int64_t slot, uint32_
 
 // conv 0: lanes 0..63 = frame 2*tp, lanes 64..127 = frame 2*tp+1, columns q = r*Wo0 + wo.
 // bias + ReLU + MaxPool(1,2,2) -> A1 chunks (bf16) [+ code (B,64,T,H1,H1)]
-__device__ __forceinline__ void epi_l0(const WsParams& p, int item, int tp, int rb, uint32_t taddr, int m) {
+__device__ __forceinline__ void epi_l0(const WsParams& p, int item, int tp, int rb, uint32_t taddr, int m, float bias_reg) {
     const Geo& g = p.epi.g;
     const int f = 2 * tp + (m >> 6), co = m & 63;
-    const float bias = __ldg(p.epi.bias + co);
+    const float bias = bias_reg;              // loaded once per kernel (ws_gemm_kernel): a global load per accumulator costs ~600 exposed cycles
     const int slice = co >> 4, k = (co >> 3) & 1, e = co & 7;
     uint8_t* vbase = p.epi.out + (int64_t)item * g.video1 + (int64_t)slice * g.slice1 + (int64_t)(f + 1) * g.frame1;
     uint8_t* cbase = (p.epi.code && item >= p.epi.code_first)
@@ -249,10 +251,10 @@ __device__ __forceinline__ void epi_l0(const WsParams& p, int item, int tp, int 
 //   store: every lane takes (chunk of 8 channels, position) items of its warp's 32 channels -> one 16-byte store each.
 constexpr int kStash0Pitch = 72;          // bf16 elements per position row (64 + 8: conflict-free 16-byte reads)
 
-__device__ __forceinline__ void epi_l0_drain(const WsParams& p, int item, int tp, int rb, uint32_t taddr, int m, uint16_t* stash) {
+__device__ __forceinline__ void epi_l0_drain(const WsParams& p, int item, int tp, int rb, uint32_t taddr, int m, uint16_t* stash, float bias_reg) {
     const Geo& g = p.epi.g;
     const int half = m >> 6, f = 2 * tp + half, co = m & 63;
-    const float bias = __ldg(p.epi.bias + co);
+    const float bias = bias_reg;              // loaded once per kernel (ws_gemm_kernel): a global load per accumulator costs ~600 exposed cycles
     const int Wp = g.Wo0 / 2, npos = (g.R0 / 2) * Wp;
     uint16_t* srow = stash + (half * npos) * kStash0Pitch + co;
     if (!(p.epi.code && item >= p.epi.code_first)) {
@@ -331,18 +333,63 @@ __device__ __forceinline__ void epi_l0_store(const WsParams& p, int item, int tp
 // stash [part][pooled position][channel] (+ routing codes for the synthetic videos).
 constexpr int kStash0sPitch = 72;         // fp16 elements per position row (64 + 8: conflict-free 16-byte reads)
 
-__device__ __forceinline__ void epi_l0s_drain(const WsParams& p, int item, int f, int rb, uint32_t taddr, int m, uint16_t* stash) {
+// [c0, c1): the accumulator columns (multiples of 8 inside a row) this epilogue group drains
+__device__ __forceinline__ void epi_l0s_drain(const WsParams& p, int item, int f, int rb, uint32_t taddr, int m, uint16_t* stash,
+                                              int c0, int c1, float bias_reg) {
     const Geo& g = p.epi.g;
     const int l = m & 31, hsel = l >> 4, co = (m >> 5) * 16 + (l & 15);
-    const float bias = __ldg(p.epi.bias + co);
+    const float bias = bias_reg;              // loaded once per kernel (ws_gemm_kernel): a global load per accumulator costs ~600 exposed cycles
     const int R = p.epi.r0s, Wp = g.Wo0 / 2, npos = (R / 2) * Wp;
     uint16_t* s_hi = stash + co;
     uint16_t* s_lo = stash + npos * kStash0sPitch + co;
     uint8_t* cbase = (p.epi.code && item >= p.epi.code_first)
                          ? p.epi.code + (((int64_t)(item - p.epi.code_first) * 64 + co) * g.T + f) * g.H1 * g.H1 : nullptr;
+    if (cbase == nullptr) {
+        // frozen real videos (no routing codes): max / add / max instead of the argmax scan.  The epilogue warps run one
+        // instruction stream each, so every dependent-instruction latency is exposed: no divisions in here.
+        const bool hi_only = p.epi.hi_only != 0;
+        const int Wo = g.Wo0;
+        // All TMEM loads of a row pair are issued before the single wait, and the (up to) four blocks of 8 columns are pooled
+        // in ONE basic block so that their dependent chains (SEL -> SHFL -> FADD -> FMNMX.. -> F2F -> STS, ~190 cycles each)
+        // interleave: a group with fewer than four blocks re-reads its last block and only the stores are predicated.
+        const int nblk = (c1 - c0) >> 3;                            // 1..4 blocks of 8 columns per group (Wo0 <= 64)
+        for (int pr = 0; pr < R / 2; ++pr) {
+            const uint32_t t0 = taddr + (2 * pr) * Wo + c0, t1 = t0 + Wo;
+            const int posr = pr * Wp + 2 * hsel + (c0 >> 1);
+            float r0[32], r1[32];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int bb = min(b, nblk - 1);
+                tmem_ld8(t0 + 8 * bb, r0 + 8 * b); tmem_ld8(t1 + 8 * bb, r1 + 8 * b);
+            }
+            tmem_ld_wait();
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                float a0[4], a1[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float s0 = hsel ? r0[8 * b + i] : r0[8 * b + 4 + i], s1 = hsel ? r1[8 * b + i] : r1[8 * b + 4 + i];
+                    const float k0 = hsel ? r0[8 * b + 4 + i] : r0[8 * b + i], k1 = hsel ? r1[8 * b + 4 + i] : r1[8 * b + i];
+                    a0[i] = k0 + __shfl_xor_sync(0xffffffffu, s0, 16);
+                    a1[i] = k1 + __shfl_xor_sync(0xffffffffu, s1, 16);
+                }
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj) {
+                    const float v = fmaxf(fmaxf(fmaxf(a0[2 * jj], a0[2 * jj + 1]), fmaxf(a1[2 * jj], a1[2 * jj + 1])) + bias, 0.f);
+                    uint16_t hi, lo;
+                    split_h(v, hi, lo);
+                    if (b < nblk) {
+                        s_hi[(posr + 4 * b + jj) * kStash0sPitch] = hi;
+                        if (!hi_only) s_lo[(posr + 4 * b + jj) * kStash0sPitch] = lo;
+                    }
+                }
+            }
+        }
+        return;
+    }
     for (int pr = 0; pr < R / 2; ++pr) {
         const int hp = rb * (R / 2) + pr;
-        for (int wb = 0; wb < g.Wo0; wb += 8) {
+        for (int wb = c0; wb < c1; wb += 8) {
             float r0[8], r1[8];
             tmem_ld8(taddr + (2 * pr) * g.Wo0 + wb, r0);
             tmem_ld8(taddr + (2 * pr + 1) * g.Wo0 + wb, r1);
@@ -376,22 +423,40 @@ __device__ __forceinline__ void epi_l0s_drain(const WsParams& p, int item, int f
 }
 
 // warp q owns channels 16q .. 16q+15 = chunks 2q, 2q+1 of A1s: (position, part, chunk) items -> one 16-byte store each
-__device__ __forceinline__ void epi_l0s_store(const WsParams& p, int item, int f, int rb, int q, int lane, const uint16_t* stash) {
+// The store of a drained tile: every lane owns up to kL0sItems (position, part, chunk) items of its group's columns -> one
+// 16-byte store each.  The stash offset and the offset inside the frame depend only on (lane, tile): they are computed once
+// per tile (epi_l0s_store_plan) so that the per-frame path is LDS.128 -> STG.128.
+constexpr int kL0sItems = 4;
+struct L0sStorePlan { int n; int soff[kL0sItems]; int doff[kL0sItems]; };
+
+__device__ __forceinline__ void epi_l0s_store_plan(const WsParams& p, int rb, int q, int lane, int c0, int c1, L0sStorePlan& sp) {
     const Geo& g = p.epi.g;
     const int R = p.epi.r0s, Wp = g.Wo0 / 2, npos = (R / 2) * Wp;
-    uint8_t* fbase = p.epi.out + (int64_t)item * (8 * g.slice1) + (int64_t)(f + 1) * g.frame1;
-    const int n_it = (p.epi.hi_only ? 2 : 4) * npos;
-    for (int it = lane; it < n_it; it += 32) {
-        const int sel = it / npos, pos = it - sel * npos;
-        const int part = sel >> 1, kk = sel & 1;
-        const int pr = pos / Wp, wp = pos - pr * Wp;
-        const int hp = rb * (R / 2) + pr;
-        const uint4 v = *reinterpret_cast<const uint4*>(stash + (part * npos + pos) * kStash0sPitch + q * 16 + kk * 8);
-        uint8_t* dst = fbase + (int64_t)(2 * q + kk) * g.slice1 +
-                       (int64_t)((part * 2 + coord_par(hp)) * 2 + coord_par(wp)) * g.plane1 +
-                       ((int64_t)coord_pos(hp) * g.P1 + coord_pos(wp)) * 16;
-        *reinterpret_cast<uint4*>(dst) = v;
+    const int w0 = c0 / 2, nw = (c1 - c0) / 2, npg = (R / 2) * nw;     // this group's pooled columns [w0, w0 + nw) of every row
+    const int n_it = (p.epi.hi_only ? 2 : 4) * npg;
+    sp.n = 0;
+#pragma unroll
+    for (int k = 0; k < kL0sItems; ++k) {
+        const int it = lane + 32 * k;
+        sp.soff[k] = 0; sp.doff[k] = 0;
+        if (it < n_it) {
+            // sel = it / npg (< 4) and pr = posl / nw (< R / 2 <= 2) by comparisons
+            const int sel = (it >= npg) + (it >= 2 * npg) + (it >= 3 * npg), posl = it - sel * npg;
+            const int part = sel >> 1, kk = sel & 1;
+            const int pr = posl >= nw ? 1 : 0, wp = w0 + posl - pr * nw;
+            const int hp = rb * (R / 2) + pr;
+            sp.soff[k] = (part * npos + pr * Wp + wp) * kStash0sPitch + q * 16 + kk * 8;
+            sp.doff[k] = (int)((int64_t)(2 * q + kk) * g.slice1 + (int64_t)((part * 2 + coord_par(hp)) * 2 + coord_par(wp)) * g.plane1 +
+                               ((int64_t)coord_pos(hp) * g.P1 + coord_pos(wp)) * 16);
+            sp.n = k + 1;
+        }
     }
+}
+
+__device__ __forceinline__ void epi_l0s_store(uint8_t* fbase, const uint16_t* stash, const L0sStorePlan& sp) {
+#pragma unroll
+    for (int k = 0; k < kL0sItems; ++k)
+        if (k < sp.n) *reinterpret_cast<uint4*>(fbase + sp.doff[k]) = *reinterpret_cast<const uint4*>(stash + sp.soff[k]);
 }
 
 // conv 1: accumulator a = frame 2*tp + a, lane = cout, columns q = ho*P1 + wo.
@@ -402,11 +467,11 @@ __device__ __forceinline__ void epi_l0s_store(const WsParams& p, int item, int f
 //          writes the chunk to all tap copies of A2 — 16-byte stores, overlapped with the next tile's MMAs.
 constexpr int kStashPitch = 136;          // bf16 elements per position row (128 + 8: conflict-free 16-byte reads)
 
-__device__ __forceinline__ void epi_l1_drain(const WsParams& p, int tile, uint32_t taddr, int m, uint16_t* stash) {
+__device__ __forceinline__ void epi_l1_drain(const WsParams& p, int tile, uint32_t taddr, int m, uint16_t* stash, float bias_reg) {
     const Geo& g = p.epi.g;
     const int item = tile / p.tiles_per_item, tq = tile % p.tiles_per_item;
     const int npair = p.n_acc >> 1;                     // accumulator pairs of the tile = pooled frames (2, or 4 accumulators at 64x64)
-    const float bias = __ldg(p.epi.bias + m);
+    const float bias = bias_reg;              // loaded once per kernel (ws_gemm_kernel): a global load per accumulator costs ~600 exposed cycles
     for (int pp = 0; pp < npair; ++pp) {
         const int tp = tq * npair + pp;                 // pooled frame index
         const uint32_t ta = taddr + (uint32_t)(2 * pp) * p.acc_cols;
@@ -475,12 +540,12 @@ __device__ __forceinline__ void epi_l1_store(const WsParams& p, int tile, int q,
 // conv 1, split-fp16 operands: same tile as epi_l1_*; the pooled fp32 value is split into fp16 hi / lo (stash
 // [part][pooled frame][position][channel]) and both parts go to every tap copy of A2s
 // ([khw 49][quarter 4][part 2][k 4][t_pad][ho][wo] x 16 B).
-__device__ __forceinline__ void epi_l1s_drain(const WsParams& p, int tile, uint32_t taddr, int m, uint16_t* stash) {
+__device__ __forceinline__ void epi_l1s_drain(const WsParams& p, int tile, uint32_t taddr, int m, uint16_t* stash, float bias_reg) {
     const Geo& g = p.epi.g;
     const int item = tile / p.tiles_per_item, tq = tile % p.tiles_per_item;
     const int npair = p.n_acc >> 1;
     const int npos = g.H2 * g.H2;
-    const float bias = __ldg(p.epi.bias + m);
+    const float bias = bias_reg;              // loaded once per kernel (ws_gemm_kernel): a global load per accumulator costs ~600 exposed cycles
     for (int pp = 0; pp < npair; ++pp) {
         const int tp = tq * npair + pp;
         const uint32_t ta = taddr + (uint32_t)(2 * pp) * p.acc_cols;
@@ -551,9 +616,9 @@ __device__ __forceinline__ void epi_l1s_store(const WsParams& p, int tile, int q
 // conv 2: accumulator a = video item*4 + a, lane = cout, columns q = to*HW2 + ho*Wo2 + wo.
 // bias + ReLU + MaxPool(2,2,2) -> fp32 embeddings (B, 128*T3p*H3p*H3p), NCDHW flatten order
 // (networks.py:750) [+ code (B,128,T3p,H3p,H3p)]
-__device__ __forceinline__ void epi_l2(const WsParams& p, int tile, uint32_t taddr, int m) {
+__device__ __forceinline__ void epi_l2(const WsParams& p, int tile, uint32_t taddr, int m, float bias_reg) {
     const Geo& g = p.epi.g;
-    const float bias = __ldg(p.epi.bias + m);
+    const float bias = bias_reg;              // loaded once per kernel (ws_gemm_kernel): a global load per accumulator costs ~600 exposed cycles
     const int per = g.T3p * g.H3p * g.H3p;
     for (int a = 0; a < p.n_acc; ++a) {
         const int video = tile * p.n_acc + a;
@@ -748,7 +813,7 @@ __device__ __forceinline__ void epi_dg0(const WsParams& p, int tile, uint32_t ta
 
 // ------------------------------------------------------------------------------------------
 template <int EPI, int NACC>
-__global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_constant__ WsParams p) {
+__global__ void __launch_bounds__(EPI == EPI_L0S ? kThreadsL0S : kThreads, 1) ws_gemm_kernel(const __grid_constant__ WsParams p) {
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte aligned carve-up: [barriers 256 B][weights][pixel ring]
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -764,7 +829,7 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
     if (threadIdx.x == 0) {
         for (int i = 0; i < 4; ++i) { mbar_init(BAR(pix_full, i), 1); mbar_init(BAR(pix_empty, i), 2); }     // empty: one commit per issuer
         for (int i = 0; i < 8; ++i) { mbar_init(BAR(w_full, i), 1); mbar_init(BAR(w_empty, i), 1); }
-        for (int i = 0; i < 4; ++i) { mbar_init(BAR(acc_full, i), 2); mbar_init(BAR(acc_empty, i), 4); }
+        for (int i = 0; i < 4; ++i) { mbar_init(BAR(acc_full, i), 2); mbar_init(BAR(acc_empty, i), EPI == EPI_L0S ? 8 : 4); }      // one arrival per epilogue warp
         for (int i = 0; i < 2; ++i) mbar_init(BAR(baton, i), 1);
         mbar_init(BAR(w_res, 0), 1);
         fence_mbar_init();
@@ -1024,6 +1089,9 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
                 if ((k & 1u) == (uint32_t)role) {
                     // ---- my group: operands (usually long there), then the baton of the previous group's issuer
                     long long t0 = prof ? clock64() : 0;
+                    // (split-fp16 conv 0: deferring the wait for the accumulator that the LAST segment initialises to just before that
+                    // segment was measured and is slower — a try_wait + fence in the middle of a group idles the pipe for longer
+                    // than the wait it saves)
                     if (r.w_acc) mbar_wait(r.w_acc, r.p_acc);   // (an already completed phase returns at once)
                     if (EPI == EPI_L0S) { if (r.w_acc2) mbar_wait(r.w_acc2, r.p_acc2); }
                     if (prof) { const long long t1 = clock64(); c_acc += t1 - t0; t0 = t1; }
@@ -1087,21 +1155,50 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
             }
             if (prof && role == 0) {
                 long long* o = p.prof + (int64_t)blockIdx.x * 8;
-                o[0] = clock64() - c_begin; o[1] = c_acc; o[2] = c_pix; o[3] = c_w; o[4] = c_issue; o[5] = c_baton; o[6] = 0;
+                o[0] = clock64() - c_begin; o[1] = c_acc; o[2] = c_pix; o[3] = c_w; o[4] = c_issue + c_baton;      // o[5..7]: epilogue warp 0
             }
         }
     } else if (warp >= 4) {
         // ===================== epilogue (128 threads, lane quarter = warp % 4) =====================
+        // EPI_L0S runs TWO such groups (warps 4..7 and 8..11), each draining half of the columns of EVERY accumulator: a drain is a
+        // chain of dependent TMEM loads / shuffles / conversions whose latencies one warp per scheduler cannot hide (measured:
+        // 2700 + 900 cycles per accumulator against 1850 cycles of MMAs per stage in the two-product mode), and a drained
+        // buffer is needed again one stage later (4 buffers, 3 frames in flight) — so both the throughput (two warps per
+        // scheduler) and the latency (half the columns) of a drain must drop below a stage.
         const int q = warp & 3;
         const int m = q * 32 + lane;
+        const int egroup = (warp - 4) >> 2;
+        uint8_t* stash_ptr = base_ptr + p.smem_stash_off + (EPI == EPI_L0S ? (uint32_t)egroup * p.stash_group_bytes : 0u);
+        float bias_reg = 0.f;                                            // per-lane bias of the fused epilogues
+        if (EPI == EPI_L0S) bias_reg = __ldg(p.epi.bias + (m >> 5) * 16 + (lane & 15));
+        else if (EPI == EPI_L0) bias_reg = __ldg(p.epi.bias + (m & 63));
+        else if (EPI == EPI_L1 || EPI == EPI_L1S || EPI == EPI_L2) bias_reg = __ldg(p.epi.bias + m);
+        const int l0s_split = ((p.epi.g.Wo0 / 8 + 1) / 2) * 8;           // group 0: columns [0, split), group 1: [split, Wo0)
+        const int l0s_c0 = egroup ? l0s_split : 0, l0s_c1 = egroup ? p.epi.g.Wo0 : l0s_split;
         uint32_t as = 0, aphase = 0;
+        const bool eprof = p.prof != nullptr;
+        long long e_wait = 0, e_drain = 0, e_store = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
             const int tile_pix = tile / p.ug_count, u0 = (tile % p.ug_count) * p.n_u;
             // conv 0 streaming: a tile is a column (video, row band) and yields stream_pairs accumulators, pair by pair
             const int n_u_eff = p.stream_pairs ? p.stream_pairs : min(p.n_u, p.nu_total - u0);
+            // split-fp16 conv 0: everything that depends on the tile only (two integer divisions and the store offsets cost a
+            // lone warp several hundred exposed cycles — per tile, not per frame)
+            int l0s_item = 0, l0s_rb = 0;
+            L0sStorePlan l0s_plan;
+            uint8_t* l0s_vbase = nullptr;
+            if (EPI == EPI_L0S) {
+                l0s_item = tile / p.tiles_per_item; l0s_rb = tile - l0s_item * p.tiles_per_item;
+                epi_l0s_store_plan(p, l0s_rb, q, lane, l0s_c0, l0s_c1, l0s_plan);
+                l0s_vbase = p.epi.out + (int64_t)l0s_item * (8 * p.epi.g.slice1) + p.epi.g.frame1;
+            }
             for (int u = 0; u < n_u_eff; ++u) {
-                if (p.dbg & 32) mbar_wait(BAR(acc_full, as), aphase); else mbar_wait<true>(BAR(acc_full, as), aphase);
+                long long e0 = eprof ? clock64() : 0;
+                if (p.dbg & 32) mbar_wait(BAR(acc_full, as), aphase);
+                else if (EPI == EPI_L0S && !(p.dbg & 64)) mbar_wait_sleep<32>(BAR(acc_full, as), aphase);     // a drained buffer is needed again one stage later
+                else mbar_wait<true>(BAR(acc_full, as), aphase);
                 tc_fence_after();
+                if (eprof) { const long long e1 = clock64(); e_wait += e1 - e0; e0 = e1; }
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * (p.acc_cols * (uint32_t)p.n_acc);
                 const bool work = !(p.dbg & 4);
                 if (work) {
@@ -1109,20 +1206,21 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
                     else if (EPI == EPI_L0) {
                         const int item = tile / p.tiles_per_item, sub = tile % p.tiles_per_item;
                         const int tp = p.stream_pairs ? u : sub / p.v_count, rb = p.stream_pairs ? sub : sub % p.v_count;
-                        if (p.smem_stash_off) epi_l0_drain(p, item, tp, rb, taddr, m, reinterpret_cast<uint16_t*>(base_ptr + p.smem_stash_off));
-                        else epi_l0(p, item, tp, rb, taddr, m);
+                        if (p.smem_stash_off) epi_l0_drain(p, item, tp, rb, taddr, m, reinterpret_cast<uint16_t*>(base_ptr + p.smem_stash_off), bias_reg);
+                        else epi_l0(p, item, tp, rb, taddr, m, bias_reg);
                     }
-                    else if (EPI == EPI_L0S) epi_l0s_drain(p, tile / p.tiles_per_item, u, tile % p.tiles_per_item, taddr, m, reinterpret_cast<uint16_t*>(base_ptr + p.smem_stash_off));
-                    else if (EPI == EPI_L1S) epi_l1s_drain(p, tile, taddr, m, reinterpret_cast<uint16_t*>(base_ptr + p.smem_stash_off));
-                    else if (EPI == EPI_L1) epi_l1_drain(p, tile, taddr, m, reinterpret_cast<uint16_t*>(base_ptr + p.smem_stash_off));
+                    else if (EPI == EPI_L0S) epi_l0s_drain(p, l0s_item, u, l0s_rb, taddr, m, reinterpret_cast<uint16_t*>(stash_ptr), l0s_c0, l0s_c1, bias_reg);
+                    else if (EPI == EPI_L1S) epi_l1s_drain(p, tile, taddr, m, reinterpret_cast<uint16_t*>(base_ptr + p.smem_stash_off), bias_reg);
+                    else if (EPI == EPI_L1) epi_l1_drain(p, tile, taddr, m, reinterpret_cast<uint16_t*>(base_ptr + p.smem_stash_off), bias_reg);
                     else if (EPI == EPI_PLAIN) epi_plain(p, tile, taddr, m);
                     else if (EPI == EPI_DG1) epi_dg1(p, tile, taddr, m);
                     else if (EPI == EPI_DG0) epi_dg0(p, tile, taddr, m);
-                    else epi_l2(p, tile, taddr, m);
+                    else epi_l2(p, tile, taddr, m, bias_reg);
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(BAR(acc_empty, as));
+                if (eprof) { const long long e1 = clock64(); e_drain += e1 - e0; e0 = e1; }
                 if (EPI == EPI_L1 && work) {
                     // the accumulator is free again: scatter the stashed tile while the next one is computed
                     epi_l1_store(p, tile, q, lane, reinterpret_cast<const uint16_t*>(base_ptr + p.smem_stash_off));
@@ -1133,7 +1231,7 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
                     __syncwarp();
                 }
                 if (EPI == EPI_L0S && work) {
-                    epi_l0s_store(p, tile / p.tiles_per_item, u, tile % p.tiles_per_item, q, lane, reinterpret_cast<const uint16_t*>(base_ptr + p.smem_stash_off));
+                    epi_l0s_store(l0s_vbase + (int64_t)u * p.epi.g.frame1, reinterpret_cast<const uint16_t*>(stash_ptr), l0s_plan);
                     __syncwarp();
                 }
                 if (EPI == EPI_L0 && work && p.smem_stash_off) {
@@ -1142,8 +1240,13 @@ __global__ void __launch_bounds__(kThreads, 1) ws_gemm_kernel(const __grid_const
                     epi_l0_store(p, item, tp, rb, q, lane, reinterpret_cast<const uint16_t*>(base_ptr + p.smem_stash_off));
                     __syncwarp();
                 }
+                if (eprof) e_store += clock64() - e0;
                 if (++as == p.acc_stages) { as = 0; aphase ^= 1; }
             }
+        }
+        if (eprof && warp == 4 && lane == 0) {          // epilogue warp 0: cycles waiting for acc_full / draining / storing
+            long long* o = p.prof + (int64_t)blockIdx.x * 8;
+            o[5] = e_wait; o[6] = e_drain; o[7] = e_store;
         }
     }
     // ===================== teardown =====================
@@ -1348,7 +1451,8 @@ static int setup_l0s(WsParams& p, const Geo& g, int B, uint32_t* smem, int passe
     p.idesc = umma_idesc_f16(128, sg.N0s);
     p.stream_pairs = g.T; p.stream_mode = 2;
     const uint32_t npos = (uint32_t)(sg.R0s / 2) * (g.Wo0 / 2);
-    return finalize_smem(p, (uint32_t)sg.w0s_bytes, smem, false, 2 * npos * kStash0sPitch * 2);
+    p.stash_group_bytes = align_up(2 * npos * kStash0sPitch * 2, 128);
+    return finalize_smem(p, (uint32_t)sg.w0s_bytes, smem, false, 2 * p.stash_group_bytes);
 }
 
 // conv 1: the tile / stage geometry of setup_l1 with 8-channel chunks carrying both parts; 74 steps per stage
@@ -1496,7 +1600,7 @@ static int launch_n(const WsParams& p, uint32_t smem, cudaStream_t stream) {
     }
     if (p.n_tiles <= 0) return 0;
     const int grid = p.n_tiles < sm_count ? p.n_tiles : sm_count;
-    ws_gemm_kernel<EPI, NACC><<<grid, kThreads, smem, stream>>>(p);
+    ws_gemm_kernel<EPI, NACC><<<grid, EPI == EPI_L0S ? kThreadsL0S : kThreads, smem, stream>>>(p);
     return check_launch("tc ws_gemm");
 }
 
