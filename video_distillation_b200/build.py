@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libvd_b200.so')
-SOURCES = ['api.cu', 'simt_conv.cu', 'pointwise.cu', 'compose_tiled.cu', 'tc_conv.cu', 'tc_pack.cu', 'tc_bwd.cu', 'tc_trio.cu']
+SOURCES = ['api.cu', 'simt_conv.cu', 'pointwise.cu', 'compose_tiled.cu', 'compose_tma.cu', 'tc_conv.cu', 'tc_pack.cu', 'tc_bwd.cu', 'tc_trio.cu']
 PROBE_SOURCES = SOURCES + ['tc_probe.cu']      # + -DVD_PROBE: scripts/libvd_b200_probe.so (tuning tools only, see scripts/_probe_lib.py)
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',

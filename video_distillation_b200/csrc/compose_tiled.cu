@@ -24,6 +24,7 @@ __device__ __forceinline__ void cpa16(float* dst_smem, const float* src) {
 }
 __device__ __forceinline__ void cpa_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cpa_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cpa_wait_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
 // rows [h0-1, h0+kTH+1) x cols [0,W) of one (H,W) fp32 plane -> smem plane [kTH+2][WP], data at column 4;
 // rows outside the image (or the whole plane when src == nullptr) are zero filled.
@@ -313,6 +314,7 @@ __global__ void __launch_bounds__(kCT) compose_bwd_wdyn_tiled_kernel(
 // The 327 sums leave the block as ONE row of `partial` (no floating-point atomics); compose_bwd_finish_kernel adds the rows in
 // block order: the hallucinator gradient is bitwise reproducible.
 constexpr int kPartialStride = 328;
+constexpr int kFR = 5;                 // frame slots of the fused backward's rings
 
 __global__ void __launch_bounds__(kCT) compose_bwd_fused_kernel(
         const float* __restrict__ gout, const float* __restrict__ static_syn, const float* __restrict__ dynamic_syn,
@@ -322,9 +324,9 @@ __global__ void __launch_bounds__(kCT) compose_bwd_fused_kernel(
     extern __shared__ float4 cmp_smem4[];
     float* smem = reinterpret_cast<float*>(cmp_smem4);
     const int plane = (kTH + 2) * WP;
-    float* Gr = smem;                                            // ring [4 frames][3 o][kTH+2][WP]
-    float* Dr = Gr + 12 * plane;                                 // ring [4 frames][kTH+2][WP]
-    float* Sp = Dr + 4 * plane;                                  // [3 i][kTH+2][WP] static image of the video
+    float* Gr = smem;                                            // ring [kFR frames][3 o][kTH+2][WP]
+    float* Dr = Gr + 3 * kFR * plane;                            // ring [kFR frames][kTH+2][WP]
+    float* Sp = Dr + kFR * plane;                                // [3 i][kTH+2][WP] static image of the video
     float4* wf = reinterpret_cast<float4*>(Sp + 3 * plane);      // [27 (a,bb,cc)] flipped dynamic-channel weights {o0,o1,o2,-}
     __shared__ float red[8 * 84];
     const int b = blockIdx.y, h0 = blockIdx.x * kTH;
@@ -333,7 +335,7 @@ __global__ void __launch_bounds__(kCT) compose_bwd_fused_kernel(
     const int64_t drow = label[b] * dpc + dynamic_idx[b];
     const float* D = dynamic_syn + drow * (int64_t)T * HW;
     const float* S = static_syn + static_idx[b] * 3 * HW;
-    zero_halo_columns(smem, 19, W, WP);
+    zero_halo_columns(smem, 4 * kFR + 3, W, WP);
     if (threadIdx.x < 27) {
         const int a = threadIdx.x / 9, bb = (threadIdx.x / 3) % 3, cc = threadIdx.x % 3;
         const int tap = ((2 - a) * 3 + (2 - bb)) * 3 + (2 - cc);
@@ -341,16 +343,22 @@ __global__ void __launch_bounds__(kCT) compose_bwd_fused_kernel(
     }
     auto stage_frame = [&](int f) {                              // f may be -1 or >= T: zeros
         const bool ok = (unsigned)f < (unsigned)T;
-        float* dst = Gr + ((f + 4) & 3) * 3 * plane;
+        float* dst = Gr + ((f + kFR) % kFR) * 3 * plane;
         for (int o = 0; o < 3; ++o) stage_plane(dst + o * plane, ok ? G + ((int64_t)f * 3 + o) * HW : nullptr, h0, H, W, WP);
-        stage_plane(Dr + ((f + 4) & 3) * plane, ok ? D + (int64_t)f * HW : nullptr, h0, H, W, WP);
+        stage_plane(Dr + ((f + kFR) % kFR) * plane, ok ? D + (int64_t)f * HW : nullptr, h0, H, W, WP);
     };
+    // ring of kFR = 5 frame slots: frames t-1 .. t+1 are read while t+2 (waited for at the NEXT iteration) and t+3 (just issued)
+    // stream in — two frames of prefetch; with four slots and cp.async.wait_all every iteration waited for the copy it had
+    // issued one iteration earlier, i.e. for a full global-memory round trip per frame
     for (int i = 0; i < 3; ++i) stage_plane(Sp + i * plane, S + i * HW, h0, H, W, WP);
     stage_frame(-1); stage_frame(0); stage_frame(1);
     cpa_commit();
+    stage_frame(2);
+    cpa_commit();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int r = warp, w0 = lane * 4;                           // one warp per image row, 4 columns per lane
-    const bool active = h0 + r < H && w0 < W;
+    const int vpr = W >> 2;
+    const int r = threadIdx.x / vpr, w0 = (threadIdx.x - r * vpr) * 4;      // (row, 4 columns): W / 4 threads per row, all lanes of a warp busy
+    const bool active = r < kTH && h0 + r < H;
     float acc[84];                                               // [o][tap] dynamic-channel weight sums, then the 3 bias sums
 #pragma unroll
     for (int k = 0; k < 84; ++k) acc[k] = 0.f;
@@ -361,12 +369,13 @@ __global__ void __launch_bounds__(kCT) compose_bwd_fused_kernel(
         for (int j = 0; j < 4; ++j) { gs[o][j] = 0.f; gf[o][j] = 0.f; gl[o][j] = 0.f; }
     float* gd = grad_dynamic + drow * (int64_t)T * HW;
     for (int t = 0; t < T; ++t) {
-        cpa_wait_all();
+        cpa_wait_but_one();                                      // frames <= t+1 have landed (t+2 may still be in flight)
         __syncthreads();
-        if (t + 2 <= T) { stage_frame(t + 2); cpa_commit(); }
+        if (t + 3 <= T) stage_frame(t + 3);                      // into the slot of frame t-2, which nobody reads any more
+        cpa_commit();                                            // (one group per iteration, possibly empty, keeps the count)
         if (!active) continue;
         float g[3][4];
-        const float* Gc = Gr + ((t + 4) & 3) * 3 * plane;        // frame t
+        const float* Gc = Gr + (t % kFR) * 3 * plane;            // frame t
 #pragma unroll
         for (int o = 0; o < 3; ++o) {
             const float4 v = *reinterpret_cast<const float4*>(Gc + o * plane + (r + 1) * WP + 4 + w0);
@@ -382,7 +391,7 @@ __global__ void __launch_bounds__(kCT) compose_bwd_fused_kernel(
         // dynamic-channel weights: g[t] x D[t + kt - 1]
 #pragma unroll
         for (int kt = 0; kt < 3; ++kt) {
-            const float* P = Dr + ((t + kt + 3) & 3) * plane;
+            const float* P = Dr + ((t + kt - 1 + kFR) % kFR) * plane;
 #pragma unroll
             for (int kh = 0; kh < 3; ++kh) {
                 float x[6];
@@ -404,7 +413,7 @@ __global__ void __launch_bounds__(kCT) compose_bwd_fused_kernel(
         float dd[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-            const float* F = Gr + ((t + a + 3) & 3) * 3 * plane;              // frame t-1+a
+            const float* F = Gr + ((t + a - 1 + kFR) % kFR) * 3 * plane;      // frame t-1+a
 #pragma unroll
             for (int bb = 0; bb < 3; ++bb) {
                 float x0[6], x1[6], x2[6];
@@ -455,7 +464,7 @@ __global__ void __launch_bounds__(kCT) compose_bwd_fused_kernel(
 #pragma unroll
                 for (int kh = 0; kh < 3; ++kh) {
                     float x[6];
-                    load_row6(Sp + i * plane + (r + kh) * WP, active ? w0 : 0, x);
+                    load_row6(Sp + i * plane + ((active ? r : 0) + kh) * WP, active ? w0 : 0, x);
 #pragma unroll
                     for (int kw = 0; kw < 3; ++kw) {
                         float sv = 0.f;
@@ -559,7 +568,7 @@ int compose_bwd_fused(const float* gout, const float* static_syn, const float* d
     const int WP = tiled_wp(W);
     const int nb = (int)ceil_div(H, kTH);
     if (scratch_floats < (int64_t)B * nb * kPartialStride) { set_error("compose_bwd_fused: scratch too small"); return -1; }
-    const size_t smem = (size_t)19 * (kTH + 2) * WP * 4 + 27 * 16;
+    const size_t smem = (size_t)(4 * kFR + 3) * (kTH + 2) * WP * 4 + 27 * 16;
     static size_t configured = 0;
     if (smem > configured) { if (int e = set_smem((const void*)compose_bwd_fused_kernel, smem)) return e; configured = smem; }
     dim3 grid((unsigned)nb, (unsigned)B, 1);
@@ -568,6 +577,10 @@ int compose_bwd_fused(const float* gout, const float* static_syn, const float* d
     if (int e = check_launch("compose_bwd_fused")) return e;
     compose_bwd_finish_kernel<<<3, 128, 0, stream>>>(scratch, B * nb, grad_weight, grad_bias);
     return check_launch("compose_bwd_finish");
+}
+
+void compose_bwd_finish(const float* scratch, int n_rows, float* grad_weight, float* grad_bias, cudaStream_t stream) {
+    compose_bwd_finish_kernel<<<3, 128, 0, stream>>>(scratch, n_rows, grad_weight, grad_bias);
 }
 
 }  // namespace vd

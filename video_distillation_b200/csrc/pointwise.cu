@@ -639,6 +639,14 @@ namespace vd {
 int compose_fwd_tiled(const float* static_syn, const float* dynamic_syn, const int64_t* static_idx, const int64_t* label,
                       const int64_t* dynamic_idx, const float* weight, const float* bias, float* out, int B, int T, int H,
                       int W, int dpc, cudaStream_t stream);
+// TMA-fed versions (compose_tma.cu); return 1 when the geometry is not covered or tensor maps are unavailable
+int compose_fwd_tma(const float* static_syn, const float* dynamic_syn, const int64_t* static_idx, const int64_t* label,
+                    const int64_t* dynamic_idx, const float* weight, const float* bias, float* out, int B, int T, int H,
+                    int W, int dpc, cudaStream_t stream);
+int compose_bwd_tma(const float* gout, const float* static_syn, const float* dynamic_syn, const int64_t* static_idx,
+                    const int64_t* label, const int64_t* dynamic_idx, const float* weight, float* grad_dynamic, float* grad_weight,
+                    float* grad_bias, float* scratch, int64_t scratch_floats, int unique_rows, int B, int T, int H, int W, int dpc,
+                    cudaStream_t stream);
 int compose_bwd_data_tiled(const float* gout, const int64_t* label, const int64_t* dynamic_idx, const float* weight,
                            float* grad_dynamic, int B, int T, int H, int W, int dpc, cudaStream_t stream);
 int compose_bwd_wdyn_tiled(const float* gout, const float* dynamic_syn, const int64_t* label, const int64_t* dynamic_idx,
@@ -656,9 +664,12 @@ extern "C" int vd_compose_fwd_f32(const float* static_syn, const float* dynamic_
     VD_REQUIRE(B >= 0 && T > 0 && H > 0 && W > 0 && dpc > 0 && T <= 65535 && B <= 65535, "compose_fwd: bad extent");
     if (B == 0) return 0;
     {
-        const int rc = compose_fwd_tiled(static_syn, dynamic_syn, static_idx, label, dynamic_idx, weight, bias, out, B, T, H, W, dpc,
-                                         (cudaStream_t)stream);
-        if (rc != 1) return rc;                 // 1 = geometry not covered by the tiled kernel
+        int rc = compose_fwd_tma(static_syn, dynamic_syn, static_idx, label, dynamic_idx, weight, bias, out, B, T, H, W, dpc,
+                                 (cudaStream_t)stream);
+        if (rc != 1) return rc;                 // 1 = not covered: the cp.async tiled kernel, then the generic one
+        rc = compose_fwd_tiled(static_syn, dynamic_syn, static_idx, label, dynamic_idx, weight, bias, out, B, T, H, W, dpc,
+                               (cudaStream_t)stream);
+        if (rc != 1) return rc;
     }
     const int W4 = (W + 3) / 4;
     dim3 grid((unsigned)ceil_div((int64_t)H * W4, 256), T, B);
@@ -721,8 +732,11 @@ extern "C" int vd_compose_bwd_fused_f32(const float* gout, const float* static_s
                "compose_bwd_fused: NULL pointer");
     VD_REQUIRE(B >= 0 && T > 0 && H > 0 && W > 0 && dpc > 0 && T <= 65535 && B <= 65535, "compose_bwd_fused: bad extent");
     if (B == 0) return 0;
-    const int rc = compose_bwd_fused(gout, static_syn, dynamic_syn, static_idx, label, dynamic_idx, weight, grad_dynamic, grad_weight,
-                                     grad_bias, scratch, scratch_floats, unique_rows, B, T, H, W, dpc, (cudaStream_t)stream);
+    int rc = compose_bwd_tma(gout, static_syn, dynamic_syn, static_idx, label, dynamic_idx, weight, grad_dynamic, grad_weight,
+                             grad_bias, scratch, scratch_floats, unique_rows, B, T, H, W, dpc, (cudaStream_t)stream);
+    if (rc != 1) return rc;
+    rc = compose_bwd_fused(gout, static_syn, dynamic_syn, static_idx, label, dynamic_idx, weight, grad_dynamic, grad_weight,
+                           grad_bias, scratch, scratch_floats, unique_rows, B, T, H, W, dpc, (cudaStream_t)stream);
     if (rc != 1) return rc;
     return vd_compose_bwd_f32(gout, static_syn, dynamic_syn, static_idx, label, dynamic_idx, weight, grad_dynamic, grad_weight,
                               grad_bias, nullptr, B, T, H, W, dpc, stream);
