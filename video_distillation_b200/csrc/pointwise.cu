@@ -404,7 +404,7 @@ __global__ void __launch_bounds__(256) class_mean_kernel(const float* __restrict
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
     if (d < D) {
         const float* p = emb + (int64_t)c * n * D + d;
-#pragma unroll 4
+#pragma unroll 16                 // batch_real = 64: all 16 loads of a thread in flight (the kernel lasts a few microseconds)
         for (int j = grp; j < n; j += 4) {
             const float4 v = __ldg(reinterpret_cast<const float4*>(p + (int64_t)j * D));
             s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;

@@ -147,53 +147,75 @@ __global__ void pack_w2_kernel(const float* __restrict__ w, uint16_t* __restrict
 }
 
 // ---- split-fp16 forward operands (SGeo, tc_layout.h) ----
-// X0s (B, T+2, part 2, 3, 2, RI0, Wo0) chunks of 8 fp16: part 0 = fp16(v), part 1 = fp16(v - part 0).  One block per
-// (video, padded frame, part, channel, row parity) plane.  U8: uint8 frames with the dataset normalisation fused in.
-// parts = 1: the hi-only layout X0h (B, T+2, 3, 2, RI0, Wo0) of the two-product mode (operand of vd_tc_x3_conv_layer_ex, passes = 2).
+// X0s (B, T+2, part 2, 3, 2, RI0, Wo0) chunks of 8 fp16: part 0 = fp16(v), part 1 = fp16(v - part 0); parts = 1: the hi-only layout
+// X0h (B, T+2, 3, 2, RI0, Wo0) of the two-product mode (operand of vd_tc_x3_conv_layer_ex, passes = 2).  U8: uint8 frames with the
+// dataset normalisation fused in.
+// One block per (video, padded frame, channel, row parity) plane pair (both parts).  A thread owns two adjacent chunks (wo = 2p,
+// 2p + 1) of a row: their 7-wide windows cover source columns 4p-3 .. 4p+5, i.e. the three ALIGNED quads at 4p-4, 4p, 4p+4 — three
+// 128-bit loads (three 32-bit loads of uint8 frames) feed four 16-byte stores, instead of seven scalar loads per store.
+constexpr int kPackPairs = 32;           // chunk pairs per block row (Wo0 / 2 <= 32)
+constexpr int kPackRows = 8;             // rows per pass
+
 template <bool U8>
-__global__ void __launch_bounds__(256) pack_video_x3_kernel(const void* __restrict__ video, const int64_t* __restrict__ index,
-                                                            uint4* __restrict__ x0, int T, int HW, int RI0, int Wo0, NormU8 nm, int parts) {
+__global__ void __launch_bounds__(kPackPairs * kPackRows) pack_video_x3_kernel(
+        const void* __restrict__ video, const int64_t* __restrict__ index, uint4* __restrict__ x0, int T, int HW, int RI0, int Wo0,
+        NormU8 nm, int parts) {
     int q = blockIdx.x;
     const int par = q & 1; q >>= 1;
     const int c = q % 3; q /= 3;
-    int part = 0;
-    if (parts == 2) { part = q & 1; q >>= 1; }
     const int tp = q % (T + 2);
     const int64_t b = q / (T + 2);
     const int t = tp - 1;
-    uint4* dst = x0 + (int64_t)blockIdx.x * RI0 * Wo0;
-    const int n = RI0 * Wo0;
-    if (t < 0 || t >= T) {
-        for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = make_uint4(0u, 0u, 0u, 0u);
+    const int n = RI0 * Wo0;                                                  // chunks per plane
+    // planes [b][t_pad][part][c][par]
+    uint4* dst_hi = x0 + ((((b * (T + 2) + tp) * parts + 0) * 3 + c) * 2 + par) * (int64_t)n;
+    uint4* dst_lo = parts == 2 ? x0 + ((((b * (T + 2) + tp) * parts + 1) * 3 + c) * 2 + par) * (int64_t)n : nullptr;
+    const int tid = threadIdx.y * kPackPairs + threadIdx.x;
+    if (t < 0 || t >= T) {                                                    // temporal halo frame: zeros
+        for (int i = tid; i < n; i += kPackPairs * kPackRows) {
+            dst_hi[i] = make_uint4(0u, 0u, 0u, 0u);
+            if (dst_lo) dst_lo[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
         return;
     }
     const int64_t src = index ? index[b] : b;
     const int64_t plane = ((src * T + t) * 3 + c) * HW * (int64_t)HW;
     const float mean = nm.mean[c], stdv = nm.stdv[c];
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int row = i / Wo0, wo = i - row * Wo0;
+    const int p = threadIdx.x;
+    if (2 * p >= Wo0) return;
+    const bool second = 2 * p + 1 < Wo0;
+    for (int row = threadIdx.y; row < RI0; row += kPackRows) {
         const int h = par ? 2 * row - 3 : 2 * row - 2;
-        uint16_t v[8];
+        float v[12];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = 0;
+        for (int k = 0; k < 12; ++k) v[k] = 0.f;
         if (h >= 0 && h < HW) {
 #pragma unroll
-            for (int k = 0; k < 7; ++k) {
-                const int w = 2 * wo + k - 3;
-                if (w >= 0 && w < HW) {
-                    float x;
-                    if (U8) x = __fdiv_rn(__fsub_rn(__fdiv_rn((float)__ldg((const uint8_t*)video + plane + (int64_t)h * HW + w), 255.f), mean), stdv);
-                    else x = __ldg((const float*)video + plane + (int64_t)h * HW + w);
-                    uint16_t hi, lo;
-                    split_h(x, hi, lo);
-                    v[k] = part ? lo : hi;
+            for (int qd = 0; qd < 3; ++qd) {
+                const int w = 4 * p - 4 + 4 * qd;
+                if (w < 0 || w >= HW) continue;
+                if (U8) {
+                    const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>((const uint8_t*)video + plane + (int64_t)h * HW + w));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        v[4 * qd + k] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)((u >> (8 * k)) & 255u), 255.f), mean), stdv);
+                } else {
+                    const float4 f = __ldg(reinterpret_cast<const float4*>((const float*)video + plane + (int64_t)h * HW + w));
+                    v[4 * qd] = f.x; v[4 * qd + 1] = f.y; v[4 * qd + 2] = f.z; v[4 * qd + 3] = f.w;
                 }
             }
         }
-        uint4 o;
-        o.x = v[0] | ((uint32_t)v[1] << 16); o.y = v[2] | ((uint32_t)v[3] << 16);
-        o.z = v[4] | ((uint32_t)v[5] << 16); o.w = v[6] | ((uint32_t)v[7] << 16);
-        dst[i] = o;
+        uint16_t hi[12], lo[12];
+#pragma unroll
+        for (int k = 1; k < 10; ++k) split_h(v[k], hi[k], lo[k]);
+        // chunk wo = 2p: columns 4p-3 .. 4p+3 = v[1..7]; chunk wo = 2p+1: columns 4p-1 .. 4p+5 = v[3..9]; 8th element (kw = 7) = 0
+        const int o = row * Wo0 + 2 * p;
+        dst_hi[o] = make_uint4(hi[1] | ((uint32_t)hi[2] << 16), hi[3] | ((uint32_t)hi[4] << 16), hi[5] | ((uint32_t)hi[6] << 16), hi[7]);
+        if (second) dst_hi[o + 1] = make_uint4(hi[3] | ((uint32_t)hi[4] << 16), hi[5] | ((uint32_t)hi[6] << 16), hi[7] | ((uint32_t)hi[8] << 16), hi[9]);
+        if (dst_lo) {
+            dst_lo[o] = make_uint4(lo[1] | ((uint32_t)lo[2] << 16), lo[3] | ((uint32_t)lo[4] << 16), lo[5] | ((uint32_t)lo[6] << 16), lo[7]);
+            if (second) dst_lo[o + 1] = make_uint4(lo[3] | ((uint32_t)lo[4] << 16), lo[5] | ((uint32_t)lo[6] << 16), lo[7] | ((uint32_t)lo[8] << 16), lo[9]);
+        }
     }
 }
 
@@ -341,10 +363,12 @@ static int pack_video_x3_impl(const void* video, bool u8, const int64_t* index, 
     const Geo g = make_geo(plan->T, plan->H);
     NormU8 nm;
     for (int c = 0; c < 3; ++c) { nm.mean[c] = mean3 ? mean3[c] : 0.f; nm.stdv[c] = std3 ? std3[c] : 1.f; }
-    const int64_t blocks = (int64_t)B * (g.T + 2) * 6 * parts;               // planes [b][t_pad][part][c][par]
+    const int64_t blocks = (int64_t)B * (g.T + 2) * 6;                       // (b, t_pad, c, par): both parts of a plane in one block
     VD_REQUIRE(blocks < (1ll << 31), "tc_x3_pack_video: grid too large");
-    if (u8) pack_video_x3_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(video, index, (uint4*)x0s, g.T, g.HW, g.RI0, g.Wo0, nm, parts);
-    else pack_video_x3_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(video, index, (uint4*)x0s, g.T, g.HW, g.RI0, g.Wo0, nm, parts);
+    VD_REQUIRE(g.Wo0 <= 2 * kPackPairs && g.HW % 4 == 0 && ((uintptr_t)video & 15) == 0, "tc_x3_pack_video: unsupported width / unaligned videos");
+    const dim3 block(kPackPairs, kPackRows, 1);
+    if (u8) pack_video_x3_kernel<true><<<(unsigned)blocks, block, 0, (cudaStream_t)stream>>>(video, index, (uint4*)x0s, g.T, g.HW, g.RI0, g.Wo0, nm, parts);
+    else pack_video_x3_kernel<false><<<(unsigned)blocks, block, 0, (cudaStream_t)stream>>>(video, index, (uint4*)x0s, g.T, g.HW, g.RI0, g.Wo0, nm, parts);
     return check_launch("tc_x3_pack_video");
 }
 
