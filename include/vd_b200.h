@@ -84,6 +84,10 @@ int vd_inorm_relu_fwd_f32(const float* x, const float* gamma, const float* beta,
 int vd_inorm_relu_bwd_f32(const float* x, const float* y, const float* gy, const float* gamma,
                           const float* mean, const float* rstd, float* gx, float* ggamma,
                           float* gbeta, int N, int C, int64_t S, void* stream);
+/* instancenorm + ReLU + AvgPool3d(2) of networks.py:784,757,772 in one launch for frozen networks (forward only): x (N,C,T,H,W)
+ * -> y (N,C,T/2,H/2,W/2); the normalised activation is never written.  mean / rstd (N*C each) may both be NULL. */
+int vd_inorm_relu_avgpool_fwd_f32(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd,
+                                  int N, int C, int T, int H, int W, void* stream);
 int vd_avgpool2_fwd_f32(const float* x, float* y, int64_t NC, int T, int H, int W, void* stream);
 int vd_avgpool2_bwd_f32(const float* gy, float* gx, int64_t NC, int T, int H, int W, void* stream);
 

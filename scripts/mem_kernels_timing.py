@@ -64,3 +64,11 @@ report('pack_video_x3 (hi + lo)', timed(lambda: tc.pack_video(video)), B * (4 * 
 report('pack_video_x3 (hi only)', timed(lambda: tc.pack_video(video, hi_only=True)), B * (4 * 3 * thw + tc.x0h_per))
 emb = torch.randn(50, 64, 2048, device=dev)
 report('class_mean (50 x 64 x 2048)', timed(lambda: ops.class_mean(emb)), emb.numel() * 4 + 50 * 2048 * 4)
+
+# instancenorm + ReLU + avgpool between the convs of the IN / avgpool variant (networks.py:765-790): conv-0 output of 32 videos
+xin = torch.randn(32, 64, 16, 56, 56, device=dev)
+gam, bet = torch.ones(64, device=dev), torch.zeros(64, device=dev)
+with torch.no_grad():
+    nb = xin.numel() * 4 + xin.numel() // 8 * 4
+    report('IN + ReLU + avgpool (one launch)', timed(lambda: ops.instancenorm_relu_avgpool(xin, gam, bet)), nb)
+    report('IN + ReLU, then avgpool (pair)', timed(lambda: ops.avgpool3d_2(ops.instancenorm_relu(xin, gam, bet))), nb)

@@ -240,6 +240,63 @@ def test_instancenorm_avgpool_variant():
     assert rel(xc.grad, xd.grad) < 1e-4 and rel(gc.grad, gd.grad) < 1e-4 and rel(bc.grad, bd.grad) < 1e-4
 
 
+def test_fused_instancenorm_relu_avgpool_forward():
+    """vd_inorm_relu_avgpool_fwd_f32 (one launch, frozen networks) against fp64 torch and against the differentiable pair."""
+    from video_distillation_b200 import ops
+    g = torch.Generator().manual_seed(16)
+    for shape in [(2, 6, 4, 6, 6), (3, 64, 8, 28, 28), (1, 128, 4, 14, 14), (2, 5, 2, 4, 4)]:
+        x = torch.randn(*shape, generator=g) * 1.7 + 0.3
+        C = shape[1]
+        gam, bet = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g)
+        y_ref = F.avg_pool3d(F.relu(F.group_norm(x.double(), C, gam.double(), bet.double(), 1e-5)), 2, 2)
+        with torch.no_grad():
+            y = ops.instancenorm_relu_avgpool(x.cuda(), gam.cuda(), bet.cuda())
+            y_pair = ops.avgpool3d_2(ops.instancenorm_relu(x.cuda(), gam.cuda(), bet.cuda()))
+        assert y.shape == y_ref.shape
+        assert rel(y, y_ref) < 2e-5, (shape, rel(y, y_ref))
+        assert rel(y, y_pair) < 1e-6
+    # with gradients enabled the op is the differentiable pair
+    xc = torch.randn(2, 6, 4, 6, 6, generator=g).cuda().requires_grad_(True)
+    gc, bc = torch.ones(6).cuda(), torch.zeros(6).cuda()
+    ops.instancenorm_relu_avgpool(xc, gc, bc).sum().backward()
+    assert xc.grad is not None and torch.isfinite(xc.grad).all()
+
+
+def test_instancenorm_avgpool_net_on_tensor_cores():
+    """ConvNet3D(instancenorm, avgpooling) (networks.py:765-790) at the bench video shape with the three feature convs on
+    tcgen05 (conv trio, split-bf16 fprop) and the fused IN + ReLU + avgpool kernel between them, against the CPU oracle."""
+    import oracle
+    from oracle import synth
+    from video_distillation_b200 import ops
+    from video_distillation_b200.networks import ConvNet3D
+    T, H = 16, 112
+    params = synth.synth_convnet3d_params(3, num_classes=5)
+    p2 = {}
+    for d in range(3):
+        p2[f'features.{4 * d}.weight'] = params[f'features.{3 * d}.weight']
+        p2[f'features.{4 * d}.bias'] = params[f'features.{3 * d}.bias']
+        c = p2[f'features.{4 * d}.weight'].shape[0]
+        p2[f'features.{4 * d + 1}.weight'] = 1.0 + synth.hash_uniform((c,), 300 + d, 0.25)
+        p2[f'features.{4 * d + 1}.bias'] = synth.hash_uniform((c,), 310 + d, 0.25)
+    p2['logit.weight'], p2['logit.bias'] = params['logit.weight'], params['logit.bias']
+    net = ConvNet3D(3, 5, 128, 3, 'relu', 'instancenorm', 'avgpooling', T, (H, H))
+    net.load_state_dict(p2)
+    net = net.cuda()
+    x = synth.hash_uniform((2, T, 3, H, H), 13)
+    ref = oracle.convnet3d_embed(p2, x, net_norm='instancenorm', net_pooling='avgpooling')
+    with torch.no_grad():
+        e32 = net.embed(x.cuda())
+        prev = ops.set_conv_backend('tc')
+        try:
+            etc = net.embed(x.cuda())
+        finally:
+            ops.set_conv_backend(prev)
+    print(f'IN/avgpool variant at 16x3x112x112: fp32 kernels {rel(e32, ref):.2e}, tensor-core convs + fused IN/ReLU/avgpool {rel(etc, ref):.2e}')
+    assert e32.shape == ref.shape
+    assert rel(e32, ref) < 1e-4
+    assert rel(etc, ref) < 1e-3
+
+
 def test_sqdist():
     from video_distillation_b200 import ops
     g = torch.Generator().manual_seed(7)

@@ -48,6 +48,7 @@ def _declare(lib):
         'vd_route_gather_f32': (c_int, [P, P, P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, P]),
         'vd_inorm_relu_fwd_f32': (c_int, [P, P, P, P, P, P, c_int, c_int, c_int64, P]),
         'vd_inorm_relu_bwd_f32': (c_int, [P, P, P, P, P, P, P, P, P, c_int, c_int, c_int64, P]),
+        'vd_inorm_relu_avgpool_fwd_f32': (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
         'vd_avgpool2_fwd_f32': (c_int, [P, P, c_int64, c_int, c_int, c_int, P]),
         'vd_avgpool2_bwd_f32': (c_int, [P, P, c_int64, c_int, c_int, c_int, P]),
         'vd_compose_fwd_f32': (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),

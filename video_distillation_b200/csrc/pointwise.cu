@@ -124,6 +124,58 @@ __global__ void avgpool2_fwd_kernel(const float* __restrict__ x, float* __restri
     }
 }
 
+// instancenorm + ReLU + AvgPool3d(2) in ONE launch (networks.py:784,757,772 as Features applies them): a block owns an (n, c)
+// instance of S = T*H*W values.  Pass 1 (HBM, 128-bit loads): shifted first and second moments -> mean, rstd; pass 2 (the
+// instance — 200 KB at most — comes back from L2): every thread normalises the 2x2x2 inputs of its pooled outputs (float2
+// loads), applies ReLU and writes the mean: the normalised activation never exists in memory.  Algorithmic HBM bytes: 4*S read
+// + S/2 written per instance (the unfused pair: 4*S + 4*S + 4*S + S/2).
+__global__ void __launch_bounds__(512) inorm_relu_avgpool_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                                     const float* __restrict__ beta, float* __restrict__ y,
+                                                                     float* __restrict__ mean, float* __restrict__ rstd,
+                                                                     int C, int T, int H, int W) {
+    __shared__ float red[32];
+    const int64_t nc = blockIdx.x;
+    const int c = (int)(nc % C);
+    const int64_t S = (int64_t)T * H * W;
+    const float* xp = x + nc * S;
+    const int64_t S4 = S >> 2;                                   // S % 4 == 0 (checked by the host)
+    const float4* x4 = reinterpret_cast<const float4*>(xp);
+    // ONE statistics pass: sums of (x - k) and (x - k)^2 around a sample k = x[0] of the instance (|k - mean| ~ sigma, so the
+    // subtraction below cancels a factor of ~2, not the mean^2 / var of the raw-moment formula)
+    const float k = __ldg(xp);
+    float s = 0.f, q = 0.f;
+#pragma unroll 4
+    for (int64_t i = threadIdx.x; i < S4; i += blockDim.x) {
+        const float4 v = __ldg(x4 + i);
+        const float a0 = v.x - k, a1 = v.y - k, a2 = v.z - k, a3 = v.w - k;
+        s += (a0 + a1) + (a2 + a3);
+        q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+    }
+    const float m1 = block_sum(s, red) / (float)S;
+    const float m2 = block_sum(q, red) / (float)S;
+    const float mu = k + m1;
+    const float var = fmaxf(m2 - m1 * m1, 0.f);
+    const float rs = rsqrtf(var + 1e-5f);
+    if (threadIdx.x == 0 && mean) { mean[nc] = mu; rstd[nc] = rs; }
+    const float g = gamma[c] * rs, b = beta[c] - mu * g;
+    const int To = T / 2, Ho = H / 2, Wo = W / 2;
+    float* yp = y + nc * (int64_t)To * Ho * Wo;
+    const int HoWo = Ho * Wo;
+    for (int o = threadIdx.x; o < To * HoWo; o += blockDim.x) {
+        const int to = o / HoWo, rem = o - to * HoWo, ho = rem / Wo, wo = rem - ho * Wo;
+        const float* p0 = xp + ((int64_t)(2 * to) * H + 2 * ho) * W + 2 * wo;
+        float acc = 0.f;
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int bb = 0; bb < 2; ++bb) {
+                const float2 v = __ldg(reinterpret_cast<const float2*>(p0 + ((int64_t)a * H + bb) * W));
+                acc += fmaxf(fmaf(v.x, g, b), 0.f) + fmaxf(fmaf(v.y, g, b), 0.f);
+            }
+        yp[o] = acc * 0.125f;
+    }
+}
+
 __global__ void avgpool2_bwd_kernel(const float* __restrict__ gy, float* __restrict__ gx, int64_t total,
                                     int T, int H, int W, int To, int Ho, int Wo) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -615,6 +667,16 @@ extern "C" int vd_inorm_relu_bwd_f32(const float* x, const float* y, const float
     VD_REQUIRE(x && y && gy && gamma && mean && rstd && gx && ggamma && gbeta && N > 0 && C > 0 && S > 0, "inorm_relu_bwd: bad argument");
     inorm_relu_bwd_kernel<<<N * C, 256, 0, (cudaStream_t)stream>>>(x, y, gy, gamma, mean, rstd, gx, ggamma, gbeta, C, S);
     return check_launch("inorm_relu_bwd_f32");
+}
+
+extern "C" int vd_inorm_relu_avgpool_fwd_f32(const float* x, const float* gamma, const float* beta, float* y, float* mean,
+                                             float* rstd, int N, int C, int T, int H, int W, void* stream) {
+    VD_REQUIRE(x && gamma && beta && y && N > 0 && C > 0 && T >= 2 && H >= 2 && W >= 2, "inorm_relu_avgpool_fwd: bad argument");
+    VD_REQUIRE(W % 2 == 0 && ((int64_t)T * H * W) % 4 == 0 && ((uintptr_t)x & 15) == 0,
+               "inorm_relu_avgpool_fwd: W must be even, T*H*W a multiple of 4 and x 16-byte aligned");
+    VD_REQUIRE((mean == nullptr) == (rstd == nullptr), "inorm_relu_avgpool_fwd: mean and rstd go together");
+    inorm_relu_avgpool_fwd_kernel<<<N * C, 512, 0, (cudaStream_t)stream>>>(x, gamma, beta, y, mean, rstd, C, T, H, W);
+    return check_launch("inorm_relu_avgpool_fwd_f32");
 }
 
 extern "C" int vd_avgpool2_fwd_f32(const float* x, float* y, int64_t NC, int T, int H, int W, void* stream) {

@@ -62,7 +62,7 @@ class InstanceNorm(nn.GroupNorm):
 
 
 class Features(nn.Sequential):
-    """nn.Sequential with the reference's module indices that fuses [ReLU, MaxPool3d] and
+    """nn.Sequential with the reference's module indices that fuses [ReLU, MaxPool3d], [InstanceNorm, ReLU, AvgPool3d] and
     [InstanceNorm, ReLU] neighbours into single kernels."""
 
     def forward(self, x):
@@ -74,6 +74,9 @@ class Features(nn.Sequential):
             if isinstance(m, ReLU) and isinstance(nxt, MaxPool3d):
                 x = ops.relu_maxpool3d(x, nxt.kernel_size)
                 i += 2
+            elif isinstance(m, InstanceNorm) and isinstance(nxt, ReLU) and i + 2 < len(mods) and isinstance(mods[i + 2], AvgPool3d):
+                x = ops.instancenorm_relu_avgpool(x, m.weight, m.bias)        # one launch when the net is frozen
+                i += 3
             elif isinstance(m, InstanceNorm) and isinstance(nxt, ReLU):
                 x = ops.instancenorm_relu(x, m.weight, m.bias)
                 i += 2

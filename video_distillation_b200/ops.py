@@ -329,6 +329,22 @@ def avgpool3d_2(x):
     return _AvgPool2.apply(x)
 
 
+def instancenorm_relu_avgpool(x, gamma, beta):
+    """AvgPool3d(2)(ReLU(GroupNorm(C, C)(x))) (networks.py:784,757,772).  Frozen network (nothing requires a gradient — the DM /
+    evaluation embeds): ONE launch that never writes the normalised activation (vd_inorm_relu_avgpool_fwd_f32); otherwise the
+    differentiable pair instancenorm_relu + avgpool3d_2."""
+    needs_grad = torch.is_grad_enabled() and (x.requires_grad or gamma.requires_grad or beta.requires_grad)
+    N, C, T, H, W = x.shape
+    if needs_grad or W % 2 or (T * H * W) % 4:
+        return avgpool3d_2(instancenorm_relu(x, gamma, beta))
+    x = _f32c(x)
+    y = torch.empty(N, C, T // 2, H // 2, W // 2, dtype=torch.float32, device=x.device)
+    if y.numel():
+        check(lib().vd_inorm_relu_avgpool_fwd_f32(ptr(x), ptr(_f32c(gamma)), ptr(_f32c(beta)), ptr(y), None, None, N, C, T, H, W, stream()),
+              'inorm_relu_avgpool_fwd')
+    return y
+
+
 # ------------------------------------------------------------------ composer
 class _Compose(torch.autograd.Function):
     @staticmethod
