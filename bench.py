@@ -349,7 +349,14 @@ def memory_kernel_rooflines(step_fn, tr, steps=3):
     tcn = tr.embedder.tc
     p = tcn.plan
     dyp1 = getattr(tcn, 'dyp1_bytes_per_video', 0)
+    # fp32 FMAs of the composer stencils (81 per output element forward; 81 + 81 backward): these kernels sit above the ridge
+    # (5.5 FMA per byte) and are bound by the fp32 pipe — `fma_frac` is the fraction of the measured 36.0 TFMA/s
+    # (scripts/microbench/ffma_rate.cu: 128 FMA / clk / SM at 1.965 GHz; FFMA2 issues two per instruction at the same rate)
+    fma = {'compose_fwd_tma_kernel': n_syn * thw * 81, 'compose_fwd_tiled_kernel': n_syn * thw * 81,
+           'compose_bwd_tma_kernel': n_syn * thw * 162, 'compose_bwd_fused_kernel': n_syn * thw * 162}
     rows = [  # (kernel-name substring, algorithmic bytes per launch, what)
+        ('compose_fwd_tma_kernel', n_syn * 4 * (3 * hw + thw + 3 * thw), 'read static+dynamic (tensor-map TMA), write video'),
+        ('compose_bwd_tma_kernel', n_syn * 4 * (3 * thw + thw + 3 * hw + thw), 'read d video + dynamic + static (tensor-map TMA), write d dynamic'),
         ('compose_fwd_tiled_kernel', n_syn * 4 * (3 * hw + thw + 3 * thw), 'read static+dynamic, write video'),
         ('compose_bwd_fused_kernel', n_syn * 4 * (3 * thw + thw + 3 * hw + thw), 'read d video + dynamic + static, write d dynamic'),
         ('compose_bwd_data_tiled_kernel', n_syn * 4 * (3 * thw + thw), 'read d video, write d dynamic'),
@@ -361,7 +368,7 @@ def memory_kernel_rooflines(step_fn, tr, steps=3):
         ('col2im_kernel<unsigned short', n_syn * (p.col2_bytes_per_video + 128 * int(p.T2p) * int(p.H2p) * int(p.W2p) + dyp1),
          'read conv-2 columns + codes, write padded planar dY1'),
         ('pack_video_kernel', n_syn * (4 * 3 * thw + p.x0_bytes_per_video), 'read fp32 video, write packed bf16 conv-0 operand'),
-        ('pack_video_x3_kernel', n_syn * (4 * 3 * thw + tcn.x0_per), 'read fp32 video, write packed fp16 hi/lo conv-0 operand'),
+        ('pack_video_x3_kernel', n_syn * (4 * 3 * thw + getattr(tcn, 'x0_per', 0)), 'read fp32 video, write packed fp16 hi/lo conv-0 operand'),
         ('sgd_momentum_kernel', None, '20 B / element (dynamic memory)'),
         ('class_mean_kernel', C * BATCH_REAL * p.embed_dim * 4, 'read real embeddings'),
     ]
@@ -379,9 +386,13 @@ def memory_kernel_rooflines(step_fn, tr, steps=3):
                         'frac': nbytes / per_step_ms / 1e6 / hbm, 'what': what})
             continue
         ms = ms_total / n
-        out.append({'kernel': key, 'ms': ms, 'bytes': int(nbytes), 'gbs': nbytes / ms / 1e6, 'frac': nbytes / ms / 1e6 / hbm,
-                    'what': what})
-    return {'peak_gbs': hbm, 'peak_kind': 'hbm_gbs of measured (copy read+write)', 'kernels': out}
+        row = {'kernel': key, 'ms': ms, 'bytes': int(nbytes), 'gbs': nbytes / ms / 1e6, 'frac': nbytes / ms / 1e6 / hbm, 'what': what}
+        if key in fma:
+            row.update({'bound': 'fp32 FMA', 'fma': int(fma[key]), 'tfma_s': fma[key] / ms / 1e9, 'fma_frac': fma[key] / ms / 1e9 / 36.0})
+        else:
+            row['bound'] = 'hbm'
+        out.append(row)
+    return {'peak_gbs': hbm, 'peak_kind': 'hbm_gbs of measured (copy read+write)', 'peak_tfma_s': 36.0, 'kernels': out}
 
 
 # ------------------------------------------------------------------------------------------ our arm
