@@ -328,6 +328,18 @@ int vd_tc_pack_dgrad0_weights(const float* w_l0, void* wimg, void* stream);
 int vd_tc_pack_dyp0(const float* gy, void* dyp, const vd_tc_plan* plan, int B, void* stream);
 int vd_tc_dgrad0(const void* dyp0, const void* wimg, float* out, const vd_tc_plan* plan, int B, int ncdhw, void* stream);
 
+/* Split-bf16 dgrad helpers (the parity backward evaluates every dgrad as dgrad(gh, wh) + dgrad(gh, wl) + dgrad(gl, wh), g = gh + gl,
+ * w = wh + wl in bf16 parts): the packers make part 0 = bf16(gy) / part 1 = bf16(gy - bf16(gy)) from the fp32 gradient itself,
+ * and the column-free dgrads can accumulate into their fp32 output (accumulate != 0: out += result), so the three passes share
+ * one tensor without elementwise launches in between. */
+int vd_tc_pack_dy_part(int layer, const float* gy, void* dy, const vd_tc_plan* plan, int B, int part, void* stream);
+int vd_tc_pack_dyp1_part(const float* gy, void* dyp, const vd_tc_plan* plan, int B, int part, void* stream);
+int vd_tc_pack_dyp0_part(const float* gy, void* dyp, const vd_tc_plan* plan, int B, int part, void* stream);
+int vd_tc_dgrad1_plain(const void* dyp, const void* wimg0, const void* wimg1, float* out, const vd_tc_plan* plan, int B,
+                       int accumulate, void* stream);
+int vd_tc_dgrad0_ex(const void* dyp0, const void* wimg, float* out, const vd_tc_plan* plan, int B, int ncdhw, int accumulate,
+                    void* stream);
+
 /* Host-only introspection (no GPU work): the launch parameters vd_tc_conv_layer would use,
  * flattened to int64 (layout documented in tests/tc_emulator.py); cap >= 248. */
 int vd_tc_debug_params(int layer, const vd_tc_plan* plan, int B, int64_t* out, int cap);   /* layer 3,4,5 = bwd gemm of conv 0,1,2; 6,7,8 = split-fp16 conv 0,1,2 */

@@ -43,6 +43,11 @@ def declare(lib):
         'vd_tc_pack_dgrad0_weights': (c_int, [P, P, P]),
         'vd_tc_pack_dyp0': (c_int, [P, P, POINTER(TcPlan), c_int, P]),
         'vd_tc_dgrad0': (c_int, [P, P, P, POINTER(TcPlan), c_int, c_int, P]),
+        'vd_tc_pack_dy_part': (c_int, [c_int, P, P, POINTER(TcPlan), c_int, c_int, P]),
+        'vd_tc_pack_dyp1_part': (c_int, [P, P, POINTER(TcPlan), c_int, c_int, P]),
+        'vd_tc_pack_dyp0_part': (c_int, [P, P, POINTER(TcPlan), c_int, c_int, P]),
+        'vd_tc_dgrad1_plain': (c_int, [P, P, P, P, POINTER(TcPlan), c_int, c_int, P]),
+        'vd_tc_dgrad0_ex': (c_int, [P, P, P, POINTER(TcPlan), c_int, c_int, c_int, P]),
         'vd_tc_debug_params': (c_int, [c_int, POINTER(TcPlan), c_int, POINTER(c_int64), c_int]),
     }
     for name, (res, args) in sig.items():

@@ -35,7 +35,7 @@ struct EpiParams {
     uint8_t* code;         // optional ReLU/argmax routing codes, NCDHW order of the pooled tensor
     int code_first;        // items below this index record no codes (frozen real videos ahead of synthetic ones)
     int layer;             // EPI_PLAIN: which conv (tile -> NCDHW mapping)
-    int accum;             // EPI_PLAIN: out += result (split-bf16 passes accumulate into the same fp32 tensor)
+    int accum;             // EPI_PLAIN, EPI_DG0, EPI_DG1 (plain output): out += result (split-bf16 passes accumulate into the same fp32 tensor)
     int ph;                // EPI_DG1: input-row parity of this launch
     int dy0_planar;        // EPI_DG1 (route mode): write the padded planar dY of conv 0 (Dg0Geo) instead of the column-GEMM operand
     int ncdhw;             // EPI_DG0: output (B,3,T,H,W) instead of the video layout (B,T,3,H,W)
@@ -760,7 +760,7 @@ __device__ __forceinline__ void epi_dg1(const WsParams& p, int tile, uint32_t ta
         for (int b = 0; b < 16; ++b) {
             if (b >= g.Wo1) continue;
             const int w = 2 * b + pw;
-            if (code == nullptr) { gx[h * g.H1 + w] = v[b]; continue; }
+            if (code == nullptr) { gx[h * g.H1 + w] = p.epi.accum ? gx[h * g.H1 + w] + v[b] : v[b]; continue; }
             const uint8_t cd = code[h * g.H1 + w];
             const uint16_t gv = f2bf((cd & 8) ? v[b] : 0.f);
             const int arg = cd & 7;
@@ -806,8 +806,13 @@ __device__ __forceinline__ void epi_dg0(const WsParams& p, int tile, uint32_t ta
     for (int ci = 0; ci < 3; ++ci) {
         const int64_t plane = p.epi.ncdhw ? ((int64_t)item * 3 + ci) * g.T + t : ((int64_t)item * g.T + t) * 3 + ci;
         float* dst = out + plane * HW + (int64_t)(2 * a) * g.HW + 2 * b;
-        *reinterpret_cast<float2*>(dst) = make_float2(v[ci * 4 + 0], v[ci * 4 + 1]);
-        *reinterpret_cast<float2*>(dst + g.HW) = make_float2(v[ci * 4 + 2], v[ci * 4 + 3]);
+        float2 r0 = make_float2(v[ci * 4 + 0], v[ci * 4 + 1]), r1 = make_float2(v[ci * 4 + 2], v[ci * 4 + 3]);
+        if (p.epi.accum) {                                   // out += result: the passes of a split-bf16 dgrad share one fp32 tensor
+            const float2 o0 = *reinterpret_cast<const float2*>(dst), o1 = *reinterpret_cast<const float2*>(dst + g.HW);
+            r0.x += o0.x; r0.y += o0.y; r1.x += o1.x; r1.y += o1.y;
+        }
+        *reinterpret_cast<float2*>(dst) = r0;
+        *reinterpret_cast<float2*>(dst + g.HW) = r1;
     }
 }
 
@@ -1853,11 +1858,17 @@ static int bwd_gemm_impl(int layer, const void* dy, const void* wt, void* col, c
 // images of vd_tc_pack_dgrad1_weights.  code0 != NULL: out = packed dY of conv 0's column GEMM (routing applied);
 // code0 == NULL: out = fp32 NCDHW (B, 64, T, H1, H1).
 static int dgrad1_impl(const void* dyp, const void* wimg0, const void* wimg1, const uint8_t* code0, void* out,
-                       const vd_tc_plan* plan, int B, int dy0_planar, void* stream);
+                       const vd_tc_plan* plan, int B, int dy0_planar, void* stream, int accumulate = 0);
 
 extern "C" int vd_tc_dgrad1(const void* dyp, const void* wimg0, const void* wimg1, const uint8_t* code0, void* out,
                             const vd_tc_plan* plan, int B, void* stream) {
     return dgrad1_impl(dyp, wimg0, wimg1, code0, out, plan, B, 0, stream);
+}
+
+// plain fp32 NCDHW output (B, 64, T, H1, H1); accumulate != 0: out += result (the passes of a split-bf16 dgrad)
+extern "C" int vd_tc_dgrad1_plain(const void* dyp, const void* wimg0, const void* wimg1, float* out, const vd_tc_plan* plan, int B,
+                                  int accumulate, void* stream) {
+    return dgrad1_impl(dyp, wimg0, wimg1, nullptr, out, plan, B, 0, stream, accumulate);
 }
 
 // out_planar != 0 (needs code0): the routed gradient goes to the padded planar dY of conv 0 consumed by vd_tc_dgrad0
@@ -1869,8 +1880,9 @@ extern "C" int vd_tc_dgrad1_ex(const void* dyp, const void* wimg0, const void* w
 }
 
 static int dgrad1_impl(const void* dyp, const void* wimg0, const void* wimg1, const uint8_t* code0, void* out,
-                       const vd_tc_plan* plan, int B, int dy0_planar, void* stream) {
+                       const vd_tc_plan* plan, int B, int dy0_planar, void* stream, int accumulate) {
     VD_REQUIRE(dyp && wimg0 && wimg1 && out && plan, "tc_dgrad1: NULL pointer");
+    VD_REQUIRE(!accumulate || !code0, "tc_dgrad1: accumulation is for the plain fp32 output");
     VD_REQUIRE(geo_supported(plan->T, plan->H) && B >= 0, "tc_dgrad1: unsupported geometry / batch");
     if (B == 0) return 0;
     const Geo g = make_geo(plan->T, plan->H);
@@ -1906,7 +1918,7 @@ static int dgrad1_impl(const void* dyp, const void* wimg0, const void* wimg1, co
         if (int rc = finalize_smem(p, (uint32_t)p.G * p.RW * kWeightTileBytes, &smem)) return rc;
         p.pix = (const uint8_t*)dyp; p.wimg = (const uint8_t*)(ph ? wimg1 : wimg0); p.item_index = nullptr;
         p.epi.out = (uint8_t*)out; p.epi.code = const_cast<uint8_t*>(code0); p.epi.T = plan->T; p.epi.n_items = B; p.epi.g = g;
-        p.epi.ph = ph; p.epi.bb = make_bwd_geo(g, 0); p.epi.dy0_planar = dy0_planar;
+        p.epi.ph = ph; p.epi.bb = make_bwd_geo(g, 0); p.epi.dy0_planar = dy0_planar; p.epi.accum = accumulate;
         if (int rc = launch<EPI_DG1>(p, smem, (cudaStream_t)stream)) return rc;
     }
     return 0;
@@ -1915,8 +1927,22 @@ static int dgrad1_impl(const void* dyp, const void* wimg0, const void* wimg1, co
 // Direct dgrad of conv 0 (no column buffer, Dg0Geo): dyp0 = padded planar dY of conv 0 (vd_tc_dgrad1_ex /
 // vd_tc_pack_dyp0), wimg = resident weight image (vd_tc_pack_dgrad0_weights), out = fp32 gradient w.r.t. the input
 // video in the (B,T,3,H,W) layout (ncdhw = 0) or (B,3,T,H,W) (ncdhw = 1).
+static int dgrad0_impl(const void* dyp0, const void* wimg, float* out, const vd_tc_plan* plan, int B, int ncdhw, int accumulate,
+                       void* stream);
+
 extern "C" int vd_tc_dgrad0(const void* dyp0, const void* wimg, float* out, const vd_tc_plan* plan, int B, int ncdhw,
                             void* stream) {
+    return dgrad0_impl(dyp0, wimg, out, plan, B, ncdhw, 0, stream);
+}
+
+// accumulate != 0: out += result (the passes of a split-bf16 dgrad share one fp32 tensor)
+extern "C" int vd_tc_dgrad0_ex(const void* dyp0, const void* wimg, float* out, const vd_tc_plan* plan, int B, int ncdhw,
+                               int accumulate, void* stream) {
+    return dgrad0_impl(dyp0, wimg, out, plan, B, ncdhw, accumulate, stream);
+}
+
+static int dgrad0_impl(const void* dyp0, const void* wimg, float* out, const vd_tc_plan* plan, int B, int ncdhw, int accumulate,
+                       void* stream) {
     VD_REQUIRE(dyp0 && wimg && out && plan, "tc_dgrad0: NULL pointer");
     VD_REQUIRE(geo_supported(plan->T, plan->H) && B >= 0, "tc_dgrad0: unsupported geometry / batch");
     if (B == 0) return 0;
@@ -1959,7 +1985,7 @@ extern "C" int vd_tc_dgrad0(const void* dyp0, const void* wimg, float* out, cons
     uint32_t smem = 0;
     if (int rc = finalize_smem(p, (uint32_t)d.wimg_bytes, &smem)) return rc;
     p.pix = (const uint8_t*)dyp0; p.wimg = (const uint8_t*)wimg; p.item_index = nullptr;
-    p.epi.out = (uint8_t*)out; p.epi.T = plan->T; p.epi.n_items = B; p.epi.g = g; p.epi.ncdhw = ncdhw;
+    p.epi.out = (uint8_t*)out; p.epi.T = plan->T; p.epi.n_items = B; p.epi.g = g; p.epi.ncdhw = ncdhw; p.epi.accum = accumulate;
     return launch<EPI_DG0>(p, smem, (cudaStream_t)stream);
 }
 

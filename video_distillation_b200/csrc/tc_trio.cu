@@ -62,8 +62,14 @@ __global__ void pack_a2_kernel(const float* __restrict__ x, uint4* __restrict__ 
     }
 }
 
+// part 0: the value (rounded to bf16 by pack8); part 1: its bf16 residual v - bf16(v) — the split-bf16 dgrad packs both parts of
+// the fp32 gradient itself instead of materialising them as tensors
+__device__ __forceinline__ float dy_part(float v, int part) {
+    return part == 0 ? v : v - __uint_as_float((uint32_t)f2bf(v) << 16);
+}
+
 // gy (B, K, To, Ho, Wo) fp32 -> dY [video][nt NT][chunk K/8][col NC][8] bf16
-__global__ void pack_dy_kernel(const float* __restrict__ gy, uint4* __restrict__ dy, int64_t total, BwdGeo b) {
+__global__ void pack_dy_kernel(const float* __restrict__ gy, uint4* __restrict__ dy, int64_t total, BwdGeo b, int part) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int col = (int)(i % b.NC); int64_t q = i / b.NC;
         int chunk = (int)(q % (b.K / 8)); q /= (b.K / 8);
@@ -71,7 +77,7 @@ __global__ void pack_dy_kernel(const float* __restrict__ gy, uint4* __restrict__
         const float* p = gy + (vid * b.K + chunk * 8) * (int64_t)b.pixels + nt * b.NC + col;
         float v[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = __ldg(p + (int64_t)e * b.pixels);
+        for (int e = 0; e < 8; ++e) v[e] = dy_part(__ldg(p + (int64_t)e * b.pixels), part);
         dy[i] = pack8(v);
     }
 }
@@ -164,7 +170,7 @@ __global__ void pack_dg1_w_kernel(const float* __restrict__ w, uint16_t* __restr
 }
 
 // gy (B, 128, T, Ho1, Wo1) fp32 -> dYP [video][t_pad T+2][chunk 16][row RD][col PD] chunks; every cell is written
-__global__ void pack_dyp1_kernel(const float* __restrict__ gy, uint4* __restrict__ dyp, int64_t total, Dg1Geo d, int T) {
+__global__ void pack_dyp1_kernel(const float* __restrict__ gy, uint4* __restrict__ dyp, int64_t total, Dg1Geo d, int T, int part) {
     const int64_t So = (int64_t)T * d.Ho * d.Wo;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int c = (int)(i % d.PD); int64_t q = i / d.PD;
@@ -176,7 +182,7 @@ __global__ void pack_dyp1_kernel(const float* __restrict__ gy, uint4* __restrict
         if (t >= 0 && t < T && ho >= 0 && ho < d.Ho && wo >= 0 && wo < d.Wo) {
             const float* p = gy + (vid * 128 + chunk * 8) * So + ((int64_t)t * d.Ho + ho) * d.Wo + wo;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = __ldg(p + e * So);
+            for (int e = 0; e < 8; ++e) v[e] = dy_part(__ldg(p + e * So), part);
         }
         dyp[i] = pack8(v);
     }
@@ -202,7 +208,7 @@ __global__ void pack_dg0_w_kernel(const float* __restrict__ w, uint16_t* __restr
 }
 
 // gy (B, 64, T, Ho0, Wo0) fp32 -> dYP0 [video][t_pad T+2][chunk 8][row RD][col PD] chunks; every cell is written
-__global__ void pack_dyp0_kernel(const float* __restrict__ gy, uint4* __restrict__ dyp, int64_t total, Dg0Geo d, int T) {
+__global__ void pack_dyp0_kernel(const float* __restrict__ gy, uint4* __restrict__ dyp, int64_t total, Dg0Geo d, int T, int part) {
     const int64_t So = (int64_t)T * d.Ho * d.Wo;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int c = (int)(i % d.PD); int64_t q = i / d.PD;
@@ -214,7 +220,7 @@ __global__ void pack_dyp0_kernel(const float* __restrict__ gy, uint4* __restrict
         if (t >= 0 && t < T && ho >= 0 && ho < d.Ho && wo >= 0 && wo < d.Wo) {
             const float* p = gy + (vid * 64 + chunk * 8) * So + ((int64_t)t * d.Ho + ho) * d.Wo + wo;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = __ldg(p + e * So);
+            for (int e = 0; e < 8; ++e) v[e] = dy_part(__ldg(p + e * So), part);
         }
         dyp[i] = pack8(v);
     }
@@ -253,14 +259,27 @@ extern "C" int vd_tc_pack_act(int layer, const float* x, void* packed, const vd_
 }
 
 // gy fp32 NCDHW (B, Cout, To, Ho, Wo) of conv `layer` -> packed dY operand of vd_tc_bwd_gemm
+static int pack_dy_impl(int layer, const float* gy, void* dy, const vd_tc_plan* plan, int B, int part, void* stream);
+
 extern "C" int vd_tc_pack_dy(int layer, const float* gy, void* dy, const vd_tc_plan* plan, int B, void* stream) {
+    return pack_dy_impl(layer, gy, dy, plan, B, 0, stream);
+}
+
+// part = 0: bf16(gy); part = 1: bf16(gy - bf16(gy)) — the two operand parts of a split-bf16 dgrad, made inside the packer
+// (vd_tc_pack_dy_part / vd_tc_pack_dyp1_part / vd_tc_pack_dyp0_part)
+extern "C" int vd_tc_pack_dy_part(int layer, const float* gy, void* dy, const vd_tc_plan* plan, int B, int part, void* stream) {
+    VD_REQUIRE(part == 0 || part == 1, "tc_pack_dy_part: part must be 0 or 1");
+    return pack_dy_impl(layer, gy, dy, plan, B, part, stream);
+}
+
+static int pack_dy_impl(int layer, const float* gy, void* dy, const vd_tc_plan* plan, int B, int part, void* stream) {
     VD_REQUIRE(gy && dy && plan, "tc_pack_dy: NULL pointer");
     VD_REQUIRE(layer >= 0 && layer <= 2 && geo_supported(plan->T, plan->H), "tc_pack_dy: bad layer / geometry");
     if (B <= 0) return 0;
     const Geo g = make_geo(plan->T, plan->H);
     const BwdGeo b = make_bwd_geo(g, layer);
     const int64_t total = (int64_t)B * b.NT * (b.K / 8) * b.NC;
-    pack_dy_kernel<<<grid_of(total), 256, 0, (cudaStream_t)stream>>>(gy, (uint4*)dy, total, b);
+    pack_dy_kernel<<<grid_of(total), 256, 0, (cudaStream_t)stream>>>(gy, (uint4*)dy, total, b, part);
     return check_launch("tc_pack_dy");
 }
 
@@ -333,13 +352,21 @@ extern "C" int vd_tc_pack_dgrad1_weights(const float* w_l1, void* wimg0, void* w
 }
 
 // gy fp32 NCDHW (B, 128, T, Ho1, Wo1) -> padded planar dY of conv 1 (every cell written, halo zeros included)
+static int pack_dyp1_impl(const float* gy, void* dyp, const vd_tc_plan* plan, int B, int part, void* stream);
 extern "C" int vd_tc_pack_dyp1(const float* gy, void* dyp, const vd_tc_plan* plan, int B, void* stream) {
+    return pack_dyp1_impl(gy, dyp, plan, B, 0, stream);
+}
+extern "C" int vd_tc_pack_dyp1_part(const float* gy, void* dyp, const vd_tc_plan* plan, int B, int part, void* stream) {
+    VD_REQUIRE(part == 0 || part == 1, "tc_pack_dyp1_part: part must be 0 or 1");
+    return pack_dyp1_impl(gy, dyp, plan, B, part, stream);
+}
+static int pack_dyp1_impl(const float* gy, void* dyp, const vd_tc_plan* plan, int B, int part, void* stream) {
     VD_REQUIRE(gy && dyp && plan && geo_supported(plan->T, plan->H), "tc_pack_dyp1: bad argument");
     if (B <= 0) return 0;
     const Geo g = make_geo(plan->T, plan->H);
     const Dg1Geo d = make_dg1_geo(g);
     const int64_t total = (int64_t)B * (d.video_bytes / 16);
-    pack_dyp1_kernel<<<grid_of(total), 256, 0, (cudaStream_t)stream>>>(gy, (uint4*)dyp, total, d, g.T);
+    pack_dyp1_kernel<<<grid_of(total), 256, 0, (cudaStream_t)stream>>>(gy, (uint4*)dyp, total, d, g.T, part);
     return check_launch("tc_pack_dyp1");
 }
 
@@ -359,12 +386,20 @@ extern "C" int vd_tc_pack_dgrad0_weights(const float* w_l0, void* wimg, void* st
 }
 
 // gy fp32 NCDHW (B, 64, T, Ho0, Wo0) -> padded planar dY of conv 0 (every cell written, halo zeros included)
+static int pack_dyp0_impl(const float* gy, void* dyp, const vd_tc_plan* plan, int B, int part, void* stream);
 extern "C" int vd_tc_pack_dyp0(const float* gy, void* dyp, const vd_tc_plan* plan, int B, void* stream) {
+    return pack_dyp0_impl(gy, dyp, plan, B, 0, stream);
+}
+extern "C" int vd_tc_pack_dyp0_part(const float* gy, void* dyp, const vd_tc_plan* plan, int B, int part, void* stream) {
+    VD_REQUIRE(part == 0 || part == 1, "tc_pack_dyp0_part: part must be 0 or 1");
+    return pack_dyp0_impl(gy, dyp, plan, B, part, stream);
+}
+static int pack_dyp0_impl(const float* gy, void* dyp, const vd_tc_plan* plan, int B, int part, void* stream) {
     VD_REQUIRE(gy && dyp && plan && geo_supported(plan->T, plan->H), "tc_pack_dyp0: bad argument");
     if (B <= 0) return 0;
     const Geo g = make_geo(plan->T, plan->H);
     const Dg0Geo d = make_dg0_geo(g);
     const int64_t total = (int64_t)B * (d.video_bytes / 16);
-    pack_dyp0_kernel<<<grid_of(total), 256, 0, (cudaStream_t)stream>>>(gy, (uint4*)dyp, total, d, g.T);
+    pack_dyp0_kernel<<<grid_of(total), 256, 0, (cudaStream_t)stream>>>(gy, (uint4*)dyp, total, d, g.T, part);
     return check_launch("tc_pack_dyp0");
 }

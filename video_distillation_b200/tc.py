@@ -69,6 +69,7 @@ class TcConvNet3D:
         self.wt2 = torch.empty(p.wt2_bytes, **u8)
         self._bwd_ready = False
         self._fp32_w = None
+        self._split_bwd_w = None    # per layer: (dgrad weight images of wh, of wl), packed on the first split backward
         self.bwd_chunk = 64
         sz = (ctypes.c_int64 * 3)()
         _lib.check(_lib.lib().vd_tc_dgrad1_sizes(ctypes.byref(p), sz), 'vd_tc_dgrad1_sizes')
@@ -98,6 +99,7 @@ class TcConvNet3D:
         self.b0, self.b1, self.b2 = (t.detach().contiguous().float() for t in (b0, b1, b2))
         self._fp32_w = ws
         self._bwd_ready = False
+        self._split_bwd_w = None
         return self
 
     def _prepare_bwd(self):
@@ -169,17 +171,21 @@ class TcConvNet3D:
         return dvideo
 
     def _embed_backward_split(self, g_emb, codes):
-        """Backward of the f16x3 mode: route-scatter (fp32) + tensor-core dgrad of each conv evaluated as split-bf16,
+        """Backward of the f16x3 modes: route-scatter (fp32) + tensor-core dgrad of each conv evaluated as split-bf16,
         gx = dgrad(gh, wh) + dgrad(gh, wl) + dgrad(gl, wh) with g = gh + gl, w = wh + wl (bf16 parts, fp32 accumulate):
-        ~16 significand bits per operand, no range limits on the gradient.  Returns d video (B,T,3,H,W)."""
+        ~16 significand bits per operand, no range limits on the gradient.  The gradient parts are made inside the packers,
+        the weight images of wh / wl are packed once per network, and the column-free dgrads of conv 1 / conv 0 accumulate
+        their three passes into one fp32 tensor (conv 0 straight into the (B,T,3,H,W) result).  Returns d video."""
         from . import ops
         from .tc_trio import TcTrio
         if self._trio is None:
             self._trio = TcTrio(self.T, self.H, self.W, self.device)
         trio, p = self._trio, self.plan
-        ws = self._fp32_w
-        wh = [w.to(torch.bfloat16).float() for w in ws]
-        wl = [w - h for w, h in zip(ws, wh)]
+        if self._split_bwd_w is None:
+            ws = self._fp32_w
+            wh = [w.to(torch.bfloat16).float() for w in ws]
+            wl = [w - h for w, h in zip(ws, wh)]
+            self._split_bwd_w = [(trio.pack_dgrad_weights(l, wh[l]), trio.pack_dgrad_weights(l, wl[l])) for l in range(3)]
         g_emb = g_emb.contiguous().float()
         B = g_emb.shape[0]
         out = torch.empty(B, self.T, 3, self.H, self.W, dtype=torch.float32, device=self.device)
@@ -191,11 +197,19 @@ class TcConvNet3D:
             g = g_emb[s:e].view(e - s, 128, p.T3p, p.H3p, p.W3p)
             for layer in (2, 1, 0):
                 gy = ops.route_scatter_raw(g, codes[layer][s:e], (e - s, cout[layer]) + tuple(ext_conv[layer]), pool[layer])
-                gh = gy.to(torch.bfloat16).float()
-                g = trio.dgrad(layer, gh, wh[layer])
-                g += trio.dgrad(layer, gh, wl[layer])
-                g += trio.dgrad(layer, gy - gh, wh[layer])
-            out[s:e] = g.permute(0, 2, 1, 3, 4)
+                pk_h, pk_l = self._split_bwd_w[layer]
+                if layer == 0:
+                    # conv 0: the three passes accumulate in the kernel's epilogue, straight into the (B,T,3,H,W) result
+                    g = trio.dgrad(0, gy, None, part=0, wpack=pk_h, out=out[s:e], ncdhw=False)
+                    trio.dgrad(0, gy, None, part=0, wpack=pk_l, out=g, accumulate=True, ncdhw=False)
+                    trio.dgrad(0, gy, None, part=1, wpack=pk_h, out=g, accumulate=True, ncdhw=False)
+                else:
+                    # conv 1 / conv 2: separate outputs added by elementwise launches (conv 1's epilogue owns one (ci, pw)
+                    # plane per lane: a read-modify-write there is 14 dependent uncoalesced loads per row and doubles the
+                    # kernel's time, measured)
+                    g = trio.dgrad(layer, gy, None, part=0, wpack=pk_h)
+                    g += trio.dgrad(layer, gy, None, part=0, wpack=pk_l)
+                    g += trio.dgrad(layer, gy, None, part=1, wpack=pk_h)
         return out
 
     def embed_autograd(self, video):

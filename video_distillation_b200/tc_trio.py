@@ -91,47 +91,79 @@ class TcTrio:
             self._conv(layer, src, wh, y, B, True)
         return y
 
-    def dgrad(self, layer, gy, w):
-        p, lib, B = self.plan, _lib.lib(), int(gy.shape[0])
-        cin, cout, ext = self.layers[layer]
+    def pack_dgrad_weights(self, layer, w):
+        """fp32 OIDHW weights of feature conv `layer` -> the weight image(s) of its dgrad kernel (fresh tensors, so that the
+        images of several weight parts can be cached side by side)."""
+        p, lib = self.plan, _lib.lib()
+        u8 = dict(dtype=torch.uint8, device=self.device)
+        plan, st = ctypes.byref(p), _lib.stream()
         if layer == 0 and self.direct_dgrad0:
-            # column-free dgrad of conv 0 (tc_layout.h: Dg0Geo): pixels on M, fp32 accumulators to (B,3,T,H,W)
             sz = (ctypes.c_int64 * 2)()
-            _lib.check(lib.vd_tc_dgrad0_sizes(ctypes.byref(p), sz), 'vd_tc_dgrad0_sizes')
-            wimg = self._buf('dg0_w', sz[1])
-            dyp = self._buf('dyp0', B * sz[0])
-            plan, st = ctypes.byref(p), _lib.stream()
+            _lib.check(lib.vd_tc_dgrad0_sizes(plan, sz), 'vd_tc_dgrad0_sizes')
+            wimg = torch.empty(int(sz[1]), **u8)
             _lib.check(lib.vd_tc_pack_dgrad0_weights(_lib.ptr(w), _lib.ptr(wimg), st), 'vd_tc_pack_dgrad0_weights')
-            _lib.check(lib.vd_tc_pack_dyp0(_lib.ptr(gy), _lib.ptr(dyp), plan, B, st), 'vd_tc_pack_dyp0')
-            gx = torch.empty(B, cin, *ext, dtype=torch.float32, device=self.device)
-            _lib.check(lib.vd_tc_dgrad0(_lib.ptr(dyp), _lib.ptr(wimg), _lib.ptr(gx), plan, B, 1, st), 'vd_tc_dgrad0')
-            return gx
+            return (wimg,)
         if layer == 1 and self.direct_dgrad1:
-            # column-free dgrad of conv 1 (tc_layout.h: Dg1Geo): fp32 accumulators go straight to the NCDHW gradient
             sz = (ctypes.c_int64 * 3)()
-            _lib.check(lib.vd_tc_dgrad1_sizes(ctypes.byref(p), sz), 'vd_tc_dgrad1_sizes')
-            w0, w1 = self._buf('dg1_w0', sz[1]), self._buf('dg1_w1', sz[2])
-            dyp = self._buf('dyp1', B * sz[0])
-            plan, st = ctypes.byref(p), _lib.stream()
+            _lib.check(lib.vd_tc_dgrad1_sizes(plan, sz), 'vd_tc_dgrad1_sizes')
+            w0, w1 = torch.empty(int(sz[1]), **u8), torch.empty(int(sz[2]), **u8)
             _lib.check(lib.vd_tc_pack_dgrad1_weights(_lib.ptr(w), _lib.ptr(w0), _lib.ptr(w1), plan, st), 'vd_tc_pack_dgrad1_weights')
-            _lib.check(lib.vd_tc_pack_dyp1(_lib.ptr(gy), _lib.ptr(dyp), plan, B, st), 'vd_tc_pack_dyp1')
-            gx = torch.empty(B, cin, *ext, dtype=torch.float32, device=self.device)
-            _lib.check(lib.vd_tc_dgrad1(_lib.ptr(dyp), _lib.ptr(w0), _lib.ptr(w1), None, _lib.ptr(gx), plan, B, st), 'vd_tc_dgrad1')
-            return gx
-        wt = self._buf(f'wt{layer}', (p.wt0_bytes, p.wt1_bytes, p.wt2_bytes)[layer])
+            return (w0, w1)
+        wt = torch.empty(int((p.wt0_bytes, p.wt1_bytes, p.wt2_bytes)[layer]), **u8)
         ws = [None, None, None]
         imgs = [None, None, None]
         ws[layer], imgs[layer] = w, wt
         _lib.check(lib.vd_tc_pack_weights_bwd(_lib.ptr(ws[0]), _lib.ptr(ws[1]), _lib.ptr(ws[2]), _lib.ptr(imgs[0]), _lib.ptr(imgs[1]),
-                                              _lib.ptr(imgs[2]), _lib.stream()), 'vd_tc_pack_weights_bwd')
+                                              _lib.ptr(imgs[2]), st), 'vd_tc_pack_weights_bwd')
+        return (wt,)
+
+    def dgrad(self, layer, gy, w, part=0, wpack=None, out=None, accumulate=False, ncdhw=True):
+        """gx = dgrad(part(gy), w) of feature conv `layer`.  part: 0 = bf16(gy), 1 = bf16(gy - bf16(gy)) (made inside the packer);
+        wpack: cached pack_dgrad_weights(layer, w); out / accumulate: write (or add) into an existing fp32 tensor — the three
+        passes of a split-bf16 dgrad then share one tensor; ncdhw=False (layer 0 only): out is (B,T,3,H,W)."""
+        p, lib, B = self.plan, _lib.lib(), int(gy.shape[0])
+        cin, cout, ext = self.layers[layer]
+        if wpack is None:
+            wpack = self.pack_dgrad_weights(layer, w)
+        plan, st = ctypes.byref(p), _lib.stream()
+        assert ncdhw or layer == 0
+        if layer == 0 and self.direct_dgrad0:
+            # column-free dgrad of conv 0 (tc_layout.h: Dg0Geo): pixels on M, fp32 accumulators to (B,3,T,H,W) / (B,T,3,H,W)
+            sz = (ctypes.c_int64 * 2)()
+            _lib.check(lib.vd_tc_dgrad0_sizes(plan, sz), 'vd_tc_dgrad0_sizes')
+            dyp = self._buf('dyp0', B * sz[0])
+            _lib.check(lib.vd_tc_pack_dyp0_part(_lib.ptr(gy), _lib.ptr(dyp), plan, B, int(part), st), 'vd_tc_pack_dyp0_part')
+            if out is None:
+                assert not accumulate
+                out = torch.empty((B, cin, *ext) if ncdhw else (B, ext[0], cin, ext[1], ext[2]), dtype=torch.float32, device=self.device)
+            _lib.check(lib.vd_tc_dgrad0_ex(_lib.ptr(dyp), _lib.ptr(wpack[0]), _lib.ptr(out), plan, B, 1 if ncdhw else 0, int(accumulate), st),
+                       'vd_tc_dgrad0_ex')
+            return out
+        if layer == 1 and self.direct_dgrad1:
+            # column-free dgrad of conv 1 (tc_layout.h: Dg1Geo): fp32 accumulators go straight to the NCDHW gradient
+            sz = (ctypes.c_int64 * 3)()
+            _lib.check(lib.vd_tc_dgrad1_sizes(plan, sz), 'vd_tc_dgrad1_sizes')
+            dyp = self._buf('dyp1', B * sz[0])
+            _lib.check(lib.vd_tc_pack_dyp1_part(_lib.ptr(gy), _lib.ptr(dyp), plan, B, int(part), st), 'vd_tc_pack_dyp1_part')
+            if out is None:
+                assert not accumulate
+                out = torch.empty(B, cin, *ext, dtype=torch.float32, device=self.device)
+            _lib.check(lib.vd_tc_dgrad1_plain(_lib.ptr(dyp), _lib.ptr(wpack[0]), _lib.ptr(wpack[1]), _lib.ptr(out), plan, B, int(accumulate), st),
+                       'vd_tc_dgrad1_plain')
+            return out
         dy = self._buf('dy', B * (p.dy0_bytes_per_video, p.dy1_bytes_per_video, p.dy2_bytes_per_video)[layer])
         f32 = 1 if self.col_fp32 else 0      # fp32 column buffers: no bf16 rounding between the GEMM and the tap sum
         col = self._buf('col', B * (p.col0_bytes_per_video, p.col1_bytes_per_video, p.col2_bytes_per_video)[layer] * (2 if f32 else 1))
-        plan, st = ctypes.byref(p), _lib.stream()
-        _lib.check(lib.vd_tc_pack_dy(layer, _lib.ptr(gy), _lib.ptr(dy), plan, B, st), 'vd_tc_pack_dy')
-        _lib.check(lib.vd_tc_bwd_gemm_ex(layer, _lib.ptr(dy), _lib.ptr(wt), _lib.ptr(col), plan, B, f32, st), 'vd_tc_bwd_gemm_ex')
+        _lib.check(lib.vd_tc_pack_dy_part(layer, _lib.ptr(gy), _lib.ptr(dy), plan, B, int(part), st), 'vd_tc_pack_dy_part')
+        _lib.check(lib.vd_tc_bwd_gemm_ex(layer, _lib.ptr(dy), _lib.ptr(wpack[0]), _lib.ptr(col), plan, B, f32, st), 'vd_tc_bwd_gemm_ex')
         gx = torch.empty(B, cin, *ext, dtype=torch.float32, device=self.device)
         _lib.check(lib.vd_tc_bwd_col2im_plain(layer, _lib.ptr(col), _lib.ptr(gx), plan, B, f32, st), 'vd_tc_bwd_col2im_plain')
+        if out is not None:
+            if accumulate:
+                out += gx
+            else:
+                out.copy_(gx)
+            return out
         return gx
 
     def wgrad(self, layer, x, gy):
