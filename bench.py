@@ -719,7 +719,7 @@ def run_ours(args):
     peak = float(peaks.get('bf16_tflops_sustained', peaks.get('bf16_tflops', 1400.0)))
     split = args.precision.startswith('f16x3')
     traffic = None
-    tpath = os.path.join(ROOT, 'profiles', 'r02_traffic.json' if split else 'r01_traffic.json')
+    tpath = os.path.join(ROOT, 'profiles', ('r02c_traffic.json' if real_products == 2 else 'r02_traffic.json') if split else 'r01_traffic.json')
     if os.path.exists(tpath) and (T, HW) == (16, 112):      # DRAM bytes per launch from the committed ncu --set full capture (U shape)
         tj = json.load(open(tpath))['dram_bytes_per_video']['conv1']
         traffic = (tj['read'] + tj['write']) * layer_videos[1] / max(1, layer_launches[1])
