@@ -143,14 +143,17 @@ __global__ void __launch_bounds__(256) col2im_kernel(const T* __restrict__ colbu
         const int pix0 = (to * b.Ho + k.ho0) * b.Wo;
         // bf16 columns whose staged pixel range is one 16-byte aligned run inside a column tile: 8 elements per load
         const int nt0 = (int)__umulhi((uint32_t)pix0, b.nc_magic), col0 = pix0 - nt0 * b.NC;
-        if (sizeof(T) == 2 && (k.npix & 7) == 0 && (col0 & 7) == 0 && (b.NC & 7) == 0 && col0 + k.npix <= b.NC && (pitch & 7) == 0) {
-            const int v8 = k.npix >> 3;
+        // columns whose staged pixel range is one 16-byte aligned run inside a column tile: VE = 16 / sizeof(T) elements per load
+        // (8 bf16 or 4 fp32: the fp32 columns of the split-bf16 backward were staged one element at a time — 0.13 of the copy rate)
+        constexpr int VE = 16 / (int)sizeof(T);
+        if ((k.npix % VE) == 0 && (col0 % VE) == 0 && (b.NC % VE) == 0 && col0 + k.npix <= b.NC && (pitch % VE) == 0) {
+            const int v8 = k.npix / VE;
             for (int i = threadIdx.x; i < cib * 49 * v8; i += blockDim.x) {
                 const int row = i / v8, jv = i - row * v8;
                 const int cl = row / 49, tap = row - cl * 49;
                 const int r = (k.ci0 + cl) * 147 + kt * 49 + tap;
                 const uint4 v = __ldg(reinterpret_cast<const uint4*>(colv + (((int64_t)nt0 * b.NU + (r >> 7)) * 128 + (r & 127)) * b.NC + col0) + jv);
-                *reinterpret_cast<uint4*>(smT + row * pitch + jv * 8) = v;
+                *reinterpret_cast<uint4*>(smT + row * pitch + jv * VE) = v;
             }
         } else
         for (int i = threadIdx.x; i < cib * 49 * k.npix; i += blockDim.x) {
