@@ -31,5 +31,20 @@ for i in range(3):
     if rank == 0:
         print(f'MTT iteration {i} [{precision}]: syn_steps={syn_steps} batch_syn={C} -> {time.perf_counter() - t0:.3f} s, grand loss {loss.item():.6f}, '
               f'world {world}, peak mem {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB', flush=True)
+if os.environ.get('VD_MTT_PROFILE') and rank == 0:      # kernel-level breakdown of one iteration (CUPTI via torch.profiler)
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        tr.step(start, target, net_seed=1)
+        torch.cuda.synchronize()
+    dur = {}
+    for e in prof.events():
+        if e.device_type == torch.autograd.DeviceType.CUDA:
+            d = dur.setdefault(e.name[:100], [0, 0.0])
+            d[0] += 1
+            d[1] += (e.time_range.end - e.time_range.start) * 1e-3
+    tot = sum(v[1] for v in dur.values())
+    print(f'sum of kernel time {tot:.1f} ms over {sum(v[0] for v in dur.values())} launches')
+    for k, v in sorted(dur.items(), key=lambda kv: -kv[1][1])[:28]:
+        print(f'{v[1]:9.2f} ms {100 * v[1] / tot:5.1f}% {v[0]:5d}x  {k}')
 if world > 1:
     dist.destroy_process_group()

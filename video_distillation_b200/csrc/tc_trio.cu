@@ -116,6 +116,56 @@ __global__ void wgrad_im2col_kernel(const float* __restrict__ x, uint4* __restri
     }
 }
 
+// The same operand, one block per (column tile, stage) = one 64 KiB GEMM stage.  The kernel above gives a thread 8 consecutive
+// pixels of ONE column: neighbouring lanes read neighbouring taps of different rows / frames / channels (5-10 sectors per
+// warp load, 8 loads per 16-byte store) and it reached 0.84 TB/s — 40 % of an MTT iteration.  Here the lanes of a warp are 32
+// CONSECUTIVE PIXELS of one column (stride-2 floats: 2-3 sectors per warp load, taps of the same pixel hit in L1), a thread walks
+// its 128 columns incrementally (no divisions in the loop), the tile is assembled in shared memory ([chunk 16][col 256 + 1 pad]
+// x 16 B: conflict-free 2-byte stores) and leaves with coalesced 16-byte stores.
+__global__ void __launch_bounds__(256) wgrad_im2col_tile_kernel(const float* __restrict__ x, uint4* __restrict__ xcol, BwdGeo b,
+                                                                int64_t P, int64_t n_stage) {
+    extern __shared__ uint4 im2col_tile[];                       // [16][257]
+    uint16_t* tile16 = reinterpret_cast<uint16_t*>(im2col_tile);
+    const int64_t stage = blockIdx.x;
+    const int ntile = blockIdx.y;
+    const int p = threadIdx.x & 127, half = threadIdx.x >> 7;
+    const int64_t Si = (int64_t)b.Ti * b.Hi * b.Wi;
+    const int64_t k = stage * 128 + p;
+    const bool valid = k < P;
+    int wo = 0, ho = 0, to = 0;
+    int64_t vid = 0;
+    if (valid) {
+        wo = (int)(k % b.Wo); int64_t r = k / b.Wo;
+        ho = (int)(r % b.Ho); r /= b.Ho;
+        to = (int)(r % b.To); vid = r / b.To;
+    }
+    const float* xv = x + vid * b.Cin * Si;
+    const int n0 = ntile * 256 + half * 128;
+    int ci = n0 / 147, tap = n0 - ci * 147;
+    int kt = tap / 49, kh = (tap / 7) % 7, kw = tap % 7;
+    uint16_t* dst = tile16 + (((p >> 3) * 257 + half * 128) * 8 + (p & 7));
+    const int ncols = b.Cin * 147;
+    // 16 columns per round: all 16 loads are issued before the first conversion (the loop is bound by load latency, not bandwidth)
+    for (int j0 = 0; j0 < 128; j0 += 16) {
+        float v[16];
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) {
+            v[jj] = 0.f;
+            if (valid && n0 + j0 + jj < ncols) {
+                const int t = to + kt - 1, h = 2 * ho + kh - 3, w = 2 * wo + kw - 3;
+                if ((unsigned)t < (unsigned)b.Ti && (unsigned)h < (unsigned)b.Hi && (unsigned)w < (unsigned)b.Wi)
+                    v[jj] = __ldg(xv + ci * Si + ((int64_t)t * b.Hi + h) * b.Wi + w);
+            }
+            if (++kw == 7) { kw = 0; if (++kh == 7) { kh = 0; if (++kt == 3) { kt = 0; ++ci; } } }
+        }
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) dst[(j0 + jj) * 8] = f2bf(v[jj]);
+    }
+    __syncthreads();
+    uint4* out = xcol + ((int64_t)ntile * n_stage + stage) * (16 * 256);
+    for (int idx = threadIdx.x; idx < 16 * 256; idx += 256) out[idx] = im2col_tile[(idx >> 8) * 257 + (idx & 255)];
+}
+
 __global__ void wgrad_gyimg_kernel(const float* __restrict__ gy, uint4* __restrict__ img, int64_t total, BwdGeo b, int64_t P) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int row = (int)(i % 128); int64_t q = i / 128;
@@ -314,7 +364,14 @@ extern "C" int vd_tc_wgrad_pack(int layer, const float* x, const float* gy, void
     const int64_t P = (int64_t)B * b.pixels, n_stage = w[0] * w[1];
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t total_x = w[2] * n_stage * 16 * 256;
-    wgrad_im2col_kernel<<<grid_of(total_x), 256, 0, s>>>(x, (uint4*)xcol, total_x, b, P, n_stage);
+    if (n_stage < (1ll << 31) && w[2] <= 65535) {
+        static bool configured = false;
+        const size_t smem = (size_t)16 * 257 * 16;
+        if (!configured) { cudaFuncSetAttribute(wgrad_im2col_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = true; }
+        wgrad_im2col_tile_kernel<<<dim3((unsigned)n_stage, (unsigned)w[2], 1), 256, smem, s>>>(x, (uint4*)xcol, b, P, n_stage);
+    } else {
+        wgrad_im2col_kernel<<<grid_of(total_x), 256, 0, s>>>(x, (uint4*)xcol, total_x, b, P, n_stage);
+    }
     if (int e = check_launch("tc_wgrad_im2col")) return e;
     const int64_t total_g = n_stage * 8 * 2 * 128;
     wgrad_gyimg_kernel<<<grid_of(total_g), 256, 0, s>>>(gy, (uint4*)gyimg, total_g, b, P);
