@@ -268,3 +268,23 @@ def test_two_product_mode_layers_embed_and_means(T, HW):
     es_full, codes_full = full.embed(syn, want_codes=True)
     assert torch.equal(er2, emb[idx]) and torch.equal(es, es_full)
     assert all(torch.equal(a, b) for a, b in zip(codes, codes_full))
+
+
+@pytest.mark.parametrize('T,HW,B', [(4, 112, 3), (12, 112, 2), (16, 112, 5), (8, 64, 9), (16, 64, 3), (24, 64, 2), (32, 64, 5)])
+def test_two_product_geometry_sweep_against_the_fp32_oracle(T, HW, B):
+    """Every supported (frames, size) geometry in the two-product mode (hi-only operands, 2 or 4 frames per conv-1 tile, one or
+    two row pairs per conv-0 band, both epilogue groups) against the fp32 CPU oracle and against the three-product network."""
+    net, ws = make_net(T, HW, seed=T + HW, reference_init=True, real_products=2)
+    full, _ = make_net(T, HW, seed=T + HW, reference_init=True)
+    video = torch.randn(B, T, 3, HW, HW, generator=torch.Generator().manual_seed(B + 1))
+    emb = net.embed(video.cuda(), frozen=True)
+    from oracle import convnet3d_embed
+    e32 = convnet3d_embed(params_of(ws), video)
+    assert torch.isfinite(emb).all()
+    worst = max(rel(emb[i], e32[i]) for i in range(B))
+    assert worst < 1e-3, (T, HW, B, worst)
+    assert rel(emb, full.embed(video.cuda())) < 1e-3
+    # the resident (index-addressed) path gives the same bits
+    x0 = net.pack_dataset(video.cuda())
+    idx = torch.arange(B - 1, -1, -1, device='cuda')
+    assert torch.equal(net.embed_resident(x0, idx), emb[idx])
