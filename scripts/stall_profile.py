@@ -12,7 +12,7 @@ from video_distillation_b200 import _lib  # noqa: E402
 from video_distillation_b200.networks import ConvNet3D  # noqa: E402
 from video_distillation_b200.tc import TcConvNet3D  # noqa: E402
 
-B, T, HW = 592, 16, 112
+B, T, HW = int(os.environ.get('B', 592)), int(os.environ.get('T', 16)), int(os.environ.get('HW', 112))
 torch.manual_seed(0)
 net = ConvNet3D(3, 50, 128, 3, 'relu', 'none', 'maxpooling', T, (HW, HW)).cuda()
 SPLIT = len(sys.argv) > 1 and sys.argv[1] in ('x3', 'x2')
