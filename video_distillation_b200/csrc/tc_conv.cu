@@ -1994,6 +1994,7 @@ static int dgrad0_impl(const void* dyp0, const void* wimg, float* out, const vd_
 // operand (4 KiB tiles streamed through the weight ring, one K = 16 pixel step each), the im2col columns are the
 // N operand (one 64 KiB stage = 128 pixels x 256 columns per bulk copy).
 extern "C" int vd_tc_wgrad_plan(int layer, const vd_tc_plan* plan, int B, int64_t* out);
+extern "C" int vd_tc_wgrad_kt_mode(int layer);
 
 extern "C" int vd_tc_wgrad_gemm(int layer, const void* xcol, const void* gyimg, float* raw, const vd_tc_plan* plan, int B,
                                 void* stream) {
@@ -2020,9 +2021,17 @@ extern "C" int vd_tc_wgrad_gemm(int layer, const void* xcol, const void* gyimg, 
     uint32_t smem = 0;
     if (int rc = finalize_smem(p, (uint32_t)p.G * p.RW * kWeightTileBytes, &smem, true)) return rc;
     const Geo g = make_geo(plan->T, plan->H);
-    p.pix = (const uint8_t*)xcol; p.wimg = (const uint8_t*)gyimg; p.item_index = nullptr;
-    p.epi.raw = raw; p.epi.raw_bf16 = 0; p.epi.T = plan->T; p.epi.n_items = B; p.epi.g = g;
-    return launch<EPI_RAW>(p, smem, (cudaStream_t)stream);
+    p.pix = (const uint8_t*)xcol; p.item_index = nullptr;
+    p.epi.raw_bf16 = 0; p.epi.T = plan->T; p.epi.n_items = B; p.epi.g = g;
+    // kt-split mode (tc_trio.cu): one GEMM per temporal tap over the same columns, against the frame-shifted gy image of that tap
+    const int n_kt = vd_tc_wgrad_kt_mode(layer) ? 3 : 1;
+    const int64_t img_bytes = (int64_t)splits * sps * 8 * kWeightTileBytes, raw_floats = (int64_t)ntiles * splits * 128 * 256;
+    for (int kt = 0; kt < n_kt; ++kt) {
+        p.wimg = (const uint8_t*)gyimg + kt * img_bytes;
+        p.epi.raw = raw + kt * raw_floats;
+        if (int rc = launch<EPI_RAW>(p, smem, (cudaStream_t)stream)) return rc;
+    }
+    return 0;
 }
 
 #ifdef VD_PROBE   // bring-up / tuning entry points: only in scripts/libvd_b200_probe.so (scripts/_probe_lib.py), never in the product library

@@ -122,8 +122,10 @@ __global__ void wgrad_im2col_kernel(const float* __restrict__ x, uint4* __restri
 // CONSECUTIVE PIXELS of one column (stride-2 floats: 2-3 sectors per warp load, taps of the same pixel hit in L1), a thread walks
 // its 128 columns incrementally (no divisions in the loop), the tile is assembled in shared memory ([chunk 16][col 256 + 1 pad]
 // x 16 B: conflict-free 2-byte stores) and leaves with coalesced 16-byte stores.
+// kt_split != 0 ("temporal taps on the gy side", see wgrad_gyimg_tile_kernel): columns n = ci*49 + (kh*7 + kw) of the CENTRE temporal
+// tap only, and the GEMM's K index runs over the pixels (video, t, ho, wo) of the INPUT frames t — a third of the columns.
 __global__ void __launch_bounds__(256) wgrad_im2col_tile_kernel(const float* __restrict__ x, uint4* __restrict__ xcol, BwdGeo b,
-                                                                int64_t P, int64_t n_stage) {
+                                                                int64_t P, int64_t n_stage, int kt_split) {
     extern __shared__ uint4 im2col_tile[];                       // [16][257]
     uint16_t* tile16 = reinterpret_cast<uint16_t*>(im2col_tile);
     const int64_t stage = blockIdx.x;
@@ -141,10 +143,11 @@ __global__ void __launch_bounds__(256) wgrad_im2col_tile_kernel(const float* __r
     }
     const float* xv = x + vid * b.Cin * Si;
     const int n0 = ntile * 256 + half * 128;
-    int ci = n0 / 147, tap = n0 - ci * 147;
-    int kt = tap / 49, kh = (tap / 7) % 7, kw = tap % 7;
+    const int tpc = kt_split ? 49 : 147;                         // taps per input channel
+    int ci = n0 / tpc, tap = n0 - ci * tpc;
+    int kt = kt_split ? 1 : tap / 49, kh = (tap / 7) % 7, kw = tap % 7;
     uint16_t* dst = tile16 + (((p >> 3) * 257 + half * 128) * 8 + (p & 7));
-    const int ncols = b.Cin * 147;
+    const int ncols = b.Cin * tpc;
     // 16 columns per round: all 16 loads are issued before the first conversion (the loop is bound by load latency, not bandwidth)
     for (int j0 = 0; j0 < 128; j0 += 16) {
         float v[16];
@@ -156,7 +159,7 @@ __global__ void __launch_bounds__(256) wgrad_im2col_tile_kernel(const float* __r
                 if ((unsigned)t < (unsigned)b.Ti && (unsigned)h < (unsigned)b.Hi && (unsigned)w < (unsigned)b.Wi)
                     v[jj] = __ldg(xv + ci * Si + ((int64_t)t * b.Hi + h) * b.Wi + w);
             }
-            if (++kw == 7) { kw = 0; if (++kh == 7) { kh = 0; if (++kt == 3) { kt = 0; ++ci; } } }
+            if (++kw == 7) { kw = 0; if (++kh == 7) { kh = 0; if (kt_split) ++ci; else if (++kt == 3) { kt = 0; ++ci; } } }
         }
 #pragma unroll
         for (int jj = 0; jj < 16; ++jj) dst[(j0 + jj) * 8] = f2bf(v[jj]);
@@ -186,14 +189,66 @@ __global__ void wgrad_gyimg_kernel(const float* __restrict__ gy, uint4* __restri
     }
 }
 
+// gy image of the kt-split wgrad, one block per 128 pixels (= 8 K-steps = 32 KiB of the image), blockIdx.y = kt:
+//   img_kt[k = (video, t, ho, wo)][co] = gy[co, video, t - kt + 1, ho, wo]   (zero when that output frame does not exist)
+// so that  gw[co, ci, kt, kh, kw] = sum_k img_kt[k][co] * xcol[k][ci*49 + kh*7 + kw]:  the temporal tap becomes a FRAME SHIFT OF
+// THE SMALL OPERAND (gy: Cout values per pixel) instead of a third of the columns of the large one (Cin*49 per pixel).
+// Lanes = consecutive pixels (coalesced reads of a gy row), tile assembled in shared memory ([chunk 16][row 128 + 1 pad] x 16 B).
+__global__ void __launch_bounds__(256) wgrad_gyimg_tile_kernel(const float* __restrict__ gy, uint4* __restrict__ img, BwdGeo b,
+                                                               int64_t P, int64_t n_kstep8, int64_t img_kt_u4) {
+    extern __shared__ uint4 gy_tile[];                           // [16][129]
+    uint16_t* tile16 = reinterpret_cast<uint16_t*>(gy_tile);
+    const int64_t blk = blockIdx.x;                              // 128 pixels
+    const int kt = blockIdx.y;
+    const int p = threadIdx.x & 127, half = threadIdx.x >> 7;
+    const int64_t k = blk * 128 + p;
+    const int HoWo = b.Ho * b.Wo;
+    bool valid = k < P;
+    int64_t src = 0;
+    if (valid) {
+        const int64_t frame = k / HoWo;                          // video * To + t
+        const int hw = (int)(k - frame * HoWo);
+        const int64_t vid = frame / b.To;
+        const int to = (int)(frame - vid * b.To) - kt + 1;
+        valid = (unsigned)to < (unsigned)b.To;
+        src = (vid * b.K * b.To + to) * (int64_t)HoWo + hw;      // + row * To * HoWo
+    }
+    const int64_t row_stride = (int64_t)b.To * HoWo;
+    uint16_t* dst = tile16 + (((p >> 3) * 129 + half * 64) * 8 + (p & 7));
+    for (int j0 = 0; j0 < 64; j0 += 16) {
+        float v[16];
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) {
+            const int row = half * 64 + j0 + jj;
+            v[jj] = (valid && row < b.K) ? __ldg(gy + src + row * row_stride) : 0.f;
+        }
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) dst[(j0 + jj) * 8] = f2bf(v[jj]);
+    }
+    __syncthreads();
+    // image [kstep][k2][128 rows][8 px]: chunk c of the block is K-step c / 2, half c % 2
+    uint4* out = img + (int64_t)kt * img_kt_u4 + blk * (16 * 128);
+    for (int idx = threadIdx.x; idx < 16 * 128; idx += 256) out[idx] = gy_tile[(idx >> 7) * 129 + (idx & 127)];
+    (void)n_kstep8;
+}
+
 // gw[co][n] = sum over split-K slices of raw[(split*ntiles + ntile)][co][col], n = ntile*256 + col
-__global__ void wgrad_reduce_kernel(const float* __restrict__ raw, float* __restrict__ gw, int Cout, int Ncols, int ntiles, int splits) {
+// kt_split: n = (ci, kt, khw) of gw comes from raw image kt (raw_kt floats apart), column ci*49 + khw
+__global__ void wgrad_reduce_kernel(const float* __restrict__ raw, float* __restrict__ gw, int Cout, int Ncols, int ntiles, int splits,
+                                    int kt_split, int64_t raw_kt) {
     const int64_t total = (int64_t)Cout * Ncols;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int n = (int)(i % Ncols), co = (int)(i / Ncols);
+        int n = (int)(i % Ncols);
+        const int co = (int)(i / Ncols);
+        const float* r = raw;
+        if (kt_split) {
+            const int ci = n / 147, tap = n - ci * 147, kt = tap / 49;
+            n = ci * 49 + (tap - kt * 49);
+            r += kt * raw_kt;
+        }
         const int ntile = n >> 8, col = n & 255;
         float s = 0.f;
-        for (int sp = 0; sp < splits; ++sp) s += raw[(((int64_t)sp * ntiles + ntile) * 128 + co) * 256 + col];
+        for (int sp = 0; sp < splits; ++sp) s += r[(((int64_t)sp * ntiles + ntile) * 128 + co) * 256 + col];
         gw[i] = s;
     }
 }
@@ -335,13 +390,23 @@ static int pack_dy_impl(int layer, const float* gy, void* dy, const vd_tc_plan* 
 
 // Sizes of the wgrad workspace for B videos: out[0] = split-K slices, out[1] = stages per slice, out[2] = column
 // tiles, out[3] = xcol bytes, out[4] = gyimg bytes, out[5] = raw (fp32 partial sums) bytes
+// kt-split mode of the wgrad (default; VD_TC_WGRAD_KT=0 restores the full im2col): the three temporal taps are three GEMMs over
+// ONE im2col of the 49 spatial taps, each against a frame-shifted gy image — 2.4x fewer im2col bytes per call (5.8 -> 2.4 GB at
+// 50 videos of 16x3x112x112), which was a third of an MTT iteration.
+extern "C" int vd_tc_wgrad_kt_mode(int layer) {
+    static int mode = -1;
+    if (mode < 0) { const char* v = getenv("VD_TC_WGRAD_KT"); mode = (v && *v) ? atoi(v) : 7; }
+    return (mode >> layer) & 1;                                  // bit per layer
+}
+
 extern "C" int vd_tc_wgrad_plan(int layer, const vd_tc_plan* plan, int B, int64_t* out) {
     VD_REQUIRE(plan && out, "tc_wgrad_plan: NULL pointer");
     VD_REQUIRE(layer >= 0 && layer <= 2 && geo_supported(plan->T, plan->H) && B > 0, "tc_wgrad_plan: bad layer / geometry / batch");
     const Geo g = make_geo(plan->T, plan->H);
     const BwdGeo b = make_bwd_geo(g, layer);
     const int64_t P = (int64_t)B * b.pixels;
-    const int64_t ntiles = (b.Cin * 147 + 255) / 256;
+    const int kts = vd_tc_wgrad_kt_mode(layer);
+    const int64_t ntiles = (b.Cin * (kts ? 49 : 147) + 255) / 256;
     const int64_t stages = (P + 127) / 128;
     int64_t splits = (2 * 148 + ntiles - 1) / ntiles;
     if (splits > stages) splits = stages;
@@ -349,8 +414,8 @@ extern "C" int vd_tc_wgrad_plan(int layer, const vd_tc_plan* plan, int B, int64_
     const int64_t sps = (stages + splits - 1) / splits;
     out[0] = splits; out[1] = sps; out[2] = ntiles;
     out[3] = ntiles * splits * sps * 65536;
-    out[4] = splits * sps * 8 * 4096;
-    out[5] = ntiles * splits * 128 * 256 * 4;
+    out[4] = (kts ? 3 : 1) * splits * sps * 8 * 4096;            // kt-split: three gy images / raw buffers, one per temporal tap
+    out[5] = (kts ? 3 : 1) * ntiles * splits * 128 * 256 * 4;
     return 0;
 }
 
@@ -364,15 +429,26 @@ extern "C" int vd_tc_wgrad_pack(int layer, const float* x, const float* gy, void
     const int64_t P = (int64_t)B * b.pixels, n_stage = w[0] * w[1];
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t total_x = w[2] * n_stage * 16 * 256;
+    const int kts = vd_tc_wgrad_kt_mode(layer);
+    VD_REQUIRE(!kts || (n_stage < (1ll << 31) && w[2] <= 65535), "tc_wgrad_pack: problem too large for the kt-split packer");
     if (n_stage < (1ll << 31) && w[2] <= 65535) {
         static bool configured = false;
         const size_t smem = (size_t)16 * 257 * 16;
-        if (!configured) { cudaFuncSetAttribute(wgrad_im2col_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = true; }
-        wgrad_im2col_tile_kernel<<<dim3((unsigned)n_stage, (unsigned)w[2], 1), 256, smem, s>>>(x, (uint4*)xcol, b, P, n_stage);
+        if (!configured) {
+            cudaFuncSetAttribute(wgrad_im2col_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(wgrad_gyimg_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 129 * 16);
+            configured = true;
+        }
+        wgrad_im2col_tile_kernel<<<dim3((unsigned)n_stage, (unsigned)w[2], 1), 256, smem, s>>>(x, (uint4*)xcol, b, P, n_stage, kts);
     } else {
         wgrad_im2col_kernel<<<grid_of(total_x), 256, 0, s>>>(x, (uint4*)xcol, total_x, b, P, n_stage);
     }
     if (int e = check_launch("tc_wgrad_im2col")) return e;
+    if (kts) {
+        const int64_t img_kt_u4 = n_stage * 8 * 2 * 128;          // uint4 per image
+        wgrad_gyimg_tile_kernel<<<dim3((unsigned)n_stage, 3, 1), 256, 16 * 129 * 16, s>>>(gy, (uint4*)gyimg, b, P, n_stage, img_kt_u4);
+        return check_launch("tc_wgrad_gyimg");
+    }
     const int64_t total_g = n_stage * 8 * 2 * 128;
     wgrad_gyimg_kernel<<<grid_of(total_g), 256, 0, s>>>(gy, (uint4*)gyimg, total_g, b, P);
     return check_launch("tc_wgrad_gyimg");
@@ -384,7 +460,9 @@ extern "C" int vd_tc_wgrad_reduce(int layer, const float* raw, float* gw, const 
     if (int rc = vd_tc_wgrad_plan(layer, plan, B, w)) return rc;
     const Geo g = make_geo(plan->T, plan->H);
     const BwdGeo b = make_bwd_geo(g, layer);
-    wgrad_reduce_kernel<<<grid_of((int64_t)b.K * b.Cin * 147), 256, 0, (cudaStream_t)stream>>>(raw, gw, b.K, b.Cin * 147, (int)w[2], (int)w[0]);
+    const int kts = vd_tc_wgrad_kt_mode(layer);
+    wgrad_reduce_kernel<<<grid_of((int64_t)b.K * b.Cin * 147), 256, 0, (cudaStream_t)stream>>>(raw, gw, b.K, b.Cin * 147, (int)w[2], (int)w[0],
+                                                                                              kts, w[2] * w[0] * 128 * 256);
     return check_launch("tc_wgrad_reduce");
 }
 
