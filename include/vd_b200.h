@@ -292,6 +292,10 @@ int vd_tc_bwd_gemm_ex(int layer, const void* dy, const void* wt, void* col, cons
                       void* stream);
 /* out[0] split-K slices, out[1] stages per slice, out[2] column tiles, out[3] xcol bytes, out[4] gyimg bytes, out[5] raw bytes */
 int vd_tc_wgrad_plan(int layer, const vd_tc_plan* plan, int B, int64_t* out);
+/* 1 when wgrad of `layer` runs kt-split (default; env VD_TC_WGRAD_KT = bit mask over the layers): the three temporal taps are
+ * three GEMMs over ONE im2col of the 49 spatial taps, each against a frame-shifted image of gy; plan / pack / gemm / reduce
+ * follow the mode by themselves, callers only size their buffers from vd_tc_wgrad_plan. */
+int vd_tc_wgrad_kt_mode(int layer);
 int vd_tc_wgrad_pack(int layer, const float* x, const float* gy, void* xcol, void* gyimg, const vd_tc_plan* plan,
                      int B, void* stream);
 int vd_tc_wgrad_gemm(int layer, const void* xcol, const void* gyimg, float* raw, const vd_tc_plan* plan, int B,
