@@ -115,6 +115,17 @@ int vd_compose_bwd_f32(const float* gout, const float* static_syn, const float* 
  * the rows in block order, so the hallucinator gradient is bitwise reproducible; grad_weight / grad_bias are accumulated
  * (+=), grad_dynamic rows are written with plain stores when unique_rows != 0 (no two videos select the same dynamic memory,
  * distill_s2d_ms.py:405) and with atomics otherwise.  grad_static is not produced (--no_train_static path). */
+/* vd_compose_fwd_ex_f32 / vd_compose_bwd_fused_ex_f32: the same operations with the extents of the memories (n_static images of
+ * (3,H,W), n_dynamic memories of (T,H,W) behind static_syn / dynamic_syn).  With them the kernels are fed by tensor-map TMA
+ * (cp.async.bulk.tensor: halo rows / columns and the frames outside the clip zero-filled by the TMA unit); a tensor map must
+ * describe the true allocation, so the entry points without extents keep to the cp.async kernels. */
+int vd_compose_fwd_ex_f32(const float* static_syn, const float* dynamic_syn, const int64_t* static_idx, const int64_t* label,
+                          const int64_t* dynamic_idx, const float* weight, const float* bias, float* out, int B, int T, int H,
+                          int W, int dpc, int64_t n_static, int64_t n_dynamic, void* stream);
+int vd_compose_bwd_fused_ex_f32(const float* gout, const float* static_syn, const float* dynamic_syn, const int64_t* static_idx,
+                                const int64_t* label, const int64_t* dynamic_idx, const float* weight, float* grad_dynamic,
+                                float* grad_weight, float* grad_bias, float* scratch, int64_t scratch_floats, int unique_rows,
+                                int B, int T, int H, int W, int dpc, int64_t n_static, int64_t n_dynamic, void* stream);
 int vd_compose_bwd_fused_f32(const float* gout, const float* static_syn, const float* dynamic_syn,
                              const int64_t* static_idx, const int64_t* label, const int64_t* dynamic_idx,
                              const float* weight, float* grad_dynamic, float* grad_weight, float* grad_bias,

@@ -54,6 +54,9 @@ def _declare(lib):
         'vd_compose_fwd_f32': (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
         'vd_compose_bwd_f32': (c_int, [P, P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
         'vd_compose_bwd_fused_f32': (c_int, [P, P, P, P, P, P, P, P, P, P, P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+        'vd_compose_fwd_ex_f32': (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int64, c_int64, P]),
+        'vd_compose_bwd_fused_ex_f32': (c_int, [P, P, P, P, P, P, P, P, P, P, P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int,
+                                                c_int64, c_int64, P]),
         'vd_class_mean_f32': (c_int, [P, P, c_int, c_int, c_int, P]),
         'vd_class_sum_ragged_f32': (c_int, [P, P, P, c_int, c_int, P]),
         'vd_dm_loss_f32': (c_int, [P, P, P, P, c_int, c_int, c_int, c_float, P]),

@@ -58,8 +58,11 @@ int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, c
         stride *= dims[i];
         if (i + 1 < rank) gs[i] = stride;                       // byte stride of dimension i + 1
     }
+    static int promo = -1;
+    if (promo < 0) { const char* v = getenv("VD_TMA_L2PROMO"); promo = (v && *v) ? atoi(v) : 2; }
     const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                          promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("composer: cuTensorMapEncodeTiled failed (%d)", (int)r); return -1; }
     return 0;
@@ -434,6 +437,12 @@ int set_smem(const void* fn, size_t bytes) {
     return 0;
 }
 
+bool tma_enabled() {                                     // VD_COMPOSE_TMA=0: the cp.async kernels of compose_tiled.cu
+    static int on = -1;
+    if (on < 0) { const char* v = getenv("VD_COMPOSE_TMA"); on = (v && *v) ? atoi(v) : 1; }
+    return on != 0;
+}
+
 int tma_wp(int W) { return (W + 8 + 31) / 32 * 32; }       // 128-byte rows: every staged plane starts 128-byte aligned
 bool tma_ok(int H, int W) { return W % 4 == 0 && W >= 8 && (W / 4) * kTH <= kCT && tma_wp(W) <= 256 && H >= 1; }
 
@@ -461,15 +470,18 @@ int sm_count() {
 }  // namespace
 
 // returns 1 when the geometry is not covered or tensor maps are unavailable (the caller falls back to the cp.async kernels)
+// n_static / n_dynamic: the number of (3,H,W) static images and (T,H,W) dynamic memories behind the pointers.  The tensor maps
+// carry the TRUE extents: with the row dimension left open (1 << 22 rows) the kernel faulted with "illegal memory access" in
+// some allocator states although every coordinate it requests is in range (reproduced, and gone with exact extents).
 int compose_fwd_tma(const float* static_syn, const float* dynamic_syn, const int64_t* static_idx, const int64_t* label,
                     const int64_t* dynamic_idx, const float* weight, const float* bias, float* out, int B, int T, int H,
-                    int W, int dpc, cudaStream_t stream) {
-    if (!tma_ok(H, W) || !encode_fn()) return 1;
+                    int W, int dpc, int64_t n_static, int64_t n_dynamic, cudaStream_t stream) {
+    if (n_static <= 0 || n_dynamic <= 0) return 1;
+    if (!tma_ok(H, W) || !encode_fn() || !tma_enabled()) return 1;
     if ((((uintptr_t)static_syn) | ((uintptr_t)dynamic_syn)) & 15) return 1;
     const int WP = tma_wp(W);
-    // the memories are addressed through the index tables: the row dimension is left open (1 << 22 rows)
     CUtensorMap tmS, tmD;
-    const uint64_t dS[4] = {(uint64_t)W, (uint64_t)H, 3, 1ull << 22}, dD[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)T, 1ull << 22};
+    const uint64_t dS[4] = {(uint64_t)W, (uint64_t)H, 3, (uint64_t)n_static}, dD[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)T, (uint64_t)n_dynamic};
     const uint32_t bS[4] = {(uint32_t)WP, kTH + 2, 3, 1}, bD[4] = {(uint32_t)WP, kTH + 2, 1, 1};
     if (make_map(&tmS, static_syn, 4, dS, bS) || make_map(&tmD, dynamic_syn, 4, dD, bD)) return -1;
     const size_t smem = (size_t)(3 + kSlots) * (kTH + 2) * WP * 4 + 27 * 16 + 8 * (kSlots + 1) + 128;
@@ -479,7 +491,13 @@ int compose_fwd_tma(const float* static_syn, const float* dynamic_syn, const int
     const int TC = pick_chunk(nb * B, T, 2 * sm_count());              // 128 registers x 256 threads: two blocks per SM
     dim3 grid((unsigned)nb, (unsigned)B, (unsigned)ceil_div(T, TC));
     compose_fwd_tma_kernel<<<grid, kCT, smem, stream>>>(tmS, tmD, static_idx, label, dynamic_idx, weight, bias, out, T, H, W, dpc, WP, TC);
-    return check_launch("compose_fwd_tma");
+    if (int e = check_launch("compose_fwd_tma")) {
+        set_error("compose_fwd_tma failed (%d): B=%d T=%d H=%d W=%d dpc=%d WP=%d TC=%d smem=%zu static=%p dynamic=%p out=%p idx=%p/%p/%p",
+                  e, B, T, H, W, dpc, WP, TC, smem, (const void*)static_syn, (const void*)dynamic_syn, (void*)out,
+                  (const void*)static_idx, (const void*)label, (const void*)dynamic_idx);
+        return e;
+    }
+    return 0;
 }
 
 }  // namespace vd
@@ -492,8 +510,8 @@ void compose_bwd_finish(const float* scratch, int n_rows, float* grad_weight, fl
 int compose_bwd_tma(const float* gout, const float* static_syn, const float* dynamic_syn, const int64_t* static_idx,
                     const int64_t* label, const int64_t* dynamic_idx, const float* weight, float* grad_dynamic, float* grad_weight,
                     float* grad_bias, float* scratch, int64_t scratch_floats, int unique_rows, int B, int T, int H, int W, int dpc,
-                    cudaStream_t stream) {
-    if (!tma_ok(H, W) || !encode_fn()) return 1;
+                    int64_t n_static, int64_t n_dynamic, cudaStream_t stream) {
+    if (!tma_ok(H, W) || !encode_fn() || !tma_enabled() || n_static <= 0 || n_dynamic <= 0) return 1;
     if ((((uintptr_t)static_syn) | ((uintptr_t)dynamic_syn) | ((uintptr_t)gout)) & 15) return 1;
     const int WP = tma_wp(W);
     if ((size_t)kSlots * 4 * (kTH + 2) * WP < (size_t)84 * kCT) return 1;            // the parked partial sums reuse the frame ring
@@ -501,7 +519,7 @@ int compose_bwd_tma(const float* gout, const float* static_syn, const float* dyn
     if (scratch_floats < (int64_t)B * nb * kPartialStride) { set_error("compose_bwd_fused: scratch too small"); return -1; }
     CUtensorMap tmG, tmS, tmD;
     const uint64_t dG[5] = {(uint64_t)W, (uint64_t)H, 3, (uint64_t)T, (uint64_t)B};
-    const uint64_t dS[4] = {(uint64_t)W, (uint64_t)H, 3, 1ull << 22}, dD[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)T, 1ull << 22};
+    const uint64_t dS[4] = {(uint64_t)W, (uint64_t)H, 3, (uint64_t)n_static}, dD[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)T, (uint64_t)n_dynamic};
     const uint32_t bG[5] = {(uint32_t)WP, kTH + 2, 3, 1, 1}, bS[4] = {(uint32_t)WP, kTH + 2, 3, 1}, bD[4] = {(uint32_t)WP, kTH + 2, 1, 1};
     if (make_map(&tmG, gout, 5, dG, bG) || make_map(&tmS, static_syn, 4, dS, bS) || make_map(&tmD, dynamic_syn, 4, dD, bD)) return -1;
     const size_t smem = (size_t)(3 + 4 * kSlots) * (kTH + 2) * WP * 4 + 27 * 16 + 8 * (kSlots + 1) + 128;

@@ -704,11 +704,11 @@ int compose_fwd_tiled(const float* static_syn, const float* dynamic_syn, const i
 // TMA-fed versions (compose_tma.cu); return 1 when the geometry is not covered or tensor maps are unavailable
 int compose_fwd_tma(const float* static_syn, const float* dynamic_syn, const int64_t* static_idx, const int64_t* label,
                     const int64_t* dynamic_idx, const float* weight, const float* bias, float* out, int B, int T, int H,
-                    int W, int dpc, cudaStream_t stream);
+                    int W, int dpc, int64_t n_static, int64_t n_dynamic, cudaStream_t stream);
 int compose_bwd_tma(const float* gout, const float* static_syn, const float* dynamic_syn, const int64_t* static_idx,
                     const int64_t* label, const int64_t* dynamic_idx, const float* weight, float* grad_dynamic, float* grad_weight,
                     float* grad_bias, float* scratch, int64_t scratch_floats, int unique_rows, int B, int T, int H, int W, int dpc,
-                    cudaStream_t stream);
+                    int64_t n_static, int64_t n_dynamic, cudaStream_t stream);
 int compose_bwd_data_tiled(const float* gout, const int64_t* label, const int64_t* dynamic_idx, const float* weight,
                            float* grad_dynamic, int B, int T, int H, int W, int dpc, cudaStream_t stream);
 int compose_bwd_wdyn_tiled(const float* gout, const float* dynamic_syn, const int64_t* label, const int64_t* dynamic_idx,
@@ -719,15 +719,39 @@ int compose_bwd_fused(const float* gout, const float* static_syn, const float* d
                       cudaStream_t stream);
 }  // namespace vd
 
+static int compose_fwd_impl(const float* static_syn, const float* dynamic_syn, const int64_t* static_idx,
+                            const int64_t* label, const int64_t* dynamic_idx, const float* weight,
+                            const float* bias, float* out, int B, int T, int H, int W, int dpc, int64_t n_static, int64_t n_dynamic,
+                            void* stream);
+
 extern "C" int vd_compose_fwd_f32(const float* static_syn, const float* dynamic_syn, const int64_t* static_idx,
                                   const int64_t* label, const int64_t* dynamic_idx, const float* weight,
                                   const float* bias, float* out, int B, int T, int H, int W, int dpc, void* stream) {
+    return compose_fwd_impl(static_syn, dynamic_syn, static_idx, label, dynamic_idx, weight, bias, out, B, T, H, W, dpc, 0, 0, stream);
+}
+
+// The same with the extents of the memories (n_static images of (3,H,W), n_dynamic memories of (T,H,W)): enables the tensor-map
+// (TMA) kernels, whose maps must describe the true allocations.
+extern "C" int vd_compose_fwd_ex_f32(const float* static_syn, const float* dynamic_syn, const int64_t* static_idx,
+                                     const int64_t* label, const int64_t* dynamic_idx, const float* weight,
+                                     const float* bias, float* out, int B, int T, int H, int W, int dpc,
+                                     int64_t n_static, int64_t n_dynamic, void* stream) {
+    VD_REQUIRE(n_static > 0 && n_dynamic > 0, "compose_fwd_ex: the memory extents must be positive");
+    return compose_fwd_impl(static_syn, dynamic_syn, static_idx, label, dynamic_idx, weight, bias, out, B, T, H, W, dpc, n_static, n_dynamic, stream);
+}
+
+static int compose_fwd_impl(const float* static_syn, const float* dynamic_syn, const int64_t* static_idx,
+                            const int64_t* label, const int64_t* dynamic_idx, const float* weight,
+                            const float* bias, float* out, int B, int T, int H, int W, int dpc, int64_t n_static, int64_t n_dynamic,
+                            void* stream) {
     VD_REQUIRE(static_syn && dynamic_syn && static_idx && label && dynamic_idx && weight && bias && out, "compose_fwd: NULL pointer");
     VD_REQUIRE(B >= 0 && T > 0 && H > 0 && W > 0 && dpc > 0 && T <= 65535 && B <= 65535, "compose_fwd: bad extent");
     if (B == 0) return 0;
     {
-        int rc = compose_fwd_tma(static_syn, dynamic_syn, static_idx, label, dynamic_idx, weight, bias, out, B, T, H, W, dpc,
-                                 (cudaStream_t)stream);
+        int rc = 1;
+        if (n_static > 0 && n_dynamic > 0)
+            rc = compose_fwd_tma(static_syn, dynamic_syn, static_idx, label, dynamic_idx, weight, bias, out, B, T, H, W, dpc,
+                                 n_static, n_dynamic, (cudaStream_t)stream);
         if (rc != 1) return rc;                 // 1 = not covered: the cp.async tiled kernel, then the generic one
         rc = compose_fwd_tiled(static_syn, dynamic_syn, static_idx, label, dynamic_idx, weight, bias, out, B, T, H, W, dpc,
                                (cudaStream_t)stream);
@@ -785,17 +809,45 @@ extern "C" int vd_compose_bwd_f32(const float* gout, const float* static_syn, co
 // One-pass deterministic backward of the composer (compose_tiled.cu: compose_bwd_fused_kernel): grad_dynamic rows written (or
 // accumulated with atomics when unique_rows == 0), grad_weight / grad_bias += block sums added in a fixed order.  Falls back to
 // vd_compose_bwd_f32 when the geometry is not covered by the tiled kernels.
+static int compose_bwd_fused_impl(const float* gout, const float* static_syn, const float* dynamic_syn,
+                                  const int64_t* static_idx, const int64_t* label, const int64_t* dynamic_idx,
+                                  const float* weight, float* grad_dynamic, float* grad_weight, float* grad_bias,
+                                  float* scratch, int64_t scratch_floats, int unique_rows,
+                                  int B, int T, int H, int W, int dpc, int64_t n_static, int64_t n_dynamic, void* stream);
+
 extern "C" int vd_compose_bwd_fused_f32(const float* gout, const float* static_syn, const float* dynamic_syn,
                                         const int64_t* static_idx, const int64_t* label, const int64_t* dynamic_idx,
                                         const float* weight, float* grad_dynamic, float* grad_weight, float* grad_bias,
                                         float* scratch, int64_t scratch_floats, int unique_rows,
                                         int B, int T, int H, int W, int dpc, void* stream) {
+    return compose_bwd_fused_impl(gout, static_syn, dynamic_syn, static_idx, label, dynamic_idx, weight, grad_dynamic, grad_weight,
+                                  grad_bias, scratch, scratch_floats, unique_rows, B, T, H, W, dpc, 0, 0, stream);
+}
+
+// with the extents of the memories (see vd_compose_fwd_ex_f32): enables the tensor-map (TMA) kernel
+extern "C" int vd_compose_bwd_fused_ex_f32(const float* gout, const float* static_syn, const float* dynamic_syn,
+                                           const int64_t* static_idx, const int64_t* label, const int64_t* dynamic_idx,
+                                           const float* weight, float* grad_dynamic, float* grad_weight, float* grad_bias,
+                                           float* scratch, int64_t scratch_floats, int unique_rows,
+                                           int B, int T, int H, int W, int dpc, int64_t n_static, int64_t n_dynamic, void* stream) {
+    VD_REQUIRE(n_static > 0 && n_dynamic > 0, "compose_bwd_fused_ex: the memory extents must be positive");
+    return compose_bwd_fused_impl(gout, static_syn, dynamic_syn, static_idx, label, dynamic_idx, weight, grad_dynamic, grad_weight,
+                                  grad_bias, scratch, scratch_floats, unique_rows, B, T, H, W, dpc, n_static, n_dynamic, stream);
+}
+
+static int compose_bwd_fused_impl(const float* gout, const float* static_syn, const float* dynamic_syn,
+                                  const int64_t* static_idx, const int64_t* label, const int64_t* dynamic_idx,
+                                  const float* weight, float* grad_dynamic, float* grad_weight, float* grad_bias,
+                                  float* scratch, int64_t scratch_floats, int unique_rows,
+                                  int B, int T, int H, int W, int dpc, int64_t n_static, int64_t n_dynamic, void* stream) {
     VD_REQUIRE(gout && static_syn && dynamic_syn && static_idx && label && dynamic_idx && weight && grad_dynamic && grad_weight && scratch,
                "compose_bwd_fused: NULL pointer");
     VD_REQUIRE(B >= 0 && T > 0 && H > 0 && W > 0 && dpc > 0 && T <= 65535 && B <= 65535, "compose_bwd_fused: bad extent");
     if (B == 0) return 0;
-    int rc = compose_bwd_tma(gout, static_syn, dynamic_syn, static_idx, label, dynamic_idx, weight, grad_dynamic, grad_weight,
-                             grad_bias, scratch, scratch_floats, unique_rows, B, T, H, W, dpc, (cudaStream_t)stream);
+    int rc = 1;
+    if (n_static > 0 && n_dynamic > 0)
+        rc = compose_bwd_tma(gout, static_syn, dynamic_syn, static_idx, label, dynamic_idx, weight, grad_dynamic, grad_weight,
+                             grad_bias, scratch, scratch_floats, unique_rows, B, T, H, W, dpc, n_static, n_dynamic, (cudaStream_t)stream);
     if (rc != 1) return rc;
     rc = compose_bwd_fused(gout, static_syn, dynamic_syn, static_idx, label, dynamic_idx, weight, grad_dynamic, grad_weight,
                            grad_bias, scratch, scratch_floats, unique_rows, B, T, H, W, dpc, (cudaStream_t)stream);

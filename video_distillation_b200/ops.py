@@ -356,8 +356,9 @@ class _Compose(torch.autograd.Function):
         B = int(label.numel())
         idx = [t.to(torch.int64).contiguous() for t in (static_idx, label, dynamic_idx)]
         out = torch.empty(B, T, 3, H, W, dtype=torch.float32, device=dynamic_syn.device)
-        check(lib().vd_compose_fwd_f32(ptr(static_syn), ptr(dynamic_syn), ptr(idx[0]), ptr(idx[1]), ptr(idx[2]),
-                                       ptr(weight), ptr(bias), ptr(out), B, T, H, W, dpc, stream()), 'compose_fwd')
+        check(lib().vd_compose_fwd_ex_f32(ptr(static_syn), ptr(dynamic_syn), ptr(idx[0]), ptr(idx[1]), ptr(idx[2]),
+                                          ptr(weight), ptr(bias), ptr(out), B, T, H, W, dpc,
+                                          int(static_syn.shape[0]), int(C * dpc), stream()), 'compose_fwd')
         ctx.save_for_backward(static_syn, dynamic_syn, weight, *idx)
         return out
 
@@ -376,9 +377,10 @@ class _Compose(torch.autograd.Function):
         if gw is not None and gs is None:
             # one pass over the video gradient, block sums added in a fixed order (no float atomics): reproducible bit for bit
             scratch = torch.empty(B * ((H + 7) // 8) * 328, dtype=torch.float32, device=gout.device)
-            check(lib().vd_compose_bwd_fused_f32(ptr(gout), ptr(static_syn), ptr(dynamic_syn), ptr(sidx), ptr(label), ptr(didx),
-                                                 ptr(weight), ptr(gd), ptr(gw), ptr(gb), ptr(scratch), scratch.numel(),
-                                                 int(ctx.unique_rows), B, T, H, W, dpc, stream()), 'compose_bwd_fused')
+            check(lib().vd_compose_bwd_fused_ex_f32(ptr(gout), ptr(static_syn), ptr(dynamic_syn), ptr(sidx), ptr(label), ptr(didx),
+                                                    ptr(weight), ptr(gd), ptr(gw), ptr(gb), ptr(scratch), scratch.numel(),
+                                                    int(ctx.unique_rows), B, T, H, W, dpc,
+                                                    int(static_syn.shape[0]), int(C * dpc), stream()), 'compose_bwd_fused')
         else:
             check(lib().vd_compose_bwd_f32(ptr(gout), ptr(static_syn), ptr(dynamic_syn), ptr(sidx), ptr(label), ptr(didx),
                                            ptr(weight), ptr(gd), ptr(gw), ptr(gb), ptr(gs), B, T, H, W, dpc, stream()), 'compose_bwd')
