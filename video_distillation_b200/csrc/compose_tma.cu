@@ -58,11 +58,8 @@ int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, c
         stride *= dims[i];
         if (i + 1 < rank) gs[i] = stride;                       // byte stride of dimension i + 1
     }
-    static int promo = -1;
-    if (promo < 0) { const char* v = getenv("VD_TMA_L2PROMO"); promo = (v && *v) ? atoi(v) : 2; }
     const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                          promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("composer: cuTensorMapEncodeTiled failed (%d)", (int)r); return -1; }
     return 0;
