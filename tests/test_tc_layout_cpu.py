@@ -236,3 +236,25 @@ def test_two_product_layer2_tables(T, HW):
     assert p.n_acc == 4 and p.n_tiles == 1 and p.n_steps == 12 and p.Gt == 0
     d = torch.from_numpy(D[0]).reshape(4, 128, g.To2, g.Ho2, g.Wo2)
     assert rel(d[:B], y) < 2e-6, rel(d[:B], y)
+
+
+def test_wgrad_plan_kt_split_sizes():
+    """vd_tc_wgrad_plan in the kt-split mode (default): one im2col of the 49 spatial taps (a third of the column tiles), three gy
+    images / raw buffers (one per temporal tap); host-only arithmetic."""
+    import ctypes
+    from video_distillation_b200 import _lib
+    lib = _lib.lib()
+    plan = _lib.TcPlan()
+    _lib.check(lib.vd_tc_plan_make(ctypes.byref(plan), 16, 112, 112), 'plan')
+    cin = (3, 64, 128)
+    pixels = (16 * 56 * 56, 16 * 14 * 14, 8 * 4 * 4)
+    for layer in range(3):
+        assert lib.vd_tc_wgrad_kt_mode(layer) == 1
+        sz = (ctypes.c_int64 * 6)()
+        _lib.check(lib.vd_tc_wgrad_plan(layer, ctypes.byref(plan), 50, sz), 'wgrad_plan')
+        splits, sps, ntiles, xcol, gyimg, raw = (int(v) for v in sz)
+        assert ntiles == -(-cin[layer] * 49 // 256)
+        stages = -(-50 * pixels[layer] // 128)
+        assert stages <= splits * sps < stages + splits                           # split-K slices cover every 128-pixel stage, < 1 padded stage per slice
+        assert xcol == ntiles * splits * sps * 65536
+        assert gyimg == 3 * splits * sps * 8 * 4096 and raw == 3 * ntiles * splits * 128 * 256 * 4
