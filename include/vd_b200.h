@@ -259,6 +259,12 @@ int vd_tc_x3_conv_layer(int layer, const void* in, const void* wimg, const float
 int vd_tc_x3_pack_video_hi(const float* video, const int64_t* index, void* x0h, const vd_tc_plan* plan, int B, void* stream);
 int vd_tc_x3_pack_video_hi_u8(const uint8_t* video, const int64_t* index, void* x0h, const vd_tc_plan* plan, int B,
                               const float* mean3, const float* std3, void* stream);
+/* One-launch split-fp16 fprop of the differentiable conv trio (layers 1 and 2): vd_tc_x3_pack_act packs an fp32 NCDHW activation
+ * into A1s / A2s, vd_tc_x3_conv_plain writes the fp32 NCDHW pre-activation (+ bias when non-NULL) with all three products
+ * accumulated in TMEM (weights from vd_tc_x3_pack_weights). */
+int vd_tc_x3_pack_act(int layer, const float* x, void* packed, const vd_tc_plan* plan, int B, void* stream);
+int vd_tc_x3_conv_plain(int layer, const void* in, const void* wimg, const float* bias, float* out, const vd_tc_plan* plan, int B,
+                        void* stream);
 int vd_tc_x3_conv_layer_ex(int layer, const void* in, const void* wimg, const float* bias, void* out, uint8_t* code,
                            int code_first_item, const vd_tc_plan* plan, const int64_t* item_index, int B, int passes, void* stream);
 

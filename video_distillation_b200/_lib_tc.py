@@ -17,6 +17,8 @@ def declare(lib):
         'vd_tc_x3_pack_weights': (c_int, [P, P, P, P, P, P, P]),
         'vd_tc_x3_conv_layer': (c_int, [c_int, P, P, P, P, P, c_int, POINTER(TcPlan), P, c_int, P]),
         'vd_tc_x3_conv_layer_ex': (c_int, [c_int, P, P, P, P, P, c_int, POINTER(TcPlan), P, c_int, c_int, P]),
+        'vd_tc_x3_pack_act': (c_int, [c_int, P, P, POINTER(TcPlan), c_int, P]),
+        'vd_tc_x3_conv_plain': (c_int, [c_int, P, P, P, P, POINTER(TcPlan), c_int, P]),
         'vd_tc_x3_pack_video_hi': (c_int, [P, P, P, POINTER(TcPlan), c_int, P]),
         'vd_tc_x3_pack_video_hi_u8': (c_int, [P, P, P, POINTER(TcPlan), c_int, P, P, P]),
         'vd_tc_pack_weights_bwd': (c_int, [P, P, P, P, P, P, P]),

@@ -698,8 +698,9 @@ __device__ __forceinline__ void epi_plain(const WsParams& p, int tile, uint32_t 
     } else if (p.epi.layer == 1) {
         const int item = tile / p.tiles_per_item, tp = tile % p.tiles_per_item;
         const float bias = p.epi.bias ? __ldg(p.epi.bias + m) : 0.f;
-        for (int a = 0; a < 2; ++a) {
-            float* dst = out + (((int64_t)item * 128 + m) * g.T + 2 * tp + a) * g.Ho1 * g.Wo1;
+        const int fpt = p.n_acc;                          // output frames per tile (2, or 4 for the split tables at 64x64)
+        for (int a = 0; a < fpt; ++a) {
+            float* dst = out + (((int64_t)item * 128 + m) * g.T + fpt * tp + a) * g.Ho1 * g.Wo1;
             for (int ho = 0; ho < g.Ho1; ++ho) {
                 float v[16];
                 tmem_ld16(taddr + a * p.acc_cols + ho * g.P1, v);
@@ -1759,6 +1760,29 @@ extern "C" int vd_tc_x3_conv_layer_ex(int layer, const void* in, const void* wim
                                       int B, int passes, void* stream) {
     VD_REQUIRE(passes == 2 || passes == 3, "tc_x3_conv_layer_ex: passes must be 2 or 3");
     return x3_conv_layer_impl(layer, in, wimg, bias, out, code, code_first_item, plan, item_index, B, passes, stream);
+}
+
+// Plain convolution of layer 1 / 2 on the split-fp16 tables: out = fp32 NCDHW (B, Cout, To, Ho, Wo), pre-activation (+ bias when
+// non-NULL) with all three products xh*wh + xl*wh + xh*wl accumulated in TMEM by ONE launch — the fprop of the differentiable
+// conv trio (MTT), which evaluated the same sum as three single-pass launches with twice the MMAs.  in = vd_tc_x3_pack_act,
+// wimg = vd_tc_x3_pack_weights.
+extern "C" int vd_tc_x3_conv_plain(int layer, const void* in, const void* wimg, const float* bias, float* out,
+                                   const vd_tc_plan* plan, int B, void* stream) {
+    VD_REQUIRE(plan && in && wimg && out, "tc_x3_conv_plain: NULL pointer");
+    VD_REQUIRE(layer == 1 || layer == 2, "tc_x3_conv_plain: layer must be 1 or 2");
+    VD_REQUIRE(B >= 0 && geo_supported(plan->T, plan->H), "tc_x3_conv_plain: bad batch / geometry");
+    if (B == 0) return 0;
+    WsParams p;
+    memset(&p, 0, sizeof(p));
+    const Geo g = make_geo(plan->T, plan->H);
+    uint32_t smem = 0;
+    int rc = layer == 1 ? setup_l1s(p, g, B, &smem, 3) : setup_l2s(p, g, B, &smem, 3);
+    if (rc) { if (rc == -2) set_error("tc x3 conv plain %d: non-monotone window offsets", layer); return rc; }
+    p.pix = (const uint8_t*)in; p.wimg = (const uint8_t*)wimg; p.item_index = nullptr;
+    p.prof = g_prof; p.dbg = env_int("VD_TC_DBG", 0);
+    p.epi.bias = bias; p.epi.out = (uint8_t*)out; p.epi.raw = out;
+    p.epi.T = plan->T; p.epi.n_items = B; p.epi.g = g; p.epi.layer = layer; p.epi.accum = 0;
+    return launch<EPI_PLAIN>(p, smem, (cudaStream_t)stream);
 }
 
 static int x3_conv_layer_impl(int layer, const void* in, const void* wimg, const float* bias, void* out,

@@ -68,6 +68,62 @@ __device__ __forceinline__ float dy_part(float v, int part) {
     return part == 0 ? v : v - __uint_as_float((uint32_t)f2bf(v) << 16);
 }
 
+// ---- split-fp16 operands of the one-launch fprop (vd_tc_x3_conv_plain): the A1s / A2s layouts of tc_layout.h from plain NCDHW
+// x (B, 64, T, H1, H1) fp32 -> A1s [item][chunk 8][t_pad T+2][part 2][ph 2][pw 2][i RI1][j P1] chunks of 8 fp16 (hi / lo part)
+__device__ __forceinline__ uint4 pack8_h(const float (&v)[8], int part) {
+    uint16_t h[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { uint16_t hi, lo; split_h(v[e], hi, lo); h[e] = part ? lo : hi; }
+    uint4 o;
+    o.x = h[0] | ((uint32_t)h[1] << 16); o.y = h[2] | ((uint32_t)h[3] << 16);
+    o.z = h[4] | ((uint32_t)h[5] << 16); o.w = h[6] | ((uint32_t)h[7] << 16);
+    return o;
+}
+
+__global__ void pack_a1s_kernel(const float* __restrict__ x, uint4* __restrict__ a1, int64_t total, Geo g) {
+    const int64_t S1 = (int64_t)g.T * g.H1 * g.H1;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int j = (int)(i % g.P1); int64_t q = i / g.P1;
+        int ii = (int)(q % g.RI1); q /= g.RI1;
+        int pw = (int)(q % 2); q /= 2;
+        int ph = (int)(q % 2); q /= 2;
+        int part = (int)(q % 2); q /= 2;
+        int tp = (int)(q % (g.T + 2)); q /= (g.T + 2);
+        int chunk = (int)(q % 8); int64_t item = q / 8;
+        const int t = tp - 1, h = ph ? 2 * ii - 3 : 2 * ii - 2, w = pw ? 2 * j - 3 : 2 * j - 2;
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (t >= 0 && t < g.T && h >= 0 && h < g.H1 && w >= 0 && w < g.H1) {
+            const float* p = x + (item * 64 + chunk * 8) * S1 + ((int64_t)t * g.H1 + h) * g.H1 + w;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = __ldg(p + e * S1);
+        }
+        a1[i] = pack8_h(v, part);
+    }
+}
+
+// x (B, 128, T2, H2, H2) fp32 -> A2s [item][khw 49][quarter 4][part 2][k 4][t_pad To2+2][ho Ho2][wo Wo2] chunks of 8 fp16
+__global__ void pack_a2s_kernel(const float* __restrict__ x, uint4* __restrict__ a2, int64_t total, Geo g) {
+    const int64_t S2 = (int64_t)g.T2 * g.H2 * g.H2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int wo = (int)(i % g.Wo2); int64_t q = i / g.Wo2;
+        int ho = (int)(q % g.Ho2); q /= g.Ho2;
+        int tp = (int)(q % (g.To2 + 2)); q /= (g.To2 + 2);
+        int k = (int)(q % 4); q /= 4;
+        int part = (int)(q % 2); q /= 2;
+        int quarter = (int)(q % 4); q /= 4;
+        int khw = (int)(q % 49); int64_t item = q / 49;
+        const int kh = khw / 7, kw = khw % 7;
+        const int t = tp - 1, h = 2 * ho + kh - 3, w = 2 * wo + kw - 3;
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (t >= 0 && t < g.T2 && h >= 0 && h < g.H2 && w >= 0 && w < g.H2) {
+            const float* p = x + (item * 128 + quarter * 32 + k * 8) * S2 + ((int64_t)t * g.H2 + h) * g.H2 + w;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = __ldg(p + e * S2);
+        }
+        a2[i] = pack8_h(v, part);
+    }
+}
+
 // gy (B, K, To, Ho, Wo) fp32 -> dY [video][nt NT][chunk K/8][col NC][8] bf16
 __global__ void pack_dy_kernel(const float* __restrict__ gy, uint4* __restrict__ dy, int64_t total, BwdGeo b, int part) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -361,6 +417,25 @@ extern "C" int vd_tc_pack_act(int layer, const float* x, void* packed, const vd_
         pack_a2_kernel<<<grid_of(total), 256, 0, s>>>(x, (uint4*)packed, total, g, part);
     }
     return check_launch("tc_pack_act");
+}
+
+// x fp32 NCDHW -> the split-fp16 operand A1s (layer 1) / A2s (layer 2) of vd_tc_x3_conv_plain; every chunk (halo included) written
+extern "C" int vd_tc_x3_pack_act(int layer, const float* x, void* packed, const vd_tc_plan* plan, int B, void* stream) {
+    VD_REQUIRE(x && packed && plan, "tc_x3_pack_act: NULL pointer");
+    VD_REQUIRE(layer == 1 || layer == 2, "tc_x3_pack_act: layer must be 1 or 2");
+    VD_REQUIRE(geo_supported(plan->T, plan->H), "tc_x3_pack_act: unsupported geometry");
+    if (B <= 0) return 0;
+    const Geo g = make_geo(plan->T, plan->H);
+    const SGeo sg = make_sgeo(g);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (layer == 1) {
+        const int64_t total = (int64_t)B * (sg.video1s / 16);
+        pack_a1s_kernel<<<grid_of(total), 256, 0, s>>>(x, (uint4*)packed, total, g);
+    } else {
+        const int64_t total = (int64_t)B * (sg.video2s / 16);
+        pack_a2s_kernel<<<grid_of(total), 256, 0, s>>>(x, (uint4*)packed, total, g);
+    }
+    return check_launch("tc_x3_pack_act");
 }
 
 // gy fp32 NCDHW (B, Cout, To, Ho, Wo) of conv `layer` -> packed dY operand of vd_tc_bwd_gemm

@@ -31,6 +31,7 @@ class TcTrio:
         self.direct_dgrad1 = True
         self.direct_dgrad0 = True
         self.col_fp32 = True
+        self.fused_split_fprop = True     # layers 1 / 2: split fprop as one launch on the split-fp16 tables
 
     # ------------------------------------------------------------------ helpers
     def layer_of(self, cin, cout, extent):
@@ -81,6 +82,21 @@ class TcTrio:
         cin, cout, _ = self.layers[layer]
         out_ext = [(p.T1, p.H1, p.W1), (p.T2, p.H2, p.W2), (p.T3, p.H3, p.W3)][layer]
         y = torch.empty(B, cout, *out_ext, dtype=torch.float32, device=self.device)
+        if split and layer in (1, 2) and self.fused_split_fprop:
+            # ONE launch on the split-fp16 tables (fp16 hi / lo pairs, three products accumulated in TMEM)
+            lib, plan, st = _lib.lib(), ctypes.byref(p), _lib.stream()
+            sz = (ctypes.c_int64 * 6)()
+            _lib.check(lib.vd_tc_x3_sizes(plan, sz), 'vd_tc_x3_sizes')
+            B4 = (B + 3) // 4 * 4 if layer == 2 else B
+            src = self._buf(f'a{layer}s', B4 * int(sz[layer]), zero=(layer == 2))
+            wimg = self._buf(f'w{layer}s', int(sz[3 + layer]))
+            ws, imgs = [None, None, None], [None, None, None]
+            ws[layer], imgs[layer] = w, wimg
+            _lib.check(lib.vd_tc_x3_pack_weights(_lib.ptr(ws[0]), _lib.ptr(ws[1]), _lib.ptr(ws[2]), _lib.ptr(imgs[0]), _lib.ptr(imgs[1]),
+                                                 _lib.ptr(imgs[2]), st), 'vd_tc_x3_pack_weights')
+            _lib.check(lib.vd_tc_x3_pack_act(layer, _lib.ptr(x), _lib.ptr(src), plan, B, st), 'vd_tc_x3_pack_act')
+            _lib.check(lib.vd_tc_x3_conv_plain(layer, _lib.ptr(src), _lib.ptr(wimg), None, _lib.ptr(y), plan, B, st), 'vd_tc_x3_conv_plain')
+            return y
         wh = self._pack_weight(layer, w, 0, f'w{layer}')
         src = self._pack_input(layer, x, 0)
         self._conv(layer, src, wh, y, B, False)
