@@ -315,6 +315,11 @@ int vd_tc_wgrad_plan(int layer, const vd_tc_plan* plan, int B, int64_t* out);
 int vd_tc_wgrad_kt_mode(int layer);
 int vd_tc_wgrad_pack(int layer, const float* x, const float* gy, void* xcol, void* gyimg, const vd_tc_plan* plan,
                      int B, void* stream);
+/* The split (parity-grade) wgrad of the MTT trio: x_part / gy_part = 0 packs the value (rounded to bf16), 1 its bf16 residual
+ * v - bf16(v); x or gy NULL keeps the operand that is already in xcol / gyimg (xl*gh, xh*gh, xh*gl need two im2cols and two
+ * gy images, not three).  [torch.autograd conv weight gradient of networks.py:799, reference fp32] */
+int vd_tc_wgrad_pack_parts(int layer, const float* x, int x_part, const float* gy, int gy_part, void* xcol, void* gyimg,
+                           const vd_tc_plan* plan, int B, void* stream);
 int vd_tc_wgrad_gemm(int layer, const void* xcol, const void* gyimg, float* raw, const vd_tc_plan* plan, int B,
                      void* stream);
 int vd_tc_wgrad_reduce(int layer, const float* raw, float* gw, const vd_tc_plan* plan, int B, void* stream);

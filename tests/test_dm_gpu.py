@@ -257,10 +257,11 @@ def test_dm_s2d_bf16x3_parity_mode_on_tensor_cores():
     assert errs[2] < 1e-2 and errs[3] < 1e-2, errs
 
 
-@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+@pytest.mark.parametrize('precision', ['fp32', 'bf16', 'bf16x3'])
 def test_mtt_s2d_golden(precision):
     """Unrolled student with second-order autograd through our conv trio vs the reference: exact fp32 kernels,
-    and the tensor-core trio (bf16 operands / fp32 accumulate, every first- and second-order conv term)."""
+    the tensor-core trio (split fprop, single-pass bf16 dgrad / wgrad, every first- and second-order conv term) and the
+    parity-grade tensor-core trio 'bf16x3' (every primitive on hi / lo operand pairs)."""
     from oracle import synth
     from video_distillation_b200.distill import MTTS2DTrainer
     from video_distillation_b200.networks import ConvNet3D
@@ -311,13 +312,20 @@ def test_mtt_s2d_golden(precision):
         assert rel(tr.syn_lr.grad, gold['grad_syn_lr']) < 1e-3
         check_summary(tr.dynamic_syn.grad, gold['grad_dynamic_sums'], gold['grad_dynamic_sample'])
     else:
-        # split-bf16 fprop (3 passes) + single-pass bf16 dgrad / wgrad: hallucinator / lr gradients within 1e-2, dynamic memory 2e-2
+        from oracle import synth as _synth
         errs = dict(grand=rel(grand, gold['grand_loss']), hal_w=rel(tr.hal.encoder.weight.grad, gold['grad_hal_weight']),
-                    hal_b=rel(tr.hal.encoder.bias.grad, gold['grad_hal_bias']), lr=rel(tr.syn_lr.grad, gold['grad_syn_lr']))
-        print('mtt bf16 tensor-core trio vs reference:', errs)
+                    hal_b=rel(tr.hal.encoder.bias.grad, gold['grad_hal_bias']), lr=rel(tr.syn_lr.grad, gold['grad_syn_lr']),
+                    dynamic_sample=rel(_synth.summarize(tr.dynamic_syn.grad.detach().cpu())[1], gold['grad_dynamic_sample']))
+        print(f'mtt {precision} tensor-core trio vs reference:', errs)
         assert errs['grand'] < 1e-5, errs
-        assert errs['hal_w'] < 1e-2 and errs['hal_b'] < 1e-2 and errs['lr'] < 1e-2, errs
-        check_summary(tr.dynamic_syn.grad, gold['grad_dynamic_sums'], gold['grad_dynamic_sample'], tol=2e-2)   # observed 1.2e-2
+        if precision == 'bf16':
+            # split fprop + single-pass bf16 dgrad / wgrad: hallucinator / lr gradients within 1e-2, dynamic memory 2e-2 (observed 1.2e-2)
+            assert errs['hal_w'] < 1e-2 and errs['hal_b'] < 1e-2 and errs['lr'] < 1e-2, errs
+            check_summary(tr.dynamic_syn.grad, gold['grad_dynamic_sums'], gold['grad_dynamic_sample'], tol=2e-2)
+        else:
+            # every primitive split: the 1e-3 gate of north_star on tensor cores (observed 1.5e-5 / 1.4e-5 / 3.1e-5 / 7e-6)
+            assert errs['hal_w'] < 2e-4 and errs['hal_b'] < 2e-4 and errs['lr'] < 2e-4, errs
+            check_summary(tr.dynamic_syn.grad, gold['grad_dynamic_sums'], gold['grad_dynamic_sample'], tol=2e-4)
 
 
 def test_streamed_real_batch_in_any_row_order():

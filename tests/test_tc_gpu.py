@@ -266,13 +266,31 @@ def test_tensor_core_trio_matches_fp32_kernels(T, HW):
             gx_ref = ops.conv3d_dgrad_raw(gy, w, tuple(x.shape), S, P)
             gw_ref = ops.conv3d_wgrad_raw(x, gy, tuple(w.shape), S, P)
             ops.set_conv_backend('tc')
-            y = ops.conv3d_fprop_raw(x, w, None, S, P)
+            y = ops.conv3d_fprop_raw(x, w, None, S, P)                       # bf16 pairs, three launches (any operand range)
+            y16 = ops.conv3d_fprop_raw(x, w, None, S, P, fp16_ok=True)       # conv 1 / 2: fp16 pairs, one launch (activation ranges)
             gx = ops.conv3d_dgrad_raw(gy, w, tuple(x.shape), S, P)
             gw = ops.conv3d_wgrad_raw(x, gy, tuple(w.shape), S, P)
+            # the parity-grade trio: every primitive on bf16 hi / lo pairs, on operands that are NOT bf16-representable
+            x3, w3, gy3 = x * 1.0009765625, w * 0.9990234375, gy * 1.0029296875
+            ops.set_conv_backend('fp32')
+            ref3 = (ops.conv3d_fprop_raw(x3, w3, None, S, P), ops.conv3d_dgrad_raw(gy3, w3, tuple(x.shape), S, P),
+                    ops.conv3d_wgrad_raw(x3, gy3, tuple(w.shape), S, P))
+            ops.set_conv_backend('tc_x3')
+            got3 = (ops.conv3d_fprop_raw(x3, w3, None, S, P), ops.conv3d_dgrad_raw(gy3, w3, tuple(x.shape), S, P),
+                    ops.conv3d_wgrad_raw(x3, gy3, tuple(w.shape), S, P))
+            # cotangent-sized operands (1e-6): the bf16 pairs keep their relative accuracy
+            ops.set_conv_backend('fp32')
+            y_small_ref = ops.conv3d_fprop_raw(x3 * 1e-6, w3 * 1e-3, None, S, P)
+            ops.set_conv_backend('tc_x3')
+            y_small = ops.conv3d_fprop_raw(x3 * 1e-6, w3 * 1e-3, None, S, P)
         finally:
             ops.set_conv_backend(prev)
         assert y.shape == y_ref.shape and gx.shape == gx_ref.shape and gw.shape == gw_ref.shape
         assert rel(y, y_ref) < 1e-5, (layer, 'fprop', rel(y, y_ref))
+        assert rel(y16, y_ref) < 1e-5, (layer, 'fprop fp16 pairs', rel(y16, y_ref))
+        errs3 = [rel(a, b) for a, b in zip(got3, ref3)] + [rel(y_small, y_small_ref)]
+        print(f'layer {layer} tc_x3 trio vs fp32 kernels (fprop, dgrad, wgrad, fprop of 1e-6-sized operands):', errs3)
+        assert max(errs3) < 1e-4, (layer, "tc_x3", errs3)
         # conv 1: column-free dgrad, fp32 accumulators straight to the output; conv 0 / 2: fp32 column buffers
         assert rel(gx, gx_ref) < 1e-5, (layer, 'dgrad', rel(gx, gx_ref))
         assert rel(gw, gw_ref) < 1e-5, (layer, 'wgrad', rel(gw, gw_ref))

@@ -34,6 +34,7 @@ def declare(lib):
         'vd_tc_wgrad_plan': (c_int, [c_int, POINTER(TcPlan), c_int, POINTER(c_int64)]),
         'vd_tc_wgrad_kt_mode': (c_int, [c_int]),
         'vd_tc_wgrad_pack': (c_int, [c_int, P, P, P, P, POINTER(TcPlan), c_int, P]),
+        'vd_tc_wgrad_pack_parts': (c_int, [c_int, P, c_int, P, c_int, P, P, POINTER(TcPlan), c_int, P]),
         'vd_tc_wgrad_gemm': (c_int, [c_int, P, P, P, POINTER(TcPlan), c_int, P]),
         'vd_tc_wgrad_reduce': (c_int, [c_int, P, P, POINTER(TcPlan), c_int, P]),
         'vd_tc_dgrad1_sizes': (c_int, [POINTER(TcPlan), POINTER(c_int64)]),

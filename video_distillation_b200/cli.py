@@ -250,6 +250,12 @@ def _tensors_of(dst):
     return torch.stack(xs), torch.tensor(ys)
 
 
+def _mtt_precision(args):
+    """Conv-trio precision of the MTT unroll: the parity-grade tensor-core trio (every primitive on bf16 hi / lo pairs) unless the
+    single-pass throughput mode or the exact fp32 kernels are asked for."""
+    return {'fp32': 'fp32', 'bf16': 'bf16'}.get(args.precision, 'bf16x3')
+
+
 def _eval_precision(args):
     return 'bf16' if args.precision in ('bf16', 'bf16x3', 'f16x3', 'f16x3r2') else 'fp32'
 
@@ -351,7 +357,7 @@ def main_s2d(args):
     if args.method == 'MTT':
         experts = ExpertBuffers(args.buffer_path, args.max_start_epoch, args.expert_epochs)
         tr = MTTS2DTrainer(syn_steps=args.syn_steps, lr_lr=args.lr_lr, lr_teacher=args.lr_teacher, train_lr=args.train_lr,
-                           batch_syn=args.batch_syn, precision='fp32' if args.precision == 'fp32' else 'bf16', **common)
+                           batch_syn=args.batch_syn, precision=_mtt_precision(args), **common)
     elif args.method == 'DM':
         videos, labels = _tensors_of(dst_train)
         ds = DeviceDataset(videos, labels, num_classes, dev, rank, world, shard='video' if world > 1 else 'class')
@@ -458,7 +464,7 @@ def main_baseline(args):
         tr = MTTBaselineTrainer(num_classes=num_classes, channel=channel, im_size=im_size, frames=args.frames, ipc=args.ipc,
                                 syn_steps=args.syn_steps, lr_img=args.lr_img, lr_lr=args.lr_lr, lr_teacher=args.lr_teacher,
                                 train_lr=args.train_lr, batch_syn=args.batch_syn, image_syn=image_syn, device=dev,
-                                precision='fp32' if args.precision == 'fp32' else 'bf16')
+                                precision=_mtt_precision(args))
     elif args.method == 'DM':
         prec = args.precision
         tr = DMBaselineTrainer(ds, num_classes=num_classes, channel=channel, im_size=im_size, frames=args.frames, ipc=args.ipc,

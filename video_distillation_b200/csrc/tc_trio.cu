@@ -143,7 +143,7 @@ __global__ void pack_dy_kernel(const float* __restrict__ gy, uint4* __restrict__
 //   xcol : [ntile][stage P_pad/128][chunk 16][col 256][8 pixels]      (N operand, one 64 KiB stage per bulk copy)
 //   gyimg: [kstep P_pad/16][k 2][128 rows = cout][8 pixels]            (M operand, 4 KiB UMMA tiles)
 __global__ void wgrad_im2col_kernel(const float* __restrict__ x, uint4* __restrict__ xcol, int64_t total, BwdGeo b,
-                                    int64_t P, int64_t n_stage) {
+                                    int64_t P, int64_t n_stage, int part) {
     const int64_t Si = (int64_t)b.Ti * b.Hi * b.Wi;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int col = (int)(i % 256); int64_t q = i / 256;
@@ -163,7 +163,7 @@ __global__ void wgrad_im2col_kernel(const float* __restrict__ x, uint4* __restri
                 if (k + e < P) {
                     const int t = to + kt - 1, h = 2 * ho + kh - 3, w = 2 * wo + kw - 3;
                     if ((unsigned)t < (unsigned)b.Ti && (unsigned)h < (unsigned)b.Hi && (unsigned)w < (unsigned)b.Wi)
-                        v[e] = __ldg(x + (vid * b.Cin + ci) * Si + ((int64_t)t * b.Hi + h) * b.Wi + w);
+                        v[e] = dy_part(__ldg(x + (vid * b.Cin + ci) * Si + ((int64_t)t * b.Hi + h) * b.Wi + w), part);
                 }
                 if (++wo == b.Wo) { wo = 0; if (++ho == b.Ho) { ho = 0; if (++to == b.To) { to = 0; ++vid; } } }
             }
@@ -181,7 +181,7 @@ __global__ void wgrad_im2col_kernel(const float* __restrict__ x, uint4* __restri
 // kt_split != 0 ("temporal taps on the gy side", see wgrad_gyimg_tile_kernel): columns n = ci*49 + (kh*7 + kw) of the CENTRE temporal
 // tap only, and the GEMM's K index runs over the pixels (video, t, ho, wo) of the INPUT frames t — a third of the columns.
 __global__ void __launch_bounds__(256) wgrad_im2col_tile_kernel(const float* __restrict__ x, uint4* __restrict__ xcol, BwdGeo b,
-                                                                int64_t P, int64_t n_stage, int kt_split) {
+                                                                int64_t P, int64_t n_stage, int kt_split, int part) {
     extern __shared__ uint4 im2col_tile[];                       // [16][257]
     uint16_t* tile16 = reinterpret_cast<uint16_t*>(im2col_tile);
     const int64_t stage = blockIdx.x;
@@ -218,14 +218,14 @@ __global__ void __launch_bounds__(256) wgrad_im2col_tile_kernel(const float* __r
             if (++kw == 7) { kw = 0; if (++kh == 7) { kh = 0; if (kt_split) ++ci; else if (++kt == 3) { kt = 0; ++ci; } } }
         }
 #pragma unroll
-        for (int jj = 0; jj < 16; ++jj) dst[(j0 + jj) * 8] = f2bf(v[jj]);
+        for (int jj = 0; jj < 16; ++jj) dst[(j0 + jj) * 8] = f2bf(dy_part(v[jj], part));
     }
     __syncthreads();
     uint4* out = xcol + ((int64_t)ntile * n_stage + stage) * (16 * 256);
     for (int idx = threadIdx.x; idx < 16 * 256; idx += 256) out[idx] = im2col_tile[(idx >> 8) * 257 + (idx & 255)];
 }
 
-__global__ void wgrad_gyimg_kernel(const float* __restrict__ gy, uint4* __restrict__ img, int64_t total, BwdGeo b, int64_t P) {
+__global__ void wgrad_gyimg_kernel(const float* __restrict__ gy, uint4* __restrict__ img, int64_t total, BwdGeo b, int64_t P, int part) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int row = (int)(i % 128); int64_t q = i / 128;
         int k2 = (int)(q % 2); int64_t kstep = q / 2;
@@ -237,7 +237,7 @@ __global__ void wgrad_gyimg_kernel(const float* __restrict__ gy, uint4* __restri
                 const int64_t k = k0 + e;
                 if (k < P) {
                     const int64_t vid = k / b.pixels, pix = k - vid * b.pixels;
-                    v[e] = __ldg(gy + (vid * b.K + row) * (int64_t)b.pixels + pix);
+                    v[e] = dy_part(__ldg(gy + (vid * b.K + row) * (int64_t)b.pixels + pix), part);
                 }
             }
         }
@@ -251,7 +251,7 @@ __global__ void wgrad_gyimg_kernel(const float* __restrict__ gy, uint4* __restri
 // THE SMALL OPERAND (gy: Cout values per pixel) instead of a third of the columns of the large one (Cin*49 per pixel).
 // Lanes = consecutive pixels (coalesced reads of a gy row), tile assembled in shared memory ([chunk 16][row 128 + 1 pad] x 16 B).
 __global__ void __launch_bounds__(256) wgrad_gyimg_tile_kernel(const float* __restrict__ gy, uint4* __restrict__ img, BwdGeo b,
-                                                               int64_t P, int64_t n_kstep8, int64_t img_kt_u4) {
+                                                               int64_t P, int64_t n_kstep8, int64_t img_kt_u4, int part) {
     extern __shared__ uint4 gy_tile[];                           // [16][129]
     uint16_t* tile16 = reinterpret_cast<uint16_t*>(gy_tile);
     const int64_t blk = blockIdx.x;                              // 128 pixels
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(256) wgrad_gyimg_tile_kernel(const float* __re
             v[jj] = (valid && row < b.K) ? __ldg(gy + src + row * row_stride) : 0.f;
         }
 #pragma unroll
-        for (int jj = 0; jj < 16; ++jj) dst[(j0 + jj) * 8] = f2bf(v[jj]);
+        for (int jj = 0; jj < 16; ++jj) dst[(j0 + jj) * 8] = f2bf(dy_part(v[jj], part));
     }
     __syncthreads();
     // image [kstep][k2][128 rows][8 px]: chunk c of the block is K-step c / 2, half c % 2
@@ -494,9 +494,12 @@ extern "C" int vd_tc_wgrad_plan(int layer, const vd_tc_plan* plan, int B, int64_
     return 0;
 }
 
-extern "C" int vd_tc_wgrad_pack(int layer, const float* x, const float* gy, void* xcol, void* gyimg, const vd_tc_plan* plan,
-                                int B, void* stream) {
-    VD_REQUIRE(x && gy && xcol && gyimg && plan, "tc_wgrad_pack: NULL pointer");
+// x / gy may be NULL: the operand already in xcol / gyimg is kept (the split wgrad packs xh once for gh and gl);
+// x_part / gy_part: 0 = the value (rounded to bf16), 1 = its bf16 residual v - bf16(v), made inside the packer
+extern "C" int vd_tc_wgrad_pack_parts(int layer, const float* x, int x_part, const float* gy, int gy_part, void* xcol, void* gyimg,
+                                      const vd_tc_plan* plan, int B, void* stream) {
+    VD_REQUIRE((x || gy) && xcol && gyimg && plan, "tc_wgrad_pack: NULL pointer");
+    VD_REQUIRE((x_part == 0 || x_part == 1) && (gy_part == 0 || gy_part == 1), "tc_wgrad_pack: part must be 0 or 1");
     int64_t w[6];
     if (int rc = vd_tc_wgrad_plan(layer, plan, B, w)) return rc;
     const Geo g = make_geo(plan->T, plan->H);
@@ -506,27 +509,36 @@ extern "C" int vd_tc_wgrad_pack(int layer, const float* x, const float* gy, void
     const int64_t total_x = w[2] * n_stage * 16 * 256;
     const int kts = vd_tc_wgrad_kt_mode(layer);
     VD_REQUIRE(!kts || (n_stage < (1ll << 31) && w[2] <= 65535), "tc_wgrad_pack: problem too large for the kt-split packer");
-    if (n_stage < (1ll << 31) && w[2] <= 65535) {
-        static bool configured = false;
-        const size_t smem = (size_t)16 * 257 * 16;
-        if (!configured) {
-            cudaFuncSetAttribute(wgrad_im2col_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            cudaFuncSetAttribute(wgrad_gyimg_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 129 * 16);
-            configured = true;
-        }
-        wgrad_im2col_tile_kernel<<<dim3((unsigned)n_stage, (unsigned)w[2], 1), 256, smem, s>>>(x, (uint4*)xcol, b, P, n_stage, kts);
-    } else {
-        wgrad_im2col_kernel<<<grid_of(total_x), 256, 0, s>>>(x, (uint4*)xcol, total_x, b, P, n_stage);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(wgrad_im2col_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 257 * 16);
+        cudaFuncSetAttribute(wgrad_gyimg_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 129 * 16);
+        configured = true;
     }
-    if (int e = check_launch("tc_wgrad_im2col")) return e;
+    if (x) {
+        if (n_stage < (1ll << 31) && w[2] <= 65535) {
+            wgrad_im2col_tile_kernel<<<dim3((unsigned)n_stage, (unsigned)w[2], 1), 256, (size_t)16 * 257 * 16, s>>>(x, (uint4*)xcol, b, P, n_stage,
+                                                                                                                  kts, x_part);
+        } else {
+            wgrad_im2col_kernel<<<grid_of(total_x), 256, 0, s>>>(x, (uint4*)xcol, total_x, b, P, n_stage, x_part);
+        }
+        if (int e = check_launch("tc_wgrad_im2col")) return e;
+    }
+    if (!gy) return 0;
     if (kts) {
         const int64_t img_kt_u4 = n_stage * 8 * 2 * 128;          // uint4 per image
-        wgrad_gyimg_tile_kernel<<<dim3((unsigned)n_stage, 3, 1), 256, 16 * 129 * 16, s>>>(gy, (uint4*)gyimg, b, P, n_stage, img_kt_u4);
+        wgrad_gyimg_tile_kernel<<<dim3((unsigned)n_stage, 3, 1), 256, 16 * 129 * 16, s>>>(gy, (uint4*)gyimg, b, P, n_stage, img_kt_u4, gy_part);
         return check_launch("tc_wgrad_gyimg");
     }
     const int64_t total_g = n_stage * 8 * 2 * 128;
-    wgrad_gyimg_kernel<<<grid_of(total_g), 256, 0, s>>>(gy, (uint4*)gyimg, total_g, b, P);
+    wgrad_gyimg_kernel<<<grid_of(total_g), 256, 0, s>>>(gy, (uint4*)gyimg, total_g, b, P, gy_part);
     return check_launch("tc_wgrad_gyimg");
+}
+
+extern "C" int vd_tc_wgrad_pack(int layer, const float* x, const float* gy, void* xcol, void* gyimg, const vd_tc_plan* plan,
+                                int B, void* stream) {
+    VD_REQUIRE(x && gy, "tc_wgrad_pack: NULL pointer");
+    return vd_tc_wgrad_pack_parts(layer, x, 0, gy, 0, xcol, gyimg, plan, B, stream);
 }
 
 extern "C" int vd_tc_wgrad_reduce(int layer, const float* raw, float* gw, const vd_tc_plan* plan, int B, void* stream) {

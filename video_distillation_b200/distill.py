@@ -624,8 +624,8 @@ class MTTS2DTrainer:
                  lr_dynamic=1e4, lr_hal=1e-2, lr_static=1e-4, lr_lr=1e-5, lr_teacher=0.01, train_static=False,
                  train_lr=True, batch_syn=None, static_syn=None, dynamic_syn=None, hal=None, device='cuda',
                  precision='fp32'):
-        if precision not in ('fp32', 'bf16'):
-            raise ValueError("precision must be 'fp32' or 'bf16'")
+        if precision not in ('fp32', 'bf16', 'bf16x3'):
+            raise ValueError("precision must be 'fp32', 'bf16' or 'bf16x3'")
         self.precision = precision
         self.C, self.channel, self.im_size, self.frames = num_classes, channel, tuple(im_size), frames
         self.vpc, self.spc, self.dpc, self.syn_steps = vpc, spc, dpc, syn_steps
@@ -655,7 +655,7 @@ class MTTS2DTrainer:
 
     def step(self, start_params, target_params, student_net=None, net_seed=None):
         """start_params / target_params: lists of expert tensors (buffer.py layout) or flat tensors."""
-        prev = ops.set_conv_backend('tc' if self.precision == 'bf16' else 'fp32')
+        prev = ops.set_conv_backend(ops.backend_for_precision(self.precision))
         try:
             return self._step(start_params, target_params, student_net, net_seed)
         finally:
@@ -744,8 +744,8 @@ class MTTBaselineTrainer:
     def __init__(self, *, num_classes, channel=3, im_size=(112, 112), frames=16, ipc=1, syn_steps=10, lr_img=1.0,
                  lr_lr=1e-5, lr_teacher=0.001, train_lr=False, batch_syn=None, image_syn=None, device='cuda',
                  precision='fp32'):
-        if precision not in ('fp32', 'bf16'):
-            raise ValueError("precision must be 'fp32' or 'bf16'")
+        if precision not in ('fp32', 'bf16', 'bf16x3'):
+            raise ValueError("precision must be 'fp32', 'bf16' or 'bf16x3'")
         self.precision = precision
         self.C, self.channel, self.im_size, self.frames = num_classes, channel, tuple(im_size), frames
         self.ipc, self.syn_steps, self.lr_img, self.lr_lr, self.train_lr = ipc, syn_steps, lr_img, lr_lr, train_lr
@@ -763,7 +763,7 @@ class MTTBaselineTrainer:
         self.last = {}
 
     def step(self, start_params, target_params, student_net=None, net_seed=None):
-        prev = ops.set_conv_backend('tc' if self.precision == 'bf16' else 'fp32')
+        prev = ops.set_conv_backend(ops.backend_for_precision(self.precision))
         try:
             return self._step(start_params, target_params, student_net, net_seed)
         finally:

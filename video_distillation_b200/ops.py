@@ -40,12 +40,19 @@ _CONV_BACKEND = 'fp32'
 
 def set_conv_backend(name):
     """'fp32': exact CUDA-core kernels (parity mode).  'tc': the feature-conv geometries of ConvNet3D run as
-    bf16 tcgen05 GEMMs with fp32 accumulation (tc_trio.py); other convolutions stay on the fp32 kernels."""
+    tcgen05 GEMMs with fp32 accumulation (tc_trio.py): split fprop (three products per MAC), single-pass bf16 dgrad / wgrad;
+    other convolutions stay on the fp32 kernels.  'tc_x3': as 'tc' with dgrad and wgrad split as well (both operands as bf16
+    hi + lo pairs, hi*hi + hi*lo + lo*hi accumulated in fp32) — the parity-grade tensor-core trio of the MTT unroll."""
     global _CONV_BACKEND
-    if name not in ('fp32', 'tc'):
-        raise ValueError("conv backend must be 'fp32' or 'tc'")
+    if name not in ('fp32', 'tc', 'tc_x3'):
+        raise ValueError("conv backend must be 'fp32', 'tc' or 'tc_x3'")
     prev, _CONV_BACKEND = _CONV_BACKEND, name
     return prev
+
+
+def backend_for_precision(precision):
+    """Conv backend of the trio for a driver-level precision string ('fp32' | 'bf16' | 'bf16x3')."""
+    return {'fp32': 'fp32', 'bf16': 'tc', 'bf16x3': 'tc_x3'}[precision]
 
 
 _TC_FPROP_SPLIT = __import__('os').environ.get('VD_TC_FPROP_SPLIT', '1') != '0'
@@ -54,14 +61,17 @@ _TC_OPS = set(__import__('os').environ.get('VD_TC_OPS', 'fprop,dgrad,wgrad').spl
 
 
 def _tc_route(x_shape, w_shape, stride, padding, device, op='fprop'):
-    if _CONV_BACKEND != 'tc' or op not in _TC_OPS:
+    if _CONV_BACKEND not in ('tc', 'tc_x3') or op not in _TC_OPS:
         return None, None
     from .tc_trio import trio_for
     return trio_for(tuple(x_shape), tuple(w_shape), _triple(stride), _triple(padding), device)
 
 
 # ------------------------------------------------------------------ raw kernels
-def conv3d_fprop_raw(x, w, bias, stride, padding):
+def conv3d_fprop_raw(x, w, bias, stride, padding, fp16_ok=False):
+    """fp16_ok: the operands have the range of activations x weights (the network's own forward), so the split fprop of
+    conv 1 / conv 2 may run as ONE launch on fp16 hi / lo pairs; cotangent operands (the fprop calls that the double backward
+    of dgrad / wgrad makes) keep to bf16 pairs, which have the exponent range of fp32."""
     x, w = _f32c(x), _f32c(w)
     trio, layer = _tc_route(x.shape, w.shape, stride, padding, x.device)
     if trio is not None and x.shape[0] > 0:
@@ -69,7 +79,7 @@ def conv3d_fprop_raw(x, w, bias, stride, padding):
         # The forward decides ReLU masks / pool argmax and the logits, so it is the precision-critical third of
         # the trio (single-pass bf16 fprop alone costs 5-7 % on MTT's second-order gradients; measured in
         # tests/test_dm_gpu.py::test_mtt_s2d_golden).
-        y = trio.fprop(layer, x, w, split=_TC_FPROP_SPLIT)
+        y = trio.fprop(layer, x, w, split=_TC_FPROP_SPLIT, fp16_ok=fp16_ok)
         return y if bias is None else y + bias.view(1, -1, 1, 1, 1)
     g = conv_geom(x.shape, w.shape, stride, padding)
     y = torch.empty(g.N, g.Cout, g.To, g.Ho, g.Wo, dtype=torch.float32, device=x.device)
@@ -85,13 +95,8 @@ def conv3d_dgrad_raw(gy, w, x_shape, stride, padding):
     assert tuple(gy.shape) == (g.N, g.Cout, g.To, g.Ho, g.Wo), (tuple(gy.shape), (g.N, g.Cout, g.To, g.Ho, g.Wo))
     trio, layer = _tc_route(x_shape, w.shape, stride, padding, gy.device, 'dgrad')
     if trio is not None and gy.shape[0] > 0:
-        if _TC_DGRAD_SPLIT:                               # same split as fprop: gy = gh + gl, w = wh + wl
-            gh = gy.to(torch.bfloat16).float()
-            wh = w.to(torch.bfloat16).float()
-            gx = trio.dgrad(layer, gh, wh)
-            gx += trio.dgrad(layer, gh, w - wh)
-            gx += trio.dgrad(layer, gy - gh, wh)
-            return gx
+        if _TC_DGRAD_SPLIT or _CONV_BACKEND == 'tc_x3':   # same split as fprop: gy = gh + gl, w = wh + wl
+            return trio.dgrad_split(layer, gy, w)
         return trio.dgrad(layer, gy, w)
     gx = torch.empty(tuple(x_shape), dtype=torch.float32, device=gy.device)
     if gx.numel():
@@ -104,7 +109,10 @@ def conv3d_wgrad_raw(x, gy, w_shape, stride, padding, want_bias=False):
     g = conv_geom(x.shape, w_shape, stride, padding)
     trio, layer = _tc_route(x.shape, w_shape, stride, padding, x.device, 'wgrad')
     if trio is not None and x.shape[0] > 0:
-        gw = trio.wgrad(layer, x, gy)
+        if _CONV_BACKEND == 'tc_x3':                      # x = xh + xl, gy = gh + gl: three products, fp32 sums
+            gw = trio.wgrad_split(layer, x, gy)
+        else:
+            gw = trio.wgrad(layer, x, gy)
         return (gw, gy.sum(dim=(0, 2, 3, 4))) if want_bias else gw
     gw = torch.zeros(tuple(w_shape), dtype=torch.float32, device=x.device)
     gb = torch.zeros(g.Cout, dtype=torch.float32, device=x.device) if want_bias else None
@@ -116,10 +124,10 @@ def conv3d_wgrad_raw(x, gy, w_shape, stride, padding, want_bias=False):
 # ------------------------------------------------------------------ conv trio as autograd Functions
 class _Fprop(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w, stride, padding):
+    def forward(ctx, x, w, stride, padding, fp16_ok=False):
         ctx.save_for_backward(x, w)
         ctx.sp = (stride, padding)
-        return conv3d_fprop_raw(x, w, None, stride, padding)
+        return conv3d_fprop_raw(x, w, None, stride, padding, fp16_ok)
 
     @staticmethod
     def backward(ctx, gy):
@@ -127,7 +135,7 @@ class _Fprop(torch.autograd.Function):
         stride, padding = ctx.sp
         gx = _Dgrad.apply(gy, w, tuple(x.shape), stride, padding) if ctx.needs_input_grad[0] else None
         gw = _Wgrad.apply(x, gy, tuple(w.shape), stride, padding) if ctx.needs_input_grad[1] else None
-        return gx, gw, None, None
+        return gx, gw, None, None, None
 
 
 class _Dgrad(torch.autograd.Function):
@@ -166,7 +174,7 @@ class _Wgrad(torch.autograd.Function):
 
 def conv3d(x, w, bias=None, stride=1, padding=0):
     """F.conv3d replacement (fp32, CUDA cores), differentiable to any order."""
-    y = _Fprop.apply(x, w, _triple(stride), _triple(padding))
+    y = _Fprop.apply(x, w, _triple(stride), _triple(padding), True)
     if bias is not None:
         y = y + bias.view(1, -1, 1, 1, 1)
     return y

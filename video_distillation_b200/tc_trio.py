@@ -75,14 +75,16 @@ class TcTrio:
                                                None, B, 3 if accumulate else 2, _lib.stream()), f'vd_tc_conv_layer({layer}, plain)')
 
     # ------------------------------------------------------------------ the trio
-    def fprop(self, layer, x, w, split=False):
+    def fprop(self, layer, x, w, split=False, fp16_ok=False):
         """y = conv3d(x, w).  split: x = xh + xl, w = wh + wl (bf16 parts made inside the packers);
-        y = xh*wh + xh*wl + xl*wh accumulated in fp32 by the plain epilogue (three launches, no temporaries)."""
+        y = xh*wh + xh*wl + xl*wh accumulated in fp32 by the plain epilogue (three launches, no temporaries).
+        fp16_ok (activation x weight ranges): layers 1 / 2 run the three products in ONE launch on fp16 pairs instead —
+        not for cotangent operands (1e-5 and below: fp16 keeps no low part there)."""
         p, B = self.plan, int(x.shape[0])
         cin, cout, _ = self.layers[layer]
         out_ext = [(p.T1, p.H1, p.W1), (p.T2, p.H2, p.W2), (p.T3, p.H3, p.W3)][layer]
         y = torch.empty(B, cout, *out_ext, dtype=torch.float32, device=self.device)
-        if split and layer in (1, 2) and self.fused_split_fprop:
+        if split and fp16_ok and layer in (1, 2) and self.fused_split_fprop:
             # ONE launch on the split-fp16 tables (fp16 hi / lo pairs, three products accumulated in TMEM)
             lib, plan, st = _lib.lib(), ctypes.byref(p), _lib.stream()
             sz = (ctypes.c_int64 * 6)()
@@ -133,10 +135,11 @@ class TcTrio:
                                               _lib.ptr(imgs[2]), st), 'vd_tc_pack_weights_bwd')
         return (wt,)
 
-    def dgrad(self, layer, gy, w, part=0, wpack=None, out=None, accumulate=False, ncdhw=True):
+    def dgrad(self, layer, gy, w, part=0, wpack=None, out=None, accumulate=False, ncdhw=True, packed=False):
         """gx = dgrad(part(gy), w) of feature conv `layer`.  part: 0 = bf16(gy), 1 = bf16(gy - bf16(gy)) (made inside the packer);
         wpack: cached pack_dgrad_weights(layer, w); out / accumulate: write (or add) into an existing fp32 tensor — the three
-        passes of a split-bf16 dgrad then share one tensor; ncdhw=False (layer 0 only): out is (B,T,3,H,W)."""
+        passes of a split-bf16 dgrad then share one tensor; ncdhw=False (layer 0 only): out is (B,T,3,H,W); packed: the operand
+        of this (gy, part) is still in the workspace from the previous call (same layer, same batch) and is not packed again."""
         p, lib, B = self.plan, _lib.lib(), int(gy.shape[0])
         cin, cout, ext = self.layers[layer]
         if wpack is None:
@@ -148,7 +151,8 @@ class TcTrio:
             sz = (ctypes.c_int64 * 2)()
             _lib.check(lib.vd_tc_dgrad0_sizes(plan, sz), 'vd_tc_dgrad0_sizes')
             dyp = self._buf('dyp0', B * sz[0])
-            _lib.check(lib.vd_tc_pack_dyp0_part(_lib.ptr(gy), _lib.ptr(dyp), plan, B, int(part), st), 'vd_tc_pack_dyp0_part')
+            if not packed:
+                _lib.check(lib.vd_tc_pack_dyp0_part(_lib.ptr(gy), _lib.ptr(dyp), plan, B, int(part), st), 'vd_tc_pack_dyp0_part')
             if out is None:
                 assert not accumulate
                 out = torch.empty((B, cin, *ext) if ncdhw else (B, ext[0], cin, ext[1], ext[2]), dtype=torch.float32, device=self.device)
@@ -160,7 +164,8 @@ class TcTrio:
             sz = (ctypes.c_int64 * 3)()
             _lib.check(lib.vd_tc_dgrad1_sizes(plan, sz), 'vd_tc_dgrad1_sizes')
             dyp = self._buf('dyp1', B * sz[0])
-            _lib.check(lib.vd_tc_pack_dyp1_part(_lib.ptr(gy), _lib.ptr(dyp), plan, B, int(part), st), 'vd_tc_pack_dyp1_part')
+            if not packed:
+                _lib.check(lib.vd_tc_pack_dyp1_part(_lib.ptr(gy), _lib.ptr(dyp), plan, B, int(part), st), 'vd_tc_pack_dyp1_part')
             if out is None:
                 assert not accumulate
                 out = torch.empty(B, cin, *ext, dtype=torch.float32, device=self.device)
@@ -170,7 +175,8 @@ class TcTrio:
         dy = self._buf('dy', B * (p.dy0_bytes_per_video, p.dy1_bytes_per_video, p.dy2_bytes_per_video)[layer])
         f32 = 1 if self.col_fp32 else 0      # fp32 column buffers: no bf16 rounding between the GEMM and the tap sum
         col = self._buf('col', B * (p.col0_bytes_per_video, p.col1_bytes_per_video, p.col2_bytes_per_video)[layer] * (2 if f32 else 1))
-        _lib.check(lib.vd_tc_pack_dy_part(layer, _lib.ptr(gy), _lib.ptr(dy), plan, B, int(part), st), 'vd_tc_pack_dy_part')
+        if not packed:
+            _lib.check(lib.vd_tc_pack_dy_part(layer, _lib.ptr(gy), _lib.ptr(dy), plan, B, int(part), st), 'vd_tc_pack_dy_part')
         _lib.check(lib.vd_tc_bwd_gemm_ex(layer, _lib.ptr(dy), _lib.ptr(wpack[0]), _lib.ptr(col), plan, B, f32, st), 'vd_tc_bwd_gemm_ex')
         gx = torch.empty(B, cin, *ext, dtype=torch.float32, device=self.device)
         _lib.check(lib.vd_tc_bwd_col2im_plain(layer, _lib.ptr(col), _lib.ptr(gx), plan, B, f32, st), 'vd_tc_bwd_col2im_plain')
@@ -182,7 +188,29 @@ class TcTrio:
             return out
         return gx
 
-    def wgrad(self, layer, x, gy):
+    def dgrad_split(self, layer, gy, w):
+        """gx = dgrad(gy, w) on bf16 hi / lo pairs: gh*wh + gh*wl + gl*wh summed in fp32 in one tensor.  The gradient parts are made
+        inside the packers, gh is packed once for both weight parts."""
+        wh = w.to(torch.bfloat16).float()
+        pk_h, pk_l = self.pack_dgrad_weights(layer, wh), self.pack_dgrad_weights(layer, w - wh)
+        gx = self.dgrad(layer, gy, None, part=0, wpack=pk_h)
+        self.dgrad(layer, gy, None, part=0, wpack=pk_l, out=gx, accumulate=True, packed=True)
+        self.dgrad(layer, gy, None, part=1, wpack=pk_h, out=gx, accumulate=True)
+        return gx
+
+    def wgrad_split(self, layer, x, gy):
+        """gw = wgrad(x, gy) on bf16 hi / lo pairs: xl*gh + xh*gh + xh*gl (parts made inside the packers; in this order the
+        im2col of xh and the image of gh are each packed once for two GEMMs)."""
+        gw = self.wgrad(layer, x, gy, parts=(1, 0))
+        gw += self.wgrad(layer, x, None, parts=(0, 0))
+        gw += self.wgrad(layer, None, gy, parts=(0, 1))
+        return gw
+
+    def wgrad(self, layer, x, gy, parts=None):
+        """parts = (x_part, gy_part), 0 = value / 1 = bf16 residual; x or gy None: that operand is still packed in the workspace
+        from the previous call of the same layer and batch."""
+        if parts is not None:
+            return self._wgrad_parts(layer, x, gy, parts)
         p, lib, B = self.plan, _lib.lib(), int(x.shape[0])
         cin, cout, _ = self.layers[layer]
         sizes = (ctypes.c_int64 * 6)()
@@ -192,6 +220,24 @@ class TcTrio:
         raw = self._buf('wraw', sizes[5])
         plan, st = ctypes.byref(p), _lib.stream()
         _lib.check(lib.vd_tc_wgrad_pack(layer, _lib.ptr(x), _lib.ptr(gy), _lib.ptr(xcol), _lib.ptr(gyimg), plan, B, st), 'vd_tc_wgrad_pack')
+        _lib.check(lib.vd_tc_wgrad_gemm(layer, _lib.ptr(xcol), _lib.ptr(gyimg), _lib.ptr(raw), plan, B, st), 'vd_tc_wgrad_gemm')
+        gw = torch.empty(cout, cin, 3, 7, 7, dtype=torch.float32, device=self.device)
+        _lib.check(lib.vd_tc_wgrad_reduce(layer, _lib.ptr(raw), _lib.ptr(gw), plan, B, st), 'vd_tc_wgrad_reduce')
+        return gw
+
+    def _wgrad_parts(self, layer, x, gy, parts):
+        p, lib = self.plan, _lib.lib()
+        B = int((x if x is not None else gy).shape[0])
+        cin, cout, _ = self.layers[layer]
+        sizes = (ctypes.c_int64 * 6)()
+        _lib.check(lib.vd_tc_wgrad_plan(layer, ctypes.byref(p), B, sizes), 'vd_tc_wgrad_plan')
+        # per-layer workspaces: an operand kept for the next call must not be overwritten by another layer's wgrad in between
+        xcol = self._buf(f'xcol{layer}', sizes[3])
+        gyimg = self._buf(f'gyimg{layer}', sizes[4])
+        raw = self._buf('wraw', sizes[5])
+        plan, st = ctypes.byref(p), _lib.stream()
+        _lib.check(lib.vd_tc_wgrad_pack_parts(layer, _lib.ptr(x), int(parts[0]), _lib.ptr(gy), int(parts[1]), _lib.ptr(xcol), _lib.ptr(gyimg),
+                                              plan, B, st), 'vd_tc_wgrad_pack_parts')
         _lib.check(lib.vd_tc_wgrad_gemm(layer, _lib.ptr(xcol), _lib.ptr(gyimg), _lib.ptr(raw), plan, B, st), 'vd_tc_wgrad_gemm')
         gw = torch.empty(cout, cin, 3, 7, 7, dtype=torch.float32, device=self.device)
         _lib.check(lib.vd_tc_wgrad_reduce(layer, _lib.ptr(raw), _lib.ptr(gw), plan, B, st), 'vd_tc_wgrad_reduce')

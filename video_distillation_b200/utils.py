@@ -196,7 +196,7 @@ def evaluate_synset(it_eval, net, images_train, labels_train, testloader, args, 
     """utils.py:848-886: train ``net`` on the synthetic set for args.epoch_eval_train epochs
     (SGD m=0.9 wd=5e-4, lr x0.1 after Epoch//2+1) and test; returns (net, acc_train, acc_test, acc_per)."""
     # args.precision = 'bf16' (optional, not a reference flag): train / test on the tensor-core conv trio
-    prev_backend = ops.set_conv_backend('tc' if getattr(args, 'precision', 'fp32') == 'bf16' else 'fp32')
+    prev_backend = ops.set_conv_backend({'bf16': 'tc', 'bf16x3': 'tc_x3'}.get(getattr(args, 'precision', 'fp32'), 'fp32'))
     try:
         return _evaluate_synset(it_eval, net, images_train, labels_train, testloader, args, mode, return_loss, test_freq)
     finally:
