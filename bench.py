@@ -870,12 +870,15 @@ def import_reference_reparam(path):
     return ref_reparam
 
 
-def reference_mtt_cpu_rate(threads, syn_steps=2, batch_syn=4):
-    """One reference MTT iteration on the host cores over a bounded sample (syn_steps x batch_syn of the workload's 10 x 50);
-    returns (it/s scaled linearly in steps x videos, seconds, description) or None when the reference modules are absent."""
+def reference_mtt_cpu_rate(threads, syn_steps=2, batch_syn=None):
+    """One reference MTT iteration on the host cores over a bounded sample: the workload's true step batch (50 videos: the CPU cost
+    per video depends on the batch) with syn_steps of its 10 unrolled steps; returns (it/s scaled linearly in the unroll depth,
+    seconds, description) or None when the reference modules are absent."""
     refdir = reference_dir()
     if refdir is None:
         return None
+    if batch_syn is None:
+        batch_syn = C * VPC
     ref_utils, _ = import_reference(refdir)
     torch.set_num_threads(threads)
     loop = ReferenceMTTLoop(ref_utils, import_reference_reparam(refdir), 'cpu', syn_steps, batch_syn)
