@@ -385,10 +385,15 @@ def memory_kernel_rooflines(step_fn, tr, steps=3):
             out.append({'kernel': key, 'ms': per_step_ms, 'bytes': nbytes, 'gbs': nbytes / per_step_ms / 1e6,
                         'frac': nbytes / per_step_ms / 1e6 / hbm, 'what': what})
             continue
-        ms = ms_total / n
-        row = {'kernel': key, 'ms': ms, 'bytes': int(nbytes), 'gbs': nbytes / ms / 1e6, 'frac': nbytes / ms / 1e6 / hbm, 'what': what}
+        # the launches of one step together cover the step's synthetic videos `covers` times (batches above max_batch are cut into
+        # several launches; the fp32 col2im runs once per pass of the split backward): bytes and time are both per step
+        covers = 3 if key == 'col2im_kernel<float' else 1
+        ms = ms_total / steps
+        nbytes = covers * nbytes
+        row = {'kernel': key, 'ms': ms / (n / steps), 'ms_per_step': ms, 'launches_per_step': n / steps, 'bytes': int(nbytes),
+               'gbs': nbytes / ms / 1e6, 'frac': nbytes / ms / 1e6 / hbm, 'what': what}
         if key in fma:
-            row.update({'bound': 'fp32 FMA', 'fma': int(fma[key]), 'tfma_s': fma[key] / ms / 1e9, 'fma_frac': fma[key] / ms / 1e9 / 36.0})
+            row.update({'bound': 'fp32 FMA', 'fma': int(fma[key]), 'tfma_s': fma[key] / ms / 1e9, 'fma_frac': fma[key] / ms / 1e9 / 36.0})      # per step, like the bytes
         else:
             row['bound'] = 'hbm'
         out.append(row)

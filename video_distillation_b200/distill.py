@@ -452,7 +452,8 @@ class DMS2DTrainer:
         maps sample j to its row of ``real_batch`` when the rows were uploaded in another order (merged host ranges);
         ``real_batch_offsets`` (device int32, C+1): class segments of the batch when the set is video-sharded."""
         if (self.embedder.tc is not None and self.syn_on_tensor_cores == 'split') or self.embedder.precision == 'bf16x3':
-            prev = ops.set_conv_backend('tc')             # forward AND backward of net.embed(...) below
+            # forward AND backward of net.embed(...) below; precision='bf16x3': every primitive of the trio on hi / lo pairs
+            prev = ops.set_conv_backend('tc_x3' if self.embedder.precision == 'bf16x3' else 'tc')
             try:
                 return self._step(net, net_seed, indices, real_idx, real_batch, real_batch_index, real_batch_offsets)
             finally:
