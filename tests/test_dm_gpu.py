@@ -367,7 +367,8 @@ def test_streamed_real_batch_in_any_row_order():
         assert torch.equal(a, b)
 
 
-def test_mtt_baseline_golden():
+@pytest.mark.parametrize('precision', ['fp32', 'bf16x3'])
+def test_mtt_baseline_golden(precision):
     """MTT on leaf synthetic videos (distill_baseline.py:196-272, MTTBaselineTrainer) against the live-reference golden:
     ipc = 2 with batch_syn = 4, so the randperm is split and the chunks are consumed last-first like the reference's pop()."""
     from oracle import synth
@@ -378,7 +379,7 @@ def test_mtt_baseline_golden():
     C, T, H, ipc, syn_steps, batch_syn = 3, 8, 64, 2, 2, 4
     tr = MTTBaselineTrainer(num_classes=C, im_size=(H, H), frames=T, ipc=ipc, syn_steps=syn_steps, lr_img=1.0, lr_lr=1e-5,
                             lr_teacher=0.01, train_lr=True, batch_syn=batch_syn, image_syn=synth.hash_uniform((C * ipc, T, 3, H, H), 91),
-                            precision='fp32')
+                            precision=precision)
     start = synth.synth_convnet3d_params(81, num_classes=C)
     target = {k: v + synth.hash_uniform(tuple(v.shape), 950 + i, 2.0 ** -10) for i, (k, v) in enumerate(start.items())}
     student = ReparamModule(ConvNet3D(3, C, 128, 3, 'relu', 'none', 'maxpooling', T, (H, H)).cuda())
@@ -406,6 +407,9 @@ def test_mtt_baseline_golden():
     assert [d.tolist() for d in tr.last['draws']] == [gold['used_0'].tolist(), gold['used_1'].tolist()]
     assert rel(tr.last['param_dist'], gold['param_dist']) < 1e-5
     assert rel(grand, gold['grand_loss']) < 1e-5
+    from oracle import synth as _synth
+    print(f'baseline MTT [{precision}] vs reference: lr grad', rel(tr.syn_lr.grad, gold['grad_syn_lr']), 'image grad sample',
+          rel(_synth.summarize(tr.image_syn.grad.detach().cpu())[1], gold['grad_image_sample']))
     assert rel(tr.syn_lr.grad, gold['grad_syn_lr']) < 1e-3
     check_summary(tr.image_syn.grad, gold['grad_image_sums'], gold['grad_image_sample'])
     rows = tr.image_syn.grad.flatten(1).abs().sum(1) > 0
