@@ -742,10 +742,42 @@ __device__ __forceinline__ void epi_plain(const WsParams& p, int tile, uint32_t 
 // dX1[ci, t, 2a+ph, 2b+pw].  code != NULL: apply the ReLU / MaxPool(1,2,2) routing code of conv 0's output and write
 // the 2x2 window of the packed dY of conv 0 (routed gradient at the recorded argmax, zeros elsewhere); code == NULL:
 // plain fp32 NCDHW gradient (B, 64, T, H1, H1).
-__device__ __forceinline__ void epi_dg1(const WsParams& p, int tile, uint32_t taddr, int m) {
+__device__ __forceinline__ void epi_dg1(const WsParams& p, int tile, uint32_t taddr, int m, float* scratch) {
     const Geo& g = p.epi.g;
     const int item = tile / p.tiles_per_item, t = tile % p.tiles_per_item;
     const int pw = m >> 6, ci = m & 63, ph = p.epi.ph;
+    if (p.epi.code == nullptr && scratch != nullptr) {
+        // Plain fp32 NCDHW gradient.  A lane owns one channel and one column parity, so stores straight from the registers put 32
+        // planes under every store instruction and fill half of every sector (measured: 0.59 ms per launch against 0.23 ms of the
+        // routed epilogue).  The two warps that hold pw = 0 / 1 of the same 32 channels (q and q + 2) assemble whole rows
+        // [32 ci][28 w] in shared memory behind a named barrier of the pair and write them as 8-byte pieces of 112 contiguous bytes.
+        const int lane = m & 31, cgrp = (m >> 5) & 1;
+        float* sw = scratch + cgrp * (32 * 34);
+        const int pair_bar = 2 + cgrp;
+        const int tid2 = pw * 32 + lane;
+        const int64_t cstride = (int64_t)g.T * g.H1 * g.H1;
+        float* gx0 = reinterpret_cast<float*>(p.epi.out) + (((int64_t)item * 64 + cgrp * 32) * g.T + t) * g.H1 * g.H1;
+        const int n2 = 32 * g.Wo1;
+        for (int a = 0; a < g.Ho1; ++a) {
+            float v[16];
+            tmem_ld16(taddr + a * g.P1, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int b = 0; b < 16; ++b)
+                if (b < g.Wo1) sw[lane * 34 + 2 * b + pw] = v[b];
+            asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+            const int h = 2 * a + ph;
+            for (int e = tid2; e < n2; e += 64) {
+                const int c = e / g.Wo1, b = e - c * g.Wo1;
+                float2 o = *reinterpret_cast<const float2*>(sw + c * 34 + 2 * b);
+                float2* d2 = reinterpret_cast<float2*>(gx0 + c * cstride + h * g.H1 + 2 * b);
+                if (p.epi.accum) { const float2 x = *d2; o.x += x.x; o.y += x.y; }
+                *d2 = o;
+            }
+            asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+        }
+        return;
+    }
     const int64_t plane = (((int64_t)item * 64 + ci) * g.T + t) * g.H1 * g.H1;
     const uint8_t* code = p.epi.code ? p.epi.code + plane : nullptr;
     float* gx = reinterpret_cast<float*>(p.epi.out) + plane;
@@ -1219,7 +1251,7 @@ __global__ void __launch_bounds__(EPI == EPI_L0S ? kThreadsL0S : kThreads, 1) ws
                     else if (EPI == EPI_L1S) epi_l1s_drain(p, tile, taddr, m, reinterpret_cast<uint16_t*>(base_ptr + p.smem_stash_off), bias_reg);
                     else if (EPI == EPI_L1) epi_l1_drain(p, tile, taddr, m, reinterpret_cast<uint16_t*>(base_ptr + p.smem_stash_off), bias_reg);
                     else if (EPI == EPI_PLAIN) epi_plain(p, tile, taddr, m);
-                    else if (EPI == EPI_DG1) epi_dg1(p, tile, taddr, m);
+                    else if (EPI == EPI_DG1) epi_dg1(p, tile, taddr, m, p.smem_epi_off ? reinterpret_cast<float*>(base_ptr + p.smem_epi_off) : nullptr);
                     else if (EPI == EPI_DG0) epi_dg0(p, tile, taddr, m);
                     else epi_l2(p, tile, taddr, m, bias_reg);
                 }
@@ -1939,7 +1971,8 @@ static int dgrad1_impl(const void* dyp, const void* wimg0, const void* wimg1, co
         p.ncols = (uint32_t)d.N; p.acc_cols = 256; p.acc_stages = 2;
         p.idesc = umma_idesc_bf16(128, (uint32_t)d.N);
         uint32_t smem = 0;
-        if (int rc = finalize_smem(p, (uint32_t)p.G * p.RW * kWeightTileBytes, &smem)) return rc;
+        // plain (unrouted) output: row-assembly scratch of the epilogue warp pairs
+        if (int rc = finalize_smem(p, (uint32_t)p.G * p.RW * kWeightTileBytes, &smem, /*epi_scratch=*/code0 == nullptr)) return rc;
         p.pix = (const uint8_t*)dyp; p.wimg = (const uint8_t*)(ph ? wimg1 : wimg0); p.item_index = nullptr;
         p.epi.out = (uint8_t*)out; p.epi.code = const_cast<uint8_t*>(code0); p.epi.T = plan->T; p.epi.n_items = B; p.epi.g = g;
         p.epi.ph = ph; p.epi.bb = make_bwd_geo(g, 0); p.epi.dy0_planar = dy0_planar; p.epi.accum = accumulate;
