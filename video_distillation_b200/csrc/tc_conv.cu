@@ -679,20 +679,29 @@ __device__ __forceinline__ void epi_plain(const WsParams& p, int tile, uint32_t 
         const int tp = sub / p.v_count, rb = sub % p.v_count;
         const int f = 2 * tp + (m >> 6), co = m & 63;
         const float bias = p.epi.bias ? __ldg(p.epi.bias + co) : 0.f;
+        // 32 columns per round: all TMEM loads and (when accumulating) all global loads of the round are in flight together —
+        // one lane per scheduler cannot hide a chain of load -> wait -> load -> add -> store per 8 columns
         for (int r = 0; r < g.R0; ++r) {
             float* dst = out + ((((int64_t)item * 64 + co) * g.T + f) * g.Ho0 + rb * g.R0 + r) * g.Wo0;
-            for (int wb = 0; wb < g.Wo0; wb += 8) {
-                float v[8];
-                tmem_ld8(taddr + r * g.Wo0 + wb, v);
-                tmem_ld_wait();
-                float4 lo = make_float4(v[0] + bias, v[1] + bias, v[2] + bias, v[3] + bias);
-                float4 hi = make_float4(v[4] + bias, v[5] + bias, v[6] + bias, v[7] + bias);
+            for (int wb0 = 0; wb0 < g.Wo0; wb0 += 32) {
+                float v[32];
+                float4 o[8];
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (wb0 + 8 * c < g.Wo0) tmem_ld8(taddr + r * g.Wo0 + wb0 + 8 * c, v + 8 * c);
                 if (p.epi.accum) {
-                    const float4 a = *reinterpret_cast<const float4*>(dst + wb), b = *reinterpret_cast<const float4*>(dst + wb + 4);
-                    lo.x += a.x; lo.y += a.y; lo.z += a.z; lo.w += a.w; hi.x += b.x; hi.y += b.y; hi.z += b.z; hi.w += b.w;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        if (wb0 + 4 * c < g.Wo0) o[c] = *reinterpret_cast<const float4*>(dst + wb0 + 4 * c);
                 }
-                *reinterpret_cast<float4*>(dst + wb) = lo;
-                *reinterpret_cast<float4*>(dst + wb + 4) = hi;
+                tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    if (wb0 + 4 * c < g.Wo0) {
+                        float4 q = make_float4(v[4 * c] + bias, v[4 * c + 1] + bias, v[4 * c + 2] + bias, v[4 * c + 3] + bias);
+                        if (p.epi.accum) { q.x += o[c].x; q.y += o[c].y; q.z += o[c].z; q.w += o[c].w; }
+                        *reinterpret_cast<float4*>(dst + wb0 + 4 * c) = q;
+                    }
             }
         }
     } else if (p.epi.layer == 1) {
@@ -701,18 +710,28 @@ __device__ __forceinline__ void epi_plain(const WsParams& p, int tile, uint32_t 
         const int fpt = p.n_acc;                          // output frames per tile (2, or 4 for the split tables at 64x64)
         for (int a = 0; a < fpt; ++a) {
             float* dst = out + (((int64_t)item * 128 + m) * g.T + fpt * tp + a) * g.Ho1 * g.Wo1;
-            for (int ho = 0; ho < g.Ho1; ++ho) {
-                float v[16];
+            for (int ho = 0; ho < g.Ho1; ho += 2) {                // two rows per round (Ho1 is even): loads of both in flight together
+                float v[32];
+                float2 o[16];
                 tmem_ld16(taddr + a * p.acc_cols + ho * g.P1, v);
+                tmem_ld16(taddr + a * p.acc_cols + (ho + 1) * g.P1, v + 16);
+                if (p.epi.accum) {
+#pragma unroll
+                    for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+                        for (int j = 0; j < 16; j += 2)
+                            if (j < g.Wo1) o[rr * 8 + j / 2] = *reinterpret_cast<const float2*>(dst + (ho + rr) * g.Wo1 + j);
+                }
                 tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 16; j += 2)
-                    if (j < g.Wo1) {
-                        float2 o = make_float2(v[j] + bias, v[j + 1] + bias);
-                        float2* d2 = reinterpret_cast<float2*>(dst + ho * g.Wo1 + j);
-                        if (p.epi.accum) { const float2 a = *d2; o.x += a.x; o.y += a.y; }
-                        *d2 = o;
-                    }
+                for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+                    for (int j = 0; j < 16; j += 2)
+                        if (j < g.Wo1) {
+                            float2 q = make_float2(v[rr * 16 + j] + bias, v[rr * 16 + j + 1] + bias);
+                            if (p.epi.accum) { q.x += o[rr * 8 + j / 2].x; q.y += o[rr * 8 + j / 2].y; }
+                            *reinterpret_cast<float2*>(dst + (ho + rr) * g.Wo1 + j) = q;
+                        }
             }
         }
     } else {
