@@ -201,14 +201,14 @@ class TcConvNet3D:
                 if layer == 0:
                     # conv 0: the three passes accumulate in the kernel's epilogue, straight into the (B,T,3,H,W) result
                     g = trio.dgrad(0, gy, None, part=0, wpack=pk_h, out=out[s:e], ncdhw=False)
-                    trio.dgrad(0, gy, None, part=0, wpack=pk_l, out=g, accumulate=True, ncdhw=False)
+                    trio.dgrad(0, gy, None, part=0, wpack=pk_l, out=g, accumulate=True, ncdhw=False, packed=True)   # gh is still packed
                     trio.dgrad(0, gy, None, part=1, wpack=pk_h, out=g, accumulate=True, ncdhw=False)
                 else:
-                    # conv 1 / conv 2: separate outputs added by elementwise launches (conv 1's epilogue owns one (ci, pw)
-                    # plane per lane: a read-modify-write there is 14 dependent uncoalesced loads per row and doubles the
-                    # kernel's time, measured)
+                    # conv 1 / conv 2: separate outputs added by elementwise launches (a read-modify-write in conv 1's epilogue
+                    # is a chain of dependent loads per row: 0.52 ms per launch against 0.17 ms for the plain store, measured
+                    # again with the row-assembling epilogue)
                     g = trio.dgrad(layer, gy, None, part=0, wpack=pk_h)
-                    g += trio.dgrad(layer, gy, None, part=0, wpack=pk_l)
+                    g += trio.dgrad(layer, gy, None, part=0, wpack=pk_l, packed=True)
                     g += trio.dgrad(layer, gy, None, part=1, wpack=pk_h)
         return out
 
