@@ -656,10 +656,13 @@ class MTTS2DTrainer:
 
     def step(self, start_params, target_params, student_net=None, net_seed=None):
         """start_params / target_params: lists of expert tensors (buffer.py layout) or flat tensors."""
+        from . import tc_trio
         prev = ops.set_conv_backend(ops.backend_for_precision(self.precision))
+        tc_trio.xcol_cache_begin()               # the im2col of a saved activation serves both wgrads of the iteration
         try:
             return self._step(start_params, target_params, student_net, net_seed)
         finally:
+            tc_trio.xcol_cache_end()
             ops.set_conv_backend(prev)
 
     def _step(self, start_params, target_params, student_net=None, net_seed=None):
@@ -764,10 +767,13 @@ class MTTBaselineTrainer:
         self.last = {}
 
     def step(self, start_params, target_params, student_net=None, net_seed=None):
+        from . import tc_trio
         prev = ops.set_conv_backend(ops.backend_for_precision(self.precision))
+        tc_trio.xcol_cache_begin()               # the im2col of a saved activation serves both wgrads of the iteration
         try:
             return self._step(start_params, target_params, student_net, net_seed)
         finally:
+            tc_trio.xcol_cache_end()
             ops.set_conv_backend(prev)
 
     def _step(self, start_params, target_params, student_net, net_seed):

@@ -104,15 +104,15 @@ def conv3d_dgrad_raw(gy, w, x_shape, stride, padding):
     return gx
 
 
-def conv3d_wgrad_raw(x, gy, w_shape, stride, padding, want_bias=False):
+def conv3d_wgrad_raw(x, gy, w_shape, stride, padding, want_bias=False, cache_x=False):
     x, gy = _f32c(x), _f32c(gy)
     g = conv_geom(x.shape, w_shape, stride, padding)
     trio, layer = _tc_route(x.shape, w_shape, stride, padding, x.device, 'wgrad')
     if trio is not None and x.shape[0] > 0:
         if _CONV_BACKEND == 'tc_x3':                      # x = xh + xl, gy = gh + gl: three products, fp32 sums
-            gw = trio.wgrad_split(layer, x, gy)
+            gw = trio.wgrad_split(layer, x, gy, cache_x=cache_x)
         else:
-            gw = trio.wgrad(layer, x, gy)
+            gw = trio.wgrad(layer, x, gy, cache_x=cache_x)
         return (gw, gy.sum(dim=(0, 2, 3, 4))) if want_bias else gw
     gw = torch.zeros(tuple(w_shape), dtype=torch.float32, device=x.device)
     gb = torch.zeros(g.Cout, dtype=torch.float32, device=x.device) if want_bias else None
@@ -134,7 +134,8 @@ class _Fprop(torch.autograd.Function):
         x, w = ctx.saved_tensors
         stride, padding = ctx.sp
         gx = _Dgrad.apply(gy, w, tuple(x.shape), stride, padding) if ctx.needs_input_grad[0] else None
-        gw = _Wgrad.apply(x, gy, tuple(w.shape), stride, padding) if ctx.needs_input_grad[1] else None
+        # cache_x: x is the activation saved by this forward — the MTT unroll differentiates it twice (tc_trio._xcol_cache)
+        gw = _Wgrad.apply(x, gy, tuple(w.shape), stride, padding, True) if ctx.needs_input_grad[1] else None
         return gx, gw, None, None, None
 
 
@@ -158,10 +159,10 @@ class _Dgrad(torch.autograd.Function):
 class _Wgrad(torch.autograd.Function):
     """gw = wgrad(x, gy); d/dx = dgrad(gy, c), d/dgy = fprop(x, c)."""
     @staticmethod
-    def forward(ctx, x, gy, w_shape, stride, padding):
+    def forward(ctx, x, gy, w_shape, stride, padding, cache_x=False):
         ctx.save_for_backward(x, gy)
         ctx.sp = (w_shape, stride, padding)
-        return conv3d_wgrad_raw(x, gy, w_shape, stride, padding)
+        return conv3d_wgrad_raw(x, gy, w_shape, stride, padding, cache_x=cache_x)
 
     @staticmethod
     def backward(ctx, c):
@@ -169,7 +170,7 @@ class _Wgrad(torch.autograd.Function):
         w_shape, stride, padding = ctx.sp
         gx = _Dgrad.apply(gy, c, tuple(x.shape), stride, padding) if ctx.needs_input_grad[0] else None
         ggy = _Fprop.apply(x, c, stride, padding) if ctx.needs_input_grad[1] else None
-        return gx, ggy, None, None, None
+        return gx, ggy, None, None, None, None
 
 
 def conv3d(x, w, bias=None, stride=1, padding=0):

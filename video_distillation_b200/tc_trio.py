@@ -15,6 +15,34 @@ from .tc import make_plan, tc_supported
 
 _KERNEL, _STRIDE, _PAD = (3, 7, 7), (1, 2, 2), (1, 3, 3)
 
+# im2col cache of the MTT unroll.  The activation x of a feature conv is the column operand of TWO wgrads per iteration: the
+# first-order one (inner-loop gradient, autograd.grad with create_graph) and, in the grand backward, the wgrad that
+# _Fprop.backward makes for the same saved x.  Between xcol_cache_begin() / xcol_cache_end() (one MTT iteration) the packed
+# columns of such an x are kept (1.3 + 1.0 + 0.1 GB per unrolled step and part at 50 videos of 16x3x112x112: HBM is there for it)
+# and the second wgrad skips its im2col.  An entry holds a reference to x, so the address it is keyed by cannot be reused.
+# Budget: at most 30 % of the device memory, and never below 20 % of it left free — a larger unroll / batch (vpc = 5) simply
+# packs its columns again.
+_xcol_cache = None
+_xcol_cache_bytes = 0
+
+
+def xcol_cache_begin():
+    global _xcol_cache, _xcol_cache_bytes
+    _xcol_cache, _xcol_cache_bytes = {}, 0
+
+
+def xcol_cache_end():
+    global _xcol_cache, _xcol_cache_bytes
+    _xcol_cache, _xcol_cache_bytes = None, 0
+
+
+def _xcol_cache_admits(nbytes, device):
+    total = torch.cuda.get_device_properties(device).total_memory
+    if _xcol_cache_bytes + nbytes > 0.30 * total:
+        return False
+    free = torch.cuda.mem_get_info(device)[0] + torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)
+    return free - nbytes > 0.20 * total
+
 
 class TcTrio:
     def __init__(self, T, H, W, device):
@@ -32,6 +60,7 @@ class TcTrio:
         self.direct_dgrad0 = True
         self.col_fp32 = True
         self.fused_split_fprop = True     # layers 1 / 2: split fprop as one launch on the split-fp16 tables
+        self._last_xcol = {}
 
     # ------------------------------------------------------------------ helpers
     def layer_of(self, cin, cout, extent):
@@ -204,46 +233,51 @@ class TcTrio:
         self.dgrad(layer, gy, None, part=1, wpack=pk_h, out=gx, accumulate=True)
         return gx
 
-    def wgrad_split(self, layer, x, gy):
+    def wgrad_split(self, layer, x, gy, cache_x=False):
         """gw = wgrad(x, gy) on bf16 hi / lo pairs: xl*gh + xh*gh + xh*gl (parts made inside the packers; in this order the
         im2col of xh and the image of gh are each packed once for two GEMMs)."""
-        gw = self.wgrad(layer, x, gy, parts=(1, 0))
-        gw += self.wgrad(layer, x, None, parts=(0, 0))
+        gw = self.wgrad(layer, x, gy, parts=(1, 0), cache_x=cache_x)
+        gw += self.wgrad(layer, x, None, parts=(0, 0), cache_x=cache_x)
         gw += self.wgrad(layer, None, gy, parts=(0, 1))
         return gw
 
-    def wgrad(self, layer, x, gy, parts=None):
+    def wgrad(self, layer, x, gy, parts=None, cache_x=False):
         """parts = (x_part, gy_part), 0 = value / 1 = bf16 residual; x or gy None: that operand is still packed in the workspace
-        from the previous call of the same layer and batch."""
-        if parts is not None:
-            return self._wgrad_parts(layer, x, gy, parts)
-        p, lib, B = self.plan, _lib.lib(), int(x.shape[0])
-        cin, cout, _ = self.layers[layer]
-        sizes = (ctypes.c_int64 * 6)()
-        _lib.check(lib.vd_tc_wgrad_plan(layer, ctypes.byref(p), B, sizes), 'vd_tc_wgrad_plan')
-        xcol = self._buf('xcol', sizes[3])
-        gyimg = self._buf('gyimg', sizes[4])
-        raw = self._buf('wraw', sizes[5])
-        plan, st = ctypes.byref(p), _lib.stream()
-        _lib.check(lib.vd_tc_wgrad_pack(layer, _lib.ptr(x), _lib.ptr(gy), _lib.ptr(xcol), _lib.ptr(gyimg), plan, B, st), 'vd_tc_wgrad_pack')
-        _lib.check(lib.vd_tc_wgrad_gemm(layer, _lib.ptr(xcol), _lib.ptr(gyimg), _lib.ptr(raw), plan, B, st), 'vd_tc_wgrad_gemm')
-        gw = torch.empty(cout, cin, 3, 7, 7, dtype=torch.float32, device=self.device)
-        _lib.check(lib.vd_tc_wgrad_reduce(layer, _lib.ptr(raw), _lib.ptr(gw), plan, B, st), 'vd_tc_wgrad_reduce')
-        return gw
+        from the previous call of the same layer and batch.  cache_x: x is an activation saved by the forward (see _xcol_cache)."""
+        return self._wgrad_parts(layer, x, gy, parts if parts is not None else (0, 0), cache_x)
 
-    def _wgrad_parts(self, layer, x, gy, parts):
+    def _xcol_for(self, layer, x, part, nbytes, cache_x):
+        """(column buffer for (x, part), True when it still has to be packed)."""
+        if x is None:
+            return self._last_xcol[layer], False
+        if cache_x and _xcol_cache is not None:
+            key = (id(self), layer, int(part), x.data_ptr(), x._version, tuple(x.shape))
+            hit = _xcol_cache.get(key)
+            if hit is not None:
+                return hit[1], False
+            if _xcol_cache_admits(int(nbytes), self.device):
+                global _xcol_cache_bytes
+                buf = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)   # every byte is written by the packer
+                _xcol_cache[key] = (x, buf)
+                _xcol_cache_bytes += int(nbytes)
+                return buf, True
+        # per-layer workspaces: an operand kept for the next call must not be overwritten by another layer's wgrad in between
+        return self._buf(f'xcol{layer}', nbytes), True
+
+    def _wgrad_parts(self, layer, x, gy, parts, cache_x=False):
         p, lib = self.plan, _lib.lib()
         B = int((x if x is not None else gy).shape[0])
         cin, cout, _ = self.layers[layer]
         sizes = (ctypes.c_int64 * 6)()
         _lib.check(lib.vd_tc_wgrad_plan(layer, ctypes.byref(p), B, sizes), 'vd_tc_wgrad_plan')
-        # per-layer workspaces: an operand kept for the next call must not be overwritten by another layer's wgrad in between
-        xcol = self._buf(f'xcol{layer}', sizes[3])
+        xcol, pack_x = self._xcol_for(layer, x, parts[0], sizes[3], cache_x)
+        self._last_xcol[layer] = xcol
         gyimg = self._buf(f'gyimg{layer}', sizes[4])
         raw = self._buf('wraw', sizes[5])
         plan, st = ctypes.byref(p), _lib.stream()
-        _lib.check(lib.vd_tc_wgrad_pack_parts(layer, _lib.ptr(x), int(parts[0]), _lib.ptr(gy), int(parts[1]), _lib.ptr(xcol), _lib.ptr(gyimg),
-                                              plan, B, st), 'vd_tc_wgrad_pack_parts')
+        if pack_x or gy is not None:
+            _lib.check(lib.vd_tc_wgrad_pack_parts(layer, _lib.ptr(x) if pack_x else None, int(parts[0]), _lib.ptr(gy), int(parts[1]),
+                                                  _lib.ptr(xcol), _lib.ptr(gyimg), plan, B, st), 'vd_tc_wgrad_pack_parts')
         _lib.check(lib.vd_tc_wgrad_gemm(layer, _lib.ptr(xcol), _lib.ptr(gyimg), _lib.ptr(raw), plan, B, st), 'vd_tc_wgrad_gemm')
         gw = torch.empty(cout, cin, 3, 7, 7, dtype=torch.float32, device=self.device)
         _lib.check(lib.vd_tc_wgrad_reduce(layer, _lib.ptr(raw), _lib.ptr(gw), plan, B, st), 'vd_tc_wgrad_reduce')
