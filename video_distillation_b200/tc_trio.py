@@ -7,6 +7,7 @@ has the geometry of networks.py:799 (k=(3,7,7), s=(1,2,2), p=(1,3,3)) on a suppo
 (the 1x1x1 logit conv, odd shapes) stays on the exact fp32 kernels.  Every launch goes through the C ABI.
 """
 import ctypes
+import os
 
 import torch
 
@@ -27,8 +28,13 @@ _xcol_cache_bytes = 0
 
 
 def xcol_cache_begin():
+    """Opt-in (VD_XCOL_CACHE=1).  Measured: a cold three-iteration run gains 8 % (0.605 -> 0.557 s, bf16x3), but in a long run
+    (bench.py: 13 iterations back to back) the 1 GB cache tensors and the activations of the autograd graph compete for the same
+    blocks of the caching allocator and the iteration gets SLOWER (568 -> 646 ms; profiles/r02r_bench_mtt_n1.json) — off by
+    default until the cache owns a pre-allocated arena."""
     global _xcol_cache, _xcol_cache_bytes
-    _xcol_cache, _xcol_cache_bytes = {}, 0
+    if os.environ.get('VD_XCOL_CACHE', '0') == '1':
+        _xcol_cache, _xcol_cache_bytes = {}, 0
 
 
 def xcol_cache_end():
