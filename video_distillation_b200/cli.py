@@ -39,7 +39,8 @@ def _extra(parser):
                         help='[B200] f16x3r2 (default): fused tensor-core pipeline on fp16 hi/lo operand pairs, the parity mode — three products '
                              'per MAC for the differentiable synthetic videos, two (exact weights, fp16 activations) for the frozen real videos '
                              'of the DM loss; f16x3: three products everywhere; bf16: single-pass throughput mode; fp32: exact CUDA-core '
-                             'kernels; bf16x3: unfused split-bf16 conv trio')
+                             'kernels; bf16x3: unfused conv trio with every fprop / dgrad / wgrad on bf16 hi/lo pairs.  The MTT unroll runs the '
+                             'bf16x3 trio (its parity mode) unless bf16 (split fprop, single-pass dgrad / wgrad) or fp32 is given')
     parser.add_argument('--run_name', type=str, default=None, help='[B200] directory name under save_path/<project> (wandb.run.name in the reference)')
     return parser
 
