@@ -228,8 +228,9 @@ def test_dm_s2d_bf16_tensor_core_real_path():
 
 
 def test_dm_s2d_bf16x3_parity_mode_on_tensor_cores():
-    """precision='bf16x3': real and synthetic embeds on the tensor-core trio with split-bf16 fprop and fp32
-    activations, against the exact fp32 path: loss / embeddings within 1e-4, gradients within 1e-2."""
+    """precision='bf16x3': real and synthetic embeds on the unfused tensor-core trio with every primitive on hi / lo operand
+    pairs and fp32 activations, against the exact fp32 path: loss / class means within 1e-4 (measured 5e-5 / 3e-5), UNconditioned
+    gradients within 5e-3 (measured 4.4e-4 / 1.4e-4; with single-pass bf16 dgrads they were 3e-3 / 1e-3)."""
     import oracle
     from oracle import synth
     from video_distillation_b200.distill import DeviceDataset, DMS2DTrainer
@@ -254,7 +255,7 @@ def test_dm_s2d_bf16x3_parity_mode_on_tensor_cores():
     errs = (abs(a[0] - b[0]) / abs(b[0]), rel(a[1], b[1]), rel(a[2], b[2]), rel(a[3], b[3]))
     print('bf16x3 vs fp32 (loss, real class means, dynamic-memory grad, hallucinator grad):', errs)
     assert errs[0] < 1e-4 and errs[1] < 1e-4, errs
-    assert errs[2] < 1e-2 and errs[3] < 1e-2, errs
+    assert errs[2] < 5e-3 and errs[3] < 5e-3, errs
 
 
 @pytest.mark.parametrize('precision', ['fp32', 'bf16', 'bf16x3'])
